@@ -1,0 +1,153 @@
+"""ctypes binding of the CPU parity oracle (oracle/libhiten_oracle.so).
+
+Test infrastructure: imported only by tests/, __graft_entry__.smoke() and bench.py's CPU legs.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+REPO = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+ORACLE_DIR = os.path.join(REPO, "oracle")
+LIB_PATH = os.path.join(ORACLE_DIR, "libhiten_oracle.so")
+
+SYS_CR3BP6, SYS_VAR42, SYS_POLYHAM = 0, 1, 2
+RK4, RK6, RK8, RK45, DOP853 = 4, 6, 8, 45, 853
+
+
+class HoSystem(C.Structure):
+    _fields_ = [("kind", C.c_int), ("dim", C.c_int), ("mu", C.c_double), ("fwd", C.c_int),
+                ("flip_lo", C.c_int), ("flip_hi", C.c_int), ("ham", C.c_void_p)]
+
+
+class HoEvent(C.Structure):
+    _fields_ = [("idx", C.c_int), ("offset", C.c_double), ("direction", C.c_int),
+                ("xtol", C.c_double), ("gtol", C.c_double)]
+
+
+class HoTol(C.Structure):
+    _fields_ = [("rtol", C.c_double), ("atol", C.c_double), ("max_step", C.c_double), ("min_step", C.c_double)]
+
+
+_lib = None
+dp = C.POINTER(C.c_double)
+ip = C.POINTER(C.c_int64)
+
+
+def build(force=False):
+    srcs = [os.path.join(ORACLE_DIR, f) for f in os.listdir(ORACLE_DIR) if f.endswith((".c", ".h"))]
+    if force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs):
+        env = dict(os.environ)
+        env.pop("CC", None)
+        subprocess.run(["make", "-C", ORACLE_DIR, "CC=gcc"], check=True, capture_output=True, env=env)
+    return LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(LIB_PATH)
+        _lib.ho_max_threads.restype = C.c_int
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(dp)
+
+
+def default_tol(rtol=1e-12, atol=1e-12, max_step=1e4, min_step=None):
+    if min_step is None:
+        min_step = 10.0 * np.finfo(float).eps       # rk.py:833-834
+    return HoTol(rtol, atol, max_step, min_step)
+
+
+def system(kind=SYS_CR3BP6, mu=0.0, fwd=1, flip=None, ham=None):
+    dim = {SYS_CR3BP6: 6, SYS_VAR42: 42}.get(kind)
+    if kind == SYS_POLYHAM:
+        dim = ham.dim
+    lo, hi = (-1, -1) if flip is None else flip
+    return HoSystem(kind, dim, float(mu), int(fwd), lo, hi, None if ham is None else ham.handle)
+
+
+def crtbp_accel(state, mu):
+    out = np.empty(6)
+    s = np.ascontiguousarray(state, dtype=np.float64)
+    lib().ho_crtbp_accel(_p(s), C.c_double(mu), _p(out))
+    return out
+
+
+def var_equations(phi, mu):
+    out = np.empty(42)
+    s = np.ascontiguousarray(phi, dtype=np.float64)
+    lib().ho_var_equations(_p(s), C.c_double(mu), _p(out))
+    return out
+
+
+def adaptive_final(sys_, method, tol, y0, t0, tf):
+    y0 = np.ascontiguousarray(y0, dtype=np.float64)
+    yf = np.empty(sys_.dim)
+    counts = np.zeros(2, dtype=np.int64)
+    lib().ho_adaptive_final(C.byref(sys_), method, C.byref(tol), _p(y0), C.c_double(t0), C.c_double(tf), _p(yf),
+                            counts.ctypes.data_as(ip))
+    return yf, counts
+
+
+def adaptive_dense(sys_, method, tol, y0, t_eval):
+    y0 = np.ascontiguousarray(y0, dtype=np.float64)
+    t_eval = np.ascontiguousarray(t_eval, dtype=np.float64)
+    out = np.empty((t_eval.size, sys_.dim))
+    counts = np.zeros(2, dtype=np.int64)
+    lib().ho_adaptive_dense(C.byref(sys_), method, C.byref(tol), _p(y0), _p(t_eval), t_eval.size, _p(out),
+                            counts.ctypes.data_as(ip))
+    return out, counts
+
+
+def adaptive_event(sys_, method, tol, ev, y0, t0, tmax):
+    y0 = np.ascontiguousarray(y0, dtype=np.float64)
+    th = C.c_double(0.0)
+    yh = np.empty(sys_.dim)
+    yl = np.empty(sys_.dim)
+    counts = np.zeros(2, dtype=np.int64)
+    hit = lib().ho_adaptive_event(C.byref(sys_), method, C.byref(tol), C.byref(ev), _p(y0), C.c_double(t0),
+                                  C.c_double(tmax), C.byref(th), _p(yh), _p(yl), counts.ctypes.data_as(ip))
+    return bool(hit), th.value, yh, yl, counts
+
+
+def fixed_dense(sys_, method, y0, t_vals):
+    y0 = np.ascontiguousarray(y0, dtype=np.float64)
+    t_vals = np.ascontiguousarray(t_vals, dtype=np.float64)
+    out = np.empty((t_vals.size, sys_.dim))
+    lib().ho_fixed_dense(C.byref(sys_), method, _p(y0), _p(t_vals), t_vals.size, _p(out))
+    return out
+
+
+def fixed_event(sys_, method, ev, y0, t_vals):
+    y0 = np.ascontiguousarray(y0, dtype=np.float64)
+    t_vals = np.ascontiguousarray(t_vals, dtype=np.float64)
+    th = C.c_double(0.0)
+    yh = np.empty(sys_.dim)
+    hit = lib().ho_fixed_event(C.byref(sys_), method, C.byref(ev), _p(y0), _p(t_vals), t_vals.size, C.byref(th), _p(yh))
+    return bool(hit), th.value, yh
+
+
+def batch_final(sys_, method, tol, y0, t0, tf, n_threads=1):
+    y0 = np.ascontiguousarray(y0, dtype=np.float64)
+    n = y0.shape[0]
+    yf = np.empty_like(y0)
+    counts = np.zeros((n, 2), dtype=np.int64)
+    lib().ho_batch_final(C.byref(sys_), method, C.byref(tol), _p(y0), C.c_int64(n), C.c_double(t0), C.c_double(tf),
+                         _p(yf), counts.ctypes.data_as(ip), n_threads)
+    return yf, counts
+
+
+def batch_dense(sys_, method, tol, y0, t_eval, n_threads=1):
+    y0 = np.ascontiguousarray(y0, dtype=np.float64)
+    t_eval = np.ascontiguousarray(t_eval, dtype=np.float64)
+    n = y0.shape[0]
+    out = np.empty((n, t_eval.size, sys_.dim))
+    counts = np.zeros((n, 2), dtype=np.int64)
+    lib().ho_batch_dense(C.byref(sys_), method, C.byref(tol), _p(y0), C.c_int64(n), _p(t_eval), t_eval.size,
+                         _p(out), counts.ctypes.data_as(ip), n_threads)
+    return out, counts
