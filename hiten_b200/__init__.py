@@ -1,0 +1,11 @@
+"""hiten_b200 -- B200-native batched trajectory propagation behind HITEN's Python API.
+
+Hand-written sm_100a CUDA kernels (fp64) reached through the C ABI in include/hiten_b200.h.
+No CPU fallback: compute entry points raise without the built library and a CUDA device.
+"""
+from . import _lib
+from ._lib import HitenB200Error
+from .propagate import BatchResult, cr3bp_dense, cr3bp_event, cr3bp_propagate, dfma_peak, make_integ
+
+__all__ = ["BatchResult", "HitenB200Error", "cr3bp_dense", "cr3bp_event", "cr3bp_propagate", "dfma_peak",
+           "make_integ", "_lib"]

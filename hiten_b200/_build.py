@@ -1,0 +1,57 @@
+"""Build the sm_100a shared library (C ABI in include/hiten_b200.h) in-tree with nvcc."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB_DIR = os.path.join(HERE, "lib")
+LIB_PATH = os.path.join(LIB_DIR, "libhiten_b200.so")
+
+NVCC_FLAGS = [
+    "-std=c++17", "-O3", "-lineinfo",
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "--expt-relaxed-constexpr",
+    "-Xcompiler", "-fPIC",
+    "-shared",
+]
+
+
+def sources():
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
+
+
+def _deps():
+    out = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    out.append(os.path.join(HERE, "..", "include", "hiten_b200.h"))
+    return out
+
+
+def needs_build():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    return any(os.path.getmtime(d) > t for d in _deps())
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return LIB_PATH
+    os.makedirs(LIB_DIR, exist_ok=True)
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    if not os.path.exists(nvcc):
+        nvcc = "nvcc"
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + sources()
+    env = dict(os.environ)
+    env.pop("CC", None)
+    env.pop("CXX", None)
+    res = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    if verbose:
+        sys.stderr.write(res.stderr)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    print(build(force=True, verbose="-v" in sys.argv))

@@ -1,0 +1,93 @@
+"""ctypes binding of libhiten_b200.so (C ABI declared in include/hiten_b200.h).
+
+There is no CPU fallback: if the shared library is missing, or CUDA is unavailable when a compute
+entry point is called, this module raises.  PyTorch is used only for device buffers and streams.
+"""
+import ctypes as C
+import os
+
+from . import _build
+
+HB_OK = 0
+HB_RK4, HB_RK6, HB_RK8, HB_RK45, HB_DOP853 = 4, 6, 8, 45, 853
+HB_ARITH_PARITY, HB_ARITH_FAST = 0, 1
+HB_TRAJ_OK, HB_TRAJ_HIT, HB_TRAJ_MAXSTEPS, HB_TRAJ_NONFINITE = 0, 1, 2, 3
+
+ERRORS = {-1: "HB_ERR_BADARG", -2: "HB_ERR_UNSUPPORTED", -3: "HB_ERR_NODEVICE"}
+
+
+class HbCr3bp(C.Structure):
+    _fields_ = [("mu", C.c_double), ("fwd", C.c_int32), ("flip_lo", C.c_int32),
+                ("flip_hi", C.c_int32), ("_pad", C.c_int32)]
+
+
+class HbInteg(C.Structure):
+    _fields_ = [("method", C.c_int32), ("arith", C.c_int32), ("rtol", C.c_double), ("atol", C.c_double),
+                ("max_step", C.c_double), ("min_step", C.c_double), ("max_attempts", C.c_int64)]
+
+
+class HbEvent(C.Structure):
+    _fields_ = [("idx", C.c_int32), ("direction", C.c_int32), ("offset", C.c_double),
+                ("xtol", C.c_double), ("gtol", C.c_double)]
+
+
+class HbSection(C.Structure):
+    _fields_ = [("idx", C.c_int32), ("direction", C.c_int32), ("offset", C.c_double),
+                ("proj_i", C.c_int32), ("proj_j", C.c_int32), ("segment_refine", C.c_int32),
+                ("max_hits_per_traj", C.c_int32), ("tol_on_surface", C.c_double),
+                ("dedup_time_tol", C.c_double), ("dedup_point_tol", C.c_double)]
+
+
+class HitenB200Error(RuntimeError):
+    pass
+
+
+_lib = None
+vp = C.c_void_p
+
+# name -> (restype, argtypes); mirrors include/hiten_b200.h
+SIGNATURES = {
+    "hb_workspace_bytes": (C.c_int64, []),
+    "hb_device_info": (C.c_int, [C.POINTER(C.c_int32)] * 3),
+    "hb_cr3bp_propagate": (C.c_int, [C.POINTER(HbCr3bp), C.POINTER(HbInteg), C.c_int64, vp, C.c_double, C.c_double,
+                                     vp, C.c_int32, vp, vp, vp, vp, vp, vp]),
+    "hb_cr3bp_dense": (C.c_int, [C.POINTER(HbCr3bp), C.POINTER(HbInteg), C.c_int64, vp, vp, C.c_int32, vp, vp, vp,
+                                 vp, vp, vp]),
+    "hb_cr3bp_event": (C.c_int, [C.POINTER(HbCr3bp), C.POINTER(HbInteg), C.POINTER(HbEvent), C.c_int64, vp,
+                                 C.c_double, C.c_double, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "hb_dfma_peak": (C.c_int, [C.c_double, C.POINTER(C.c_double), vp]),
+}
+
+
+def lib_path():
+    return _build.LIB_PATH
+
+
+def load():
+    """Load the shared library (building it first if sources are newer and nvcc is available)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB_PATH
+    if not os.path.exists(path):
+        try:
+            _build.build()
+        except Exception as exc:  # pragma: no cover
+            raise HitenB200Error(
+                f"libhiten_b200.so is missing and could not be built ({exc}); "
+                "run `python -c 'import __graft_entry__ as g; g.build()'`") from exc
+    lib = C.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc == HB_OK:
+        return
+    if rc < 0:
+        raise HitenB200Error(f"{what}: {ERRORS.get(rc, rc)}")
+    raise HitenB200Error(f"{what}: CUDA error {rc}")

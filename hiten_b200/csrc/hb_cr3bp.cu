@@ -1,0 +1,630 @@
+// hb_cr3bp.cu -- batched 6-state CR3BP propagation with DOP853 on sm_100a.
+//
+// One trajectory per thread, all stage vectors in registers (13 x 6 doubles), tableau entries
+// folded into the instruction stream at compile time (templates over hb_coeffs.h), per-thread
+// adaptive step control, and a persistent-thread work queue: a lane whose trajectory reached tf
+// immediately pulls the next index from an atomic cursor, so uneven step counts (2x inside one
+// manifold tube) do not idle lanes.
+//
+// Reference routines restated here (paths relative to hiten/ in iamgadmarconi/hiten v0.5.4):
+//   _crtbp_accel                      algorithms/dynamics/rtbp.py:31-74
+//   _DirectedSystem wrapper           algorithms/dynamics/base.py:296-305
+//   dop853_step_jit_kernel            algorithms/integrators/rk.py:1637-1708
+//   _integrate_dop853 (+ dense)       algorithms/integrators/rk.py:2377-2549
+//   _integrate_dop853_until_event     algorithms/integrators/rk.py:2680-2803
+//   _dop853_build_dense_cache / _dop853_eval_dense / _dop853_refine_in_step   rk.py:1791-2102
+//   controller helpers                algorithms/integrators/utils.py
+#include "hb_common.cuh"
+
+namespace {
+
+enum { MODE_FINAL = 0, MODE_DENSE = 1, MODE_EVENT = 2 };
+
+struct PropParams {
+    double mu, om;
+    unsigned negmask;  // bit d set -> derivative d negated (fwd == -1 wrapper)
+    double rtol, atol, max_step, min_step;
+    long long max_attempts;
+    long long n;
+    const double *y0;
+    double t0, tf;
+    const double *tf_arr;
+    double *yf;
+    int *nacc, *nrej, *status;
+    HbWorkspace *ws;
+    const double *t_eval;
+    int m;
+    double *dense_out;
+    int ev_idx, ev_dir;
+    double ev_off, xtol, gtol;
+    double *t_hit;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Vector field.  Parity form keeps rtbp.py:65-74's operation order:
+//   r1 = sqrt((x+mu)**2 + y**2 + z**2);  r**3 -> r*(r*r)
+//   ax = 2*vy + x - (1-mu)*(x+mu)/r1**3 - mu*(x-1+mu)/r2**3   (left to right)
+// Fast form: rsqrt-based, 2 MUFU + Newton instead of 2 sqrt + 6 div.
+// ---------------------------------------------------------------------------------------------
+template <class AR>
+HB_DEV void crtbp_rhs(const double (&s)[6], const PropParams &p, double (&out)[6])
+{
+    const double x = s[0], y = s[1], z = s[2], vx = s[3], vy = s[4], vz = s[5];
+    const double mu = p.mu, om = p.om;
+    double ax, ay, az;
+    if constexpr (AR::parity) {
+        const double xm = AR::add(x, mu);
+        const double xo = AR::sub(x, om);
+        const double yy = AR::mul(y, y), zz = AR::mul(z, z);
+        const double r1 = AR::sqrt(AR::add(AR::add(AR::mul(xm, xm), yy), zz));
+        const double r2 = AR::sqrt(AR::add(AR::add(AR::mul(xo, xo), yy), zz));
+        const double r1c = AR::mul(r1, AR::mul(r1, r1));
+        const double r2c = AR::mul(r2, AR::mul(r2, r2));
+        const double xq = AR::add(AR::sub(x, 1.0), mu);  // (x - 1 + mu)
+        ax = AR::sub(AR::sub(AR::add(AR::mul(2.0, vy), x), AR::div(AR::mul(om, xm), r1c)),
+                     AR::div(AR::mul(mu, xq), r2c));
+        ay = AR::sub(AR::sub(AR::add(AR::mul(-2.0, vx), y), AR::div(AR::mul(om, y), r1c)),
+                     AR::div(AR::mul(mu, y), r2c));
+        az = AR::sub(AR::div(AR::mul(-om, z), r1c), AR::div(AR::mul(mu, z), r2c));
+    } else {
+        const double xm = x + mu;
+        const double xo = x - om;
+        const double yz = fma(y, y, z * z);
+        const double i1 = rsqrt(fma(xm, xm, yz));
+        const double i2 = rsqrt(fma(xo, xo, yz));
+        const double c1 = om * (i1 * i1 * i1);
+        const double c2 = mu * (i2 * i2 * i2);
+        const double cs = c1 + c2;
+        ax = fma(2.0, vy, x) - fma(c1, xm, c2 * xo);
+        ay = fma(-2.0, vx, y) - cs * y;
+        az = -cs * z;
+    }
+    out[0] = (p.negmask & 1u) ? -vx : vx;
+    out[1] = (p.negmask & 2u) ? -vy : vy;
+    out[2] = (p.negmask & 4u) ? -vz : vz;
+    out[3] = (p.negmask & 8u) ? -ax : ax;
+    out[4] = (p.negmask & 16u) ? -ay : ay;
+    out[5] = (p.negmask & 32u) ? -az : az;
+}
+
+// ---------------------------------------------------------------------------------------------
+// DOP853 stages, tableau resolved at compile time.
+//   y_stage = y; for j < i with a_ij != 0: y_stage += (h * a_ij) * k_j      (rk.py:1674-1678)
+// ---------------------------------------------------------------------------------------------
+template <class AR, int I, int J>
+HB_DEV void stage_acc(double (&ys)[6], const double (&k)[13][6], double h)
+{
+    if constexpr (J < I) {
+        if constexpr (HB_DOP853_A[I][J] != 0.0) {
+            constexpr double a = HB_DOP853_A[I][J];
+            const double ha = AR::mul(h, a);
+#pragma unroll
+            for (int d = 0; d < 6; ++d) ys[d] = AR::madd(ha, k[J][d], ys[d]);
+        }
+        stage_acc<AR, I, J + 1>(ys, k, h);
+    }
+}
+
+template <class AR, int I>
+HB_DEV void run_stages(const double (&y)[6], double (&k)[13][6], double h, const PropParams &p)
+{
+    if constexpr (I < 12) {
+        double ys[6];
+#pragma unroll
+        for (int d = 0; d < 6; ++d) ys[d] = y[d];
+        stage_acc<AR, I, 0>(ys, k, h);
+        crtbp_rhs<AR>(ys, p, k[I]);
+        run_stages<AR, I + 1>(y, k, h, p);
+    }
+}
+
+template <class AR, int J>
+HB_DEV void high_acc(double (&yh)[6], const double (&k)[13][6], double h)
+{
+    if constexpr (J < 12) {
+        if constexpr (HB_DOP853_B[J] != 0.0) {
+            constexpr double b = HB_DOP853_B[J];
+            const double hb = AR::mul(h, b);
+#pragma unroll
+            for (int d = 0; d < 6; ++d) yh[d] = AR::madd(hb, k[J][d], yh[d]);
+        }
+        high_acc<AR, J + 1>(yh, k, h);
+    }
+}
+
+// err5 += E5_j * k_j ; err3 += E3_j * k_j     (rk.py:1691-1697)
+template <class AR, int J>
+HB_DEV void err_acc(double (&e5)[6], double (&e3)[6], const double (&k)[13][6])
+{
+    if constexpr (J < 13) {
+        if constexpr (HB_DOP853_E5[J] != 0.0) {
+            constexpr double c = HB_DOP853_E5[J];
+#pragma unroll
+            for (int d = 0; d < 6; ++d) e5[d] = AR::madd(c, k[J][d], e5[d]);
+        }
+        if constexpr (HB_DOP853_E3[J] != 0.0) {
+            constexpr double c = HB_DOP853_E3[J];
+#pragma unroll
+            for (int d = 0; d < 6; ++d) e3[d] = AR::madd(c, k[J][d], e3[d]);
+        }
+        err_acc<AR, J + 1>(e5, e3, k);
+    }
+}
+
+// One attempted step.  k[0] must hold f(t, y).  Returns the SciPy-style combined error norm
+// (rk.py:2457-2467): err = |h| * n5 / sqrt((n5 + 0.01 n3) * n), n5 = dot(e5/scale, e5/scale)
+// with np.dot's sequential FMA accumulation.
+template <class AR>
+HB_DEV double dop853_attempt(const double (&y)[6], double (&k)[13][6], double h, double (&yh)[6],
+                             const PropParams &p)
+{
+    run_stages<AR, 1>(y, k, h, p);
+#pragma unroll
+    for (int d = 0; d < 6; ++d) yh[d] = y[d];
+    high_acc<AR, 0>(yh, k, h);
+    crtbp_rhs<AR>(yh, p, k[12]);
+
+    double e5[6], e3[6];
+#pragma unroll
+    for (int d = 0; d < 6; ++d) { e5[d] = 0.0; e3[d] = 0.0; }
+    err_acc<AR, 0>(e5, e3, k);
+    double n5 = 0.0, n3 = 0.0;
+#pragma unroll
+    for (int d = 0; d < 6; ++d) {
+        const double sc = AR::madd(p.rtol, fmax(fabs(y[d]), fabs(yh[d])), p.atol);
+        const double a = AR::div(AR::mul(e5[d], h), sc);
+        const double b = AR::div(AR::mul(e3[d], h), sc);
+        n5 = fma(a, a, n5);
+        n3 = fma(b, b, n3);
+    }
+    if (n5 == 0.0 && n3 == 0.0) return 0.0;
+    const double denom = AR::madd(0.01, n3, n5);
+    return AR::div(AR::mul(fabs(h), n5), AR::sqrt(AR::mul(denom, 6.0)));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Dense output of one accepted segment (rk.py:1836-1875): three extra stages (rows 13..15 of the
+// extended tableau), then F[0..6].  k[0] = f_old, k[12] = f_new.
+// ---------------------------------------------------------------------------------------------
+template <class AR, int S, int R>
+HB_DEV void ext_acc(double (&acc)[6], const double (&k)[13][6], const double (&kx)[3][6])
+{
+    if constexpr (R < S) {
+        if constexpr (HB_DOP853_A[S][R] != 0.0) {
+            constexpr double a = HB_DOP853_A[S][R];
+#pragma unroll
+            for (int d = 0; d < 6; ++d) {
+                const double kv = (R < 13) ? k[R < 13 ? R : 0][d] : kx[R >= 13 ? R - 13 : 0][d];
+                acc[d] = AR::madd(a, kv, acc[d]);
+            }
+        }
+        ext_acc<AR, S, R + 1>(acc, k, kx);
+    }
+}
+
+template <class AR, int S>
+HB_DEV void ext_stage(const double (&y_old)[6], double h, const double (&k)[13][6], double (&kx)[3][6],
+                      const PropParams &p)
+{
+    double acc[6], ys[6];
+#pragma unroll
+    for (int d = 0; d < 6; ++d) acc[d] = 0.0;
+    ext_acc<AR, S, 0>(acc, k, kx);
+#pragma unroll
+    for (int d = 0; d < 6; ++d) ys[d] = AR::madd(h, acc[d], y_old[d]);
+    crtbp_rhs<AR>(ys, p, kx[S - 13]);
+}
+
+template <class AR, int I, int R>
+HB_DEV void d_acc(double (&acc)[6], const double (&k)[13][6], const double (&kx)[3][6])
+{
+    if constexpr (R < 16) {
+        if constexpr (HB_DOP853_D[I][R] != 0.0) {
+            constexpr double c = HB_DOP853_D[I][R];
+#pragma unroll
+            for (int d = 0; d < 6; ++d) {
+                const double kv = (R < 13) ? k[R < 13 ? R : 0][d] : kx[R >= 13 ? R - 13 : 0][d];
+                acc[d] = AR::madd(c, kv, acc[d]);
+            }
+        }
+        d_acc<AR, I, R + 1>(acc, k, kx);
+    }
+}
+
+template <class AR, int I>
+HB_DEV void d_rows(double (&F)[7][6], double h, const double (&k)[13][6], const double (&kx)[3][6])
+{
+    if constexpr (I < 4) {
+        double acc[6];
+#pragma unroll
+        for (int d = 0; d < 6; ++d) acc[d] = 0.0;
+        d_acc<AR, I, 0>(acc, k, kx);
+#pragma unroll
+        for (int d = 0; d < 6; ++d) F[3 + I][d] = AR::mul(h, acc[d]);
+        d_rows<AR, I + 1>(F, h, k, kx);
+    }
+}
+
+template <class AR>
+HB_DEV void dense_cache(const double (&y_old)[6], const double (&y_new)[6], double h,
+                        const double (&k)[13][6], double (&F)[7][6], const PropParams &p)
+{
+    double kx[3][6];
+    ext_stage<AR, 13>(y_old, h, k, kx, p);
+    ext_stage<AR, 14>(y_old, h, k, kx, p);
+    ext_stage<AR, 15>(y_old, h, k, kx, p);
+#pragma unroll
+    for (int d = 0; d < 6; ++d) {
+        const double dy = AR::sub(y_new[d], y_old[d]);
+        F[0][d] = dy;
+        F[1][d] = AR::sub(AR::mul(h, k[0][d]), dy);
+        F[2][d] = AR::sub(AR::mul(2.0, dy), AR::mul(h, AR::add(k[12][d], k[0][d])));
+    }
+    d_rows<AR, 0>(F, h, k, kx);
+}
+
+// _dop853_eval_dense (rk.py:1989-2003): alternating x / (1-x) Horner form.
+template <class AR>
+HB_DEV void dense_eval(const double (&y_old)[6], const double (&F)[7][6], double x, double (&out)[6])
+{
+    const double omx = AR::sub(1.0, x);
+#pragma unroll
+    for (int d = 0; d < 6; ++d) {
+        double v = 0.0;
+#pragma unroll
+        for (int i = 6; i >= 0; --i) {
+            v = AR::add(v, F[i][d]);
+            v = AR::mul(v, ((6 - i) % 2 == 0) ? x : omx);
+        }
+        out[d] = AR::add(v, y_old[d]);
+    }
+}
+
+// Component select without dynamic register-array indexing (which would force local memory).
+HB_DEV double pick6(const double (&v)[6], int i)
+{
+    double r = v[0];
+#pragma unroll
+    for (int d = 1; d < 6; ++d) r = (i == d) ? v[d] : r;
+    return r;
+}
+
+// scale0, d0, d1, h0 (rk.py:2445-2448; utils.py:127-157).  The reference's np.linalg.norm is
+// OpenBLAS dnrm2 (x87 extended accumulation); a double-double sum of squares stands in for it.
+HB_DEV double norm2_ext6(const double (&v)[6])
+{
+    double hi = 0.0, lo = 0.0;
+#pragma unroll
+    for (int d = 0; d < 6; ++d) {
+        const double ph = __dmul_rn(v[d], v[d]);
+        const double pl = __fma_rn(v[d], v[d], -ph);           // exact product = ph + pl
+        const double s = __dadd_rn(hi, ph);                     // two-sum(hi, ph)
+        const double bb = __dsub_rn(s, hi);
+        const double e = __dadd_rn(__dsub_rn(hi, __dsub_rn(s, bb)), __dsub_rn(ph, bb));
+        hi = s;
+        lo = __dadd_rn(lo, __dadd_rn(e, pl));
+    }
+    const double s = __dadd_rn(hi, lo);
+    const double r = __dsqrt_rn(s);
+    // one Newton correction with the residual taken in double-double: r + (S - r*r) / (2r)
+    const double res = __dadd_rn(__fma_rn(-r, r, hi), lo);
+    return __dadd_rn(r, __ddiv_rn(res, __dmul_rn(2.0, r)));
+}
+
+template <class AR>
+HB_DEV double initial_step(const double (&y)[6], const double (&f)[6], const PropParams &p)
+{
+    double a[6], b[6];
+#pragma unroll
+    for (int d = 0; d < 6; ++d) {
+        const double sc = AR::madd(p.rtol, fabs(y[d]), p.atol);
+        a[d] = AR::div(y[d], sc);
+        b[d] = AR::div(f[d], sc);
+    }
+    const double sq = AR::sqrt(6.0);
+    const double d0 = AR::div(norm2_ext6(a), sq);
+    const double d1 = AR::div(norm2_ext6(b), sq);
+    double h = (d0 < 1.0e-5 || d1 < 1.0e-5) ? 1.0e-6 : AR::div(AR::mul(0.01, d0), d1);
+    if (h > p.max_step) h = p.max_step;
+    if (h < p.min_step) h = p.min_step;
+    return h;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The persistent-thread kernel.
+// ---------------------------------------------------------------------------------------------
+template <class AR, int MODE>
+__global__ void __launch_bounds__(128, 2) k_dop853_6(const PropParams p)
+{
+    double y[6], yh[6], k[13][6];
+    double t = 0.0, h = 0.0, err_prev = -1.0, tf = 0.0, g_prev = 0.0;
+    long long idx = -1;
+    long long attempts = 0;
+    int nacc = 0, nrej = 0, cursor = 0;
+    bool have = false, exhausted = false;
+
+    for (;;) {
+        if (!have && !exhausted) {
+            idx = hb_fetch_index(p.ws);
+            if (idx < p.n) {
+#pragma unroll
+                for (int d = 0; d < 6; ++d) y[d] = p.y0[(long long)d * p.n + idx];
+                crtbp_rhs<AR>(y, p, k[0]);
+                t = p.t0;
+                tf = p.tf_arr ? p.tf_arr[idx] : p.tf;
+                h = initial_step<AR>(y, k[0], p);
+                err_prev = -1.0;
+                nacc = 0; nrej = 0; cursor = 0; attempts = 0;
+                if (MODE == MODE_EVENT) g_prev = AR::sub(pick6(y, p.ev_idx), p.ev_off);
+                have = true;
+                if (!((t - tf) < 0.0)) {
+                    // zero-length span: nothing to integrate
+                    if (MODE != MODE_DENSE) {
+#pragma unroll
+                        for (int d = 0; d < 6; ++d) p.yf[(long long)d * p.n + idx] = y[d];
+                    } else {
+                        for (int c = 0; c < p.m; ++c)
+#pragma unroll
+                            for (int d = 0; d < 6; ++d)
+                                p.dense_out[((long long)idx * p.m + c) * 6 + d] = y[d];
+                    }
+                    if (MODE == MODE_EVENT) p.t_hit[idx] = t;
+                    p.nacc[idx] = 0; p.nrej[idx] = 0; p.status[idx] = HB_TRAJ_OK;
+                    have = false;
+                }
+            } else {
+                exhausted = true;
+            }
+        }
+        if (__all_sync(0xffffffffu, !have && exhausted)) break;
+        if (!have) continue;
+
+        // ---- one attempted step (rk.py:2452-2484) ----
+        h = hb_clamp_step(h, p.max_step, p.min_step);
+        if (AR::add(t, h) > tf) h = fabs(AR::sub(tf, t));
+        const double err = dop853_attempt<AR>(y, k, h, yh, p);
+        ++attempts;
+        int fin = -1;  // >= 0: trajectory finished with this status
+
+        if (err <= 1.0) {
+            const double t_new = AR::add(t, h);
+            ++nacc;
+            const bool last = !((t_new - tf) < 0.0);
+            if (MODE == MODE_EVENT) {
+                const double g_new = AR::sub(pick6(yh, p.ev_idx), p.ev_off);
+                if (hb_event_crossed(g_prev, g_new, p.ev_dir)) {
+                    // _dop853_refine_in_step (rk.py:2079-2102): bisection on the dense interpolant
+                    double F[7][6], ym[6];
+                    dense_cache<AR>(y, yh, h, k, F, p);
+                    double a = 0.0, b = 1.0, g_left = g_prev, xh = 1.0;
+                    bool found = false;
+                    for (int it = 0; it < 128; ++it) {
+                        const double mid = AR::mul(0.5, AR::add(a, b));
+                        dense_eval<AR>(y, F, mid, ym);
+                        const double g_mid = AR::sub(pick6(ym, p.ev_idx), p.ev_off);
+                        if (fabs(g_mid) <= p.gtol) { xh = mid; found = true; break; }
+                        if (hb_crossed_direction(g_left, g_mid, p.ev_dir)) b = mid;
+                        else { a = mid; g_left = g_mid; }
+                        if (AR::mul(AR::sub(b, a), fabs(h)) <= p.xtol) break;
+                    }
+                    if (!found) xh = b;
+                    dense_eval<AR>(y, F, xh, ym);
+                    p.t_hit[idx] = AR::madd(xh, h, t);
+#pragma unroll
+                    for (int d = 0; d < 6; ++d) p.yf[(long long)d * p.n + idx] = ym[d];
+                    fin = HB_TRAJ_HIT;
+                } else {
+                    g_prev = g_new;
+                    if (last) {
+                        p.t_hit[idx] = t_new;
+#pragma unroll
+                        for (int d = 0; d < 6; ++d) p.yf[(long long)d * p.n + idx] = yh[d];
+                        fin = HB_TRAJ_OK;
+                    }
+                }
+            } else if (MODE == MODE_DENSE) {
+                // searchsorted(ts, t_q, 'right') - 1 semantics (rk.py:2505-2509): this segment owns
+                // every grid time t_q < t_new, and the last segment owns everything that is left.
+                if (cursor < p.m && (last || p.t_eval[cursor] < t_new)) {
+                    const double hseg = AR::sub(t_new, t);
+                    double F[7][6], yo[6];
+                    if (hseg != 0.0) dense_cache<AR>(y, yh, hseg, k, F, p);
+                    while (cursor < p.m) {
+                        const double tq = p.t_eval[cursor];
+                        if (!(last || tq < t_new)) break;
+                        if (hseg == 0.0) {
+#pragma unroll
+                            for (int d = 0; d < 6; ++d) yo[d] = y[d];
+                        } else {
+                            dense_eval<AR>(y, F, AR::div(AR::sub(tq, t), hseg), yo);
+                        }
+                        double *o = p.dense_out + ((long long)idx * p.m + cursor) * 6;
+#pragma unroll
+                        for (int d = 0; d < 6; ++d) o[d] = yo[d];
+                        ++cursor;
+                    }
+                }
+                if (last) fin = HB_TRAJ_OK;
+            } else {  // MODE_FINAL: the dense interpolant at tf on the last segment
+                if (last) {
+                    const double hseg = AR::sub(t_new, t);
+                    double yo[6];
+                    if (hseg == 0.0) {
+#pragma unroll
+                        for (int d = 0; d < 6; ++d) yo[d] = y[d];
+                    } else {
+                        const double x = AR::div(AR::sub(tf, t), hseg);
+                        if (x == 1.0) {
+                            // every (1-x) factor is zero: y_old + (y_new - y_old)
+#pragma unroll
+                            for (int d = 0; d < 6; ++d) yo[d] = AR::add(AR::sub(yh[d], y[d]), y[d]);
+                        } else {
+                            double F[7][6];
+                            dense_cache<AR>(y, yh, hseg, k, F, p);
+                            dense_eval<AR>(y, F, x, yo);
+                        }
+                    }
+#pragma unroll
+                    for (int d = 0; d < 6; ++d) p.yf[(long long)d * p.n + idx] = yo[d];
+                    fin = HB_TRAJ_OK;
+                }
+            }
+            // advance
+            t = t_new;
+#pragma unroll
+            for (int d = 0; d < 6; ++d) { y[d] = yh[d]; k[0][d] = k[12][d]; }
+            h = AR::mul(h, hb_pi_accept_factor<AR>(err, err_prev, 8.0));
+            err_prev = err;
+        } else {
+            ++nrej;
+            h = AR::mul(h, hb_pi_reject_factor<AR>(err, 8.0));
+            h = hb_clamp_step(h, p.max_step, p.min_step);
+        }
+        if (fin < 0) {
+            if (!(h == h) || !(err == err)) fin = HB_TRAJ_NONFINITE;
+            else if (attempts >= p.max_attempts) fin = HB_TRAJ_MAXSTEPS;
+            if (fin >= 0) {
+                if (MODE != MODE_DENSE) {
+#pragma unroll
+                    for (int d = 0; d < 6; ++d) p.yf[(long long)d * p.n + idx] = y[d];
+                }
+                if (MODE == MODE_EVENT) p.t_hit[idx] = t;
+            }
+        }
+        if (fin >= 0) {
+            p.nacc[idx] = nacc; p.nrej[idx] = nrej; p.status[idx] = fin;
+            have = false;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------------------------
+int fill_params(const hb_cr3bp *sys, const hb_integ *integ, PropParams &p)
+{
+    if (!sys || !integ) return HB_ERR_BADARG;
+    if (integ->method != HB_DOP853) return HB_ERR_UNSUPPORTED;
+    if (integ->arith != HB_ARITH_PARITY && integ->arith != HB_ARITH_FAST) return HB_ERR_BADARG;
+    p.mu = sys->mu;
+    p.om = 1.0 - sys->mu;
+    p.negmask = 0;
+    if (sys->fwd < 0) {
+        int lo = sys->flip_lo, hi = sys->flip_hi;
+        if (lo < 0) { lo = 0; hi = 6; }
+        if (hi > 6 || lo > hi) return HB_ERR_BADARG;
+        for (int d = lo; d < hi; ++d) p.negmask |= 1u << d;
+    }
+    p.rtol = integ->rtol; p.atol = integ->atol;
+    p.max_step = integ->max_step; p.min_step = integ->min_step;
+    p.max_attempts = integ->max_attempts > 0 ? integ->max_attempts : 2147483647LL;
+    return HB_OK;
+}
+
+int g_sm_count = 0;
+int sm_count()
+{
+    if (g_sm_count == 0) {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+        g_sm_count = n;
+    }
+    return g_sm_count;
+}
+
+template <int MODE>
+int launch(const PropParams &p, int arith, cudaStream_t st)
+{
+    HB_CUDA_TRY(cudaMemsetAsync(p.ws, 0, sizeof(HbWorkspace), st));
+    const int threads = 128;
+    long long blocks_needed = (p.n + threads - 1) / threads;
+    long long grid = 2LL * sm_count();           // persistent: 2 CTAs per SM
+    if (blocks_needed < grid) grid = blocks_needed;
+    if (grid < 1) grid = 1;
+    if (arith == HB_ARITH_PARITY) k_dop853_6<ArParity, MODE><<<(unsigned)grid, threads, 0, st>>>(p);
+    else k_dop853_6<ArFast, MODE><<<(unsigned)grid, threads, 0, st>>>(p);
+    HB_CUDA_TRY(cudaGetLastError());
+    return HB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t hb_workspace_bytes(void) { return (int64_t)sizeof(HbWorkspace); }
+
+int hb_device_info(int32_t *sm, int32_t *major, int32_t *minor)
+{
+    int dev = 0, n = 0, ma = 0, mi = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return HB_ERR_NODEVICE;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return HB_ERR_NODEVICE;
+    cudaDeviceGetAttribute(&ma, cudaDevAttrComputeCapabilityMajor, dev);
+    cudaDeviceGetAttribute(&mi, cudaDevAttrComputeCapabilityMinor, dev);
+    if (sm) *sm = n;
+    if (major) *major = ma;
+    if (minor) *minor = mi;
+    return HB_OK;
+}
+
+int hb_cr3bp_propagate(const hb_cr3bp *sys, const hb_integ *integ, int64_t n, const double *y0_soa,
+                       double t0, double tf, const double *tf_per_traj, int32_t n_fixed_steps,
+                       double *yf_soa, int32_t *n_acc, int32_t *n_rej, int32_t *status,
+                       void *workspace, void *stream)
+{
+    (void)n_fixed_steps;
+    PropParams p{};
+    int rc = fill_params(sys, integ, p);
+    if (rc != HB_OK) return rc;
+    if (n < 0 || !workspace || (n > 0 && (!y0_soa || !yf_soa || !n_acc || !n_rej || !status))) return HB_ERR_BADARG;
+    if (n == 0) return HB_OK;
+    p.n = n; p.y0 = y0_soa; p.t0 = t0; p.tf = tf; p.tf_arr = tf_per_traj;
+    p.yf = yf_soa; p.nacc = n_acc; p.nrej = n_rej; p.status = status;
+    p.ws = (HbWorkspace *)workspace;
+    return launch<MODE_FINAL>(p, integ->arith, (cudaStream_t)stream);
+}
+
+int hb_cr3bp_dense(const hb_cr3bp *sys, const hb_integ *integ, int64_t n, const double *y0_soa,
+                   const double *t_eval, int32_t m, double *states_out, int32_t *n_acc,
+                   int32_t *n_rej, int32_t *status, void *workspace, void *stream)
+{
+    PropParams p{};
+    int rc = fill_params(sys, integ, p);
+    if (rc != HB_OK) return rc;
+    if (n < 0 || m < 2 || !workspace || !t_eval ||
+        (n > 0 && (!y0_soa || !states_out || !n_acc || !n_rej || !status)))
+        return HB_ERR_BADARG;
+    if (n == 0) return HB_OK;
+    // t0 / tf are the ends of the grid (rk.py:2431-2432); fetch them from the device array
+    double ends[2];
+    cudaStream_t st = (cudaStream_t)stream;
+    HB_CUDA_TRY(cudaMemcpyAsync(&ends[0], t_eval, sizeof(double), cudaMemcpyDeviceToHost, st));
+    HB_CUDA_TRY(cudaMemcpyAsync(&ends[1], t_eval + (m - 1), sizeof(double), cudaMemcpyDeviceToHost, st));
+    HB_CUDA_TRY(cudaStreamSynchronize(st));
+    p.n = n; p.y0 = y0_soa; p.t0 = ends[0]; p.tf = ends[1]; p.tf_arr = nullptr;
+    p.nacc = n_acc; p.nrej = n_rej; p.status = status;
+    p.t_eval = t_eval; p.m = m; p.dense_out = states_out;
+    p.ws = (HbWorkspace *)workspace;
+    return launch<MODE_DENSE>(p, integ->arith, st);
+}
+
+int hb_cr3bp_event(const hb_cr3bp *sys, const hb_integ *integ, const hb_event *ev, int64_t n,
+                   const double *y0_soa, double t0, double tmax, const double *tmax_per_traj,
+                   double *t_hit, double *y_hit_soa, int32_t *n_acc, int32_t *n_rej,
+                   int32_t *status, void *workspace, void *stream)
+{
+    PropParams p{};
+    int rc = fill_params(sys, integ, p);
+    if (rc != HB_OK) return rc;
+    if (!ev || ev->idx < 0 || ev->idx > 5) return HB_ERR_BADARG;
+    if (n < 0 || !workspace || (n > 0 && (!y0_soa || !y_hit_soa || !t_hit || !n_acc || !n_rej || !status)))
+        return HB_ERR_BADARG;
+    if (n == 0) return HB_OK;
+    p.n = n; p.y0 = y0_soa; p.t0 = t0; p.tf = tmax; p.tf_arr = tmax_per_traj;
+    p.yf = y_hit_soa; p.t_hit = t_hit; p.nacc = n_acc; p.nrej = n_rej; p.status = status;
+    p.ev_idx = ev->idx; p.ev_dir = ev->direction; p.ev_off = ev->offset; p.xtol = ev->xtol; p.gtol = ev->gtol;
+    p.ws = (HbWorkspace *)workspace;
+    return launch<MODE_EVENT>(p, integ->arith, (cudaStream_t)stream);
+}
+
+}  // extern "C"

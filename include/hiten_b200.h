@@ -1,0 +1,149 @@
+/* hiten_b200.h -- C ABI of the B200-native HITEN propagation hot path.
+ *
+ * Drop-in boundary: these entry points are what a binding of the reference
+ * (iamgadmarconi/hiten v0.5.4, pure Python + Numba) calls in place of its @njit kernels.  Each
+ * function cites the reference routine it replaces (paths relative to src/hiten/).
+ *
+ * Conventions
+ *   - plain C, no exceptions, no torch types; every function returns an int status:
+ *       0 = HB_OK, negative = usage error (HB_ERR_*), positive = cudaError_t of the failed CUDA call;
+ *   - all array pointers are DEVICE pointers owned by the caller (the library never frees or
+ *     reallocates them); `stream` is a cudaStream_t passed as void*; calls are asynchronous;
+ *   - batch state arrays are struct-of-arrays ("SoA"): component c of trajectory i lives at
+ *     a[c * n + i], so warps read and write coalesced;
+ *   - per-trajectory results: status[i] (HB_TRAJ_*), n_acc[i] / n_rej[i] accepted / rejected
+ *     attempted steps ("RK step" of the headline metric = one attempted step);
+ *   - the library keeps no mutable global state: the work-queue cursor and hit counter live in a
+ *     caller-provided workspace of hb_workspace_bytes() bytes, so concurrent calls on different
+ *     streams with different workspaces are safe (the reference calls backends from a thread pool,
+ *     algorithms/poincare/synodic/engine.py:135).
+ *
+ * Arithmetic variants (hb_integ.arith)
+ *   HB_ARITH_PARITY  separately rounded mul/add/div/sqrt in the reference's operation order
+ *                    (Numba fastmath=False, algorithms/utils/config.py:1): reproduces the reference's
+ *                    step sequence; this is the variant parity is claimed for.
+ *   HB_ARITH_FAST    same algorithm and controller, FMA-contracted and algebraically simplified RHS.
+ */
+#ifndef HITEN_B200_H
+#define HITEN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HB_OK 0
+#define HB_ERR_BADARG (-1)
+#define HB_ERR_UNSUPPORTED (-2)
+#define HB_ERR_NODEVICE (-3)
+
+/* per-trajectory status */
+#define HB_TRAJ_OK 0
+#define HB_TRAJ_HIT 1        /* terminal event found                                  */
+#define HB_TRAJ_MAXSTEPS 2   /* attempt cap reached before tf                         */
+#define HB_TRAJ_NONFINITE 3  /* state or step size became NaN/Inf                     */
+
+/* integrator ids = RungeKutta._map keys (algorithms/integrators/rk.py:2950) */
+#define HB_RK4 4
+#define HB_RK6 6
+#define HB_RK8 8
+#define HB_RK45 45
+#define HB_DOP853 853
+
+#define HB_ARITH_PARITY 0
+#define HB_ARITH_FAST 1
+
+/* CR3BP system + _DirectedSystem wrapper (algorithms/dynamics/rtbp.py:31, base.py:186-310). */
+typedef struct {
+    double mu;       /* mass parameter                                                         */
+    int32_t fwd;     /* +1 forward, -1 backward (derivatives negated, base.py:296-305)         */
+    int32_t flip_lo; /* fwd == -1: negate dy[flip_lo:flip_hi]; flip_lo < 0 -> all components   */
+    int32_t flip_hi;
+    int32_t _pad;
+} hb_cr3bp;
+
+/* Integrator settings (AdaptiveRK(order, max_step, rtol, atol), algorithms/dynamics/base.py:446-450;
+ * min_step default 10*eps, rk.py:833-834). */
+typedef struct {
+    int32_t method;       /* HB_DOP853, HB_RK45, HB_RK4/6/8                                   */
+    int32_t arith;        /* HB_ARITH_*                                                       */
+    double rtol, atol;
+    double max_step, min_step;
+    int64_t max_attempts; /* safety cap per trajectory (the reference has none); <=0 -> 2^31-1 */
+} hb_integ;
+
+/* Plane event g(t,y) = y[idx] - offset (algorithms/poincare/singlehit/backend.py:30-67) with the
+ * direction / tolerance fields of EventConfig / EventOptions (algorithms/types/configs.py:195,
+ * options.py:280). */
+typedef struct {
+    int32_t idx;
+    int32_t direction;  /* 0 any, >0 increasing, <0 decreasing */
+    double offset;
+    double xtol, gtol;
+} hb_event;
+
+/* Synodic section detector settings = _SynodicDetectionBackend defaults
+ * (algorithms/poincare/synodic/backend.py:458-659, algorithms/types/services/maps.py:753-774). */
+typedef struct {
+    int32_t idx;             /* section_axis component                                          */
+    int32_t direction;       /* None -> 0, +1, -1                                               */
+    double offset;           /* section_offset                                                  */
+    int32_t proj_i, proj_j;  /* plane_coords -> state indices (dedup distance is measured here) */
+    int32_t segment_refine;  /* sub-intervals per sample segment minus one                      */
+    int32_t max_hits_per_traj; /* <=0: unlimited                                                */
+    double tol_on_surface;
+    double dedup_time_tol, dedup_point_tol;
+} hb_section;
+
+/* One section hit (record of _SectionHit, algorithms/poincare/core/types.py:45). 72 bytes. */
+typedef struct {
+    int64_t traj;     /* trajectory index in the batch                      */
+    int64_t seq;      /* ordinal of the hit inside its trajectory            */
+    double t;         /* integrator time (>= 0); caller applies the fwd sign */
+    double state[6];
+} hb_hit;
+
+/* Bytes of caller-provided device workspace every batch call needs (>= 256). */
+int64_t hb_workspace_bytes(void);
+
+/* Library / device probe: fills sm_count and compute capability; HB_ERR_NODEVICE without a GPU. */
+int hb_device_info(int32_t *sm_count, int32_t *cc_major, int32_t *cc_minor);
+
+/* Batched 6-state propagation to tf, end states only.
+ * Replaces the serial loop  for fraction in ...: _propagate_dynsys(..., steps=2)
+ * (algorithms/types/services/manifold.py:381-409 -> algorithms/dynamics/base.py:346-458 ->
+ *  algorithms/integrators/rk.py:2377-2549 / 1269-1399 / 533-588).
+ * yf uses the reference's API semantics: the dense interpolant evaluated at tf on the last
+ * accepted segment (what states[-1] of _propagate_dynsys is).
+ * tf_per_traj may be NULL (then tf is used for all).  For fixed-step methods n_fixed_steps is the
+ * number of equal steps over [t0, tf] (t_vals = linspace(t0, tf, n_fixed_steps + 1)).           */
+int hb_cr3bp_propagate(const hb_cr3bp *sys, const hb_integ *integ, int64_t n, const double *y0_soa,
+                       double t0, double tf, const double *tf_per_traj, int32_t n_fixed_steps,
+                       double *yf_soa, int32_t *n_acc, int32_t *n_rej, int32_t *status,
+                       void *workspace, void *stream);
+
+/* Same propagation with dense output on a shared ascending grid t_eval[m] (device pointer):
+ * states_out[i][k][c] (row-major [n][m][6], the reference's states array per trajectory).
+ * Replaces _integrate_dop853's dense-output pass (rk.py:2498-2543).                             */
+int hb_cr3bp_dense(const hb_cr3bp *sys, const hb_integ *integ, int64_t n, const double *y0_soa,
+                   const double *t_eval, int32_t m, double *states_out, int32_t *n_acc,
+                   int32_t *n_rej, int32_t *status, void *workspace, void *stream);
+
+/* Propagation with a terminal plane event (event always terminal, as in the reference):
+ * replaces _integrate_dop853_until_event + _dop853_refine_in_step (rk.py:2680-2803, 2006-2102).
+ * On a hit status[i] = HB_TRAJ_HIT, t_hit[i] / y_hit_soa hold the refined crossing; otherwise
+ * t_hit[i] = tmax reached and y_hit = final state.                                              */
+int hb_cr3bp_event(const hb_cr3bp *sys, const hb_integ *integ, const hb_event *ev, int64_t n,
+                   const double *y0_soa, double t0, double tmax, const double *tmax_per_traj,
+                   double *t_hit, double *y_hit_soa, int32_t *n_acc, int32_t *n_rej,
+                   int32_t *status, void *workspace, void *stream);
+
+/* Measured FP64 FMA throughput of this device: runs a register-resident DFMA chain for about
+ * `millis` ms and returns flop/s (2 flop per FMA).  Used as the roofline denominator.           */
+int hb_dfma_peak(double millis, double *flops_per_s, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HITEN_B200_H */

@@ -1,0 +1,93 @@
+"""GPU parity: the sm_100a DOP853 kernels through the C ABI against the oracle and the golden vectors."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return np.linalg.norm(a - b, axis=-1) / np.linalg.norm(b, axis=-1)
+
+
+def _report(name, rel):
+    print(f"[parity] {name}: median={np.median(rel):.3e} p90={np.quantile(rel, 0.9):.3e} "
+          f"max={rel.max():.3e} n>1e-9={(rel > 1e-9).sum()}/{rel.size} bit-exact={(rel == 0).sum()}")
+
+
+def test_c1_end_states_parity(c1):
+    import hiten_b200 as hb
+    mu, tf = float(c1["mu"]), float(c1["tf"])
+    res = hb.cr3bp_propagate(c1["x0W"], mu, tf, forward=-1, flip=(0, 6))
+    assert (res.status == 0).all()
+    s = O.system(O.SYS_CR3BP6, mu, fwd=-1, flip=(0, 6))
+    yo, counts = O.batch_final(s, O.DOP853, O.default_tol(), c1["x0W"], 0.0, tf, 2)
+    rel = _rel(res.yf, c1["yf_steps2"])
+    _report("C1 end states vs reference", rel)
+    same_steps = (res.n_acc == counts[:, 0]) & (res.n_rej == counts[:, 1])
+    print(f"[parity] C1 step counts identical: {same_steps.sum()}/50")
+    assert same_steps.all()
+    # tolerance of BASELINE.json north_star: 1e-9 relative at the default horizon
+    assert np.quantile(rel, 0.9) <= 1e-9
+    assert rel.max() <= 5e-8
+
+
+def test_c1_dense_parity(c1):
+    import hiten_b200 as hb
+    mu, tf = float(c1["mu"]), float(c1["tf"])
+    t_eval = np.linspace(0.0, tf, int(c1["steps"]))
+    res = hb.cr3bp_dense(c1["x0W"], mu, t_eval, forward=-1, flip=(0, 6))
+    assert (res.status == 0).all()
+    got = res.states[:, c1["dense_idx"], :]
+    err = np.abs(got - c1["dense"]).max(axis=2)         # synodic coordinates, absolute
+    print(f"[parity] C1 dense samples |diff|: median={np.median(err):.3e} max={err.max():.3e}")
+    # t <= half the horizon: well conditioned
+    half = c1["dense_idx"] <= int(c1["steps"]) // 2
+    assert err[:, half].max() <= 1e-9
+    assert np.array_equal(res.states[:, 0, :], c1["x0W"])
+
+
+def test_fast_variant_tracks_parity(c1):
+    import hiten_b200 as hb
+    mu, tf = float(c1["mu"]), float(c1["tf"])
+    a = hb.cr3bp_propagate(c1["x0W"], mu, tf, forward=-1, flip=(0, 6))
+    b = hb.cr3bp_propagate(c1["x0W"], mu, tf, forward=-1, flip=(0, 6), integ=hb.make_integ(arith="fast"))
+    rel = _rel(b.yf, a.yf)
+    _report("C1 fast vs parity", rel)
+    assert np.median(rel) <= 1e-9 and rel.max() <= 1e-6
+    assert np.abs(b.n_acc - a.n_acc).max() <= 2
+
+
+def test_event_matches_oracle(c1):
+    import hiten_b200 as hb
+    mu, tf = float(c1["mu"]), float(c1["tf"])
+    x0 = c1["x0W"]
+    res = hb.cr3bp_event(x0, mu, tf, 1, event_offset=0.0, direction=0, forward=-1, flip=(0, 6))
+    s = O.system(O.SYS_CR3BP6, mu, fwd=-1, flip=(0, 6))
+    ev = O.HoEvent(1, 0.0, 0, 1e-12, 1e-12)
+    n_hit = 0
+    for i in range(len(x0)):
+        hit, th, yh, yl, _ = O.adaptive_event(s, O.DOP853, O.default_tol(), ev, x0[i], 0.0, tf)
+        assert bool(res.status[i] == 1) == hit
+        if hit:
+            n_hit += 1
+            assert abs(res.t_hit[i] - th) <= 1e-9
+            assert np.abs(res.yf[i] - yh).max() <= 1e-9
+    print(f"[parity] event hits {n_hit}/50")
+    assert n_hit > 0
+
+
+def test_large_batch_properties(c1):
+    """BASELINE-size property checks: permutation invariance and replication consistency at N = 65536."""
+    import hiten_b200 as hb
+    import torch
+    mu, tf = float(c1["mu"]), float(c1["tf"])
+    reps = 65536 // 50 + 1
+    y0 = np.tile(c1["x0W"], (reps, 1))[:65536]
+    perm = np.random.default_rng(0).permutation(len(y0))
+    r1 = hb.cr3bp_propagate(y0, mu, tf, forward=-1, flip=(0, 6))
+    r2 = hb.cr3bp_propagate(y0[perm], mu, tf, forward=-1, flip=(0, 6))
+    assert np.array_equal(r1.yf[perm], r2.yf)                 # results do not depend on lane/queue order
+    assert np.array_equal(r1.yf[:50], r1.yf[50:100])          # replicas are bit-identical
+    assert (r1.status == 0).all()
