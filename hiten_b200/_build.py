@@ -34,14 +34,15 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in _deps())
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, extra_flags=(), out=None):
+    if out is None and not force and not needs_build():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     if not os.path.exists(nvcc):
         nvcc = "nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + sources()
+    target = LIB_PATH if out is None else out
+    cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else []) + ["-o", target] + sources()
     env = dict(os.environ)
     env.pop("CC", None)
     env.pop("CXX", None)
@@ -50,7 +51,7 @@ def build(force=False, verbose=False):
         sys.stderr.write(res.stderr)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
-    return LIB_PATH
+    return target
 
 
 if __name__ == "__main__":

@@ -56,6 +56,7 @@ SIGNATURES = {
     "hb_cr3bp_event": (C.c_int, [C.POINTER(HbCr3bp), C.POINTER(HbInteg), C.POINTER(HbEvent), C.c_int64, vp,
                                  C.c_double, C.c_double, vp, vp, vp, vp, vp, vp, vp, vp]),
     "hb_dfma_peak": (C.c_int, [C.c_double, C.POINTER(C.c_double), vp]),
+    "hb_selftest_arith": (C.c_int, [vp, vp, C.c_int64, vp, vp, vp, vp, vp, vp]),
 }
 
 
@@ -68,7 +69,7 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB_PATH
+    path = os.environ.get("HITEN_B200_LIB", _build.LIB_PATH)   # override: kernel-variant experiments
     if not os.path.exists(path):
         try:
             _build.build()

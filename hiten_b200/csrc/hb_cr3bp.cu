@@ -20,6 +20,15 @@ namespace {
 
 enum { MODE_FINAL = 0, MODE_DENSE = 1, MODE_EVENT = 2 };
 
+// 256 resident threads per SM (8 warps) is what 240+ registers per thread allow; one 256-thread CTA
+// per SM measured ~8% faster than two of 128 (gpurun probe, round 1).
+#ifndef HB_BLOCK
+#define HB_BLOCK 256
+#endif
+#ifndef HB_MINBLOCKS
+#define HB_MINBLOCKS 1
+#endif
+
 struct PropParams {
     double mu, om;
     unsigned negmask;  // bit d set -> derivative d negated (fwd == -1 wrapper)
@@ -46,7 +55,9 @@ struct PropParams {
 //   ax = 2*vy + x - (1-mu)*(x+mu)/r1**3 - mu*(x-1+mu)/r2**3   (left to right)
 // Fast form: rsqrt-based, 2 MUFU + Newton instead of 2 sqrt + 6 div.
 // ---------------------------------------------------------------------------------------------
-template <class AR>
+// NEG: 0 = forward (no sign change), 1 = every derivative negated (fwd = -1, flip all, the manifold
+// case base.py:296-300), 2 = generic per-component mask.
+template <class AR, int NEG>
 HB_DEV void crtbp_rhs(const double (&s)[6], const PropParams &p, double (&out)[6])
 {
     const double x = s[0], y = s[1], z = s[2], vx = s[3], vy = s[4], vz = s[5];
@@ -60,18 +71,20 @@ HB_DEV void crtbp_rhs(const double (&s)[6], const PropParams &p, double (&out)[6
         const double r2 = AR::sqrt(AR::add(AR::add(AR::mul(xo, xo), yy), zz));
         const double r1c = AR::mul(r1, AR::mul(r1, r1));
         const double r2c = AR::mul(r2, AR::mul(r2, r2));
+        // three quotients per denominator share one refined reciprocal (each stays correctly rounded)
+        const double i1 = hb_rcp_refined(r1c), i2 = hb_rcp_refined(r2c);
         const double xq = AR::add(AR::sub(x, 1.0), mu);  // (x - 1 + mu)
-        ax = AR::sub(AR::sub(AR::add(AR::mul(2.0, vy), x), AR::div(AR::mul(om, xm), r1c)),
-                     AR::div(AR::mul(mu, xq), r2c));
-        ay = AR::sub(AR::sub(AR::add(AR::mul(-2.0, vx), y), AR::div(AR::mul(om, y), r1c)),
-                     AR::div(AR::mul(mu, y), r2c));
-        az = AR::sub(AR::div(AR::mul(-om, z), r1c), AR::div(AR::mul(mu, z), r2c));
+        ax = AR::sub(AR::sub(AR::add(AR::mul(2.0, vy), x), hb_div_with(AR::mul(om, xm), r1c, i1)),
+                     hb_div_with(AR::mul(mu, xq), r2c, i2));
+        ay = AR::sub(AR::sub(AR::add(AR::mul(-2.0, vx), y), hb_div_with(AR::mul(om, y), r1c, i1)),
+                     hb_div_with(AR::mul(mu, y), r2c, i2));
+        az = AR::sub(hb_div_with(AR::mul(-om, z), r1c, i1), hb_div_with(AR::mul(mu, z), r2c, i2));
     } else {
         const double xm = x + mu;
         const double xo = x - om;
         const double yz = fma(y, y, z * z);
-        const double i1 = rsqrt(fma(xm, xm, yz));
-        const double i2 = rsqrt(fma(xo, xo, yz));
+        const double i1 = hb_rsqrt_fast(fma(xm, xm, yz));
+        const double i2 = hb_rsqrt_fast(fma(xo, xo, yz));
         const double c1 = om * (i1 * i1 * i1);
         const double c2 = mu * (i2 * i2 * i2);
         const double cs = c1 + c2;
@@ -79,12 +92,18 @@ HB_DEV void crtbp_rhs(const double (&s)[6], const PropParams &p, double (&out)[6
         ay = fma(-2.0, vx, y) - cs * y;
         az = -cs * z;
     }
-    out[0] = (p.negmask & 1u) ? -vx : vx;
-    out[1] = (p.negmask & 2u) ? -vy : vy;
-    out[2] = (p.negmask & 4u) ? -vz : vz;
-    out[3] = (p.negmask & 8u) ? -ax : ax;
-    out[4] = (p.negmask & 16u) ? -ay : ay;
-    out[5] = (p.negmask & 32u) ? -az : az;
+    if constexpr (NEG == 0) {
+        out[0] = vx; out[1] = vy; out[2] = vz; out[3] = ax; out[4] = ay; out[5] = az;
+    } else if constexpr (NEG == 1) {
+        out[0] = -vx; out[1] = -vy; out[2] = -vz; out[3] = -ax; out[4] = -ay; out[5] = -az;
+    } else {
+        out[0] = (p.negmask & 1u) ? -vx : vx;
+        out[1] = (p.negmask & 2u) ? -vy : vy;
+        out[2] = (p.negmask & 4u) ? -vz : vz;
+        out[3] = (p.negmask & 8u) ? -ax : ax;
+        out[4] = (p.negmask & 16u) ? -ay : ay;
+        out[5] = (p.negmask & 32u) ? -az : az;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -105,7 +124,7 @@ HB_DEV void stage_acc(double (&ys)[6], const double (&k)[13][6], double h)
     }
 }
 
-template <class AR, int I>
+template <class AR, int NEG, int I>
 HB_DEV void run_stages(const double (&y)[6], double (&k)[13][6], double h, const PropParams &p)
 {
     if constexpr (I < 12) {
@@ -113,8 +132,8 @@ HB_DEV void run_stages(const double (&y)[6], double (&k)[13][6], double h, const
 #pragma unroll
         for (int d = 0; d < 6; ++d) ys[d] = y[d];
         stage_acc<AR, I, 0>(ys, k, h);
-        crtbp_rhs<AR>(ys, p, k[I]);
-        run_stages<AR, I + 1>(y, k, h, p);
+        crtbp_rhs<AR, NEG>(ys, p, k[I]);
+        run_stages<AR, NEG, I + 1>(y, k, h, p);
     }
 }
 
@@ -154,15 +173,15 @@ HB_DEV void err_acc(double (&e5)[6], double (&e3)[6], const double (&k)[13][6])
 // One attempted step.  k[0] must hold f(t, y).  Returns the SciPy-style combined error norm
 // (rk.py:2457-2467): err = |h| * n5 / sqrt((n5 + 0.01 n3) * n), n5 = dot(e5/scale, e5/scale)
 // with np.dot's sequential FMA accumulation.
-template <class AR>
+template <class AR, int NEG>
 HB_DEV double dop853_attempt(const double (&y)[6], double (&k)[13][6], double h, double (&yh)[6],
                              const PropParams &p)
 {
-    run_stages<AR, 1>(y, k, h, p);
+    run_stages<AR, NEG, 1>(y, k, h, p);
 #pragma unroll
     for (int d = 0; d < 6; ++d) yh[d] = y[d];
     high_acc<AR, 0>(yh, k, h);
-    crtbp_rhs<AR>(yh, p, k[12]);
+    crtbp_rhs<AR, NEG>(yh, p, k[12]);
 
     double e5[6], e3[6];
 #pragma unroll
@@ -172,14 +191,23 @@ HB_DEV double dop853_attempt(const double (&y)[6], double (&k)[13][6], double h,
 #pragma unroll
     for (int d = 0; d < 6; ++d) {
         const double sc = AR::madd(p.rtol, fmax(fabs(y[d]), fabs(yh[d])), p.atol);
-        const double a = AR::div(AR::mul(e5[d], h), sc);
-        const double b = AR::div(AR::mul(e3[d], h), sc);
+        double a, b;
+        if constexpr (AR::parity) {
+            const double isc = hb_rcp_refined(sc);                 // both quotients correctly rounded
+            a = hb_div_with(AR::mul(e5[d], h), sc, isc);
+            b = hb_div_with(AR::mul(e3[d], h), sc, isc);
+        } else {
+            const double hs = h * hb_rcp_approx(sc);
+            a = e5[d] * hs;
+            b = e3[d] * hs;
+        }
         n5 = fma(a, a, n5);
         n3 = fma(b, b, n3);
     }
     if (n5 == 0.0 && n3 == 0.0) return 0.0;
     const double denom = AR::madd(0.01, n3, n5);
-    return AR::div(AR::mul(fabs(h), n5), AR::sqrt(AR::mul(denom, 6.0)));
+    if constexpr (AR::parity) return AR::div(AR::mul(fabs(h), n5), AR::sqrt(AR::mul(denom, 6.0)));
+    else return fabs(h) * n5 * hb_rsqrt_fast(denom * 6.0);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -202,7 +230,7 @@ HB_DEV void ext_acc(double (&acc)[6], const double (&k)[13][6], const double (&k
     }
 }
 
-template <class AR, int S>
+template <class AR, int NEG, int S>
 HB_DEV void ext_stage(const double (&y_old)[6], double h, const double (&k)[13][6], double (&kx)[3][6],
                       const PropParams &p)
 {
@@ -212,7 +240,7 @@ HB_DEV void ext_stage(const double (&y_old)[6], double h, const double (&k)[13][
     ext_acc<AR, S, 0>(acc, k, kx);
 #pragma unroll
     for (int d = 0; d < 6; ++d) ys[d] = AR::madd(h, acc[d], y_old[d]);
-    crtbp_rhs<AR>(ys, p, kx[S - 13]);
+    crtbp_rhs<AR, NEG>(ys, p, kx[S - 13]);
 }
 
 template <class AR, int I, int R>
@@ -245,14 +273,14 @@ HB_DEV void d_rows(double (&F)[7][6], double h, const double (&k)[13][6], const 
     }
 }
 
-template <class AR>
+template <class AR, int NEG>
 HB_DEV void dense_cache(const double (&y_old)[6], const double (&y_new)[6], double h,
                         const double (&k)[13][6], double (&F)[7][6], const PropParams &p)
 {
     double kx[3][6];
-    ext_stage<AR, 13>(y_old, h, k, kx, p);
-    ext_stage<AR, 14>(y_old, h, k, kx, p);
-    ext_stage<AR, 15>(y_old, h, k, kx, p);
+    ext_stage<AR, NEG, 13>(y_old, h, k, kx, p);
+    ext_stage<AR, NEG, 14>(y_old, h, k, kx, p);
+    ext_stage<AR, NEG, 15>(y_old, h, k, kx, p);
 #pragma unroll
     for (int d = 0; d < 6; ++d) {
         const double dy = AR::sub(y_new[d], y_old[d]);
@@ -333,8 +361,8 @@ HB_DEV double initial_step(const double (&y)[6], const double (&f)[6], const Pro
 // ---------------------------------------------------------------------------------------------
 // The persistent-thread kernel.
 // ---------------------------------------------------------------------------------------------
-template <class AR, int MODE>
-__global__ void __launch_bounds__(128, 2) k_dop853_6(const PropParams p)
+template <class AR, int MODE, int NEG>
+__global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) k_dop853_6(const PropParams p)
 {
     double y[6], yh[6], k[13][6];
     double t = 0.0, h = 0.0, err_prev = -1.0, tf = 0.0, g_prev = 0.0;
@@ -349,7 +377,7 @@ __global__ void __launch_bounds__(128, 2) k_dop853_6(const PropParams p)
             if (idx < p.n) {
 #pragma unroll
                 for (int d = 0; d < 6; ++d) y[d] = p.y0[(long long)d * p.n + idx];
-                crtbp_rhs<AR>(y, p, k[0]);
+                crtbp_rhs<AR, NEG>(y, p, k[0]);
                 t = p.t0;
                 tf = p.tf_arr ? p.tf_arr[idx] : p.tf;
                 h = initial_step<AR>(y, k[0], p);
@@ -382,7 +410,7 @@ __global__ void __launch_bounds__(128, 2) k_dop853_6(const PropParams p)
         // ---- one attempted step (rk.py:2452-2484) ----
         h = hb_clamp_step(h, p.max_step, p.min_step);
         if (AR::add(t, h) > tf) h = fabs(AR::sub(tf, t));
-        const double err = dop853_attempt<AR>(y, k, h, yh, p);
+        const double err = dop853_attempt<AR, NEG>(y, k, h, yh, p);
         ++attempts;
         int fin = -1;  // >= 0: trajectory finished with this status
 
@@ -395,7 +423,7 @@ __global__ void __launch_bounds__(128, 2) k_dop853_6(const PropParams p)
                 if (hb_event_crossed(g_prev, g_new, p.ev_dir)) {
                     // _dop853_refine_in_step (rk.py:2079-2102): bisection on the dense interpolant
                     double F[7][6], ym[6];
-                    dense_cache<AR>(y, yh, h, k, F, p);
+                    dense_cache<AR, NEG>(y, yh, h, k, F, p);
                     double a = 0.0, b = 1.0, g_left = g_prev, xh = 1.0;
                     bool found = false;
                     for (int it = 0; it < 128; ++it) {
@@ -428,7 +456,7 @@ __global__ void __launch_bounds__(128, 2) k_dop853_6(const PropParams p)
                 if (cursor < p.m && (last || p.t_eval[cursor] < t_new)) {
                     const double hseg = AR::sub(t_new, t);
                     double F[7][6], yo[6];
-                    if (hseg != 0.0) dense_cache<AR>(y, yh, hseg, k, F, p);
+                    if (hseg != 0.0) dense_cache<AR, NEG>(y, yh, hseg, k, F, p);
                     while (cursor < p.m) {
                         const double tq = p.t_eval[cursor];
                         if (!(last || tq < t_new)) break;
@@ -460,7 +488,7 @@ __global__ void __launch_bounds__(128, 2) k_dop853_6(const PropParams p)
                             for (int d = 0; d < 6; ++d) yo[d] = AR::add(AR::sub(yh[d], y[d]), y[d]);
                         } else {
                             double F[7][6];
-                            dense_cache<AR>(y, yh, hseg, k, F, p);
+                            dense_cache<AR, NEG>(y, yh, hseg, k, F, p);
                             dense_eval<AR>(y, F, x, yo);
                         }
                     }
@@ -533,19 +561,26 @@ int sm_count()
     return g_sm_count;
 }
 
+template <class AR, int MODE>
+int launch_neg(const PropParams &p, unsigned grid, cudaStream_t st)
+{
+    if (p.negmask == 0u) k_dop853_6<AR, MODE, 0><<<grid, HB_BLOCK, 0, st>>>(p);
+    else if (p.negmask == 63u) k_dop853_6<AR, MODE, 1><<<grid, HB_BLOCK, 0, st>>>(p);
+    else k_dop853_6<AR, MODE, 2><<<grid, HB_BLOCK, 0, st>>>(p);
+    HB_CUDA_TRY(cudaGetLastError());
+    return HB_OK;
+}
+
 template <int MODE>
 int launch(const PropParams &p, int arith, cudaStream_t st)
 {
     HB_CUDA_TRY(cudaMemsetAsync(p.ws, 0, sizeof(HbWorkspace), st));
-    const int threads = 128;
-    long long blocks_needed = (p.n + threads - 1) / threads;
-    long long grid = 2LL * sm_count();           // persistent: 2 CTAs per SM
+    long long blocks_needed = (p.n + HB_BLOCK - 1) / HB_BLOCK;
+    long long grid = (long long)HB_MINBLOCKS * sm_count();   // persistent: resident CTAs only
     if (blocks_needed < grid) grid = blocks_needed;
     if (grid < 1) grid = 1;
-    if (arith == HB_ARITH_PARITY) k_dop853_6<ArParity, MODE><<<(unsigned)grid, threads, 0, st>>>(p);
-    else k_dop853_6<ArFast, MODE><<<(unsigned)grid, threads, 0, st>>>(p);
-    HB_CUDA_TRY(cudaGetLastError());
-    return HB_OK;
+    if (arith == HB_ARITH_PARITY) return launch_neg<ArParity, MODE>(p, (unsigned)grid, st);
+    return launch_neg<ArFast, MODE>(p, (unsigned)grid, st);
 }
 
 }  // namespace

@@ -143,6 +143,12 @@ int hb_cr3bp_event(const hb_cr3bp *sys, const hb_integ *integ, const hb_event *e
  * `millis` ms and returns flop/s (2 flop per FMA).  Used as the roofline denominator.           */
 int hb_dfma_peak(double millis, double *flops_per_s, void *stream);
 
+/* Arithmetic self-test: for every pair (a[i], b[i]) evaluates the shared-reciprocal division and the
+ * restated sqrt fast path used by the parity variant next to the compiler's div.rn / sqrt.rn, and
+ * the controller's pow(b, a).  All pointers are device arrays of n doubles.                      */
+int hb_selftest_arith(const double *a, const double *b, int64_t n, double *div_shared, double *div_ref,
+                      double *sqrt_fast, double *sqrt_ref, double *pow_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
