@@ -1,0 +1,86 @@
+"""Synodic-section detection on the GPU (host wrapper over hb_synodic_detect).
+
+Reference: hiten/algorithms/poincare/synodic/backend.py (_SynodicDetectionBackend.run :823-887).
+Axis / plane-coordinate names follow _PlaneEvent._IDX_MAP (x, y, z, vx, vy, vz -> 0..5).
+"""
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .propagate import _require_cuda, _stream_ptr, workspace
+
+IDX = {"x": 0, "y": 1, "z": 2, "vx": 3, "vy": 4, "vz": 5}
+HIT_DTYPE = np.dtype([("traj", "<i8"), ("seq", "<i8"), ("t", "<f8"), ("state", "<f8", (6,))])
+assert HIT_DTYPE.itemsize == 72
+
+
+@dataclass
+class SectionHits:
+    """Hits in the reference's order: by trajectory, then by position along the trajectory."""
+    trajectory_indices: np.ndarray   # [K] int64
+    times: np.ndarray                # [K]
+    states: np.ndarray               # [K, 6]
+    points: np.ndarray               # [K, 2]
+    hits_per_traj: np.ndarray        # [N] int32
+
+
+def make_section(section_axis="x", section_offset=0.0, plane_coords=("y", "vy"), direction=None,
+                 segment_refine=50, tol_on_surface=1e-6, dedup_time_tol=1e-9, dedup_point_tol=1e-6,
+                 max_hits_per_traj=None):
+    """hb_section with the reference's SynodicMap defaults (algorithms/types/services/maps.py:753-774)."""
+    idx = IDX[section_axis.lower()] if isinstance(section_axis, str) else int(section_axis)
+    pi, pj = (IDX[c.lower()] if isinstance(c, str) else int(c) for c in plane_coords)
+    return L.HbSection(idx, 0 if direction is None else int(direction), float(section_offset), pi, pj,
+                       int(segment_refine), 0 if max_hits_per_traj is None else int(max_hits_per_traj),
+                       float(tol_on_surface), float(dedup_time_tol), float(dedup_point_tol))
+
+
+def detect(states, times, section, *, offsets=None, hit_capacity=None, device=None, stream=None, ws=None):
+    """Detect section hits.
+
+    states : CUDA tensor / ndarray [N, m, 6] (uniform) or [sum m_i, 6] with `offsets` [N + 1];
+    times  : [m] shared signed times, [N, m], or concatenated [sum m_i].
+    """
+    _require_cuda()
+    lib = L.load()
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    with torch.cuda.device(device):
+        st = states if isinstance(states, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(states, dtype=np.float64))
+        st = st.to(device).contiguous()
+        tm = times if isinstance(times, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(times, dtype=np.float64))
+        tm = tm.to(device).contiguous()
+        if offsets is None:
+            if st.dim() != 3 or st.shape[2] != 6:
+                raise ValueError("states must have shape [N, m, 6] when offsets is None")
+            n, m = int(st.shape[0]), int(st.shape[1])
+            shared = 1 if tm.dim() == 1 and tm.numel() == m else 0
+            if not shared and tm.numel() != n * m:
+                raise ValueError("times must have m or N*m entries")
+            off_t = None
+        else:
+            off_np = np.ascontiguousarray(offsets, dtype=np.int64)
+            n, m, shared = off_np.size - 1, 0, 0
+            off_t = torch.from_numpy(off_np).to(device)
+        cap = int(hit_capacity) if hit_capacity is not None else max(1024, 8 * n)
+        ws = workspace(device) if ws is None else ws
+        while True:
+            hits = torch.empty(cap * 9, dtype=torch.float64, device=device)      # 72-byte records
+            per = torch.empty(max(n, 1), dtype=torch.int32, device=device)
+            rc = lib.hb_synodic_detect(section, n, st.data_ptr(), tm.data_ptr(),
+                                       None if off_t is None else off_t.data_ptr(), m, shared, hits.data_ptr(), cap,
+                                       per.data_ptr(), ws.data_ptr(), _stream_ptr(stream))
+            L.check(rc, "hb_synodic_detect")
+            nh, no = L.C.c_int64(0), L.C.c_int64(0)
+            L.check(lib.hb_read_hit_count(ws.data_ptr(), L.C.byref(nh), L.C.byref(no), _stream_ptr(stream)),
+                    "hb_read_hit_count")
+            if no.value == 0:
+                break
+            cap = int(nh.value) + 16                                             # retry once with room for all
+        k = int(nh.value)
+        rec = hits[: k * 9].cpu().numpy().view(HIT_DTYPE) if k else np.empty(0, dtype=HIT_DTYPE)
+        order = np.lexsort((rec["seq"], rec["traj"]))
+        rec = rec[order]
+        pts = np.column_stack((rec["state"][:, section.proj_i], rec["state"][:, section.proj_j])) if k else np.empty((0, 2))
+        return SectionHits(rec["traj"].copy(), rec["t"].copy(), rec["state"].copy(), pts, per[:n].cpu().numpy())

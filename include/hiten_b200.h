@@ -143,6 +143,25 @@ int hb_cr3bp_event(const hb_cr3bp *sys, const hb_integ *integ, const hb_event *e
  * `millis` ms and returns flop/s (2 flop per FMA).  Used as the roofline denominator.           */
 int hb_dfma_peak(double millis, double *flops_per_s, void *stream);
 
+/* Synodic-section crossing detection on precomputed trajectories (linear branch, the one the
+ * reference's defaults select): replaces _SynodicDetectionBackend.run / detect_on_trajectory /
+ * _detect_with_segment_refine / _order_and_dedup_hits (algorithms/poincare/synodic/backend.py:
+ * 823-887, 687-821, 458-659, 382-455).
+ *   states  : samples of all trajectories concatenated, row-major [sum m_i][6] (the reference's
+ *             per-trajectory `states` arrays back to back);
+ *   times   : signed sample times, concatenated like states, or ONE shared array of m_uniform
+ *             entries when times_shared != 0 (a manifold tube: forward * linspace(0, tf, steps));
+ *   offsets : [n_traj + 1] sample offsets, or NULL when every trajectory has m_uniform samples.
+ * Hits are appended to hits[0 .. hit_capacity) in arbitrary order ((traj, seq) gives the reference
+ * order); hits_per_traj (optional, [n_traj]) receives the per-trajectory count.  The number of hits
+ * and of hits dropped for lack of capacity is read back with hb_read_hit_count.                   */
+int hb_synodic_detect(const hb_section *sec, int64_t n_traj, const double *states, const double *times,
+                      const int64_t *offsets, int32_t m_uniform, int32_t times_shared, hb_hit *hits,
+                      int64_t hit_capacity, int32_t *hits_per_traj, void *workspace, void *stream);
+
+/* Hit / overflow counters of the last call that used `workspace` (synchronises `stream`). */
+int hb_read_hit_count(const void *workspace, int64_t *n_hits, int64_t *n_overflow, void *stream);
+
 /* Arithmetic self-test: for every pair (a[i], b[i]) evaluates the shared-reciprocal division and the
  * restated sqrt fast path used by the parity variant next to the compiler's div.rn / sqrt.rn, and
  * the controller's pow(b, a).  All pointers are device arrays of n doubles.                      */

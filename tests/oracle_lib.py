@@ -151,3 +151,19 @@ def batch_dense(sys_, method, tol, y0, t_eval, n_threads=1):
     lib().ho_batch_dense(C.byref(sys_), method, C.byref(tol), _p(y0), C.c_int64(n), _p(t_eval), t_eval.size,
                          _p(out), counts.ctypes.data_as(ip), n_threads)
     return out, counts
+
+
+def synodic_detect(times, states, idx, offset=0.0, direction=0, proj=(0, 2), segment_refine=50,
+                   tol_on_surface=1e-6, dedup_time_tol=1e-9, dedup_point_tol=1e-6, max_hits=0, cap=64):
+    """Hits (times[K], states[K, dim]) of one sampled trajectory, reference detector semantics."""
+    times = np.ascontiguousarray(times, dtype=np.float64)
+    states = np.ascontiguousarray(states, dtype=np.float64)
+    m, dim = states.shape
+    ht = np.empty(cap)
+    hs = np.empty((cap, dim))
+    lib().ho_synodic_detect.restype = C.c_int
+    k = lib().ho_synodic_detect(_p(times), _p(states), m, dim, int(idx), C.c_double(offset), int(direction),
+                                int(proj[0]), int(proj[1]), int(segment_refine), C.c_double(tol_on_surface),
+                                C.c_double(dedup_time_tol), C.c_double(dedup_point_tol), int(max_hits), _p(ht),
+                                _p(hs), cap)
+    return ht[:k].copy(), hs[:k].copy()

@@ -1,0 +1,69 @@
+"""GPU parity: dense tube on device -> section detection on device vs the reference's hits (C1, C2)."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from test_oracle_synodic import oracle_hits
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _section(g):
+    from hiten_b200 import synodic
+    return synodic.make_section("y", float(g["req_offset"]), ("x", "z"), int(g["req_direction"]),
+                                int(g["req_segment_refine"]), float(g["req_tol_on_surface"]),
+                                float(g["req_dedup_time_tol"]), float(g["req_dedup_point_tol"]))
+
+
+@pytest.mark.parametrize("name", ["c1", "c2"])
+def test_gpu_detector_bit_exact_on_identical_samples(name):
+    """Same dense samples in -> identical hits out (integer/index work and IEEE arithmetic: bit-exact)."""
+    from hiten_b200 import synodic
+    g = np.load(os.path.join(HERE, "golden", f"synodic_{name}.npz"))
+    dense, times, hi, ht, hs = oracle_hits(g)
+    got = synodic.detect(dense, times, _section(g))
+    assert np.array_equal(got.trajectory_indices, g["hit_traj"])
+    assert np.array_equal(got.times, g["hit_time"])
+    assert np.array_equal(got.states, g["hit_state"])
+    assert np.array_equal(got.points, g["hit_point"])
+
+
+@pytest.mark.parametrize("name", ["c1", "c2"])
+def test_gpu_tube_and_section_vs_reference(name):
+    """Full GPU chain (Manifold.compute -> SynodicMap.compute): identical crossing counts, crossing points
+    within 1e-9 in synodic coordinates (BASELINE.json north_star)."""
+    import hiten_b200 as hb
+    from hiten_b200 import synodic
+    g = np.load(os.path.join(HERE, "golden", f"synodic_{name}.npz"))
+    mu, tf, steps, fwd = float(g["mu"]), float(g["tf"]), int(g["steps"]), int(g["forward"])
+    t_eval = np.linspace(0.0, tf, steps)
+    res = hb.cr3bp_dense(g["x0W"], mu, t_eval, forward=fwd, flip=(0, 6), keep_on_device=True)
+    got = synodic.detect(res.states, fwd * t_eval, _section(g))
+    assert len(got.times) == len(g["hit_time"])
+    assert np.array_equal(got.trajectory_indices, g["hit_traj"])
+    dp = np.abs(got.points - g["hit_point"]).max(axis=1)
+    dt = np.abs(got.times - g["hit_time"])
+    ds = np.abs(got.states - g["hit_state"]).max(axis=1)
+    print(f"[parity] {name}: {len(dp)} hits; |d point| median {np.median(dp):.2e} max {dp.max():.2e}; "
+          f"|d t| max {dt.max():.2e}; |d state| max {ds.max():.2e}; >1e-9: {(dp > 1e-9).sum()}")
+    assert dp.max() <= 1e-9
+
+
+def test_detector_ragged_and_empty():
+    from hiten_b200 import synodic
+    sec = synodic.make_section("y", 0.0, ("x", "z"), -1)
+    t = np.linspace(0.0, 1.0, 11)
+    x = np.zeros((11, 6)); x[:, 1] = 0.5 - t
+    lens = [11, 1, 7, 2]
+    states = np.concatenate([x[:m] for m in lens])
+    times = np.concatenate([t[:m] for m in lens])
+    off = np.concatenate([[0], np.cumsum(lens)])
+    got = synodic.detect(states, times, sec, offsets=off)
+    assert got.hits_per_traj.tolist() == [1, 0, 1, 0]
+    ref_t, ref_x = O.synodic_detect(t[:7], x[:7], 1, 0.0, -1)
+    assert np.array_equal(got.times[got.trajectory_indices == 2], ref_t)
+    empty = synodic.detect(np.empty((0, 5, 6)), t[:5], sec)
+    assert len(empty.times) == 0
