@@ -14,7 +14,7 @@
 //   _integrate_dop853_until_event     algorithms/integrators/rk.py:2680-2803
 //   _dop853_build_dense_cache / _dop853_eval_dense / _dop853_refine_in_step   rk.py:1791-2102
 //   controller helpers                algorithms/integrators/utils.py
-#include "hb_common.cuh"
+#include "hb_dop853.cuh"
 
 namespace {
 
@@ -106,207 +106,11 @@ HB_DEV void crtbp_rhs(const double (&s)[6], const PropParams &p, double (&out)[6
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// DOP853 stages, tableau resolved at compile time.
-//   y_stage = y; for j < i with a_ij != 0: y_stage += (h * a_ij) * k_j      (rk.py:1674-1678)
-// ---------------------------------------------------------------------------------------------
-template <class AR, int I, int J>
-HB_DEV void stage_acc(double (&ys)[6], const double (&k)[13][6], double h)
-{
-    if constexpr (J < I) {
-        if constexpr (HB_DOP853_A[I][J] != 0.0) {
-            constexpr double a = HB_DOP853_A[I][J];
-            const double ha = AR::mul(h, a);
-#pragma unroll
-            for (int d = 0; d < 6; ++d) ys[d] = AR::madd(ha, k[J][d], ys[d]);
-        }
-        stage_acc<AR, I, J + 1>(ys, k, h);
-    }
-}
-
-template <class AR, int NEG, int I>
-HB_DEV void run_stages(const double (&y)[6], double (&k)[13][6], double h, const PropParams &p)
-{
-    if constexpr (I < 12) {
-        double ys[6];
-#pragma unroll
-        for (int d = 0; d < 6; ++d) ys[d] = y[d];
-        stage_acc<AR, I, 0>(ys, k, h);
-        crtbp_rhs<AR, NEG>(ys, p, k[I]);
-        run_stages<AR, NEG, I + 1>(y, k, h, p);
-    }
-}
-
-template <class AR, int J>
-HB_DEV void high_acc(double (&yh)[6], const double (&k)[13][6], double h)
-{
-    if constexpr (J < 12) {
-        if constexpr (HB_DOP853_B[J] != 0.0) {
-            constexpr double b = HB_DOP853_B[J];
-            const double hb = AR::mul(h, b);
-#pragma unroll
-            for (int d = 0; d < 6; ++d) yh[d] = AR::madd(hb, k[J][d], yh[d]);
-        }
-        high_acc<AR, J + 1>(yh, k, h);
-    }
-}
-
-// err5 += E5_j * k_j ; err3 += E3_j * k_j     (rk.py:1691-1697)
-template <class AR, int J>
-HB_DEV void err_acc(double (&e5)[6], double (&e3)[6], const double (&k)[13][6])
-{
-    if constexpr (J < 13) {
-        if constexpr (HB_DOP853_E5[J] != 0.0) {
-            constexpr double c = HB_DOP853_E5[J];
-#pragma unroll
-            for (int d = 0; d < 6; ++d) e5[d] = AR::madd(c, k[J][d], e5[d]);
-        }
-        if constexpr (HB_DOP853_E3[J] != 0.0) {
-            constexpr double c = HB_DOP853_E3[J];
-#pragma unroll
-            for (int d = 0; d < 6; ++d) e3[d] = AR::madd(c, k[J][d], e3[d]);
-        }
-        err_acc<AR, J + 1>(e5, e3, k);
-    }
-}
-
-// One attempted step.  k[0] must hold f(t, y).  Returns the SciPy-style combined error norm
-// (rk.py:2457-2467): err = |h| * n5 / sqrt((n5 + 0.01 n3) * n), n5 = dot(e5/scale, e5/scale)
-// with np.dot's sequential FMA accumulation.
 template <class AR, int NEG>
-HB_DEV double dop853_attempt(const double (&y)[6], double (&k)[13][6], double h, double (&yh)[6],
-                             const PropParams &p)
-{
-    run_stages<AR, NEG, 1>(y, k, h, p);
-#pragma unroll
-    for (int d = 0; d < 6; ++d) yh[d] = y[d];
-    high_acc<AR, 0>(yh, k, h);
-    crtbp_rhs<AR, NEG>(yh, p, k[12]);
-
-    double e5[6], e3[6];
-#pragma unroll
-    for (int d = 0; d < 6; ++d) { e5[d] = 0.0; e3[d] = 0.0; }
-    err_acc<AR, 0>(e5, e3, k);
-    double n5 = 0.0, n3 = 0.0;
-#pragma unroll
-    for (int d = 0; d < 6; ++d) {
-        const double sc = AR::madd(p.rtol, fmax(fabs(y[d]), fabs(yh[d])), p.atol);
-        double a, b;
-        if constexpr (AR::parity) {
-            const double isc = hb_rcp_refined(sc);                 // both quotients correctly rounded
-            a = hb_div_with(AR::mul(e5[d], h), sc, isc);
-            b = hb_div_with(AR::mul(e3[d], h), sc, isc);
-        } else {
-            const double hs = h * hb_rcp_approx(sc);
-            a = e5[d] * hs;
-            b = e3[d] * hs;
-        }
-        n5 = fma(a, a, n5);
-        n3 = fma(b, b, n3);
-    }
-    if (n5 == 0.0 && n3 == 0.0) return 0.0;
-    const double denom = AR::madd(0.01, n3, n5);
-    if constexpr (AR::parity) return AR::div(AR::mul(fabs(h), n5), AR::sqrt(AR::mul(denom, 6.0)));
-    else return fabs(h) * n5 * hb_rsqrt_fast(denom * 6.0);
-}
-
-// ---------------------------------------------------------------------------------------------
-// Dense output of one accepted segment (rk.py:1836-1875): three extra stages (rows 13..15 of the
-// extended tableau), then F[0..6].  k[0] = f_old, k[12] = f_new.
-// ---------------------------------------------------------------------------------------------
-template <class AR, int S, int R>
-HB_DEV void ext_acc(double (&acc)[6], const double (&k)[13][6], const double (&kx)[3][6])
-{
-    if constexpr (R < S) {
-        if constexpr (HB_DOP853_A[S][R] != 0.0) {
-            constexpr double a = HB_DOP853_A[S][R];
-#pragma unroll
-            for (int d = 0; d < 6; ++d) {
-                const double kv = (R < 13) ? k[R < 13 ? R : 0][d] : kx[R >= 13 ? R - 13 : 0][d];
-                acc[d] = AR::madd(a, kv, acc[d]);
-            }
-        }
-        ext_acc<AR, S, R + 1>(acc, k, kx);
-    }
-}
-
-template <class AR, int NEG, int S>
-HB_DEV void ext_stage(const double (&y_old)[6], double h, const double (&k)[13][6], double (&kx)[3][6],
-                      const PropParams &p)
-{
-    double acc[6], ys[6];
-#pragma unroll
-    for (int d = 0; d < 6; ++d) acc[d] = 0.0;
-    ext_acc<AR, S, 0>(acc, k, kx);
-#pragma unroll
-    for (int d = 0; d < 6; ++d) ys[d] = AR::madd(h, acc[d], y_old[d]);
-    crtbp_rhs<AR, NEG>(ys, p, kx[S - 13]);
-}
-
-template <class AR, int I, int R>
-HB_DEV void d_acc(double (&acc)[6], const double (&k)[13][6], const double (&kx)[3][6])
-{
-    if constexpr (R < 16) {
-        if constexpr (HB_DOP853_D[I][R] != 0.0) {
-            constexpr double c = HB_DOP853_D[I][R];
-#pragma unroll
-            for (int d = 0; d < 6; ++d) {
-                const double kv = (R < 13) ? k[R < 13 ? R : 0][d] : kx[R >= 13 ? R - 13 : 0][d];
-                acc[d] = AR::madd(c, kv, acc[d]);
-            }
-        }
-        d_acc<AR, I, R + 1>(acc, k, kx);
-    }
-}
-
-template <class AR, int I>
-HB_DEV void d_rows(double (&F)[7][6], double h, const double (&k)[13][6], const double (&kx)[3][6])
-{
-    if constexpr (I < 4) {
-        double acc[6];
-#pragma unroll
-        for (int d = 0; d < 6; ++d) acc[d] = 0.0;
-        d_acc<AR, I, 0>(acc, k, kx);
-#pragma unroll
-        for (int d = 0; d < 6; ++d) F[3 + I][d] = AR::mul(h, acc[d]);
-        d_rows<AR, I + 1>(F, h, k, kx);
-    }
-}
-
-template <class AR, int NEG>
-HB_DEV void dense_cache(const double (&y_old)[6], const double (&y_new)[6], double h,
-                        const double (&k)[13][6], double (&F)[7][6], const PropParams &p)
-{
-    double kx[3][6];
-    ext_stage<AR, NEG, 13>(y_old, h, k, kx, p);
-    ext_stage<AR, NEG, 14>(y_old, h, k, kx, p);
-    ext_stage<AR, NEG, 15>(y_old, h, k, kx, p);
-#pragma unroll
-    for (int d = 0; d < 6; ++d) {
-        const double dy = AR::sub(y_new[d], y_old[d]);
-        F[0][d] = dy;
-        F[1][d] = AR::sub(AR::mul(h, k[0][d]), dy);
-        F[2][d] = AR::sub(AR::mul(2.0, dy), AR::mul(h, AR::add(k[12][d], k[0][d])));
-    }
-    d_rows<AR, 0>(F, h, k, kx);
-}
-
-// _dop853_eval_dense (rk.py:1989-2003): alternating x / (1-x) Horner form.
-template <class AR>
-HB_DEV void dense_eval(const double (&y_old)[6], const double (&F)[7][6], double x, double (&out)[6])
-{
-    const double omx = AR::sub(1.0, x);
-#pragma unroll
-    for (int d = 0; d < 6; ++d) {
-        double v = 0.0;
-#pragma unroll
-        for (int i = 6; i >= 0; --i) {
-            v = AR::add(v, F[i][d]);
-            v = AR::mul(v, ((6 - i) % 2 == 0) ? x : omx);
-        }
-        out[d] = AR::add(v, y_old[d]);
-    }
-}
+struct Cr3bpRhs {
+    const PropParams &p;
+    HB_DEV void operator()(const double (&y)[6], double (&dy)[6]) const { crtbp_rhs<AR, NEG>(y, p, dy); }
+};
 
 // Component select without dynamic register-array indexing (which would force local memory).
 HB_DEV double pick6(const double (&v)[6], int i)
@@ -365,6 +169,7 @@ template <class AR, int MODE, int NEG>
 __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) k_dop853_6(const PropParams p)
 {
     double y[6], yh[6], k[13][6];
+    const Cr3bpRhs<AR, NEG> rhs{p};
     double t = 0.0, h = 0.0, err_prev = -1.0, tf = 0.0, g_prev = 0.0;
     long long idx = -1;
     long long attempts = 0;
@@ -410,7 +215,10 @@ __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) k_dop853_6(const PropP
         // ---- one attempted step (rk.py:2452-2484) ----
         h = hb_clamp_step(h, p.max_step, p.min_step);
         if (AR::add(t, h) > tf) h = fabs(AR::sub(tf, t));
-        const double err = dop853_attempt<AR, NEG>(y, k, h, yh, p);
+        dop853_stages<AR>(y, k, h, yh, rhs);
+        double n5 = 0.0, n3 = 0.0;
+        dop853_err_sums<AR>(y, yh, k, h, p.rtol, p.atol, n5, n3);
+        const double err = dop853_err_norm<AR>(n5, n3, h, 6.0);
         ++attempts;
         int fin = -1;  // >= 0: trajectory finished with this status
 
@@ -423,7 +231,7 @@ __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) k_dop853_6(const PropP
                 if (hb_event_crossed(g_prev, g_new, p.ev_dir)) {
                     // _dop853_refine_in_step (rk.py:2079-2102): bisection on the dense interpolant
                     double F[7][6], ym[6];
-                    dense_cache<AR, NEG>(y, yh, h, k, F, p);
+                    dense_cache<AR>(y, yh, h, k, F, rhs);
                     double a = 0.0, b = 1.0, g_left = g_prev, xh = 1.0;
                     bool found = false;
                     for (int it = 0; it < 128; ++it) {
@@ -456,7 +264,7 @@ __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) k_dop853_6(const PropP
                 if (cursor < p.m && (last || p.t_eval[cursor] < t_new)) {
                     const double hseg = AR::sub(t_new, t);
                     double F[7][6], yo[6];
-                    if (hseg != 0.0) dense_cache<AR, NEG>(y, yh, hseg, k, F, p);
+                    if (hseg != 0.0) dense_cache<AR>(y, yh, hseg, k, F, rhs);
                     while (cursor < p.m) {
                         const double tq = p.t_eval[cursor];
                         if (!(last || tq < t_new)) break;
@@ -488,7 +296,7 @@ __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) k_dop853_6(const PropP
                             for (int d = 0; d < 6; ++d) yo[d] = AR::add(AR::sub(yh[d], y[d]), y[d]);
                         } else {
                             double F[7][6];
-                            dense_cache<AR, NEG>(y, yh, hseg, k, F, p);
+                            dense_cache<AR>(y, yh, hseg, k, F, rhs);
                             dense_eval<AR>(y, F, x, yo);
                         }
                     }

@@ -1,0 +1,221 @@
+// hb_dop853.cuh -- DOP853 machinery on a lane-local 6-component slice, tableau resolved at compile time.
+//
+// Shared by the 6-state kernel (one trajectory per thread: the slice IS the state) and the 42-state
+// state+STM kernel (8-lane group per trajectory: each lane carries one STM column or the state).
+// RHS is a functor  void operator()(const double (&y)[6], double (&dy)[6]) const .
+// Reference: hiten/algorithms/integrators/rk.py  dop853_step_jit_kernel :1637-1708,
+// _dop853_build_dense_cache :1791-1875, _dop853_eval_dense :1962-2003.
+#pragma once
+#include "hb_common.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// DOP853 stages, tableau resolved at compile time.
+//   y_stage = y; for j < i with a_ij != 0: y_stage += (h * a_ij) * k_j      (rk.py:1674-1678)
+// ---------------------------------------------------------------------------------------------
+template <class AR, int I, int J>
+HB_DEV void stage_acc(double (&ys)[6], const double (&k)[13][6], double h)
+{
+    if constexpr (J < I) {
+        if constexpr (HB_DOP853_A[I][J] != 0.0) {
+            constexpr double a = HB_DOP853_A[I][J];
+            const double ha = AR::mul(h, a);
+#pragma unroll
+            for (int d = 0; d < 6; ++d) ys[d] = AR::madd(ha, k[J][d], ys[d]);
+        }
+        stage_acc<AR, I, J + 1>(ys, k, h);
+    }
+}
+
+template <class AR, class RHS, int I>
+HB_DEV void run_stages(const double (&y)[6], double (&k)[13][6], double h, const RHS &rhs)
+{
+    if constexpr (I < 12) {
+        double ys[6];
+#pragma unroll
+        for (int d = 0; d < 6; ++d) ys[d] = y[d];
+        stage_acc<AR, I, 0>(ys, k, h);
+        rhs(ys, k[I]);
+        run_stages<AR, RHS, I + 1>(y, k, h, rhs);
+    }
+}
+
+template <class AR, int J>
+HB_DEV void high_acc(double (&yh)[6], const double (&k)[13][6], double h)
+{
+    if constexpr (J < 12) {
+        if constexpr (HB_DOP853_B[J] != 0.0) {
+            constexpr double b = HB_DOP853_B[J];
+            const double hb = AR::mul(h, b);
+#pragma unroll
+            for (int d = 0; d < 6; ++d) yh[d] = AR::madd(hb, k[J][d], yh[d]);
+        }
+        high_acc<AR, J + 1>(yh, k, h);
+    }
+}
+
+// err5 += E5_j * k_j ; err3 += E3_j * k_j     (rk.py:1691-1697)
+template <class AR, int J>
+HB_DEV void err_acc(double (&e5)[6], double (&e3)[6], const double (&k)[13][6])
+{
+    if constexpr (J < 13) {
+        if constexpr (HB_DOP853_E5[J] != 0.0) {
+            constexpr double c = HB_DOP853_E5[J];
+#pragma unroll
+            for (int d = 0; d < 6; ++d) e5[d] = AR::madd(c, k[J][d], e5[d]);
+        }
+        if constexpr (HB_DOP853_E3[J] != 0.0) {
+            constexpr double c = HB_DOP853_E3[J];
+#pragma unroll
+            for (int d = 0; d < 6; ++d) e3[d] = AR::madd(c, k[J][d], e3[d]);
+        }
+        err_acc<AR, J + 1>(e5, e3, k);
+    }
+}
+
+// One attempted step, stage part.  k[0] must hold f(t, y); fills k[1..12] and y_high.
+template <class AR, class RHS>
+HB_DEV void dop853_stages(const double (&y)[6], double (&k)[13][6], double h, double (&yh)[6], const RHS &rhs)
+{
+    run_stages<AR, RHS, 1>(y, k, h, rhs);
+#pragma unroll
+    for (int d = 0; d < 6; ++d) yh[d] = y[d];
+    high_acc<AR, 0>(yh, k, h);
+    rhs(yh, k[12]);
+}
+
+// Error sums of this lane's 6 components (rk.py:1686-1699, 2457-2462):
+//   n5 = dot(e5/scale, e5/scale), n3 = dot(e3/scale, e3/scale), sequential FMA accumulation like np.dot.
+template <class AR>
+HB_DEV void dop853_err_sums(const double (&y)[6], const double (&yh)[6], const double (&k)[13][6], double h,
+                            double rtol, double atol, double &n5, double &n3)
+{
+    double e5[6], e3[6];
+#pragma unroll
+    for (int d = 0; d < 6; ++d) { e5[d] = 0.0; e3[d] = 0.0; }
+    err_acc<AR, 0>(e5, e3, k);
+#pragma unroll
+    for (int d = 0; d < 6; ++d) {
+        const double sc = AR::madd(rtol, fmax(fabs(y[d]), fabs(yh[d])), atol);
+        double a, b;
+        if constexpr (AR::parity) {
+            const double isc = hb_rcp_refined(sc);                 // both quotients correctly rounded
+            a = hb_div_with(AR::mul(e5[d], h), sc, isc);
+            b = hb_div_with(AR::mul(e3[d], h), sc, isc);
+        } else {
+            const double hs = h * hb_rcp_approx(sc);
+            a = e5[d] * hs;
+            b = e3[d] * hs;
+        }
+        n5 = fma(a, a, n5);
+        n3 = fma(b, b, n3);
+    }
+}
+
+// SciPy-style combined error norm (rk.py:2463-2467): err = |h| * n5 / sqrt((n5 + 0.01 n3) * n)
+template <class AR>
+HB_DEV double dop853_err_norm(double n5, double n3, double h, double ndim)
+{
+    if (n5 == 0.0 && n3 == 0.0) return 0.0;
+    const double denom = AR::madd(0.01, n3, n5);
+    if constexpr (AR::parity) return AR::div(AR::mul(fabs(h), n5), AR::sqrt(AR::mul(denom, ndim)));
+    else return fabs(h) * n5 * hb_rsqrt_fast(denom * ndim);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Dense output of one accepted segment (rk.py:1836-1875): three extra stages (rows 13..15 of the
+// extended tableau), then F[0..6].  k[0] = f_old, k[12] = f_new.
+// ---------------------------------------------------------------------------------------------
+template <class AR, int S, int R>
+HB_DEV void ext_acc(double (&acc)[6], const double (&k)[13][6], const double (&kx)[3][6])
+{
+    if constexpr (R < S) {
+        if constexpr (HB_DOP853_A[S][R] != 0.0) {
+            constexpr double a = HB_DOP853_A[S][R];
+#pragma unroll
+            for (int d = 0; d < 6; ++d) {
+                const double kv = (R < 13) ? k[R < 13 ? R : 0][d] : kx[R >= 13 ? R - 13 : 0][d];
+                acc[d] = AR::madd(a, kv, acc[d]);
+            }
+        }
+        ext_acc<AR, S, R + 1>(acc, k, kx);
+    }
+}
+
+template <class AR, class RHS, int S>
+HB_DEV void ext_stage(const double (&y_old)[6], double h, const double (&k)[13][6], double (&kx)[3][6],
+                      const RHS &rhs)
+{
+    double acc[6], ys[6];
+#pragma unroll
+    for (int d = 0; d < 6; ++d) acc[d] = 0.0;
+    ext_acc<AR, S, 0>(acc, k, kx);
+#pragma unroll
+    for (int d = 0; d < 6; ++d) ys[d] = AR::madd(h, acc[d], y_old[d]);
+    rhs(ys, kx[S - 13]);
+}
+
+template <class AR, int I, int R>
+HB_DEV void d_acc(double (&acc)[6], const double (&k)[13][6], const double (&kx)[3][6])
+{
+    if constexpr (R < 16) {
+        if constexpr (HB_DOP853_D[I][R] != 0.0) {
+            constexpr double c = HB_DOP853_D[I][R];
+#pragma unroll
+            for (int d = 0; d < 6; ++d) {
+                const double kv = (R < 13) ? k[R < 13 ? R : 0][d] : kx[R >= 13 ? R - 13 : 0][d];
+                acc[d] = AR::madd(c, kv, acc[d]);
+            }
+        }
+        d_acc<AR, I, R + 1>(acc, k, kx);
+    }
+}
+
+template <class AR, int I>
+HB_DEV void d_rows(double (&F)[7][6], double h, const double (&k)[13][6], const double (&kx)[3][6])
+{
+    if constexpr (I < 4) {
+        double acc[6];
+#pragma unroll
+        for (int d = 0; d < 6; ++d) acc[d] = 0.0;
+        d_acc<AR, I, 0>(acc, k, kx);
+#pragma unroll
+        for (int d = 0; d < 6; ++d) F[3 + I][d] = AR::mul(h, acc[d]);
+        d_rows<AR, I + 1>(F, h, k, kx);
+    }
+}
+
+template <class AR, class RHS>
+HB_DEV void dense_cache(const double (&y_old)[6], const double (&y_new)[6], double h,
+                        const double (&k)[13][6], double (&F)[7][6], const RHS &rhs)
+{
+    double kx[3][6];
+    ext_stage<AR, RHS, 13>(y_old, h, k, kx, rhs);
+    ext_stage<AR, RHS, 14>(y_old, h, k, kx, rhs);
+    ext_stage<AR, RHS, 15>(y_old, h, k, kx, rhs);
+#pragma unroll
+    for (int d = 0; d < 6; ++d) {
+        const double dy = AR::sub(y_new[d], y_old[d]);
+        F[0][d] = dy;
+        F[1][d] = AR::sub(AR::mul(h, k[0][d]), dy);
+        F[2][d] = AR::sub(AR::mul(2.0, dy), AR::mul(h, AR::add(k[12][d], k[0][d])));
+    }
+    d_rows<AR, 0>(F, h, k, kx);
+}
+
+// _dop853_eval_dense (rk.py:1989-2003): alternating x / (1-x) Horner form.
+template <class AR>
+HB_DEV void dense_eval(const double (&y_old)[6], const double (&F)[7][6], double x, double (&out)[6])
+{
+    const double omx = AR::sub(1.0, x);
+#pragma unroll
+    for (int d = 0; d < 6; ++d) {
+        double v = 0.0;
+#pragma unroll
+        for (int i = 6; i >= 0; --i) {
+            v = AR::add(v, F[i][d]);
+            v = AR::mul(v, ((6 - i) % 2 == 0) ? x : omx);
+        }
+        out[d] = AR::add(v, y_old[d]);
+    }
+}
+

@@ -158,6 +158,67 @@ def cr3bp_event(y0, mu, tmax, event_idx, *, event_offset=0.0, direction=0, xtol=
         return BatchResult(yh, nacc, nrej, status, t_hit=th)
 
 
+def cr3bp_stm(x0, mu, tf, *, t0=0.0, forward=1, flip=(36, 42), tf_per_traj=None, integ=None, device=None,
+              stream=None, ws=None):
+    """Batched _compute_stm end result: PHI rows [N, 42] at tf (Phi row-major, then the state).
+
+    tf may differ per trajectory (tf_per_traj, e.g. the period of each family member)."""
+    _require_cuda()
+    lib = L.load()
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    with torch.cuda.device(device):
+        x0d, host = _to_device_soa(x0, device)
+        n = x0d.shape[1]
+        _, nacc, nrej, status = _alloc_out(n, device)
+        out = torch.empty((n, 42), dtype=torch.float64, device=device)
+        ws = workspace(device) if ws is None else ws
+        integ = make_integ() if integ is None else integ
+        sys_ = make_sys(mu, forward, flip)
+        tfp = None
+        if tf_per_traj is not None:
+            tfp = torch.as_tensor(np.asarray(tf_per_traj, dtype=np.float64)).to(device) \
+                if not isinstance(tf_per_traj, torch.Tensor) else tf_per_traj
+        rc = lib.hb_cr3bp_stm(sys_, integ, n, x0d.data_ptr(), float(t0), float(tf),
+                              None if tfp is None else tfp.data_ptr(), out.data_ptr(), nacc.data_ptr(),
+                              nrej.data_ptr(), status.data_ptr(), ws.data_ptr(), _stream_ptr(stream))
+        L.check(rc, "hb_cr3bp_stm")
+        if host:
+            return BatchResult(None, nacc.cpu().numpy(), nrej.cpu().numpy(), status.cpu().numpy(),
+                               states=out.cpu().numpy())
+        return BatchResult(None, nacc, nrej, status, states=out)
+
+
+def cr3bp_stm_dense(x0, mu, t_eval, *, forward=1, flip=(36, 42), integ=None, device=None, stream=None, ws=None,
+                    keep_on_device=False):
+    """Batched _compute_stm with dense output PHI[N, m, 42]; t_eval is [m] (shared) or [N, m]."""
+    _require_cuda()
+    lib = L.load()
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    with torch.cuda.device(device):
+        x0d, host = _to_device_soa(x0, device)
+        n = x0d.shape[1]
+        te = t_eval if isinstance(t_eval, torch.Tensor) else torch.from_numpy(
+            np.ascontiguousarray(np.asarray(t_eval, dtype=np.float64)))
+        te = te.to(device).contiguous()
+        per = 1 if te.dim() == 2 else 0
+        m = int(te.shape[-1])
+        if per and te.shape[0] != n:
+            raise ValueError("per-trajectory t_eval must have shape [N, m]")
+        out = torch.empty((n, m, 42), dtype=torch.float64, device=device)
+        _, nacc, nrej, status = _alloc_out(n, device)
+        ws = workspace(device) if ws is None else ws
+        integ = make_integ() if integ is None else integ
+        sys_ = make_sys(mu, forward, flip)
+        rc = lib.hb_cr3bp_stm_dense(sys_, integ, n, x0d.data_ptr(), te.data_ptr(), m, per, out.data_ptr(),
+                                    nacc.data_ptr(), nrej.data_ptr(), status.data_ptr(), ws.data_ptr(),
+                                    _stream_ptr(stream))
+        L.check(rc, "hb_cr3bp_stm_dense")
+        if host and not keep_on_device:
+            return BatchResult(None, nacc.cpu().numpy(), nrej.cpu().numpy(), status.cpu().numpy(),
+                               states=out.cpu().numpy())
+        return BatchResult(None, nacc, nrej, status, states=out)
+
+
 def dfma_peak(millis=50.0):
     """Measured FP64 FMA flop/s of the current device (roofline denominator)."""
     _require_cuda()

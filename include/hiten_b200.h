@@ -143,6 +143,24 @@ int hb_cr3bp_event(const hb_cr3bp *sys, const hb_integ *integ, const hb_event *e
  * `millis` ms and returns flop/s (2 flop per FMA).  Used as the roofline denominator.           */
 int hb_dfma_peak(double millis, double *flops_per_s, void *stream);
 
+/* Batched 42-dimensional state + STM propagation: replaces _compute_stm / _var_equations /
+ * _jacobian_crtbp (algorithms/dynamics/rtbp.py:258-340, 168-255, 77-165) as called by the manifold
+ * service (algorithms/types/services/manifold.py:236-243), the corrector
+ * (algorithms/corrector/operators.py:298-307) and orbit stability (services/orbits.py).
+ * The initial condition is PHI0 = [I6 row-major, x0]; sys->flip_lo/hi select the derivative block the
+ * backward wrapper negates: (36,42) = state only (what _compute_stm passes), <0 = everything.
+ * phi_out[i][0..41] is the reference's flat PHI row at tf (Phi row-major in [0,36), state in [36,42)),
+ * with the same dense-interpolant-at-tf semantics as hb_cr3bp_propagate.                          */
+int hb_cr3bp_stm(const hb_cr3bp *sys, const hb_integ *integ, int64_t n, const double *x0_soa, double t0,
+                 double tf, const double *tf_per_traj, double *phi_out, int32_t *n_acc, int32_t *n_rej,
+                 int32_t *status, void *workspace, void *stream);
+
+/* The same with dense output PHI[i][k][0..41] on an ascending grid: t_eval is one shared array of m
+ * times, or (t_eval_per_traj != 0) one row of m times per trajectory (each orbit its own period). */
+int hb_cr3bp_stm_dense(const hb_cr3bp *sys, const hb_integ *integ, int64_t n, const double *x0_soa,
+                       const double *t_eval, int32_t m, int32_t t_eval_per_traj, double *phi_dense,
+                       int32_t *n_acc, int32_t *n_rej, int32_t *status, void *workspace, void *stream);
+
 /* Synodic-section crossing detection on precomputed trajectories (linear branch, the one the
  * reference's defaults select): replaces _SynodicDetectionBackend.run / detect_on_trajectory /
  * _detect_with_segment_refine / _order_and_dedup_hits (algorithms/poincare/synodic/backend.py:
