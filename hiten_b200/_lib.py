@@ -38,6 +38,21 @@ class HbSection(C.Structure):
                 ("dedup_time_tol", C.c_double), ("dedup_point_tol", C.c_double)]
 
 
+class HbPolyHam(C.Structure):
+    _fields_ = [("n_dof", C.c_int32), ("max_deg", C.c_int32), ("ptr", C.c_int64 * 7), ("terms", C.c_void_p)]
+
+
+HB_MAX_TAO_SUBSTEPS = 27
+HB_SYMPLECTIC = 2
+
+
+class HbCmOpts(C.Structure):
+    _fields_ = [("dt", C.c_double), ("max_steps", C.c_int32), ("method", C.c_int32), ("order", C.c_int32),
+                ("section", C.c_int32), ("arith", C.c_int32), ("n_sub", C.c_int32),
+                ("sub_ts", C.c_double * HB_MAX_TAO_SUBSTEPS), ("sub_cos", C.c_double * HB_MAX_TAO_SUBSTEPS),
+                ("sub_sin", C.c_double * HB_MAX_TAO_SUBSTEPS)]
+
+
 class HitenB200Error(RuntimeError):
     pass
 
@@ -60,6 +75,8 @@ SIGNATURES = {
                                vp, vp, vp, vp, vp]),
     "hb_cr3bp_stm_dense": (C.c_int, [C.POINTER(HbCr3bp), C.POINTER(HbInteg), C.c_int64, vp, vp, C.c_int32, C.c_int32,
                                      vp, vp, vp, vp, vp, vp]),
+    "hb_cm_prepare": (C.c_int, [C.POINTER(HbCmOpts), C.c_double]),
+    "hb_cm_poincare_map": (C.c_int, [C.POINTER(HbPolyHam), C.POINTER(HbCmOpts), C.c_int64, vp, vp, vp, vp, vp, vp]),
     "hb_synodic_detect": (C.c_int, [C.POINTER(HbSection), C.c_int64, vp, vp, vp, C.c_int32, C.c_int32, vp, C.c_int64,
                                     vp, vp, vp]),
     "hb_read_hit_count": (C.c_int, [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), vp]),

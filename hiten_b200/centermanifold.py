@@ -1,0 +1,118 @@
+"""Centre-manifold Poincare map on the GPU (host wrapper over hb_cm_poincare_map).
+
+Reference: hiten/algorithms/poincare/centermanifold/backend.py (_CenterManifoldBackend.run :404-466,
+_poincare_map :314-382).  The polynomial tables arrive as the reference's jac_H / clmo_table and are reduced
+once, on the host, to the sparse real term list the kernel keeps in shared memory.
+"""
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .propagate import _require_cuda, _stream_ptr, workspace
+
+SECTION = {"q2": 0, "p2": 1, "q3": 2, "p3": 3}
+TERM_DTYPE = np.dtype([("coef", "<f8"), ("ex", "<u8")])
+
+
+@dataclass
+class PolyTable:
+    """Sparse gradient table: terms of partial p are rows ptr[p]:ptr[p+1] (order of evaluation preserved)."""
+    ptr: np.ndarray      # [7] int64
+    deg: np.ndarray      # [T] int32
+    coef: np.ndarray     # [T] float64
+    exp: np.ndarray      # [T, 6] int32
+    _dev: dict = None
+
+    @property
+    def max_deg(self):
+        return int(self.exp.max()) if self.exp.size else 0
+
+    @classmethod
+    def from_reference(cls, jac_H, clmo):
+        """jac_H[p][d] = packed complex coefficients of degree d of dH/dvar_p; clmo[d][i] = packed exponents
+        (6 bits each for k1..k5, k0 = d - sum; hiten/algorithms/polynomial/base.py:222-259)."""
+        ptr, deg, coef, exp = [0], [], [], []
+        for p in range(6):
+            for d in range(len(jac_H[p])):
+                arr = np.asarray(jac_H[p][d])
+                nz = np.nonzero(arr != 0)[0]
+                if nz.size == 0:
+                    continue
+                packed = np.asarray(clmo[d])[nz].astype(np.int64)
+                ks = np.stack([(packed >> s) & 0x3F for s in (0, 6, 12, 18, 24)], axis=1)
+                k0 = d - ks.sum(axis=1)
+                deg.append(np.full(nz.size, d, dtype=np.int32))
+                coef.append(np.real(arr[nz]).astype(np.float64))
+                exp.append(np.column_stack([k0, ks]).astype(np.int32))
+            ptr.append(sum(len(x) for x in deg))
+        if not deg:
+            return cls(np.array(ptr, dtype=np.int64), np.empty(0, np.int32), np.empty(0), np.empty((0, 6), np.int32))
+        return cls(np.array(ptr, dtype=np.int64), np.concatenate(deg), np.concatenate(coef), np.concatenate(exp))
+
+    def packed(self):
+        rec = np.empty(self.coef.size, dtype=TERM_DTYPE)
+        rec["coef"] = self.coef
+        ex = np.zeros(self.coef.size, dtype=np.uint64)
+        for v in range(6):
+            ex |= self.exp[:, v].astype(np.uint64) << np.uint64(8 * v)
+        ex |= self.deg.astype(np.uint64) << np.uint64(48)
+        rec["ex"] = ex
+        return rec
+
+    def device_struct(self, device):
+        key = str(device)
+        if self._dev is None:
+            self._dev = {}
+        if key not in self._dev:
+            rec = self.packed()
+            buf = torch.from_numpy(rec.view(np.float64).copy() if rec.size else np.zeros(2)).to(device)
+            self._dev[key] = buf
+        buf = self._dev[key]
+        return L.HbPolyHam(3, self.max_deg, (L.C.c_int64 * 7)(*[int(x) for x in self.ptr]), buf.data_ptr()), buf
+
+
+def make_opts(dt=0.01, max_steps=2000, method="fixed", order=4, section_coord="q3", c_omega_heuristic=20.0,
+              arith="parity"):
+    """method/order as in IntegrationOptions + config.integration.method ("fixed" | "symplectic")."""
+    if method == "adaptive":
+        raise NotImplementedError("Adaptive integrator is not implemented in CM backend; use 'fixed' (RK) or 'symplectic'.")
+    if method == "symplectic":
+        m = L.HB_SYMPLECTIC
+    elif method == "fixed":
+        m = {4: L.HB_RK4, 6: L.HB_RK6, 8: L.HB_RK8}.get(int(order))
+        if m is None:
+            raise ValueError("RK order must be 4, 6, or 8")
+    else:
+        raise ValueError(f"unknown integration method {method!r}")
+    o = L.HbCmOpts()
+    o.dt, o.max_steps, o.method, o.order = float(dt), int(max_steps), m, int(order)
+    o.section = SECTION[section_coord]
+    o.arith = {"parity": L.HB_ARITH_PARITY, "fast": L.HB_ARITH_FAST}[arith]
+    L.check(L.load().hb_cm_prepare(L.C.byref(o), float(c_omega_heuristic)), "hb_cm_prepare")
+    return o
+
+
+def poincare_map(table, seeds, opts, *, device=None, stream=None, ws=None):
+    """_poincare_map on the GPU: seeds [N, 4] (host ndarray or CUDA tensor) -> (flags, states[N,4], times[N])."""
+    _require_cuda()
+    lib = L.load()
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    with torch.cuda.device(device):
+        host = not (isinstance(seeds, torch.Tensor) and seeds.is_cuda)
+        sd = torch.from_numpy(np.ascontiguousarray(seeds, dtype=np.float64)).to(device) if host else seeds.contiguous()
+        if sd.dim() != 2 or sd.shape[1] != 4:
+            raise ValueError("seeds must have shape (N, 4) = (q2, p2, q3, p3)")
+        n = int(sd.shape[0])
+        flags = torch.zeros(n, dtype=torch.int32, device=device)
+        out = torch.zeros((n, 4), dtype=torch.float64, device=device)
+        tt = torch.zeros(n, dtype=torch.float64, device=device)
+        ws = workspace(device) if ws is None else ws
+        ham, keep = table.device_struct(device)
+        rc = lib.hb_cm_poincare_map(ham, opts, n, sd.data_ptr(), flags.data_ptr(), out.data_ptr(), tt.data_ptr(),
+                                    ws.data_ptr(), _stream_ptr(stream))
+        L.check(rc, "hb_cm_poincare_map")
+        if host:
+            return flags.cpu().numpy().astype(np.int64), out.cpu().numpy(), tt.cpu().numpy()
+        return flags, out, tt

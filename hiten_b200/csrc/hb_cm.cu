@@ -1,0 +1,359 @@
+// hb_cm.cu -- centre-manifold Poincare map: fixed-step RK4/6/8 or Tao extended-phase-space symplectic
+// steps on a polynomial Hamiltonian, with in-loop section detection and cubic-Hermite hit interpolation.
+//
+// One seed per thread.  The polynomial gradient is evaluated from a sparse real term table
+// {coef, 6 exponents, degree} held in shared memory (uniform across the block -> broadcast reads) and a
+// per-thread power table x_v^e, also in shared memory, laid out [v][e][thread] (conflict-free).  Terms are
+// visited in the reference's order (degree ascending, packed index ascending) and summed per degree
+// first, so the parity variant reproduces its rounding.
+//
+// Reference routines (paths relative to hiten/):
+//   _poly_evaluate / _polynomial_evaluate   algorithms/polynomial/algebra.py:403-461, operations.py:551-583
+//   _hamiltonian_rhs                        algorithms/dynamics/hamiltonian.py:35-90
+//   _eval_dH_dQ / _eval_dH_dP               algorithms/integrators/symplectic.py:105-178
+//   _phi_H_a/_b/_phi_omega_H_c/_recursive_update_poly/_integrate_symplectic   symplectic.py:370-653
+//   _integrate_rk_ham, _detect_crossing, _poincare_step, _poincare_map
+//                                           algorithms/poincare/centermanifold/backend.py:35-382
+//   _hermite_scalar                         algorithms/poincare/utils.py:54-97
+#include "hb_common.cuh"
+
+#include <cmath>
+
+namespace {
+
+constexpr int CM_BLOCK = 128;
+
+struct TermMeta {          // 16 bytes
+    double coef;
+    unsigned long long ex; // exponents of (q1,q2,q3,p1,p2,p3) in bytes 0..5, degree in bytes 6..7
+};
+
+struct CmParams {
+    hb_cm_opts o;
+    long long n;
+    const double *seeds;   // [n][4] (q2,p2,q3,p3)
+    int *flags;
+    double *out;           // [n][4]
+    double *t_out;
+    HbWorkspace *ws;
+    const TermMeta *terms; // device, all partials back to back
+    int ptr[7];
+    int n_terms;
+    int D;                 // max exponent
+};
+
+// ---- polynomial gradient -----------------------------------------------------------------------
+// pw points at this thread's column of the shared power table: pw[(v*(D+1)+e)*CM_BLOCK].
+template <class AR>
+__device__ __noinline__ void cm_grad(const CmParams &p, double *pw, const TermMeta *terms, const double (&pt)[6],
+                                     double (&g)[6])
+{
+    const int D1 = p.D + 1;
+#pragma unroll
+    for (int v = 0; v < 6; ++v) {
+        double w = 1.0;
+        pw[(v * D1) * CM_BLOCK] = 1.0;
+        for (int e = 1; e < D1; ++e) {
+            w = AR::mul(w, pt[v]);
+            pw[(v * D1 + e) * CM_BLOCK] = w;
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+        double total = 0.0, acc = 0.0;
+        int dcur = -1;
+        for (int i = p.ptr[q]; i < p.ptr[q + 1]; ++i) {
+            const TermMeta tm = terms[i];
+            const int d = (int)(tm.ex >> 48);
+            if (d != dcur) {
+                if (dcur >= 0) total = AR::add(total, acc);
+                acc = 0.0;
+                dcur = d;
+            }
+            double t = 1.0;
+            bool first = true;
+#pragma unroll
+            for (int v = 0; v < 6; ++v) {
+                const int e = (int)((tm.ex >> (8 * v)) & 0xffu);
+                if (e) {
+                    const double f = pw[(v * D1 + e) * CM_BLOCK];
+                    t = first ? f : AR::mul(t, f);
+                    first = false;
+                }
+            }
+            acc = AR::madd(tm.coef, t, acc);
+        }
+        if (dcur >= 0) total = AR::add(total, acc);
+        g[q] = total;
+    }
+}
+
+// rhs = [dH/dP, -dH/dQ]  (hamiltonian.py:80-90)
+template <class AR>
+HB_DEV void cm_rhs(const CmParams &p, double *pw, const TermMeta *terms, const double (&y)[6], double (&dy)[6])
+{
+    double g[6];
+    cm_grad<AR>(p, pw, terms, y, g);
+    dy[0] = g[3]; dy[1] = g[4]; dy[2] = g[5];
+    dy[3] = -g[0]; dy[4] = -g[1]; dy[5] = -g[2];
+}
+
+// ---- fixed-step explicit RK with compile-time tableau --------------------------------------------
+struct TabRK4 { static constexpr int S = 4; static constexpr double a(int i, int j) { return HB_RK4_A[i][j]; } static constexpr double b(int i) { return HB_RK4_B[i]; } };
+struct TabRK6 { static constexpr int S = 7; static constexpr double a(int i, int j) { return HB_RK6_A[i][j]; } static constexpr double b(int i) { return HB_RK6_B[i]; } };
+struct TabRK8 { static constexpr int S = 13; static constexpr double a(int i, int j) { return HB_RK8_A[i][j]; } static constexpr double b(int i) { return HB_RK8_B[i]; } };
+
+template <class AR, class TAB, int I, int J>
+HB_DEV void g_stage_acc(double (&ys)[6], const double (&k)[TAB::S][6], double h)
+{
+    if constexpr (J < I) {
+        if constexpr (TAB::a(I, J) != 0.0) {
+            constexpr double a = TAB::a(I, J);
+            const double ha = AR::mul(h, a);
+#pragma unroll
+            for (int d = 0; d < 6; ++d) ys[d] = AR::madd(ha, k[J][d], ys[d]);
+        }
+        g_stage_acc<AR, TAB, I, J + 1>(ys, k, h);
+    }
+}
+// is stage I referenced by a later stage or by B?  (the 7th DOPRI5 stage of "RK6" is not)
+template <class TAB, int I, int R>
+constexpr bool g_stage_used()
+{
+    if constexpr (R >= TAB::S) return TAB::b(I) != 0.0;
+    else return (TAB::a(R, I) != 0.0) || g_stage_used<TAB, I, R + 1>();
+}
+template <class AR, class TAB, int I>
+HB_DEV void g_run_stages(const CmParams &p, double *pw, const TermMeta *terms, const double (&y)[6],
+                         double (&k)[TAB::S][6], double h)
+{
+    if constexpr (I < TAB::S) {
+        if constexpr (g_stage_used<TAB, I, I + 1>()) {
+            double ys[6];
+#pragma unroll
+            for (int d = 0; d < 6; ++d) ys[d] = y[d];
+            g_stage_acc<AR, TAB, I, 0>(ys, k, h);
+            cm_rhs<AR>(p, pw, terms, ys, k[I]);
+        }
+        g_run_stages<AR, TAB, I + 1>(p, pw, terms, y, k, h);
+    }
+}
+template <class AR, class TAB, int J>
+HB_DEV void g_high_acc(double (&yn)[6], const double (&k)[TAB::S][6], double h)
+{
+    if constexpr (J < TAB::S) {
+        if constexpr (TAB::b(J) != 0.0) {
+            constexpr double b = TAB::b(J);
+            const double hb = AR::mul(h, b);
+#pragma unroll
+            for (int d = 0; d < 6; ++d) yn[d] = AR::madd(hb, k[J][d], yn[d]);
+        }
+        g_high_acc<AR, TAB, J + 1>(yn, k, h);
+    }
+}
+
+// _hermite_scalar (poincare/utils.py:93-97)
+template <class AR>
+HB_DEV double hermite_scalar(double s, double y0, double y1, double dy0, double dy1, double dt)
+{
+    const double oms = AR::sub(1.0, s);
+    const double oms2 = AR::mul(oms, oms), s2 = AR::mul(s, s);
+    const double h00 = AR::mul(AR::add(1.0, AR::mul(2.0, s)), oms2);
+    const double h10 = AR::mul(s, oms2);
+    const double h01 = AR::mul(s2, AR::sub(3.0, AR::mul(2.0, s)));
+    const double h11 = AR::mul(s2, AR::sub(s, 1.0));
+    return AR::add(AR::add(AR::add(AR::mul(h00, y0), AR::mul(AR::mul(h10, dy0), dt)), AR::mul(h01, y1)),
+                   AR::mul(AR::mul(h11, dy1), dt));
+}
+
+// TAB = void selects the Tao symplectic integrator.
+template <class AR, class TAB>
+__global__ void __launch_bounds__(CM_BLOCK) k_cm_map(const CmParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    TermMeta *terms = reinterpret_cast<TermMeta *>(smem);
+    double *pw_all = reinterpret_cast<double *>(smem + (((size_t)p.n_terms * sizeof(TermMeta) + 15) & ~(size_t)15));
+    for (int i = threadIdx.x; i < p.n_terms; i += CM_BLOCK) terms[i] = p.terms[i];
+    __syncthreads();
+    double *pw = pw_all + threadIdx.x;
+    constexpr bool TAO = std::is_same<TAB, void>::value;
+    const int sec = p.o.section;                       // 0 q2, 1 p2, 2 q3, 3 p3
+    const double dt = p.o.dt;
+
+    for (;;) {
+        const long long idx = hb_fetch_index(p.ws);
+        if (idx >= p.n) break;
+        const double *sd = p.seeds + idx * 4;
+        double so[6] = {0.0, sd[0], sd[2], 0.0, sd[1], sd[3]}, sn[6], rn[6], ro[6];
+        if (!TAO) cm_rhs<AR>(p, pw, terms, so, ro);     // stage 0 of the first step; later steps reuse rn
+        double elapsed = 0.0;
+        int flag = 0;
+        double o4[4] = {0.0, 0.0, 0.0, 0.0}, tc = 0.0;
+        for (int it = 0; it < p.o.max_steps; ++it) {
+            if constexpr (TAO) {
+                // q_ext = [Q, P, X = Q, Y = P] rebuilt every dt (backend.py:289-291, symplectic.py:636-640)
+                double Q[3] = {so[0], so[1], so[2]}, P[3] = {so[3], so[4], so[5]};
+                double X[3] = {so[0], so[1], so[2]}, Y[3] = {so[3], so[4], so[5]};
+                double g[6], pt[6];
+                for (int j = 0; j < p.o.n_sub; ++j) {
+                    const double ts = p.o.sub_ts[j], hd = AR::mul(0.5, ts);
+                    const double c = p.o.sub_cos[j], s = p.o.sub_sin[j];
+#pragma unroll 1
+                    for (int ph = 0; ph < 5; ++ph) {
+                        if (ph == 2) {                   // phi_omega_H_c (symplectic.py:486-506)
+#pragma unroll
+                            for (int i = 0; i < 3; ++i) {
+                                const double qpx = AR::add(Q[i], X[i]), qmx = AR::sub(Q[i], X[i]);
+                                const double ppy = AR::add(P[i], Y[i]), pmy = AR::sub(P[i], Y[i]);
+                                Q[i] = AR::mul(0.5, AR::add(AR::add(qpx, AR::mul(c, qmx)), AR::mul(s, pmy)));
+                                P[i] = AR::mul(0.5, AR::add(AR::sub(ppy, AR::mul(s, qmx)), AR::mul(c, pmy)));
+                                X[i] = AR::mul(0.5, AR::sub(AR::sub(qpx, AR::mul(c, qmx)), AR::mul(s, pmy)));
+                                Y[i] = AR::mul(0.5, AR::sub(AR::add(ppy, AR::mul(s, qmx)), AR::mul(c, pmy)));
+                            }
+                        } else if (ph == 0 || ph == 4) { // phi_H_a: gradient at (Q, Y); P -= d*dHdQ, X += d*dHdP
+#pragma unroll
+                            for (int i = 0; i < 3; ++i) { pt[i] = Q[i]; pt[3 + i] = Y[i]; }
+                            cm_grad<AR>(p, pw, terms, pt, g);
+#pragma unroll
+                            for (int i = 0; i < 3; ++i) {
+                                P[i] = AR::sub(P[i], AR::mul(hd, g[i]));
+                                X[i] = AR::add(X[i], AR::mul(hd, g[3 + i]));
+                            }
+                        } else {                         // phi_H_b: gradient at (X, P); Q += d*dHdP, Y -= d*dHdQ
+#pragma unroll
+                            for (int i = 0; i < 3; ++i) { pt[i] = X[i]; pt[3 + i] = P[i]; }
+                            cm_grad<AR>(p, pw, terms, pt, g);
+#pragma unroll
+                            for (int i = 0; i < 3; ++i) {
+                                Q[i] = AR::add(Q[i], AR::mul(hd, g[3 + i]));
+                                Y[i] = AR::sub(Y[i], AR::mul(hd, g[i]));
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 3; ++i) { sn[i] = Q[i]; sn[3 + i] = P[i]; }
+            } else {
+                double k[TAB::S][6];
+#pragma unroll
+                for (int d = 0; d < 6; ++d) k[0][d] = ro[d];
+                g_run_stages<AR, TAB, 1>(p, pw, terms, so, k, dt);
+#pragma unroll
+                for (int d = 0; d < 6; ++d) sn[d] = so[d];
+                g_high_acc<AR, TAB, 0>(sn, k, dt);
+            }
+            cm_rhs<AR>(p, pw, terms, sn, rn);
+            // _detect_crossing (backend.py:58-89)
+            const double f_old = (sec == 0) ? so[1] : (sec == 1) ? so[4] : (sec == 2) ? so[2] : so[5];
+            const double f_new = (sec == 0) ? sn[1] : (sec == 1) ? sn[4] : (sec == 2) ? sn[2] : sn[5];
+            bool crossed = false;
+            if (!(AR::mul(f_old, f_new) >= 0.0)) {
+                crossed = (sec == 2) ? (sn[5] > 0.0) : (sec == 0) ? (sn[4] > 0.0) : (sec == 3) ? (rn[2] > 0.0) : (rn[1] > 0.0);
+            }
+            if (crossed) {
+                const double alpha = AR::div(f_old, AR::sub(f_old, f_new));
+                if (TAO) cm_rhs<AR>(p, pw, terms, so, ro);
+                o4[0] = hermite_scalar<AR>(alpha, so[1], sn[1], ro[1], rn[1], dt);
+                o4[1] = hermite_scalar<AR>(alpha, so[4], sn[4], ro[4], rn[4], dt);
+                o4[2] = hermite_scalar<AR>(alpha, so[2], sn[2], ro[2], rn[2], dt);
+                o4[3] = hermite_scalar<AR>(alpha, so[5], sn[5], ro[5], rn[5], dt);
+                tc = AR::add(elapsed, AR::mul(alpha, dt));
+                flag = 1;
+                break;
+            }
+#pragma unroll
+            for (int d = 0; d < 6; ++d) { so[d] = sn[d]; ro[d] = rn[d]; }
+            elapsed = AR::add(elapsed, dt);
+        }
+        p.flags[idx] = flag;
+        p.t_out[idx] = tc;
+        double *o = p.out + idx * 4;
+        o[0] = o4[0]; o[1] = o4[1]; o[2] = o4[2]; o[3] = o4[3];
+    }
+}
+
+template <class AR, class TAB>
+int launch_cm(const CmParams &p, size_t smem, cudaStream_t st)
+{
+    auto kern = k_cm_map<AR, TAB>;
+    HB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int dev = 0, sms = 148, per_sm = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    HB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CM_BLOCK, smem));
+    if (per_sm < 1) per_sm = 1;
+    long long blocks = (p.n + CM_BLOCK - 1) / CM_BLOCK;
+    const long long cap = (long long)sms * per_sm;       // persistent: resident CTAs, seeds pulled from the queue
+    if (blocks > cap) blocks = cap;
+    kern<<<(unsigned)blocks, CM_BLOCK, smem, st>>>(p);
+    HB_CUDA_TRY(cudaGetLastError());
+    return HB_OK;
+}
+
+template <class AR>
+int dispatch(const CmParams &p, size_t smem, cudaStream_t st)
+{
+    if (p.o.method == HB_SYMPLECTIC) return launch_cm<AR, void>(p, smem, st);
+    if (p.o.method == HB_RK4) return launch_cm<AR, TabRK4>(p, smem, st);
+    if (p.o.method == HB_RK6) return launch_cm<AR, TabRK6>(p, smem, st);
+    if (p.o.method == HB_RK8) return launch_cm<AR, TabRK8>(p, smem, st);
+    return HB_ERR_UNSUPPORTED;
+}
+
+// _recursive_update_poly's schedule flattened (symplectic.py:543-560): order-2 kernels with their time steps
+void tao_schedule(double ts, int order, hb_cm_opts *o)
+{
+    if (order == 2) {
+        if (o->n_sub < HB_MAX_TAO_SUBSTEPS) o->sub_ts[o->n_sub] = ts;
+        o->n_sub++;
+    } else {
+        const double gamma = 1.0 / (2.0 - std::pow(2.0, 1.0 / ((double)order + 1.0)));
+        tao_schedule(gamma * ts, order - 2, o);
+        tao_schedule((1.0 - 2.0 * gamma) * ts, order - 2, o);
+        tao_schedule(gamma * ts, order - 2, o);
+    }
+}
+
+}  // namespace
+
+extern "C" int hb_cm_prepare(hb_cm_opts *o, double c_omega)
+{
+    if (!o) return HB_ERR_BADARG;
+    o->n_sub = 0;
+    if (o->method != HB_SYMPLECTIC) return (o->method == HB_RK4 || o->method == HB_RK6 || o->method == HB_RK8) ? HB_OK : HB_ERR_UNSUPPORTED;
+    if (o->order < 2 || (o->order % 2) != 0 || o->order > 8) return HB_ERR_UNSUPPORTED;
+    const double step = o->dt - 0.0;                                   // np.diff([0, dt])
+    const double omega = std::pow(c_omega * step, -(double)o->order);  // _get_tao_omega (symplectic.py:38-60)
+    tao_schedule(step, o->order, o);
+    if (o->n_sub > HB_MAX_TAO_SUBSTEPS) return HB_ERR_UNSUPPORTED;
+    for (int j = 0; j < o->n_sub; ++j) {
+        o->sub_cos[j] = std::cos(2 * omega * o->sub_ts[j]);
+        o->sub_sin[j] = std::sin(2 * omega * o->sub_ts[j]);
+    }
+    return HB_OK;
+}
+
+extern "C" int hb_cm_poincare_map(const hb_polyham *ham, const hb_cm_opts *opts, int64_t n, const double *seeds,
+                                  int32_t *flags, double *out, double *t_out, void *workspace, void *stream)
+{
+    if (!ham || !opts || !workspace || n < 0) return HB_ERR_BADARG;
+    if (ham->n_dof != 3 || ham->max_deg < 0 || ham->max_deg > 30) return HB_ERR_UNSUPPORTED;
+    if (opts->section < 0 || opts->section > 3 || opts->max_steps < 0) return HB_ERR_BADARG;
+    if (opts->arith != HB_ARITH_PARITY && opts->arith != HB_ARITH_FAST) return HB_ERR_BADARG;
+    if (opts->method == HB_SYMPLECTIC && opts->n_sub <= 0) return HB_ERR_BADARG;   // hb_cm_prepare not called
+    if (n > 0 && (!seeds || !flags || !out || !t_out || !ham->terms)) return HB_ERR_BADARG;
+    if (n == 0) return HB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    HB_CUDA_TRY(cudaMemsetAsync(workspace, 0, sizeof(HbWorkspace), st));
+    CmParams p{};
+    p.o = *opts; p.n = n; p.seeds = seeds; p.flags = flags; p.out = out; p.t_out = t_out;
+    p.ws = (HbWorkspace *)workspace;
+    p.terms = (const TermMeta *)ham->terms;
+    for (int i = 0; i < 7; ++i) p.ptr[i] = (int)ham->ptr[i];
+    p.n_terms = (int)ham->ptr[6];
+    p.D = ham->max_deg;
+    const size_t smem = (((size_t)p.n_terms * sizeof(TermMeta) + 15) & ~(size_t)15) +
+                        (size_t)6 * (p.D + 1) * CM_BLOCK * sizeof(double);
+    if (smem > 227 * 1024) return HB_ERR_UNSUPPORTED;
+    return (opts->arith == HB_ARITH_PARITY) ? dispatch<ArParity>(p, smem, st) : dispatch<ArFast>(p, smem, st);
+}

@@ -51,6 +51,8 @@ extern "C" {
 #define HB_RK45 45
 #define HB_DOP853 853
 
+#define HB_SYMPLECTIC 2   /* Tao extended-phase-space integrator (_ExtendedSymplectic), order in hb_cm_opts */
+
 #define HB_ARITH_PARITY 0
 #define HB_ARITH_FAST 1
 
@@ -160,6 +162,42 @@ int hb_cr3bp_stm(const hb_cr3bp *sys, const hb_integ *integ, int64_t n, const do
 int hb_cr3bp_stm_dense(const hb_cr3bp *sys, const hb_integ *integ, int64_t n, const double *x0_soa,
                        const double *t_eval, int32_t m, int32_t t_eval_per_traj, double *phi_dense,
                        int32_t *n_acc, int32_t *n_rej, int32_t *status, void *workspace, void *stream);
+
+/* ---- centre-manifold Poincare map (polynomial Hamiltonian) ---------------------------------------
+ * Sparse real term table of the six partials dH/d(q1,q2,q3,p1,p2,p3): the reference's jac_H
+ * (lists of packed complex128 coefficient arrays + clmo exponent tables, algorithms/polynomial/base.py:
+ * 99-259) reduced to its non-zero terms in evaluation order.  `terms` is a DEVICE array of 16-byte
+ * records {double coef; uint64 ex} with the exponents of (q1,q2,q3,p1,p2,p3) in bytes 0..5 of `ex` and
+ * the homogeneous degree in bits 48..63 (summation is grouped by degree like _polynomial_evaluate). */
+typedef struct {
+    int32_t n_dof;      /* 3 */
+    int32_t max_deg;    /* largest exponent in the table */
+    int64_t ptr[7];     /* terms of partial p are [ptr[p], ptr[p+1]) */
+    const void *terms;
+} hb_polyham;
+
+#define HB_MAX_TAO_SUBSTEPS 27
+/* Options of _poincare_map (algorithms/poincare/centermanifold/backend.py:314-382). */
+typedef struct {
+    double dt;
+    int32_t max_steps;
+    int32_t method;   /* HB_RK4 / HB_RK6 / HB_RK8 ("fixed") or HB_SYMPLECTIC                       */
+    int32_t order;    /* symplectic order 2, 4, 6, 8                                                */
+    int32_t section;  /* section coordinate: 0 q2, 1 p2, 2 q3, 3 p3                                 */
+    int32_t arith;    /* HB_ARITH_*                                                                 */
+    int32_t n_sub;    /* filled by hb_cm_prepare: order-2 Tao kernels per dt and their parameters   */
+    double sub_ts[HB_MAX_TAO_SUBSTEPS], sub_cos[HB_MAX_TAO_SUBSTEPS], sub_sin[HB_MAX_TAO_SUBSTEPS];
+} hb_cm_opts;
+
+/* Host-only: flattens the triple-jump recursion (algorithms/integrators/symplectic.py:509-560) into
+ * sub_ts[] and evaluates omega = (c_omega*dt)^-order and cos/sin(2*omega*ts) with the host libm, exactly
+ * as the reference does per step.  Needs no GPU.                                                  */
+int hb_cm_prepare(hb_cm_opts *opts, double c_omega);
+
+/* _poincare_map / _poincare_step / _detect_crossing: seeds[n][4] = (q2,p2,q3,p3) -> flags[n] (1 = section
+ * crossing found within max_steps), out[n][4] the Hermite-interpolated crossing state, t_out[n].     */
+int hb_cm_poincare_map(const hb_polyham *ham, const hb_cm_opts *opts, int64_t n, const double *seeds,
+                       int32_t *flags, double *out, double *t_out, void *workspace, void *stream);
 
 /* Synodic-section crossing detection on precomputed trajectories (linear branch, the one the
  * reference's defaults select): replaces _SynodicDetectionBackend.run / detect_on_trajectory /

@@ -1,11 +1,32 @@
-/* ho_poly.h -- polynomial Hamiltonian vector field of the oracle (TEST INFRASTRUCTURE). */
+/* ho_poly.h -- polynomial Hamiltonian vector field + centre-manifold Poincare map of the oracle
+ * (TEST INFRASTRUCTURE, see hiten_oracle.h). */
 #ifndef HO_POLY_H
 #define HO_POLY_H
 #include "hiten_oracle.h"
 #ifdef __cplusplus
 extern "C" {
 #endif
-void ho_polyham_rhs(const ho_polyham *ham, const double *y, double *dy);
+
+/* Sparse real term table of the six partials dH/d(q1,q2,q3,p1,p2,p3) (the reference's jac_H), terms in
+ * the reference's evaluation order: degree ascending, packed index ascending, zero coefficients skipped
+ * (algorithms/polynomial/operations.py:551-583, algebra.py:403-461). */
+struct ho_polyham {
+    int n_dof;             /* 3 */
+    int max_deg;           /* largest exponent that occurs */
+    int64_t ptr[7];        /* CSR: terms of partial p are [ptr[p], ptr[p+1]) */
+    const int32_t *deg;    /* [T] homogeneous degree of the term (summation is grouped by degree) */
+    const double *coef;    /* [T] */
+    const int32_t *exp;    /* [T][6] exponents of (q1,q2,q3,p1,p2,p3) */
+};
+
+double ho_poly_eval_partial(const ho_polyham *ham, int p, const double *point6);
+void ho_polyham_rhs(const ho_polyham *ham, const double *y, double *dy);   /* dynamics/hamiltonian.py:35-90 */
+
+/* _poincare_map (algorithms/poincare/centermanifold/backend.py:314-382): seeds[n][4] = (q2,p2,q3,p3);
+ * section: 0 q2, 1 p2, 2 q3, 3 p3; out[n][4], t_out[n], flags[n] (int64). */
+int ho_cm_poincare_map(const ho_polyham *ham, const double *seeds, int64_t n, double dt, int order, int max_steps,
+                       int use_symplectic, int section, double c_omega, int64_t *flags, double *out, double *t_out,
+                       int n_threads);
 #ifdef __cplusplus
 }
 #endif

@@ -167,3 +167,45 @@ def synodic_detect(times, states, idx, offset=0.0, direction=0, proj=(0, 2), seg
                                 C.c_double(dedup_time_tol), C.c_double(dedup_point_tol), int(max_hits), _p(ht),
                                 _p(hs), cap)
     return ht[:k].copy(), hs[:k].copy()
+
+
+class HoPolyHam(C.Structure):
+    _fields_ = [("n_dof", C.c_int), ("max_deg", C.c_int), ("ptr", C.c_int64 * 7), ("deg", C.c_void_p),
+                ("coef", C.c_void_p), ("exp", C.c_void_p)]
+
+
+class PolyHam:
+    """Oracle-side polynomial Hamiltonian table (keeps the numpy arrays alive)."""
+
+    def __init__(self, ptr, deg, coef, exp):
+        self.ptr = np.ascontiguousarray(ptr, dtype=np.int64)
+        self.deg = np.ascontiguousarray(deg, dtype=np.int32)
+        self.coef = np.ascontiguousarray(coef, dtype=np.float64)
+        self.exp = np.ascontiguousarray(exp, dtype=np.int32).reshape(-1, 6)
+        self.dim = 6
+        self.struct = HoPolyHam(3, int(self.exp.max()) if self.exp.size else 0, (C.c_int64 * 7)(*self.ptr.tolist()),
+                                self.deg.ctypes.data, self.coef.ctypes.data, self.exp.ctypes.data)
+        self.handle = C.addressof(self.struct)
+
+
+SECTION = {"q2": 0, "p2": 1, "q3": 2, "p3": 3}
+
+
+def polyham_rhs(ham, y):
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    out = np.empty(6)
+    lib().ho_polyham_rhs(C.byref(ham.struct), _p(y), _p(out))
+    return out
+
+
+def cm_poincare_map(ham, seeds, dt, order, max_steps, use_symplectic, section, c_omega=20.0, n_threads=1):
+    seeds = np.ascontiguousarray(seeds, dtype=np.float64)
+    n = seeds.shape[0]
+    flags = np.zeros(n, dtype=np.int64)
+    out = np.zeros((n, 4))
+    tt = np.zeros(n)
+    rc = lib().ho_cm_poincare_map(C.byref(ham.struct), _p(seeds), C.c_int64(n), C.c_double(dt), int(order),
+                                  int(max_steps), int(bool(use_symplectic)), SECTION[section], C.c_double(c_omega),
+                                  flags.ctypes.data_as(ip), _p(out), _p(tt), int(n_threads))
+    assert rc == 0
+    return flags, out, tt

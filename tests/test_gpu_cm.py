@@ -1,0 +1,65 @@
+"""GPU parity: centre-manifold Poincare map kernel vs the reference's _poincare_map (BASELINE config 3)."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from test_oracle_cm import CASES
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _table(g):
+    from hiten_b200.centermanifold import PolyTable
+    return PolyTable(g["jac_ptr"], g["jac_deg"], g["jac_coef"], g["jac_exp"])
+
+
+@pytest.mark.parametrize("name,order,symp,sec", CASES)
+def test_map_vs_reference(name, order, symp, sec):
+    from hiten_b200 import centermanifold as cmod
+    g = np.load(os.path.join(HERE, "golden", "cm_map.npz"))
+    ref = g[name]
+    seeds = g["seeds_" + sec][: len(ref)]
+    opts = cmod.make_opts(float(g["dt"]), int(g["max_steps"]), "symplectic" if symp else "fixed", order, sec,
+                          float(g["c_omega"]))
+    f, o, t = cmod.poincare_map(_table(g), seeds, opts)
+    assert np.array_equal(f, ref[:, 0].astype(np.int64))              # identical crossing flags
+    d = np.abs(o - ref[:, 1:5]).max()
+    print(f"[parity] CM {name}: {len(ref)} seeds, |d state| max {d:.2e}, |d t| max {np.abs(t - ref[:, 5]).max():.2e}, "
+          f"bit-exact {np.array_equal(o, ref[:, 1:5])}")
+    assert d <= 1e-12 and np.abs(t - ref[:, 5]).max() <= 1e-12
+
+
+def test_fast_variant_and_failures():
+    from hiten_b200 import centermanifold as cmod
+    g = np.load(os.path.join(HERE, "golden", "cm_map.npz"))
+    tab = _table(g)
+    ref = g["rk4_p3_maxsteps200"]
+    f, o, t = cmod.poincare_map(tab, g["seeds_p3"][:64], cmod.make_opts(0.01, 200, "fixed", 4, "p3"))
+    assert np.array_equal(f, ref[:, 0].astype(np.int64)) and (o[f == 0] == 0).all()
+    ref = g["tao4_p3"]
+    f, o, t = cmod.poincare_map(tab, g["seeds_p3"][:256], cmod.make_opts(0.01, 2000, "symplectic", 4, "p3", arith="fast"))
+    assert np.array_equal(f, ref[:, 0].astype(np.int64))
+    assert np.abs(o - ref[:, 1:5]).max() <= 1e-9
+    with pytest.raises(NotImplementedError):
+        cmod.make_opts(method="adaptive")
+    e = cmod.poincare_map(tab, np.empty((0, 4)), cmod.make_opts())
+    assert e[0].size == 0 and e[1].shape == (0, 4)
+
+
+def test_large_batch_returns_on_section():
+    """1e5 seeds (BASELINE size): every returned point lies on the section and conserves energy."""
+    from hiten_b200 import centermanifold as cmod
+    g = np.load(os.path.join(HERE, "golden", "cm_map.npz"))
+    tab = _table(g)
+    rng = np.random.default_rng(1)
+    base = g["seeds_p3"]
+    seeds = base[rng.integers(0, len(base), 100_000)]
+    f, o, t = cmod.poincare_map(tab, seeds, cmod.make_opts(0.01, 2000, "symplectic", 4, "p3"))
+    assert f.all()
+    assert np.abs(o[:, 3]).max() < 1e-6                    # p3 ~ 0 on the section (Hermite interpolant)
+    # identical seeds -> identical results regardless of lane / queue order
+    idx = np.where((seeds == base[0]).all(axis=1))[0]
+    assert len(idx) > 1 and (o[idx] == o[idx[0]]).all()
