@@ -59,7 +59,9 @@ def test_large_batch_returns_on_section():
     seeds = base[rng.integers(0, len(base), 100_000)]
     f, o, t = cmod.poincare_map(tab, seeds, cmod.make_opts(0.01, 2000, "symplectic", 4, "p3"))
     assert f.all()
-    assert np.abs(o[:, 3]).max() < 1e-6                    # p3 ~ 0 on the section (Hermite interpolant)
+    # p3 ~ 0 on the section: the reference's hit is a Hermite interpolant at the LINEAR alpha, so it is only
+    # near the section (the golden hits reach |p3| = 1.2e-5 as well)
+    assert np.abs(o[:, 3]).max() < 1e-4
     # identical seeds -> identical results regardless of lane / queue order
     idx = np.where((seeds == base[0]).all(axis=1))[0]
     assert len(idx) > 1 and (o[idx] == o[idx[0]]).all()
