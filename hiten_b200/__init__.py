@@ -5,8 +5,9 @@ No CPU fallback: compute entry points raise without the built library and a CUDA
 """
 from . import _lib
 from ._lib import HitenB200Error
+from .dropin import install, uninstall
 from .propagate import (BatchResult, cr3bp_dense, cr3bp_event, cr3bp_propagate, cr3bp_stm, cr3bp_stm_dense,
                         dfma_peak, make_integ)
 
-__all__ = ["BatchResult", "HitenB200Error", "cr3bp_dense", "cr3bp_event", "cr3bp_propagate", "cr3bp_stm", "cr3bp_stm_dense", "dfma_peak",
+__all__ = ["install", "uninstall", "BatchResult", "HitenB200Error", "cr3bp_dense", "cr3bp_event", "cr3bp_propagate", "cr3bp_stm", "cr3bp_stm_dense", "dfma_peak",
            "make_integ", "_lib"]

@@ -1,0 +1,423 @@
+"""Drop-in installer: rebinds HITEN's propagation funnels to the GPU path.
+
+    import hiten, hiten_b200
+    hiten_b200.install()          # orbit.manifold().compute(), SynodicMap.compute(), cm.poincare_map().compute(),
+                                  # _propagate_dynsys / _compute_stm / the DOP853 integrator class now run on the GPU
+    hiten_b200.uninstall()
+
+No reference file is edited.  What is rebound (paths relative to hiten/):
+  * `_propagate_dynsys`  (algorithms/dynamics/base.py:346) in every module that imported it by value
+    -> CR3BP 6-state and 42-state systems with method="adaptive", order=8 go to the DOP853 kernels
+       (dense grid, or a recognised plane event); `_compute_stm` (algorithms/dynamics/rtbp.py:258) follows
+       because it calls the rebound name;
+  * `_ManifoldDynamicsService._run_compute` (algorithms/types/services/manifold.py:293): the serial fraction loop
+    becomes ONE batched dense propagation;
+  * `_SynodicDetectionBackend.run` (algorithms/poincare/synodic/backend.py:823);
+  * `_CenterManifoldBackend.run` (algorithms/poincare/centermanifold/backend.py:404);
+  * `_DOP853.integrate` (algorithms/integrators/rk.py:2221).
+Anything the GPU path cannot express (user-defined RHS or event callables, RK45 / fixed-step / symplectic generic
+integration, cubic synodic refinement) is handed to the reference's ORIGINAL function -- that is the reference's
+own code for inputs outside this path, not a fallback of the kernels: for recognised inputs a missing library
+or GPU raises.
+"""
+import sys
+
+import numpy as np
+
+from . import centermanifold as _cm
+from . import propagate as _prop
+from . import synodic as _syn
+
+_STATE = {"installed": False, "orig": {}, "patched_modules": [], "arith": "parity"}
+
+
+# ------------------------------------------------------------------------------------------------
+# recognition helpers
+# ------------------------------------------------------------------------------------------------
+def _norm_flip(flip, dim):
+    """flip_indices of _DirectedSystem -> (lo, hi) or None (= all); raises LookupError if not a contiguous range."""
+    if flip is None:
+        return None
+    if isinstance(flip, slice):
+        lo, hi, st = flip.indices(dim)
+        if st != 1:
+            raise LookupError("strided flip")
+        return (lo, hi)
+    idx = np.asarray(flip, dtype=np.int64).ravel()
+    if idx.size == 0:
+        raise LookupError("empty flip")
+    srt = np.sort(idx)
+    if not np.array_equal(srt, np.arange(srt[0], srt[0] + idx.size)):
+        raise LookupError("non-contiguous flip")
+    return (int(srt[0]), int(srt[0]) + idx.size)
+
+
+def recognise_system(dynsys):
+    """-> (dim, mu, fwd, flip) for the CR3BP 6- or 42-state systems (possibly wrapped by _DirectedSystem), else None."""
+    from hiten.algorithms.dynamics.base import _DirectedSystem
+    from hiten.algorithms.dynamics.rtbp import _RTBPRHS, _VarEqRHS
+    fwd, flip, base = 1, None, dynsys
+    if isinstance(dynsys, _DirectedSystem):
+        base = dynsys._base
+        fwd = int(dynsys._fwd)
+        try:
+            flip = _norm_flip(dynsys._flip_idx, dynsys.dim)
+        except LookupError:
+            return None
+        if isinstance(base, _DirectedSystem):
+            return None
+    if type(base) is _RTBPRHS:
+        return 6, float(base.mu), fwd, flip
+    if type(base) is _VarEqRHS:
+        return 42, float(base.mu), fwd, flip
+    return None
+
+
+def recognise_event(event_fn):
+    """-> (idx, offset) for g(t,y) = y[idx] - offset plane events (singlehit/backend.py:30-67), else None."""
+    from hiten.algorithms.poincare.singlehit import backend as sh
+    for i, fn in enumerate((sh._g_x0, sh._g_y0, sh._g_z0)):
+        if event_fn is fn:
+            return i, 0.0
+    for (idx, off), fn in list(sh._PLANE_EVENT_FN_CACHE.items()):
+        if event_fn is fn:
+            return int(idx), float(off)
+    return None
+
+
+def _integ(kwargs=None, rtol=None, atol=None, max_step=None):
+    kwargs = kwargs or {}
+    return _prop.make_integ(arith=_STATE["arith"],
+                            rtol=kwargs.get("rtol", 1e-12) if rtol is None else rtol,
+                            atol=kwargs.get("atol", 1e-12) if atol is None else atol,
+                            max_step=kwargs.get("max_step", 1e4) if max_step is None else max_step)
+
+
+def _rhs6_numpy(states, mu, fwd, flip):
+    """Vectorised _crtbp_accel (+ direction wrapper) for the `derivatives` field of _Solution."""
+    x, y, z, vx, vy, vz = states.T
+    r1 = np.sqrt((x + mu) ** 2 + y ** 2 + z ** 2)
+    r2 = np.sqrt((x - (1 - mu)) ** 2 + y ** 2 + z ** 2)
+    ax = 2 * vy + x - (1 - mu) * (x + mu) / r1 ** 3 - mu * (x - 1 + mu) / r2 ** 3
+    ay = -2 * vx + y - (1 - mu) * y / r1 ** 3 - mu * y / r2 ** 3
+    az = -(1 - mu) * z / r1 ** 3 - mu * z / r2 ** 3
+    out = np.column_stack([vx, vy, vz, ax, ay, az])
+    if fwd == -1:
+        lo, hi = (0, 6) if flip is None else flip
+        out[:, lo:hi] *= -1
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# shared GPU integration of ONE trajectory on a grid / to an event (used by the two integrate funnels)
+# ------------------------------------------------------------------------------------------------
+def _gpu_integrate(dim, mu, fwd, flip, y0, t_vals, integ, event=None):
+    """Returns (times, states) like _DOP853.integrate: the dense grid, or the 2-row event solution."""
+    y0 = np.ascontiguousarray(y0, dtype=np.float64)
+    t_vals = np.ascontiguousarray(t_vals, dtype=np.float64)
+    if event is not None:
+        idx, off, direction, xtol, gtol = event
+        if dim != 6:
+            raise LookupError("event propagation is a 6-state path")
+        res = _prop.cr3bp_event(y0[None, :], mu, float(t_vals[-1]), idx, event_offset=off, direction=direction,
+                                xtol=xtol, gtol=gtol, t0=float(t_vals[0]), forward=fwd, flip=flip, integ=integ)
+        _raise_on_status(res.status)
+        if int(res.status[0]) == 1:
+            return np.array([t_vals[0], res.t_hit[0]]), np.vstack([y0, res.yf[0]])
+        return np.array([t_vals[0], t_vals[-1]]), np.vstack([y0, res.yf[0]])
+    if dim == 6:
+        res = _prop.cr3bp_dense(y0[None, :], mu, t_vals, forward=fwd, flip=flip, integ=integ)
+        _raise_on_status(res.status)
+        return t_vals.copy(), res.states[0]
+    if y0.shape != (42,) or not np.array_equal(y0[:36], np.eye(6).ravel()):
+        raise LookupError("42-state kernel starts from PHI0 = [I, x0]")
+    res = _prop.cr3bp_stm_dense(y0[None, 36:], mu, t_vals, forward=fwd, flip=(0, 42) if flip is None else flip,
+                                integ=integ)
+    _raise_on_status(res.status)
+    return t_vals.copy(), res.states[0]
+
+
+def _raise_on_status(status):
+    bad = np.nonzero(np.asarray(status) > 1)[0]
+    if bad.size:
+        from hiten.algorithms.types.exceptions import ConvergenceError
+        raise ConvergenceError(f"GPU propagation failed for trajectory {int(bad[0])} (status {int(status[bad[0]])})")
+
+
+# ------------------------------------------------------------------------------------------------
+# replacements
+# ------------------------------------------------------------------------------------------------
+def _make_propagate_dynsys(orig):
+    def _propagate_dynsys(dynsys, state0, t0, tf, forward=1, steps=1000, method="adaptive", order=8,
+                          flip_indices=None, **kwargs):
+        from hiten.algorithms.dynamics.base import _validate_initial_state
+        from hiten.algorithms.integrators.types import _Solution
+        rec = recognise_system(dynsys)
+        known = {"rtol", "atol", "max_step", "event_fn", "event_cfg", "event_options"}
+        if rec is None or rec[2] != 1 or method != "adaptive" or order != 8 or (set(kwargs) - known):
+            return orig(dynsys, state0, t0, tf, forward=forward, steps=steps, method=method, order=order,
+                        flip_indices=flip_indices, **kwargs)
+        dim, mu, _, _ = rec
+        try:
+            flip = _norm_flip(flip_indices, dim)
+        except LookupError:
+            return orig(dynsys, state0, t0, tf, forward=forward, steps=steps, method=method, order=order,
+                        flip_indices=flip_indices, **kwargs)
+        fwd = 1 if forward >= 0 else -1
+        event = None
+        event_fn = kwargs.get("event_fn")
+        if event_fn is not None:
+            ev = recognise_event(event_fn)
+            if ev is None or dim != 6:
+                return orig(dynsys, state0, t0, tf, forward=forward, steps=steps, method=method, order=order,
+                            flip_indices=flip_indices, **kwargs)
+            cfg, opt = kwargs.get("event_cfg"), kwargs.get("event_options")
+            event = (ev[0], ev[1], 0 if cfg is None else int(cfg.direction),
+                     1e-12 if opt is None else float(opt.xtol), 1e-12 if opt is None else float(opt.gtol))
+        state0_np = _validate_initial_state(state0, dynsys.dim)
+        t_eval = np.linspace(t0, tf, steps)
+        if steps >= 2 and np.isclose(t_eval[0], t_eval[-1]):          # base.py:421-424
+            return _Solution(forward * t_eval, np.repeat(state0_np[None, :], repeats=len(t_eval), axis=0))
+        try:
+            times, states = _gpu_integrate(dim, mu, fwd, flip, state0_np, t_eval, _integ(kwargs), event)
+        except LookupError:
+            return orig(dynsys, state0, t0, tf, forward=forward, steps=steps, method=method, order=order,
+                        flip_indices=flip_indices, **kwargs)
+        return _Solution(forward * times, states)
+
+    _propagate_dynsys.__wrapped__ = orig
+    _propagate_dynsys.__doc__ = orig.__doc__
+    return _propagate_dynsys
+
+
+def _make_dop853_integrate(orig):
+    def integrate(self, system, y0, t_vals, *, event_fn=None, event_cfg=None, event_options=None, **kwargs):
+        from hiten.algorithms.integrators.types import _Solution
+        rec = recognise_system(system)
+        ev = None
+        if event_fn is not None:
+            ev = recognise_event(event_fn)
+        if rec is None or (event_fn is not None and (ev is None or rec[0] != 6)):
+            return orig(self, system, y0, t_vals, event_fn=event_fn, event_cfg=event_cfg,
+                        event_options=event_options, **kwargs)
+        self.validate_inputs(system, y0, t_vals)
+        const = self._maybe_constant_solution(system, y0, t_vals)
+        if const is not None:
+            return const
+        t_vals = np.asarray(t_vals, dtype=np.float64)
+        if not np.all(np.diff(t_vals) > 0):
+            return orig(self, system, y0, t_vals, event_fn=event_fn, event_cfg=event_cfg,
+                        event_options=event_options, **kwargs)
+        dim, mu, fwd, flip = rec
+        integ = _prop.make_integ(arith=_STATE["arith"], rtol=self._rtol, atol=self._atol,
+                                 max_step=min(float(self._max_step), 1e300), min_step=self._min_step)
+        event = None
+        if ev is not None:
+            event = (ev[0], ev[1], 0 if event_cfg is None else int(event_cfg.direction),
+                     float(event_options.xtol if event_options is not None else 1.0e-12),
+                     float(event_options.gtol if event_options is not None else 1.0e-12))
+        try:
+            times, states = _gpu_integrate(dim, mu, fwd, flip, np.asarray(y0, dtype=np.float64), t_vals, integ, event)
+        except LookupError:
+            return orig(self, system, y0, t_vals, event_fn=event_fn, event_cfg=event_cfg,
+                        event_options=event_options, **kwargs)
+        if event is not None:
+            return _Solution(times=times, states=states)
+        derivs = _rhs6_numpy(states, mu, fwd, flip) if dim == 6 else None
+        return _Solution(times=times, states=states, derivatives=derivs)
+
+    integrate.__wrapped__ = orig
+    integrate.__doc__ = orig.__doc__
+    return integrate
+
+
+def _make_run_compute(orig):
+    def _run_compute(self, *, step, integration_fraction, NN, displacement, method, order, dt, energy_tol,
+                     safe_distance, show_progress):
+        if method != "adaptive" or order != 8:
+            return orig(self, step=step, integration_fraction=integration_fraction, NN=NN,
+                        displacement=displacement, method=method, order=order, dt=dt, energy_tol=energy_tol,
+                        safe_distance=safe_distance, show_progress=show_progress)
+        from hiten.algorithms.common.energy import _max_rel_energy_error
+        orbit = self.orbit
+        mu, forward = self.mu, self.forward
+        dist_m = self.system.distance * 1e3                                 # manifold.py:341-345 (kept as is)
+        safe_r1 = safe_distance * (self.system.primary.radius / dist_m)
+        safe_r2 = safe_distance * (self.system.secondary.radius / dist_m)
+        sn, un, _ = self.eigenvalues
+        Ws, Wu, _ = self.eigenvectors
+        _, snreal_vecs = self.stability.get_real_eigenvectors(Ws, sn)
+        _, unreal_vecs = self.stability.get_real_eigenvectors(Wu, un)
+        col_idx = NN - 1
+        vecs, label = (snreal_vecs, "stable") if self.stable == 1 else (unreal_vecs, "unstable")
+        if vecs.shape[1] <= col_idx or col_idx < 0:
+            raise ValueError(f"Requested {label} eigenvector {NN} not available. "
+                             f"Only {vecs.shape[1]} real {label} eigenvectors found.")
+        eigvec = vecs[:, col_idx]
+        fractions = tuple(np.arange(0.0, 1.0, step))
+        xx, tt, _, PHI = self.compute_stm(steps=2000)
+        x0W = np.stack([self._compute_manifold_section(period=orbit.period, fraction=f, displacement=displacement,
+                                                       xx=xx, tt=tt, PHI=PHI, eigvec=eigvec).astype(np.float64)
+                        for f in fractions]) if fractions else np.empty((0, 6))
+        tf = integration_fraction * 2 * np.pi
+        steps = max(int(abs(tf) / dt) + 1, 100)
+        t_eval = np.linspace(0.0, tf, steps)
+        ysos, dysos, states_list, times_list = [], [], [], []
+        successes, attempts = 0, len(fractions)
+        if attempts == 0:
+            return (ysos, dysos, states_list, times_list, 0, 0)
+        # the batch axis: every fraction in ONE launch (replaces the loop at manifold.py:381-440)
+        res = _prop.cr3bp_dense(x0W, mu, t_eval, forward=forward, flip=(0, 6), integ=_integ())
+        times = forward * t_eval
+        for i in range(attempts):
+            if int(res.status[i]) != 0:
+                continue                                                    # "discard and continue", manifold.py:438-440
+            states = res.states[i]
+            x, y, z = states[:, 0], states[:, 1], states[:, 2]
+            r1 = np.sqrt((x + mu) ** 2 + y ** 2 + z ** 2)
+            r2 = np.sqrt((x - 1 + mu) ** 2 + y ** 2 + z ** 2)
+            if (r1.min() < safe_r1) or (r2.min() < safe_r2):
+                continue
+            if _max_rel_energy_error(states, mu) > energy_tol:
+                continue
+            states_list.append(states)
+            times_list.append(times.copy())
+            successes += 1
+        return (ysos, dysos, states_list, times_list, successes, attempts)
+
+    _run_compute.__wrapped__ = orig
+    return _run_compute
+
+
+def _make_synodic_run(orig):
+    def run(self, request):
+        from hiten.algorithms.poincare.core.types import _SectionHit
+        from hiten.algorithms.poincare.synodic.types import SynodicBackendResponse
+        normal = np.asarray(request.normal, dtype=float).ravel()
+        nz = np.nonzero(normal)[0]
+        trajs = list(request.trajectories)
+        one_hot = normal.size == 6 and nz.size == 1 and normal[nz[0]] == 1.0
+        linear = request.interp_kind != "cubic"        # the reference's own test (backend.py:762)
+        names_ok = all(isinstance(c, str) and c.lower() in _syn.IDX for c in request.plane_coords)
+        if not (one_hot and linear and names_ok) or any(np.asarray(s).shape[1] != 6 for _, s in trajs if len(s)):
+            return orig(self, request)
+        sec = _syn.make_section(int(nz[0]), float(request.offset), request.plane_coords, request.direction,
+                                int(request.segment_refine), request.tol_on_surface, request.dedup_time_tol,
+                                request.dedup_point_tol, request.max_hits_per_traj)
+        idxs = [int(i) for i in request.trajectory_indices]
+        n = min(len(idxs), len(trajs))
+        lens = [len(trajs[k][0]) for k in range(n)]
+        hits = [[] for _ in range(n)]
+        if n and sum(lens):
+            states = np.concatenate([np.asarray(trajs[k][1], dtype=np.float64).reshape(-1, 6) for k in range(n)])
+            times = np.concatenate([np.asarray(trajs[k][0], dtype=np.float64).ravel() for k in range(n)])
+            off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+            got = _syn.detect(states, times, sec, offsets=off)
+            for k, t, s, p in zip(got.trajectory_indices, got.times, got.states, got.points):
+                hits[int(k)].append(_SectionHit(time=float(t), state=s.copy(), point2d=p.copy(),
+                                                trajectory_index=idxs[int(k)]))
+        pts, sts, ts, tis = [], [], [], []
+        for th in hits:
+            for h in th:
+                pts.append(h.point2d); sts.append(h.state); ts.append(h.time); tis.append(h.trajectory_index)
+        return SynodicBackendResponse(
+            hits=hits,
+            points=np.asarray(pts, dtype=float) if pts else np.empty((0, 2)),
+            states=np.asarray(sts, dtype=float) if sts else np.empty((0, 6)),
+            times=np.asarray(ts, dtype=float) if ts else None,
+            trajectory_indices=np.asarray(tis, dtype=int) if tis else np.empty((0,), dtype=int),
+            metadata={},
+        )
+
+    run.__wrapped__ = orig
+    return run
+
+
+_TABLES = {}
+
+
+def _make_cm_run(orig):
+    def run(self, request):
+        from hiten.algorithms.poincare.centermanifold.types import CenterManifoldBackendResponse
+        seeds = np.asarray(request.seeds)
+        if seeds.size == 0:
+            return CenterManifoldBackendResponse(states=np.empty((0, 4)), times=np.empty((0,)),
+                                                 flags=np.empty((0,), dtype=np.int64), metadata={})
+        if request.method == "adaptive":
+            raise NotImplementedError("Adaptive integrator is not implemented in CM backend; use 'fixed' (RK) or 'symplectic'.")
+        key = (id(request.jac_H), id(request.clmo_table))
+        if key not in _TABLES:
+            if len(_TABLES) > 16:
+                _TABLES.clear()
+            _TABLES[key] = (_cm.PolyTable.from_reference(request.jac_H, request.clmo_table), request.jac_H)
+        table = _TABLES[key][0]
+        opts = _cm.make_opts(request.dt, request.max_steps, "symplectic" if request.method == "symplectic" else "fixed",
+                             request.order, request.section_coord, request.c_omega_heuristic, _STATE["arith"])
+        flags, out, tt = _cm.poincare_map(table, np.ascontiguousarray(seeds, dtype=np.float64), opts)
+        ok = flags.astype(bool)                                             # failed seeds are dropped, backend.py:455-459
+        return CenterManifoldBackendResponse(states=np.asarray(out[ok], dtype=np.float64).reshape(-1, 4),
+                                             times=np.asarray(tt[ok], dtype=np.float64),
+                                             flags=np.asarray(flags, dtype=np.int64), metadata={})
+
+    run.__wrapped__ = orig
+    return run
+
+
+# ------------------------------------------------------------------------------------------------
+# install / uninstall
+# ------------------------------------------------------------------------------------------------
+def install(arith="parity"):
+    """Rebind the reference's funnels.  Requires `hiten` to be importable; idempotent."""
+    if _STATE["installed"]:
+        _STATE["arith"] = arith
+        return
+    import hiten  # noqa: F401
+    import hiten.algorithms.dynamics.base as dbase
+    from hiten.algorithms.integrators.rk import _DOP853
+    from hiten.algorithms.poincare.centermanifold.backend import _CenterManifoldBackend
+    from hiten.algorithms.poincare.synodic.backend import _SynodicDetectionBackend
+    from hiten.algorithms.types.services.manifold import _ManifoldDynamicsService
+
+    _STATE["arith"] = arith
+    orig_prop = dbase._propagate_dynsys
+    new_prop = _make_propagate_dynsys(orig_prop)
+    patched = []
+    for name, mod in list(sys.modules.items()):
+        if name.startswith("hiten") and mod is not None and getattr(mod, "_propagate_dynsys", None) is orig_prop:
+            setattr(mod, "_propagate_dynsys", new_prop)
+            patched.append(mod)
+    _STATE["patched_modules"] = patched
+    _STATE["orig"] = {
+        "propagate": orig_prop,
+        "dop853": _DOP853.integrate,
+        "run_compute": _ManifoldDynamicsService._run_compute,
+        "synodic": _SynodicDetectionBackend.run,
+        "cm": _CenterManifoldBackend.run,
+    }
+    _DOP853.integrate = _make_dop853_integrate(_STATE["orig"]["dop853"])
+    _ManifoldDynamicsService._run_compute = _make_run_compute(_STATE["orig"]["run_compute"])
+    _SynodicDetectionBackend.run = _make_synodic_run(_STATE["orig"]["synodic"])
+    _CenterManifoldBackend.run = _make_cm_run(_STATE["orig"]["cm"])
+    _STATE["installed"] = True
+
+
+def uninstall():
+    if not _STATE["installed"]:
+        return
+    from hiten.algorithms.integrators.rk import _DOP853
+    from hiten.algorithms.poincare.centermanifold.backend import _CenterManifoldBackend
+    from hiten.algorithms.poincare.synodic.backend import _SynodicDetectionBackend
+    from hiten.algorithms.types.services.manifold import _ManifoldDynamicsService
+    o = _STATE["orig"]
+    for mod in _STATE["patched_modules"]:
+        setattr(mod, "_propagate_dynsys", o["propagate"])
+    _DOP853.integrate = o["dop853"]
+    _ManifoldDynamicsService._run_compute = o["run_compute"]
+    _SynodicDetectionBackend.run = o["synodic"]
+    _CenterManifoldBackend.run = o["cm"]
+    _STATE.update(installed=False, orig={}, patched_modules=[])
+    _TABLES.clear()
+
+
+def is_installed():
+    return _STATE["installed"]

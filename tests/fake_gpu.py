@@ -1,0 +1,88 @@
+"""Oracle-backed stand-ins for the GPU entry points, for CPU tests of the HOST plumbing only.
+
+tests/test_dropin_reference.py runs the real reference (when /root/reference is present) with
+hiten_b200.install() active and these fakes patched over hiten_b200.propagate / synodic / centermanifold, so
+that argument translation, result types and filters of the drop-in are checked against the reference's own
+objects without a GPU.  Product code never imports this module.
+"""
+import numpy as np
+
+import oracle_lib as O
+from hiten_b200.propagate import BatchResult
+from hiten_b200.synodic import SectionHits
+
+
+def _tol(integ):
+    return O.HoTol(integ.rtol, integ.atol, integ.max_step, integ.min_step)
+
+
+def cr3bp_dense(y0, mu, t_eval, *, forward=1, flip=None, integ=None, **kw):
+    s = O.system(O.SYS_CR3BP6, mu, fwd=forward, flip=flip)
+    dense, counts = O.batch_dense(s, O.DOP853, _tol(integ), np.asarray(y0), np.asarray(t_eval), 4)
+    n = len(dense)
+    return BatchResult(None, counts[:, 0].astype(np.int32), counts[:, 1].astype(np.int32), np.zeros(n, np.int32),
+                       states=dense)
+
+
+def cr3bp_stm_dense(x0, mu, t_eval, *, forward=1, flip=(36, 42), integ=None, **kw):
+    s = O.system(O.SYS_VAR42, mu, fwd=forward, flip=flip)
+    x0 = np.asarray(x0)
+    y0 = np.concatenate([np.tile(np.eye(6).ravel(), (len(x0), 1)), x0], axis=1)
+    dense, counts = O.batch_dense(s, O.DOP853, _tol(integ), y0, np.asarray(t_eval), 4)
+    return BatchResult(None, counts[:, 0].astype(np.int32), counts[:, 1].astype(np.int32),
+                       np.zeros(len(x0), np.int32), states=dense)
+
+
+def cr3bp_event(y0, mu, tmax, event_idx, *, event_offset=0.0, direction=0, xtol=1e-12, gtol=1e-12, t0=0.0,
+                forward=1, flip=None, integ=None, **kw):
+    s = O.system(O.SYS_CR3BP6, mu, fwd=forward, flip=flip)
+    ev = O.HoEvent(int(event_idx), float(event_offset), int(direction), xtol, gtol)
+    y0 = np.asarray(y0)
+    yf, th, st = np.empty_like(y0), np.empty(len(y0)), np.zeros(len(y0), np.int32)
+    for i in range(len(y0)):
+        hit, t, yh, yl, _ = O.adaptive_event(s, O.DOP853, _tol(integ), ev, y0[i], t0, tmax)
+        yf[i], th[i], st[i] = yh, t, 1 if hit else 0
+    return BatchResult(yf, np.zeros(len(y0), np.int32), np.zeros(len(y0), np.int32), st, t_hit=th)
+
+
+def detect(states, times, section, *, offsets=None, **kw):
+    states, times = np.asarray(states), np.asarray(times)
+    if offsets is None:
+        n, m = states.shape[:2]
+        offsets = np.arange(n + 1) * m
+        states = states.reshape(-1, 6)
+        if times.size == m:
+            times = np.tile(times, n)
+    ti, tt, ss = [], [], []
+    per = np.zeros(len(offsets) - 1, np.int32)
+    for k in range(len(offsets) - 1):
+        a, b = offsets[k], offsets[k + 1]
+        t, x = O.synodic_detect(times[a:b], states[a:b], section.idx, section.offset, section.direction,
+                                (section.proj_i, section.proj_j), section.segment_refine, section.tol_on_surface,
+                                section.dedup_time_tol, section.dedup_point_tol, section.max_hits_per_traj, cap=256)
+        per[k] = len(t)
+        ti += [k] * len(t); tt += list(t); ss += list(x)
+    ss = np.array(ss).reshape(-1, 6)
+    return SectionHits(np.array(ti, dtype=np.int64), np.array(tt), ss, ss[:, [section.proj_i, section.proj_j]], per)
+
+
+def poincare_map(table, seeds, opts, **kw):
+    ham = O.PolyHam(table.ptr, table.deg, table.coef, table.exp)
+    sec = {0: "q2", 1: "p2", 2: "q3", 3: "p3"}[opts.section]
+    symp = opts.method == 2
+    order = opts.order if symp else {4: 4, 6: 6, 8: 8}[opts.method]
+    c_omega = 20.0
+    if symp:                                   # recover c_omega from omega = (c*dt)^-order is not needed: sub_* carry it
+        c_omega = getattr(opts, "_c_omega", 20.0)
+    return O.cm_poincare_map(ham, seeds, opts.dt, order, opts.max_steps, symp, sec, c_omega, 4)
+
+
+def patch(monkeypatch):
+    import hiten_b200.centermanifold as cm
+    import hiten_b200.propagate as prop
+    import hiten_b200.synodic as syn
+    monkeypatch.setattr(prop, "cr3bp_dense", cr3bp_dense)
+    monkeypatch.setattr(prop, "cr3bp_stm_dense", cr3bp_stm_dense)
+    monkeypatch.setattr(prop, "cr3bp_event", cr3bp_event)
+    monkeypatch.setattr(syn, "detect", detect)
+    monkeypatch.setattr(cm, "poincare_map", poincare_map)
