@@ -7,8 +7,10 @@ Earth-Moon L1 halo (Az=0.2 S) of configs[0]: 2000 orbit nodes x D displacements 
 DOP853 at rtol = atol = 1e-12 -- N = 131072 trajectories per GPU (8 GPUs ~ 1e6 = configs[4]),
 weak scaling, no data-path collective, one gather of end states at the end of a step (N > 1).
 
-A "step" = one pass of the hot path over the per-GPU batch.  metric = fp64 CR3BP RK steps/s
-(attempted DOP853 steps, accepted + rejected, whole job).
+A "step" = one pass of the hot path over the per-GPU batch: the fused tube + synodic-section kernel
+(hb_cr3bp_section: DOP853 propagation, dense samples on the reference's dt = 1e-3 grid streamed through the
+reference's section detector, hits appended to a buffer, end states written).  metric = fp64 CR3BP RK steps/s
+(attempted DOP853 steps, accepted + rejected, whole job); crossings/s is reported beside it.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--arith parity|fast] [--impl ours|reference]
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
@@ -30,6 +32,9 @@ for _p in (REPO, os.path.join(REPO, "tests")):
         sys.path.insert(0, _p)
 
 FLOP_PER_STEP = 1350.0          # algorithmic flop per attempted 6-state DOP853 step
+FLOP_PER_SEGMENT = 1050.0       # dense-output cache of one accepted step (3 RHS + D/A_ext rows)
+FLOP_PER_SAMPLE = 84.0          # one dense sample (7-term Horner x 6 components)
+GRID_DT = 1.0e-3                # Manifold.compute default dt -> 4713 samples over tf
 N_PER_GPU = 131072
 TF = 0.75 * 2.0 * np.pi
 
@@ -95,56 +100,81 @@ class ClockSampler:
                 "samples": len(self.samples)}
 
 
-def cpu_port_throughput(ics, mu, n_threads, seconds_target=12.0):
-    """The oracle (C port of the reference algorithm) on the host cores, bounded sample."""
+def cpu_tube_section(ics, mu, n_threads):
+    """The same step on the CPU oracle: dense tube on the dt=1e-3 grid + section detection. Returns RK steps, hits."""
     import oracle_lib as O
     s = O.system(O.SYS_CR3BP6, mu, fwd=-1, flip=(0, 6))
-    tol = O.default_tol()
-    probe = ics[:256]
+    m = max(int(abs(TF) / GRID_DT) + 1, 100)
+    t_eval = np.linspace(0.0, TF, m)
+    times = -t_eval
+    steps, hits = 0, 0
+    chunk = 512                                            # 512 x 4713 x 48 B = 116 MB of dense output at a time
+    for a in range(0, len(ics), chunk):
+        dense, c = O.batch_dense(s, O.DOP853, O.default_tol(), ics[a:a + chunk], t_eval, n_threads)
+        steps += int(c.sum())
+        hits += O.batch_synodic_count(times, dense, 1, 0.0, -1, (0, 2), 50, 1e-6, 1e-9, 1e-6, n_threads)
+    return steps, hits
+
+
+def cpu_port_throughput(ics, mu, n_threads, seconds_target=12.0):
+    """The oracle (C port of the reference algorithm) on the host cores, bounded sample of the same step."""
     t0 = time.perf_counter()
-    _, c = O.batch_final(s, O.DOP853, tol, probe, 0.0, TF, n_threads)
+    cpu_tube_section(ics[:256], mu, n_threads)
     dt = max(time.perf_counter() - t0, 1e-4)
-    rate = len(probe) / dt
-    n = int(min(len(ics), max(512, rate * seconds_target)))
+    n = int(min(len(ics), max(512, 256 / dt * seconds_target)))
     t0 = time.perf_counter()
-    _, c = O.batch_final(s, O.DOP853, tol, ics[:n], 0.0, TF, n_threads)
+    steps, _ = cpu_tube_section(ics[:n], mu, n_threads)
     dt = time.perf_counter() - t0
-    return float(c.sum()) / dt, n, dt
+    return steps / dt, n, dt
 
 
 def run_reference(args):
-    """--impl reference: the reference algorithm's CPU restatement (oracle port) on all host threads."""
+    """--impl reference: the reference algorithm's CPU restatement (oracle port, all host threads) on the same
+    step -- tube propagation, dense samples on the dt=1e-3 grid, section detection -- on a bounded sample."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import oracle_lib as O
     n_threads = O.lib().ho_max_threads()
-    sample = 16384
+    sample = 8192
     ics, mu = build_ics(sample)
-    s = O.system(O.SYS_CR3BP6, mu, fwd=-1, flip=(0, 6))
-    tol = O.default_tol()
     for _ in range(args.warmup):
-        O.batch_final(s, O.DOP853, tol, ics[:2048], 0.0, TF, n_threads)
-    steps_total, t_total = 0.0, 0.0
+        cpu_tube_section(ics[:512], mu, n_threads)
+    steps_total, hits_total, t_total = 0.0, 0.0, 0.0
     for _ in range(args.steps):
         t0 = time.perf_counter()
-        _, c = O.batch_final(s, O.DOP853, tol, ics, 0.0, TF, n_threads)
+        st, hi = cpu_tube_section(ics, mu, n_threads)
         t_total += time.perf_counter() - t0
-        steps_total += float(c.sum())
+        steps_total += st
+        hits_total += hi
     val = steps_total / t_total
     line = {
         "impl": "reference", "metric": "fp64 CR3BP RK steps/s", "value": val, "unit": "RK steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C5-tube: EM L1 halo stable-manifold tube, DOP853 rtol=atol=1e-12, tf=0.75*2pi, "
-                               f"bounded sample of {sample} trajectories per step (CPU)"},
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "crossings_per_s": hits_total / t_total,
+        "config": {"workload": "C5-tube: EM L1 halo stable-manifold tube, DOP853 rtol=atol=1e-12, tf=0.75*2pi, dense "
+                               "dt=1e-3 grid + synodic detector y=0/(x,z)/-1; "
+                               f"bounded sample of {sample} trajectories per step (CPU oracle port)"},
         "cpu_baseline": {"value": val, "unit": "RK steps/s", "cores": n_threads, "kind": "port",
                          "sample": f"{sample} trajectories per step, {args.steps} steps"},
         "e2e": {"value": val, "unit": "RK steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+def time_steps(fn, steps, flush, barrier, torch):
+    """K timed iterations with an L2 flush between them; returns summed CUDA-event seconds."""
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    barrier()
+    for i in range(steps):
+        flush.fill_(float(i))                                            # L2 flush between timed iterations
+        ev[i][0].record()
+        fn()
+        ev[i][1].record()
+    barrier()
+    return sum(a.elapsed_time(b) for a, b in ev) * 1e-3
 
 
 def main():
@@ -156,6 +186,7 @@ def main():
     ap.add_argument("--arith", default="parity", choices=["parity", "fast"])
     ap.add_argument("--n-per-gpu", type=int, default=N_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary (propagate-only / fast) timings")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -167,6 +198,7 @@ def main():
     import torch.distributed as dist
     import hiten_b200 as hb
     from hiten_b200 import propagate as P
+    from hiten_b200 import synodic
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -182,26 +214,32 @@ def main():
     n = args.n_per_gpu
     ics, mu = build_ics(n, rank, world)
     integ = hb.make_integ(arith=args.arith)
-    ws = P.workspace(dev)
+    m = max(int(abs(TF) / GRID_DT) + 1, 100)                              # manifold.py:396-397 -> 4713
+    t_eval = np.linspace(0.0, TF, m)
+    sec = synodic.make_section("y", 0.0, ("x", "z"), -1)                  # configs[1]'s SynodicMap call
+    runner = synodic.TubeSectionRunner(n, mu, t_eval, sec, forward=-1, flip=(0, 6), integ=integ, device=dev)
     y0_soa = torch.from_numpy(np.ascontiguousarray(ics.T)).to(dev)       # resident input [6, N]
     host_in = torch.from_numpy(ics).pin_memory()                          # e2e input  [N, 6]
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)  # > 126 MB L2
-    gather_buf = None
+    gather_yf = gather_cnt = None
     if world > 1 and rank == 0:
-        gather_buf = [torch.empty((6, n), dtype=torch.float64, device=dev) for _ in range(world)]
+        gather_yf = [torch.empty((6, n), dtype=torch.float64, device=dev) for _ in range(world)]
+        gather_cnt = [torch.empty(n, dtype=torch.int32, device=dev) for _ in range(world)]
 
     def step_resident():
-        r = hb.cr3bp_propagate(y0_soa, mu, TF, forward=-1, flip=(0, 6), integ=integ, ws=ws)
-        if world > 1:
-            dist.gather(r.yf, gather_buf, dst=0)       # the one exchange: end states to rank 0
-        return r
+        runner.launch(y0_soa)
+        if world > 1:                                   # the one exchange: end states + hit counts to rank 0
+            dist.gather(runner.yf, gather_yf, dst=0)
+            dist.gather(runner.per, gather_cnt, dst=0)
 
     def step_e2e():
         d = host_in.to(dev, non_blocking=True).t().contiguous()          # H2D + AoS->SoA on device
-        r = hb.cr3bp_propagate(d, mu, TF, forward=-1, flip=(0, 6), integ=integ, ws=ws)
-        yf = r.yf.t().contiguous().cpu()                                  # D2H of the results
-        na, nr = r.n_acc.cpu(), r.n_rej.cpu()
-        return yf, na, nr
+        runner.launch(d)
+        k = runner.hit_count()                                            # syncs; then D2H of the results
+        hits = runner.hits[: k * 9].cpu()
+        yf = runner.yf.t().contiguous().cpu()
+        na, nr = runner.nacc.cpu(), runner.nrej.cpu()
+        return k, hits, yf, na, nr
 
     def barrier():
         if world > 1:
@@ -214,22 +252,15 @@ def main():
 
     sampler = ClockSampler(local)
     sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
     wall0 = time.perf_counter()
-    rk_steps = 0
-    last = None
-    for i in range(args.steps):
-        flush.fill_(float(i))                                            # L2 flush between timed iterations
-        ev[i][0].record()
-        last = step_resident()
-        ev[i][1].record()
-    barrier()
+    t_dev = time_steps(step_resident, args.steps, flush, barrier, torch)
     wall = time.perf_counter() - wall0
     clocks = sampler.stop()
-    t_dev = sum(a.elapsed_time(b) for a, b in ev) * 1e-3
-    steps_per_pass = int((last.n_acc.sum() + last.n_rej.sum()).item())
-    ok = bool((last.status == 0).all().item())
+    n_hits = runner.hit_count()
+    steps_acc = int(runner.nacc.sum().item())
+    steps_per_pass = steps_acc + int(runner.nrej.sum().item())
+    ok = bool((runner.status == 0).all().item())
+    t_kernel_local = t_dev
 
     # e2e: host buffers in, host results out, copies inside the timed region
     for _ in range(2):
@@ -237,52 +268,93 @@ def main():
     barrier()
     e2e_t0 = time.perf_counter()
     for _ in range(args.steps):
-        step_e2e()
+        k_e2e = step_e2e()[0]
     barrier()
     e2e_t = time.perf_counter() - e2e_t0
 
-    tt = torch.tensor([t_dev, e2e_t, float(steps_per_pass)], dtype=torch.float64, device=dev)
+    tt = torch.tensor([t_dev, e2e_t, float(steps_per_pass), float(n_hits), float(steps_acc)], dtype=torch.float64,
+                      device=dev)
     if world > 1:
         tmax = tt.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = tt.clone()
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        t_dev, e2e_t, total_steps_pass = tmax[0].item(), tmax[1].item(), tsum[2].item()
+        t_dev, e2e_t = tmax[0].item(), tmax[1].item()
+        total_steps_pass, total_hits, total_acc = tsum[2].item(), tsum[3].item(), tsum[4].item()
     else:
-        total_steps_pass = float(steps_per_pass)
+        total_steps_pass, total_hits, total_acc = float(steps_per_pass), float(n_hits), float(steps_acc)
+
+    extra = {}
+    if not args.no_extra and world == 1:
+        # secondary numbers that explain the headline: propagation only (end states), both arithmetic variants,
+        # and the fused step in the other variant
+        ws = P.workspace(dev)
+        for name in ("parity", "fast"):
+            ig = hb.make_integ(arith=name)
+            hold = {}
+
+            def prop():
+                hold["r"] = hb.cr3bp_propagate(y0_soa, mu, TF, forward=-1, flip=(0, 6), integ=ig, ws=ws)
+
+            for _ in range(3):
+                prop()
+            tp = time_steps(prop, args.steps, flush, barrier, torch)
+            sp = int((hold["r"].n_acc.sum() + hold["r"].n_rej.sum()).item())
+            extra[f"propagate_only_{name}"] = {"rk_steps_per_s": sp * args.steps / tp,
+                                               "tflops": sp * args.steps * FLOP_PER_STEP / tp / 1e12}
+        other = "fast" if args.arith == "parity" else "parity"
+        r2 = synodic.TubeSectionRunner(n, mu, t_eval, sec, forward=-1, flip=(0, 6), integ=hb.make_integ(arith=other),
+                                       device=dev)
+        for _ in range(3):
+            r2.launch(y0_soa)
+        t2 = time_steps(lambda: r2.launch(y0_soa), args.steps, flush, barrier, torch)
+        s2 = int((r2.nacc.sum() + r2.nrej.sum()).item())
+        extra[f"section_{other}"] = {"rk_steps_per_s": s2 * args.steps / t2,
+                                     "crossings_per_s": r2.hit_count() * args.steps / t2}
 
     if rank == 0:
         value = total_steps_pass * args.steps / t_dev
         e2e_value = total_steps_pass * args.steps / e2e_t
         peak = hb.dfma_peak(200.0)
-        kernel_rate = steps_per_pass * args.steps / (sum(a.elapsed_time(b) for a, b in ev) * 1e-3)
-        achieved = kernel_rate * FLOP_PER_STEP
+        flop_pass = steps_per_pass * FLOP_PER_STEP + steps_acc * FLOP_PER_SEGMENT + n * m * FLOP_PER_SAMPLE
+        achieved = flop_pass * args.steps / t_kernel_local
+        for v in extra.values():
+            if "tflops" in v:
+                v["frac_of_fp64_peak"] = v["tflops"] * 1e12 / peak
         line = {
             "metric": "fp64 CR3BP RK steps/s", "value": value, "unit": "RK steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
+            "crossings_per_s": total_hits * args.steps / t_dev,
             "config": {
-                "workload": "C5-tube: EM L1 halo (Az=0.2 S) stable-manifold tube, 2000 nodes x log-spaced "
-                            "displacements, DOP853 rtol=atol=1e-12, backward tf=0.75*2pi, end states",
-                "trajectories_per_gpu": n, "arith": args.arith, "l2": "flushed between timed iterations "
-                "(256 MB fill); inputs 6 MB/GPU are L2-resident by nature, kernel is FP64-pipe bound",
-                "rk_steps_per_pass": total_steps_pass, "all_status_ok": ok,
+                "workload": "C5-tube (BASELINE configs[4] per-GPU share, configs[1] section): EM L1 halo (Az=0.2 S) "
+                            "stable-manifold tube, 2000 nodes x log-spaced displacements, DOP853 rtol=atol=1e-12, "
+                            "backward tf=0.75*2pi, dense samples on the dt=1e-3 grid (4713) streamed through the "
+                            "synodic detector y=0 / (x,z) / direction=-1 (segment_refine=50), hits + end states out",
+                "trajectories_per_gpu": n, "grid_samples": m, "arith": args.arith,
+                "l2": "flushed between timed iterations (256 MB fill); inputs 6 MB/GPU, kernel is FP64-pipe bound",
+                "rk_steps_per_pass": total_steps_pass, "accepted_steps_per_pass": total_acc,
+                "crossings_per_pass": total_hits, "all_status_ok": ok,
             },
             "roofline": {"bound": "fp64", "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "TFLOP/s",
                          "frac": achieved / peak, "traffic": None,
-                         "note": "FP64 FMA pipe roofline (no tensor/HBM bound applies): achieved = attempted steps "
-                                 "x 1350 algorithmic flop / kernel time; peak = hb_dfma_peak measured in this process"},
+                         "note": "FP64 FMA pipe roofline (neither HBM nor tensor bound applies: 96 B + hits per "
+                                 "trajectory of HBM traffic). achieved = (attempted steps x 1350 + accepted steps x 1050 "
+                                 "+ grid samples x 84 algorithmic flop, SURVEY 8d) / kernel time (CUDA events); "
+                                 "peak = hb_dfma_peak measured in this process (of measured)"},
             "e2e": {"value": e2e_value, "unit": "RK steps/s", "h2d_bytes_per_step": int(n * 48),
-                    "d2h_bytes_per_step": int(n * (48 + 8))},
-            "gpu_launches": args.steps, "clocks": clocks, "wall_s_timed_region": wall,
+                    "d2h_bytes_per_step": int(n * (48 + 8) + 72 * k_e2e),
+                    "crossings_per_s": total_hits * args.steps / e2e_t},
+            "gpu_launches": args.steps, "clocks": clocks, "wall_s_timed_region": wall, "extra": extra,
         }
         if not args.no_cpu_baseline and world == 1:
             import oracle_lib as O
             nthr = O.lib().ho_max_threads()
             v, ns, dt = cpu_port_throughput(ics, mu, nthr)
             line["cpu_baseline"] = {"value": v, "unit": "RK steps/s", "cores": nthr, "kind": "port",
-                                    "sample": f"first {ns} trajectories of the same batch, {dt:.1f} s"}
+                                    "sample": f"{ns} trajectories of the same batch (tube propagation + dense grid + "
+                                              f"section detection per trajectory), {dt:.1f} s"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

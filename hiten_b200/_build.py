@@ -12,6 +12,7 @@ NVCC_FLAGS = [
     "-std=c++17", "-O3", "-lineinfo",
     "-gencode", "arch=compute_100a,code=sm_100a",
     "--expt-relaxed-constexpr",
+    "-t", "8",
     "-Xcompiler", "-fPIC",
     "-shared",
 ]

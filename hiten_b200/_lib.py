@@ -68,6 +68,8 @@ SIGNATURES = {
                                      vp, C.c_int32, vp, vp, vp, vp, vp, vp]),
     "hb_cr3bp_dense": (C.c_int, [C.POINTER(HbCr3bp), C.POINTER(HbInteg), C.c_int64, vp, vp, C.c_int32, vp, vp, vp,
                                  vp, vp, vp]),
+    "hb_cr3bp_section": (C.c_int, [C.POINTER(HbCr3bp), C.POINTER(HbInteg), C.POINTER(HbSection), C.c_int64, vp, vp,
+                                   C.c_int32, vp, C.c_int64, vp, vp, vp, vp, vp, vp, vp]),
     "hb_cr3bp_event": (C.c_int, [C.POINTER(HbCr3bp), C.POINTER(HbInteg), C.POINTER(HbEvent), C.c_int64, vp,
                                  C.c_double, C.c_double, vp, vp, vp, vp, vp, vp, vp, vp]),
     "hb_dfma_peak": (C.c_int, [C.c_double, C.POINTER(C.c_double), vp]),

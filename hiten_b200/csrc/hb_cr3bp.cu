@@ -15,10 +15,11 @@
 //   _dop853_build_dense_cache / _dop853_eval_dense / _dop853_refine_in_step   rk.py:1791-2102
 //   controller helpers                algorithms/integrators/utils.py
 #include "hb_dop853.cuh"
+#include "hb_section.cuh"
 
 namespace {
 
-enum { MODE_FINAL = 0, MODE_DENSE = 1, MODE_EVENT = 2 };
+enum { MODE_FINAL = 0, MODE_DENSE = 1, MODE_EVENT = 2, MODE_SECTION = 3 };
 
 // 256 resident threads per SM (8 warps) is what 240+ registers per thread allow; one 256-thread CTA
 // per SM measured ~8% faster than two of 128 (gpurun probe, round 1).
@@ -47,6 +48,9 @@ struct PropParams {
     int ev_idx, ev_dir;
     double ev_off, xtol, gtol;
     double *t_hit;
+    HitSink sink;          // MODE_SECTION: detector settings + hit buffer
+    int *hits_per_traj;
+    double tsign;          // sign applied to grid times for the detector (times = forward * t_eval)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -175,6 +179,10 @@ __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) k_dop853_6(const PropP
     long long attempts = 0;
     int nacc = 0, nrej = 0, cursor = 0;
     bool have = false, exhausted = false;
+    // MODE_SECTION: previous grid sample, its event value and the one before, de-duplication state
+    double xs_prev[6], gs_prev = 0.0, gs_prev2 = 0.0;
+    Dedup dd{0.0, 0.0, 0.0, 0};
+    bool sec_alive = true;
 
     for (;;) {
         if (!have && !exhausted) {
@@ -188,10 +196,12 @@ __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) k_dop853_6(const PropP
                 h = initial_step<AR>(y, k[0], p);
                 err_prev = -1.0;
                 nacc = 0; nrej = 0; cursor = 0; attempts = 0;
+                if (MODE == MODE_SECTION) { dd = Dedup{0.0, 0.0, 0.0, 0}; sec_alive = true; }
                 if (MODE == MODE_EVENT) g_prev = AR::sub(pick6(y, p.ev_idx), p.ev_off);
                 have = true;
                 if (!((t - tf) < 0.0)) {
                     // zero-length span: nothing to integrate
+                    if (MODE == MODE_SECTION && p.hits_per_traj) p.hits_per_traj[idx] = 0;
                     if (MODE != MODE_DENSE) {
 #pragma unroll
                         for (int d = 0; d < 6; ++d) p.yf[(long long)d * p.n + idx] = y[d];
@@ -281,6 +291,45 @@ __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) k_dop853_6(const PropP
                     }
                 }
                 if (last) fin = HB_TRAJ_OK;
+            } else if (MODE == MODE_SECTION) {
+                // Reference semantics without materialising the tube: the dense samples on the t_eval grid are
+                // produced exactly as in MODE_DENSE and streamed through the synodic detector (segment k is
+                // processed when sample k+1 exists), so hits are the reference's linear interpolants.
+                if (cursor < p.m && (last || p.t_eval[cursor] < t_new)) {
+                    const double hseg = AR::sub(t_new, t);
+                    double F[7][6], yo[6];
+                    if (hseg != 0.0) dense_cache<AR>(y, yh, hseg, k, F, rhs);
+                    while (cursor < p.m) {
+                        const double tq = p.t_eval[cursor];
+                        if (!(last || tq < t_new)) break;
+                        if (hseg == 0.0) {
+#pragma unroll
+                            for (int d = 0; d < 6; ++d) yo[d] = y[d];
+                        } else {
+                            dense_eval<AR>(y, F, AR::div(AR::sub(tq, t), hseg), yo);
+                        }
+                        const double g_now = __dsub_rn(pick(yo, p.sink.sec.idx), p.sink.sec.offset);
+                        if (cursor > 0 && sec_alive) {
+                            const bool same = (gs_prev > 0.0 && g_now > 0.0) || (gs_prev < 0.0 && g_now < 0.0);
+                            if (!same || fabs(gs_prev) < p.sink.sec.tol_on_surface) {
+                                const double t0s = __dmul_rn(p.tsign, p.t_eval[cursor - 1]);
+                                const double t1s = __dmul_rn(p.tsign, tq);
+                                sec_alive = process_segment(p.sink, dd, idx, 0, cursor > 1, gs_prev2, t0s, t1s, xs_prev, yo);
+                            }
+                        }
+                        gs_prev2 = gs_prev;
+                        gs_prev = g_now;
+#pragma unroll
+                        for (int d = 0; d < 6; ++d) xs_prev[d] = yo[d];
+                        ++cursor;
+                    }
+                }
+                if (last) {
+#pragma unroll
+                    for (int d = 0; d < 6; ++d) p.yf[(long long)d * p.n + idx] = xs_prev[d];
+                    if (p.hits_per_traj) p.hits_per_traj[idx] = dd.n;
+                    fin = HB_TRAJ_OK;
+                }
             } else {  // MODE_FINAL: the dense interpolant at tf on the last segment
                 if (last) {
                     const double hseg = AR::sub(t_new, t);
@@ -325,6 +374,7 @@ __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) k_dop853_6(const PropP
                     for (int d = 0; d < 6; ++d) p.yf[(long long)d * p.n + idx] = y[d];
                 }
                 if (MODE == MODE_EVENT) p.t_hit[idx] = t;
+                if (MODE == MODE_SECTION && p.hits_per_traj) p.hits_per_traj[idx] = dd.n;
             }
         }
         if (fin >= 0) {
@@ -468,6 +518,36 @@ int hb_cr3bp_event(const hb_cr3bp *sys, const hb_integ *integ, const hb_event *e
     p.ev_idx = ev->idx; p.ev_dir = ev->direction; p.ev_off = ev->offset; p.xtol = ev->xtol; p.gtol = ev->gtol;
     p.ws = (HbWorkspace *)workspace;
     return launch<MODE_EVENT>(p, integ->arith, (cudaStream_t)stream);
+}
+
+int hb_cr3bp_section(const hb_cr3bp *sys, const hb_integ *integ, const hb_section *sec, int64_t n,
+                     const double *y0_soa, const double *t_eval, int32_t m, hb_hit *hits, int64_t hit_capacity,
+                     int32_t *hits_per_traj, double *yf_soa, int32_t *n_acc, int32_t *n_rej, int32_t *status,
+                     void *workspace, void *stream)
+{
+    PropParams p{};
+    int rc = fill_params(sys, integ, p);
+    if (rc != HB_OK) return rc;
+    if (!sec || sec->idx < 0 || sec->idx > 5 || sec->proj_i < 0 || sec->proj_i > 5 || sec->proj_j < 0 ||
+        sec->proj_j > 5 || sec->segment_refine < 0 || hit_capacity < 0)
+        return HB_ERR_BADARG;
+    if (n < 0 || m < 2 || !workspace || !t_eval ||
+        (n > 0 && (!y0_soa || !yf_soa || !n_acc || !n_rej || !status || (hit_capacity > 0 && !hits))))
+        return HB_ERR_BADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n == 0) { HB_CUDA_TRY(cudaMemsetAsync(workspace, 0, sizeof(HbWorkspace), st)); return HB_OK; }
+    double ends[2];
+    HB_CUDA_TRY(cudaMemcpyAsync(&ends[0], t_eval, sizeof(double), cudaMemcpyDeviceToHost, st));
+    HB_CUDA_TRY(cudaMemcpyAsync(&ends[1], t_eval + (m - 1), sizeof(double), cudaMemcpyDeviceToHost, st));
+    HB_CUDA_TRY(cudaStreamSynchronize(st));
+    p.n = n; p.y0 = y0_soa; p.t0 = ends[0]; p.tf = ends[1]; p.tf_arr = nullptr;
+    p.yf = yf_soa; p.nacc = n_acc; p.nrej = n_rej; p.status = status;
+    p.t_eval = t_eval; p.m = m;
+    p.ws = (HbWorkspace *)workspace;
+    p.sink.sec = *sec; p.sink.hits = hits; p.sink.capacity = hit_capacity; p.sink.ws = p.ws;
+    p.hits_per_traj = hits_per_traj;
+    p.tsign = sys->fwd < 0 ? -1.0 : 1.0;
+    return launch<MODE_SECTION>(p, integ->arith, st);
 }
 
 }  // extern "C"

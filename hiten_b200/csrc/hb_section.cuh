@@ -1,0 +1,119 @@
+// hb_section.cuh -- the reference's synodic-section detector on ONE sample segment, plus hit de-duplication.
+// Shared by the stand-alone detector (hb_synodic.cu, warp per trajectory, executed warp-uniformly) and the fused
+// section mode of the DOP853 kernel (hb_cr3bp.cu, thread per trajectory).
+// Reference: hiten/algorithms/poincare/synodic/backend.py  _detect_with_segment_refine :458-659 (linear branch),
+// detect_on_trajectory :782-821 (segment_refine == 0), _order_and_dedup_hits :382-455.
+#pragma once
+#include "hb_common.cuh"
+
+struct HitSink {
+    hb_section sec;
+    hb_hit *hits;
+    long long capacity;
+    HbWorkspace *ws;
+};
+
+HB_DEV double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+struct Dedup {
+    double last_t, last_u, last_v;
+    int n;
+};
+
+// _order_and_dedup_hits (backend.py:440-454); returns false when the per-trajectory cap is reached
+HB_DEV bool push_hit(const HitSink &p, Dedup &dd, long long traj, double th, const double (&xh)[6], int lane)
+{
+    const int mh = p.sec.max_hits_per_traj;
+    if (mh > 0 && dd.n >= mh) return false;
+    const double u = (p.sec.proj_i == 0) ? xh[0] : (p.sec.proj_i == 1) ? xh[1] : (p.sec.proj_i == 2) ? xh[2]
+                   : (p.sec.proj_i == 3) ? xh[3] : (p.sec.proj_i == 4) ? xh[4] : xh[5];
+    const double v = (p.sec.proj_j == 0) ? xh[0] : (p.sec.proj_j == 1) ? xh[1] : (p.sec.proj_j == 2) ? xh[2]
+                   : (p.sec.proj_j == 3) ? xh[3] : (p.sec.proj_j == 4) ? xh[4] : xh[5];
+    if (dd.n > 0) {
+        if (fabs(__dsub_rn(th, dd.last_t)) <= p.sec.dedup_time_tol) return true;
+        const double du = __dsub_rn(u, dd.last_u), dv = __dsub_rn(v, dd.last_v);
+        const double d2 = __dadd_rn(__dmul_rn(du, du), __dmul_rn(dv, dv));
+        if (d2 <= __dmul_rn(p.sec.dedup_point_tol, p.sec.dedup_point_tol)) return true;
+    }
+    if (lane == 0) {
+        const unsigned long long slot = atomicAdd(&p.ws->hit_count, 1ULL);
+        if ((long long)slot < p.capacity) {
+            hb_hit *h = p.hits + slot;
+            h->traj = traj; h->seq = dd.n; h->t = th;
+#pragma unroll
+            for (int d = 0; d < 6; ++d) h->state[d] = xh[d];
+        } else {
+            atomicAdd(&p.ws->overflow, 1ULL);
+        }
+    }
+    dd.last_t = th; dd.last_u = u; dd.last_v = v;
+    dd.n++;
+    return true;
+}
+
+HB_DEV double pick(const double (&x)[6], int i)
+{
+    double r = x[0];
+#pragma unroll
+    for (int d = 1; d < 6; ++d) r = (i == d) ? x[d] : r;
+    return r;
+}
+
+// Full per-segment logic of _detect_with_segment_refine / the r == 0 path, executed warp-uniformly.
+HB_DEV bool process_segment(const HitSink &p, Dedup &dd, long long traj, int lane, bool has_prev, double g_prev,
+                            double t0, double t1, const double (&x0)[6], const double (&x1)[6])
+{
+    const int dir = p.sec.direction;
+    const double gk = __dsub_rn(pick(x0, p.sec.idx), p.sec.offset);
+    const double gk1 = __dsub_rn(pick(x1, p.sec.idx), p.sec.offset);
+    bool accept_left = false;
+    if (fabs(gk) < p.sec.tol_on_surface) {
+        if (dir == 0) accept_left = true;
+        else if (dir > 0) accept_left = (gk1 >= 0.0) || (has_prev && g_prev <= 0.0);
+        else accept_left = (gk1 <= 0.0) || (has_prev && g_prev >= 0.0);
+    }
+    const int r = p.sec.segment_refine;
+    double xh[6];
+    if (r > 0) {
+        if (accept_left && !push_hit(p, dd, traj, t0, x0, lane)) return false;
+        const double step = __ddiv_rn(1.0, (double)(r + 1));
+        for (int mm = 0; mm <= r; ++mm) {
+            const double s_lo = __dmul_rn((double)mm, step), s_hi = __dmul_rn((double)(mm + 1), step);
+            if (s_hi > 1.0 + 1e-15) break;
+            if (accept_left && mm == 0) continue;
+            const double g_lo = __dadd_rn(__dmul_rn(__dsub_rn(1.0, s_lo), gk), __dmul_rn(s_lo, gk1));
+            const double g_hi = __dadd_rn(__dmul_rn(__dsub_rn(1.0, s_hi), gk), __dmul_rn(s_hi, gk1));
+            bool crosses;
+            if (dir == 0) crosses = (__dmul_rn(g_lo, g_hi) <= 0.0) && (g_lo != g_hi);
+            else if (dir > 0) crosses = (g_lo < 0.0) && (g_hi >= 0.0);
+            else crosses = (g_lo > 0.0) && (g_hi <= 0.0);
+            if (!crosses) continue;
+            double s_star;
+            if (g_lo == g_hi) s_star = __dmul_rn(0.5, __dadd_rn(s_lo, s_hi));
+            else {
+                double al = __ddiv_rn(g_lo, __dsub_rn(g_lo, g_hi));
+                al = fmin(1.0, fmax(0.0, al));
+                s_star = __dadd_rn(s_lo, __dmul_rn(al, __dsub_rn(s_hi, s_lo)));
+            }
+            const double th = __dadd_rn(__dmul_rn(__dsub_rn(1.0, s_star), t0), __dmul_rn(s_star, t1));
+#pragma unroll
+            for (int d = 0; d < 6; ++d) xh[d] = __dadd_rn(x0[d], __dmul_rn(s_star, __dsub_rn(x1[d], x0[d])));
+            if (!push_hit(p, dd, traj, th, xh, lane)) return false;
+        }
+    } else {
+        if (accept_left) return push_hit(p, dd, traj, t0, x0, lane);
+        bool crosses;
+        if (dir == 0) crosses = (__dmul_rn(gk, gk1) <= 0.0) && (gk != gk1);
+        else if (dir > 0) crosses = (gk < 0.0) && (gk1 >= 0.0);
+        else crosses = (gk > 0.0) && (gk1 <= 0.0);
+        if (!crosses) return true;
+        double al = __ddiv_rn(gk, __dsub_rn(gk, gk1));
+        al = fmin(1.0, fmax(0.0, al));
+        const double th = __dadd_rn(__dmul_rn(__dsub_rn(1.0, al), t0), __dmul_rn(al, t1));
+#pragma unroll
+        for (int d = 0; d < 6; ++d) xh[d] = __dadd_rn(x0[d], __dmul_rn(al, __dsub_rn(x1[d], x0[d])));
+        return push_hit(p, dd, traj, th, xh, lane);
+    }
+    return true;
+}
+

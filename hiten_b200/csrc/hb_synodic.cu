@@ -13,7 +13,7 @@
 // segments take the serial path, which every lane executes redundantly so that the de-duplication
 // state (last kept hit) stays warp-uniform.  All arithmetic is separately rounded (__d*_rn) in the
 // reference's operation order.
-#include "hb_common.cuh"
+#include "hb_section.cuh"
 
 namespace {
 
@@ -24,116 +24,9 @@ struct SynParams {
     int m_uniform;
     int times_shared;
     long long n;
-    hb_section sec;
-    hb_hit *hits;
-    long long capacity;
+    HitSink sink;
     int *hits_per_traj;        // optional [n]
-    HbWorkspace *ws;
 };
-
-struct Dedup {
-    double last_t, last_u, last_v;
-    int n;
-};
-
-HB_DEV double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
-
-// _order_and_dedup_hits (backend.py:440-454); returns false when the per-trajectory cap is reached
-HB_DEV bool push_hit(const SynParams &p, Dedup &dd, long long traj, double th, const double (&xh)[6], int lane)
-{
-    const int mh = p.sec.max_hits_per_traj;
-    if (mh > 0 && dd.n >= mh) return false;
-    const double u = (p.sec.proj_i == 0) ? xh[0] : (p.sec.proj_i == 1) ? xh[1] : (p.sec.proj_i == 2) ? xh[2]
-                   : (p.sec.proj_i == 3) ? xh[3] : (p.sec.proj_i == 4) ? xh[4] : xh[5];
-    const double v = (p.sec.proj_j == 0) ? xh[0] : (p.sec.proj_j == 1) ? xh[1] : (p.sec.proj_j == 2) ? xh[2]
-                   : (p.sec.proj_j == 3) ? xh[3] : (p.sec.proj_j == 4) ? xh[4] : xh[5];
-    if (dd.n > 0) {
-        if (fabs(__dsub_rn(th, dd.last_t)) <= p.sec.dedup_time_tol) return true;
-        const double du = __dsub_rn(u, dd.last_u), dv = __dsub_rn(v, dd.last_v);
-        const double d2 = __dadd_rn(__dmul_rn(du, du), __dmul_rn(dv, dv));
-        if (d2 <= __dmul_rn(p.sec.dedup_point_tol, p.sec.dedup_point_tol)) return true;
-    }
-    if (lane == 0) {
-        const unsigned long long slot = atomicAdd(&p.ws->hit_count, 1ULL);
-        if ((long long)slot < p.capacity) {
-            hb_hit *h = p.hits + slot;
-            h->traj = traj; h->seq = dd.n; h->t = th;
-#pragma unroll
-            for (int d = 0; d < 6; ++d) h->state[d] = xh[d];
-        } else {
-            atomicAdd(&p.ws->overflow, 1ULL);
-        }
-    }
-    dd.last_t = th; dd.last_u = u; dd.last_v = v;
-    dd.n++;
-    return true;
-}
-
-HB_DEV double pick(const double (&x)[6], int i)
-{
-    double r = x[0];
-#pragma unroll
-    for (int d = 1; d < 6; ++d) r = (i == d) ? x[d] : r;
-    return r;
-}
-
-// Full per-segment logic of _detect_with_segment_refine / the r == 0 path, executed warp-uniformly.
-HB_DEV bool process_segment(const SynParams &p, Dedup &dd, long long traj, int lane, bool has_prev, double g_prev,
-                            double t0, double t1, const double (&x0)[6], const double (&x1)[6])
-{
-    const int dir = p.sec.direction;
-    const double gk = __dsub_rn(pick(x0, p.sec.idx), p.sec.offset);
-    const double gk1 = __dsub_rn(pick(x1, p.sec.idx), p.sec.offset);
-    bool accept_left = false;
-    if (fabs(gk) < p.sec.tol_on_surface) {
-        if (dir == 0) accept_left = true;
-        else if (dir > 0) accept_left = (gk1 >= 0.0) || (has_prev && g_prev <= 0.0);
-        else accept_left = (gk1 <= 0.0) || (has_prev && g_prev >= 0.0);
-    }
-    const int r = p.sec.segment_refine;
-    double xh[6];
-    if (r > 0) {
-        if (accept_left && !push_hit(p, dd, traj, t0, x0, lane)) return false;
-        const double step = __ddiv_rn(1.0, (double)(r + 1));
-        for (int mm = 0; mm <= r; ++mm) {
-            const double s_lo = __dmul_rn((double)mm, step), s_hi = __dmul_rn((double)(mm + 1), step);
-            if (s_hi > 1.0 + 1e-15) break;
-            if (accept_left && mm == 0) continue;
-            const double g_lo = __dadd_rn(__dmul_rn(__dsub_rn(1.0, s_lo), gk), __dmul_rn(s_lo, gk1));
-            const double g_hi = __dadd_rn(__dmul_rn(__dsub_rn(1.0, s_hi), gk), __dmul_rn(s_hi, gk1));
-            bool crosses;
-            if (dir == 0) crosses = (__dmul_rn(g_lo, g_hi) <= 0.0) && (g_lo != g_hi);
-            else if (dir > 0) crosses = (g_lo < 0.0) && (g_hi >= 0.0);
-            else crosses = (g_lo > 0.0) && (g_hi <= 0.0);
-            if (!crosses) continue;
-            double s_star;
-            if (g_lo == g_hi) s_star = __dmul_rn(0.5, __dadd_rn(s_lo, s_hi));
-            else {
-                double al = __ddiv_rn(g_lo, __dsub_rn(g_lo, g_hi));
-                al = fmin(1.0, fmax(0.0, al));
-                s_star = __dadd_rn(s_lo, __dmul_rn(al, __dsub_rn(s_hi, s_lo)));
-            }
-            const double th = __dadd_rn(__dmul_rn(__dsub_rn(1.0, s_star), t0), __dmul_rn(s_star, t1));
-#pragma unroll
-            for (int d = 0; d < 6; ++d) xh[d] = __dadd_rn(x0[d], __dmul_rn(s_star, __dsub_rn(x1[d], x0[d])));
-            if (!push_hit(p, dd, traj, th, xh, lane)) return false;
-        }
-    } else {
-        if (accept_left) return push_hit(p, dd, traj, t0, x0, lane);
-        bool crosses;
-        if (dir == 0) crosses = (__dmul_rn(gk, gk1) <= 0.0) && (gk != gk1);
-        else if (dir > 0) crosses = (gk < 0.0) && (gk1 >= 0.0);
-        else crosses = (gk > 0.0) && (gk1 <= 0.0);
-        if (!crosses) return true;
-        double al = __ddiv_rn(gk, __dsub_rn(gk, gk1));
-        al = fmin(1.0, fmax(0.0, al));
-        const double th = __dadd_rn(__dmul_rn(__dsub_rn(1.0, al), t0), __dmul_rn(al, t1));
-#pragma unroll
-        for (int d = 0; d < 6; ++d) xh[d] = __dadd_rn(x0[d], __dmul_rn(al, __dsub_rn(x1[d], x0[d])));
-        return push_hit(p, dd, traj, th, xh, lane);
-    }
-    return true;
-}
 
 __global__ void __launch_bounds__(256) k_synodic_detect(const SynParams p)
 {
@@ -160,12 +53,12 @@ __global__ void __launch_bounds__(256) k_synodic_detect(const SynParams p)
                 const double nb = __shfl_down_sync(0xffffffffu, x0[d], 1);
                 x1[d] = (lane == 31 || k + 1 >= m - 1) ? X[(long long)(kk + 1) * 6 + d] : nb;
             }
-            const double gk = __dsub_rn(pick(x0, p.sec.idx), p.sec.offset);
-            const double gk1 = __dsub_rn(pick(x1, p.sec.idx), p.sec.offset);
+            const double gk = __dsub_rn(pick(x0, p.sink.sec.idx), p.sink.sec.offset);
+            const double gk1 = __dsub_rn(pick(x1, p.sink.sec.idx), p.sink.sec.offset);
             double g_prev = __shfl_up_sync(0xffffffffu, gk, 1);
-            if (lane == 0 && k > 0) g_prev = __dsub_rn(X[(long long)(k - 1) * 6 + p.sec.idx], p.sec.offset);
+            if (lane == 0 && k > 0) g_prev = __dsub_rn(X[(long long)(k - 1) * 6 + p.sink.sec.idx], p.sink.sec.offset);
             const bool same_sign = (gk > 0.0 && gk1 > 0.0) || (gk < 0.0 && gk1 < 0.0);
-            const bool flagged = valid && (!same_sign || fabs(gk) < p.sec.tol_on_surface);
+            const bool flagged = valid && (!same_sign || fabs(gk) < p.sink.sec.tol_on_surface);
             unsigned mask = __ballot_sync(0xffffffffu, flagged);
             while (mask) {
                 const int src = __ffs(mask) - 1;
@@ -176,7 +69,7 @@ __global__ void __launch_bounds__(256) k_synodic_detect(const SynParams p)
                 const double gp = shfl_d(g_prev, src);
                 const int ks = base + src;
                 const double t0 = T[ks], t1 = T[ks + 1];
-                if (!process_segment(p, dd, traj, lane, ks > 0, gp, t0, t1, a0, a1)) { alive = false; break; }
+                if (!process_segment(p.sink, dd, traj, lane, ks > 0, gp, t0, t1, a0, a1)) { alive = false; break; }
             }
         }
         if (p.hits_per_traj && lane == 0) p.hits_per_traj[traj] = dd.n;
@@ -201,8 +94,9 @@ extern "C" int hb_synodic_detect(const hb_section *sec, int64_t n_traj, const do
     if (n_traj == 0) return HB_OK;
     SynParams p{};
     p.states = states; p.times = times; p.offsets = (const long long *)offsets; p.m_uniform = m_uniform;
-    p.times_shared = times_shared; p.n = n_traj; p.sec = *sec; p.hits = hits; p.capacity = hit_capacity;
-    p.hits_per_traj = hits_per_traj; p.ws = (HbWorkspace *)workspace;
+    p.times_shared = times_shared; p.n = n_traj;
+    p.sink.sec = *sec; p.sink.hits = hits; p.sink.capacity = hit_capacity; p.sink.ws = (HbWorkspace *)workspace;
+    p.hits_per_traj = hits_per_traj;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -84,3 +84,88 @@ def detect(states, times, section, *, offsets=None, hit_capacity=None, device=No
         rec = rec[order]
         pts = np.column_stack((rec["state"][:, section.proj_i], rec["state"][:, section.proj_j])) if k else np.empty((0, 2))
         return SectionHits(rec["traj"].copy(), rec["t"].copy(), rec["state"].copy(), pts, per[:n].cpu().numpy())
+
+
+def tube_section(y0, mu, t_eval, section, *, forward=1, flip=None, integ=None, hit_capacity=None, device=None,
+                 stream=None, ws=None, sort=True):
+    """Fused Manifold.compute() + SynodicMap.compute(): propagate a batch over the t_eval grid and detect section
+    hits in-kernel, without storing the dense tube.  Returns (SectionHits, BatchResult with end states)."""
+    from . import propagate as P
+    _require_cuda()
+    lib = L.load()
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    with torch.cuda.device(device):
+        y0d, host = P._to_device_soa(y0, device)
+        n = y0d.shape[1]
+        te = t_eval if isinstance(t_eval, torch.Tensor) else torch.from_numpy(
+            np.ascontiguousarray(np.asarray(t_eval, dtype=np.float64)))
+        te = te.to(device).contiguous()
+        m = te.numel()
+        yf, nacc, nrej, status = P._alloc_out(n, device)
+        per = torch.zeros(max(n, 1), dtype=torch.int32, device=device)
+        ws = workspace(device) if ws is None else ws
+        integ = P.make_integ() if integ is None else integ
+        sys_ = P.make_sys(mu, forward, flip)
+        cap = int(hit_capacity) if hit_capacity is not None else max(1024, 8 * n)
+        while True:
+            hits = torch.empty(cap * 9, dtype=torch.float64, device=device)
+            rc = lib.hb_cr3bp_section(sys_, integ, section, n, y0d.data_ptr(), te.data_ptr(), m, hits.data_ptr(), cap,
+                                      per.data_ptr(), yf.data_ptr(), nacc.data_ptr(), nrej.data_ptr(),
+                                      status.data_ptr(), ws.data_ptr(), _stream_ptr(stream))
+            L.check(rc, "hb_cr3bp_section")
+            nh, no = L.C.c_int64(0), L.C.c_int64(0)
+            L.check(lib.hb_read_hit_count(ws.data_ptr(), L.C.byref(nh), L.C.byref(no), _stream_ptr(stream)),
+                    "hb_read_hit_count")
+            if no.value == 0:
+                break
+            cap = int(nh.value) + 16
+        k = int(nh.value)
+        if host:
+            res = P.BatchResult(yf.t().contiguous().cpu().numpy(), nacc.cpu().numpy(), nrej.cpu().numpy(),
+                                status.cpu().numpy())
+        else:
+            res = P.BatchResult(yf, nacc, nrej, status)
+        if not sort:
+            return (hits[: k * 9], per[:n], k), res
+        rec = hits[: k * 9].cpu().numpy().view(HIT_DTYPE) if k else np.empty(0, dtype=HIT_DTYPE)
+        rec = rec[np.lexsort((rec["seq"], rec["traj"]))]
+        pts = np.column_stack((rec["state"][:, section.proj_i], rec["state"][:, section.proj_j])) if k else np.empty((0, 2))
+        return SectionHits(rec["traj"].copy(), rec["t"].copy(), rec["state"].copy(), pts, per[:n].cpu().numpy()), res
+
+
+class TubeSectionRunner:
+    """Pre-allocated, repeatable form of tube_section for resident batches (what bench.py times): all device
+    buffers are created once; run() launches hb_cr3bp_section and returns the hit count."""
+
+    def __init__(self, n, mu, t_eval, section, *, forward=1, flip=None, integ=None, hit_capacity=None, device=None):
+        from . import propagate as P
+        _require_cuda()
+        self.lib = L.load()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.n, self.section = int(n), section
+        te = t_eval if isinstance(t_eval, torch.Tensor) else torch.from_numpy(
+            np.ascontiguousarray(np.asarray(t_eval, dtype=np.float64)))
+        self.te = te.to(self.device).contiguous()
+        self.yf, self.nacc, self.nrej, self.status = P._alloc_out(self.n, self.device)
+        self.per = torch.zeros(max(self.n, 1), dtype=torch.int32, device=self.device)
+        self.ws = workspace(self.device)
+        self.integ = P.make_integ() if integ is None else integ
+        self.sys = P.make_sys(mu, forward, flip)
+        self.cap = int(hit_capacity) if hit_capacity is not None else max(1024, 8 * self.n)
+        self.hits = torch.empty(self.cap * 9, dtype=torch.float64, device=self.device)
+
+    def launch(self, y0_soa, stream=None):
+        rc = self.lib.hb_cr3bp_section(self.sys, self.integ, self.section, self.n, y0_soa.data_ptr(),
+                                       self.te.data_ptr(), self.te.numel(), self.hits.data_ptr(), self.cap,
+                                       self.per.data_ptr(), self.yf.data_ptr(), self.nacc.data_ptr(),
+                                       self.nrej.data_ptr(), self.status.data_ptr(), self.ws.data_ptr(),
+                                       _stream_ptr(stream))
+        L.check(rc, "hb_cr3bp_section")
+
+    def hit_count(self, stream=None):
+        nh, no = L.C.c_int64(0), L.C.c_int64(0)
+        L.check(self.lib.hb_read_hit_count(self.ws.data_ptr(), L.C.byref(nh), L.C.byref(no), _stream_ptr(stream)),
+                "hb_read_hit_count")
+        if no.value:
+            raise L.HitenB200Error(f"hit buffer overflow: {no.value} hits dropped (capacity {self.cap})")
+        return int(nh.value)

@@ -132,6 +132,17 @@ int hb_cr3bp_dense(const hb_cr3bp *sys, const hb_integ *integ, int64_t n, const 
                    const double *t_eval, int32_t m, double *states_out, int32_t *n_acc,
                    int32_t *n_rej, int32_t *status, void *workspace, void *stream);
 
+/* Fused tube + section: propagates like hb_cr3bp_dense but, instead of storing the m samples, streams
+ * them through the synodic detector (same semantics as hb_synodic_detect on the stored tube: hits are
+ * the reference's linear interpolants between grid samples, times carry the sign of sys->fwd).  This is
+ * Manifold.compute() followed by SynodicMap.compute() (system/manifold.py:226, system/maps/synodic.py:121)
+ * without the 226 KB per trajectory of dense output -- the form BASELINE config 5 (1e6 trajectories) needs.
+ * yf = the last grid sample (what states[-1] is).  Read the hit count with hb_read_hit_count.       */
+int hb_cr3bp_section(const hb_cr3bp *sys, const hb_integ *integ, const hb_section *sec, int64_t n,
+                     const double *y0_soa, const double *t_eval, int32_t m, hb_hit *hits, int64_t hit_capacity,
+                     int32_t *hits_per_traj, double *yf_soa, int32_t *n_acc, int32_t *n_rej, int32_t *status,
+                     void *workspace, void *stream);
+
 /* Propagation with a terminal plane event (event always terminal, as in the reference):
  * replaces _integrate_dop853_until_event + _dop853_refine_in_step (rk.py:2680-2803, 2006-2102).
  * On a hit status[i] = HB_TRAJ_HIT, t_hit[i] / y_hit_soa hold the refined crossing; otherwise

@@ -101,3 +101,33 @@ int ho_synodic_detect(const double *times, const double *states, int m, int dim,
 #undef G
     return s.n < cap ? s.n : cap;
 }
+
+/* Batch form for bench.py's CPU legs: hit count over n uniformly sampled trajectories (pthreads). */
+void ho_parallel_for(int64_t n, int n_threads, int64_t chunk, void (*fn)(int64_t, void *), void *ctx);
+
+typedef struct {
+    const double *times, *states; int m, dim, idx; double offset; int direction, pi, pj, refine;
+    double tol, dtt, dpt; int64_t *counts;
+} syn_ctx;
+
+static void syn_item(int64_t i, void *p)
+{
+    syn_ctx *c = (syn_ctx *)p;
+    double ht[64], hs[64 * 6];
+    c->counts[i] = ho_synodic_detect(c->times, c->states + (size_t)i * c->m * c->dim, c->m, c->dim, c->idx, c->offset,
+                                     c->direction, c->pi, c->pj, c->refine, c->tol, c->dtt, c->dpt, 0, ht, hs, 64);
+}
+
+int64_t ho_batch_synodic_count(const double *times, const double *states, int64_t n, int m, int dim, int idx,
+                               double offset, int direction, int proj_i, int proj_j, int segment_refine,
+                               double tol_on_surface, double dedup_time_tol, double dedup_point_tol, int n_threads)
+{
+    int64_t *counts = (int64_t *)__builtin_malloc(sizeof(int64_t) * (size_t)(n > 0 ? n : 1));
+    syn_ctx c = { times, states, m, dim, idx, offset, direction, proj_i, proj_j, segment_refine, tol_on_surface,
+                  dedup_time_tol, dedup_point_tol, counts };
+    ho_parallel_for(n, n_threads, 8, syn_item, &c);
+    int64_t tot = 0;
+    for (int64_t i = 0; i < n; ++i) tot += counts[i];
+    __builtin_free(counts);
+    return tot;
+}

@@ -209,3 +209,16 @@ def cm_poincare_map(ham, seeds, dt, order, max_steps, use_symplectic, section, c
                                   flags.ctypes.data_as(ip), _p(out), _p(tt), int(n_threads))
     assert rc == 0
     return flags, out, tt
+
+
+def batch_synodic_count(times, dense, idx, offset, direction, proj, segment_refine, tol_on_surface, dedup_time_tol,
+                        dedup_point_tol, n_threads=1):
+    """Total hit count over a uniformly sampled batch dense[N, m, dim] (bench.py CPU legs)."""
+    times = np.ascontiguousarray(times, dtype=np.float64)
+    dense = np.ascontiguousarray(dense, dtype=np.float64)
+    n, m, dim = dense.shape
+    f = lib().ho_batch_synodic_count
+    f.restype = C.c_int64
+    return int(f(_p(times), _p(dense), C.c_int64(n), m, dim, int(idx), C.c_double(offset), int(direction),
+                 int(proj[0]), int(proj[1]), int(segment_refine), C.c_double(tol_on_surface),
+                 C.c_double(dedup_time_tol), C.c_double(dedup_point_tol), int(n_threads)))

@@ -67,3 +67,24 @@ def test_detector_ragged_and_empty():
     assert np.array_equal(got.times[got.trajectory_indices == 2], ref_t)
     empty = synodic.detect(np.empty((0, 5, 6)), t[:5], sec)
     assert len(empty.times) == 0
+
+
+@pytest.mark.parametrize("name", ["c1", "c2"])
+def test_fused_section_equals_two_kernel_chain(name):
+    """hb_cr3bp_section (no dense tube) == hb_cr3bp_dense + hb_synodic_detect, bit for bit, and both match the
+    reference's crossing counts / points."""
+    import hiten_b200 as hb
+    from hiten_b200 import synodic
+    g = np.load(os.path.join(HERE, "golden", f"synodic_{name}.npz"))
+    mu, tf, steps, fwd = float(g["mu"]), float(g["tf"]), int(g["steps"]), int(g["forward"])
+    t_eval = np.linspace(0.0, tf, steps)
+    sec = _section(g)
+    dense = hb.cr3bp_dense(g["x0W"], mu, t_eval, forward=fwd, flip=(0, 6), keep_on_device=True)
+    two = synodic.detect(dense.states, fwd * t_eval, sec)
+    fused, res = synodic.tube_section(g["x0W"], mu, t_eval, sec, forward=fwd, flip=(0, 6))
+    assert np.array_equal(fused.trajectory_indices, two.trajectory_indices)
+    assert np.array_equal(fused.times, two.times) and np.array_equal(fused.states, two.states)
+    assert np.array_equal(fused.hits_per_traj, two.hits_per_traj)
+    assert np.array_equal(res.yf, dense.states[:, -1, :].cpu().numpy())
+    assert len(fused.times) == len(g["hit_time"])
+    assert np.abs(fused.points - g["hit_point"]).max() <= 1e-9
