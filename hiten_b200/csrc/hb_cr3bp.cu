@@ -14,157 +14,12 @@
 //   _integrate_dop853_until_event     algorithms/integrators/rk.py:2680-2803
 //   _dop853_build_dense_cache / _dop853_eval_dense / _dop853_refine_in_step   rk.py:1791-2102
 //   controller helpers                algorithms/integrators/utils.py
-#include "hb_dop853.cuh"
-#include "hb_section.cuh"
+#include "hb_cr3bp_common.cuh"
 
 namespace {
+using namespace hbc;
 
-enum { MODE_FINAL = 0, MODE_DENSE = 1, MODE_EVENT = 2, MODE_SECTION = 3 };
-
-// 256 resident threads per SM (8 warps) is what 240+ registers per thread allow; one 256-thread CTA
-// per SM measured ~8% faster than two of 128 (gpurun probe, round 1).
-#ifndef HB_BLOCK
-#define HB_BLOCK 256
-#endif
-#ifndef HB_MINBLOCKS
-#define HB_MINBLOCKS 1
-#endif
-
-struct PropParams {
-    double mu, om;
-    unsigned negmask;  // bit d set -> derivative d negated (fwd == -1 wrapper)
-    double rtol, atol, max_step, min_step;
-    long long max_attempts;
-    long long n;
-    const double *y0;
-    double t0, tf;
-    const double *tf_arr;
-    double *yf;
-    int *nacc, *nrej, *status;
-    HbWorkspace *ws;
-    const double *t_eval;
-    int m;
-    double *dense_out;
-    int ev_idx, ev_dir;
-    double ev_off, xtol, gtol;
-    double *t_hit;
-    HitSink sink;          // MODE_SECTION: detector settings + hit buffer
-    int *hits_per_traj;
-    double tsign;          // sign applied to grid times for the detector (times = forward * t_eval)
-};
-
-// ---------------------------------------------------------------------------------------------
-// Vector field.  Parity form keeps rtbp.py:65-74's operation order:
-//   r1 = sqrt((x+mu)**2 + y**2 + z**2);  r**3 -> r*(r*r)
-//   ax = 2*vy + x - (1-mu)*(x+mu)/r1**3 - mu*(x-1+mu)/r2**3   (left to right)
-// Fast form: rsqrt-based, 2 MUFU + Newton instead of 2 sqrt + 6 div.
-// ---------------------------------------------------------------------------------------------
-// NEG: 0 = forward (no sign change), 1 = every derivative negated (fwd = -1, flip all, the manifold
-// case base.py:296-300), 2 = generic per-component mask.
-template <class AR, int NEG>
-HB_DEV void crtbp_rhs(const double (&s)[6], const PropParams &p, double (&out)[6])
-{
-    const double x = s[0], y = s[1], z = s[2], vx = s[3], vy = s[4], vz = s[5];
-    const double mu = p.mu, om = p.om;
-    double ax, ay, az;
-    if constexpr (AR::parity) {
-        const double xm = AR::add(x, mu);
-        const double xo = AR::sub(x, om);
-        const double yy = AR::mul(y, y), zz = AR::mul(z, z);
-        const double r1 = AR::sqrt(AR::add(AR::add(AR::mul(xm, xm), yy), zz));
-        const double r2 = AR::sqrt(AR::add(AR::add(AR::mul(xo, xo), yy), zz));
-        const double r1c = AR::mul(r1, AR::mul(r1, r1));
-        const double r2c = AR::mul(r2, AR::mul(r2, r2));
-        // three quotients per denominator share one refined reciprocal (each stays correctly rounded)
-        const double i1 = hb_rcp_refined(r1c), i2 = hb_rcp_refined(r2c);
-        const double xq = AR::add(AR::sub(x, 1.0), mu);  // (x - 1 + mu)
-        ax = AR::sub(AR::sub(AR::add(AR::mul(2.0, vy), x), hb_div_with(AR::mul(om, xm), r1c, i1)),
-                     hb_div_with(AR::mul(mu, xq), r2c, i2));
-        ay = AR::sub(AR::sub(AR::add(AR::mul(-2.0, vx), y), hb_div_with(AR::mul(om, y), r1c, i1)),
-                     hb_div_with(AR::mul(mu, y), r2c, i2));
-        az = AR::sub(hb_div_with(AR::mul(-om, z), r1c, i1), hb_div_with(AR::mul(mu, z), r2c, i2));
-    } else {
-        const double xm = x + mu;
-        const double xo = x - om;
-        const double yz = fma(y, y, z * z);
-        const double i1 = hb_rsqrt_fast(fma(xm, xm, yz));
-        const double i2 = hb_rsqrt_fast(fma(xo, xo, yz));
-        const double c1 = om * (i1 * i1 * i1);
-        const double c2 = mu * (i2 * i2 * i2);
-        const double cs = c1 + c2;
-        ax = fma(2.0, vy, x) - fma(c1, xm, c2 * xo);
-        ay = fma(-2.0, vx, y) - cs * y;
-        az = -cs * z;
-    }
-    if constexpr (NEG == 0) {
-        out[0] = vx; out[1] = vy; out[2] = vz; out[3] = ax; out[4] = ay; out[5] = az;
-    } else if constexpr (NEG == 1) {
-        out[0] = -vx; out[1] = -vy; out[2] = -vz; out[3] = -ax; out[4] = -ay; out[5] = -az;
-    } else {
-        out[0] = (p.negmask & 1u) ? -vx : vx;
-        out[1] = (p.negmask & 2u) ? -vy : vy;
-        out[2] = (p.negmask & 4u) ? -vz : vz;
-        out[3] = (p.negmask & 8u) ? -ax : ax;
-        out[4] = (p.negmask & 16u) ? -ay : ay;
-        out[5] = (p.negmask & 32u) ? -az : az;
-    }
-}
-
-template <class AR, int NEG>
-struct Cr3bpRhs {
-    const PropParams &p;
-    HB_DEV void operator()(const double (&y)[6], double (&dy)[6]) const { crtbp_rhs<AR, NEG>(y, p, dy); }
-};
-
-// Component select without dynamic register-array indexing (which would force local memory).
-HB_DEV double pick6(const double (&v)[6], int i)
-{
-    double r = v[0];
-#pragma unroll
-    for (int d = 1; d < 6; ++d) r = (i == d) ? v[d] : r;
-    return r;
-}
-
-// scale0, d0, d1, h0 (rk.py:2445-2448; utils.py:127-157).  The reference's np.linalg.norm is
-// OpenBLAS dnrm2 (x87 extended accumulation); a double-double sum of squares stands in for it.
-HB_DEV double norm2_ext6(const double (&v)[6])
-{
-    double hi = 0.0, lo = 0.0;
-#pragma unroll
-    for (int d = 0; d < 6; ++d) {
-        const double ph = __dmul_rn(v[d], v[d]);
-        const double pl = __fma_rn(v[d], v[d], -ph);           // exact product = ph + pl
-        const double s = __dadd_rn(hi, ph);                     // two-sum(hi, ph)
-        const double bb = __dsub_rn(s, hi);
-        const double e = __dadd_rn(__dsub_rn(hi, __dsub_rn(s, bb)), __dsub_rn(ph, bb));
-        hi = s;
-        lo = __dadd_rn(lo, __dadd_rn(e, pl));
-    }
-    const double s = __dadd_rn(hi, lo);
-    const double r = __dsqrt_rn(s);
-    // one Newton correction with the residual taken in double-double: r + (S - r*r) / (2r)
-    const double res = __dadd_rn(__fma_rn(-r, r, hi), lo);
-    return __dadd_rn(r, __ddiv_rn(res, __dmul_rn(2.0, r)));
-}
-
-template <class AR>
-HB_DEV double initial_step(const double (&y)[6], const double (&f)[6], const PropParams &p)
-{
-    double a[6], b[6];
-#pragma unroll
-    for (int d = 0; d < 6; ++d) {
-        const double sc = AR::madd(p.rtol, fabs(y[d]), p.atol);
-        a[d] = AR::div(y[d], sc);
-        b[d] = AR::div(f[d], sc);
-    }
-    const double sq = AR::sqrt(6.0);
-    const double d0 = AR::div(norm2_ext6(a), sq);
-    const double d1 = AR::div(norm2_ext6(b), sq);
-    double h = (d0 < 1.0e-5 || d1 < 1.0e-5) ? 1.0e-6 : AR::div(AR::mul(0.01, d0), d1);
-    if (h > p.max_step) h = p.max_step;
-    if (h < p.min_step) h = p.min_step;
-    return h;
-}
+enum { MODE_FINAL = 0, MODE_DENSE = 1, MODE_EVENT = 2 };
 
 // ---------------------------------------------------------------------------------------------
 // The persistent-thread kernel.
@@ -179,11 +34,6 @@ __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) k_dop853_6(const PropP
     long long attempts = 0;
     int nacc = 0, nrej = 0, cursor = 0;
     bool have = false, exhausted = false;
-    // MODE_SECTION: previous grid sample, its event value and the one before, de-duplication state
-    double xs_prev[6], gs_prev = 0.0, gs_prev2 = 0.0;
-    Dedup dd{0.0, 0.0, 0.0, 0};
-    bool sec_alive = true;
-
     for (;;) {
         if (!have && !exhausted) {
             idx = hb_fetch_index(p.ws);
@@ -196,12 +46,10 @@ __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) k_dop853_6(const PropP
                 h = initial_step<AR>(y, k[0], p);
                 err_prev = -1.0;
                 nacc = 0; nrej = 0; cursor = 0; attempts = 0;
-                if (MODE == MODE_SECTION) { dd = Dedup{0.0, 0.0, 0.0, 0}; sec_alive = true; }
                 if (MODE == MODE_EVENT) g_prev = AR::sub(pick6(y, p.ev_idx), p.ev_off);
                 have = true;
                 if (!((t - tf) < 0.0)) {
                     // zero-length span: nothing to integrate
-                    if (MODE == MODE_SECTION && p.hits_per_traj) p.hits_per_traj[idx] = 0;
                     if (MODE != MODE_DENSE) {
 #pragma unroll
                         for (int d = 0; d < 6; ++d) p.yf[(long long)d * p.n + idx] = y[d];
@@ -291,45 +139,6 @@ __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) k_dop853_6(const PropP
                     }
                 }
                 if (last) fin = HB_TRAJ_OK;
-            } else if (MODE == MODE_SECTION) {
-                // Reference semantics without materialising the tube: the dense samples on the t_eval grid are
-                // produced exactly as in MODE_DENSE and streamed through the synodic detector (segment k is
-                // processed when sample k+1 exists), so hits are the reference's linear interpolants.
-                if (cursor < p.m && (last || p.t_eval[cursor] < t_new)) {
-                    const double hseg = AR::sub(t_new, t);
-                    double F[7][6], yo[6];
-                    if (hseg != 0.0) dense_cache<AR>(y, yh, hseg, k, F, rhs);
-                    while (cursor < p.m) {
-                        const double tq = p.t_eval[cursor];
-                        if (!(last || tq < t_new)) break;
-                        if (hseg == 0.0) {
-#pragma unroll
-                            for (int d = 0; d < 6; ++d) yo[d] = y[d];
-                        } else {
-                            dense_eval<AR>(y, F, AR::div(AR::sub(tq, t), hseg), yo);
-                        }
-                        const double g_now = __dsub_rn(pick(yo, p.sink.sec.idx), p.sink.sec.offset);
-                        if (cursor > 0 && sec_alive) {
-                            const bool same = (gs_prev > 0.0 && g_now > 0.0) || (gs_prev < 0.0 && g_now < 0.0);
-                            if (!same || fabs(gs_prev) < p.sink.sec.tol_on_surface) {
-                                const double t0s = __dmul_rn(p.tsign, p.t_eval[cursor - 1]);
-                                const double t1s = __dmul_rn(p.tsign, tq);
-                                sec_alive = process_segment(p.sink, dd, idx, 0, cursor > 1, gs_prev2, t0s, t1s, xs_prev, yo);
-                            }
-                        }
-                        gs_prev2 = gs_prev;
-                        gs_prev = g_now;
-#pragma unroll
-                        for (int d = 0; d < 6; ++d) xs_prev[d] = yo[d];
-                        ++cursor;
-                    }
-                }
-                if (last) {
-#pragma unroll
-                    for (int d = 0; d < 6; ++d) p.yf[(long long)d * p.n + idx] = xs_prev[d];
-                    if (p.hits_per_traj) p.hits_per_traj[idx] = dd.n;
-                    fin = HB_TRAJ_OK;
-                }
             } else {  // MODE_FINAL: the dense interpolant at tf on the last segment
                 if (last) {
                     const double hseg = AR::sub(t_new, t);
@@ -374,7 +183,6 @@ __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) k_dop853_6(const PropP
                     for (int d = 0; d < 6; ++d) p.yf[(long long)d * p.n + idx] = y[d];
                 }
                 if (MODE == MODE_EVENT) p.t_hit[idx] = t;
-                if (MODE == MODE_SECTION && p.hits_per_traj) p.hits_per_traj[idx] = dd.n;
             }
         }
         if (fin >= 0) {
@@ -387,38 +195,6 @@ __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) k_dop853_6(const PropP
 // ---------------------------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------------------------
-int fill_params(const hb_cr3bp *sys, const hb_integ *integ, PropParams &p)
-{
-    if (!sys || !integ) return HB_ERR_BADARG;
-    if (integ->method != HB_DOP853) return HB_ERR_UNSUPPORTED;
-    if (integ->arith != HB_ARITH_PARITY && integ->arith != HB_ARITH_FAST) return HB_ERR_BADARG;
-    p.mu = sys->mu;
-    p.om = 1.0 - sys->mu;
-    p.negmask = 0;
-    if (sys->fwd < 0) {
-        int lo = sys->flip_lo, hi = sys->flip_hi;
-        if (lo < 0) { lo = 0; hi = 6; }
-        if (hi > 6 || lo > hi) return HB_ERR_BADARG;
-        for (int d = lo; d < hi; ++d) p.negmask |= 1u << d;
-    }
-    p.rtol = integ->rtol; p.atol = integ->atol;
-    p.max_step = integ->max_step; p.min_step = integ->min_step;
-    p.max_attempts = integ->max_attempts > 0 ? integ->max_attempts : 2147483647LL;
-    return HB_OK;
-}
-
-int g_sm_count = 0;
-int sm_count()
-{
-    if (g_sm_count == 0) {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
-        g_sm_count = n;
-    }
-    return g_sm_count;
-}
-
 template <class AR, int MODE>
 int launch_neg(const PropParams &p, unsigned grid, cudaStream_t st)
 {
@@ -518,36 +294,6 @@ int hb_cr3bp_event(const hb_cr3bp *sys, const hb_integ *integ, const hb_event *e
     p.ev_idx = ev->idx; p.ev_dir = ev->direction; p.ev_off = ev->offset; p.xtol = ev->xtol; p.gtol = ev->gtol;
     p.ws = (HbWorkspace *)workspace;
     return launch<MODE_EVENT>(p, integ->arith, (cudaStream_t)stream);
-}
-
-int hb_cr3bp_section(const hb_cr3bp *sys, const hb_integ *integ, const hb_section *sec, int64_t n,
-                     const double *y0_soa, const double *t_eval, int32_t m, hb_hit *hits, int64_t hit_capacity,
-                     int32_t *hits_per_traj, double *yf_soa, int32_t *n_acc, int32_t *n_rej, int32_t *status,
-                     void *workspace, void *stream)
-{
-    PropParams p{};
-    int rc = fill_params(sys, integ, p);
-    if (rc != HB_OK) return rc;
-    if (!sec || sec->idx < 0 || sec->idx > 5 || sec->proj_i < 0 || sec->proj_i > 5 || sec->proj_j < 0 ||
-        sec->proj_j > 5 || sec->segment_refine < 0 || hit_capacity < 0)
-        return HB_ERR_BADARG;
-    if (n < 0 || m < 2 || !workspace || !t_eval ||
-        (n > 0 && (!y0_soa || !yf_soa || !n_acc || !n_rej || !status || (hit_capacity > 0 && !hits))))
-        return HB_ERR_BADARG;
-    cudaStream_t st = (cudaStream_t)stream;
-    if (n == 0) { HB_CUDA_TRY(cudaMemsetAsync(workspace, 0, sizeof(HbWorkspace), st)); return HB_OK; }
-    double ends[2];
-    HB_CUDA_TRY(cudaMemcpyAsync(&ends[0], t_eval, sizeof(double), cudaMemcpyDeviceToHost, st));
-    HB_CUDA_TRY(cudaMemcpyAsync(&ends[1], t_eval + (m - 1), sizeof(double), cudaMemcpyDeviceToHost, st));
-    HB_CUDA_TRY(cudaStreamSynchronize(st));
-    p.n = n; p.y0 = y0_soa; p.t0 = ends[0]; p.tf = ends[1]; p.tf_arr = nullptr;
-    p.yf = yf_soa; p.nacc = n_acc; p.nrej = n_rej; p.status = status;
-    p.t_eval = t_eval; p.m = m;
-    p.ws = (HbWorkspace *)workspace;
-    p.sink.sec = *sec; p.sink.hits = hits; p.sink.capacity = hit_capacity; p.sink.ws = p.ws;
-    p.hits_per_traj = hits_per_traj;
-    p.tsign = sys->fwd < 0 ? -1.0 : 1.0;
-    return launch<MODE_SECTION>(p, integ->arith, st);
 }
 
 }  // extern "C"

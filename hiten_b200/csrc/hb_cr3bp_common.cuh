@@ -1,0 +1,188 @@
+// hb_cr3bp_common.cuh -- pieces shared by the 6-state DOP853 kernels (hb_cr3bp.cu, hb_cr3bp_section.cu):
+// kernel parameters, the CR3BP vector field, initial-step heuristic, host-side parameter filling.
+#pragma once
+#include "hb_dop853.cuh"
+#include "hb_section.cuh"
+
+namespace hbc {
+
+
+
+
+// 256 resident threads per SM (8 warps) is what 240+ registers per thread allow; one 256-thread CTA
+// per SM measured ~8% faster than two of 128 (gpurun probe, round 1).
+#ifndef HB_BLOCK
+#define HB_BLOCK 256
+#endif
+#ifndef HB_MINBLOCKS
+#define HB_MINBLOCKS 1
+#endif
+
+struct PropParams {
+    double mu, om;
+    unsigned negmask;  // bit d set -> derivative d negated (fwd == -1 wrapper)
+    double rtol, atol, max_step, min_step;
+    long long max_attempts;
+    long long n;
+    const double *y0;
+    double t0, tf;
+    const double *tf_arr;
+    double *yf;
+    int *nacc, *nrej, *status;
+    HbWorkspace *ws;
+    const double *t_eval;
+    int m;
+    double *dense_out;
+    int ev_idx, ev_dir;
+    double ev_off, xtol, gtol;
+    double *t_hit;
+    HitSink sink;          // MODE_SECTION: detector settings + hit buffer
+    int *hits_per_traj;
+    double tsign;          // sign applied to grid times for the detector (times = forward * t_eval)
+    double inv_grid_dt;    // (m-1)/(t_eval[m-1]-t_eval[0]): first guess when locating grid samples
+};
+
+// ---------------------------------------------------------------------------------------------
+// Vector field.  Parity form keeps rtbp.py:65-74's operation order:
+//   r1 = sqrt((x+mu)**2 + y**2 + z**2);  r**3 -> r*(r*r)
+//   ax = 2*vy + x - (1-mu)*(x+mu)/r1**3 - mu*(x-1+mu)/r2**3   (left to right)
+// Fast form: rsqrt-based, 2 MUFU + Newton instead of 2 sqrt + 6 div.
+// ---------------------------------------------------------------------------------------------
+// NEG: 0 = forward (no sign change), 1 = every derivative negated (fwd = -1, flip all, the manifold
+// case base.py:296-300), 2 = generic per-component mask.
+template <class AR, int NEG>
+HB_DEV void crtbp_rhs(const double (&s)[6], const PropParams &p, double (&out)[6])
+{
+    const double x = s[0], y = s[1], z = s[2], vx = s[3], vy = s[4], vz = s[5];
+    const double mu = p.mu, om = p.om;
+    double ax, ay, az;
+    if constexpr (AR::parity) {
+        const double xm = AR::add(x, mu);
+        const double xo = AR::sub(x, om);
+        const double yy = AR::mul(y, y), zz = AR::mul(z, z);
+        const double r1 = AR::sqrt(AR::add(AR::add(AR::mul(xm, xm), yy), zz));
+        const double r2 = AR::sqrt(AR::add(AR::add(AR::mul(xo, xo), yy), zz));
+        const double r1c = AR::mul(r1, AR::mul(r1, r1));
+        const double r2c = AR::mul(r2, AR::mul(r2, r2));
+        // three quotients per denominator share one refined reciprocal (each stays correctly rounded)
+        const double i1 = hb_rcp_refined(r1c), i2 = hb_rcp_refined(r2c);
+        const double xq = AR::add(AR::sub(x, 1.0), mu);  // (x - 1 + mu)
+        ax = AR::sub(AR::sub(AR::add(AR::mul(2.0, vy), x), hb_div_with(AR::mul(om, xm), r1c, i1)),
+                     hb_div_with(AR::mul(mu, xq), r2c, i2));
+        ay = AR::sub(AR::sub(AR::add(AR::mul(-2.0, vx), y), hb_div_with(AR::mul(om, y), r1c, i1)),
+                     hb_div_with(AR::mul(mu, y), r2c, i2));
+        az = AR::sub(hb_div_with(AR::mul(-om, z), r1c, i1), hb_div_with(AR::mul(mu, z), r2c, i2));
+    } else {
+        const double xm = x + mu;
+        const double xo = x - om;
+        const double yz = fma(y, y, z * z);
+        const double i1 = hb_rsqrt_fast(fma(xm, xm, yz));
+        const double i2 = hb_rsqrt_fast(fma(xo, xo, yz));
+        const double c1 = om * (i1 * i1 * i1);
+        const double c2 = mu * (i2 * i2 * i2);
+        const double cs = c1 + c2;
+        ax = fma(2.0, vy, x) - fma(c1, xm, c2 * xo);
+        ay = fma(-2.0, vx, y) - cs * y;
+        az = -cs * z;
+    }
+    if constexpr (NEG == 0) {
+        out[0] = vx; out[1] = vy; out[2] = vz; out[3] = ax; out[4] = ay; out[5] = az;
+    } else if constexpr (NEG == 1) {
+        out[0] = -vx; out[1] = -vy; out[2] = -vz; out[3] = -ax; out[4] = -ay; out[5] = -az;
+    } else {
+        out[0] = (p.negmask & 1u) ? -vx : vx;
+        out[1] = (p.negmask & 2u) ? -vy : vy;
+        out[2] = (p.negmask & 4u) ? -vz : vz;
+        out[3] = (p.negmask & 8u) ? -ax : ax;
+        out[4] = (p.negmask & 16u) ? -ay : ay;
+        out[5] = (p.negmask & 32u) ? -az : az;
+    }
+}
+
+template <class AR, int NEG>
+struct Cr3bpRhs {
+    const PropParams &p;
+    HB_DEV void operator()(const double (&y)[6], double (&dy)[6]) const { crtbp_rhs<AR, NEG>(y, p, dy); }
+};
+
+// Component select without dynamic register-array indexing (which would force local memory).
+HB_DEV double pick6(const double (&v)[6], int i)
+{
+    double r = v[0];
+#pragma unroll
+    for (int d = 1; d < 6; ++d) r = (i == d) ? v[d] : r;
+    return r;
+}
+
+// scale0, d0, d1, h0 (rk.py:2445-2448; utils.py:127-157).  The reference's np.linalg.norm is
+// OpenBLAS dnrm2 (x87 extended accumulation); a double-double sum of squares stands in for it.
+HB_DEV double norm2_ext6(const double (&v)[6])
+{
+    double hi = 0.0, lo = 0.0;
+#pragma unroll
+    for (int d = 0; d < 6; ++d) {
+        const double ph = __dmul_rn(v[d], v[d]);
+        const double pl = __fma_rn(v[d], v[d], -ph);           // exact product = ph + pl
+        const double s = __dadd_rn(hi, ph);                     // two-sum(hi, ph)
+        const double bb = __dsub_rn(s, hi);
+        const double e = __dadd_rn(__dsub_rn(hi, __dsub_rn(s, bb)), __dsub_rn(ph, bb));
+        hi = s;
+        lo = __dadd_rn(lo, __dadd_rn(e, pl));
+    }
+    const double s = __dadd_rn(hi, lo);
+    const double r = __dsqrt_rn(s);
+    // one Newton correction with the residual taken in double-double: r + (S - r*r) / (2r)
+    const double res = __dadd_rn(__fma_rn(-r, r, hi), lo);
+    return __dadd_rn(r, __ddiv_rn(res, __dmul_rn(2.0, r)));
+}
+
+template <class AR>
+HB_DEV double initial_step(const double (&y)[6], const double (&f)[6], const PropParams &p)
+{
+    double a[6], b[6];
+#pragma unroll
+    for (int d = 0; d < 6; ++d) {
+        const double sc = AR::madd(p.rtol, fabs(y[d]), p.atol);
+        a[d] = AR::div(y[d], sc);
+        b[d] = AR::div(f[d], sc);
+    }
+    const double sq = AR::sqrt(6.0);
+    const double d0 = AR::div(norm2_ext6(a), sq);
+    const double d1 = AR::div(norm2_ext6(b), sq);
+    double h = (d0 < 1.0e-5 || d1 < 1.0e-5) ? 1.0e-6 : AR::div(AR::mul(0.01, d0), d1);
+    if (h > p.max_step) h = p.max_step;
+    if (h < p.min_step) h = p.min_step;
+    return h;
+}
+
+
+inline int fill_params(const hb_cr3bp *sys, const hb_integ *integ, PropParams &p)
+{
+    if (!sys || !integ) return HB_ERR_BADARG;
+    if (integ->method != HB_DOP853) return HB_ERR_UNSUPPORTED;
+    if (integ->arith != HB_ARITH_PARITY && integ->arith != HB_ARITH_FAST) return HB_ERR_BADARG;
+    p.mu = sys->mu;
+    p.om = 1.0 - sys->mu;
+    p.negmask = 0;
+    if (sys->fwd < 0) {
+        int lo = sys->flip_lo, hi = sys->flip_hi;
+        if (lo < 0) { lo = 0; hi = 6; }
+        if (hi > 6 || lo > hi) return HB_ERR_BADARG;
+        for (int d = lo; d < hi; ++d) p.negmask |= 1u << d;
+    }
+    p.rtol = integ->rtol; p.atol = integ->atol;
+    p.max_step = integ->max_step; p.min_step = integ->min_step;
+    p.max_attempts = integ->max_attempts > 0 ? integ->max_attempts : 2147483647LL;
+    return HB_OK;
+}
+
+inline int sm_count()
+{
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+    return n;
+}
+
+
+}  // namespace hbc

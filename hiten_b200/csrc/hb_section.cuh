@@ -117,3 +117,96 @@ HB_DEV bool process_segment(const HitSink &p, Dedup &dd, long long traj, int lan
     return true;
 }
 
+
+// Warp-cooperative form of process_segment for the fused section kernel: every lane calls it with the SAME
+// (broadcast) segment values; the r+1 sub-intervals of _detect_with_segment_refine are tested 32 at a time
+// instead of in a 51-iteration scalar loop, and only the owner lane (is_owner) materialises the two end
+// states -- lazily, through `eval`, and only when the segment actually produces a candidate -- and pushes
+// hits.  Arithmetic per sub-interval is unchanged, candidates are pushed in the reference's order.
+//   eval(which, out): which = 0 -> state at the left sample, 1 -> at the right sample (owner lane only).
+template <class EVAL>
+HB_DEV bool process_segment_coop(const HitSink &p, Dedup &dd, long long traj, int lane, bool is_owner, bool has_prev,
+                                 double g_prev, double gk, double gk1, double t0, double t1, EVAL eval)
+{
+    const int dir = p.sec.direction;
+    bool accept_left = false;
+    if (fabs(gk) < p.sec.tol_on_surface) {
+        if (dir == 0) accept_left = true;
+        else if (dir > 0) accept_left = (gk1 >= 0.0) || (has_prev && g_prev <= 0.0);
+        else accept_left = (gk1 <= 0.0) || (has_prev && g_prev >= 0.0);
+    }
+    const int r = p.sec.segment_refine;
+    bool alive = true, have_states = false;
+    double x0[6], x1[6], xh[6];
+    if (r > 0) {
+        const double step = __ddiv_rn(1.0, (double)(r + 1));
+        // highest sub-interval index that passes the reference's `s_hi > 1.0 + 1e-15 -> break` test
+        if (accept_left && is_owner) {
+            eval(0, x0); eval(1, x1); have_states = true;
+            alive = push_hit(p, dd, traj, t0, x0, 0);
+        }
+        for (int base = 0; base <= r; base += 32) {
+            const int mm = base + lane;
+            bool crosses = false;
+            double g_lo = 0.0, g_hi = 0.0, s_lo = 0.0, s_hi = 0.0;
+            bool stop = false;
+            if (mm <= r) {
+                s_lo = __dmul_rn((double)mm, step);
+                s_hi = __dmul_rn((double)(mm + 1), step);
+                stop = s_hi > 1.0 + 1e-15;
+                if (!stop && !(accept_left && mm == 0)) {
+                    g_lo = __dadd_rn(__dmul_rn(__dsub_rn(1.0, s_lo), gk), __dmul_rn(s_lo, gk1));
+                    g_hi = __dadd_rn(__dmul_rn(__dsub_rn(1.0, s_hi), gk), __dmul_rn(s_hi, gk1));
+                    if (dir == 0) crosses = (__dmul_rn(g_lo, g_hi) <= 0.0) && (g_lo != g_hi);
+                    else if (dir > 0) crosses = (g_lo < 0.0) && (g_hi >= 0.0);
+                    else crosses = (g_lo > 0.0) && (g_hi <= 0.0);
+                }
+            }
+            // the reference BREAKS at the first sub-interval with s_hi > 1 + 1e-15: ignore everything after it
+            const unsigned stopm = __ballot_sync(0xffffffffu, stop);
+            unsigned cm = __ballot_sync(0xffffffffu, crosses);
+            if (stopm) cm &= (1u << (__ffs(stopm) - 1)) - 1u;
+            while (cm) {
+                const int i = __ffs(cm) - 1;
+                cm &= cm - 1;
+                const double a_lo = shfl_d(g_lo, i), a_hi = shfl_d(g_hi, i);
+                const double b_lo = shfl_d(s_lo, i), b_hi = shfl_d(s_hi, i);
+                if (is_owner && alive) {
+                    double s_star;
+                    if (a_lo == a_hi) s_star = __dmul_rn(0.5, __dadd_rn(b_lo, b_hi));
+                    else {
+                        double al = __ddiv_rn(a_lo, __dsub_rn(a_lo, a_hi));
+                        al = fmin(1.0, fmax(0.0, al));
+                        s_star = __dadd_rn(b_lo, __dmul_rn(al, __dsub_rn(b_hi, b_lo)));
+                    }
+                    if (!have_states) { eval(0, x0); eval(1, x1); have_states = true; }
+                    const double th = __dadd_rn(__dmul_rn(__dsub_rn(1.0, s_star), t0), __dmul_rn(s_star, t1));
+#pragma unroll
+                    for (int d = 0; d < 6; ++d) xh[d] = __dadd_rn(x0[d], __dmul_rn(s_star, __dsub_rn(x1[d], x0[d])));
+                    alive = push_hit(p, dd, traj, th, xh, 0);
+                }
+            }
+            if (stopm) break;
+        }
+    } else if (is_owner) {
+        if (accept_left) {
+            eval(0, x0);
+            alive = push_hit(p, dd, traj, t0, x0, 0);
+        } else {
+            bool crosses;
+            if (dir == 0) crosses = (__dmul_rn(gk, gk1) <= 0.0) && (gk != gk1);
+            else if (dir > 0) crosses = (gk < 0.0) && (gk1 >= 0.0);
+            else crosses = (gk > 0.0) && (gk1 <= 0.0);
+            if (crosses) {
+                double al = __ddiv_rn(gk, __dsub_rn(gk, gk1));
+                al = fmin(1.0, fmax(0.0, al));
+                eval(0, x0); eval(1, x1);
+                const double th = __dadd_rn(__dmul_rn(__dsub_rn(1.0, al), t0), __dmul_rn(al, t1));
+#pragma unroll
+                for (int d = 0; d < 6; ++d) xh[d] = __dadd_rn(x0[d], __dmul_rn(al, __dsub_rn(x1[d], x0[d])));
+                alive = push_hit(p, dd, traj, th, xh, 0);
+            }
+        }
+    }
+    return alive;
+}
