@@ -1,0 +1,75 @@
+"""CPU, world_size 2 over gloo: the index sharding + final gather used by bench.py --gpus N.
+
+The data path has no collective (trajectories are independent); the only exchange is the gather of end states
+and per-trajectory hit counts to rank 0.  Here each rank propagates its shard with the CPU oracle (the GPU kernels
+are covered by the -m gpu tests) and rank 0 checks that the gathered, re-interleaved result equals the unsharded run.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+
+
+def _worker(rank, world, port, out_path):
+    sys.path.insert(0, REPO)
+    sys.path.insert(0, HERE)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import bench
+    import oracle_lib as O
+    n = 24
+    ics, mu = bench.build_ics(n, rank, world)                     # ics_all[rank::world][:n]
+    s = O.system(O.SYS_CR3BP6, mu, fwd=-1, flip=(0, 6))
+    yf, counts = O.batch_final(s, O.DOP853, O.default_tol(), ics, 0.0, 1.0, 1)
+    t_yf = torch.from_numpy(np.ascontiguousarray(yf.T))            # [6, n] like the kernels' SoA output
+    t_steps = torch.from_numpy(counts.sum(axis=1).astype(np.int32))
+    g_yf = [torch.empty_like(t_yf) for _ in range(world)] if rank == 0 else None
+    g_st = [torch.empty_like(t_steps) for _ in range(world)] if rank == 0 else None
+    dist.gather(t_yf, g_yf, dst=0)
+    dist.gather(t_steps, g_st, dst=0)
+    tt = torch.tensor([0.5 + rank, float(t_steps.sum())], dtype=torch.float64)
+    tmax, tsum = tt.clone(), tt.clone()
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)                    # time: max over ranks
+    dist.all_reduce(tsum, op=dist.ReduceOp.SUM)                    # work: sum over ranks
+    if rank == 0:
+        full = np.empty((n * world, 6))
+        for r in range(world):
+            full[r::world] = g_yf[r].numpy().T
+        np.savez(out_path, yf=full, steps=int(tsum[1].item()), tmax=float(tmax[0].item()))
+    dist.destroy_process_group()
+
+
+def test_two_rank_shard_and_gather(tmp_path):
+    sys.path.insert(0, REPO)
+    import bench
+    import oracle_lib as O
+    O.build()
+    world, n = 2, 24
+    out = str(tmp_path / "gathered.npz")
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+    got = np.load(out)
+    ics, mu = bench.build_ics(n * world)                           # the unsharded batch
+    s = O.system(O.SYS_CR3BP6, mu, fwd=-1, flip=(0, 6))
+    yf, counts = O.batch_final(s, O.DOP853, O.default_tol(), ics, 0.0, 1.0, 1)
+    assert np.array_equal(got["yf"], yf)                           # shards re-interleave to the unsharded result
+    assert int(got["steps"]) == int(counts.sum())
+    assert float(got["tmax"]) == 1.5                               # MAX over ranks, not rank 0's time
+
+
+def test_shards_partition_the_batch():
+    sys.path.insert(0, REPO)
+    import bench
+    full, _ = bench.build_ics(64)
+    parts = [bench.build_ics(16, r, 4)[0] for r in range(4)]
+    rebuilt = np.empty_like(full)
+    for r in range(4):
+        rebuilt[r::4] = parts[r]
+    assert np.array_equal(rebuilt, full)
