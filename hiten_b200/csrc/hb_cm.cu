@@ -15,7 +15,7 @@
 //   _integrate_rk_ham, _detect_crossing, _poincare_step, _poincare_map
 //                                           algorithms/poincare/centermanifold/backend.py:35-382
 //   _hermite_scalar                         algorithms/poincare/utils.py:54-97
-#include "hb_common.cuh"
+#include "hb_rkgen.cuh"
 
 #include <cmath>
 
@@ -98,59 +98,13 @@ HB_DEV void cm_rhs(const CmParams &p, double *pw, const TermMeta *terms, const d
     dy[3] = -g[0]; dy[4] = -g[1]; dy[5] = -g[2];
 }
 
-// ---- fixed-step explicit RK with compile-time tableau --------------------------------------------
-struct TabRK4 { static constexpr int S = 4; static constexpr double a(int i, int j) { return HB_RK4_A[i][j]; } static constexpr double b(int i) { return HB_RK4_B[i]; } };
-struct TabRK6 { static constexpr int S = 7; static constexpr double a(int i, int j) { return HB_RK6_A[i][j]; } static constexpr double b(int i) { return HB_RK6_B[i]; } };
-struct TabRK8 { static constexpr int S = 13; static constexpr double a(int i, int j) { return HB_RK8_A[i][j]; } static constexpr double b(int i) { return HB_RK8_B[i]; } };
-
-template <class AR, class TAB, int I, int J>
-HB_DEV void g_stage_acc(double (&ys)[6], const double (&k)[TAB::S][6], double h)
-{
-    if constexpr (J < I) {
-        if constexpr (TAB::a(I, J) != 0.0) {
-            constexpr double a = TAB::a(I, J);
-            const double ha = AR::mul(h, a);
-#pragma unroll
-            for (int d = 0; d < 6; ++d) ys[d] = AR::madd(ha, k[J][d], ys[d]);
-        }
-        g_stage_acc<AR, TAB, I, J + 1>(ys, k, h);
-    }
-}
-// is stage I referenced by a later stage or by B?  (the 7th DOPRI5 stage of "RK6" is not)
-template <class TAB, int I, int R>
-constexpr bool g_stage_used()
-{
-    if constexpr (R >= TAB::S) return TAB::b(I) != 0.0;
-    else return (TAB::a(R, I) != 0.0) || g_stage_used<TAB, I, R + 1>();
-}
-template <class AR, class TAB, int I>
-HB_DEV void g_run_stages(const CmParams &p, double *pw, const TermMeta *terms, const double (&y)[6],
-                         double (&k)[TAB::S][6], double h)
-{
-    if constexpr (I < TAB::S) {
-        if constexpr (g_stage_used<TAB, I, I + 1>()) {
-            double ys[6];
-#pragma unroll
-            for (int d = 0; d < 6; ++d) ys[d] = y[d];
-            g_stage_acc<AR, TAB, I, 0>(ys, k, h);
-            cm_rhs<AR>(p, pw, terms, ys, k[I]);
-        }
-        g_run_stages<AR, TAB, I + 1>(p, pw, terms, y, k, h);
-    }
-}
-template <class AR, class TAB, int J>
-HB_DEV void g_high_acc(double (&yn)[6], const double (&k)[TAB::S][6], double h)
-{
-    if constexpr (J < TAB::S) {
-        if constexpr (TAB::b(J) != 0.0) {
-            constexpr double b = TAB::b(J);
-            const double hb = AR::mul(h, b);
-#pragma unroll
-            for (int d = 0; d < 6; ++d) yn[d] = AR::madd(hb, k[J][d], yn[d]);
-        }
-        g_high_acc<AR, TAB, J + 1>(yn, k, h);
-    }
-}
+template <class AR>
+struct CmRhs {
+    const CmParams &p;
+    double *pw;
+    const TermMeta *terms;
+    HB_DEV void operator()(const double (&y)[6], double (&dy)[6]) const { cm_rhs<AR>(p, pw, terms, y, dy); }
+};
 
 // _hermite_scalar (poincare/utils.py:93-97)
 template <class AR>
@@ -237,7 +191,7 @@ __global__ void __launch_bounds__(CM_BLOCK) k_cm_map(const CmParams p)
                 double k[TAB::S][6];
 #pragma unroll
                 for (int d = 0; d < 6; ++d) k[0][d] = ro[d];
-                g_run_stages<AR, TAB, 1>(p, pw, terms, so, k, dt);
+                g_run_stages<AR, TAB, CmRhs<AR>, 1>(CmRhs<AR>{p, pw, terms}, so, k, dt);
 #pragma unroll
                 for (int d = 0; d < 6; ++d) sn[d] = so[d];
                 g_high_acc<AR, TAB, 0>(sn, k, dt);

@@ -241,7 +241,6 @@ int hb_cr3bp_propagate(const hb_cr3bp *sys, const hb_integ *integ, int64_t n, co
                        double *yf_soa, int32_t *n_acc, int32_t *n_rej, int32_t *status,
                        void *workspace, void *stream)
 {
-    (void)n_fixed_steps;
     PropParams p{};
     int rc = fill_params(sys, integ, p);
     if (rc != HB_OK) return rc;
@@ -250,6 +249,9 @@ int hb_cr3bp_propagate(const hb_cr3bp *sys, const hb_integ *integ, int64_t n, co
     p.n = n; p.y0 = y0_soa; p.t0 = t0; p.tf = tf; p.tf_arr = tf_per_traj;
     p.yf = yf_soa; p.nacc = n_acc; p.nrej = n_rej; p.status = status;
     p.ws = (HbWorkspace *)workspace;
+    if (integ->method != HB_DOP853)
+        return hb_rk_dispatch(p, integ->method, integ->arith, 0, n_fixed_steps > 0 ? n_fixed_steps : integ->n_fixed_steps,
+                              (cudaStream_t)stream);
     return launch<MODE_FINAL>(p, integ->arith, (cudaStream_t)stream);
 }
 
@@ -274,6 +276,7 @@ int hb_cr3bp_dense(const hb_cr3bp *sys, const hb_integ *integ, int64_t n, const 
     p.nacc = n_acc; p.nrej = n_rej; p.status = status;
     p.t_eval = t_eval; p.m = m; p.dense_out = states_out;
     p.ws = (HbWorkspace *)workspace;
+    if (integ->method != HB_DOP853) return hb_rk_dispatch(p, integ->method, integ->arith, 1, 0, st);
     return launch<MODE_DENSE>(p, integ->arith, st);
 }
 
@@ -293,6 +296,8 @@ int hb_cr3bp_event(const hb_cr3bp *sys, const hb_integ *integ, const hb_event *e
     p.yf = y_hit_soa; p.t_hit = t_hit; p.nacc = n_acc; p.nrej = n_rej; p.status = status;
     p.ev_idx = ev->idx; p.ev_dir = ev->direction; p.ev_off = ev->offset; p.xtol = ev->xtol; p.gtol = ev->gtol;
     p.ws = (HbWorkspace *)workspace;
+    if (integ->method != HB_DOP853)
+        return hb_rk_dispatch(p, integ->method, integ->arith, 2, integ->n_fixed_steps, (cudaStream_t)stream);
     return launch<MODE_EVENT>(p, integ->arith, (cudaStream_t)stream);
 }
 

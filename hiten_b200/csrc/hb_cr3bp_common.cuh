@@ -159,7 +159,9 @@ HB_DEV double initial_step(const double (&y)[6], const double (&f)[6], const Pro
 inline int fill_params(const hb_cr3bp *sys, const hb_integ *integ, PropParams &p)
 {
     if (!sys || !integ) return HB_ERR_BADARG;
-    if (integ->method != HB_DOP853) return HB_ERR_UNSUPPORTED;
+    if (integ->method != HB_DOP853 && integ->method != HB_RK45 && integ->method != HB_RK4 &&
+        integ->method != HB_RK6 && integ->method != HB_RK8)
+        return HB_ERR_UNSUPPORTED;
     if (integ->arith != HB_ARITH_PARITY && integ->arith != HB_ARITH_FAST) return HB_ERR_BADARG;
     p.mu = sys->mu;
     p.om = 1.0 - sys->mu;
@@ -186,3 +188,6 @@ inline int sm_count()
 
 
 }  // namespace hbc
+
+// hb_cr3bp_rk.cu: RK45 and fixed-step RK4/6/8 (mode 0 end state, 1 dense grid, 2 terminal event)
+int hb_rk_dispatch(const hbc::PropParams &p, int method, int arith, int mode, int n_fixed, cudaStream_t st);

@@ -73,6 +73,8 @@ typedef struct {
     double rtol, atol;
     double max_step, min_step;
     int64_t max_attempts; /* safety cap per trajectory (the reference has none); <=0 -> 2^31-1 */
+    int32_t n_fixed_steps;/* fixed-step methods: number of equal steps over [t0, tf]             */
+    int32_t _pad;
 } hb_integ;
 
 /* Plane event g(t,y) = y[idx] - offset (algorithms/poincare/singlehit/backend.py:30-67) with the
@@ -118,8 +120,9 @@ int hb_device_info(int32_t *sm_count, int32_t *cc_major, int32_t *cc_minor);
  *  algorithms/integrators/rk.py:2377-2549 / 1269-1399 / 533-588).
  * yf uses the reference's API semantics: the dense interpolant evaluated at tf on the last
  * accepted segment (what states[-1] of _propagate_dynsys is).
- * tf_per_traj may be NULL (then tf is used for all).  For fixed-step methods n_fixed_steps is the
- * number of equal steps over [t0, tf] (t_vals = linspace(t0, tf, n_fixed_steps + 1)).           */
+ * tf_per_traj may be NULL (then tf is used for all).  For fixed-step methods (HB_RK4/6/8,
+ * rk.py:533-588) n_fixed_steps (or, if 0, integ->n_fixed_steps) is the number of equal steps over
+ * [t0, tf] (t_vals = linspace(t0, tf, n_fixed_steps + 1)); HB_RK45 is _RK45 (rk.py:1269-1399).   */
 int hb_cr3bp_propagate(const hb_cr3bp *sys, const hb_integ *integ, int64_t n, const double *y0_soa,
                        double t0, double tf, const double *tf_per_traj, int32_t n_fixed_steps,
                        double *yf_soa, int32_t *n_acc, int32_t *n_rej, int32_t *status,
