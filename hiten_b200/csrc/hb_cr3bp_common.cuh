@@ -114,26 +114,14 @@ HB_DEV double pick6(const double (&v)[6], int i)
     return r;
 }
 
-// scale0, d0, d1, h0 (rk.py:2445-2448; utils.py:127-157).  The reference's np.linalg.norm is
-// OpenBLAS dnrm2 (x87 extended accumulation); a double-double sum of squares stands in for it.
+// scale0, d0, d1, h0 (rk.py:2445-2448; utils.py:127-157).  The reference's np.linalg.norm is OpenBLAS dnrm2
+// (x87 extended accumulation), emulated bit for bit by hb_x87_norm2.
 HB_DEV double norm2_ext6(const double (&v)[6])
 {
-    double hi = 0.0, lo = 0.0;
+    double w[6];
 #pragma unroll
-    for (int d = 0; d < 6; ++d) {
-        const double ph = __dmul_rn(v[d], v[d]);
-        const double pl = __fma_rn(v[d], v[d], -ph);           // exact product = ph + pl
-        const double s = __dadd_rn(hi, ph);                     // two-sum(hi, ph)
-        const double bb = __dsub_rn(s, hi);
-        const double e = __dadd_rn(__dsub_rn(hi, __dsub_rn(s, bb)), __dsub_rn(ph, bb));
-        hi = s;
-        lo = __dadd_rn(lo, __dadd_rn(e, pl));
-    }
-    const double s = __dadd_rn(hi, lo);
-    const double r = __dsqrt_rn(s);
-    // one Newton correction with the residual taken in double-double: r + (S - r*r) / (2r)
-    const double res = __dadd_rn(__fma_rn(-r, r, hi), lo);
-    return __dadd_rn(r, __ddiv_rn(res, __dmul_rn(2.0, r)));
+    for (int d = 0; d < 6; ++d) w[d] = v[d];
+    return hb_x87_norm2(w, 6);       // bit-exact x87 dnrm2 (hb_x87.cuh)
 }
 
 template <class AR>

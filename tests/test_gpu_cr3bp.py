@@ -28,9 +28,10 @@ def test_c1_end_states_parity(c1):
     same_steps = (res.n_acc == counts[:, 0]) & (res.n_rej == counts[:, 1])
     print(f"[parity] C1 step counts identical: {same_steps.sum()}/50")
     assert same_steps.all()
-    # tolerance of BASELINE.json north_star: 1e-9 relative at the default horizon
-    assert np.quantile(rel, 0.9) <= 1e-9
-    assert rel.max() <= 5e-8
+    # BASELINE.json north_star asks for 1e-9 relative at the default horizon; with glibc's pow() and the x87 norm
+    # restated on the device the parity variant reproduces the reference's step sequence and rounding exactly
+    assert rel.max() <= 1e-9
+    assert np.array_equal(res.yf, c1["yf_steps2"])
 
 
 def test_c1_dense_parity(c1):
@@ -43,8 +44,8 @@ def test_c1_dense_parity(c1):
     err = np.abs(got - c1["dense"]).max(axis=2)         # synodic coordinates, absolute
     print(f"[parity] C1 dense samples |diff|: median={np.median(err):.3e} max={err.max():.3e}")
     # t <= half the horizon: well conditioned
-    half = c1["dense_idx"] <= int(c1["steps"]) // 2
-    assert err[:, half].max() <= 1e-9
+    assert err.max() <= 1e-9
+    assert np.array_equal(got, c1["dense"])                      # bit-exact on every committed sample
     assert np.array_equal(res.states[:, 0, :], c1["x0W"])
 
 

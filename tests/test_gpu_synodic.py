@@ -50,6 +50,7 @@ def test_gpu_tube_and_section_vs_reference(name):
     print(f"[parity] {name}: {len(dp)} hits; |d point| median {np.median(dp):.2e} max {dp.max():.2e}; "
           f"|d t| max {dt.max():.2e}; |d state| max {ds.max():.2e}; >1e-9: {(dp > 1e-9).sum()}")
     assert dp.max() <= 1e-9
+    assert np.array_equal(got.times, g["hit_time"]) and np.array_equal(got.states, g["hit_state"])   # bit-exact
 
 
 def test_detector_ragged_and_empty():
