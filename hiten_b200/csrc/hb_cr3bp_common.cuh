@@ -135,8 +135,17 @@ HB_DEV double initial_step(const double (&y)[6], const double (&f)[6], const Pro
         b[d] = AR::div(f[d], sc);
     }
     const double sq = AR::sqrt(6.0);
-    const double d0 = AR::div(norm2_ext6(a), sq);
-    const double d1 = AR::div(norm2_ext6(b), sq);
+    double d0, d1;
+    if constexpr (AR::parity) {
+        d0 = AR::div(norm2_ext6(a), sq);
+        d1 = AR::div(norm2_ext6(b), sq);
+    } else {
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int d = 0; d < 6; ++d) { s0 = fma(a[d], a[d], s0); s1 = fma(b[d], b[d], s1); }
+        d0 = ::sqrt(s0) / sq;
+        d1 = ::sqrt(s1) / sq;
+    }
     double h = (d0 < 1.0e-5 || d1 < 1.0e-5) ? 1.0e-6 : AR::div(AR::mul(0.01, d0), d1);
     if (h > p.max_step) h = p.max_step;
     if (h < p.min_step) h = p.min_step;
