@@ -15,6 +15,7 @@ NVCC_FLAGS = [
     "-t", "8",
     "-Xcompiler", "-fPIC",
     "-shared",
+    "-ldl",
 ]
 
 

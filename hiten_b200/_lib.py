@@ -80,6 +80,9 @@ SIGNATURES = {
                                      vp, vp, vp, vp, vp, vp]),
     "hb_cm_prepare": (C.c_int, [C.POINTER(HbCmOpts), C.c_double]),
     "hb_cm_poincare_map": (C.c_int, [C.POINTER(HbPolyHam), C.POINTER(HbCmOpts), C.c_int64, vp, vp, vp, vp, vp, vp]),
+    "hb_cm_poincare_map_jit": (C.c_int, [C.POINTER(HbPolyHam), C.POINTER(HbCmOpts), C.c_int64, vp, vp, vp, vp, vp, vp]),
+    "hb_cm_jit_compile_host": (C.c_int, [vp, C.POINTER(C.c_int64), C.c_int32, C.POINTER(HbCmOpts), C.POINTER(C.c_int64),
+                                         C.c_char_p, C.c_int64]),
     "hb_synodic_detect": (C.c_int, [C.POINTER(HbSection), C.c_int64, vp, vp, vp, C.c_int32, C.c_int32, vp, C.c_int64,
                                     vp, vp, vp]),
     "hb_read_hit_count": (C.c_int, [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), vp]),

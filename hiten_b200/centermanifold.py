@@ -94,8 +94,27 @@ def make_opts(dt=0.01, max_steps=2000, method="fixed", order=4, section_coord="q
     return o
 
 
-def poincare_map(table, seeds, opts, *, device=None, stream=None, ws=None):
-    """_poincare_map on the GPU: seeds [N, 4] (host ndarray or CUDA tensor) -> (flags, states[N,4], times[N])."""
+def jit_compile_host(table, opts, want_source=False):
+    """Generate + compile the specialised kernel offline (no GPU): returns (cubin_bytes, source or None)."""
+    lib = L.load()
+    rec = table.packed()
+    ptr = (L.C.c_int64 * 7)(*[int(x) for x in table.ptr])
+    nbytes = L.C.c_int64(0)
+    cap = 4 << 20
+    buf = L.C.create_string_buffer(cap) if want_source else None
+    rc = lib.hb_cm_jit_compile_host(rec.ctypes.data if rec.size else None, ptr, table.max_deg, opts, L.C.byref(nbytes),
+                                    buf, cap if want_source else 0)
+    if rc != 0 and buf is not None:
+        raise L.HitenB200Error(f"hb_cm_jit_compile_host: {rc}: {buf.value.decode(errors='replace')[:2000]}")
+    L.check(rc, "hb_cm_jit_compile_host")
+    return int(nbytes.value), (buf.value.decode() if want_source else None)
+
+
+def poincare_map(table, seeds, opts, *, device=None, stream=None, ws=None, jit=True):
+    """_poincare_map on the GPU: seeds [N, 4] (host ndarray or CUDA tensor) -> (flags, states[N,4], times[N]).
+
+    jit=True (default) runs the kernel specialised for this Hamiltonian (hb_cm_poincare_map_jit);
+    jit=False the table-driven kernel (hb_cm_poincare_map).  Both are bit-identical in the parity variant."""
     _require_cuda()
     lib = L.load()
     device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -110,9 +129,10 @@ def poincare_map(table, seeds, opts, *, device=None, stream=None, ws=None):
         tt = torch.zeros(n, dtype=torch.float64, device=device)
         ws = workspace(device) if ws is None else ws
         ham, keep = table.device_struct(device)
-        rc = lib.hb_cm_poincare_map(ham, opts, n, sd.data_ptr(), flags.data_ptr(), out.data_ptr(), tt.data_ptr(),
-                                    ws.data_ptr(), _stream_ptr(stream))
-        L.check(rc, "hb_cm_poincare_map")
+        fn = lib.hb_cm_poincare_map_jit if jit else lib.hb_cm_poincare_map
+        rc = fn(ham, opts, n, sd.data_ptr(), flags.data_ptr(), out.data_ptr(), tt.data_ptr(), ws.data_ptr(),
+                _stream_ptr(stream))
+        L.check(rc, "hb_cm_poincare_map_jit" if jit else "hb_cm_poincare_map")
         if host:
             return flags.cpu().numpy().astype(np.int64), out.cpu().numpy(), tt.cpu().numpy()
         return flags, out, tt

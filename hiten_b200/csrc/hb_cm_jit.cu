@@ -1,0 +1,442 @@
+// hb_cm_jit.cu -- centre-manifold Poincare map, SPECIALISED at run time for the Hamiltonian at hand.
+//
+// The polynomial tables of a centre manifold are fixed for the life of the object (they take the reference
+// ~34 s to build) while the map evaluates their gradient ~1e9 times.  Instead of interpreting a term table
+// (hb_cm.cu: ~60 instructions of decoding per term) this path GENERATES the gradient as straight-line CUDA --
+// powers in registers, coefficients as hex-float immediates, terms in the reference's evaluation order -- wraps it
+// in the map kernel (Tao symplectic or RK4/6/8 step, crossing test, Hermite hit), compiles it for sm_100a with
+// NVRTC and launches it through the driver API on the caller's stream.  Modules are cached per generated source.
+// The parity build keeps every mul/add separately rounded, so results stay bit-identical to the reference.
+//
+// libnvrtc / libcuda are loaded lazily with dlopen: the shared library itself still loads on a machine without a
+// GPU driver (the CPU test suite checks exactly that, and compiles a specialised kernel offline).
+//
+// Reference routines: see hb_cm.cu (same algorithms, same order of operations).
+#include "hb_common.cuh"
+
+#include <dlfcn.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+namespace {
+
+struct TermHost {
+    double coef;
+    unsigned long long ex;
+};
+
+std::string hexf(double v)
+{
+    char buf[64];
+    snprintf(buf, sizeof buf, "%a", v);
+    return std::string(buf);
+}
+
+void appendf(std::string &s, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    s += buf;
+}
+
+// ---- code generation ---------------------------------------------------------------------------
+// gradient: g[q] = sum over degree groups (each summed from 0.0 in term order) of coef * prod_v pt[v]^e_v
+std::string gen_grad(const std::vector<TermHost> &terms, const int64_t *ptr)
+{
+    int maxe[6] = {0, 0, 0, 0, 0, 0};
+    for (const TermHost &t : terms)
+        for (int v = 0; v < 6; ++v) {
+            const int e = (int)((t.ex >> (8 * v)) & 0xff);
+            if (e > maxe[v]) maxe[v] = e;
+        }
+    std::string s = "DEV void grad(const double (&pt)[6], double (&g)[6])\n{\n";
+    for (int v = 0; v < 6; ++v)
+        for (int e = 1; e <= maxe[v]; ++e) {
+            if (e == 1) appendf(s, "    const double w%d_1 = pt[%d];\n", v, v);
+            else appendf(s, "    const double w%d_%d = MUL(w%d_%d, pt[%d]);\n", v, e, v, e - 1, v);
+        }
+    for (int q = 0; q < 6; ++q) {
+        appendf(s, "    {\n        double tot = 0.0, acc = 0.0;\n");
+        int dcur = -1;
+        for (int64_t i = ptr[q]; i < ptr[q + 1]; ++i) {
+            const TermHost &t = terms[(size_t)i];
+            const int d = (int)(t.ex >> 48);
+            if (d != dcur) {
+                if (dcur >= 0) s += "        tot = ADD(tot, acc); acc = 0.0;\n";
+                dcur = d;
+            }
+            std::string prod;
+            for (int v = 0; v < 6; ++v) {
+                const int e = (int)((t.ex >> (8 * v)) & 0xff);
+                if (!e) continue;
+                char w[32];
+                snprintf(w, sizeof w, "w%d_%d", v, e);
+                prod = prod.empty() ? std::string(w) : "MUL(" + prod + ", " + w + ")";
+            }
+            if (prod.empty()) prod = "1.0";
+            s += "        acc = MADD(" + hexf(t.coef) + ", " + prod + ", acc);\n";
+        }
+        if (dcur >= 0) s += "        tot = ADD(tot, acc);\n";
+        appendf(s, "        g[%d] = tot;\n    }\n", q);
+    }
+    s += "}\n";
+    return s;
+}
+
+template <int S>
+std::string gen_rk_step(const double (&A)[S][S], const double (&B)[S])
+{
+    // k[s] = rhs(y + sum_j (h*a_sj) k_j);  yn = y + sum_s (h*b_s) k_s   (backend.py:160-180); k0 = ro (rhs of so)
+    std::string s;
+    bool used[S];
+    for (int i = 0; i < S; ++i) {
+        used[i] = B[i] != 0.0;
+        for (int r = i + 1; r < S; ++r) used[i] = used[i] || (A[r][i] != 0.0);
+    }
+    appendf(s, "            double k[%d][6], ys[6];\n", S);
+    s += "            UNROLL for (int d = 0; d < 6; ++d) k[0][d] = ro[d];\n";
+    for (int i = 1; i < S; ++i) {
+        if (!used[i]) continue;
+        s += "            UNROLL for (int d = 0; d < 6; ++d) ys[d] = so[d];\n";
+        for (int j = 0; j < i; ++j)
+            if (A[i][j] != 0.0)
+                appendf(s, "            { const double ha = MUL(DT, %s); UNROLL for (int d = 0; d < 6; ++d) ys[d] = MADD(ha, k[%d][d], ys[d]); }\n",
+                        hexf(A[i][j]).c_str(), j);
+        appendf(s, "            rhs(ys, k[%d]);\n", i);
+    }
+    s += "            UNROLL for (int d = 0; d < 6; ++d) sn[d] = so[d];\n";
+    for (int j = 0; j < S; ++j)
+        if (B[j] != 0.0)
+            appendf(s, "            { const double hb = MUL(DT, %s); UNROLL for (int d = 0; d < 6; ++d) sn[d] = MADD(hb, k[%d][d], sn[d]); }\n",
+                    hexf(B[j]).c_str(), j);
+    return s;
+}
+
+const char *PRELUDE = R"SRC(
+typedef unsigned long long u64;
+struct Ws { u64 cursor, hit_count, overflow, pad[29]; };
+#define DEV __device__ __forceinline__
+#define UNROLL _Pragma("unroll")
+#if PARITY
+DEV double ADD(double a, double b) { return __dadd_rn(a, b); }
+DEV double SUB(double a, double b) { return __dsub_rn(a, b); }
+DEV double MUL(double a, double b) { return __dmul_rn(a, b); }
+DEV double DIV(double a, double b) { return __ddiv_rn(a, b); }
+DEV double MADD(double a, double b, double c) { return __dadd_rn(c, __dmul_rn(a, b)); }
+#else
+DEV double ADD(double a, double b) { return a + b; }
+DEV double SUB(double a, double b) { return a - b; }
+DEV double MUL(double a, double b) { return a * b; }
+DEV double DIV(double a, double b) { return a / b; }
+DEV double MADD(double a, double b, double c) { return fma(a, b, c); }
+#endif
+)SRC";
+
+const char *KERNEL_HEAD = R"SRC(
+DEV void rhs(const double (&y)[6], double (&dy)[6])          // [dH/dP, -dH/dQ]
+{
+    double g[6];
+    grad(y, g);
+    dy[0] = g[3]; dy[1] = g[4]; dy[2] = g[5];
+    dy[3] = -g[0]; dy[4] = -g[1]; dy[5] = -g[2];
+}
+DEV double hermite(double s, double y0, double y1, double dy0, double dy1)
+{
+    const double oms = SUB(1.0, s);
+    const double oms2 = MUL(oms, oms), s2 = MUL(s, s);
+    const double h00 = MUL(ADD(1.0, MUL(2.0, s)), oms2);
+    const double h10 = MUL(s, oms2);
+    const double h01 = MUL(s2, SUB(3.0, MUL(2.0, s)));
+    const double h11 = MUL(s2, SUB(s, 1.0));
+    return ADD(ADD(ADD(MUL(h00, y0), MUL(MUL(h10, dy0), DT)), MUL(h01, y1)), MUL(MUL(h11, dy1), DT));
+}
+extern "C" __global__ void __launch_bounds__(256) cm_map(const double *seeds, long long n, int *flags, double *out,
+                                                         double *t_out, Ws *ws)
+{
+    for (;;) {
+        const long long idx = (long long)atomicAdd(&ws->cursor, 1ULL);
+        if (idx >= n) break;
+        const double *sd = seeds + idx * 4;
+        double so[6] = {0.0, sd[0], sd[2], 0.0, sd[1], sd[3]}, sn[6], rn[6], ro[6];
+#if !TAO
+        rhs(so, ro);
+#endif
+        double elapsed = 0.0, tc = 0.0, o0 = 0.0, o1 = 0.0, o2 = 0.0, o3 = 0.0;
+        int flag = 0;
+        for (int it = 0; it < MAX_STEPS; ++it) {
+)SRC";
+
+const char *TAO_STEP = R"SRC(
+            double Q[3] = {so[0], so[1], so[2]}, P[3] = {so[3], so[4], so[5]};
+            double X[3] = {so[0], so[1], so[2]}, Y[3] = {so[3], so[4], so[5]};
+#pragma unroll 1
+            for (int j = 0; j < N_SUB; ++j) {
+                const double ts = SUB_TS[j], hd = MUL(0.5, ts), c = SUB_COS[j], s = SUB_SIN[j];
+#pragma unroll 1
+                for (int ph = 0; ph < 5; ++ph) {
+                    if (ph == 2) {
+                        UNROLL for (int i = 0; i < 3; ++i) {
+                            const double qpx = ADD(Q[i], X[i]), qmx = SUB(Q[i], X[i]);
+                            const double ppy = ADD(P[i], Y[i]), pmy = SUB(P[i], Y[i]);
+                            Q[i] = MUL(0.5, ADD(ADD(qpx, MUL(c, qmx)), MUL(s, pmy)));
+                            P[i] = MUL(0.5, ADD(SUB(ppy, MUL(s, qmx)), MUL(c, pmy)));
+                            X[i] = MUL(0.5, SUB(SUB(qpx, MUL(c, qmx)), MUL(s, pmy)));
+                            Y[i] = MUL(0.5, SUB(ADD(ppy, MUL(s, qmx)), MUL(c, pmy)));
+                        }
+                    } else {
+                        const bool isA = (ph == 0) || (ph == 4);         // phi_a: (Q,Y); phi_b: (X,P)
+                        double pt[6], g[6];
+                        UNROLL for (int i = 0; i < 3; ++i) { pt[i] = isA ? Q[i] : X[i]; pt[3 + i] = isA ? Y[i] : P[i]; }
+                        grad(pt, g);
+                        UNROLL for (int i = 0; i < 3; ++i) {
+                            const double dq = MUL(hd, g[i]), dp = MUL(hd, g[3 + i]);
+                            if (isA) { P[i] = SUB(P[i], dq); X[i] = ADD(X[i], dp); }
+                            else { Q[i] = ADD(Q[i], dp); Y[i] = SUB(Y[i], dq); }
+                        }
+                    }
+                }
+            }
+            UNROLL for (int i = 0; i < 3; ++i) { sn[i] = Q[i]; sn[3 + i] = P[i]; }
+)SRC";
+
+const char *KERNEL_TAIL = R"SRC(
+            rhs(sn, rn);
+            const double f_old = so[FIDX], f_new = sn[FIDX];
+            bool crossed = false;
+            if (!(MUL(f_old, f_new) >= 0.0)) crossed = GOOD_DIR;
+            if (crossed) {
+                const double alpha = DIV(f_old, SUB(f_old, f_new));
+#if TAO
+                rhs(so, ro);
+#endif
+                o0 = hermite(alpha, so[1], sn[1], ro[1], rn[1]);
+                o1 = hermite(alpha, so[4], sn[4], ro[4], rn[4]);
+                o2 = hermite(alpha, so[2], sn[2], ro[2], rn[2]);
+                o3 = hermite(alpha, so[5], sn[5], ro[5], rn[5]);
+                tc = ADD(elapsed, MUL(alpha, DT));
+                flag = 1;
+                break;
+            }
+            UNROLL for (int d = 0; d < 6; ++d) { so[d] = sn[d]; ro[d] = rn[d]; }
+            elapsed = ADD(elapsed, DT);
+        }
+        flags[idx] = flag;
+        t_out[idx] = tc;
+        out[idx * 4 + 0] = o0; out[idx * 4 + 1] = o1; out[idx * 4 + 2] = o2; out[idx * 4 + 3] = o3;
+    }
+}
+)SRC";
+
+std::string gen_source(const std::vector<TermHost> &terms, const int64_t *ptr, const hb_cm_opts &o)
+{
+    std::string s;
+    const bool tao = o.method == HB_SYMPLECTIC;
+    appendf(s, "#define PARITY %d\n#define TAO %d\n#define MAX_STEPS %d\n#define DT %s\n", o.arith == HB_ARITH_PARITY ? 1 : 0,
+            tao ? 1 : 0, o.max_steps, hexf(o.dt).c_str());
+    static const int fidx[4] = {1, 4, 2, 5};                       // q2, p2, q3, p3 in [q1,q2,q3,p1,p2,p3]
+    static const char *good[4] = {"(sn[4] > 0.0)", "(rn[1] > 0.0)", "(sn[5] > 0.0)", "(rn[2] > 0.0)"};
+    appendf(s, "#define FIDX %d\n#define GOOD_DIR %s\n", fidx[o.section], good[o.section]);
+    if (tao) {
+        appendf(s, "#define N_SUB %d\n", o.n_sub);
+        for (const char *nm : {"SUB_TS", "SUB_COS", "SUB_SIN"}) {
+            const double *arr = !strcmp(nm, "SUB_TS") ? o.sub_ts : !strcmp(nm, "SUB_COS") ? o.sub_cos : o.sub_sin;
+            appendf(s, "__device__ const double %s[%d] = {", nm, o.n_sub);
+            for (int j = 0; j < o.n_sub; ++j) s += hexf(arr[j]) + (j + 1 < o.n_sub ? ", " : "");
+            s += "};\n";
+        }
+    }
+    s += PRELUDE;
+    s += gen_grad(terms, ptr);
+    s += KERNEL_HEAD;
+    if (tao) s += TAO_STEP;
+    else if (o.method == HB_RK4) s += gen_rk_step<4>(HB_RK4_A, HB_RK4_B);
+    else if (o.method == HB_RK6) s += gen_rk_step<7>(HB_RK6_A, HB_RK6_B);
+    else s += gen_rk_step<13>(HB_RK8_A, HB_RK8_B);
+    s += KERNEL_TAIL;
+    return s;
+}
+
+// ---- NVRTC + driver API through dlopen -----------------------------------------------------------
+typedef int (*nvrtcCreate_t)(void **, const char *, const char *, int, const char *const *, const char *const *);
+typedef int (*nvrtcCompile_t)(void *, int, const char *const *);
+typedef int (*nvrtcSize_t)(void *, size_t *);
+typedef int (*nvrtcGet_t)(void *, char *);
+typedef int (*nvrtcDestroy_t)(void **);
+typedef int (*cuModuleLoadData_t)(void **, const void *);
+typedef int (*cuModuleGetFunction_t)(void **, void *, const char *);
+typedef int (*cuLaunchKernel_t)(void *, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, void *,
+                                void **, void **);
+typedef int (*cuOccupancy_t)(int *, void *, int, size_t);
+
+struct Api {
+    void *nvrtc = nullptr, *cuda = nullptr;
+    nvrtcCreate_t create = nullptr;
+    nvrtcCompile_t compile = nullptr;
+    nvrtcSize_t cubin_size = nullptr, log_size = nullptr;
+    nvrtcGet_t cubin = nullptr, log = nullptr;
+    nvrtcDestroy_t destroy = nullptr;
+    cuModuleLoadData_t load = nullptr;
+    cuModuleGetFunction_t getfn = nullptr;
+    cuLaunchKernel_t launch = nullptr;
+    cuOccupancy_t occ = nullptr;
+};
+
+std::mutex g_mu;
+Api g_api;
+std::unordered_map<std::string, void *> g_functions;   // generated source -> CUfunction (per process, one device)
+std::string g_last_log;
+
+bool load_nvrtc()
+{
+    if (g_api.create) return true;
+    for (const char *nm : {"libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so.12", "libnvrtc.so"}) {
+        g_api.nvrtc = dlopen(nm, RTLD_NOW | RTLD_LOCAL);
+        if (g_api.nvrtc) break;
+    }
+    if (!g_api.nvrtc) return false;
+    g_api.create = (nvrtcCreate_t)dlsym(g_api.nvrtc, "nvrtcCreateProgram");
+    g_api.compile = (nvrtcCompile_t)dlsym(g_api.nvrtc, "nvrtcCompileProgram");
+    g_api.cubin_size = (nvrtcSize_t)dlsym(g_api.nvrtc, "nvrtcGetCUBINSize");
+    g_api.cubin = (nvrtcGet_t)dlsym(g_api.nvrtc, "nvrtcGetCUBIN");
+    g_api.log_size = (nvrtcSize_t)dlsym(g_api.nvrtc, "nvrtcGetProgramLogSize");
+    g_api.log = (nvrtcGet_t)dlsym(g_api.nvrtc, "nvrtcGetProgramLog");
+    g_api.destroy = (nvrtcDestroy_t)dlsym(g_api.nvrtc, "nvrtcDestroyProgram");
+    return g_api.create && g_api.compile && g_api.cubin_size && g_api.cubin && g_api.destroy;
+}
+
+bool load_driver()
+{
+    if (g_api.launch) return true;
+    g_api.cuda = dlopen("libcuda.so.1", RTLD_NOW | RTLD_LOCAL);
+    if (!g_api.cuda) return false;
+    g_api.load = (cuModuleLoadData_t)dlsym(g_api.cuda, "cuModuleLoadData");
+    g_api.getfn = (cuModuleGetFunction_t)dlsym(g_api.cuda, "cuModuleGetFunction");
+    g_api.launch = (cuLaunchKernel_t)dlsym(g_api.cuda, "cuLaunchKernel");
+    g_api.occ = (cuOccupancy_t)dlsym(g_api.cuda, "cuOccupancyMaxActiveBlocksPerMultiprocessor");
+    return g_api.load && g_api.getfn && g_api.launch;
+}
+
+int compile_cubin(const std::string &src, std::vector<char> &cubin)
+{
+    if (!load_nvrtc()) return HB_ERR_UNSUPPORTED;
+    void *prog = nullptr;
+    if (g_api.create(&prog, src.c_str(), "hb_cm_specialised.cu", 0, nullptr, nullptr) != 0) return HB_ERR_BADARG;
+    const char *opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "--fmad=true"};
+    const int rc = g_api.compile(prog, 4, opts);
+    if (rc != 0) {
+        size_t ls = 0;
+        if (g_api.log_size && g_api.log && g_api.log_size(prog, &ls) == 0 && ls > 1) {
+            g_last_log.resize(ls);
+            g_api.log(prog, &g_last_log[0]);
+        }
+        g_api.destroy(&prog);
+        return HB_ERR_BADARG;
+    }
+    size_t n = 0;
+    g_api.cubin_size(prog, &n);
+    cubin.resize(n);
+    g_api.cubin(prog, cubin.data());
+    g_api.destroy(&prog);
+    return HB_OK;
+}
+
+int check_opts(const hb_polyham *ham, const hb_cm_opts *o)
+{
+    if (!ham || !o) return HB_ERR_BADARG;
+    if (ham->n_dof != 3 || ham->max_deg < 0 || ham->max_deg > 60) return HB_ERR_UNSUPPORTED;
+    if (o->section < 0 || o->section > 3 || o->max_steps < 0) return HB_ERR_BADARG;
+    if (o->arith != HB_ARITH_PARITY && o->arith != HB_ARITH_FAST) return HB_ERR_BADARG;
+    if (o->method == HB_SYMPLECTIC) { if (o->n_sub <= 0 || o->n_sub > HB_MAX_TAO_SUBSTEPS) return HB_ERR_BADARG; }
+    else if (o->method != HB_RK4 && o->method != HB_RK6 && o->method != HB_RK8) return HB_ERR_UNSUPPORTED;
+    return HB_OK;
+}
+
+}  // namespace
+
+// Host-only: generate and compile the specialised kernel for a term table in HOST memory; returns the cubin size.
+// Needs libnvrtc but no GPU -- used by the CPU test-suite and by tools that want to inspect the generated code.
+extern "C" int hb_cm_jit_compile_host(const void *terms_host, const int64_t *ptr, int32_t max_deg, const hb_cm_opts *opts,
+                                      int64_t *cubin_bytes, char *source_out, int64_t source_cap)
+{
+    hb_polyham h{};
+    h.n_dof = 3; h.max_deg = max_deg;
+    int rc = check_opts(&h, opts);
+    if (rc != HB_OK || !ptr || (ptr[6] > 0 && !terms_host)) return rc != HB_OK ? rc : HB_ERR_BADARG;
+    std::vector<TermHost> terms((size_t)ptr[6]);
+    if (ptr[6]) memcpy(terms.data(), terms_host, sizeof(TermHost) * (size_t)ptr[6]);
+    const std::string src = gen_source(terms, ptr, *opts);
+    if (source_out && source_cap > 0) {
+        const size_t n = src.size() < (size_t)source_cap - 1 ? src.size() : (size_t)source_cap - 1;
+        memcpy(source_out, src.data(), n);
+        source_out[n] = 0;
+    }
+    std::lock_guard<std::mutex> lk(g_mu);
+    std::vector<char> cubin;
+    rc = compile_cubin(src, cubin);
+    if (rc == HB_OK && cubin_bytes) *cubin_bytes = (int64_t)cubin.size();
+    if (rc != HB_OK && source_out && source_cap > 0 && !g_last_log.empty()) {
+        const size_t n = g_last_log.size() < (size_t)source_cap - 1 ? g_last_log.size() : (size_t)source_cap - 1;
+        memcpy(source_out, g_last_log.data(), n);
+        source_out[n] = 0;
+    }
+    return rc;
+}
+
+// Same contract as hb_cm_poincare_map (hb_cm.cu), specialised kernel.
+extern "C" int hb_cm_poincare_map_jit(const hb_polyham *ham, const hb_cm_opts *opts, int64_t n, const double *seeds,
+                                      int32_t *flags, double *out, double *t_out, void *workspace, void *stream)
+{
+    int rc = check_opts(ham, opts);
+    if (rc != HB_OK) return rc;
+    if (!workspace || n < 0) return HB_ERR_BADARG;
+    if (n > 0 && (!seeds || !flags || !out || !t_out || (ham->ptr[6] > 0 && !ham->terms))) return HB_ERR_BADARG;
+    if (n == 0) return HB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    std::vector<TermHost> terms((size_t)ham->ptr[6]);
+    if (ham->ptr[6]) {
+        HB_CUDA_TRY(cudaMemcpyAsync(terms.data(), ham->terms, sizeof(TermHost) * terms.size(), cudaMemcpyDeviceToHost, st));
+        HB_CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    const std::string src = gen_source(terms, ham->ptr, *opts);
+    void *fn = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_functions.find(src);
+        if (it != g_functions.end()) fn = it->second;
+        else {
+            if (!load_driver()) return HB_ERR_NODEVICE;
+            std::vector<char> cubin;
+            rc = compile_cubin(src, cubin);
+            if (rc != HB_OK) return rc;
+            void *mod = nullptr;
+            int e = g_api.load(&mod, cubin.data());
+            if (e != 0) return 1000 + e;
+            e = g_api.getfn(&fn, mod, "cm_map");
+            if (e != 0) return 1000 + e;
+            g_functions.emplace(src, fn);
+        }
+    }
+    HB_CUDA_TRY(cudaMemsetAsync(workspace, 0, sizeof(HbWorkspace), st));
+    int dev = 0, sms = 148, per_sm = 2;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_api.occ && g_api.occ(&per_sm, fn, 256, 0) != 0) per_sm = 2;
+    if (per_sm < 1) per_sm = 1;
+    long long blocks = (n + 255) / 256;
+    const long long cap = (long long)sms * per_sm;
+    if (blocks > cap) blocks = cap;
+    long long nn = n;
+    void *args[] = {(void *)&seeds, (void *)&nn, (void *)&flags, (void *)&out, (void *)&t_out, (void *)&workspace};
+    const int e = g_api.launch(fn, (unsigned)blocks, 1, 1, 256, 1, 1, 0, (void *)st, args, nullptr);
+    return e == 0 ? HB_OK : 1000 + e;
+}

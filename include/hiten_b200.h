@@ -213,6 +213,20 @@ int hb_cm_prepare(hb_cm_opts *opts, double c_omega);
 int hb_cm_poincare_map(const hb_polyham *ham, const hb_cm_opts *opts, int64_t n, const double *seeds,
                        int32_t *flags, double *out, double *t_out, void *workspace, void *stream);
 
+/* The same map with a kernel SPECIALISED at run time for this Hamiltonian (hb_cm_jit.cu): the gradient is
+ * generated as straight-line code (powers in registers, coefficients as immediates, the reference's term order),
+ * compiled for sm_100a with NVRTC and cached.  Same arguments, same results (bit-identical in the parity
+ * variant); ~50x the throughput of the table-driven kernel.  Needs libnvrtc.so.12 and the CUDA driver at run time
+ * (loaded lazily); returns HB_ERR_UNSUPPORTED if NVRTC is not available.                                  */
+int hb_cm_poincare_map_jit(const hb_polyham *ham, const hb_cm_opts *opts, int64_t n, const double *seeds,
+                           int32_t *flags, double *out, double *t_out, void *workspace, void *stream);
+
+/* Host-only: generate + compile the specialised kernel for a term table in HOST memory (no GPU needed);
+ * *cubin_bytes receives the cubin size, source_out (optional, source_cap bytes) the generated CUDA source or,
+ * on failure, the compiler log.                                                                       */
+int hb_cm_jit_compile_host(const void *terms_host, const int64_t *ptr, int32_t max_deg, const hb_cm_opts *opts,
+                           int64_t *cubin_bytes, char *source_out, int64_t source_cap);
+
 /* Synodic-section crossing detection on precomputed trajectories (linear branch, the one the
  * reference's defaults select): replaces _SynodicDetectionBackend.run / detect_on_trajectory /
  * _detect_with_segment_refine / _order_and_dedup_hits (algorithms/poincare/synodic/backend.py:

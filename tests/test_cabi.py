@@ -37,3 +37,31 @@ def test_compute_fails_loudly_without_cuda():
         pytest.skip("CUDA present")
     with pytest.raises(hiten_b200.HitenB200Error):
         hiten_b200.cr3bp_propagate([[0.8, 0, 0, 0, 0.1, 0]], 0.0121, 1.0)
+
+
+def test_specialised_cm_kernel_compiles_offline():
+    """The run-time specialised centre-manifold kernel (hb_cm_jit.cu) is generated and compiled for sm_100a with
+    NVRTC here, without a GPU: one straight-line MADD per non-zero gradient term, both arithmetic variants."""
+    import numpy as np
+    from hiten_b200 import centermanifold as cm
+    g = np.load(os.path.join(REPO, "tests", "golden", "cm_map.npz"))
+    tab = cm.PolyTable(g["jac_ptr"], g["jac_deg"], g["jac_coef"], g["jac_exp"])
+    for method, order in (("symplectic", 4), ("fixed", 4)):
+        for arith in ("parity", "fast"):
+            nbytes, src = cm.jit_compile_host(tab, cm.make_opts(0.01, 2000, method, order, "p3", 20.0, arith), True)
+            assert nbytes > 10_000
+            assert src.count("acc = MADD(") == 119 and "extern \"C\" __global__" in src
+
+
+def test_tao_schedule_matches_reference_recursion():
+    """hb_cm_prepare flattens _recursive_update_poly (symplectic.py:543-560): 3^(order/2 - 1) order-2 kernels whose
+    time steps sum to dt, with omega = (c*dt)^-order."""
+    from hiten_b200 import centermanifold as cm
+    for order, n_sub in ((2, 1), (4, 3), (6, 9), (8, 27)):
+        o = cm.make_opts(0.01, 10, "symplectic", order, "q3", 20.0)
+        assert o.n_sub == n_sub
+        ts = [o.sub_ts[i] for i in range(n_sub)]
+        assert abs(sum(ts) - 0.01) < 1e-15
+        omega = (20.0 * 0.01) ** (-float(order))
+        import math
+        assert o.sub_cos[0] == math.cos(2 * omega * ts[0]) and o.sub_sin[0] == math.sin(2 * omega * ts[0])

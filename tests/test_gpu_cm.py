@@ -16,20 +16,21 @@ def _table(g):
     return PolyTable(g["jac_ptr"], g["jac_deg"], g["jac_coef"], g["jac_exp"])
 
 
+@pytest.mark.parametrize("jit", [True, False], ids=["specialised", "table"])
 @pytest.mark.parametrize("name,order,symp,sec", CASES)
-def test_map_vs_reference(name, order, symp, sec):
+def test_map_vs_reference(name, order, symp, sec, jit):
     from hiten_b200 import centermanifold as cmod
     g = np.load(os.path.join(HERE, "golden", "cm_map.npz"))
     ref = g[name]
     seeds = g["seeds_" + sec][: len(ref)]
     opts = cmod.make_opts(float(g["dt"]), int(g["max_steps"]), "symplectic" if symp else "fixed", order, sec,
                           float(g["c_omega"]))
-    f, o, t = cmod.poincare_map(_table(g), seeds, opts)
+    f, o, t = cmod.poincare_map(_table(g), seeds, opts, jit=jit)
     assert np.array_equal(f, ref[:, 0].astype(np.int64))              # identical crossing flags
     d = np.abs(o - ref[:, 1:5]).max()
     print(f"[parity] CM {name}: {len(ref)} seeds, |d state| max {d:.2e}, |d t| max {np.abs(t - ref[:, 5]).max():.2e}, "
           f"bit-exact {np.array_equal(o, ref[:, 1:5])}")
-    assert d <= 1e-12 and np.abs(t - ref[:, 5]).max() <= 1e-12
+    assert np.array_equal(o, ref[:, 1:5]) and np.array_equal(t, ref[:, 5])      # bit-exact
 
 
 def test_fast_variant_and_failures():
