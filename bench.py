@@ -177,6 +177,45 @@ def time_steps(fn, steps, flush, barrier, torch):
     return sum(a.elapsed_time(b) for a, b in ev) * 1e-3
 
 
+def secondary_configs(hb, torch, steps, flush, barrier):
+    """BASELINE configs[2] (centre-manifold map, 1e5 seeds, Tao symplectic order 4) and configs[3] (42-state STM of
+    the 100-member halo family, x128 replicas) -- reported beside the headline, parity variant."""
+    from hiten_b200 import centermanifold as cm
+    out = {}
+    g = np.load(os.path.join(REPO, "tests", "golden", "cm_map.npz"))
+    tab = cm.PolyTable(g["jac_ptr"], g["jac_deg"], g["jac_coef"], g["jac_exp"])
+    rng = np.random.default_rng(1)
+    seeds = torch.from_numpy(g["seeds_p3"][rng.integers(0, 512, 100_000)]).cuda()
+    opts = cm.make_opts(0.01, 2000, "symplectic", 4, "p3", 20.0, "parity")
+    hold = {}
+
+    def run_cm():
+        hold["r"] = cm.poincare_map(tab, seeds, opts)
+
+    for _ in range(3):
+        run_cm()                                     # first call compiles the specialised kernel (NVRTC)
+    t = time_steps(run_cm, steps, flush, barrier, torch)
+    f, _, tt = hold["r"]
+    cm_steps = float((tt / 0.01).ceil().sum().item())
+    out["cm_map_tao4_1e5_seeds"] = {"steps_per_s": cm_steps * steps / t, "crossings_per_s": int(f.sum().item()) * steps / t,
+                                    "ms_per_return": 1e3 * t / steps, "tflops": cm_steps * steps * 8100.0 / t / 1e12}
+    s = np.load(os.path.join(REPO, "tests", "golden", "stm_family.npz"))
+    x0 = torch.from_numpy(np.ascontiguousarray(np.tile(s["x0"], (128, 1)).T)).cuda()
+    T = torch.from_numpy(np.tile(s["period"], 128)).cuda()
+    integ = hb.make_integ(arith="parity")
+
+    def run_stm():
+        hold["s"] = hb.cr3bp_stm(x0, float(s["mu"]), 0.0, tf_per_traj=T, integ=integ)
+
+    for _ in range(3):
+        run_stm()
+    t = time_steps(run_stm, steps, flush, barrier, torch)
+    st = int((hold["s"].n_acc.sum() + hold["s"].n_rej.sum()).item())
+    out["stm42_family_x128"] = {"rk_steps_per_s": st * steps / t, "trajectories": int(x0.shape[1]),
+                                "tflops": st * steps * 9500.0 / t / 1e12}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -311,6 +350,7 @@ def main():
         s2 = int((r2.nacc.sum() + r2.nrej.sum()).item())
         extra[f"section_{other}"] = {"rk_steps_per_s": s2 * args.steps / t2,
                                      "crossings_per_s": r2.hit_count() * args.steps / t2}
+        extra.update(secondary_configs(hb, torch, args.steps, flush, barrier))
 
     if rank == 0:
         value = total_steps_pass * args.steps / t_dev
