@@ -11,7 +11,7 @@ from . import _build
 HB_OK = 0
 HB_RK4, HB_RK6, HB_RK8, HB_RK45, HB_DOP853 = 4, 6, 8, 45, 853
 HB_ARITH_PARITY, HB_ARITH_FAST = 0, 1
-HB_TRAJ_OK, HB_TRAJ_HIT, HB_TRAJ_MAXSTEPS, HB_TRAJ_NONFINITE = 0, 1, 2, 3
+HB_TRAJ_OK, HB_TRAJ_HIT, HB_TRAJ_MAXSTEPS, HB_TRAJ_NONFINITE, HB_TRAJ_RECORD_OVERFLOW = 0, 1, 2, 3, 4
 
 ERRORS = {-1: "HB_ERR_BADARG", -2: "HB_ERR_UNSUPPORTED", -3: "HB_ERR_NODEVICE"}
 
@@ -71,6 +71,9 @@ SIGNATURES = {
                                  vp, vp, vp]),
     "hb_cr3bp_section": (C.c_int, [C.POINTER(HbCr3bp), C.POINTER(HbInteg), C.POINTER(HbSection), C.c_int64, vp, vp,
                                    C.c_int32, vp, C.c_int64, vp, vp, vp, vp, vp, vp, vp]),
+    "hb_section2_scratch_bytes": (C.c_int64, [C.c_int64, C.c_int32]),
+    "hb_cr3bp_section2": (C.c_int, [C.POINTER(HbCr3bp), C.POINTER(HbInteg), C.POINTER(HbSection), C.c_int64, vp, vp,
+                                    C.c_int32, vp, C.c_int64, vp, vp, vp, vp, vp, vp, C.c_int64, vp, vp]),
     "hb_cr3bp_event": (C.c_int, [C.POINTER(HbCr3bp), C.POINTER(HbInteg), C.POINTER(HbEvent), C.c_int64, vp,
                                  C.c_double, C.c_double, vp, vp, vp, vp, vp, vp, vp, vp]),
     "hb_dfma_peak": (C.c_int, [C.c_double, C.POINTER(C.c_double), vp]),

@@ -19,7 +19,7 @@
 namespace {
 using namespace hbc;
 
-enum { MODE_FINAL = 0, MODE_DENSE = 1, MODE_EVENT = 2 };
+enum { MODE_FINAL = 0, MODE_DENSE = 1, MODE_EVENT = 2, MODE_RECORD = 3 };
 
 // ---------------------------------------------------------------------------------------------
 // The persistent-thread kernel.
@@ -139,6 +139,38 @@ __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) k_dop853_6(const PropP
                     }
                 }
                 if (last) fin = HB_TRAJ_OK;
+            } else if (MODE == MODE_RECORD) {
+                // Store the dense interpolant of every accepted step (400 B) for the section-scan kernel; the end
+                // state is the last grid sample = the interpolant at tf on the last segment.
+                const double hseg = AR::sub(t_new, t);
+                double F[7][6];
+                if (hseg != 0.0) dense_cache<AR>(y, yh, hseg, k, F, rhs);
+                if (nacc <= p.rec_cap) {
+                    double *r = p.rec + ((long long)idx * p.rec_cap + (nacc - 1)) * HB_REC_DOUBLES;
+                    r[0] = t; r[1] = t_new; r[2] = hseg; r[3] = pick6(y, p.sink.sec.idx);
+#pragma unroll
+                    for (int i = 0; i < 7; ++i) r[4 + i] = (hseg != 0.0) ? pick6(F[i], p.sink.sec.idx) : 0.0;
+#pragma unroll
+                    for (int d = 0; d < 6; ++d) r[HB_REC_Y + d] = y[d];
+                    if (hseg != 0.0) {
+#pragma unroll
+                        for (int i = 0; i < 7; ++i)
+#pragma unroll
+                            for (int d = 0; d < 6; ++d) r[HB_REC_F + 6 * i + d] = F[i][d];
+                    }
+                }
+                if (last) {
+                    double yo[6];
+                    if (hseg == 0.0) {
+#pragma unroll
+                        for (int d = 0; d < 6; ++d) yo[d] = y[d];
+                    } else {
+                        dense_eval<AR>(y, F, AR::div(AR::sub(tf, t), hseg), yo);
+                    }
+#pragma unroll
+                    for (int d = 0; d < 6; ++d) p.yf[(long long)d * p.n + idx] = yo[d];
+                    fin = (nacc <= p.rec_cap) ? HB_TRAJ_OK : HB_TRAJ_RECORD_OVERFLOW;
+                }
             } else {  // MODE_FINAL: the dense interpolant at tf on the last segment
                 if (last) {
                     const double hseg = AR::sub(t_new, t);
@@ -299,6 +331,22 @@ int hb_cr3bp_event(const hb_cr3bp *sys, const hb_integ *integ, const hb_event *e
     if (integ->method != HB_DOP853)
         return hb_rk_dispatch(p, integ->method, integ->arith, 2, integ->n_fixed_steps, (cudaStream_t)stream);
     return launch<MODE_EVENT>(p, integ->arith, (cudaStream_t)stream);
+}
+
+// Kernel A of the two-kernel section path (hb_section_scan.cu): propagate and record every step's interpolant.
+int hb_cr3bp_record_launch(const hb_cr3bp *sys, const hb_integ *integ, int32_t section_idx, int64_t n,
+                           const double *y0_soa, double t0, double tf, double *rec, int32_t rec_cap, double *yf_soa,
+                           int32_t *n_acc, int32_t *n_rej, int32_t *status, void *workspace, cudaStream_t st)
+{
+    PropParams p{};
+    int rc = fill_params(sys, integ, p);
+    if (rc != HB_OK) return rc;
+    if (integ->method != HB_DOP853) return HB_ERR_UNSUPPORTED;
+    p.n = n; p.y0 = y0_soa; p.t0 = t0; p.tf = tf; p.tf_arr = nullptr;
+    p.yf = yf_soa; p.nacc = n_acc; p.nrej = n_rej; p.status = status;
+    p.rec = rec; p.rec_cap = rec_cap; p.sink.sec.idx = section_idx;
+    p.ws = (HbWorkspace *)workspace;
+    return launch<MODE_RECORD>(p, integ->arith, st);
 }
 
 }  // extern "C"

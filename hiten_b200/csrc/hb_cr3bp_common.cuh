@@ -40,7 +40,16 @@ struct PropParams {
     int *hits_per_traj;
     double tsign;          // sign applied to grid times for the detector (times = forward * t_eval)
     double inv_grid_dt;    // (m-1)/(t_eval[m-1]-t_eval[0]): first guess when locating grid samples
+    double *rec;           // MODE_RECORD: per-step dense records [n][rec_cap][HB_REC_DOUBLES]
+    int rec_cap;
 };
+
+// One accepted step as stored by MODE_RECORD (hb_cr3bp.cu) and consumed by the scan kernels (hb_section_scan.cu):
+//   header (3 sectors): [0] t_old [1] t_new [2] hseg [3] y_old[sidx] [4..10] F[0..6][sidx]   (event component)
+//   body              : [11..16] y_old  [17..58] F[7][6] row-major  [59] pad
+#define HB_REC_DOUBLES 60
+#define HB_REC_Y 11
+#define HB_REC_F 17
 
 // ---------------------------------------------------------------------------------------------
 // Vector field.  Parity form keeps rtbp.py:65-74's operation order:

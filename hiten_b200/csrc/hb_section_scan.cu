@@ -1,0 +1,401 @@
+// hb_section_scan.cu -- tube + synodic section as a short pipeline with a compact intermediate (hb_cr3bp_section2).
+//
+//   A  k_dop853_6<.., MODE_RECORD, ..> (hb_cr3bp.cu): the plain propagation kernel, which additionally builds the
+//      dense-output coefficients of every accepted step and stores them (480 B per step: an event-component header
+//      t_old, t_new, hseg, y_c, F_0..6,c followed by y_old and F[7][6]) in a caller-provided scratch
+//      [n][cap][60] -- ~40 KB per trajectory instead of the 226 KB of the 4713-sample tube;
+//   B1 k_step_candidates: ONE THREAD PER STEP RECORD (fully parallel: ~1e7 threads).  From the header alone it finds
+//      the grid samples the step owns and proves most steps quiet (interpolant bound, see hb_cr3bp_section.cu);
+//      the others evaluate the event component at their samples, and segments that can hold a hit run the
+//      reference's sub-interval logic and append CANDIDATE hits {sample index, order, t, state} to a small
+//      per-trajectory list;
+//   B2 k_order_dedup: one thread per trajectory sorts its few candidates into the reference's order and applies
+//      _order_and_dedup_hits (dedup against the previous kept hit, max_hits_per_traj), appending the hits.
+//
+// Why: the fused kernel (hb_cr3bp_section.cu) carries the scan state and 42 dense coefficients through the
+// integration loop and is instruction-fetch bound (ncu); detection itself has no sequential dependence except
+// the final de-duplication, so it is split off and made embarrassingly parallel.  Arithmetic per sample / segment
+// is unchanged, so the hits are bit-identical to the fused kernel and to hb_cr3bp_dense + hb_synodic_detect
+// (tests/test_gpu_synodic.py).  Trajectories with more accepted steps than `cap`, or more candidates than
+// HB_CAND_CAP, get status HB_TRAJ_RECORD_OVERFLOW: rerun those with hb_cr3bp_section.
+//
+// Reference: algorithms/poincare/synodic/backend.py:458-659 (_detect_with_segment_refine), :382-455.
+#include "hb_cr3bp_common.cuh"
+
+extern "C" int hb_cr3bp_record_launch(const hb_cr3bp *sys, const hb_integ *integ, int32_t section_idx, int64_t n,
+                                      const double *y0_soa, double t0, double tf, double *rec, int32_t rec_cap,
+                                      double *yf_soa, int32_t *n_acc, int32_t *n_rej, int32_t *status, void *workspace,
+                                      cudaStream_t st);
+
+namespace {
+using namespace hbc;
+
+constexpr int HB_CAND_CAP = 32;       // candidate hits per trajectory (before de-duplication)
+constexpr int HB_CAND_DOUBLES = 8;    // key, t, state[6]
+constexpr int HB_DESC_DOUBLES = 6;
+
+struct ScanParams {
+    long long n;
+    const double *rec;
+    int rec_cap;
+    const int *nacc;
+    int *status;
+    const double *t_eval;
+    int m;
+    double tsign, inv_grid_dt;
+    HitSink sink;
+    int *hits_per_traj;
+    int *cand_count;        // [n]
+    double *cand;           // [n][HB_CAND_CAP][HB_CAND_DOUBLES]
+    int *desc_count;        // [n]   segments that can hold a hit, found by k_step_candidates
+    double *desc;           // [n][HB_CAND_CAP][HB_DESC_DOUBLES] = {cs, step of cs-1, step of cs, g(cs-1), g(cs), g(cs-2)}
+};
+
+template <class AR>
+HB_DEV double g_comp(const double *hdr, double xq, double offset)     // hdr = record header
+{
+    const double hseg = hdr[2];
+    double ge = hdr[3];
+    if (hseg != 0.0) {
+        const double omx = AR::sub(1.0, xq);
+        double v = 0.0;
+#pragma unroll
+        for (int i = 6; i >= 0; --i) {
+            v = AR::add(v, hdr[4 + i]);
+            v = AR::mul(v, ((6 - i) % 2 == 0) ? xq : omx);
+        }
+        ge = AR::add(v, hdr[3]);
+    }
+    return __dsub_rn(ge, offset);
+}
+template <class AR>
+HB_DEV double xpar(double tq, double t, double hseg) { return (hseg == 0.0) ? 0.0 : AR::div(AR::sub(tq, t), hseg); }
+
+template <class AR>
+HB_DEV void state_from_record(const double *r, double tq, double (&out)[6])
+{
+    const double t = r[0], hseg = r[2];
+    double y[6], F[7][6];
+#pragma unroll
+    for (int d = 0; d < 6; ++d) y[d] = r[HB_REC_Y + d];
+    if (hseg == 0.0) {
+#pragma unroll
+        for (int d = 0; d < 6; ++d) out[d] = y[d];
+        return;
+    }
+#pragma unroll
+    for (int i = 0; i < 7; ++i)
+#pragma unroll
+        for (int d = 0; d < 6; ++d) F[i][d] = r[HB_REC_F + 6 * i + d];
+    dense_eval<AR>(y, F, xpar<AR>(tq, t, hseg), out);
+}
+
+// first index c in [lo, m] with t_eval[c] >= tv  (guess from the uniform spacing, then fix up)
+HB_DEV int first_at_or_after(const ScanParams &p, double tv, int lo)
+{
+    int c = (int)fmin(fmax((tv - p.t_eval[0]) * p.inv_grid_dt, (double)lo), (double)p.m);
+    while (c < p.m && p.t_eval[c] < tv) ++c;
+    while (c > lo && !(p.t_eval[c - 1] < tv)) --c;
+    return c;
+}
+
+// record of the step that owns grid sample c, searching backwards from step s
+HB_DEV const double *owner_record(const double *base, int s, double tq)
+{
+    while (s > 0 && tq < base[(long long)s * HB_REC_DOUBLES]) --s;
+    return base + (long long)s * HB_REC_DOUBLES;
+}
+
+// _detect_with_segment_refine on ONE segment (linear branch), emitting raw candidates in order
+template <class EMIT>
+HB_DEV void segment_candidates(const hb_section &sec, bool has_prev, double g_prev, double gk, double gk1, double t0,
+                               double t1, const double (&x0)[6], const double (&x1)[6], EMIT emit)
+{
+    const int dir = sec.direction;
+    bool accept_left = false;
+    if (fabs(gk) < sec.tol_on_surface) {
+        if (dir == 0) accept_left = true;
+        else if (dir > 0) accept_left = (gk1 >= 0.0) || (has_prev && g_prev <= 0.0);
+        else accept_left = (gk1 <= 0.0) || (has_prev && g_prev >= 0.0);
+    }
+    const int r = sec.segment_refine;
+    double xh[6];
+    int order = 0;
+    if (r > 0) {
+        if (accept_left) emit(order++, t0, x0);
+        const double step = __ddiv_rn(1.0, (double)(r + 1));
+        for (int mm = 0; mm <= r; ++mm) {
+            const double s_lo = __dmul_rn((double)mm, step), s_hi = __dmul_rn((double)(mm + 1), step);
+            if (s_hi > 1.0 + 1e-15) break;
+            if (accept_left && mm == 0) continue;
+            const double g_lo = __dadd_rn(__dmul_rn(__dsub_rn(1.0, s_lo), gk), __dmul_rn(s_lo, gk1));
+            const double g_hi = __dadd_rn(__dmul_rn(__dsub_rn(1.0, s_hi), gk), __dmul_rn(s_hi, gk1));
+            bool crosses;
+            if (dir == 0) crosses = (__dmul_rn(g_lo, g_hi) <= 0.0) && (g_lo != g_hi);
+            else if (dir > 0) crosses = (g_lo < 0.0) && (g_hi >= 0.0);
+            else crosses = (g_lo > 0.0) && (g_hi <= 0.0);
+            if (!crosses) continue;
+            double s_star;
+            if (g_lo == g_hi) s_star = __dmul_rn(0.5, __dadd_rn(s_lo, s_hi));
+            else {
+                double al = __ddiv_rn(g_lo, __dsub_rn(g_lo, g_hi));
+                al = fmin(1.0, fmax(0.0, al));
+                s_star = __dadd_rn(s_lo, __dmul_rn(al, __dsub_rn(s_hi, s_lo)));
+            }
+            const double th = __dadd_rn(__dmul_rn(__dsub_rn(1.0, s_star), t0), __dmul_rn(s_star, t1));
+#pragma unroll
+            for (int d = 0; d < 6; ++d) xh[d] = __dadd_rn(x0[d], __dmul_rn(s_star, __dsub_rn(x1[d], x0[d])));
+            emit(order++, th, xh);
+        }
+    } else {
+        if (accept_left) { emit(order++, t0, x0); return; }
+        bool crosses;
+        if (dir == 0) crosses = (__dmul_rn(gk, gk1) <= 0.0) && (gk != gk1);
+        else if (dir > 0) crosses = (gk < 0.0) && (gk1 >= 0.0);
+        else crosses = (gk > 0.0) && (gk1 <= 0.0);
+        if (!crosses) return;
+        double al = __ddiv_rn(gk, __dsub_rn(gk, gk1));
+        al = fmin(1.0, fmax(0.0, al));
+        const double th = __dadd_rn(__dmul_rn(__dsub_rn(1.0, al), t0), __dmul_rn(al, t1));
+#pragma unroll
+        for (int d = 0; d < 6; ++d) xh[d] = __dadd_rn(x0[d], __dmul_rn(al, __dsub_rn(x1[d], x0[d])));
+        emit(order++, th, xh);
+    }
+}
+
+// k_step_candidates only NOTES the segments that can hold a hit (6 numbers each); k_emit_candidates below turns them
+// into candidate hits.  Keeping the state reconstruction out of the scan kernel keeps it small (no spills, no call).
+HB_DEV void note_segment(const ScanParams &p, long long traj, int cs, int s0, int s1, double gk, double gk1, double gm2)
+{
+    const int slot = atomicAdd(&p.desc_count[traj], 1);
+    if (slot < HB_CAND_CAP) {
+        double *d = p.desc + (traj * HB_CAND_CAP + slot) * HB_DESC_DOUBLES;
+        d[0] = (double)cs; d[1] = (double)s0; d[2] = (double)s1; d[3] = gk; d[4] = gk1; d[5] = gm2;
+    }
+}
+
+// One warp = 32 consecutive step records of one trajectory (rec_cap is a multiple of 32).  Quiet tests run one
+// step per lane; the few non-quiet steps are then scanned by the whole warp, 32 grid samples per instruction.
+template <class AR>
+__global__ void __launch_bounds__(256, 2) k_step_candidates(const ScanParams p)
+{
+    const int lane = threadIdx.x & 31;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long traj = gid / p.rec_cap;
+    const int s = (int)(gid - traj * p.rec_cap);
+    if (traj >= p.n) return;                                  // whole warp (rec_cap % 32 == 0)
+    const int nacc = p.nacc[traj];
+    const double *base = p.rec + traj * (long long)p.rec_cap * HB_REC_DOUBLES;
+    const double *r = base + (long long)s * HB_REC_DOUBLES;
+    const double off = p.sink.sec.offset, tol_s = p.sink.sec.tol_on_surface;
+    const bool have_rec = s < nacc;
+    double hdr[11];
+#pragma unroll
+    for (int i = 0; i < 11; ++i) hdr[i] = have_rec ? r[i] : 0.0;
+    const double t_old = hdr[0], t_new = hdr[1], hseg = hdr[2];
+    int c0 = 0, cend = 0;
+    if (have_rec) {
+        // grid samples owned by this segment: t_old <= t_q < t_new (searchsorted 'right' - 1, rk.py:2505); the
+        // first step also owns t_q = t0 and the last one everything that is left
+        c0 = (s == 0) ? 0 : first_at_or_after(p, t_old, 0);
+        cend = (s == nacc - 1) ? p.m : first_at_or_after(p, t_new, c0);
+    }
+    const bool owns = have_rec && c0 < cend;
+    double g_first = 0.0, g_prev = 0.0;
+    bool scan = false;
+    if (owns) {
+        g_first = g_comp<AR>(hdr, xpar<AR>(p.t_eval[c0], t_old, hseg), off);
+        if (c0 > 0) {
+            // last sample of the previous step(s)
+            const double *rp = owner_record(base, s - 1, p.t_eval[c0 - 1]);
+            double h2[11];
+#pragma unroll
+            for (int i = 0; i < 11; ++i) h2[i] = rp[i];
+            g_prev = g_comp<AR>(h2, xpar<AR>(p.t_eval[c0 - 1], h2[0], h2[2]), off);
+            const bool same = (g_prev > 0.0 && g_first > 0.0) || (g_prev < 0.0 && g_first < 0.0);
+            if (!same || fabs(g_prev) < tol_s) {
+                double gm2 = 0.0;
+                if (c0 > 1) {
+                    const double *rq = owner_record(base, s - 1, p.t_eval[c0 - 2]);
+#pragma unroll
+                    for (int i = 0; i < 11; ++i) h2[i] = rq[i];
+                    gm2 = g_comp<AR>(h2, xpar<AR>(p.t_eval[c0 - 2], h2[0], h2[2]), off);
+                }
+                note_segment(p, traj, c0, (int)((rp - base) / HB_REC_DOUBLES), s, g_prev, g_first, gm2);
+            }
+        }
+        scan = cend - c0 >= 2;
+        // quiet step: no sample can be on the surface or change sign (|p(x) - (y0 + x F0)| <= sum_{i>=1}|F_i| / 4)
+        if (scan && hseg != 0.0 && cend - c0 > 4) {
+            const double g_old = __dsub_rn(hdr[3], off);
+            const double g_new = g_comp<AR>(hdr, 1.0, off);
+            double S = 0.0;
+#pragma unroll
+            for (int i = 1; i < 7; ++i) S += fabs(hdr[4 + i]);
+            const double margin = 0.25 * S + tol_s + 1e-9 * (fabs(hdr[3]) + fabs(hdr[4]) + fabs(off)) + 1e-290;
+            const bool same = (g_old > 0.0 && g_new > 0.0) || (g_old < 0.0 && g_new < 0.0);
+            if (same && fmin(fabs(g_old), fabs(g_new)) > margin) scan = false;
+        }
+    }
+    // cooperative scan of the non-quiet steps of this warp, one owner lane at a time
+    unsigned req = __ballot_sync(0xffffffffu, scan);
+    while (req) {
+        const int L = __ffs(req) - 1;
+        req &= req - 1;
+        double bh[11];
+#pragma unroll
+        for (int i = 0; i < 11; ++i) bh[i] = shfl_d(hdr[i], L);
+        const int b0 = __shfl_sync(0xffffffffu, c0, L), b1 = __shfl_sync(0xffffffffu, cend, L);
+        double carry1 = shfl_d(g_first, L), carry2 = shfl_d(g_prev, L);
+        const int sL = s - lane + L;
+        for (int b = b0 + 1; b < b1; b += 32) {
+            const int c = b + lane;
+            const bool valid = c < b1;
+            const double tq = p.t_eval[valid ? c : b1 - 1];
+            const double g = g_comp<AR>(bh, xpar<AR>(tq, bh[0], bh[2]), off);
+            double g_m1 = __shfl_up_sync(0xffffffffu, g, 1);
+            double g_m2 = __shfl_up_sync(0xffffffffu, g, 2);
+            if (lane == 0) { g_m1 = carry1; g_m2 = carry2; }
+            if (lane == 1) g_m2 = carry1;
+            const bool same = (g_m1 > 0.0 && g > 0.0) || (g_m1 < 0.0 && g < 0.0);
+            const bool flagged = valid && (!same || fabs(g_m1) < tol_s);
+            if (flagged) note_segment(p, traj, c, sL, sL, g_m1, g, g_m2);
+            const int nvalid = min(32, b1 - b);
+            const double l1 = shfl_d(g, nvalid - 1);
+            const double l2 = shfl_d(g, nvalid >= 2 ? nvalid - 2 : 0);
+            carry2 = (nvalid >= 2) ? l2 : carry1;
+            carry1 = l1;
+        }
+    }
+}
+
+// One thread per noted segment: rebuild the two end states from the step records and run the reference's
+// sub-interval logic, appending candidate hits.
+template <class AR>
+__global__ void __launch_bounds__(128) k_emit_candidates(const ScanParams p)
+{
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long traj = gid / HB_CAND_CAP;
+    const int slot = (int)(gid - traj * HB_CAND_CAP);
+    if (traj >= p.n) return;
+    int nd = p.desc_count[traj];
+    if (nd > HB_CAND_CAP) nd = HB_CAND_CAP;
+    if (slot >= nd) return;
+    const double *d = p.desc + (traj * HB_CAND_CAP + slot) * HB_DESC_DOUBLES;
+    const int cs = (int)d[0], s0 = (int)d[1], s1 = (int)d[2];
+    const double *base = p.rec + traj * (long long)p.rec_cap * HB_REC_DOUBLES;
+    double x0[6], x1[6];
+    state_from_record<AR>(base + (long long)s0 * HB_REC_DOUBLES, p.t_eval[cs - 1], x0);
+    state_from_record<AR>(base + (long long)s1 * HB_REC_DOUBLES, p.t_eval[cs], x1);
+    auto emit = [&](int order, double th, const double (&xh)[6]) {
+        const int k = atomicAdd(&p.cand_count[traj], 1);
+        if (k < HB_CAND_CAP) {
+            double *c = p.cand + (traj * HB_CAND_CAP + k) * HB_CAND_DOUBLES;
+            c[0] = (double)cs * 4096.0 + (double)order;        // sort key: grid segment, then order inside it
+            c[1] = th;
+#pragma unroll
+            for (int q = 0; q < 6; ++q) c[2 + q] = xh[q];
+        }
+    };
+    segment_candidates(p.sink.sec, cs > 1, d[5], d[3], d[4], __dmul_rn(p.tsign, p.t_eval[cs - 1]),
+                       __dmul_rn(p.tsign, p.t_eval[cs]), x0, x1, emit);
+}
+
+// _order_and_dedup_hits (backend.py:430-455) on the candidates of one trajectory
+__global__ void __launch_bounds__(256) k_order_dedup(const ScanParams p)
+{
+    const long long traj = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (traj >= p.n) return;
+    int k = p.cand_count[traj];
+    if (p.nacc[traj] > p.rec_cap || k > HB_CAND_CAP || p.desc_count[traj] > HB_CAND_CAP) {
+        if (p.status[traj] == HB_TRAJ_OK) p.status[traj] = HB_TRAJ_RECORD_OVERFLOW;
+        if (k > HB_CAND_CAP) k = HB_CAND_CAP;
+    }
+    const double *c = p.cand + traj * HB_CAND_CAP * HB_CAND_DOUBLES;
+    unsigned long long used = 0ULL;
+    Dedup dd{0.0, 0.0, 0.0, 0};
+    for (int it = 0; it < k; ++it) {
+        int best = -1;
+        double bk = 0.0;
+        for (int j = 0; j < k; ++j) {                        // k is tiny: selection by key
+            if ((used >> j) & 1ULL) continue;
+            const double key = c[j * HB_CAND_DOUBLES];
+            if (best < 0 || key < bk) { best = j; bk = key; }
+        }
+        used |= 1ULL << best;
+        const double *e = c + best * HB_CAND_DOUBLES;
+        const double xh[6] = {e[2], e[3], e[4], e[5], e[6], e[7]};
+        if (!push_hit(p.sink, dd, traj, e[1], xh, 0)) break;
+    }
+    if (p.hits_per_traj) p.hits_per_traj[traj] = dd.n;
+}
+
+}  // namespace
+
+extern "C" int64_t hb_section2_scratch_bytes(int64_t n, int32_t steps_capacity)
+{
+    if (n < 0 || steps_capacity < 1) return -1;
+    steps_capacity = (steps_capacity + 31) / 32 * 32;
+    return n * ((int64_t)steps_capacity * HB_REC_DOUBLES + HB_CAND_CAP * (HB_CAND_DOUBLES + HB_DESC_DOUBLES) + 1) *
+           (int64_t)sizeof(double);
+}
+
+extern "C" int hb_cr3bp_section2(const hb_cr3bp *sys, const hb_integ *integ, const hb_section *sec, int64_t n,
+                                 const double *y0_soa, const double *t_eval, int32_t m, hb_hit *hits,
+                                 int64_t hit_capacity, int32_t *hits_per_traj, double *yf_soa, int32_t *n_acc,
+                                 int32_t *n_rej, int32_t *status, void *scratch, int64_t scratch_bytes, void *workspace,
+                                 void *stream)
+{
+    if (!sys || !integ || !sec) return HB_ERR_BADARG;
+    if (integ->method != HB_DOP853) return HB_ERR_UNSUPPORTED;
+    if (sec->idx < 0 || sec->idx > 5 || sec->proj_i < 0 || sec->proj_i > 5 || sec->proj_j < 0 || sec->proj_j > 5 ||
+        sec->segment_refine < 0 || hit_capacity < 0)
+        return HB_ERR_BADARG;
+    if (n < 0 || m < 2 || !workspace || !t_eval ||
+        (n > 0 && (!y0_soa || !yf_soa || !n_acc || !n_rej || !status || !scratch || (hit_capacity > 0 && !hits))))
+        return HB_ERR_BADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n == 0) { HB_CUDA_TRY(cudaMemsetAsync(workspace, 0, sizeof(HbWorkspace), st)); return HB_OK; }
+    const long long per_traj_fixed = (HB_CAND_CAP * (HB_CAND_DOUBLES + HB_DESC_DOUBLES) + 1) * (long long)sizeof(double);
+    long long cap = (scratch_bytes / n - per_traj_fixed) / (HB_REC_DOUBLES * (long long)sizeof(double));
+    cap -= cap % 32;                                 // one warp of k_step_candidates = 32 records of ONE trajectory
+    if (cap < 32) return HB_ERR_BADARG;
+    const int rec_cap = cap > 100000 ? 99968 : (int)cap;
+    double *rec = (double *)scratch;
+    double *cand = rec + n * (long long)rec_cap * HB_REC_DOUBLES;
+    double *desc = cand + n * (long long)HB_CAND_CAP * HB_CAND_DOUBLES;
+    int *cand_count = (int *)(desc + n * (long long)HB_CAND_CAP * HB_DESC_DOUBLES);    // n doubles = 2n ints
+    int *desc_count = cand_count + n;
+    double ends[2];
+    HB_CUDA_TRY(cudaMemcpyAsync(&ends[0], t_eval, sizeof(double), cudaMemcpyDeviceToHost, st));
+    HB_CUDA_TRY(cudaMemcpyAsync(&ends[1], t_eval + (m - 1), sizeof(double), cudaMemcpyDeviceToHost, st));
+    HB_CUDA_TRY(cudaStreamSynchronize(st));
+    HB_CUDA_TRY(cudaMemsetAsync(cand_count, 0, sizeof(int) * 2 * (size_t)n, st));
+    int rc = hb_cr3bp_record_launch(sys, integ, sec->idx, n, y0_soa, ends[0], ends[1], rec, rec_cap, yf_soa, n_acc, n_rej,
+                                    status, workspace, st);
+    if (rc != HB_OK) return rc;
+    ScanParams p{};
+    p.n = n; p.rec = rec; p.rec_cap = rec_cap; p.nacc = n_acc; p.status = status;
+    p.t_eval = t_eval; p.m = m;
+    p.tsign = sys->fwd < 0 ? -1.0 : 1.0;
+    p.inv_grid_dt = (ends[1] > ends[0]) ? (double)(m - 1) / (ends[1] - ends[0]) : 0.0;
+    p.sink.sec = *sec; p.sink.hits = hits; p.sink.capacity = hit_capacity; p.sink.ws = (HbWorkspace *)workspace;
+    p.hits_per_traj = hits_per_traj;
+    p.cand_count = cand_count; p.cand = cand; p.desc_count = desc_count; p.desc = desc;
+    const int threads = 256;
+    const long long total = n * (long long)rec_cap;
+    const long long b1 = (total + threads - 1) / threads;
+    if (b1 > 2147483647LL) return HB_ERR_BADARG;
+    if (integ->arith == HB_ARITH_PARITY) k_step_candidates<ArParity><<<(unsigned)b1, threads, 0, st>>>(p);
+    else k_step_candidates<ArFast><<<(unsigned)b1, threads, 0, st>>>(p);
+    HB_CUDA_TRY(cudaGetLastError());
+    {
+        const long long tb = (n * HB_CAND_CAP + 127) / 128;
+        if (integ->arith == HB_ARITH_PARITY) k_emit_candidates<ArParity><<<(unsigned)tb, 128, 0, st>>>(p);
+        else k_emit_candidates<ArFast><<<(unsigned)tb, 128, 0, st>>>(p);
+        HB_CUDA_TRY(cudaGetLastError());
+    }
+    k_order_dedup<<<(unsigned)((n + threads - 1) / threads), threads, 0, st>>>(p);
+    HB_CUDA_TRY(cudaGetLastError());
+    return HB_OK;
+}

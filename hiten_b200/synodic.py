@@ -137,7 +137,10 @@ class TubeSectionRunner:
     """Pre-allocated, repeatable form of tube_section for resident batches (what bench.py times): all device
     buffers are created once; run() launches hb_cr3bp_section and returns the hit count."""
 
-    def __init__(self, n, mu, t_eval, section, *, forward=1, flip=None, integ=None, hit_capacity=None, device=None):
+    def __init__(self, n, mu, t_eval, section, *, forward=1, flip=None, integ=None, hit_capacity=None, device=None,
+                 steps_capacity=0):
+        """steps_capacity > 0 selects the two-kernel path (hb_cr3bp_section2) with a scratch for that many accepted
+        steps per trajectory; 0 the fused kernel (hb_cr3bp_section)."""
         from . import propagate as P
         _require_cuda()
         self.lib = L.load()
@@ -153,8 +156,21 @@ class TubeSectionRunner:
         self.sys = P.make_sys(mu, forward, flip)
         self.cap = int(hit_capacity) if hit_capacity is not None else max(1024, 8 * self.n)
         self.hits = torch.empty(self.cap * 9, dtype=torch.float64, device=self.device)
+        self.steps_capacity = int(steps_capacity)
+        self.scratch = None
+        if self.steps_capacity > 0:
+            nbytes = int(self.lib.hb_section2_scratch_bytes(self.n, self.steps_capacity))
+            self.scratch = torch.empty(nbytes // 8, dtype=torch.float64, device=self.device)
 
     def launch(self, y0_soa, stream=None):
+        if self.scratch is not None:
+            rc = self.lib.hb_cr3bp_section2(self.sys, self.integ, self.section, self.n, y0_soa.data_ptr(),
+                                            self.te.data_ptr(), self.te.numel(), self.hits.data_ptr(), self.cap,
+                                            self.per.data_ptr(), self.yf.data_ptr(), self.nacc.data_ptr(),
+                                            self.nrej.data_ptr(), self.status.data_ptr(), self.scratch.data_ptr(),
+                                            self.scratch.numel() * 8, self.ws.data_ptr(), _stream_ptr(stream))
+            L.check(rc, "hb_cr3bp_section2")
+            return
         rc = self.lib.hb_cr3bp_section(self.sys, self.integ, self.section, self.n, y0_soa.data_ptr(),
                                        self.te.data_ptr(), self.te.numel(), self.hits.data_ptr(), self.cap,
                                        self.per.data_ptr(), self.yf.data_ptr(), self.nacc.data_ptr(),
@@ -169,3 +185,12 @@ class TubeSectionRunner:
         if no.value:
             raise L.HitenB200Error(f"hit buffer overflow: {no.value} hits dropped (capacity {self.cap})")
         return int(nh.value)
+
+    def sorted_hits(self, stream=None):
+        """SectionHits in the reference's order (by trajectory, then along the trajectory)."""
+        k = self.hit_count(stream)
+        rec = self.hits[: k * 9].cpu().numpy().view(HIT_DTYPE) if k else np.empty(0, dtype=HIT_DTYPE)
+        rec = rec[np.lexsort((rec["seq"], rec["traj"]))]
+        sec = self.section
+        pts = np.column_stack((rec["state"][:, sec.proj_i], rec["state"][:, sec.proj_j])) if k else np.empty((0, 2))
+        return SectionHits(rec["traj"].copy(), rec["t"].copy(), rec["state"].copy(), pts, self.per[: self.n].cpu().numpy())

@@ -43,6 +43,7 @@ extern "C" {
 #define HB_TRAJ_HIT 1        /* terminal event found                                  */
 #define HB_TRAJ_MAXSTEPS 2   /* attempt cap reached before tf                         */
 #define HB_TRAJ_NONFINITE 3  /* state or step size became NaN/Inf                     */
+#define HB_TRAJ_RECORD_OVERFLOW 4 /* hb_cr3bp_section2: more accepted steps than the scratch holds; rerun with hb_cr3bp_section */
 
 /* integrator ids = RungeKutta._map keys (algorithms/integrators/rk.py:2950) */
 #define HB_RK4 4
@@ -145,6 +146,18 @@ int hb_cr3bp_section(const hb_cr3bp *sys, const hb_integ *integ, const hb_sectio
                      const double *y0_soa, const double *t_eval, int32_t m, hb_hit *hits, int64_t hit_capacity,
                      int32_t *hits_per_traj, double *yf_soa, int32_t *n_acc, int32_t *n_rej, int32_t *status,
                      void *workspace, void *stream);
+
+/* The same result as hb_cr3bp_section computed as TWO kernels with a compact intermediate (hb_section_scan.cu):
+ * the propagation kernel records the dense-output coefficients of every accepted step (416 B per step) in
+ * `scratch`, then a warp-per-trajectory kernel applies the detector to the records.  Faster than the fused kernel
+ * (which is instruction-fetch bound) whenever the scratch fits: hb_section2_scratch_bytes(n, steps_capacity) bytes
+ * for at most steps_capacity accepted steps per trajectory.  Trajectories that need more get
+ * status = HB_TRAJ_RECORD_OVERFLOW (their hits are incomplete): rerun those with hb_cr3bp_section.          */
+int64_t hb_section2_scratch_bytes(int64_t n, int32_t steps_capacity);
+int hb_cr3bp_section2(const hb_cr3bp *sys, const hb_integ *integ, const hb_section *sec, int64_t n,
+                      const double *y0_soa, const double *t_eval, int32_t m, hb_hit *hits, int64_t hit_capacity,
+                      int32_t *hits_per_traj, double *yf_soa, int32_t *n_acc, int32_t *n_rej, int32_t *status,
+                      void *scratch, int64_t scratch_bytes, void *workspace, void *stream);
 
 /* Propagation with a terminal plane event (event always terminal, as in the reference):
  * replaces _integrate_dop853_until_event + _dop853_refine_in_step (rk.py:2680-2803, 2006-2102).

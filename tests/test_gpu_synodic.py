@@ -89,3 +89,47 @@ def test_fused_section_equals_two_kernel_chain(name):
     assert np.array_equal(res.yf, dense.states[:, -1, :].cpu().numpy())
     assert len(fused.times) == len(g["hit_time"])
     assert np.abs(fused.points - g["hit_point"]).max() <= 1e-9
+
+
+@pytest.mark.parametrize("name", ["c1", "c2"])
+@pytest.mark.parametrize("arith", ["parity", "fast"])
+def test_two_kernel_section_equals_fused(name, arith):
+    """hb_cr3bp_section2 (record + scan) == hb_cr3bp_section, bit for bit; parity also == the reference's hits."""
+    import torch
+    import hiten_b200 as hb
+    from hiten_b200 import synodic
+    g = np.load(os.path.join(HERE, "golden", f"synodic_{name}.npz"))
+    mu, tf, steps, fwd = float(g["mu"]), float(g["tf"]), int(g["steps"]), int(g["forward"])
+    t_eval = np.linspace(0.0, tf, steps)
+    sec = _section(g)
+    y0 = torch.from_numpy(np.ascontiguousarray(g["x0W"].T)).cuda()
+    integ = hb.make_integ(arith=arith)
+    a = synodic.TubeSectionRunner(len(g["x0W"]), mu, t_eval, sec, forward=fwd, flip=(0, 6), integ=integ)
+    b = synodic.TubeSectionRunner(len(g["x0W"]), mu, t_eval, sec, forward=fwd, flip=(0, 6), integ=integ, steps_capacity=256)
+    a.launch(y0); b.launch(y0)
+    ha, hb_ = a.sorted_hits(), b.sorted_hits()
+    assert (b.status == 0).all().item()
+    assert np.array_equal(ha.trajectory_indices, hb_.trajectory_indices)
+    assert np.array_equal(ha.hits_per_traj, hb_.hits_per_traj)
+    assert torch.equal(a.nacc, b.nacc)
+    if arith == "parity":      # separately rounded arithmetic: identical in every kernel
+        assert np.array_equal(ha.times, hb_.times) and np.array_equal(ha.states, hb_.states)
+        assert torch.equal(a.yf, b.yf)
+    else:                      # FMA contraction differs between kernels in the fast variant
+        assert np.abs(ha.points - hb_.points).max() <= 1e-8 and np.abs(ha.times - hb_.times).max() <= 1e-8
+    if arith == "parity":
+        assert np.array_equal(hb_.times, g["hit_time"]) and np.array_equal(hb_.states, g["hit_state"])
+
+
+def test_two_kernel_overflow_is_flagged():
+    import torch
+    import hiten_b200 as hb
+    from hiten_b200 import synodic
+    g = np.load(os.path.join(HERE, "golden", "synodic_c1.npz"))
+    t_eval = np.linspace(0.0, float(g["tf"]), int(g["steps"]))
+    y0 = torch.from_numpy(np.ascontiguousarray(g["x0W"].T)).cuda()
+    r = synodic.TubeSectionRunner(50, float(g["mu"]), t_eval, _section(g), forward=-1, flip=(0, 6), steps_capacity=80)
+    r.launch(y0)
+    st = r.status.cpu().numpy()
+    na = r.nacc.cpu().numpy()
+    assert ((st == 4) == (na > 96)).all() and (st == 4).any() and (st == 0).any()      # capacity rounds up to 96

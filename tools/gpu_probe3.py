@@ -15,7 +15,7 @@ t_eval = np.linspace(0.0, bench.TF, m)
 sec = synodic.make_section("y", 0.0, ("x", "z"), -1)
 for arith in ("parity", "fast"):
     integ = hb.make_integ(arith=arith)
-    run = synodic.TubeSectionRunner(n, mu, t_eval, sec, forward=-1, flip=(0, 6), integ=integ)
+    run = synodic.TubeSectionRunner(n, mu, t_eval, sec, forward=-1, flip=(0, 6), integ=integ, steps_capacity=int(os.environ.get("HB_STEPS_CAP", "0")))
     for kind in ("propagate", "section"):
         best = 1e9
         for rep in range(6):
