@@ -140,38 +140,27 @@ __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) k_dop853_6(const PropP
                 }
                 if (last) fin = HB_TRAJ_OK;
             } else if (MODE == MODE_RECORD) {
-                // Store the dense interpolant of every accepted step (400 B) for the section-scan kernel; the end
-                // state is the last grid sample = the interpolant at tf on the last segment.
-                const double hseg = AR::sub(t_new, t);
-                double F[7][6];
-                if (hseg != 0.0) dense_cache<AR>(y, yh, hseg, k, F, rhs);
+                // Store what the dense output of this accepted step depends on (512 B, sixteen 256-bit stores); the
+                // section-scan kernels rebuild the interpolant where they need it (hb_section_scan.cu).
                 if (nacc <= p.rec_cap) {
                     double *r = p.rec + ((long long)idx * p.rec_cap + (nacc - 1)) * HB_REC_DOUBLES;
-                    r[0] = t; r[1] = t_new; r[2] = hseg; r[3] = pick6(y, p.sink.sec.idx);
+                    hb_st4(r + 0, t, t_new, y[0], y[1]);
+                    hb_st4(r + 4, y[2], y[3], y[4], y[5]);
+                    hb_st4(r + 8, yh[0], yh[1], yh[2], yh[3]);
+                    hb_st4(r + 12, yh[4], yh[5], k[5][0], k[5][1]);
+                    hb_st4(r + 16, k[5][2], k[5][3], k[5][4], k[5][5]);
 #pragma unroll
-                    for (int i = 0; i < 7; ++i) r[4 + i] = (hseg != 0.0) ? pick6(F[i], p.sink.sec.idx) : 0.0;
-#pragma unroll
-                    for (int d = 0; d < 6; ++d) r[HB_REC_Y + d] = y[d];
-                    if (hseg != 0.0) {
-#pragma unroll
-                        for (int i = 0; i < 7; ++i)
-#pragma unroll
-                            for (int d = 0; d < 6; ++d) r[HB_REC_F + 6 * i + d] = F[i][d];
+                    for (int j = 6; j < 12; j += 2) {
+                        double *q = r + HB_REC_K5 + 6 * (j - 5);
+                        hb_st4(q + 0, k[j][0], k[j][1], k[j][2], k[j][3]);
+                        hb_st4(q + 4, k[j][4], k[j][5], k[j + 1][0], k[j + 1][1]);
+                        hb_st4(q + 8, k[j + 1][2], k[j + 1][3], k[j + 1][4], k[j + 1][5]);
                     }
+                    hb_st4(r + 56, k[12][0], k[12][1], k[12][2], k[12][3]);
+                    hb_st4(r + 60, k[12][4], k[12][5], 0.0, 0.0);
                 }
-                if (last) {
-                    double yo[6];
-                    if (hseg == 0.0) {
-#pragma unroll
-                        for (int d = 0; d < 6; ++d) yo[d] = y[d];
-                    } else {
-                        dense_eval<AR>(y, F, AR::div(AR::sub(tf, t), hseg), yo);
-                    }
-#pragma unroll
-                    for (int d = 0; d < 6; ++d) p.yf[(long long)d * p.n + idx] = yo[d];
-                    fin = (nacc <= p.rec_cap) ? HB_TRAJ_OK : HB_TRAJ_RECORD_OVERFLOW;
-                }
-            } else {  // MODE_FINAL: the dense interpolant at tf on the last segment
+            }
+            if (MODE == MODE_RECORD || MODE == MODE_FINAL) {   // the dense interpolant at tf on the last segment
                 if (last) {
                     const double hseg = AR::sub(t_new, t);
                     double yo[6];
@@ -192,7 +181,7 @@ __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) k_dop853_6(const PropP
                     }
 #pragma unroll
                     for (int d = 0; d < 6; ++d) p.yf[(long long)d * p.n + idx] = yo[d];
-                    fin = HB_TRAJ_OK;
+                    fin = (MODE == MODE_RECORD && nacc > p.rec_cap) ? HB_TRAJ_RECORD_OVERFLOW : HB_TRAJ_OK;
                 }
             }
             // advance

@@ -40,16 +40,33 @@ struct PropParams {
     int *hits_per_traj;
     double tsign;          // sign applied to grid times for the detector (times = forward * t_eval)
     double inv_grid_dt;    // (m-1)/(t_eval[m-1]-t_eval[0]): first guess when locating grid samples
-    double *rec;           // MODE_RECORD: per-step dense records [n][rec_cap][HB_REC_DOUBLES]
+    double *rec;           // MODE_RECORD: per-step stage records [n][rec_cap][HB_REC_DOUBLES]
     int rec_cap;
 };
 
 // One accepted step as stored by MODE_RECORD (hb_cr3bp.cu) and consumed by the scan kernels (hb_section_scan.cu):
 //   header (3 sectors): [0] t_old [1] t_new [2] hseg [3] y_old[sidx] [4..10] F[0..6][sidx]   (event component)
 //   body              : [11..16] y_old  [17..58] F[7][6] row-major  [59] pad
-#define HB_REC_DOUBLES 60
-#define HB_REC_Y 11
-#define HB_REC_F 17
+// MODE_RECORD step record (512 B = 16 x 32-byte sectors, written/read with 256-bit accesses): everything the dense
+// output of one accepted step is a function of.  Stages 2..5 do not enter it (the extra-stage rows and D have zero
+// columns 1..4) and k1 = f(y_old) is recomputed by the consumer.
+#define HB_REC_DOUBLES 64
+#define HB_REC_T 0        // t_old, t_new
+#define HB_REC_YOLD 2
+#define HB_REC_YNEW 8
+#define HB_REC_K5 14      // k[5..11] (7 x 6)
+#define HB_REC_K12 56     // k[12] = f(y_new); [62], [63] unused
+// event-component header derived from a record by k_step_headers (hb_section_scan.cu)
+#define HB_HDR_DOUBLES 12 // t_old, t_new, hseg, y_c, F_0..6,c, pad
+
+HB_DEV void hb_st4(double *p, double a, double b, double c, double d)
+{
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+HB_DEV void hb_ld4(const double *p, double &a, double &b, double &c, double &d)
+{
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
 
 // ---------------------------------------------------------------------------------------------
 // Vector field.  Parity form keeps rtbp.py:65-74's operation order:

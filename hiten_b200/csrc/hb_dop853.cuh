@@ -202,6 +202,69 @@ HB_DEV void dense_cache(const double (&y_old)[6], const double (&y_new)[6], doub
     d_rows<AR, 0>(F, h, k, kx);
 }
 
+// The same interpolant restricted to ONE component c, with the stage rows STREAMED in ascending order into the
+// accumulators of the three extra stages and of the four D rows (each accumulator still sees its terms in the
+// reference's order, so the numbers are those of dense_cache).  `row(R, kr)` delivers k[R] for R = 5..12;
+// k[0] = f(y_old) is evaluated here.  Used by the section-scan kernel, which needs ~1/6 of F and little state.
+template <class AR, int R>
+HB_DEV void stream_row(const double (&kr)[6], double kc, double (&a13)[6], double (&a14)[6], double (&a15)[6],
+                       double (&da)[4])
+{
+    constexpr double c13 = HB_DOP853_A[13][R], c14 = HB_DOP853_A[14][R], c15 = HB_DOP853_A[15][R];
+    constexpr double d0 = HB_DOP853_D[0][R], d1 = HB_DOP853_D[1][R], d2 = HB_DOP853_D[2][R], d3 = HB_DOP853_D[3][R];
+#pragma unroll
+    for (int d = 0; d < 6; ++d) {
+        if constexpr (c13 != 0.0) a13[d] = AR::madd(c13, kr[d], a13[d]);
+        if constexpr (R < 14 && c14 != 0.0) a14[d] = AR::madd(c14, kr[d], a14[d]);
+        if constexpr (R < 15 && c15 != 0.0) a15[d] = AR::madd(c15, kr[d], a15[d]);
+    }
+    if constexpr (d0 != 0.0) da[0] = AR::madd(d0, kc, da[0]);
+    if constexpr (d1 != 0.0) da[1] = AR::madd(d1, kc, da[1]);
+    if constexpr (d2 != 0.0) da[2] = AR::madd(d2, kc, da[2]);
+    if constexpr (d3 != 0.0) da[3] = AR::madd(d3, kc, da[3]);
+}
+
+template <class AR, class RHS, class ROW, class PICK>
+HB_DEV void dense_component(const double (&y_old)[6], const double (&y_new)[6], double h, ROW row, PICK pick,
+                            const RHS &rhs, double (&f)[7])
+{
+    static_assert(HB_DOP853_A[13][13] == 0.0 && HB_DOP853_A[13][14] == 0.0 && HB_DOP853_A[14][14] == 0.0, "tableau");
+    double a13[6], a14[6], a15[6], da[4] = {0.0, 0.0, 0.0, 0.0}, kr[6], ys[6];
+#pragma unroll
+    for (int d = 0; d < 6; ++d) { a13[d] = 0.0; a14[d] = 0.0; a15[d] = 0.0; }
+    rhs(y_old, kr);
+    const double k0c = pick(kr);
+    stream_row<AR, 0>(kr, k0c, a13, a14, a15, da);
+    row(5, kr);  stream_row<AR, 5>(kr, pick(kr), a13, a14, a15, da);
+    row(6, kr);  stream_row<AR, 6>(kr, pick(kr), a13, a14, a15, da);
+    row(7, kr);  stream_row<AR, 7>(kr, pick(kr), a13, a14, a15, da);
+    row(8, kr);  stream_row<AR, 8>(kr, pick(kr), a13, a14, a15, da);
+    row(9, kr);  stream_row<AR, 9>(kr, pick(kr), a13, a14, a15, da);
+    row(10, kr); stream_row<AR, 10>(kr, pick(kr), a13, a14, a15, da);
+    row(11, kr); stream_row<AR, 11>(kr, pick(kr), a13, a14, a15, da);
+    row(12, kr);
+    const double k12c = pick(kr);
+    stream_row<AR, 12>(kr, k12c, a13, a14, a15, da);
+#pragma unroll
+    for (int d = 0; d < 6; ++d) ys[d] = AR::madd(h, a13[d], y_old[d]);
+    rhs(ys, kr);
+    stream_row<AR, 13>(kr, pick(kr), a13, a14, a15, da);
+#pragma unroll
+    for (int d = 0; d < 6; ++d) ys[d] = AR::madd(h, a14[d], y_old[d]);
+    rhs(ys, kr);
+    stream_row<AR, 14>(kr, pick(kr), a13, a14, a15, da);
+#pragma unroll
+    for (int d = 0; d < 6; ++d) ys[d] = AR::madd(h, a15[d], y_old[d]);
+    rhs(ys, kr);
+    stream_row<AR, 15>(kr, pick(kr), a13, a14, a15, da);
+    const double dy = AR::sub(pick(y_new), pick(y_old));
+    f[0] = dy;
+    f[1] = AR::sub(AR::mul(h, k0c), dy);
+    f[2] = AR::sub(AR::mul(2.0, dy), AR::mul(h, AR::add(k12c, k0c)));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) f[3 + i] = AR::mul(h, da[i]);
+}
+
 // _dop853_eval_dense (rk.py:1989-2003): alternating x / (1-x) Horner form.
 template <class AR>
 HB_DEV void dense_eval(const double (&y_old)[6], const double (&F)[7][6], double x, double (&out)[6])

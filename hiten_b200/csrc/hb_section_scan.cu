@@ -1,15 +1,18 @@
 // hb_section_scan.cu -- tube + synodic section as a short pipeline with a compact intermediate (hb_cr3bp_section2).
 //
-//   A  k_dop853_6<.., MODE_RECORD, ..> (hb_cr3bp.cu): the plain propagation kernel, which additionally builds the
-//      dense-output coefficients of every accepted step and stores them (480 B per step: an event-component header
-//      t_old, t_new, hseg, y_c, F_0..6,c followed by y_old and F[7][6]) in a caller-provided scratch
-//      [n][cap][60] -- ~40 KB per trajectory instead of the 226 KB of the 4713-sample tube;
-//   B1 k_step_candidates: ONE THREAD PER STEP RECORD (fully parallel: ~1e7 threads).  From the header alone it finds
-//      the grid samples the step owns and proves most steps quiet (interpolant bound, see hb_cr3bp_section.cu);
-//      the others evaluate the event component at their samples, and segments that can hold a hit run the
-//      reference's sub-interval logic and append CANDIDATE hits {sample index, order, t, state} to a small
-//      per-trajectory list;
-//   B2 k_order_dedup: one thread per trajectory sorts its few candidates into the reference's order and applies
+//   A  k_dop853_6<.., MODE_RECORD, ..> (hb_cr3bp.cu): the plain propagation kernel, which additionally stores what
+//      the dense output of every accepted step depends on (512 B: t_old, t_new, y_old, y_new, k6..k13) in a
+//      caller-provided scratch [n][cap][64] -- ~45 KB per trajectory instead of the 226 KB of the 4713-sample tube.
+//      It does NOT build the interpolant: that would double the loop body of a kernel that is instruction-fetch bound;
+//   B0 k_step_headers: one thread per step record.  Runs the three extra DOP853 stages, builds the interpolant
+//      and keeps its EVENT COMPONENT (96 B header: t_old, t_new, hseg, y_c, F_0..6,c);
+//   B1 k_step_candidates: one thread per step header (a warp = 32 consecutive steps of one trajectory).  Finds the
+//      grid samples the step owns and proves most steps quiet (interpolant bound, see hb_cr3bp_section.cu); the
+//      others are scanned by the whole warp, 32 grid samples per instruction, and the segments that can hold a hit
+//      are NOTED (6 numbers);
+//   B2 k_emit_candidates: one thread per noted segment rebuilds the two end states from the step records, runs
+//      the reference's sub-interval logic and appends CANDIDATE hits {sample index, order, t, state};
+//   B3 k_order_dedup: one thread per trajectory sorts its few candidates into the reference's order and applies
 //      _order_and_dedup_hits (dedup against the previous kept hit, max_hits_per_traj), appending the hits.
 //
 // Why: the fused kernel (hb_cr3bp_section.cu) carries the scan state and 42 dense coefficients through the
@@ -32,11 +35,13 @@ using namespace hbc;
 
 constexpr int HB_CAND_CAP = 32;       // candidate hits per trajectory (before de-duplication)
 constexpr int HB_CAND_DOUBLES = 8;    // key, t, state[6]
-constexpr int HB_DESC_DOUBLES = 6;
+constexpr int HB_DESC_DOUBLES = 8;    // traj, cs, step of cs-1, step of cs, g(cs-1), g(cs), g(cs-2), pad
 
 struct ScanParams {
+    PropParams prop;        // mu, 1-mu, sign mask (vector field of the extra stages)
     long long n;
-    const double *rec;
+    const double *rec;      // [n][rec_cap][HB_REC_DOUBLES] stage records
+    double *hdr;            // [n][rec_cap][HB_HDR_DOUBLES] event-component headers
     int rec_cap;
     const int *nacc;
     int *status;
@@ -48,7 +53,8 @@ struct ScanParams {
     int *cand_count;        // [n]
     double *cand;           // [n][HB_CAND_CAP][HB_CAND_DOUBLES]
     int *desc_count;        // [n]   segments that can hold a hit, found by k_step_candidates
-    double *desc;           // [n][HB_CAND_CAP][HB_DESC_DOUBLES] = {cs, step of cs-1, step of cs, g(cs-1), g(cs), g(cs-2)}
+    int *desc_total;        // [1]   length of the (global, unordered) list below
+    double *desc;           // [n * HB_CAND_CAP][HB_DESC_DOUBLES]
 };
 
 template <class AR>
@@ -71,23 +77,43 @@ HB_DEV double g_comp(const double *hdr, double xq, double offset)     // hdr = r
 template <class AR>
 HB_DEV double xpar(double tq, double t, double hseg) { return (hseg == 0.0) ? 0.0 : AR::div(AR::sub(tq, t), hseg); }
 
+// y_old, y_new and the stage rows the dense output uses (k[1..4] do not enter it; k[0] = f(y_old) is recomputed)
 template <class AR>
-HB_DEV void state_from_record(const double *r, double tq, double (&out)[6])
+HB_DEV void load_record(const double *r, const PropParams &pp, double &t_old, double &t_new, double (&y)[6],
+                        double (&yn)[6], double (&k)[13][6])
 {
-    const double t = r[0], hseg = r[2];
-    double y[6], F[7][6];
+    double v[HB_REC_DOUBLES];
 #pragma unroll
-    for (int d = 0; d < 6; ++d) y[d] = r[HB_REC_Y + d];
+    for (int i = 0; i < HB_REC_DOUBLES; i += 4) hb_ld4(r + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+    t_old = v[0]; t_new = v[1];
+#pragma unroll
+    for (int d = 0; d < 6; ++d) {
+        y[d] = v[HB_REC_YOLD + d];
+        yn[d] = v[HB_REC_YNEW + d];
+#pragma unroll
+        for (int j = 1; j < 5; ++j) k[j][d] = 0.0;
+#pragma unroll
+        for (int j = 5; j < 13; ++j) k[j][d] = v[HB_REC_K5 + 6 * (j - 5) + d];
+    }
+    crtbp_rhs<AR, 2>(y, pp, k[0]);
+}
+
+template <class AR>
+__device__ __noinline__ void states_from_record(const double *r, const PropParams &pp, double tq0, double tq1,
+                                                double (&out0)[6], double (&out1)[6])
+{
+    double t, t_new, y[6], yn[6], k[13][6], F[7][6];
+    load_record<AR>(r, pp, t, t_new, y, yn, k);
+    const double hseg = AR::sub(t_new, t);
     if (hseg == 0.0) {
 #pragma unroll
-        for (int d = 0; d < 6; ++d) out[d] = y[d];
+        for (int d = 0; d < 6; ++d) { out0[d] = y[d]; out1[d] = y[d]; }
         return;
     }
-#pragma unroll
-    for (int i = 0; i < 7; ++i)
-#pragma unroll
-        for (int d = 0; d < 6; ++d) F[i][d] = r[HB_REC_F + 6 * i + d];
-    dense_eval<AR>(y, F, xpar<AR>(tq, t, hseg), out);
+    const Cr3bpRhs<AR, 2> rhs{pp};
+    dense_cache<AR>(y, yn, hseg, k, F, rhs);
+    dense_eval<AR>(y, F, xpar<AR>(tq0, t, hseg), out0);
+    dense_eval<AR>(y, F, xpar<AR>(tq1, t, hseg), out1);
 }
 
 // first index c in [lo, m] with t_eval[c] >= tv  (guess from the uniform spacing, then fix up)
@@ -102,8 +128,8 @@ HB_DEV int first_at_or_after(const ScanParams &p, double tv, int lo)
 // record of the step that owns grid sample c, searching backwards from step s
 HB_DEV const double *owner_record(const double *base, int s, double tq)
 {
-    while (s > 0 && tq < base[(long long)s * HB_REC_DOUBLES]) --s;
-    return base + (long long)s * HB_REC_DOUBLES;
+    while (s > 0 && tq < base[(long long)s * HB_HDR_DOUBLES]) --s;
+    return base + (long long)s * HB_HDR_DOUBLES;
 }
 
 // _detect_with_segment_refine on ONE segment (linear branch), emitting raw candidates in order
@@ -167,14 +193,48 @@ HB_DEV void segment_candidates(const hb_section &sec, bool has_prev, double g_pr
 // into candidate hits.  Keeping the state reconstruction out of the scan kernel keeps it small (no spills, no call).
 HB_DEV void note_segment(const ScanParams &p, long long traj, int cs, int s0, int s1, double gk, double gk1, double gm2)
 {
-    const int slot = atomicAdd(&p.desc_count[traj], 1);
-    if (slot < HB_CAND_CAP) {
-        double *d = p.desc + (traj * HB_CAND_CAP + slot) * HB_DESC_DOUBLES;
-        d[0] = (double)cs; d[1] = (double)s0; d[2] = (double)s1; d[3] = gk; d[4] = gk1; d[5] = gm2;
-    }
+    // per-trajectory count = overflow check (and keeps the global list within n * HB_CAND_CAP)
+    if (atomicAdd(&p.desc_count[traj], 1) >= HB_CAND_CAP) return;
+    const int slot = atomicAdd(p.desc_total, 1);
+    double *d = p.desc + (long long)slot * HB_DESC_DOUBLES;
+    hb_st4(d, (double)traj, (double)cs, (double)s0, (double)s1);
+    hb_st4(d + 4, gk, gk1, gm2, 0.0);
 }
 
-// One warp = 32 consecutive step records of one trajectory (rec_cap is a multiple of 32).  Quiet tests run one
+// One thread per step record: the interpolant of the step, event component only.
+template <class AR>
+__global__ void __launch_bounds__(128, 4) k_step_headers(const ScanParams p)
+{
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long traj = gid / p.rec_cap;
+    const int s = (int)(gid - traj * p.rec_cap);
+    if (traj >= p.n || s >= p.nacc[traj]) return;
+    const double *r = p.rec + gid * HB_REC_DOUBLES;
+    double v[16];
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) hb_ld4(r + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+    const double t = v[0], t_new = v[1];
+    const double y[6] = {v[2], v[3], v[4], v[5], v[6], v[7]}, yn[6] = {v[8], v[9], v[10], v[11], v[12], v[13]};
+    const double hseg = AR::sub(t_new, t);
+    const int c = p.sink.sec.idx;
+    double f[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    if (hseg != 0.0) {
+        const Cr3bpRhs<AR, 2> rhs{p.prop};
+        auto row = [&](int R, double (&kr)[6]) {
+            const double2 *q = (const double2 *)(r + HB_REC_K5 + 6 * (R - 5));
+            const double2 a = __ldg(q), b = __ldg(q + 1), cc = __ldg(q + 2);
+            kr[0] = a.x; kr[1] = a.y; kr[2] = b.x; kr[3] = b.y; kr[4] = cc.x; kr[5] = cc.y;
+        };
+        auto pick = [&](const double (&w)[6]) { return pick6(w, c); };
+        dense_component<AR>(y, yn, hseg, row, pick, rhs, f);
+    }
+    double *h = p.hdr + gid * HB_HDR_DOUBLES;
+    hb_st4(h + 0, t, t_new, hseg, pick6(y, c));
+    hb_st4(h + 4, f[0], f[1], f[2], f[3]);
+    hb_st4(h + 8, f[4], f[5], f[6], 0.0);
+}
+
+// One warp = 32 consecutive step headers of one trajectory (rec_cap is a multiple of 32).  Quiet tests run one
 // step per lane; the few non-quiet steps are then scanned by the whole warp, 32 grid samples per instruction.
 template <class AR>
 __global__ void __launch_bounds__(256, 2) k_step_candidates(const ScanParams p)
@@ -185,8 +245,8 @@ __global__ void __launch_bounds__(256, 2) k_step_candidates(const ScanParams p)
     const int s = (int)(gid - traj * p.rec_cap);
     if (traj >= p.n) return;                                  // whole warp (rec_cap % 32 == 0)
     const int nacc = p.nacc[traj];
-    const double *base = p.rec + traj * (long long)p.rec_cap * HB_REC_DOUBLES;
-    const double *r = base + (long long)s * HB_REC_DOUBLES;
+    const double *base = p.hdr + traj * (long long)p.rec_cap * HB_HDR_DOUBLES;
+    const double *r = base + (long long)s * HB_HDR_DOUBLES;
     const double off = p.sink.sec.offset, tol_s = p.sink.sec.tol_on_surface;
     const bool have_rec = s < nacc;
     double hdr[11];
@@ -221,7 +281,7 @@ __global__ void __launch_bounds__(256, 2) k_step_candidates(const ScanParams p)
                     for (int i = 0; i < 11; ++i) h2[i] = rq[i];
                     gm2 = g_comp<AR>(h2, xpar<AR>(p.t_eval[c0 - 2], h2[0], h2[2]), off);
                 }
-                note_segment(p, traj, c0, (int)((rp - base) / HB_REC_DOUBLES), s, g_prev, g_first, gm2);
+                note_segment(p, traj, c0, (int)((rp - base) / HB_HDR_DOUBLES), s, g_prev, g_first, gm2);
             }
         }
         scan = cend - c0 >= 2;
@@ -269,36 +329,41 @@ __global__ void __launch_bounds__(256, 2) k_step_candidates(const ScanParams p)
     }
 }
 
-// One thread per noted segment: rebuild the two end states from the step records and run the reference's
-// sub-interval logic, appending candidate hits.
+// One thread per noted segment (grid-stride over the global list): rebuild the two end states from the step
+// records and run the reference's sub-interval logic, appending candidate hits.
 template <class AR>
 __global__ void __launch_bounds__(128) k_emit_candidates(const ScanParams p)
 {
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long traj = gid / HB_CAND_CAP;
-    const int slot = (int)(gid - traj * HB_CAND_CAP);
-    if (traj >= p.n) return;
-    int nd = p.desc_count[traj];
-    if (nd > HB_CAND_CAP) nd = HB_CAND_CAP;
-    if (slot >= nd) return;
-    const double *d = p.desc + (traj * HB_CAND_CAP + slot) * HB_DESC_DOUBLES;
-    const int cs = (int)d[0], s0 = (int)d[1], s1 = (int)d[2];
-    const double *base = p.rec + traj * (long long)p.rec_cap * HB_REC_DOUBLES;
-    double x0[6], x1[6];
-    state_from_record<AR>(base + (long long)s0 * HB_REC_DOUBLES, p.t_eval[cs - 1], x0);
-    state_from_record<AR>(base + (long long)s1 * HB_REC_DOUBLES, p.t_eval[cs], x1);
-    auto emit = [&](int order, double th, const double (&xh)[6]) {
-        const int k = atomicAdd(&p.cand_count[traj], 1);
-        if (k < HB_CAND_CAP) {
-            double *c = p.cand + (traj * HB_CAND_CAP + k) * HB_CAND_DOUBLES;
-            c[0] = (double)cs * 4096.0 + (double)order;        // sort key: grid segment, then order inside it
-            c[1] = th;
-#pragma unroll
-            for (int q = 0; q < 6; ++q) c[2 + q] = xh[q];
+    const int total = *p.desc_total;
+    for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < total;
+         it += (long long)gridDim.x * blockDim.x) {
+        const double *d = p.desc + it * HB_DESC_DOUBLES;
+        double d0, d1, d2, d3, gk, gk1, gm2, pad;
+        hb_ld4(d, d0, d1, d2, d3);
+        hb_ld4(d + 4, gk, gk1, gm2, pad);
+        const long long traj = (long long)d0;
+        const int cs = (int)d1, s0 = (int)d2, s1 = (int)d3;
+        const double *base = p.rec + traj * (long long)p.rec_cap * HB_REC_DOUBLES;
+        double x0[6], x1[6];
+        if (s0 == s1) {
+            states_from_record<AR>(base + (long long)s1 * HB_REC_DOUBLES, p.prop, p.t_eval[cs - 1], p.t_eval[cs], x0, x1);
+        } else {
+            double dummy[6];
+            states_from_record<AR>(base + (long long)s0 * HB_REC_DOUBLES, p.prop, p.t_eval[cs - 1], p.t_eval[cs - 1], x0, dummy);
+            states_from_record<AR>(base + (long long)s1 * HB_REC_DOUBLES, p.prop, p.t_eval[cs], p.t_eval[cs], x1, dummy);
         }
-    };
-    segment_candidates(p.sink.sec, cs > 1, d[5], d[3], d[4], __dmul_rn(p.tsign, p.t_eval[cs - 1]),
-                       __dmul_rn(p.tsign, p.t_eval[cs]), x0, x1, emit);
+        auto emit = [&](int order, double th, const double (&xh)[6]) {
+            const int k = atomicAdd(&p.cand_count[traj], 1);
+            if (k < HB_CAND_CAP) {
+                double *c = p.cand + (traj * HB_CAND_CAP + k) * HB_CAND_DOUBLES;
+                // sort key: grid segment, then order inside it
+                hb_st4(c, (double)cs * 4096.0 + (double)order, th, xh[0], xh[1]);
+                hb_st4(c + 4, xh[2], xh[3], xh[4], xh[5]);
+            }
+        };
+        segment_candidates(p.sink.sec, cs > 1, gm2, gk, gk1, __dmul_rn(p.tsign, p.t_eval[cs - 1]),
+                           __dmul_rn(p.tsign, p.t_eval[cs]), x0, x1, emit);
+    }
 }
 
 // _order_and_dedup_hits (backend.py:430-455) on the candidates of one trajectory
@@ -336,8 +401,8 @@ extern "C" int64_t hb_section2_scratch_bytes(int64_t n, int32_t steps_capacity)
 {
     if (n < 0 || steps_capacity < 1) return -1;
     steps_capacity = (steps_capacity + 31) / 32 * 32;
-    return n * ((int64_t)steps_capacity * HB_REC_DOUBLES + HB_CAND_CAP * (HB_CAND_DOUBLES + HB_DESC_DOUBLES) + 1) *
-           (int64_t)sizeof(double);
+    return n * ((int64_t)steps_capacity * (HB_REC_DOUBLES + HB_HDR_DOUBLES) + HB_CAND_CAP * (HB_CAND_DOUBLES + HB_DESC_DOUBLES) + 1) *
+               (int64_t)sizeof(double) + 256;
 }
 
 extern "C" int hb_cr3bp_section2(const hb_cr3bp *sys, const hb_integ *integ, const hb_section *sec, int64_t n,
@@ -357,42 +422,50 @@ extern "C" int hb_cr3bp_section2(const hb_cr3bp *sys, const hb_integ *integ, con
     cudaStream_t st = (cudaStream_t)stream;
     if (n == 0) { HB_CUDA_TRY(cudaMemsetAsync(workspace, 0, sizeof(HbWorkspace), st)); return HB_OK; }
     const long long per_traj_fixed = (HB_CAND_CAP * (HB_CAND_DOUBLES + HB_DESC_DOUBLES) + 1) * (long long)sizeof(double);
-    long long cap = (scratch_bytes / n - per_traj_fixed) / (HB_REC_DOUBLES * (long long)sizeof(double));
+    long long cap = ((scratch_bytes - 256) / n - per_traj_fixed) / ((HB_REC_DOUBLES + HB_HDR_DOUBLES) * (long long)sizeof(double));
     cap -= cap % 32;                                 // one warp of k_step_candidates = 32 records of ONE trajectory
     if (cap < 32) return HB_ERR_BADARG;
     const int rec_cap = cap > 100000 ? 99968 : (int)cap;
     double *rec = (double *)scratch;
-    double *cand = rec + n * (long long)rec_cap * HB_REC_DOUBLES;
+    double *hdr = rec + n * (long long)rec_cap * HB_REC_DOUBLES;
+    double *cand = hdr + n * (long long)rec_cap * HB_HDR_DOUBLES;
     double *desc = cand + n * (long long)HB_CAND_CAP * HB_CAND_DOUBLES;
     int *cand_count = (int *)(desc + n * (long long)HB_CAND_CAP * HB_DESC_DOUBLES);    // n doubles = 2n ints
     int *desc_count = cand_count + n;
+    int *desc_total = desc_count + n;                 // first of the 256 trailing bytes
     double ends[2];
     HB_CUDA_TRY(cudaMemcpyAsync(&ends[0], t_eval, sizeof(double), cudaMemcpyDeviceToHost, st));
     HB_CUDA_TRY(cudaMemcpyAsync(&ends[1], t_eval + (m - 1), sizeof(double), cudaMemcpyDeviceToHost, st));
     HB_CUDA_TRY(cudaStreamSynchronize(st));
-    HB_CUDA_TRY(cudaMemsetAsync(cand_count, 0, sizeof(int) * 2 * (size_t)n, st));
+    HB_CUDA_TRY(cudaMemsetAsync(cand_count, 0, sizeof(int) * (2 * (size_t)n + 1), st));
     int rc = hb_cr3bp_record_launch(sys, integ, sec->idx, n, y0_soa, ends[0], ends[1], rec, rec_cap, yf_soa, n_acc, n_rej,
                                     status, workspace, st);
     if (rc != HB_OK) return rc;
     ScanParams p{};
+    rc = fill_params(sys, integ, p.prop);
+    if (rc != HB_OK) return rc;
+    p.hdr = hdr;
     p.n = n; p.rec = rec; p.rec_cap = rec_cap; p.nacc = n_acc; p.status = status;
     p.t_eval = t_eval; p.m = m;
     p.tsign = sys->fwd < 0 ? -1.0 : 1.0;
     p.inv_grid_dt = (ends[1] > ends[0]) ? (double)(m - 1) / (ends[1] - ends[0]) : 0.0;
     p.sink.sec = *sec; p.sink.hits = hits; p.sink.capacity = hit_capacity; p.sink.ws = (HbWorkspace *)workspace;
     p.hits_per_traj = hits_per_traj;
-    p.cand_count = cand_count; p.cand = cand; p.desc_count = desc_count; p.desc = desc;
+    p.cand_count = cand_count; p.cand = cand; p.desc_count = desc_count; p.desc_total = desc_total; p.desc = desc;
     const int threads = 256;
     const long long total = n * (long long)rec_cap;
     const long long b1 = (total + threads - 1) / threads;
-    if (b1 > 2147483647LL) return HB_ERR_BADARG;
+    if (b1 > 1073741823LL) return HB_ERR_BADARG;
+    if (integ->arith == HB_ARITH_PARITY) k_step_headers<ArParity><<<(unsigned)(2 * b1), 128, 0, st>>>(p);
+    else k_step_headers<ArFast><<<(unsigned)(2 * b1), 128, 0, st>>>(p);
+    HB_CUDA_TRY(cudaGetLastError());
     if (integ->arith == HB_ARITH_PARITY) k_step_candidates<ArParity><<<(unsigned)b1, threads, 0, st>>>(p);
     else k_step_candidates<ArFast><<<(unsigned)b1, threads, 0, st>>>(p);
     HB_CUDA_TRY(cudaGetLastError());
     {
-        const long long tb = (n * HB_CAND_CAP + 127) / 128;
-        if (integ->arith == HB_ARITH_PARITY) k_emit_candidates<ArParity><<<(unsigned)tb, 128, 0, st>>>(p);
-        else k_emit_candidates<ArFast><<<(unsigned)tb, 128, 0, st>>>(p);
+        const unsigned tb = (unsigned)sm_count() * 8u;
+        if (integ->arith == HB_ARITH_PARITY) k_emit_candidates<ArParity><<<tb, 128, 0, st>>>(p);
+        else k_emit_candidates<ArFast><<<tb, 128, 0, st>>>(p);
         HB_CUDA_TRY(cudaGetLastError());
     }
     k_order_dedup<<<(unsigned)((n + threads - 1) / threads), threads, 0, st>>>(p);
