@@ -205,10 +205,12 @@ HB_DEV void note_segment(const ScanParams &p, long long traj, int cs, int s0, in
 template <class AR>
 __global__ void __launch_bounds__(128, 4) k_step_headers(const ScanParams p)
 {
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long traj = gid / p.rec_cap;
-    const int s = (int)(gid - traj * p.rec_cap);
-    if (traj >= p.n || s >= p.nacc[traj]) return;
+    // one warp per trajectory, a lane per step: no idle warps however far nacc is below the capacity
+    const long long traj = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (traj >= p.n) return;
+    const int nacc = min(p.nacc[traj], p.rec_cap);
+    for (int s = threadIdx.x & 31; s < nacc; s += 32) {
+    const long long gid = traj * p.rec_cap + s;
     const double *r = p.rec + gid * HB_REC_DOUBLES;
     double v[16];
 #pragma unroll
@@ -232,6 +234,7 @@ __global__ void __launch_bounds__(128, 4) k_step_headers(const ScanParams p)
     hb_st4(h + 0, t, t_new, hseg, pick6(y, c));
     hb_st4(h + 4, f[0], f[1], f[2], f[3]);
     hb_st4(h + 8, f[4], f[5], f[6], 0.0);
+    }
 }
 
 // One warp = 32 consecutive step headers of one trajectory (rec_cap is a multiple of 32).  Quiet tests run one
@@ -240,11 +243,10 @@ template <class AR>
 __global__ void __launch_bounds__(256, 2) k_step_candidates(const ScanParams p)
 {
     const int lane = threadIdx.x & 31;
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long traj = gid / p.rec_cap;
-    const int s = (int)(gid - traj * p.rec_cap);
-    if (traj >= p.n) return;                                  // whole warp (rec_cap % 32 == 0)
-    const int nacc = p.nacc[traj];
+    const long long traj = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (traj >= p.n) return;                                  // whole warp
+    const int nacc = min(p.nacc[traj], p.rec_cap);
+    for (int s = lane; s - lane < nacc; s += 32) {            // warp-uniform trip count
     const double *base = p.hdr + traj * (long long)p.rec_cap * HB_HDR_DOUBLES;
     const double *r = base + (long long)s * HB_HDR_DOUBLES;
     const double off = p.sink.sec.offset, tol_s = p.sink.sec.tol_on_surface;
@@ -326,6 +328,7 @@ __global__ void __launch_bounds__(256, 2) k_step_candidates(const ScanParams p)
             carry2 = (nvalid >= 2) ? l2 : carry1;
             carry1 = l1;
         }
+    }
     }
 }
 
@@ -453,8 +456,7 @@ extern "C" int hb_cr3bp_section2(const hb_cr3bp *sys, const hb_integ *integ, con
     p.hits_per_traj = hits_per_traj;
     p.cand_count = cand_count; p.cand = cand; p.desc_count = desc_count; p.desc_total = desc_total; p.desc = desc;
     const int threads = 256;
-    const long long total = n * (long long)rec_cap;
-    const long long b1 = (total + threads - 1) / threads;
+    const long long b1 = (n * 32 + threads - 1) / threads;       // one warp per trajectory
     if (b1 > 1073741823LL) return HB_ERR_BADARG;
     if (integ->arith == HB_ARITH_PARITY) k_step_headers<ArParity><<<(unsigned)(2 * b1), 128, 0, st>>>(p);
     else k_step_headers<ArFast><<<(unsigned)(2 * b1), 128, 0, st>>>(p);
