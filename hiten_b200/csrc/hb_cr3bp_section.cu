@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) k_dop853_6_section(con
                 crtbp_rhs<AR, NEG>(y, p, k[0]);
                 t = p.t0;
                 tf = p.tf;
-                h = initial_step<AR>(y, k[0], p);
+                h = p.h0 ? p.h0[idx] : initial_step<AR>(y, k[0], p);
                 err_prev = -1.0;
                 nacc = 0; nrej = 0; cursor = 0; attempts = 0;
                 dd = Dedup{0.0, 0.0, 0.0, 0};
@@ -271,9 +271,14 @@ __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) k_dop853_6_section(con
 }
 
 template <class AR>
-int launch_section(const PropParams &p, cudaStream_t st)
+int launch_section(const PropParams &p_in, cudaStream_t st)
 {
+    PropParams p = p_in;
     HB_CUDA_TRY(cudaMemsetAsync(p.ws, 0, sizeof(HbWorkspace), st));
+    if constexpr (AR::parity) {
+        const int rc = first_steps_prepass<AR>(p, st);
+        if (rc != HB_OK) return rc;
+    }
     long long blocks_needed = (p.n + HB_BLOCK - 1) / HB_BLOCK;
     long long grid = (long long)HB_MINBLOCKS * sm_count();
     if (blocks_needed < grid) grid = blocks_needed;
