@@ -224,6 +224,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--arith", default="parity", choices=["parity", "fast"])
     ap.add_argument("--n-per-gpu", type=int, default=N_PER_GPU)
+    ap.add_argument("--steps-capacity", type=int, default=192,
+                    help="accepted steps per trajectory the hb_cr3bp_section2 scratch holds (0: fused hb_cr3bp_section)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary (propagate-only / fast) timings")
     args = ap.parse_args()
@@ -256,7 +258,8 @@ def main():
     m = max(int(abs(TF) / GRID_DT) + 1, 100)                              # manifold.py:396-397 -> 4713
     t_eval = np.linspace(0.0, TF, m)
     sec = synodic.make_section("y", 0.0, ("x", "z"), -1)                  # configs[1]'s SynodicMap call
-    runner = synodic.TubeSectionRunner(n, mu, t_eval, sec, forward=-1, flip=(0, 6), integ=integ, device=dev)
+    runner = synodic.TubeSectionRunner(n, mu, t_eval, sec, forward=-1, flip=(0, 6), integ=integ, device=dev,
+                                       steps_capacity=args.steps_capacity)
     y0_soa = torch.from_numpy(np.ascontiguousarray(ics.T)).to(dev)       # resident input [6, N]
     host_in = torch.from_numpy(ics).pin_memory()                          # e2e input  [N, 6]
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)  # > 126 MB L2
@@ -271,14 +274,22 @@ def main():
             dist.gather(runner.yf, gather_yf, dst=0)
             dist.gather(runner.per, gather_cnt, dst=0)
 
+    # pinned host result buffers (what a host caller that keeps its arrays registered would pass)
+    host_hits = torch.empty(runner.cap * 9, dtype=torch.float64).pin_memory()
+    host_yf = torch.empty((n, 6), dtype=torch.float64).pin_memory()
+    host_na = torch.empty(n, dtype=torch.int32).pin_memory()
+    host_nr = torch.empty(n, dtype=torch.int32).pin_memory()
+
     def step_e2e():
         d = host_in.to(dev, non_blocking=True).t().contiguous()          # H2D + AoS->SoA on device
         runner.launch(d)
-        k = runner.hit_count()                                            # syncs; then D2H of the results
-        hits = runner.hits[: k * 9].cpu()
-        yf = runner.yf.t().contiguous().cpu()
-        na, nr = runner.nacc.cpu(), runner.nrej.cpu()
-        return k, hits, yf, na, nr
+        host_yf.copy_(runner.yf.view(6, n).t(), non_blocking=True)        # SoA->AoS on device, then D2H
+        host_na.copy_(runner.nacc[:n], non_blocking=True)
+        host_nr.copy_(runner.nrej[:n], non_blocking=True)
+        k = runner.hit_count()                                            # syncs; the hit list length is now known
+        host_hits[: k * 9].copy_(runner.hits[: k * 9], non_blocking=True)
+        torch.cuda.synchronize()
+        return k, host_hits, host_yf, host_na, host_nr
 
     def barrier():
         if world > 1:
@@ -300,6 +311,22 @@ def main():
     steps_per_pass = steps_acc + int(runner.nrej.sum().item())
     ok = bool((runner.status == 0).all().item())
     t_kernel_local = t_dev
+
+    # per-kernel split of the pipeline (CUDA events recorded inside hb_cr3bp_section2, same stream), separate pass
+    stage_ms = None
+    if args.steps_capacity > 0:
+        import ctypes
+        lib = runner.lib
+        lib.hb_section2_profile(1)
+        acc = np.zeros(5)
+        buf = (ctypes.c_float * 5)()
+        for i in range(args.steps):
+            flush.fill_(float(i))
+            runner.launch(y0_soa)
+            lib.hb_section2_read_profile(buf)
+            acc += np.array(list(buf))
+        lib.hb_section2_profile(0)
+        stage_ms = (acc / args.steps).tolist()
 
     # e2e: host buffers in, host results out, copies inside the timed region
     for _ in range(2):
@@ -342,23 +369,42 @@ def main():
             extra[f"propagate_only_{name}"] = {"rk_steps_per_s": sp * args.steps / tp,
                                                "tflops": sp * args.steps * FLOP_PER_STEP / tp / 1e12}
         other = "fast" if args.arith == "parity" else "parity"
-        r2 = synodic.TubeSectionRunner(n, mu, t_eval, sec, forward=-1, flip=(0, 6), integ=hb.make_integ(arith=other),
-                                       device=dev)
-        for _ in range(3):
-            r2.launch(y0_soa)
-        t2 = time_steps(lambda: r2.launch(y0_soa), args.steps, flush, barrier, torch)
-        s2 = int((r2.nacc.sum() + r2.nrej.sum()).item())
-        extra[f"section_{other}"] = {"rk_steps_per_s": s2 * args.steps / t2,
-                                     "crossings_per_s": r2.hit_count() * args.steps / t2}
+        for label, ar, cap in ((f"section_{other}", other, args.steps_capacity),
+                               ("section_fused_kernel_parity", "parity", 0), ("section_fused_kernel_fast", "fast", 0)):
+            r2 = synodic.TubeSectionRunner(n, mu, t_eval, sec, forward=-1, flip=(0, 6), integ=hb.make_integ(arith=ar),
+                                           device=dev, steps_capacity=cap)
+            for _ in range(3):
+                r2.launch(y0_soa)
+            t2 = time_steps(lambda: r2.launch(y0_soa), args.steps, flush, barrier, torch)
+            s2 = int((r2.nacc.sum() + r2.nrej.sum()).item())
+            extra[label] = {"rk_steps_per_s": s2 * args.steps / t2, "ms_per_step": 1e3 * t2 / args.steps,
+                            "crossings_per_s": r2.hit_count() * args.steps / t2}
+            del r2
         extra.update(secondary_configs(hb, torch, args.steps, flush, barrier))
 
     if rank == 0:
         value = total_steps_pass * args.steps / t_dev
         e2e_value = total_steps_pass * args.steps / e2e_t
         peak = hb.dfma_peak(200.0)
-        # grid samples are NOT counted: the kernel proves most of them irrelevant (quiet steps) and skips them
-        flop_pass = steps_per_pass * FLOP_PER_STEP + steps_acc * FLOP_PER_SEGMENT
-        achieved = flop_pass * args.steps / t_kernel_local
+        # Roofline of the DOMINANT kernel (k_dop853_6 in record mode + its first-step pre-pass): attempted steps x
+        # 1350 algorithmic flop over that kernel's own duration.  With the fused kernel (--steps-capacity 0) the
+        # whole step is one kernel and the accepted steps' dense caches (1050 flop) are added.
+        if stage_ms is not None:
+            achieved = steps_per_pass * FLOP_PER_STEP / (stage_ms[0] * 1e-3)
+            hbm = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))["hbm_gbs"] \
+                if os.path.exists(os.path.join(REPO, "MEASURED_PEAKS.json")) else 6500.0
+            rec_bytes = steps_acc * 512.0
+            extra["pipeline"] = {
+                "stage_ms": dict(zip(("propagate_record", "step_headers", "sample_scan", "emit_candidates",
+                                      "order_dedup"), stage_ms)),
+                "share_of_step_dominant": stage_ms[0] / sum(stage_ms),
+                "propagate_record_hbm_write_gbs": rec_bytes / (stage_ms[0] * 1e-3) / 1e9,
+                "step_headers_hbm_gbs": steps_acc * (512.0 + 96.0) / (stage_ms[1] * 1e-3) / 1e9,
+                "step_headers_frac_of_hbm_peak": steps_acc * (512.0 + 96.0) / (stage_ms[1] * 1e-3) / 1e9 / hbm,
+                "hbm_peak_gbs": hbm,
+            }
+        else:
+            achieved = (steps_per_pass * FLOP_PER_STEP + steps_acc * FLOP_PER_SEGMENT) * args.steps / t_kernel_local
         for v in extra.values():
             if "tflops" in v:
                 v["frac_of_fp64_peak"] = v["tflops"] * 1e12 / peak
@@ -374,20 +420,30 @@ def main():
                             "backward tf=0.75*2pi, dense samples on the dt=1e-3 grid (4713) streamed through the "
                             "synodic detector y=0 / (x,z) / direction=-1 (segment_refine=50), hits + end states out",
                 "trajectories_per_gpu": n, "grid_samples": m, "arith": args.arith,
+                "path": "hb_cr3bp_section2 (propagate+record -> step headers -> sample scan -> emit -> order+dedup)"
+                        if args.steps_capacity > 0 else "hb_cr3bp_section (fused kernel)",
+                "steps_capacity": args.steps_capacity,
                 "l2": "flushed between timed iterations (256 MB fill); inputs 6 MB/GPU, kernel is FP64-pipe bound",
                 "rk_steps_per_pass": total_steps_pass, "accepted_steps_per_pass": total_acc,
                 "crossings_per_pass": total_hits, "all_status_ok": ok,
             },
             "roofline": {"bound": "fp64", "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "TFLOP/s",
-                         "frac": achieved / peak, "traffic": None,
-                         "note": "FP64 FMA pipe roofline (neither HBM nor tensor bound applies: 96 B + hits per "
-                                 "trajectory of HBM traffic). achieved = (attempted steps x 1350 + accepted steps x 1050 "
-                                 "+ grid samples x 84 algorithmic flop, SURVEY 8d) / kernel time (CUDA events); "
-                                 "peak = hb_dfma_peak measured in this process (of measured)"},
+                         "frac": achieved / peak,
+                         "traffic": (5.763e9 if (n == N_PER_GPU and args.steps_capacity > 0) else None),
+                         "kernel": "k_dop853_6<MODE_RECORD> (+ k_first_steps)" if stage_ms is not None
+                                   else "k_dop853_6_section",
+                         "note": "FP64 FMA pipe roofline of the dominant kernel (its HBM side: 512 B written per "
+                                 "accepted step = 5.8 GB per launch, ~1.4 TB/s, far from the HBM roof; traffic = "
+                                 "dram read+write of one ncu --set full capture, profiles/r01_recA_v3_summary.md). "
+                                 "achieved = attempted steps x 1350 algorithmic flop (SURVEY 8d) / the kernel's own "
+                                 "duration (CUDA events recorded between the pipeline's kernels on the launching "
+                                 "stream); peak = hb_dfma_peak measured in this process"},
             "e2e": {"value": e2e_value, "unit": "RK steps/s", "h2d_bytes_per_step": int(n * 48),
                     "d2h_bytes_per_step": int(n * (48 + 8) + 72 * k_e2e),
                     "crossings_per_s": total_hits * args.steps / e2e_t},
-            "gpu_launches": args.steps, "clocks": clocks, "wall_s_timed_region": wall, "extra": extra,
+            "gpu_launches": args.steps * ((6 if args.arith == "parity" else 5) if args.steps_capacity > 0
+                                          else (2 if args.arith == "parity" else 1)),
+            "clocks": clocks, "wall_s_timed_region": wall, "extra": extra,
         }
         if not args.no_cpu_baseline and world == 1:
             import oracle_lib as O

@@ -89,6 +89,9 @@ SIGNATURES = {
     "hb_synodic_detect": (C.c_int, [C.POINTER(HbSection), C.c_int64, vp, vp, vp, C.c_int32, C.c_int32, vp, C.c_int64,
                                     vp, vp, vp]),
     "hb_read_hit_count": (C.c_int, [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), vp]),
+    "hb_read_record_overflow": (C.c_int, [vp, C.POINTER(C.c_int64), vp]),
+    "hb_section2_profile": (C.c_int, [C.c_int32]),
+    "hb_section2_read_profile": (C.c_int, [C.POINTER(C.c_float)]),
     "hb_selftest_arith": (C.c_int, [vp, vp, C.c_int64, vp, vp, vp, vp, vp, vp]),
 }
 

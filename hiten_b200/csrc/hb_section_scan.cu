@@ -376,8 +376,11 @@ __global__ void __launch_bounds__(256) k_order_dedup(const ScanParams p)
     if (traj >= p.n) return;
     int k = p.cand_count[traj];
     if (p.nacc[traj] > p.rec_cap || k > HB_CAND_CAP || p.desc_count[traj] > HB_CAND_CAP) {
-        if (p.status[traj] == HB_TRAJ_OK) p.status[traj] = HB_TRAJ_RECORD_OVERFLOW;
-        if (k > HB_CAND_CAP) k = HB_CAND_CAP;
+        // incomplete: report no hits for this trajectory; the caller reruns it with hb_cr3bp_section
+        p.status[traj] = HB_TRAJ_RECORD_OVERFLOW;
+        atomicAdd(&p.sink.ws->rec_overflow, 1ULL);
+        if (p.hits_per_traj) p.hits_per_traj[traj] = 0;
+        return;
     }
     const double *c = p.cand + traj * HB_CAND_CAP * HB_CAND_DOUBLES;
     unsigned long long used = 0ULL;
@@ -399,6 +402,31 @@ __global__ void __launch_bounds__(256) k_order_dedup(const ScanParams p)
 }
 
 }  // namespace
+
+// Optional per-kernel timing of the pipeline (bench.py's roofline): CUDA events recorded on the launching stream
+// between the kernels.  Off by default; not thread safe (one profiled caller at a time).
+namespace {
+constexpr int HB_S2_STAGES = 5;      // propagate+record, headers, candidates, emit, order+dedup
+bool g_profile = false;
+cudaEvent_t g_ev[HB_S2_STAGES + 1] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+inline void mark(int i, cudaStream_t st) { if (g_profile && g_ev[i]) cudaEventRecord(g_ev[i], st); }
+}  // namespace
+
+extern "C" int hb_section2_profile(int32_t enable)
+{
+    if (enable && !g_ev[0])
+        for (int i = 0; i <= HB_S2_STAGES; ++i) HB_CUDA_TRY(cudaEventCreate(&g_ev[i]));
+    g_profile = enable != 0;
+    return HB_OK;
+}
+
+extern "C" int hb_section2_read_profile(float *ms_out)
+{
+    if (!ms_out || !g_ev[0]) return HB_ERR_BADARG;
+    HB_CUDA_TRY(cudaEventSynchronize(g_ev[HB_S2_STAGES]));
+    for (int i = 0; i < HB_S2_STAGES; ++i) HB_CUDA_TRY(cudaEventElapsedTime(&ms_out[i], g_ev[i], g_ev[i + 1]));
+    return HB_OK;
+}
 
 extern "C" int64_t hb_section2_scratch_bytes(int64_t n, int32_t steps_capacity)
 {
@@ -441,9 +469,11 @@ extern "C" int hb_cr3bp_section2(const hb_cr3bp *sys, const hb_integ *integ, con
     HB_CUDA_TRY(cudaMemcpyAsync(&ends[1], t_eval + (m - 1), sizeof(double), cudaMemcpyDeviceToHost, st));
     HB_CUDA_TRY(cudaStreamSynchronize(st));
     HB_CUDA_TRY(cudaMemsetAsync(cand_count, 0, sizeof(int) * (2 * (size_t)n + 1), st));
+    mark(0, st);
     int rc = hb_cr3bp_record_launch(sys, integ, sec->idx, n, y0_soa, ends[0], ends[1], rec, rec_cap, yf_soa, n_acc, n_rej,
                                     status, workspace, st);
     if (rc != HB_OK) return rc;
+    mark(1, st);
     ScanParams p{};
     rc = fill_params(sys, integ, p.prop);
     if (rc != HB_OK) return rc;
@@ -461,16 +491,20 @@ extern "C" int hb_cr3bp_section2(const hb_cr3bp *sys, const hb_integ *integ, con
     if (integ->arith == HB_ARITH_PARITY) k_step_headers<ArParity><<<(unsigned)(2 * b1), 128, 0, st>>>(p);
     else k_step_headers<ArFast><<<(unsigned)(2 * b1), 128, 0, st>>>(p);
     HB_CUDA_TRY(cudaGetLastError());
+    mark(2, st);
     if (integ->arith == HB_ARITH_PARITY) k_step_candidates<ArParity><<<(unsigned)b1, threads, 0, st>>>(p);
     else k_step_candidates<ArFast><<<(unsigned)b1, threads, 0, st>>>(p);
     HB_CUDA_TRY(cudaGetLastError());
+    mark(3, st);
     {
         const unsigned tb = (unsigned)sm_count() * 8u;
         if (integ->arith == HB_ARITH_PARITY) k_emit_candidates<ArParity><<<tb, 128, 0, st>>>(p);
         else k_emit_candidates<ArFast><<<tb, 128, 0, st>>>(p);
         HB_CUDA_TRY(cudaGetLastError());
     }
+    mark(4, st);
     k_order_dedup<<<(unsigned)((n + threads - 1) / threads), threads, 0, st>>>(p);
     HB_CUDA_TRY(cudaGetLastError());
+    mark(5, st);
     return HB_OK;
 }

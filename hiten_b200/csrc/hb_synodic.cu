@@ -121,3 +121,14 @@ extern "C" int hb_read_hit_count(const void *workspace, int64_t *n_hits, int64_t
     if (n_overflow) *n_overflow = (int64_t)h.overflow;
     return HB_OK;
 }
+
+extern "C" int hb_read_record_overflow(const void *workspace, int64_t *n_traj, void *stream)
+{
+    if (!workspace || !n_traj) return HB_ERR_BADARG;
+    HbWorkspace h;
+    cudaStream_t st = (cudaStream_t)stream;
+    HB_CUDA_TRY(cudaMemcpyAsync(&h, workspace, sizeof(h), cudaMemcpyDeviceToHost, st));
+    HB_CUDA_TRY(cudaStreamSynchronize(st));
+    *n_traj = (int64_t)h.rec_overflow;
+    return HB_OK;
+}

@@ -135,12 +135,13 @@ def tube_section(y0, mu, t_eval, section, *, forward=1, flip=None, integ=None, h
 
 class TubeSectionRunner:
     """Pre-allocated, repeatable form of tube_section for resident batches (what bench.py times): all device
-    buffers are created once; run() launches hb_cr3bp_section and returns the hit count."""
+    buffers are created once; launch() enqueues the kernels, hit_count() / sorted_hits() read the result."""
 
     def __init__(self, n, mu, t_eval, section, *, forward=1, flip=None, integ=None, hit_capacity=None, device=None,
                  steps_capacity=0):
-        """steps_capacity > 0 selects the two-kernel path (hb_cr3bp_section2) with a scratch for that many accepted
-        steps per trajectory; 0 the fused kernel (hb_cr3bp_section)."""
+        """steps_capacity > 0 selects the kernel pipeline hb_cr3bp_section2 with a scratch for that many accepted
+        steps per trajectory (608 B per step); 0 the fused kernel hb_cr3bp_section.  Trajectories that do not fit
+        the scratch are rerun with the fused kernel by hit_count() / sorted_hits(), so the result is the same."""
         from . import propagate as P
         _require_cuda()
         self.lib = L.load()
@@ -153,16 +154,20 @@ class TubeSectionRunner:
         self.per = torch.zeros(max(self.n, 1), dtype=torch.int32, device=self.device)
         self.ws = workspace(self.device)
         self.integ = P.make_integ() if integ is None else integ
+        self.mu, self.forward, self.flip = mu, forward, flip
         self.sys = P.make_sys(mu, forward, flip)
         self.cap = int(hit_capacity) if hit_capacity is not None else max(1024, 8 * self.n)
         self.hits = torch.empty(self.cap * 9, dtype=torch.float64, device=self.device)
         self.steps_capacity = int(steps_capacity)
         self.scratch = None
+        self._y0 = None
+        self._extra = None          # (indices, SectionHits) of the trajectories rerun with the fused kernel
         if self.steps_capacity > 0:
             nbytes = int(self.lib.hb_section2_scratch_bytes(self.n, self.steps_capacity))
             self.scratch = torch.empty(nbytes // 8, dtype=torch.float64, device=self.device)
 
     def launch(self, y0_soa, stream=None):
+        self._y0, self._extra = y0_soa, None
         if self.scratch is not None:
             rc = self.lib.hb_cr3bp_section2(self.sys, self.integ, self.section, self.n, y0_soa.data_ptr(),
                                             self.te.data_ptr(), self.te.numel(), self.hits.data_ptr(), self.cap,
@@ -178,19 +183,61 @@ class TubeSectionRunner:
                                        _stream_ptr(stream))
         L.check(rc, "hb_cr3bp_section")
 
+    def _rerun_overflowed(self, stream=None):
+        """Trajectories the step scratch could not hold (status HB_TRAJ_RECORD_OVERFLOW): fused kernel, on the GPU."""
+        if self.scratch is None or self._extra is not None:
+            return
+        nt = L.C.c_int64(0)
+        L.check(self.lib.hb_read_record_overflow(self.ws.data_ptr(), L.C.byref(nt), _stream_ptr(stream)),
+                "hb_read_record_overflow")
+        if nt.value == 0:
+            self._extra = (None, None)
+            return
+        idx = torch.nonzero(self.status[: self.n] == L.HB_TRAJ_RECORD_OVERFLOW).flatten()
+        sub = TubeSectionRunner(idx.numel(), self.mu, self.te, self.section, forward=self.forward, flip=self.flip,
+                                integ=self.integ, device=self.device)
+        y0 = self._y0.view(6, self.n)[:, idx].contiguous()
+        sub.launch(y0, stream)
+        h = sub.sorted_hits(stream)
+        self.yf.view(6, self.n)[:, idx] = sub.yf.view(6, idx.numel())
+        self.nacc[idx], self.nrej[idx], self.status[idx] = sub.nacc[: idx.numel()], sub.nrej[: idx.numel()], \
+            sub.status[: idx.numel()]
+        self.per[idx] = sub.per[: idx.numel()]
+        self._extra = (idx.cpu().numpy(), h)
+
     def hit_count(self, stream=None):
         nh, no = L.C.c_int64(0), L.C.c_int64(0)
         L.check(self.lib.hb_read_hit_count(self.ws.data_ptr(), L.C.byref(nh), L.C.byref(no), _stream_ptr(stream)),
                 "hb_read_hit_count")
         if no.value:
             raise L.HitenB200Error(f"hit buffer overflow: {no.value} hits dropped (capacity {self.cap})")
-        return int(nh.value)
+        self._main_hits = int(nh.value)
+        self._rerun_overflowed(stream)
+        extra = self._extra[1] if self._extra is not None else None
+        return self._main_hits + (len(extra.times) if extra is not None else 0)
 
     def sorted_hits(self, stream=None):
         """SectionHits in the reference's order (by trajectory, then along the trajectory)."""
-        k = self.hit_count(stream)
+        self.hit_count(stream)
+        k = self._main_hits
         rec = self.hits[: k * 9].cpu().numpy().view(HIT_DTYPE) if k else np.empty(0, dtype=HIT_DTYPE)
-        rec = rec[np.lexsort((rec["seq"], rec["traj"]))]
+        traj, seq, t, state = rec["traj"], rec["seq"], rec["t"], rec["state"].reshape(-1, 6)
+        if self._extra is not None and self._extra[1] is not None and len(self._extra[1].times):
+            idx, h = self._extra
+            traj = np.concatenate((traj, idx[h.trajectory_indices]))
+            seq = np.concatenate((seq, _seq_within(h.trajectory_indices)))
+            t = np.concatenate((t, h.times))
+            state = np.concatenate((state, h.states))
+        order = np.lexsort((seq, traj))
+        traj, t, state = traj[order], t[order], state[order]
         sec = self.section
-        pts = np.column_stack((rec["state"][:, sec.proj_i], rec["state"][:, sec.proj_j])) if k else np.empty((0, 2))
-        return SectionHits(rec["traj"].copy(), rec["t"].copy(), rec["state"].copy(), pts, self.per[: self.n].cpu().numpy())
+        pts = np.column_stack((state[:, sec.proj_i], state[:, sec.proj_j])) if len(t) else np.empty((0, 2))
+        return SectionHits(traj.copy(), t.copy(), state.copy(), pts, self.per[: self.n].cpu().numpy())
+
+
+def _seq_within(traj):
+    """0, 1, 2 ... within each run of equal (sorted) trajectory indices."""
+    if len(traj) == 0:
+        return np.empty(0, dtype=np.int64)
+    start = np.r_[0, np.flatnonzero(np.diff(traj)) + 1]
+    return np.arange(len(traj)) - np.repeat(start, np.diff(np.r_[start, len(traj)]))

@@ -147,17 +147,27 @@ int hb_cr3bp_section(const hb_cr3bp *sys, const hb_integ *integ, const hb_sectio
                      int32_t *hits_per_traj, double *yf_soa, int32_t *n_acc, int32_t *n_rej, int32_t *status,
                      void *workspace, void *stream);
 
-/* The same result as hb_cr3bp_section computed as TWO kernels with a compact intermediate (hb_section_scan.cu):
- * the propagation kernel records the dense-output coefficients of every accepted step (416 B per step) in
- * `scratch`, then a warp-per-trajectory kernel applies the detector to the records.  Faster than the fused kernel
- * (which is instruction-fetch bound) whenever the scratch fits: hb_section2_scratch_bytes(n, steps_capacity) bytes
- * for at most steps_capacity accepted steps per trajectory.  Trajectories that need more get
- * status = HB_TRAJ_RECORD_OVERFLOW (their hits are incomplete): rerun those with hb_cr3bp_section.          */
+/* The same hits as hb_cr3bp_section (bit for bit) computed as a PIPELINE of small kernels with a compact
+ * intermediate (hb_section_scan.cu): the propagation kernel stores what the dense output of every accepted step
+ * depends on (512 B per step) in `scratch`; data-parallel kernels then build the event component of each step's
+ * interpolant, scan the grid samples, refine the segments that can hold a hit and order + de-duplicate the hits.
+ * About 2x faster than the fused kernel (which is instruction-fetch bound) whenever the scratch fits:
+ * hb_section2_scratch_bytes(n, steps_capacity) bytes for at most steps_capacity accepted steps per trajectory
+ * (608 B per step + 4.1 KB per trajectory).  Trajectories that need more steps, or have more than 32 candidate
+ * hits, get status = HB_TRAJ_RECORD_OVERFLOW and NO hits; their number is read with hb_read_record_overflow --
+ * rerun those with hb_cr3bp_section.                                                                 */
 int64_t hb_section2_scratch_bytes(int64_t n, int32_t steps_capacity);
 int hb_cr3bp_section2(const hb_cr3bp *sys, const hb_integ *integ, const hb_section *sec, int64_t n,
                       const double *y0_soa, const double *t_eval, int32_t m, hb_hit *hits, int64_t hit_capacity,
                       int32_t *hits_per_traj, double *yf_soa, int32_t *n_acc, int32_t *n_rej, int32_t *status,
                       void *scratch, int64_t scratch_bytes, void *workspace, void *stream);
+
+/* Per-kernel timing of hb_cr3bp_section2 (measurement aid, used by bench.py): after hb_section2_profile(1) every
+ * call records CUDA events on its stream between the five stages (propagate + record, step headers, sample scan,
+ * candidate emission, order + dedup); hb_section2_read_profile waits for the last call and returns the five
+ * durations in ms.  Not thread safe.                                                                 */
+int hb_section2_profile(int32_t enable);
+int hb_section2_read_profile(float *ms_out /* [5] */);
 
 /* Propagation with a terminal plane event (event always terminal, as in the reference):
  * replaces _integrate_dop853_until_event + _dop853_refine_in_step (rk.py:2680-2803, 2006-2102).
@@ -258,6 +268,10 @@ int hb_synodic_detect(const hb_section *sec, int64_t n_traj, const double *state
 
 /* Hit / overflow counters of the last call that used `workspace` (synchronises `stream`). */
 int hb_read_hit_count(const void *workspace, int64_t *n_hits, int64_t *n_overflow, void *stream);
+
+/* Number of trajectories of the last hb_cr3bp_section2 call that got HB_TRAJ_RECORD_OVERFLOW (no hits were
+ * reported for them; rerun those with hb_cr3bp_section).  Synchronises `stream`.                   */
+int hb_read_record_overflow(const void *workspace, int64_t *n_traj, void *stream);
 
 /* Arithmetic self-test: for every pair (a[i], b[i]) evaluates the shared-reciprocal division and the
  * restated sqrt fast path used by the parity variant next to the compiler's div.rn / sqrt.rn, and

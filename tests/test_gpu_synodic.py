@@ -133,3 +133,9 @@ def test_two_kernel_overflow_is_flagged():
     st = r.status.cpu().numpy()
     na = r.nacc.cpu().numpy()
     assert ((st == 4) == (na > 96)).all() and (st == 4).any() and (st == 0).any()      # capacity rounds up to 96
+    # ... and transparently rerun with the fused kernel: the final hits are the reference's, bit for bit
+    h = r.sorted_hits()
+    assert (r.status == 0).all().item()
+    assert np.array_equal(h.times, g["hit_time"]) and np.array_equal(h.states, g["hit_state"])
+    assert np.array_equal(h.trajectory_indices, g["hit_traj"])
+    assert int(h.hits_per_traj.sum()) == len(g["hit_time"]) == r.hit_count()
