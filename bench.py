@@ -318,8 +318,8 @@ def main():
         import ctypes
         lib = runner.lib
         lib.hb_section2_profile(1)
-        acc = np.zeros(5)
-        buf = (ctypes.c_float * 5)()
+        acc = np.zeros(4)
+        buf = (ctypes.c_float * 4)()
         for i in range(args.steps):
             flush.fill_(float(i))
             runner.launch(y0_soa)
@@ -395,12 +395,11 @@ def main():
                 if os.path.exists(os.path.join(REPO, "MEASURED_PEAKS.json")) else 6500.0
             rec_bytes = steps_acc * 512.0
             extra["pipeline"] = {
-                "stage_ms": dict(zip(("propagate_record", "step_headers", "sample_scan", "emit_candidates",
-                                      "order_dedup"), stage_ms)),
+                "stage_ms": dict(zip(("propagate_record", "step_scan", "emit_candidates", "order_dedup"), stage_ms)),
                 "share_of_step_dominant": stage_ms[0] / sum(stage_ms),
                 "propagate_record_hbm_write_gbs": rec_bytes / (stage_ms[0] * 1e-3) / 1e9,
-                "step_headers_hbm_gbs": steps_acc * (512.0 + 96.0) / (stage_ms[1] * 1e-3) / 1e9,
-                "step_headers_frac_of_hbm_peak": steps_acc * (512.0 + 96.0) / (stage_ms[1] * 1e-3) / 1e9 / hbm,
+                "step_scan_hbm_read_gbs": rec_bytes / (stage_ms[1] * 1e-3) / 1e9,
+                "step_scan_frac_of_hbm_peak": rec_bytes / (stage_ms[1] * 1e-3) / 1e9 / hbm,
                 "hbm_peak_gbs": hbm,
             }
         else:
@@ -420,7 +419,7 @@ def main():
                             "backward tf=0.75*2pi, dense samples on the dt=1e-3 grid (4713) streamed through the "
                             "synodic detector y=0 / (x,z) / direction=-1 (segment_refine=50), hits + end states out",
                 "trajectories_per_gpu": n, "grid_samples": m, "arith": args.arith,
-                "path": "hb_cr3bp_section2 (propagate+record -> step headers -> sample scan -> emit -> order+dedup)"
+                "path": "hb_cr3bp_section2 (propagate+record -> step scan -> emit -> order+dedup)"
                         if args.steps_capacity > 0 else "hb_cr3bp_section (fused kernel)",
                 "steps_capacity": args.steps_capacity,
                 "l2": "flushed between timed iterations (256 MB fill); inputs 6 MB/GPU, kernel is FP64-pipe bound",
@@ -441,7 +440,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "RK steps/s", "h2d_bytes_per_step": int(n * 48),
                     "d2h_bytes_per_step": int(n * (48 + 8) + 72 * k_e2e),
                     "crossings_per_s": total_hits * args.steps / e2e_t},
-            "gpu_launches": args.steps * ((6 if args.arith == "parity" else 5) if args.steps_capacity > 0
+            "gpu_launches": args.steps * ((5 if args.arith == "parity" else 4) if args.steps_capacity > 0
                                           else (2 if args.arith == "parity" else 1)),
             "clocks": clocks, "wall_s_timed_region": wall, "extra": extra,
         }

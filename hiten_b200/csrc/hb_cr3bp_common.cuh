@@ -57,8 +57,6 @@ struct PropParams {
 #define HB_REC_YNEW 8
 #define HB_REC_K5 14      // k[5..11] (7 x 6)
 #define HB_REC_K12 56     // k[12] = f(y_new); [62], [63] unused
-// event-component header derived from a record by k_step_headers (hb_section_scan.cu)
-#define HB_HDR_DOUBLES 12 // t_old, t_new, hseg, y_c, F_0..6,c, pad
 
 HB_DEV void hb_st4(double *p, double a, double b, double c, double d)
 {

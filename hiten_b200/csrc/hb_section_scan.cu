@@ -4,12 +4,10 @@
 //      the dense output of every accepted step depends on (512 B: t_old, t_new, y_old, y_new, k6..k13) in a
 //      caller-provided scratch [n][cap][64] -- ~45 KB per trajectory instead of the 226 KB of the 4713-sample tube.
 //      It does NOT build the interpolant: that would double the loop body of a kernel that is instruction-fetch bound;
-//   B0 k_step_headers: one thread per step record.  Runs the three extra DOP853 stages, builds the interpolant
-//      and keeps its EVENT COMPONENT (96 B header: t_old, t_new, hseg, y_c, F_0..6,c);
-//   B1 k_step_candidates: one thread per step header (a warp = 32 consecutive steps of one trajectory).  Finds the
-//      grid samples the step owns and proves most steps quiet (interpolant bound, see hb_cr3bp_section.cu); the
-//      others are scanned by the whole warp, 32 grid samples per instruction, and the segments that can hold a hit
-//      are NOTED (6 numbers);
+//   B1 k_step_scan: one warp per trajectory, a lane per step.  Runs the three extra DOP853 stages and builds the
+//      EVENT COMPONENT of the step's interpolant in registers, finds the grid samples the step owns and proves
+//      most steps quiet (interpolant bound, see hb_cr3bp_section.cu); the others are scanned by the whole warp,
+//      32 grid samples per instruction, and the segments that can hold a hit are NOTED (8 numbers);
 //   B2 k_emit_candidates: one thread per noted segment rebuilds the two end states from the step records, runs
 //      the reference's sub-interval logic and appends CANDIDATE hits {sample index, order, t, state};
 //   B3 k_order_dedup: one thread per trajectory sorts its few candidates into the reference's order and applies
@@ -41,7 +39,6 @@ struct ScanParams {
     PropParams prop;        // mu, 1-mu, sign mask (vector field of the extra stages)
     long long n;
     const double *rec;      // [n][rec_cap][HB_REC_DOUBLES] stage records
-    double *hdr;            // [n][rec_cap][HB_HDR_DOUBLES] event-component headers
     int rec_cap;
     const int *nacc;
     int *status;
@@ -52,7 +49,7 @@ struct ScanParams {
     int *hits_per_traj;
     int *cand_count;        // [n]
     double *cand;           // [n][HB_CAND_CAP][HB_CAND_DOUBLES]
-    int *desc_count;        // [n]   segments that can hold a hit, found by k_step_candidates
+    int *desc_count;        // [n]   segments that can hold a hit, found by k_step_scan
     int *desc_total;        // [1]   length of the (global, unordered) list below
     double *desc;           // [n * HB_CAND_CAP][HB_DESC_DOUBLES]
 };
@@ -125,13 +122,6 @@ HB_DEV int first_at_or_after(const ScanParams &p, double tv, int lo)
     return c;
 }
 
-// record of the step that owns grid sample c, searching backwards from step s
-HB_DEV const double *owner_record(const double *base, int s, double tq)
-{
-    while (s > 0 && tq < base[(long long)s * HB_HDR_DOUBLES]) --s;
-    return base + (long long)s * HB_HDR_DOUBLES;
-}
-
 // _detect_with_segment_refine on ONE segment (linear branch), emitting raw candidates in order
 template <class EMIT>
 HB_DEV void segment_candidates(const hb_section &sec, bool has_prev, double g_prev, double gk, double gk1, double t0,
@@ -189,7 +179,7 @@ HB_DEV void segment_candidates(const hb_section &sec, bool has_prev, double g_pr
     }
 }
 
-// k_step_candidates only NOTES the segments that can hold a hit (6 numbers each); k_emit_candidates below turns them
+// k_step_scan only NOTES the segments that can hold a hit (8 numbers each); k_emit_candidates below turns them
 // into candidate hits.  Keeping the state reconstruction out of the scan kernel keeps it small (no spills, no call).
 HB_DEV void note_segment(const ScanParams &p, long long traj, int cs, int s0, int s1, double gk, double gk1, double gm2)
 {
@@ -201,134 +191,144 @@ HB_DEV void note_segment(const ScanParams &p, long long traj, int cs, int s0, in
     hb_st4(d + 4, gk, gk1, gm2, 0.0);
 }
 
-// One thread per step record: the interpolant of the step, event component only.
+// One warp per trajectory, a lane per accepted step (chunks of 32 steps).  Each lane
+//   1. rebuilds the EVENT COMPONENT of its step's dense interpolant from the stage record (three extra stages +
+//      one column of the D rows: dense_component) -- the only HBM traffic of this kernel, 512 B per step;
+//   2. finds the grid samples its step owns, t_old <= t_q < t_new (searchsorted 'right' - 1, rk.py:2505; the first
+//      step also owns t_q = t0 and the last one everything that is left), and evaluates the event function at the
+//      first / last / second-to-last of them; the segment that straddles two steps is tested with the neighbour's
+//      values, which travel by shuffle (and, across chunks, in warp-uniform carries);
+//   3. proves its step quiet where it can (interpolant bound, see hb_cr3bp_section.cu); the remaining steps are
+//      scanned by the whole warp, 32 grid samples per instruction.
+// Segments that can hold a hit are only NOTED here (8 numbers); k_emit_candidates refines them.
 template <class AR>
-__global__ void __launch_bounds__(128, 4) k_step_headers(const ScanParams p)
+__global__ void __launch_bounds__(128, 4) k_step_scan(const ScanParams p)
 {
-    // one warp per trajectory, a lane per step: no idle warps however far nacc is below the capacity
-    const long long traj = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (traj >= p.n) return;
-    const int nacc = min(p.nacc[traj], p.rec_cap);
-    for (int s = threadIdx.x & 31; s < nacc; s += 32) {
-    const long long gid = traj * p.rec_cap + s;
-    const double *r = p.rec + gid * HB_REC_DOUBLES;
-    double v[16];
-#pragma unroll
-    for (int i = 0; i < 16; i += 4) hb_ld4(r + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
-    const double t = v[0], t_new = v[1];
-    const double y[6] = {v[2], v[3], v[4], v[5], v[6], v[7]}, yn[6] = {v[8], v[9], v[10], v[11], v[12], v[13]};
-    const double hseg = AR::sub(t_new, t);
-    const int c = p.sink.sec.idx;
-    double f[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-    if (hseg != 0.0) {
-        const Cr3bpRhs<AR, 2> rhs{p.prop};
-        auto row = [&](int R, double (&kr)[6]) {
-            const double2 *q = (const double2 *)(r + HB_REC_K5 + 6 * (R - 5));
-            const double2 a = __ldg(q), b = __ldg(q + 1), cc = __ldg(q + 2);
-            kr[0] = a.x; kr[1] = a.y; kr[2] = b.x; kr[3] = b.y; kr[4] = cc.x; kr[5] = cc.y;
-        };
-        auto pick = [&](const double (&w)[6]) { return pick6(w, c); };
-        dense_component<AR>(y, yn, hseg, row, pick, rhs, f);
-    }
-    double *h = p.hdr + gid * HB_HDR_DOUBLES;
-    hb_st4(h + 0, t, t_new, hseg, pick6(y, c));
-    hb_st4(h + 4, f[0], f[1], f[2], f[3]);
-    hb_st4(h + 8, f[4], f[5], f[6], 0.0);
-    }
-}
-
-// One warp = 32 consecutive step headers of one trajectory (rec_cap is a multiple of 32).  Quiet tests run one
-// step per lane; the few non-quiet steps are then scanned by the whole warp, 32 grid samples per instruction.
-template <class AR>
-__global__ void __launch_bounds__(256, 2) k_step_candidates(const ScanParams p)
-{
+    constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const long long traj = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (traj >= p.n) return;                                  // whole warp
     const int nacc = min(p.nacc[traj], p.rec_cap);
-    for (int s = lane; s - lane < nacc; s += 32) {            // warp-uniform trip count
-    const double *base = p.hdr + traj * (long long)p.rec_cap * HB_HDR_DOUBLES;
-    const double *r = base + (long long)s * HB_HDR_DOUBLES;
     const double off = p.sink.sec.offset, tol_s = p.sink.sec.tol_on_surface;
-    const bool have_rec = s < nacc;
-    double hdr[11];
+    const int c = p.sink.sec.idx;
+    int carry_c = 0;                       // first grid sample not owned yet
+    int carry_step = 0;                    // step that owns sample carry_c - 1
+    double carry1 = 0.0, carry2 = 0.0;     // event function at samples carry_c - 1, carry_c - 2
+    for (int base = 0; base < nacc; base += 32) {
+        const int s = base + lane;
+        const bool have_rec = s < nacc;
+        double hdr[11];
 #pragma unroll
-    for (int i = 0; i < 11; ++i) hdr[i] = have_rec ? r[i] : 0.0;
-    const double t_old = hdr[0], t_new = hdr[1], hseg = hdr[2];
-    int c0 = 0, cend = 0;
-    if (have_rec) {
-        // grid samples owned by this segment: t_old <= t_q < t_new (searchsorted 'right' - 1, rk.py:2505); the
-        // first step also owns t_q = t0 and the last one everything that is left
-        c0 = (s == 0) ? 0 : first_at_or_after(p, t_old, 0);
-        cend = (s == nacc - 1) ? p.m : first_at_or_after(p, t_new, c0);
-    }
-    const bool owns = have_rec && c0 < cend;
-    double g_first = 0.0, g_prev = 0.0;
-    bool scan = false;
-    if (owns) {
-        g_first = g_comp<AR>(hdr, xpar<AR>(p.t_eval[c0], t_old, hseg), off);
-        if (c0 > 0) {
-            // last sample of the previous step(s)
-            const double *rp = owner_record(base, s - 1, p.t_eval[c0 - 1]);
-            double h2[11];
+        for (int i = 0; i < 11; ++i) hdr[i] = 0.0;
+        int cend = p.m;
+        if (have_rec) {
+            const double *r = p.rec + (traj * p.rec_cap + s) * HB_REC_DOUBLES;
+            double v[16];
 #pragma unroll
-            for (int i = 0; i < 11; ++i) h2[i] = rp[i];
-            g_prev = g_comp<AR>(h2, xpar<AR>(p.t_eval[c0 - 1], h2[0], h2[2]), off);
-            const bool same = (g_prev > 0.0 && g_first > 0.0) || (g_prev < 0.0 && g_first < 0.0);
-            if (!same || fabs(g_prev) < tol_s) {
-                double gm2 = 0.0;
-                if (c0 > 1) {
-                    const double *rq = owner_record(base, s - 1, p.t_eval[c0 - 2]);
+            for (int i = 0; i < 16; i += 4) hb_ld4(r + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+            const double y[6] = {v[2], v[3], v[4], v[5], v[6], v[7]}, yn[6] = {v[8], v[9], v[10], v[11], v[12], v[13]};
+            const double hseg = AR::sub(v[1], v[0]);
+            hdr[0] = v[0]; hdr[1] = v[1]; hdr[2] = hseg; hdr[3] = pick6(y, c);
+            if (hseg != 0.0) {
+                const Cr3bpRhs<AR, 2> rhs{p.prop};
+                auto row = [&](int R, double (&kr)[6]) {
+                    const double2 *q = (const double2 *)(r + HB_REC_K5 + 6 * (R - 5));
+                    const double2 a = __ldg(q), b = __ldg(q + 1), cc = __ldg(q + 2);
+                    kr[0] = a.x; kr[1] = a.y; kr[2] = b.x; kr[3] = b.y; kr[4] = cc.x; kr[5] = cc.y;
+                };
+                auto pick = [&](const double (&w)[6]) { return pick6(w, c); };
+                double f[7];
+                dense_component<AR>(y, yn, hseg, row, pick, rhs, f);
 #pragma unroll
-                    for (int i = 0; i < 11; ++i) h2[i] = rq[i];
-                    gm2 = g_comp<AR>(h2, xpar<AR>(p.t_eval[c0 - 2], h2[0], h2[2]), off);
-                }
-                note_segment(p, traj, c0, (int)((rp - base) / HB_HDR_DOUBLES), s, g_prev, g_first, gm2);
+                for (int i = 0; i < 7; ++i) hdr[4 + i] = f[i];
+            }
+            if (s != nacc - 1) cend = first_at_or_after(p, v[1], 0);
+        }
+        int c0 = __shfl_up_sync(FULL, cend, 1);               // t_new of a step is t_old of the next, bit for bit
+        if (lane == 0) c0 = carry_c;
+        const int nown = (have_rec && c0 < cend) ? cend - c0 : 0;
+        const bool owns = nown > 0;
+        // event function at the first (g_first), last (A) and second-to-last (B) owned sample
+        double g_first = 0.0, A = 0.0, B = 0.0;
+        if (owns) {
+            g_first = g_comp<AR>(hdr, xpar<AR>(p.t_eval[c0], hdr[0], hdr[2]), off);
+            A = g_first;
+            if (nown >= 2) {
+                A = g_comp<AR>(hdr, xpar<AR>(p.t_eval[cend - 1], hdr[0], hdr[2]), off);
+                B = (nown >= 3) ? g_comp<AR>(hdr, xpar<AR>(p.t_eval[cend - 2], hdr[0], hdr[2]), off) : g_first;
             }
         }
-        scan = cend - c0 >= 2;
-        // quiet step: no sample can be on the surface or change sign (|p(x) - (y0 + x F0)| <= sum_{i>=1}|F_i| / 4)
-        if (scan && hseg != 0.0 && cend - c0 > 4) {
-            const double g_old = __dsub_rn(hdr[3], off);
-            const double g_new = g_comp<AR>(hdr, 1.0, off);
-            double S = 0.0;
+        const unsigned own_mask = __ballot_sync(FULL, owns);
+        const unsigned two_mask = __ballot_sync(FULL, nown >= 2);
+        // nearest owner below this lane (q) and below that (q2): they hold samples c0 - 1 and (maybe) c0 - 2
+        const unsigned below = own_mask & ((1u << lane) - 1u);
+        const int q = below ? 31 - __clz(below) : -1;
+        const unsigned below2 = (q >= 0) ? (own_mask & ((1u << q) - 1u)) : 0u;
+        const int q2 = below2 ? 31 - __clz(below2) : -1;
+        const double Aq = shfl_d(A, q >= 0 ? q : 0), Bq = shfl_d(B, q >= 0 ? q : 0), Aq2 = shfl_d(A, q2 >= 0 ? q2 : 0);
+        const double g_prev = (q >= 0) ? Aq : carry1;
+        const double gm2 = (q >= 0) ? (((two_mask >> q) & 1u) ? Bq : (q2 >= 0 ? Aq2 : carry1)) : carry2;
+        const int s_prev = (q >= 0) ? base + q : carry_step;
+        bool scan = false;
+        if (owns) {
+            if (c0 > 0) {                                     // the segment that ends at this step's first sample
+                const bool same = (g_prev > 0.0 && g_first > 0.0) || (g_prev < 0.0 && g_first < 0.0);
+                if (!same || fabs(g_prev) < tol_s) note_segment(p, traj, c0, s_prev, s, g_prev, g_first, c0 > 1 ? gm2 : 0.0);
+            }
+            scan = nown >= 2;
+            // quiet step: no sample can be on the surface or change sign (|p(x) - (y0 + x F0)| <= sum_{i>=1}|F_i| / 4)
+            if (scan && hdr[2] != 0.0 && nown > 4) {
+                const double g_old = __dsub_rn(hdr[3], off);
+                const double g_new = g_comp<AR>(hdr, 1.0, off);
+                double S = 0.0;
 #pragma unroll
-            for (int i = 1; i < 7; ++i) S += fabs(hdr[4 + i]);
-            const double margin = 0.25 * S + tol_s + 1e-9 * (fabs(hdr[3]) + fabs(hdr[4]) + fabs(off)) + 1e-290;
-            const bool same = (g_old > 0.0 && g_new > 0.0) || (g_old < 0.0 && g_new < 0.0);
-            if (same && fmin(fabs(g_old), fabs(g_new)) > margin) scan = false;
+                for (int i = 1; i < 7; ++i) S += fabs(hdr[4 + i]);
+                const double margin = 0.25 * S + tol_s + 1e-9 * (fabs(hdr[3]) + fabs(hdr[4]) + fabs(off)) + 1e-290;
+                const bool same = (g_old > 0.0 && g_new > 0.0) || (g_old < 0.0 && g_new < 0.0);
+                if (same && fmin(fabs(g_old), fabs(g_new)) > margin) scan = false;
+            }
         }
-    }
-    // cooperative scan of the non-quiet steps of this warp, one owner lane at a time
-    unsigned req = __ballot_sync(0xffffffffu, scan);
-    while (req) {
-        const int L = __ffs(req) - 1;
-        req &= req - 1;
-        double bh[11];
+        // cooperative scan of the non-quiet steps of this chunk, one owner lane at a time
+        unsigned req = __ballot_sync(FULL, scan);
+        while (req) {
+            const int L = __ffs(req) - 1;
+            req &= req - 1;
+            double bh[11];
 #pragma unroll
-        for (int i = 0; i < 11; ++i) bh[i] = shfl_d(hdr[i], L);
-        const int b0 = __shfl_sync(0xffffffffu, c0, L), b1 = __shfl_sync(0xffffffffu, cend, L);
-        double carry1 = shfl_d(g_first, L), carry2 = shfl_d(g_prev, L);
-        const int sL = s - lane + L;
-        for (int b = b0 + 1; b < b1; b += 32) {
-            const int c = b + lane;
-            const bool valid = c < b1;
-            const double tq = p.t_eval[valid ? c : b1 - 1];
-            const double g = g_comp<AR>(bh, xpar<AR>(tq, bh[0], bh[2]), off);
-            double g_m1 = __shfl_up_sync(0xffffffffu, g, 1);
-            double g_m2 = __shfl_up_sync(0xffffffffu, g, 2);
-            if (lane == 0) { g_m1 = carry1; g_m2 = carry2; }
-            if (lane == 1) g_m2 = carry1;
-            const bool same = (g_m1 > 0.0 && g > 0.0) || (g_m1 < 0.0 && g < 0.0);
-            const bool flagged = valid && (!same || fabs(g_m1) < tol_s);
-            if (flagged) note_segment(p, traj, c, sL, sL, g_m1, g, g_m2);
-            const int nvalid = min(32, b1 - b);
-            const double l1 = shfl_d(g, nvalid - 1);
-            const double l2 = shfl_d(g, nvalid >= 2 ? nvalid - 2 : 0);
-            carry2 = (nvalid >= 2) ? l2 : carry1;
-            carry1 = l1;
+            for (int i = 0; i < 11; ++i) bh[i] = shfl_d(hdr[i], L);
+            const int b0 = __shfl_sync(FULL, c0, L), b1 = __shfl_sync(FULL, cend, L);
+            double c1 = shfl_d(g_first, L), c2 = shfl_d(g_prev, L);
+            const int sL = base + L;
+            for (int b = b0 + 1; b < b1; b += 32) {
+                const int cs = b + lane;
+                const bool valid = cs < b1;
+                const double tq = p.t_eval[valid ? cs : b1 - 1];
+                const double g = g_comp<AR>(bh, xpar<AR>(tq, bh[0], bh[2]), off);
+                double g_m1 = __shfl_up_sync(FULL, g, 1);
+                double g_m2 = __shfl_up_sync(FULL, g, 2);
+                if (lane == 0) { g_m1 = c1; g_m2 = c2; }
+                if (lane == 1) g_m2 = c1;
+                const bool same = (g_m1 > 0.0 && g > 0.0) || (g_m1 < 0.0 && g < 0.0);
+                const bool flagged = valid && (!same || fabs(g_m1) < tol_s);
+                if (flagged) note_segment(p, traj, cs, sL, sL, g_m1, g, g_m2);
+                const int nvalid = min(32, b1 - b);
+                const double l1 = shfl_d(g, nvalid - 1);
+                const double l2 = shfl_d(g, nvalid >= 2 ? nvalid - 2 : 0);
+                c2 = (nvalid >= 2) ? l2 : c1;
+                c1 = l1;
+            }
         }
-    }
+        // carries for the next chunk
+        if (own_mask) {
+            const int qL = 31 - __clz(own_mask);
+            const unsigned bl = own_mask & ((1u << qL) - 1u);
+            const int qL2 = bl ? 31 - __clz(bl) : -1;
+            const double a = shfl_d(A, qL), b = shfl_d(B, qL), a2 = shfl_d(A, qL2 >= 0 ? qL2 : 0);
+            carry2 = ((two_mask >> qL) & 1u) ? b : (qL2 >= 0 ? a2 : carry1);
+            carry1 = a;
+            carry_step = base + qL;
+        }
+        carry_c = __shfl_sync(FULL, cend, 31);
     }
 }
 
@@ -406,9 +406,9 @@ __global__ void __launch_bounds__(256) k_order_dedup(const ScanParams p)
 // Optional per-kernel timing of the pipeline (bench.py's roofline): CUDA events recorded on the launching stream
 // between the kernels.  Off by default; not thread safe (one profiled caller at a time).
 namespace {
-constexpr int HB_S2_STAGES = 5;      // propagate+record, headers, candidates, emit, order+dedup
+constexpr int HB_S2_STAGES = 4;      // propagate+record, step scan, emit, order+dedup
 bool g_profile = false;
-cudaEvent_t g_ev[HB_S2_STAGES + 1] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+cudaEvent_t g_ev[HB_S2_STAGES + 1] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 inline void mark(int i, cudaStream_t st) { if (g_profile && g_ev[i]) cudaEventRecord(g_ev[i], st); }
 }  // namespace
 
@@ -432,7 +432,7 @@ extern "C" int64_t hb_section2_scratch_bytes(int64_t n, int32_t steps_capacity)
 {
     if (n < 0 || steps_capacity < 1) return -1;
     steps_capacity = (steps_capacity + 31) / 32 * 32;
-    return n * ((int64_t)steps_capacity * (HB_REC_DOUBLES + HB_HDR_DOUBLES) + HB_CAND_CAP * (HB_CAND_DOUBLES + HB_DESC_DOUBLES) + 1) *
+    return n * ((int64_t)steps_capacity * HB_REC_DOUBLES + HB_CAND_CAP * (HB_CAND_DOUBLES + HB_DESC_DOUBLES) + 1) *
                (int64_t)sizeof(double) + 256;
 }
 
@@ -453,13 +453,12 @@ extern "C" int hb_cr3bp_section2(const hb_cr3bp *sys, const hb_integ *integ, con
     cudaStream_t st = (cudaStream_t)stream;
     if (n == 0) { HB_CUDA_TRY(cudaMemsetAsync(workspace, 0, sizeof(HbWorkspace), st)); return HB_OK; }
     const long long per_traj_fixed = (HB_CAND_CAP * (HB_CAND_DOUBLES + HB_DESC_DOUBLES) + 1) * (long long)sizeof(double);
-    long long cap = ((scratch_bytes - 256) / n - per_traj_fixed) / ((HB_REC_DOUBLES + HB_HDR_DOUBLES) * (long long)sizeof(double));
-    cap -= cap % 32;                                 // one warp of k_step_candidates = 32 records of ONE trajectory
+    long long cap = ((scratch_bytes - 256) / n - per_traj_fixed) / (HB_REC_DOUBLES * (long long)sizeof(double));
+    cap -= cap % 32;                                 // keeps every trajectory's records 32-step aligned
     if (cap < 32) return HB_ERR_BADARG;
     const int rec_cap = cap > 100000 ? 99968 : (int)cap;
     double *rec = (double *)scratch;
-    double *hdr = rec + n * (long long)rec_cap * HB_REC_DOUBLES;
-    double *cand = hdr + n * (long long)rec_cap * HB_HDR_DOUBLES;
+    double *cand = rec + n * (long long)rec_cap * HB_REC_DOUBLES;
     double *desc = cand + n * (long long)HB_CAND_CAP * HB_CAND_DOUBLES;
     int *cand_count = (int *)(desc + n * (long long)HB_CAND_CAP * HB_DESC_DOUBLES);    // n doubles = 2n ints
     int *desc_count = cand_count + n;
@@ -477,7 +476,6 @@ extern "C" int hb_cr3bp_section2(const hb_cr3bp *sys, const hb_integ *integ, con
     ScanParams p{};
     rc = fill_params(sys, integ, p.prop);
     if (rc != HB_OK) return rc;
-    p.hdr = hdr;
     p.n = n; p.rec = rec; p.rec_cap = rec_cap; p.nacc = n_acc; p.status = status;
     p.t_eval = t_eval; p.m = m;
     p.tsign = sys->fwd < 0 ? -1.0 : 1.0;
@@ -486,25 +484,21 @@ extern "C" int hb_cr3bp_section2(const hb_cr3bp *sys, const hb_integ *integ, con
     p.hits_per_traj = hits_per_traj;
     p.cand_count = cand_count; p.cand = cand; p.desc_count = desc_count; p.desc_total = desc_total; p.desc = desc;
     const int threads = 256;
-    const long long b1 = (n * 32 + threads - 1) / threads;       // one warp per trajectory
-    if (b1 > 1073741823LL) return HB_ERR_BADARG;
-    if (integ->arith == HB_ARITH_PARITY) k_step_headers<ArParity><<<(unsigned)(2 * b1), 128, 0, st>>>(p);
-    else k_step_headers<ArFast><<<(unsigned)(2 * b1), 128, 0, st>>>(p);
+    const long long b1 = (n * 32 + 127) / 128;                    // one warp per trajectory
+    if (b1 > 2147483647LL) return HB_ERR_BADARG;
+    if (integ->arith == HB_ARITH_PARITY) k_step_scan<ArParity><<<(unsigned)b1, 128, 0, st>>>(p);
+    else k_step_scan<ArFast><<<(unsigned)b1, 128, 0, st>>>(p);
     HB_CUDA_TRY(cudaGetLastError());
     mark(2, st);
-    if (integ->arith == HB_ARITH_PARITY) k_step_candidates<ArParity><<<(unsigned)b1, threads, 0, st>>>(p);
-    else k_step_candidates<ArFast><<<(unsigned)b1, threads, 0, st>>>(p);
-    HB_CUDA_TRY(cudaGetLastError());
-    mark(3, st);
     {
         const unsigned tb = (unsigned)sm_count() * 8u;
         if (integ->arith == HB_ARITH_PARITY) k_emit_candidates<ArParity><<<tb, 128, 0, st>>>(p);
         else k_emit_candidates<ArFast><<<tb, 128, 0, st>>>(p);
         HB_CUDA_TRY(cudaGetLastError());
     }
-    mark(4, st);
+    mark(3, st);
     k_order_dedup<<<(unsigned)((n + threads - 1) / threads), threads, 0, st>>>(p);
     HB_CUDA_TRY(cudaGetLastError());
-    mark(5, st);
+    mark(4, st);
     return HB_OK;
 }

@@ -140,7 +140,7 @@ class TubeSectionRunner:
     def __init__(self, n, mu, t_eval, section, *, forward=1, flip=None, integ=None, hit_capacity=None, device=None,
                  steps_capacity=0):
         """steps_capacity > 0 selects the kernel pipeline hb_cr3bp_section2 with a scratch for that many accepted
-        steps per trajectory (608 B per step); 0 the fused kernel hb_cr3bp_section.  Trajectories that do not fit
+        steps per trajectory (512 B per step); 0 the fused kernel hb_cr3bp_section.  Trajectories that do not fit
         the scratch are rerun with the fused kernel by hit_count() / sorted_hits(), so the result is the same."""
         from . import propagate as P
         _require_cuda()

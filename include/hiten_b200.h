@@ -153,7 +153,7 @@ int hb_cr3bp_section(const hb_cr3bp *sys, const hb_integ *integ, const hb_sectio
  * interpolant, scan the grid samples, refine the segments that can hold a hit and order + de-duplicate the hits.
  * About 2x faster than the fused kernel (which is instruction-fetch bound) whenever the scratch fits:
  * hb_section2_scratch_bytes(n, steps_capacity) bytes for at most steps_capacity accepted steps per trajectory
- * (608 B per step + 4.1 KB per trajectory).  Trajectories that need more steps, or have more than 32 candidate
+ * (512 B per step + 4.1 KB per trajectory).  Trajectories that need more steps, or have more than 32 candidate
  * hits, get status = HB_TRAJ_RECORD_OVERFLOW and NO hits; their number is read with hb_read_record_overflow --
  * rerun those with hb_cr3bp_section.                                                                 */
 int64_t hb_section2_scratch_bytes(int64_t n, int32_t steps_capacity);
@@ -163,11 +163,11 @@ int hb_cr3bp_section2(const hb_cr3bp *sys, const hb_integ *integ, const hb_secti
                       void *scratch, int64_t scratch_bytes, void *workspace, void *stream);
 
 /* Per-kernel timing of hb_cr3bp_section2 (measurement aid, used by bench.py): after hb_section2_profile(1) every
- * call records CUDA events on its stream between the five stages (propagate + record, step headers, sample scan,
- * candidate emission, order + dedup); hb_section2_read_profile waits for the last call and returns the five
- * durations in ms.  Not thread safe.                                                                 */
+ * call records CUDA events on its stream between the four stages (propagate + record, step scan, candidate
+ * emission, order + dedup); hb_section2_read_profile waits for the last call and returns the four durations
+ * in ms.  Not thread safe.                                                                           */
 int hb_section2_profile(int32_t enable);
-int hb_section2_read_profile(float *ms_out /* [5] */);
+int hb_section2_read_profile(float *ms_out /* [4] */);
 
 /* Propagation with a terminal plane event (event always terminal, as in the reference):
  * replaces _integrate_dop853_until_event + _dop853_refine_in_step (rk.py:2680-2803, 2006-2102).
