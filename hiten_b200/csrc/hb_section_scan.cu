@@ -73,6 +73,12 @@ HB_DEV double g_comp(const double *hdr, double xq, double offset)     // hdr = r
 }
 template <class AR>
 HB_DEV double xpar(double tq, double t, double hseg) { return (hseg == 0.0) ? 0.0 : AR::div(AR::sub(tq, t), hseg); }
+// the same quotient with the reciprocal of hseg prepared once (AR::rcp): used where many samples share a step
+template <class AR>
+HB_DEV double xpar_by(double tq, double t, double hseg, double inv)
+{
+    return (hseg == 0.0) ? 0.0 : AR::div_by(AR::sub(tq, t), hseg, inv);
+}
 
 // y_old, y_new and the stage rows the dense output uses (k[1..4] do not enter it; k[0] = f(y_old) is recomputed)
 template <class AR>
@@ -201,16 +207,42 @@ HB_DEV void note_segment(const ScanParams &p, long long traj, int cs, int s0, in
 //   3. proves its step quiet where it can (interpolant bound, see hb_cr3bp_section.cu); the remaining steps are
 //      scanned by the whole warp, 32 grid samples per instruction.
 // Segments that can hold a hit are only NOTED here (8 numbers); k_emit_candidates refines them.
-template <class AR>
-__global__ void __launch_bounds__(128, 4) k_step_scan(const ScanParams p)
+// The 32 records of a chunk are staged in shared memory by the copy engine: every lane issues ONE 512-byte bulk
+// copy (cp.async.bulk, completion counted on a per-warp mbarrier) instead of 28 dependent vector loads, so the HBM
+// latency is paid once per chunk and other warps compute meanwhile.  Rows are padded to 528 B (33 x 16 B): the
+// lanes' 16-byte reads then hit distinct banks.
+constexpr int HB_SCAN_WARPS = 4;
+constexpr int HB_SCAN_ROW = HB_REC_DOUBLES * 8 + 16;
+constexpr int HB_SCAN_SMEM = HB_SCAN_WARPS * (32 * HB_SCAN_ROW + 16);
+
+HB_DEV unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+HB_DEV void mbar_wait(unsigned mbar, unsigned parity)
+{
+    unsigned done = 0;
+    while (!done)
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
+}
+
+template <class AR, int C>      // C = section component (compile time: the unused parts of the extra stages fall away)
+__global__ void __launch_bounds__(32 * HB_SCAN_WARPS, 3) k_step_scan(const ScanParams p)
 {
     constexpr unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
+    extern __shared__ __align__(128) unsigned char scan_smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const long long traj = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (traj >= p.n) return;                                  // whole warp
+    unsigned char *wbase = scan_smem + wid * (32 * HB_SCAN_ROW + 16);
+    const double *row_ptr = (const double *)(wbase + lane * HB_SCAN_ROW);
+    const unsigned mbar = smem_u32(wbase + 32 * HB_SCAN_ROW), row_u32 = smem_u32(row_ptr);
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 32;" ::"r"(mbar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    unsigned phase = 0;
     const int nacc = min(p.nacc[traj], p.rec_cap);
     const double off = p.sink.sec.offset, tol_s = p.sink.sec.tol_on_surface;
-    const int c = p.sink.sec.idx;
     int carry_c = 0;                       // first grid sample not owned yet
     int carry_step = 0;                    // step that owns sample carry_c - 1
     double carry1 = 0.0, carry2 = 0.0;     // event function at samples carry_c - 1, carry_c - 2
@@ -222,21 +254,35 @@ __global__ void __launch_bounds__(128, 4) k_step_scan(const ScanParams p)
         for (int i = 0; i < 11; ++i) hdr[i] = 0.0;
         int cend = p.m;
         if (have_rec) {
-            const double *r = p.rec + (traj * p.rec_cap + s) * HB_REC_DOUBLES;
+            const double *src = p.rec + (traj * p.rec_cap + s) * HB_REC_DOUBLES;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(HB_REC_DOUBLES * 8)
+                         : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(row_u32), "l"(src), "r"(HB_REC_DOUBLES * 8), "r"(mbar) : "memory");
+        } else {
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
+        }
+        mbar_wait(mbar, phase);
+        phase ^= 1u;
+        if (have_rec) {
+            const double *r = row_ptr;
             double v[16];
 #pragma unroll
-            for (int i = 0; i < 16; i += 4) hb_ld4(r + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+            for (int i = 0; i < 16; i += 2) {
+                const double2 w = *(const double2 *)(r + i);
+                v[i] = w.x; v[i + 1] = w.y;
+            }
             const double y[6] = {v[2], v[3], v[4], v[5], v[6], v[7]}, yn[6] = {v[8], v[9], v[10], v[11], v[12], v[13]};
             const double hseg = AR::sub(v[1], v[0]);
-            hdr[0] = v[0]; hdr[1] = v[1]; hdr[2] = hseg; hdr[3] = pick6(y, c);
+            hdr[0] = v[0]; hdr[1] = v[1]; hdr[2] = hseg; hdr[3] = y[C];
             if (hseg != 0.0) {
                 const Cr3bpRhs<AR, 2> rhs{p.prop};
                 auto row = [&](int R, double (&kr)[6]) {
                     const double2 *q = (const double2 *)(r + HB_REC_K5 + 6 * (R - 5));
-                    const double2 a = __ldg(q), b = __ldg(q + 1), cc = __ldg(q + 2);
+                    const double2 a = q[0], b = q[1], cc = q[2];
                     kr[0] = a.x; kr[1] = a.y; kr[2] = b.x; kr[3] = b.y; kr[4] = cc.x; kr[5] = cc.y;
                 };
-                auto pick = [&](const double (&w)[6]) { return pick6(w, c); };
+                auto pick = [&](const double (&w)[6]) { return w[C]; };
                 double f[7];
                 dense_component<AR>(y, yn, hseg, row, pick, rhs, f);
 #pragma unroll
@@ -250,12 +296,13 @@ __global__ void __launch_bounds__(128, 4) k_step_scan(const ScanParams p)
         const bool owns = nown > 0;
         // event function at the first (g_first), last (A) and second-to-last (B) owned sample
         double g_first = 0.0, A = 0.0, B = 0.0;
+        const double inv_h = (hdr[2] != 0.0) ? AR::rcp(hdr[2]) : 0.0;
         if (owns) {
-            g_first = g_comp<AR>(hdr, xpar<AR>(p.t_eval[c0], hdr[0], hdr[2]), off);
+            g_first = g_comp<AR>(hdr, xpar_by<AR>(p.t_eval[c0], hdr[0], hdr[2], inv_h), off);
             A = g_first;
             if (nown >= 2) {
-                A = g_comp<AR>(hdr, xpar<AR>(p.t_eval[cend - 1], hdr[0], hdr[2]), off);
-                B = (nown >= 3) ? g_comp<AR>(hdr, xpar<AR>(p.t_eval[cend - 2], hdr[0], hdr[2]), off) : g_first;
+                A = g_comp<AR>(hdr, xpar_by<AR>(p.t_eval[cend - 1], hdr[0], hdr[2], inv_h), off);
+                B = (nown >= 3) ? g_comp<AR>(hdr, xpar_by<AR>(p.t_eval[cend - 2], hdr[0], hdr[2], inv_h), off) : g_first;
             }
         }
         const unsigned own_mask = __ballot_sync(FULL, owns);
@@ -298,12 +345,13 @@ __global__ void __launch_bounds__(128, 4) k_step_scan(const ScanParams p)
             for (int i = 0; i < 11; ++i) bh[i] = shfl_d(hdr[i], L);
             const int b0 = __shfl_sync(FULL, c0, L), b1 = __shfl_sync(FULL, cend, L);
             double c1 = shfl_d(g_first, L), c2 = shfl_d(g_prev, L);
+            const double binv = shfl_d(inv_h, L);
             const int sL = base + L;
             for (int b = b0 + 1; b < b1; b += 32) {
                 const int cs = b + lane;
                 const bool valid = cs < b1;
                 const double tq = p.t_eval[valid ? cs : b1 - 1];
-                const double g = g_comp<AR>(bh, xpar<AR>(tq, bh[0], bh[2]), off);
+                const double g = g_comp<AR>(bh, xpar_by<AR>(tq, bh[0], bh[2], binv), off);
                 double g_m1 = __shfl_up_sync(FULL, g, 1);
                 double g_m2 = __shfl_up_sync(FULL, g, 2);
                 if (lane == 0) { g_m1 = c1; g_m2 = c2; }
@@ -329,6 +377,7 @@ __global__ void __launch_bounds__(128, 4) k_step_scan(const ScanParams p)
             carry_step = base + qL;
         }
         carry_c = __shfl_sync(FULL, cend, 31);
+        __syncwarp();                                         // every lane is done with its row before the next copy
     }
 }
 
@@ -401,6 +450,32 @@ __global__ void __launch_bounds__(256) k_order_dedup(const ScanParams p)
     if (p.hits_per_traj) p.hits_per_traj[traj] = dd.n;
 }
 
+}  // namespace
+
+namespace {
+template <class AR, int C>
+int launch_scan_c(const ScanParams &p, unsigned grid, cudaStream_t st)
+{
+    static bool smem_set = false;       // (per instantiation)
+    if (!smem_set) {
+        HB_CUDA_TRY(cudaFuncSetAttribute(k_step_scan<AR, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, HB_SCAN_SMEM));
+        smem_set = true;
+    }
+    k_step_scan<AR, C><<<grid, 32 * HB_SCAN_WARPS, HB_SCAN_SMEM, st>>>(p);
+    return HB_OK;
+}
+template <class AR>
+int launch_scan(const ScanParams &p, unsigned grid, cudaStream_t st)
+{
+    switch (p.sink.sec.idx) {
+    case 0: return launch_scan_c<AR, 0>(p, grid, st);
+    case 1: return launch_scan_c<AR, 1>(p, grid, st);
+    case 2: return launch_scan_c<AR, 2>(p, grid, st);
+    case 3: return launch_scan_c<AR, 3>(p, grid, st);
+    case 4: return launch_scan_c<AR, 4>(p, grid, st);
+    default: return launch_scan_c<AR, 5>(p, grid, st);
+    }
+}
 }  // namespace
 
 // Optional per-kernel timing of the pipeline (bench.py's roofline): CUDA events recorded on the launching stream
@@ -484,10 +559,10 @@ extern "C" int hb_cr3bp_section2(const hb_cr3bp *sys, const hb_integ *integ, con
     p.hits_per_traj = hits_per_traj;
     p.cand_count = cand_count; p.cand = cand; p.desc_count = desc_count; p.desc_total = desc_total; p.desc = desc;
     const int threads = 256;
-    const long long b1 = (n * 32 + 127) / 128;                    // one warp per trajectory
+    const long long b1 = (n + HB_SCAN_WARPS - 1) / HB_SCAN_WARPS;      // one warp per trajectory
     if (b1 > 2147483647LL) return HB_ERR_BADARG;
-    if (integ->arith == HB_ARITH_PARITY) k_step_scan<ArParity><<<(unsigned)b1, 128, 0, st>>>(p);
-    else k_step_scan<ArFast><<<(unsigned)b1, 128, 0, st>>>(p);
+    rc = (integ->arith == HB_ARITH_PARITY) ? launch_scan<ArParity>(p, (unsigned)b1, st) : launch_scan<ArFast>(p, (unsigned)b1, st);
+    if (rc != HB_OK) return rc;
     HB_CUDA_TRY(cudaGetLastError());
     mark(2, st);
     {
