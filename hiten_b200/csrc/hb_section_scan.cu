@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(32 * HB_SCAN_WARPS, 3) k_step_scan(const ScanP
             }
             scan = nown >= 2;
             // quiet step: no sample can be on the surface or change sign (|p(x) - (y0 + x F0)| <= sum_{i>=1}|F_i| / 4)
-            if (scan && hdr[2] != 0.0 && nown > 4) {
+            if (scan && hdr[2] != 0.0) {
                 const double g_old = __dsub_rn(hdr[3], off);
                 const double g_new = g_comp<AR>(hdr, 1.0, off);
                 double S = 0.0;
