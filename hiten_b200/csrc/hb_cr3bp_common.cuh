@@ -57,6 +57,7 @@ struct PropParams {
 #define HB_REC_YNEW 8
 #define HB_REC_K5 14      // k[5..11] (7 x 6)
 #define HB_REC_K12 56     // k[12] = f(y_new); [62], [63] unused
+#define HB_REC_ROW_BYTES (HB_REC_DOUBLES * 8 + 16)   // shared-memory staging row, padded: conflict-free 16 B accesses
 
 HB_DEV void hb_st4(double *p, double a, double b, double c, double d)
 {

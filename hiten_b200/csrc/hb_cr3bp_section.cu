@@ -237,6 +237,7 @@ __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) k_dop853_6_section(con
             }
         }
         int fin = -1;
+        const double h_factor = hb_pi_factor<AR>(err, err_prev, accepted, 8.0);   // both branches, one pow
         if (accepted) {
             ++nacc;
             if (last) {
@@ -247,11 +248,11 @@ __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) k_dop853_6_section(con
             t = t_new;
 #pragma unroll
             for (int d = 0; d < 6; ++d) { y[d] = yh[d]; k[0][d] = k[12][d]; }
-            h = AR::mul(h, hb_pi_accept_factor<AR>(err, err_prev, 8.0));
+            h = AR::mul(h, h_factor);
             err_prev = err;
         } else if (have) {
             ++nrej;
-            h = AR::mul(h, hb_pi_reject_factor<AR>(err, 8.0));
+            h = AR::mul(h, h_factor);
             h = hb_clamp_step(h, p.max_step, p.min_step);
         }
         if (have && fin < 0) {

@@ -210,6 +210,7 @@ __global__ void __launch_bounds__(256, 1) k_dop853_stm(const StmParams p)
         ++attempts;
         int fin = -1;
 
+        const double h_factor = hb_pi_factor<AR>(err, err_prev, err <= 1.0, 8.0);   // both branches, one pow
         if (err <= 1.0) {
             const double t_new = AR::add(t, h);
             ++nacc;
@@ -264,11 +265,11 @@ __global__ void __launch_bounds__(256, 1) k_dop853_stm(const StmParams p)
             t = t_new;
 #pragma unroll
             for (int d = 0; d < 6; ++d) { y[d] = yh[d]; k[0][d] = k[12][d]; }
-            h = AR::mul(h, hb_pi_accept_factor<AR>(err, err_prev, 8.0));
+            h = AR::mul(h, h_factor);
             err_prev = err;
         } else {
             ++nrej;
-            h = AR::mul(h, hb_pi_reject_factor<AR>(err, 8.0));
+            h = AR::mul(h, h_factor);
             h = hb_clamp_step(h, p.max_step, p.min_step);
         }
         if (fin < 0) {

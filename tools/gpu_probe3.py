@@ -30,3 +30,5 @@ for arith in ("parity", "fast"):
         steps = int((r.n_acc.sum() + r.n_rej.sum()).item()) if kind == "propagate" else int((run.nacc.sum() + run.nrej.sum()).item())
         print(json.dumps({"lib": os.environ.get("HITEN_B200_LIB", "default"), "kind": kind, "arith": arith, "ms": round(best, 3),
                           "steps_per_s": steps / (best * 1e-3), "hits": run.hit_count() if kind == "section" else None}))
+print(json.dumps({"nacc_max": int(run.nacc.max().item()), "nacc_mean": float(run.nacc.float().mean().item()),
+                  "att_std": float((run.nacc + run.nrej).float().std().item()), "status_nonzero": int((run.status != 0).sum().item())}))
