@@ -35,7 +35,7 @@ FLOP_PER_STEP = 1350.0          # algorithmic flop per attempted 6-state DOP853 
 FLOP_PER_SEGMENT = 1050.0       # dense-output cache of one accepted step (3 RHS + D/A_ext rows)
 FLOP_PER_SAMPLE = 84.0          # one dense sample (7-term Horner x 6 components)
 GRID_DT = 1.0e-3                # Manifold.compute default dt -> 4713 samples over tf
-N_PER_GPU = 131072
+N_PER_GPU = 1_000_000            # BASELINE configs[4]: 1e6 manifold trajectories (fits one B200: 82 GB of step scratch)
 TF = 0.75 * 2.0 * np.pi
 
 
@@ -224,7 +224,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--arith", default="parity", choices=["parity", "fast"])
     ap.add_argument("--n-per-gpu", type=int, default=N_PER_GPU)
-    ap.add_argument("--steps-capacity", type=int, default=192,
+    ap.add_argument("--steps-capacity", type=int, default=160,
                     help="accepted steps per trajectory the hb_cr3bp_section2 scratch holds (0: fused hb_cr3bp_section)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary (propagate-only / fast) timings")
@@ -372,7 +372,7 @@ def main():
         for label, ar, cap in ((f"section_{other}", other, args.steps_capacity),
                                ("section_fused_kernel_parity", "parity", 0), ("section_fused_kernel_fast", "fast", 0)):
             r2 = synodic.TubeSectionRunner(n, mu, t_eval, sec, forward=-1, flip=(0, 6), integ=hb.make_integ(arith=ar),
-                                           device=dev, steps_capacity=cap)
+                                           device=dev, steps_capacity=cap, scratch=runner.scratch if cap > 0 else None)
             for _ in range(3):
                 r2.launch(y0_soa)
             t2 = time_steps(lambda: r2.launch(y0_soa), args.steps, flush, barrier, torch)
@@ -414,7 +414,7 @@ def main():
             "data": "synthetic",
             "crossings_per_s": total_hits * args.steps / t_dev,
             "config": {
-                "workload": "C5-tube (BASELINE configs[4] per-GPU share, configs[1] section): EM L1 halo (Az=0.2 S) "
+                "workload": "C5-tube (BASELINE configs[4] = 1e6 trajectories per GPU, configs[1] section): EM L1 halo (Az=0.2 S) "
                             "stable-manifold tube, 2000 nodes x log-spaced displacements, DOP853 rtol=atol=1e-12, "
                             "backward tf=0.75*2pi, dense samples on the dt=1e-3 grid (4713) streamed through the "
                             "synodic detector y=0 / (x,z) / direction=-1 (segment_refine=50), hits + end states out",
@@ -422,7 +422,7 @@ def main():
                 "path": "hb_cr3bp_section2 (propagate+record -> step scan -> emit -> order+dedup)"
                         if args.steps_capacity > 0 else "hb_cr3bp_section (fused kernel)",
                 "steps_capacity": args.steps_capacity,
-                "l2": "flushed between timed iterations (256 MB fill); inputs 6 MB/GPU, kernel is FP64-pipe bound",
+                "l2": "flushed between timed iterations (256 MB fill); inputs 48 B and step records ~44 KB per trajectory (>> L2)",
                 "rk_steps_per_pass": total_steps_pass, "accepted_steps_per_pass": total_acc,
                 "crossings_per_pass": total_hits, "all_status_ok": ok,
             },

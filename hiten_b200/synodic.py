@@ -138,10 +138,11 @@ class TubeSectionRunner:
     buffers are created once; launch() enqueues the kernels, hit_count() / sorted_hits() read the result."""
 
     def __init__(self, n, mu, t_eval, section, *, forward=1, flip=None, integ=None, hit_capacity=None, device=None,
-                 steps_capacity=0):
+                 steps_capacity=0, scratch=None):
         """steps_capacity > 0 selects the kernel pipeline hb_cr3bp_section2 with a scratch for that many accepted
         steps per trajectory (512 B per step); 0 the fused kernel hb_cr3bp_section.  Trajectories that do not fit
-        the scratch are rerun with the fused kernel by hit_count() / sorted_hits(), so the result is the same."""
+        the scratch are rerun with the fused kernel by hit_count() / sorted_hits(), so the result is the same.
+        `scratch` lets several runners share one (large) scratch tensor."""
         from . import propagate as P
         _require_cuda()
         self.lib = L.load()
@@ -164,7 +165,12 @@ class TubeSectionRunner:
         self._extra = None          # (indices, SectionHits) of the trajectories rerun with the fused kernel
         if self.steps_capacity > 0:
             nbytes = int(self.lib.hb_section2_scratch_bytes(self.n, self.steps_capacity))
-            self.scratch = torch.empty(nbytes // 8, dtype=torch.float64, device=self.device)
+            if scratch is not None:
+                if scratch.numel() * scratch.element_size() < nbytes or scratch.device != self.device:
+                    raise ValueError("scratch tensor too small or on another device")
+                self.scratch = scratch
+            else:
+                self.scratch = torch.empty(nbytes // 8, dtype=torch.float64, device=self.device)
 
     def launch(self, y0_soa, stream=None):
         self._y0, self._extra = y0_soa, None
