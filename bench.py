@@ -428,12 +428,12 @@ def main():
             },
             "roofline": {"bound": "fp64", "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "TFLOP/s",
                          "frac": achieved / peak,
-                         "traffic": (5.763e9 if (n == N_PER_GPU and args.steps_capacity > 0) else None),
+                         "traffic": (4.437e10 if (n == N_PER_GPU and args.steps_capacity > 0 and args.arith == "parity") else None),
                          "kernel": "k_dop853_6<MODE_RECORD> (+ k_first_steps)" if stage_ms is not None
                                    else "k_dop853_6_section",
                          "note": "FP64 FMA pipe roofline of the dominant kernel (its HBM side: 512 B written per "
-                                 "accepted step = 5.8 GB per launch, ~1.4 TB/s, far from the HBM roof; traffic = "
-                                 "dram read+write of one ncu --set full capture, profiles/r01_recA_v3_summary.md). "
+                                 "accepted step = 44.3 GB per launch at ~2.2 TB/s, a third of the HBM roof; traffic = "
+                                 "dram read+write of one ncu --set full capture, profiles/r01_pipeline_v4_summary.md). "
                                  "achieved = attempted steps x 1350 algorithmic flop (SURVEY 8d) / the kernel's own "
                                  "duration (CUDA events recorded between the pipeline's kernels on the launching "
                                  "stream); peak = hb_dfma_peak measured in this process"},
