@@ -153,8 +153,9 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "crossings_per_s": hits_total / t_total,
-        "config": {"workload": "C5-tube: EM L1 halo stable-manifold tube, DOP853 rtol=atol=1e-12, tf=0.75*2pi, dense "
-                               "dt=1e-3 grid + synodic detector y=0/(x,z)/-1; "
+        "config": {"workload": "C5-tube (BASELINE configs[4] trajectories, configs[1] section): EM L1 halo (Az=0.2 S) "
+                               "stable-manifold tube, DOP853 rtol=atol=1e-12, backward tf=0.75*2pi, dense samples on "
+                               "the dt=1e-3 grid (4713) + synodic detector y=0 / (x,z) / direction=-1; "
                                f"bounded sample of {sample} trajectories per step (CPU oracle port)"},
         "cpu_baseline": {"value": val, "unit": "RK steps/s", "cores": n_threads, "kind": "port",
                          "sample": f"{sample} trajectories per step, {args.steps} steps"},
