@@ -86,10 +86,25 @@ def detect(states, times, section, *, offsets=None, hit_capacity=None, device=No
         return SectionHits(rec["traj"].copy(), rec["t"].copy(), rec["state"].copy(), pts, per[:n].cpu().numpy())
 
 
+def _auto_steps_capacity(n, device, want=160):
+    """Accepted steps per trajectory the step scratch of hb_cr3bp_section2 can hold in ~60 % of the free HBM
+    (512 B per step); 0 = use the fused kernel (tiny batches, or no room)."""
+    if n < 256:
+        return 0
+    free, _ = torch.cuda.mem_get_info(device)
+    cap = min(want, int(0.6 * free / (n * 512.0)))
+    cap -= cap % 32
+    return cap if cap >= 64 else 0
+
+
 def tube_section(y0, mu, t_eval, section, *, forward=1, flip=None, integ=None, hit_capacity=None, device=None,
-                 stream=None, ws=None, sort=True):
-    """Fused Manifold.compute() + SynodicMap.compute(): propagate a batch over the t_eval grid and detect section
-    hits in-kernel, without storing the dense tube.  Returns (SectionHits, BatchResult with end states)."""
+                 stream=None, ws=None, sort=True, steps_capacity="auto"):
+    """Manifold.compute() + SynodicMap.compute() in one call: propagate a batch over the t_eval grid and detect the
+    section hits on the device, without storing the dense tube.  Returns (SectionHits, BatchResult with end states).
+
+    steps_capacity: "auto" (default) picks the kernel pipeline hb_cr3bp_section2 when the batch is large enough and
+    its step scratch fits the free device memory, else the fused kernel hb_cr3bp_section; an int forces the scratch
+    size (0 = fused kernel).  Both give the same hits, bit for bit."""
     from . import propagate as P
     _require_cuda()
     lib = L.load()
@@ -97,6 +112,19 @@ def tube_section(y0, mu, t_eval, section, *, forward=1, flip=None, integ=None, h
     with torch.cuda.device(device):
         y0d, host = P._to_device_soa(y0, device)
         n = y0d.shape[1]
+        if steps_capacity == "auto":
+            steps_capacity = _auto_steps_capacity(n, device) if sort else 0
+        if steps_capacity and sort and n > 0:
+            run = TubeSectionRunner(n, mu, t_eval, section, forward=forward, flip=flip, integ=integ,
+                                    hit_capacity=hit_capacity, device=device, steps_capacity=int(steps_capacity))
+            run.launch(y0d, stream)
+            h = run.sorted_hits(stream)
+            if host:
+                res = P.BatchResult(run.yf.t().contiguous().cpu().numpy(), run.nacc.cpu().numpy(),
+                                    run.nrej.cpu().numpy(), run.status.cpu().numpy())
+            else:
+                res = P.BatchResult(run.yf, run.nacc, run.nrej, run.status)
+            return h, res
         te = t_eval if isinstance(t_eval, torch.Tensor) else torch.from_numpy(
             np.ascontiguousarray(np.asarray(t_eval, dtype=np.float64)))
         te = te.to(device).contiguous()

@@ -139,3 +139,41 @@ def test_two_kernel_overflow_is_flagged():
     assert np.array_equal(h.times, g["hit_time"]) and np.array_equal(h.states, g["hit_state"])
     assert np.array_equal(h.trajectory_indices, g["hit_traj"])
     assert int(h.hits_per_traj.sum()) == len(g["hit_time"]) == r.hit_count()
+
+
+@pytest.mark.parametrize("axis,offset,plane,direction", [
+    ("x", 0.95, ("y", "vy"), 0), ("y", 0.0, ("x", "z"), 1), ("z", 0.0, ("x", "y"), 0),
+    ("vx", 0.0, ("x", "y"), 0), ("vy", 0.0, ("x", "z"), -1), ("vz", 0.0, ("x", "y"), 0)])
+def test_pipeline_every_section_component(axis, offset, plane, direction):
+    """The scan kernel is instantiated per section component: each one against the fused kernel AND against the
+    stored tube + detector chain (parity arithmetic: bit for bit), on the 200-trajectory tube of config 2."""
+    import torch
+    import hiten_b200 as hb
+    from hiten_b200 import synodic
+    g = np.load(os.path.join(HERE, "golden", "synodic_c2.npz"))
+    mu, tf, steps, fwd = float(g["mu"]), float(g["tf"]), int(g["steps"]), int(g["forward"])
+    t_eval = np.linspace(0.0, tf, steps)
+    sec = synodic.make_section(axis, offset, plane, direction)
+    a, ra = synodic.tube_section(g["x0W"], mu, t_eval, sec, forward=fwd, flip=(0, 6), steps_capacity=0)
+    b, rb = synodic.tube_section(g["x0W"], mu, t_eval, sec, forward=fwd, flip=(0, 6), steps_capacity=192)
+    dense = hb.cr3bp_dense(g["x0W"], mu, t_eval, forward=fwd, flip=(0, 6), keep_on_device=True)
+    c = synodic.detect(dense.states, fwd * t_eval, sec)
+    assert len(c.times) > 0, "test section has no crossings"
+    for h in (a, b):
+        assert np.array_equal(h.trajectory_indices, c.trajectory_indices)
+        assert np.array_equal(h.times, c.times) and np.array_equal(h.states, c.states)
+        assert np.array_equal(h.hits_per_traj, c.hits_per_traj)
+    assert np.array_equal(ra.yf, rb.yf) and (rb.status == 0).all()
+
+
+def test_tube_section_auto_picks_pipeline_and_matches_reference():
+    from hiten_b200 import synodic
+    g = np.load(os.path.join(HERE, "golden", "synodic_c2.npz"))
+    t_eval = np.linspace(0.0, float(g["tf"]), int(g["steps"]))
+    x0 = np.tile(g["x0W"], (2, 1))                      # 400 trajectories: above the auto threshold
+    assert synodic._auto_steps_capacity(len(x0), "cuda") > 0
+    h, res = synodic.tube_section(x0, float(g["mu"]), t_eval, _section(g), forward=int(g["forward"]), flip=(0, 6))
+    k = len(g["hit_time"])
+    assert len(h.times) == 2 * k and (res.status == 0).all()
+    assert np.array_equal(h.times[:k], g["hit_time"]) and np.array_equal(h.states[:k], g["hit_state"])
+    assert np.array_equal(h.times[k:], g["hit_time"]) and np.array_equal(h.trajectory_indices[k:], g["hit_traj"] + 200)
