@@ -441,7 +441,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "RK steps/s", "h2d_bytes_per_step": int(n * 48),
                     "d2h_bytes_per_step": int(n * (48 + 8) + 72 * k_e2e),
                     "crossings_per_s": total_hits * args.steps / e2e_t},
-            "gpu_launches": world * args.steps * ((5 if args.arith == "parity" else 4) if args.steps_capacity > 0
+            "gpu_launches": world * args.steps * ((6 if args.arith == "parity" else 5) if args.steps_capacity > 0
                                           else (2 if args.arith == "parity" else 1)),
             "clocks": clocks, "wall_s_timed_region": wall, "extra": extra,
         }

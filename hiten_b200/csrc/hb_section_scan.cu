@@ -50,8 +50,9 @@ struct ScanParams {
     int *cand_count;        // [n]
     double *cand;           // [n][HB_CAND_CAP][HB_CAND_DOUBLES]
     int *desc_count;        // [n]   segments that can hold a hit, found by k_step_scan
-    int *desc_total;        // [1]   length of the (global, unordered) list below
-    double *desc;           // [n * HB_CAND_CAP][HB_DESC_DOUBLES]
+    double *desc;           // [n][HB_CAND_CAP][HB_DESC_DOUBLES]
+    int *desc_total;        // [1]   length of the compact index below
+    int *desc_index;        // [n * HB_CAND_CAP] positions in desc of all noted segments (k_compact_segments)
 };
 
 template <class AR>
@@ -185,14 +186,14 @@ HB_DEV void segment_candidates(const hb_section &sec, bool has_prev, double g_pr
     }
 }
 
-// k_step_scan only NOTES the segments that can hold a hit (8 numbers each); k_emit_candidates below turns them
+// k_step_scan only NOTES the segments that can hold a hit (8 numbers each, per-trajectory list); k_emit_candidates turns them
 // into candidate hits.  Keeping the state reconstruction out of the scan kernel keeps it small (no spills, no call).
-HB_DEV void note_segment(const ScanParams &p, long long traj, int cs, int s0, int s1, double gk, double gk1, double gm2)
+// (the warp owns its trajectory, so slots come from a warp-uniform counter and a ballot -- no atomics, no waiting)
+HB_DEV void store_segment(const ScanParams &p, long long traj, int slot, int cs, int s0, int s1, double gk, double gk1,
+                          double gm2)
 {
-    // per-trajectory count = overflow check (and keeps the global list within n * HB_CAND_CAP)
-    if (atomicAdd(&p.desc_count[traj], 1) >= HB_CAND_CAP) return;
-    const int slot = atomicAdd(p.desc_total, 1);
-    double *d = p.desc + (long long)slot * HB_DESC_DOUBLES;
+    if (slot >= HB_CAND_CAP) return;                          // counted, reported as overflow by k_order_dedup
+    double *d = p.desc + (traj * HB_CAND_CAP + slot) * HB_DESC_DOUBLES;
     hb_st4(d, (double)traj, (double)cs, (double)s0, (double)s1);
     hb_st4(d + 4, gk, gk1, gm2, 0.0);
 }
@@ -243,6 +244,7 @@ __global__ void __launch_bounds__(32 * HB_SCAN_WARPS, 3) k_step_scan(const ScanP
     unsigned phase = 0;
     const int nacc = min(p.nacc[traj], p.rec_cap);
     const double off = p.sink.sec.offset, tol_s = p.sink.sec.tol_on_surface;
+    int ndesc = 0;                         // segments noted so far (warp-uniform)
     int carry_c = 0;                       // first grid sample not owned yet
     int carry_step = 0;                    // step that owns sample carry_c - 1
     double carry1 = 0.0, carry2 = 0.0;     // event function at samples carry_c - 1, carry_c - 2
@@ -317,11 +319,16 @@ __global__ void __launch_bounds__(32 * HB_SCAN_WARPS, 3) k_step_scan(const ScanP
         const double gm2 = (q >= 0) ? (((two_mask >> q) & 1u) ? Bq : (q2 >= 0 ? Aq2 : carry1)) : carry2;
         const int s_prev = (q >= 0) ? base + q : carry_step;
         bool scan = false;
+        {                                                     // the segment that ends at this step's first sample
+            const bool same = (g_prev > 0.0 && g_first > 0.0) || (g_prev < 0.0 && g_first < 0.0);
+            const bool flag = owns && c0 > 0 && (!same || fabs(g_prev) < tol_s);
+            const unsigned fm = __ballot_sync(FULL, flag);
+            if (flag)
+                store_segment(p, traj, ndesc + __popc(fm & ((1u << lane) - 1u)), c0, s_prev, s, g_prev, g_first,
+                              c0 > 1 ? gm2 : 0.0);
+            ndesc += __popc(fm);
+        }
         if (owns) {
-            if (c0 > 0) {                                     // the segment that ends at this step's first sample
-                const bool same = (g_prev > 0.0 && g_first > 0.0) || (g_prev < 0.0 && g_first < 0.0);
-                if (!same || fabs(g_prev) < tol_s) note_segment(p, traj, c0, s_prev, s, g_prev, g_first, c0 > 1 ? gm2 : 0.0);
-            }
             scan = nown >= 2;
             // quiet step: no sample can be on the surface or change sign (|p(x) - (y0 + x F0)| <= sum_{i>=1}|F_i| / 4)
             if (scan && hdr[2] != 0.0) {
@@ -347,10 +354,12 @@ __global__ void __launch_bounds__(32 * HB_SCAN_WARPS, 3) k_step_scan(const ScanP
             double c1 = shfl_d(g_first, L), c2 = shfl_d(g_prev, L);
             const double binv = shfl_d(inv_h, L);
             const int sL = base + L;
+            double tq_next = p.t_eval[min(b0 + 1 + lane, b1 - 1)];
             for (int b = b0 + 1; b < b1; b += 32) {
                 const int cs = b + lane;
                 const bool valid = cs < b1;
-                const double tq = p.t_eval[valid ? cs : b1 - 1];
+                const double tq = tq_next;                    // (out-of-range lanes read sample b1 - 1: unused)
+                if (b + 32 < b1) tq_next = p.t_eval[min(cs + 32, b1 - 1)];   // in flight during this batch
                 const double g = g_comp<AR>(bh, xpar_by<AR>(tq, bh[0], bh[2], binv), off);
                 double g_m1 = __shfl_up_sync(FULL, g, 1);
                 double g_m2 = __shfl_up_sync(FULL, g, 2);
@@ -358,7 +367,9 @@ __global__ void __launch_bounds__(32 * HB_SCAN_WARPS, 3) k_step_scan(const ScanP
                 if (lane == 1) g_m2 = c1;
                 const bool same = (g_m1 > 0.0 && g > 0.0) || (g_m1 < 0.0 && g < 0.0);
                 const bool flagged = valid && (!same || fabs(g_m1) < tol_s);
-                if (flagged) note_segment(p, traj, cs, sL, sL, g_m1, g, g_m2);
+                const unsigned fm = __ballot_sync(FULL, flagged);
+                if (flagged) store_segment(p, traj, ndesc + __popc(fm & ((1u << lane) - 1u)), cs, sL, sL, g_m1, g, g_m2);
+                ndesc += __popc(fm);
                 const int nvalid = min(32, b1 - b);
                 const double l1 = shfl_d(g, nvalid - 1);
                 const double l2 = shfl_d(g, nvalid >= 2 ? nvalid - 2 : 0);
@@ -379,9 +390,30 @@ __global__ void __launch_bounds__(32 * HB_SCAN_WARPS, 3) k_step_scan(const ScanP
         carry_c = __shfl_sync(FULL, cend, 31);
         __syncwarp();                                         // every lane is done with its row before the next copy
     }
+    if (lane == 0) p.desc_count[traj] = ndesc;
 }
 
-// One thread per noted segment (grid-stride over the global list): rebuild the two end states from the step
+// Compact index of all noted segments (so that k_emit_candidates runs full warps): one thread per trajectory, one
+// atomic per warp.
+__global__ void __launch_bounds__(256) k_compact_segments(const ScanParams p)
+{
+    const long long traj = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int nd = (traj < p.n) ? min(p.desc_count[traj], HB_CAND_CAP) : 0;
+    int incl = nd;                                            // inclusive warp scan
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    int base = 0;
+    if (lane == 31 && total > 0) base = atomicAdd(p.desc_total, total);
+    base = __shfl_sync(0xffffffffu, base, 31) + incl - nd;
+    for (int i = 0; i < nd; ++i) p.desc_index[base + i] = (int)(traj * HB_CAND_CAP + i);
+}
+
+// One thread per noted segment (grid-stride over the compact index): rebuild the two end states from the step
 // records and run the reference's sub-interval logic, appending candidate hits.
 template <class AR>
 __global__ void __launch_bounds__(128) k_emit_candidates(const ScanParams p)
@@ -389,7 +421,7 @@ __global__ void __launch_bounds__(128) k_emit_candidates(const ScanParams p)
     const int total = *p.desc_total;
     for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < total;
          it += (long long)gridDim.x * blockDim.x) {
-        const double *d = p.desc + it * HB_DESC_DOUBLES;
+        const double *d = p.desc + (long long)p.desc_index[it] * HB_DESC_DOUBLES;
         double d0, d1, d2, d3, gk, gk1, gm2, pad;
         hb_ld4(d, d0, d1, d2, d3);
         hb_ld4(d + 4, gk, gk1, gm2, pad);
@@ -507,7 +539,7 @@ extern "C" int64_t hb_section2_scratch_bytes(int64_t n, int32_t steps_capacity)
 {
     if (n < 0 || steps_capacity < 1) return -1;
     steps_capacity = (steps_capacity + 31) / 32 * 32;
-    return n * ((int64_t)steps_capacity * HB_REC_DOUBLES + HB_CAND_CAP * (HB_CAND_DOUBLES + HB_DESC_DOUBLES) + 1) *
+    return n * ((int64_t)steps_capacity * HB_REC_DOUBLES + HB_CAND_CAP * (HB_CAND_DOUBLES + HB_DESC_DOUBLES) + HB_CAND_CAP / 2 + 1) *
                (int64_t)sizeof(double) + 256;
 }
 
@@ -527,7 +559,8 @@ extern "C" int hb_cr3bp_section2(const hb_cr3bp *sys, const hb_integ *integ, con
         return HB_ERR_BADARG;
     cudaStream_t st = (cudaStream_t)stream;
     if (n == 0) { HB_CUDA_TRY(cudaMemsetAsync(workspace, 0, sizeof(HbWorkspace), st)); return HB_OK; }
-    const long long per_traj_fixed = (HB_CAND_CAP * (HB_CAND_DOUBLES + HB_DESC_DOUBLES) + 1) * (long long)sizeof(double);
+    const long long per_traj_fixed =
+        (HB_CAND_CAP * (HB_CAND_DOUBLES + HB_DESC_DOUBLES) + HB_CAND_CAP / 2 + 1) * (long long)sizeof(double);
     long long cap = ((scratch_bytes - 256) / n - per_traj_fixed) / (HB_REC_DOUBLES * (long long)sizeof(double));
     cap -= cap % 32;                                 // keeps every trajectory's records 32-step aligned
     if (cap < 32) return HB_ERR_BADARG;
@@ -537,12 +570,14 @@ extern "C" int hb_cr3bp_section2(const hb_cr3bp *sys, const hb_integ *integ, con
     double *desc = cand + n * (long long)HB_CAND_CAP * HB_CAND_DOUBLES;
     int *cand_count = (int *)(desc + n * (long long)HB_CAND_CAP * HB_DESC_DOUBLES);    // n doubles = 2n ints
     int *desc_count = cand_count + n;
-    int *desc_total = desc_count + n;                 // first of the 256 trailing bytes
+    int *desc_index = desc_count + n;                 // n * HB_CAND_CAP ints
+    int *desc_total = desc_index + n * (long long)HB_CAND_CAP;   // first of the 256 trailing bytes
     double ends[2];
     HB_CUDA_TRY(cudaMemcpyAsync(&ends[0], t_eval, sizeof(double), cudaMemcpyDeviceToHost, st));
     HB_CUDA_TRY(cudaMemcpyAsync(&ends[1], t_eval + (m - 1), sizeof(double), cudaMemcpyDeviceToHost, st));
     HB_CUDA_TRY(cudaStreamSynchronize(st));
-    HB_CUDA_TRY(cudaMemsetAsync(cand_count, 0, sizeof(int) * (2 * (size_t)n + 1), st));
+    HB_CUDA_TRY(cudaMemsetAsync(cand_count, 0, sizeof(int) * 2 * (size_t)n, st));
+    HB_CUDA_TRY(cudaMemsetAsync(desc_total, 0, sizeof(int), st));
     mark(0, st);
     int rc = hb_cr3bp_record_launch(sys, integ, sec->idx, n, y0_soa, ends[0], ends[1], rec, rec_cap, yf_soa, n_acc, n_rej,
                                     status, workspace, st);
@@ -557,7 +592,7 @@ extern "C" int hb_cr3bp_section2(const hb_cr3bp *sys, const hb_integ *integ, con
     p.inv_grid_dt = (ends[1] > ends[0]) ? (double)(m - 1) / (ends[1] - ends[0]) : 0.0;
     p.sink.sec = *sec; p.sink.hits = hits; p.sink.capacity = hit_capacity; p.sink.ws = (HbWorkspace *)workspace;
     p.hits_per_traj = hits_per_traj;
-    p.cand_count = cand_count; p.cand = cand; p.desc_count = desc_count; p.desc_total = desc_total; p.desc = desc;
+    p.cand_count = cand_count; p.cand = cand; p.desc_count = desc_count; p.desc = desc; p.desc_total = desc_total; p.desc_index = desc_index;
     const int threads = 256;
     const long long b1 = (n + HB_SCAN_WARPS - 1) / HB_SCAN_WARPS;      // one warp per trajectory
     if (b1 > 2147483647LL) return HB_ERR_BADARG;
@@ -566,6 +601,8 @@ extern "C" int hb_cr3bp_section2(const hb_cr3bp *sys, const hb_integ *integ, con
     HB_CUDA_TRY(cudaGetLastError());
     mark(2, st);
     {
+        k_compact_segments<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p);
+        HB_CUDA_TRY(cudaGetLastError());
         const unsigned tb = (unsigned)sm_count() * 8u;
         if (integ->arith == HB_ARITH_PARITY) k_emit_candidates<ArParity><<<tb, 128, 0, st>>>(p);
         else k_emit_candidates<ArFast><<<tb, 128, 0, st>>>(p);
