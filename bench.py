@@ -275,22 +275,10 @@ def main():
             dist.gather(runner.yf, gather_yf, dst=0)
             dist.gather(runner.per, gather_cnt, dst=0)
 
-    # pinned host result buffers (what a host caller that keeps its arrays registered would pass)
-    host_hits = torch.empty(runner.cap * 9, dtype=torch.float64).pin_memory()
-    host_yf = torch.empty((n, 6), dtype=torch.float64).pin_memory()
-    host_na = torch.empty(n, dtype=torch.int32).pin_memory()
-    host_nr = torch.empty(n, dtype=torch.int32).pin_memory()
-
-    def step_e2e():
-        d = host_in.to(dev, non_blocking=True).t().contiguous()          # H2D + AoS->SoA on device
-        runner.launch(d)
-        host_yf.copy_(runner.yf.view(6, n).t(), non_blocking=True)        # SoA->AoS on device, then D2H
-        host_na.copy_(runner.nacc[:n], non_blocking=True)
-        host_nr.copy_(runner.nrej[:n], non_blocking=True)
-        k = runner.hit_count()                                            # syncs; the hit list length is now known
-        host_hits[: k * 9].copy_(runner.hits[: k * 9], non_blocking=True)
-        torch.cuda.synchronize()
-        return k, host_hits, host_yf, host_na, host_nr
+    def make_e2e():
+        # the public streaming API: host batches in (pinned), host results out (pinned), double-buffered copies
+        return synodic.TubeSectionStream(n, mu, t_eval, sec, forward=-1, flip=(0, 6), integ=integ, device=dev,
+                                         steps_capacity=args.steps_capacity, scratch=runner.scratch)
 
     def barrier():
         if world > 1:
@@ -329,15 +317,20 @@ def main():
         lib.hb_section2_profile(0)
         stage_ms = (acc / args.steps).tolist()
 
-    # e2e: host buffers in, host results out, copies inside the timed region
-    for _ in range(2):
-        step_e2e()
+    # e2e: host buffers in, host results out, every step's H2D and D2H inside the timed region (overlapped with the
+    # neighbouring steps' compute by TubeSectionStream's double buffering)
+    stream_api = make_e2e()
+    for r in stream_api.run([host_in] * 3):
+        pass
     barrier()
     e2e_t0 = time.perf_counter()
-    for _ in range(args.steps):
-        k_e2e = step_e2e()[0]
+    k_e2e = 0
+    for r in stream_api.run([host_in] * args.steps):
+        k_e2e = r.n_hits
     barrier()
     e2e_t = time.perf_counter() - e2e_t0
+    e2e_ok = bool(k_e2e == n_hits and (r.status == 0).all())
+    del stream_api
 
     tt = torch.tensor([t_dev, e2e_t, float(steps_per_pass), float(n_hits), float(steps_acc)], dtype=torch.float64,
                       device=dev)
@@ -439,7 +432,8 @@ def main():
                                  "duration (CUDA events recorded between the pipeline's kernels on the launching "
                                  "stream); peak = hb_dfma_peak measured in this process"},
             "e2e": {"value": e2e_value, "unit": "RK steps/s", "h2d_bytes_per_step": int(n * 48),
-                    "d2h_bytes_per_step": int(n * (48 + 8) + 72 * k_e2e),
+                    "d2h_bytes_per_step": int(n * (48 + 16) + 72 * k_e2e), "same_hits_as_resident_run": e2e_ok,
+                    "api": "synodic.TubeSectionStream.run (pinned host batches in, pinned host results out)",
                     "crossings_per_s": total_hits * args.steps / e2e_t},
             "gpu_launches": world * args.steps * ((6 if args.arith == "parity" else 5) if args.steps_capacity > 0
                                           else (2 if args.arith == "parity" else 1)),

@@ -275,3 +275,107 @@ def _seq_within(traj):
         return np.empty(0, dtype=np.int64)
     start = np.r_[0, np.flatnonzero(np.diff(traj)) + 1]
     return np.arange(len(traj)) - np.repeat(start, np.diff(np.r_[start, len(traj)]))
+
+
+@dataclass
+class HostBatchResult:
+    """One batch of TubeSectionStream, in pinned host memory (valid until two more batches have been drained)."""
+    n_hits: int
+    hits: np.ndarray            # [K] HIT_DTYPE records, unordered ((traj, seq) gives the reference order)
+    end_states: np.ndarray      # [N, 6]
+    n_acc: np.ndarray           # [N]
+    n_rej: np.ndarray           # [N]
+    status: np.ndarray          # [N]
+    hits_per_traj: np.ndarray   # [N]
+
+
+class TubeSectionStream:
+    """Sweep of many equally sized host batches through tube + section (BASELINE config 5: connection sweeps):
+    double-buffered so that the host->device copy of batch i+1 and the device->host copy of batch i-1 run on
+    their own streams while batch i computes.  Inputs are [N, 6] host arrays (pinned for full overlap); results
+    come back in pinned host buffers.  The two buffer sets share one step scratch (compute is serial anyway)."""
+
+    def __init__(self, n, mu, t_eval, section, *, forward=1, flip=None, integ=None, hit_capacity=None, device=None,
+                 steps_capacity=160, scratch=None):
+        _require_cuda()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.n = int(n)
+        with torch.cuda.device(self.device):
+            r0 = TubeSectionRunner(n, mu, t_eval, section, forward=forward, flip=flip, integ=integ,
+                                   hit_capacity=hit_capacity, device=self.device, steps_capacity=steps_capacity,
+                                   scratch=scratch)
+            r1 = TubeSectionRunner(n, mu, t_eval, section, forward=forward, flip=flip, integ=integ,
+                                   hit_capacity=hit_capacity, device=self.device, steps_capacity=steps_capacity,
+                                   scratch=r0.scratch)
+            self.runners = (r0, r1)
+            self.s_in, self.s_run, self.s_out = (torch.cuda.Stream(self.device) for _ in range(3))
+            self.d_in = [torch.empty((self.n, 6), dtype=torch.float64, device=self.device) for _ in range(2)]
+            self.d_soa = [torch.empty((6, self.n), dtype=torch.float64, device=self.device) for _ in range(2)]
+            self.d_yf = [torch.empty((self.n, 6), dtype=torch.float64, device=self.device) for _ in range(2)]
+            pin = dict(pin_memory=True)
+            self.h_hits = [torch.empty(r0.cap * 9, dtype=torch.float64, **pin) for _ in range(2)]
+            self.h_yf = [torch.empty((self.n, 6), dtype=torch.float64, **pin) for _ in range(2)]
+            self.h_i32 = [torch.empty((4, self.n), dtype=torch.int32, **pin) for _ in range(2)]
+            self.ev_in = [torch.cuda.Event() for _ in range(2)]
+            self.ev_run = [torch.cuda.Event() for _ in range(2)]
+            self.ev_free = [torch.cuda.Event() for _ in range(2)]
+            for e in self.ev_free:
+                e.record(self.s_out)
+        self.h2d_bytes = self.n * 48
+        self.d2h_bytes_fixed = self.n * (48 + 16)
+
+    def _submit(self, slot, host_batch):
+        hb = host_batch if isinstance(host_batch, torch.Tensor) else torch.from_numpy(
+            np.ascontiguousarray(host_batch, dtype=np.float64))
+        if tuple(hb.shape) != (self.n, 6):
+            raise ValueError(f"batch must have shape ({self.n}, 6)")
+        run = self.runners[slot]
+        with torch.cuda.stream(self.s_in):
+            self.s_in.wait_event(self.ev_run[slot])          # the previous use of this input buffer has been consumed
+            self.d_in[slot].copy_(hb, non_blocking=True)
+            self.ev_in[slot].record(self.s_in)
+        with torch.cuda.stream(self.s_run):
+            self.s_run.wait_event(self.ev_in[slot])
+            self.s_run.wait_event(self.ev_free[slot])        # outputs of this slot have left for the host
+            self.d_soa[slot].copy_(self.d_in[slot].t())      # AoS -> SoA on the device
+            run.launch(self.d_soa[slot], self.s_run)
+            self.d_yf[slot].copy_(run.yf.view(6, self.n).t())
+            self.ev_run[slot].record(self.s_run)
+
+    def _drain(self, slot):
+        run = self.runners[slot]
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(self.ev_run[slot])
+            self.h_yf[slot].copy_(self.d_yf[slot], non_blocking=True)
+            h32 = self.h_i32[slot]
+            h32[0].copy_(run.nacc[: self.n], non_blocking=True)
+            h32[1].copy_(run.nrej[: self.n], non_blocking=True)
+            k = run.hit_count(self.s_out)                    # waits for this batch only (s_out); reruns overflows
+            h32[2].copy_(run.status[: self.n], non_blocking=True)
+            h32[3].copy_(run.per[: self.n], non_blocking=True)
+            km = run._main_hits
+            self.h_hits[slot][: km * 9].copy_(run.hits[: km * 9], non_blocking=True)
+            self.s_out.synchronize()
+            self.ev_free[slot].record(self.s_out)
+        rec = self.h_hits[slot][: km * 9].numpy().view(HIT_DTYPE)
+        if k != km:                                          # trajectories rerun with the fused kernel (rare)
+            idx, h = run._extra
+            extra = np.empty(len(h.times), dtype=HIT_DTYPE)
+            extra["traj"], extra["seq"] = idx[h.trajectory_indices], _seq_within(h.trajectory_indices)
+            extra["t"], extra["state"] = h.times, h.states
+            rec = np.concatenate((rec, extra))
+            self.h_yf[slot].copy_(run.yf.view(6, self.n).t())
+        return HostBatchResult(k, rec, self.h_yf[slot].numpy(), h32[0].numpy(), h32[1].numpy(), h32[2].numpy(),
+                               h32[3].numpy())
+
+    def run(self, batches):
+        """Generator: yields one HostBatchResult per input batch, in order."""
+        pending = None
+        for i, hb in enumerate(batches):
+            slot = i & 1
+            self._submit(slot, hb)
+            if pending is not None:
+                yield self._drain(pending)
+            pending = slot
+        if pending is not None:
+            yield self._drain(pending)

@@ -177,3 +177,31 @@ def test_tube_section_auto_picks_pipeline_and_matches_reference():
     assert len(h.times) == 2 * k and (res.status == 0).all()
     assert np.array_equal(h.times[:k], g["hit_time"]) and np.array_equal(h.states[:k], g["hit_state"])
     assert np.array_equal(h.times[k:], g["hit_time"]) and np.array_equal(h.trajectory_indices[k:], g["hit_traj"] + 200)
+
+
+def test_stream_api_double_buffered_batches_match_reference():
+    """TubeSectionStream: three host batches (two distinct) through the double-buffered pipeline; every result equals
+    the reference's hits for that batch, bit for bit."""
+    from hiten_b200 import synodic
+    g = np.load(os.path.join(HERE, "golden", "synodic_c2.npz"))
+    t_eval = np.linspace(0.0, float(g["tf"]), int(g["steps"]))
+    x0 = np.ascontiguousarray(g["x0W"])
+    rev = np.ascontiguousarray(x0[::-1])
+    st = synodic.TubeSectionStream(len(x0), float(g["mu"]), t_eval, _section(g), forward=int(g["forward"]), flip=(0, 6),
+                                   steps_capacity=192)
+    outs = []
+    for r in st.run([x0, rev, x0]):
+        rec = r.hits[np.lexsort((r.hits["seq"], r.hits["traj"]))]
+        outs.append((r.n_hits, rec["traj"].copy(), rec["t"].copy(), rec["state"].copy(), r.end_states.copy(), r.status.copy()))
+    k = len(g["hit_time"])
+    for i in (0, 2):
+        n_hits, traj, t, state, yf, status = outs[i]
+        assert n_hits == k and (status == 0).all()
+        assert np.array_equal(traj, g["hit_traj"]) and np.array_equal(t, g["hit_time"]) and np.array_equal(state, g["hit_state"])
+        assert np.array_equal(yf, g["yf"])
+    n_hits, traj, t, state, yf, status = outs[1]                 # reversed batch: same hits under the index map
+    assert n_hits == k and np.array_equal(yf, g["yf"][::-1])
+    back = len(x0) - 1 - traj
+    o = np.lexsort((t * 0, back))                                # stable within a trajectory
+    assert np.array_equal(np.sort(back), np.sort(g["hit_traj"]))
+    assert np.array_equal(np.sort(t), np.sort(g["hit_time"]))
