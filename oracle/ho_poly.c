@@ -211,3 +211,105 @@ int ho_cm_poincare_map(const ho_polyham *ham, const double *seeds, int64_t n, do
     ho_parallel_for(n, n_threads, 1, cm_item, &c);
     return 0;
 }
+
+
+/* ---- seed lifting ------------------------------------------------------------------------------- */
+typedef struct { const ho_polyham *H; double st[6]; int idx; double h0; } resid_ctx;
+
+static double residual(resid_ctx *c, double x)                     /* interfaces.py:232-238 */
+{
+    c->st[c->idx] = x;
+    return ho_poly_eval_partial(c->H, 0, c->st) - c->h0;
+}
+
+/* solve_bracketed_brent, rootfinding.py:92-190; returns 1 and *root, or 0 (None) */
+static int brent(resid_ctx *c, double a, double b, double xtol, int max_iter, double *root)
+{
+    double fa = residual(c, a), fb = residual(c, b);
+    if (fa == 0.0) { *root = a; return 1; }
+    if (fb == 0.0) { *root = b; return 1; }
+    if (fa * fb > 0.0) return 0;
+    double cc = a, fc = fa, d = b - a, e = d;
+    const double eps = 2.220446049250313e-16;
+    double tol, m;
+    for (int it = 0; it < max_iter; ++it) {
+        if (fb == 0.0) { *root = b; return 1; }
+        if (fb * fc > 0.0) { cc = a; fc = fa; d = b - a; e = d; }
+        if (fabs(fc) < fabs(fb)) {
+            a = b; b = cc; cc = a;                               /* a, b, c = b, c, b */
+            fa = fb; fb = fc; fc = fa;
+        }
+        tol = 2.0 * eps * fabs(b) + 0.5 * xtol;
+        m = 0.5 * (cc - b);
+        if (fabs(m) <= tol) { *root = b; return 1; }
+        if (fabs(e) >= tol && fabs(fa) > fabs(fb)) {
+            const double s = fb / fa;
+            double p, q;
+            if (a == cc) {
+                p = 2.0 * m * s;
+                q = 1.0 - s;
+            } else {
+                const double q_ = fa / fc, r = fb / fc;
+                p = s * (2.0 * m * q_ * (q_ - r) - (b - a) * (r - 1.0));
+                q = (q_ - 1.0) * (r - 1.0) * (s - 1.0);
+            }
+            if (p > 0.0) q = -q; else p = -p;
+            const double lim1 = 3.0 * m * q - fabs(tol * q), lim2 = fabs(e * q);
+            if ((2.0 * p) < (lim2 < lim1 ? lim2 : lim1)) { e = d; d = p / q; }   /* Python min(): first arg unless second is smaller */
+            else { d = m; e = m; }
+        } else { d = m; e = m; }
+        a = b; fa = fb;
+        if (fabs(d) > tol) b = b + d;
+        else b = b + (m > 0.0 ? tol : -tol);
+        fb = residual(c, b);
+    }
+    tol = 2.0 * eps * fabs(b) + 0.5 * xtol;
+    m = 0.5 * (cc - b);
+    if (fabs(m) <= tol || fb == 0.0) { *root = b; return 1; }
+    return 0;
+}
+
+int ho_cm_solve_missing(const ho_polyham *H, const double *fixed6, int solve_idx, double h0, double initial_guess,
+                        double expand_factor, int max_expand, int symmetric, double xtol, double *root)
+{
+    resid_ctx c;
+    c.H = H; c.idx = solve_idx; c.h0 = h0;
+    memcpy(c.st, fixed6, sizeof c.st);
+    if (residual(&c, 0.0) > 0.0) return 0;
+    double b = initial_guess, r_b = residual(&c, b);
+    int n_expand = 0;
+    while (r_b <= 0.0 && n_expand < max_expand) { b *= expand_factor; r_b = residual(&c, b); ++n_expand; }
+    if (r_b > 0.0) return brent(&c, 0.0, b, xtol, 200, root);
+    if (symmetric) {
+        double a_neg = -initial_guess, r_a = residual(&c, a_neg);
+        n_expand = 0;
+        while (r_a <= 0.0 && n_expand < max_expand) { a_neg *= expand_factor; r_a = residual(&c, a_neg); ++n_expand; }
+        if (r_a > 0.0) return brent(&c, a_neg, 0.0, xtol, 200, root);
+    }
+    return 0;
+}
+
+int ho_cm_lift(const ho_polyham *H, int section, const double *pts, int64_t n, double h0, double initial_guess,
+               double expand_factor, int max_expand, int symmetric, double xtol, int64_t *ok, double *states)
+{
+    if (section < 0 || section > 3) return -1;
+    /* variable slots: q1 0, q2 1, q3 2, p1 3, p2 4, p3 5; output order (q2, p2, q3, p3) */
+    static const int plane_a[4] = {2, 2, 1, 1}, plane_b[4] = {5, 5, 4, 4};      /* plane coordinates per section */
+    static const int missing[4] = {4, 1, 5, 2};                                  /* q2->p2, p2->q2, q3->p3, p3->q3 */
+    static const int out_slot[6] = {-1, 0, 2, -1, 1, 3};
+    for (int64_t i = 0; i < n; ++i) {
+        double fixed[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, root = 0.0;
+        fixed[plane_a[section]] = pts[2 * i];
+        fixed[plane_b[section]] = pts[2 * i + 1];
+        ok[i] = ho_cm_solve_missing(H, fixed, missing[section], h0, initial_guess, expand_factor, max_expand, symmetric,
+                                    xtol, &root);
+        double *o = states + 4 * i;
+        o[0] = o[1] = o[2] = o[3] = 0.0;
+        if (ok[i]) {
+            o[out_slot[plane_a[section]]] = pts[2 * i];
+            o[out_slot[plane_b[section]]] = pts[2 * i + 1];
+            o[out_slot[missing[section]]] = root;
+        }
+    }
+    return 0;
+}

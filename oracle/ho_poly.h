@@ -27,6 +27,15 @@ void ho_polyham_rhs(const ho_polyham *ham, const double *y, double *dy);   /* dy
 int ho_cm_poincare_map(const ho_polyham *ham, const double *seeds, int64_t n, double dt, int order, int max_steps,
                        int use_symplectic, int section, double c_omega, int64_t *flags, double *out, double *t_out,
                        int n_threads);
+
+/* Seed lifting: _CenterManifoldInterface.solve_missing_coord / lift_plane_point
+ * (algorithms/poincare/centermanifold/interfaces.py:212-268, 297-337) with solve_bracketed_brent
+ * (algorithms/utils/rootfinding.py:92-190).  `H` holds the Hamiltonian itself as polynomial 0 of the table.
+ * section: 0 q2, 1 p2, 2 q3, 3 p3; pts[n][2] plane points; states[n][4] = (q2,p2,q3,p3); ok[n] (int64). */
+int ho_cm_solve_missing(const ho_polyham *H, const double *fixed6, int solve_idx, double h0, double initial_guess,
+                        double expand_factor, int max_expand, int symmetric, double xtol, double *root);
+int ho_cm_lift(const ho_polyham *H, int section, const double *pts, int64_t n, double h0, double initial_guess,
+               double expand_factor, int max_expand, int symmetric, double xtol, int64_t *ok, double *states);
 #ifdef __cplusplus
 }
 #endif

@@ -222,3 +222,22 @@ def batch_synodic_count(times, dense, idx, offset, direction, proj, segment_refi
     return int(f(_p(times), _p(dense), C.c_int64(n), m, dim, int(idx), C.c_double(offset), int(direction),
                  int(proj[0]), int(proj[1]), int(segment_refine), C.c_double(tol_on_surface),
                  C.c_double(dedup_time_tol), C.c_double(dedup_point_tol), int(n_threads)))
+
+
+def single_poly(deg, coef, exp):
+    """Oracle table holding ONE polynomial (e.g. the Hamiltonian itself) as polynomial 0."""
+    t = len(deg)
+    return PolyHam([0, t, t, t, t, t, t], deg, coef, exp)
+
+
+def cm_lift(ham_H, section, pts, h0, initial_guess=1e-3, expand_factor=2.0, max_expand=40, symmetric=False, xtol=1e-12):
+    """lift_plane_point over a batch: returns ok[n] (int64), states[n, 4] = (q2, p2, q3, p3)."""
+    pts = np.ascontiguousarray(pts, dtype=np.float64)
+    n = pts.shape[0]
+    ok = np.zeros(n, dtype=np.int64)
+    out = np.zeros((n, 4))
+    rc = lib().ho_cm_lift(C.byref(ham_H.struct), SECTION[section], _p(pts), C.c_int64(n), C.c_double(h0),
+                          C.c_double(initial_guess), C.c_double(expand_factor), int(max_expand), int(bool(symmetric)),
+                          C.c_double(xtol), ok.ctypes.data_as(ip), _p(out))
+    assert rc == 0
+    return ok, out
