@@ -54,6 +54,11 @@ class HbCmOpts(C.Structure):
                 ("sub_sin", C.c_double * HB_MAX_TAO_SUBSTEPS)]
 
 
+class HbCmLiftOpts(C.Structure):
+    _fields_ = [("h0", C.c_double), ("initial_guess", C.c_double), ("expand_factor", C.c_double), ("xtol", C.c_double),
+                ("max_expand", C.c_int32), ("symmetric", C.c_int32), ("section", C.c_int32), ("max_iter", C.c_int32)]
+
+
 class HitenB200Error(RuntimeError):
     pass
 
@@ -82,6 +87,7 @@ SIGNATURES = {
     "hb_cr3bp_stm_dense": (C.c_int, [C.POINTER(HbCr3bp), C.POINTER(HbInteg), C.c_int64, vp, vp, C.c_int32, C.c_int32,
                                      vp, vp, vp, vp, vp, vp]),
     "hb_cm_prepare": (C.c_int, [C.POINTER(HbCmOpts), C.c_double]),
+    "hb_cm_lift": (C.c_int, [C.POINTER(HbPolyHam), C.POINTER(HbCmLiftOpts), C.c_int64, vp, vp, vp, vp]),
     "hb_cm_poincare_map": (C.c_int, [C.POINTER(HbPolyHam), C.POINTER(HbCmOpts), C.c_int64, vp, vp, vp, vp, vp, vp]),
     "hb_cm_poincare_map_jit": (C.c_int, [C.POINTER(HbPolyHam), C.POINTER(HbCmOpts), C.c_int64, vp, vp, vp, vp, vp, vp]),
     "hb_cm_jit_compile_host": (C.c_int, [vp, C.POINTER(C.c_int64), C.c_int32, C.POINTER(HbCmOpts), C.POINTER(C.c_int64),

@@ -51,6 +51,20 @@ class PolyTable:
             return cls(np.array(ptr, dtype=np.int64), np.empty(0, np.int32), np.empty(0), np.empty((0, 6), np.int32))
         return cls(np.array(ptr, dtype=np.int64), np.concatenate(deg), np.concatenate(coef), np.concatenate(exp))
 
+    @classmethod
+    def from_hamiltonian(cls, H_blocks, clmo):
+        """The Hamiltonian ITSELF (hamsys.poly_H(): H_blocks[d] = packed coefficients of degree d) as polynomial 0
+        of a table -- what lift_plane_points evaluates."""
+        t = cls.from_reference([H_blocks] + [[]] * 5, clmo)
+        return t
+
+    @classmethod
+    def single(cls, deg, coef, exp):
+        """One polynomial given as sparse terms in evaluation order (polynomial 0 of the table)."""
+        n = len(deg)
+        return cls(np.array([0] + [n] * 6, dtype=np.int64), np.asarray(deg, dtype=np.int32),
+                   np.asarray(coef, dtype=np.float64), np.asarray(exp, dtype=np.int32).reshape(-1, 6))
+
     def packed(self):
         rec = np.empty(self.coef.size, dtype=TERM_DTYPE)
         rec["coef"] = self.coef
@@ -136,3 +150,30 @@ def poincare_map(table, seeds, opts, *, device=None, stream=None, ws=None, jit=T
         if host:
             return flags.cpu().numpy().astype(np.int64), out.cpu().numpy(), tt.cpu().numpy()
         return flags, out, tt
+
+
+def lift_plane_points(H_table, section_coord, plane_points, h0, *, initial_guess=1e-3, expand_factor=2.0, max_expand=40,
+                      symmetric=False, xtol=1e-12, device=None, stream=None):
+    """Batched _CenterManifoldInterface.lift_plane_point (interfaces.py:297-337): plane_points [N, 2] in the section's
+    plane coordinates -> (ok[N] bool, states[N, 4] = (q2, p2, q3, p3)); ok is False where the reference returns None.
+    H_table: PolyTable.from_hamiltonian(hamsys.poly_H(), hamsys.clmo_table).  Bit-identical to the reference."""
+    _require_cuda()
+    lib = L.load()
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    with torch.cuda.device(device):
+        host = not (isinstance(plane_points, torch.Tensor) and plane_points.is_cuda)
+        pts = torch.from_numpy(np.ascontiguousarray(plane_points, dtype=np.float64)).to(device) if host \
+            else plane_points.contiguous()
+        if pts.dim() != 2 or pts.shape[1] != 2:
+            raise ValueError("plane_points must have shape (N, 2)")
+        n = int(pts.shape[0])
+        ok = torch.zeros(n, dtype=torch.int32, device=device)
+        out = torch.zeros((n, 4), dtype=torch.float64, device=device)
+        o = L.HbCmLiftOpts(float(h0), float(initial_guess), float(expand_factor), float(xtol), int(max_expand),
+                           int(bool(symmetric)), SECTION[section_coord], 200)
+        ham, keep = H_table.device_struct(device)
+        L.check(lib.hb_cm_lift(ham, L.C.byref(o), n, pts.data_ptr(), out.data_ptr(), ok.data_ptr(), _stream_ptr(stream)),
+                "hb_cm_lift")
+        if host:
+            return ok.cpu().numpy().astype(bool), out.cpu().numpy()
+        return ok.bool(), out

@@ -250,6 +250,27 @@ int hb_cm_poincare_map_jit(const hb_polyham *ham, const hb_cm_opts *opts, int64_
 int hb_cm_jit_compile_host(const void *terms_host, const int64_t *ptr, int32_t max_deg, const hb_cm_opts *opts,
                            int64_t *cubin_bytes, char *source_out, int64_t source_cap);
 
+/* Seed lifting for the centre-manifold map: replaces the per-seed Python Brent solves of
+ * _CenterManifoldInterface.lift_plane_point / solve_missing_coord (algorithms/poincare/centermanifold/
+ * interfaces.py:297-337, 212-268; solve_bracketed_brent algorithms/utils/rootfinding.py:92-190) that the seeding
+ * strategies (centermanifold/strategies.py:67-520) call once per candidate.  `H` holds the Hamiltonian ITSELF
+ * (hamsys.poly_H()) as polynomial 0 of a term table in hb_polyham format.  plane_pts[n][2] are points in the
+ * section's plane coordinates -- (q2,p2) for sections q3/p3, (q3,p3) for sections q2/p2 --; states[n][4] receives
+ * (q2,p2,q3,p3) with the section coordinate 0 and the missing coordinate solved from H = h0; ok[n] is 0 where the
+ * reference returns None (no bracket, or Brent did not converge).  Bit-identical to the reference.        */
+typedef struct {
+    double h0;             /* energy level                                                  */
+    double initial_guess;  /* 1e-3                                                          */
+    double expand_factor;  /* 2.0                                                           */
+    double xtol;           /* 1e-12                                                         */
+    int32_t max_expand;    /* 40                                                            */
+    int32_t symmetric;     /* also try the negative bracket                                 */
+    int32_t section;       /* 0 q2, 1 p2, 2 q3, 3 p3                                        */
+    int32_t max_iter;      /* Brent iterations, 200                                         */
+} hb_cm_lift_opts;
+int hb_cm_lift(const hb_polyham *H, const hb_cm_lift_opts *opts, int64_t n, const double *plane_pts,
+               double *states, int32_t *ok, void *stream);
+
 /* Synodic-section crossing detection on precomputed trajectories (linear branch, the one the
  * reference's defaults select): replaces _SynodicDetectionBackend.run / detect_on_trajectory /
  * _detect_with_segment_refine / _order_and_dedup_hits (algorithms/poincare/synodic/backend.py:
