@@ -200,6 +200,21 @@ def secondary_configs(hb, torch, steps, flush, barrier):
     cm_steps = float((tt / 0.01).ceil().sum().item())
     out["cm_map_tao4_1e5_seeds"] = {"steps_per_s": cm_steps * steps / t, "crossings_per_s": int(f.sum().item()) * steps / t,
                                     "ms_per_return": 1e3 * t / steps, "tflops": cm_steps * steps * 8100.0 / t / 1e12}
+    # seed lifting for the CM map (1e6 plane points -> states on the energy surface)
+    gl = np.load(os.path.join(REPO, "tests", "golden", "cm_lift.npz"))
+    Ht = cm.PolyTable.single(gl["H_deg"], gl["H_coef"], gl["H_exp"])
+    pts = torch.from_numpy(np.column_stack((rng.uniform(-1.1, 1.1, 1_000_000) * gl["turning"][0],
+                                            rng.uniform(-1.1, 1.1, 1_000_000) * gl["turning"][1]))).cuda()
+
+    def run_lift():
+        hold["l"] = cm.lift_plane_points(Ht, "p3", pts, float(gl["energy"]))
+
+    for _ in range(3):
+        run_lift()
+    t = time_steps(run_lift, steps, flush, barrier, torch)
+    out["cm_lift_1e6_plane_points"] = {"lifts_per_s": 1e6 * steps / t, "ms_per_batch": 1e3 * t / steps,
+                                       "liftable_fraction": float(hold["l"][0].float().mean().item()),
+                                       "reference": "~1e3 lifts/s (one Python Brent solve per point)"}
     s = np.load(os.path.join(REPO, "tests", "golden", "stm_family.npz"))
     x0 = torch.from_numpy(np.ascontiguousarray(np.tile(s["x0"], (128, 1)).T)).cuda()
     T = torch.from_numpy(np.tile(s["period"], 128)).cuda()
