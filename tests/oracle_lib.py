@@ -241,3 +241,22 @@ def cm_lift(ham_H, section, pts, h0, initial_guess=1e-3, expand_factor=2.0, max_
                           C.c_double(xtol), ok.ctypes.data_as(ip), _p(out))
     assert rc == 0
     return ok, out
+
+
+def connections(pu, ps, Xu, Xs, eps, dv_tol, bal_tol):
+    """_ConnectionsBackend.run restated: dict of result arrays sorted by delta_v, plus pairs_considered."""
+    pu, ps = np.ascontiguousarray(pu, dtype=np.float64), np.ascontiguousarray(ps, dtype=np.float64)
+    Xu, Xs = np.ascontiguousarray(Xu, dtype=np.float64), np.ascontiguousarray(Xs, dtype=np.float64)
+    n, m = len(pu), len(ps)
+    cap = max(min(n, m), 1)
+    kind, iu, is_ = (np.zeros(cap, dtype=np.int64) for _ in range(3))
+    dv, pt, su, ss = np.zeros(cap), np.zeros((cap, 2)), np.zeros((cap, 6)), np.zeros((cap, 6))
+    considered = C.c_int64(0)
+    f = lib().ho_connections
+    f.restype = C.c_int64
+    k = f(_p(pu), C.c_int64(n), _p(ps), C.c_int64(m), _p(Xu), _p(Xs), C.c_double(eps), C.c_double(dv_tol),
+          C.c_double(bal_tol), C.c_int64(cap), kind.ctypes.data_as(ip), _p(dv), _p(pt), _p(su), _p(ss),
+          iu.ctypes.data_as(ip), is_.ctypes.data_as(ip), C.byref(considered))
+    assert 0 <= k <= cap
+    return dict(kind=kind[:k], dv=dv[:k], pt=pt[:k], su=su[:k], ss=ss[:k], iu=iu[:k], is_=is_[:k],
+                pairs_considered=int(considered.value))
