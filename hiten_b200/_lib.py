@@ -87,6 +87,9 @@ SIGNATURES = {
     "hb_cr3bp_stm_dense": (C.c_int, [C.POINTER(HbCr3bp), C.POINTER(HbInteg), C.c_int64, vp, vp, C.c_int32, C.c_int32,
                                      vp, vp, vp, vp, vp, vp]),
     "hb_cm_prepare": (C.c_int, [C.POINTER(HbCmOpts), C.c_double]),
+    "hb_connections_scratch_bytes": (C.c_int64, [C.c_int64, C.c_int64]),
+    "hb_connections": (C.c_int, [vp, C.c_int64, vp, C.c_int64, vp, vp, C.c_double, C.c_double, C.c_double, vp, C.c_int64,
+                                 C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64), vp, C.c_int64, vp]),
     "hb_cm_lift": (C.c_int, [C.POINTER(HbPolyHam), C.POINTER(HbCmLiftOpts), C.c_int64, vp, vp, vp, vp]),
     "hb_cm_poincare_map": (C.c_int, [C.POINTER(HbPolyHam), C.POINTER(HbCmOpts), C.c_int64, vp, vp, vp, vp, vp, vp]),
     "hb_cm_poincare_map_jit": (C.c_int, [C.POINTER(HbPolyHam), C.POINTER(HbCmOpts), C.c_int64, vp, vp, vp, vp, vp, vp]),

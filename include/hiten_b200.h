@@ -271,6 +271,27 @@ typedef struct {
 int hb_cm_lift(const hb_polyham *H, const hb_cm_lift_opts *opts, int64_t n, const double *plane_pts,
                double *states, int32_t *ok, void *stream);
 
+/* Connection search between two sets of section hits: replaces _ConnectionsBackend.run
+ * (algorithms/connections/backends.py:425-540): radius pairing on the 2-D section plane (_radius_pairs_2d :100-171),
+ * mutual-nearest filter (:468-489), segment refinement with each member's nearest same-set neighbour
+ * (_nearest_neighbor_2d :174-233, _refine_pairs_on_section :323-423), Delta-V = |v_u - v_s| and the dv_tol /
+ * bal_tol classification (:507-533).  pu[n_u][2] / ps[n_s][2] are the section points of the unstable (source) and
+ * stable (target) manifolds, Xu / Xs their 6-states; all DEVICE arrays.  Accepted connections are appended to
+ * out[0 .. capacity) in arbitrary order -- the reference's order is ascending (delta_v, index_u) --; n_out,
+ * n_dropped (no room) and pairs_considered (the reference's metadata) are HOST outputs; the call synchronises
+ * `stream`.  Indices, Delta-V, points and states are bit-identical to the reference.  Points must be finite.  */
+typedef struct {
+    int64_t index_u, index_s;   /* hit indices in pu / ps                                   */
+    double delta_v;
+    double point2d[2];          /* refined common point on the section plane                */
+    double state_u[6], state_s[6];
+    int64_t kind;               /* 0 ballistic (delta_v <= bal_tol), 1 impulsive            */
+} hb_connection;
+int64_t hb_connections_scratch_bytes(int64_t n_u, int64_t n_s);
+int hb_connections(const double *pu, int64_t n_u, const double *ps, int64_t n_s, const double *Xu, const double *Xs,
+                   double eps, double dv_tol, double bal_tol, hb_connection *out, int64_t capacity, int64_t *n_out,
+                   int64_t *n_dropped, int64_t *pairs_considered, void *scratch, int64_t scratch_bytes, void *stream);
+
 /* Synodic-section crossing detection on precomputed trajectories (linear branch, the one the
  * reference's defaults select): replaces _SynodicDetectionBackend.run / detect_on_trajectory /
  * _detect_with_segment_refine / _order_and_dedup_hits (algorithms/poincare/synodic/backend.py:
