@@ -9,8 +9,8 @@
 // The hit buffers of a config-5 run hold millions of points, where the O(N*M) loops are out of reach.  Here both
 // sets are binned into a hashed uniform grid of cell size eps (counting sort: histogram, exclusive scan, scatter),
 // every point finds its best partner in the other set by scanning the 3 x 3 neighbouring cells, the mutual pairs
-// are compacted, and only THEIR nearest same-set neighbours are searched (a CTA per pair side, exact brute force
-// with the reference's first-minimum tie rule).  Distances are evaluated with the reference's expression and
+// are compacted, and only THEIR nearest same-set neighbours are searched (ring search on the own grid; sparse cases fall
+// back to an exact scan by one CTA per pair side; both with the reference's first-minimum tie rule).  Distances are evaluated with the reference's expression and
 // rounding, minima with explicit (value, index) ordering, so indices, Delta-V and refined points are bit-identical
 // whatever the order in which the grid delivers the candidates.
 #include "hb_common.cuh"
@@ -123,11 +123,50 @@ __global__ void k_mutual(const ConnParams p)
     }
 }
 
-// Nearest same-set neighbour of each pair member: one CTA per (pair, side), exact scan of the whole set.
+// Nearest same-set neighbour of each pair member, phase 1: one thread per (pair, side) searches its own grid in
+// growing square rings.  After ring r every unvisited point is at least r cells away, so the search stops as soon as
+// the best distance is strictly inside that radius (ties at the boundary cannot be missed).  Sparse neighbourhoods
+// that are not settled within NN_MAX_RING rings are left to the exact scan below (nn = -2).
+constexpr int NN_MAX_RING = 6;
+__global__ void __launch_bounds__(CB) k_pair_neighbours_grid(const ConnParams p)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 2 * (long long)p.counters[1]) return;
+    const int side = (int)(t & 1);
+    const double *P = side ? p.ps : p.pu;
+    const long long n = side ? p.ns : p.nu;
+    const Grid &g = side ? p.gs : p.gu;
+    const int self = p.pairs[t];
+    if (n < 2) { p.nn[t] = -1; return; }
+    const double sx = P[2 * self], sy = P[2 * self + 1];
+    const long long cx = cell_of(sx, p.cell), cy = cell_of(sy, p.cell);
+    double best_v = 1e300;
+    int best = -1;
+    bool settled = false;
+    for (int r = 0; r <= NN_MAX_RING && !settled; ++r) {
+        for (int oy = -r; oy <= r; ++oy)
+            for (int ox = -r; ox <= r; ++ox) {
+                if (max(abs(ox), abs(oy)) != r) continue;                 // ring r only
+                const int b = bucket_of(cx + ox, cy + oy, g.mask);
+                for (int k = g.count[b]; k < g.count[b + 1]; ++k) {
+                    const int j = g.order[k];
+                    if (j == self) continue;
+                    const double v = dist2(sx, sy, P[2 * j], P[2 * j + 1]);
+                    if (v < best_v || (v == best_v && j < best)) { best_v = v; best = j; }
+                }
+            }
+        const double reach = (double)r * p.cell;
+        settled = best >= 0 && best_v < reach * reach * (1.0 - 1e-12);
+    }
+    p.nn[t] = settled ? best : -2;
+}
+
+// Phase 2: one CTA per (pair, side) still open, exact scan of the whole set.
 __global__ void __launch_bounds__(CB) k_pair_neighbours(const ConnParams p)
 {
     const long long pair = blockIdx.x >> 1;
     const int side = blockIdx.x & 1;
+    if (p.nn[2 * pair + side] != -2) return;
     const double *P = side ? p.ps : p.pu;
     const long long n = side ? p.ns : p.nu;
     const int self = p.pairs[2 * pair + side];
@@ -329,6 +368,7 @@ extern "C" int hb_connections(const double *pu, int64_t n_u, const double *ps, i
     const long long n_pairs = (long long)h[1];
     if (n_pairs == 0) return HB_OK;
     if (2 * n_pairs > 2147483647LL) return HB_ERR_UNSUPPORTED;
+    k_pair_neighbours_grid<<<(unsigned)((2 * n_pairs + CB - 1) / CB), CB, 0, st>>>(p);
     k_pair_neighbours<<<(unsigned)(2 * n_pairs), CB, 0, st>>>(p);
     k_refine<<<(unsigned)((n_pairs + CB - 1) / CB), CB, 0, st>>>(p);
     HB_CUDA_TRY(cudaGetLastError());
