@@ -215,6 +215,25 @@ def secondary_configs(hb, torch, steps, flush, barrier):
     out["cm_lift_1e6_plane_points"] = {"lifts_per_s": 1e6 * steps / t, "ms_per_batch": 1e3 * t / steps,
                                        "liftable_fraction": float(hold["l"][0].float().mean().item()),
                                        "reference": "~1e3 lifts/s (one Python Brent solve per point)"}
+    # connection search between two sets of 2e6 section hits (what a config-5 sweep produces)
+    from hiten_b200 import connections as cn
+    nn, eps = 2_000_000, 1.5e-4
+    pu = rng.uniform(-0.4, 0.4, (nn, 2))
+    ps = np.vstack((pu[rng.choice(nn, nn // 2, replace=False)] + rng.uniform(-1, 1, (nn // 2, 2)) * eps * 0.8,
+                    rng.uniform(-0.4, 0.4, (nn - nn // 2, 2))))
+    dd = [torch.from_numpy(a).cuda() for a in (pu, ps, rng.normal(0, 0.2, (nn, 6)), rng.normal(0, 0.2, (nn, 6)))]
+    best = 1e9
+    for _ in range(3):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        rc = cn.find_connections(*dd, eps, 0.5, 1e-3)
+        torch.cuda.synchronize()
+        best = min(best, time.perf_counter() - t0)
+    out["connections_2e6_x_2e6_hits"] = {"ms": 1e3 * best, "pairs_considered": rc.pairs_considered,
+                                         "accepted": int(len(rc.delta_v)),
+                                         "note": "wall time incl. result D2H and ordering; the reference's pairing is an "
+                                                 "O(N*M) = 4e12 double loop plus Python dicts"}
+    del dd
     s = np.load(os.path.join(REPO, "tests", "golden", "stm_family.npz"))
     x0 = torch.from_numpy(np.ascontiguousarray(np.tile(s["x0"], (128, 1)).T)).cuda()
     T = torch.from_numpy(np.tile(s["period"], 128)).cuda()

@@ -25,6 +25,7 @@ import sys
 import numpy as np
 
 from . import centermanifold as _cm
+from . import connections as _conn
 from . import propagate as _prop
 from . import synodic as _syn
 
@@ -363,6 +364,32 @@ def _make_cm_run(orig):
     return run
 
 
+def _make_connections_run(orig):
+    def run(self, request):
+        """_ConnectionsBackend.run (algorithms/connections/backends.py:425-540) through hb_connections."""
+        from hiten.algorithms.connections.types import ConnectionsBackendResponse, _ConnectionResult
+        pu, ps = np.asarray(request.points_u, dtype=np.float64), np.asarray(request.points_s, dtype=np.float64)
+        if pu.size == 0 or ps.size == 0:
+            return ConnectionsBackendResponse(results=[], metadata={})
+        c = _conn.find_connections(pu, ps, request.states_u, request.states_s, float(request.eps), float(request.dv_tol),
+                                   float(request.bal_tol), traj_indices_u=request.traj_indices_u,
+                                   traj_indices_s=request.traj_indices_s)
+        if c.pairs_considered == 0:
+            return ConnectionsBackendResponse(results=[], metadata={})
+        results = [_ConnectionResult(kind=_conn.KINDS[int(c.kind[k])], delta_v=float(c.delta_v[k]),
+                                     point2d=(float(c.point2d[k, 0]), float(c.point2d[k, 1])),
+                                     state_u=c.state_u[k].copy(), state_s=c.state_s[k].copy(),
+                                     index_u=int(c.index_u[k]), index_s=int(c.index_s[k]),
+                                     trajectory_index_u=int(c.trajectory_index_u[k]),
+                                     trajectory_index_s=int(c.trajectory_index_s[k])) for k in range(len(c.delta_v))]
+        metadata = dict(request.metadata)
+        metadata.update({"pairs_considered": c.pairs_considered, "accepted": len(results)})
+        return ConnectionsBackendResponse(results=results, metadata=metadata)
+
+    run.__wrapped__ = orig
+    return run
+
+
 # ------------------------------------------------------------------------------------------------
 # install / uninstall
 # ------------------------------------------------------------------------------------------------
@@ -373,6 +400,7 @@ def install(arith="parity"):
         return
     import hiten  # noqa: F401
     import hiten.algorithms.dynamics.base as dbase
+    from hiten.algorithms.connections.backends import _ConnectionsBackend
     from hiten.algorithms.integrators.rk import _DOP853
     from hiten.algorithms.poincare.centermanifold.backend import _CenterManifoldBackend
     from hiten.algorithms.poincare.synodic.backend import _SynodicDetectionBackend
@@ -393,11 +421,13 @@ def install(arith="parity"):
         "run_compute": _ManifoldDynamicsService._run_compute,
         "synodic": _SynodicDetectionBackend.run,
         "cm": _CenterManifoldBackend.run,
+        "connections": _ConnectionsBackend.run,
     }
     _DOP853.integrate = _make_dop853_integrate(_STATE["orig"]["dop853"])
     _ManifoldDynamicsService._run_compute = _make_run_compute(_STATE["orig"]["run_compute"])
     _SynodicDetectionBackend.run = _make_synodic_run(_STATE["orig"]["synodic"])
     _CenterManifoldBackend.run = _make_cm_run(_STATE["orig"]["cm"])
+    _ConnectionsBackend.run = _make_connections_run(_STATE["orig"]["connections"])
     _STATE["installed"] = True
 
 
@@ -415,6 +445,8 @@ def uninstall():
     _ManifoldDynamicsService._run_compute = o["run_compute"]
     _SynodicDetectionBackend.run = o["synodic"]
     _CenterManifoldBackend.run = o["cm"]
+    from hiten.algorithms.connections.backends import _ConnectionsBackend
+    _ConnectionsBackend.run = o["connections"]
     _STATE.update(installed=False, orig={}, patched_modules=[])
     _TABLES.clear()
 

@@ -77,6 +77,15 @@ def poincare_map(table, seeds, opts, **kw):
     return O.cm_poincare_map(ham, seeds, opts.dt, order, opts.max_steps, symp, sec, c_omega, 4)
 
 
+def find_connections(points_u, points_s, states_u, states_s, eps, dv_tol, bal_tol, *, traj_indices_u=None,
+                     traj_indices_s=None, **kw):
+    from hiten_b200.connections import Connections
+    r = O.connections(points_u, points_s, states_u, states_s, eps, dv_tol, bal_tol)
+    tu = np.asarray(traj_indices_u)[r["iu"]] if traj_indices_u is not None else np.zeros(len(r["iu"]), np.int64)
+    ts = np.asarray(traj_indices_s)[r["is_"]] if traj_indices_s is not None else np.zeros(len(r["iu"]), np.int64)
+    return Connections(r["kind"], r["dv"], r["pt"], r["su"], r["ss"], r["iu"], r["is_"], tu, ts, r["pairs_considered"])
+
+
 def patch(monkeypatch):
     import hiten_b200.centermanifold as cm
     import hiten_b200.propagate as prop
@@ -86,3 +95,5 @@ def patch(monkeypatch):
     monkeypatch.setattr(prop, "cr3bp_event", cr3bp_event)
     monkeypatch.setattr(syn, "detect", detect)
     monkeypatch.setattr(cm, "poincare_map", poincare_map)
+    import hiten_b200.connections as conn
+    monkeypatch.setattr(conn, "find_connections", find_connections)

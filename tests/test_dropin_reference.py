@@ -139,3 +139,28 @@ def test_centre_manifold_map_through_the_public_api(ref, monkeypatch):
         hiten_b200.uninstall()
     assert got.shape == want.shape and got.shape[0] > 0
     assert np.array_equal(got, want)
+
+
+def test_connections_backend_through_the_drop_in(ref, monkeypatch):
+    """_ConnectionsBackend.run with the drop-in installed returns the reference's own result objects, identical to
+    the unpatched backend (SURVEY 8f#2)."""
+    import fake_gpu
+    import hiten_b200
+    from hiten.algorithms.connections.backends import _ConnectionsBackend
+    from hiten.algorithms.connections.types import ConnectionsBackendRequest
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "connections.npz"))
+    req = ConnectionsBackendRequest(points_u=g["b_pu"], points_s=g["b_ps"], states_u=g["b_Xu"], states_s=g["b_Xs"],
+                                    traj_indices_u=g["b_tu"], traj_indices_s=g["b_ts"], eps=float(g["b_eps"]),
+                                    dv_tol=float(g["b_dv_tol"]), bal_tol=float(g["b_bal_tol"]), metadata={"tag": 1})
+    want = _ConnectionsBackend().run(req)
+    fake_gpu.patch(monkeypatch)
+    hiten_b200.install()
+    try:
+        got = _ConnectionsBackend().run(req)
+    finally:
+        hiten_b200.uninstall()
+    assert got.metadata == want.metadata and len(got.results) == len(want.results) > 100
+    for a, b in zip(got.results, want.results):
+        assert (a.kind, a.delta_v, a.point2d, a.index_u, a.index_s, a.trajectory_index_u, a.trajectory_index_s) == \
+               (b.kind, b.delta_v, b.point2d, b.index_u, b.index_s, b.trajectory_index_u, b.trajectory_index_s)
+        assert np.array_equal(a.state_u, b.state_u) and np.array_equal(a.state_s, b.state_s)
