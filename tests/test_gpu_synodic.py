@@ -205,3 +205,28 @@ def test_stream_api_double_buffered_batches_match_reference():
     o = np.lexsort((t * 0, back))                                # stable within a trajectory
     assert np.array_equal(np.sort(back), np.sort(g["hit_traj"]))
     assert np.array_equal(np.sort(t), np.sort(g["hit_time"]))
+
+
+def test_pipeline_equals_fused_on_a_bench_sized_slice_with_overflow_rerun():
+    """20000 trajectories of the bench batch: the pipeline (with a scratch too small for the longest trajectories, so
+    that the fused-kernel rerun path is exercised) returns exactly the fused kernel's hits, counts and end states."""
+    import torch
+    import bench
+    from hiten_b200 import synodic
+    n = 20000
+    ics, mu = bench.build_ics(n)
+    m = max(int(abs(bench.TF) / bench.GRID_DT) + 1, 100)
+    t_eval = np.linspace(0.0, bench.TF, m)
+    sec = synodic.make_section("y", 0.0, ("x", "z"), -1)
+    y0 = torch.from_numpy(np.ascontiguousarray(ics.T)).cuda()
+    a = synodic.TubeSectionRunner(n, mu, t_eval, sec, forward=-1, flip=(0, 6))
+    b = synodic.TubeSectionRunner(n, mu, t_eval, sec, forward=-1, flip=(0, 6), steps_capacity=96)
+    a.launch(y0); b.launch(y0)
+    overflowed = int((b.status == 4).sum().item())
+    ha, hb_ = a.sorted_hits(), b.sorted_hits()
+    assert 0 < overflowed < n // 2                      # some, not most, trajectories need more than 96 steps
+    assert (b.status == 0).all().item() and a.hit_count() == b.hit_count() > n
+    assert np.array_equal(ha.trajectory_indices, hb_.trajectory_indices)
+    assert np.array_equal(ha.times, hb_.times) and np.array_equal(ha.states, hb_.states)
+    assert np.array_equal(ha.hits_per_traj, hb_.hits_per_traj)
+    assert torch.equal(a.yf, b.yf) and torch.equal(a.nacc, b.nacc) and torch.equal(a.nrej, b.nrej)
