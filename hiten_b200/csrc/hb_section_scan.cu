@@ -8,8 +8,9 @@
 //      EVENT COMPONENT of the step's interpolant in registers, finds the grid samples the step owns and proves
 //      most steps quiet (interpolant bound, see hb_cr3bp_section.cu); the others are scanned by the whole warp,
 //      32 grid samples per instruction, and the segments that can hold a hit are NOTED (8 numbers);
-//   B2 k_emit_candidates: one thread per noted segment rebuilds the two end states from the step records, runs
-//      the reference's sub-interval logic and appends CANDIDATE hits {sample index, order, t, state};
+//   B2 k_compact_segments + k_emit_candidates: a compact index over the per-trajectory segment lists, then one
+//      thread per noted segment rebuilds the two end states from the step records, runs the reference's
+//      sub-interval logic and appends CANDIDATE hits {sample index, order, t, state};
 //   B3 k_order_dedup: one thread per trajectory sorts its few candidates into the reference's order and applies
 //      _order_and_dedup_hits (dedup against the previous kept hit, max_hits_per_traj), appending the hits.
 //
