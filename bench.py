@@ -461,7 +461,7 @@ def main():
                                    else "k_dop853_6_section",
                          "note": "FP64 FMA pipe roofline of the dominant kernel (its HBM side: 512 B written per "
                                  "accepted step = 44.3 GB per launch at ~2.2 TB/s, a third of the HBM roof; traffic = "
-                                 "dram read+write of one ncu --set full capture, profiles/r01_pipeline_v4_summary.md). "
+                                 "dram read+write of one ncu --set full capture, profiles/r01_pipeline_v5_summary.md). "
                                  "achieved = attempted steps x 1350 algorithmic flop (SURVEY 8d) / the kernel's own "
                                  "duration (CUDA events recorded between the pipeline's kernels on the launching "
                                  "stream); peak = hb_dfma_peak measured in this process"},
