@@ -65,3 +65,34 @@ def test_tao_schedule_matches_reference_recursion():
         omega = (20.0 * 0.01) ** (-float(order))
         import math
         assert o.sub_cos[0] == math.cos(2 * omega * ts[0]) and o.sub_sin[0] == math.sin(2 * omega * ts[0])
+
+
+def test_argument_validation_needs_no_gpu():
+    """Usage errors are rejected with HB_ERR_BADARG (-1) / HB_ERR_UNSUPPORTED before anything touches the device, and
+    the size helpers are pure host arithmetic."""
+    lib = _lib.load()
+    C = ctypes
+    i64 = C.c_int64
+    # scratch sizes: monotone, 512 B per step per trajectory plus the fixed part
+    a, b = lib.hb_section2_scratch_bytes(1000, 64), lib.hb_section2_scratch_bytes(1000, 128)
+    assert b - a == 1000 * 64 * 512 and a > 1000 * 64 * 512
+    assert lib.hb_section2_scratch_bytes(10, 0) < 0 and lib.hb_section2_scratch_bytes(-1, 64) < 0
+    assert lib.hb_connections_scratch_bytes(1000, 2000) > 0 and lib.hb_connections_scratch_bytes(-1, 5) < 0
+    # null / inconsistent arguments
+    n_out = i64(7)
+    assert lib.hb_connections(None, 5, None, 5, None, None, 1e-3, 1.0, 1e-3, None, 0, C.byref(n_out), None, None, None, 0,
+                              None) < 0
+    assert lib.hb_connections(None, 0, None, 5, None, None, 1e-3, 1.0, 1e-3, None, 0, C.byref(n_out), None, None, None, 0,
+                              None) == 0 and n_out.value == 0                     # an empty set: no connections
+    assert lib.hb_connections(None, 5, None, 5, None, None, -1.0, 1.0, 1e-3, None, 0, C.byref(n_out), None, None, None, 0,
+                              None) < 0                                           # eps must be positive
+    ham = _lib.HbPolyHam(3, 6, (C.c_int64 * 7)(0, 0, 0, 0, 0, 0, 0), None)
+    o = _lib.HbCmLiftOpts(0.7, 1e-3, 2.0, 1e-12, 40, 0, 7, 200)                   # section 7 does not exist
+    assert lib.hb_cm_lift(C.byref(ham), C.byref(o), 4, None, None, None, None) < 0
+    o.section = 3
+    assert lib.hb_cm_lift(C.byref(ham), C.byref(o), 0, None, None, None, None) == 0   # n = 0 is a no-op
+    assert lib.hb_cm_lift(C.byref(ham), C.byref(o), 4, None, None, None, None) < 0    # null arrays
+    sysd, integ, sec = _lib.HbCr3bp(0.0121, 1, -1, -1, 0), hiten_b200.make_integ(), hiten_b200.synodic.make_section("y")
+    assert lib.hb_cr3bp_section2(C.byref(sysd), C.byref(integ), C.byref(sec), 8, None, None, 1, None, 0, None, None, None,
+                                 None, None, None, 0, None, None) < 0             # m < 2, no workspace
+    assert lib.hb_read_record_overflow(None, None, None) < 0
