@@ -203,6 +203,31 @@ def secondary_configs(hb, torch, steps, flush, barrier):
                       "ms_per_return": 1e3 * t / steps, "tflops": cm_steps * steps * 8100.0 / t / 1e12}
     out["cm_map_tao4_1e5_seeds"]["note"] = ("critical-path bound: the slowest seed needs ~1300 sequential steps of "
                                             "~20 us; 1e6 seeds fill the machine")
+    # BASELINE configs[0] / [1] as they are (50 / 200 trajectories): small-batch latency, not throughput
+    from hiten_b200 import synodic as syn
+    c1 = np.load(os.path.join(REPO, "tests", "golden", "c1_manifold.npz"))
+    te1 = np.linspace(0.0, float(c1["tf"]), 4713)
+    x1 = torch.from_numpy(np.ascontiguousarray(c1["x0W"].T)).cuda()
+    c2 = np.load(os.path.join(REPO, "tests", "golden", "synodic_c2.npz"))
+    te2 = np.linspace(0.0, float(c2["tf"]), int(c2["steps"]))
+    x2 = torch.from_numpy(np.ascontiguousarray(c2["x0W"].T)).cuda()
+    sec2 = syn.make_section("y", 0.0, ("x", "z"), -1)
+    r2 = syn.TubeSectionRunner(x2.shape[1], float(c2["mu"]), te2, sec2, forward=int(c2["forward"]), flip=(0, 6))
+
+    def run_c1():
+        hold["c1"] = hb.cr3bp_dense(x1, float(c1["mu"]), te1, forward=-1, flip=(0, 6), keep_on_device=True)
+
+    def run_c2():
+        r2.launch(x2)
+
+    for fn in (run_c1, run_c2):
+        for _ in range(3):
+            fn()
+    out["config1_manifold_50_trajectories_dense_4713"] = {"ms": 1e3 * time_steps(run_c1, steps, flush, barrier, torch) / steps,
+                                                          "reference": "3.95 ms per trajectory (BASELINE.md) = ~200 ms"}
+    out["config2_tube_200_trajectories_plus_section"] = {"ms": 1e3 * time_steps(run_c2, steps, flush, barrier, torch) / steps,
+                                                         "crossings": r2.hit_count(),
+                                                         "reference": "~0.8 s propagation + 21 s detection (SURVEY 8a17)"}
     # seed lifting for the CM map (1e6 plane points -> states on the energy surface)
     gl = np.load(os.path.join(REPO, "tests", "golden", "cm_lift.npz"))
     Ht = cm.PolyTable.single(gl["H_deg"], gl["H_coef"], gl["H_exp"])

@@ -494,6 +494,19 @@ extern "C" int hb_cm_poincare_map_jit(const hb_polyham *ham, const hb_cm_opts *o
     const size_t b_cont = sizeof(double) * 16 * (size_t)n, b_list = sizeof(int) * (size_t)n;
     const size_t b_ctr = 16 * (size_t)(rounds + 1);                  // per round: u64 cursor + int count (+pad)
     char *tmp = nullptr;
+    {
+        // keep the stream-ordered pool's memory across calls (the default releases it at every synchronisation and
+        // the next call pays for a fresh 100+ MB allocation)
+        static bool pool_set = false;
+        if (!pool_set) {
+            cudaMemPool_t pool = nullptr;
+            if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess && pool) {
+                unsigned long long keep = ~0ULL;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+            pool_set = true;
+        }
+    }
     HB_CUDA_TRY(cudaMallocAsync((void **)&tmp, b_cont + 2 * b_list + b_ctr, st));
     double *cont = (double *)tmp;
     int *lists[2] = {(int *)(tmp + b_cont), (int *)(tmp + b_cont + b_list)};
