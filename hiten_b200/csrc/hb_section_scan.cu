@@ -52,7 +52,7 @@ struct ScanParams {
     double *cand;           // [n][HB_CAND_CAP][HB_CAND_DOUBLES]
     int *desc_count;        // [n]   segments that can hold a hit, found by k_step_scan
     double *desc;           // [n][HB_CAND_CAP][HB_DESC_DOUBLES]
-    int *desc_total;        // [1]   length of the compact index below
+    int *desc_total;        // [2]   entries at the front / at the back of the compact index below
     int *desc_index;        // [n * HB_CAND_CAP] positions in desc of all noted segments (k_compact_segments)
 };
 
@@ -394,14 +394,12 @@ __global__ void __launch_bounds__(32 * HB_SCAN_WARPS, 3) k_step_scan(const ScanP
     if (lane == 0) p.desc_count[traj] = ndesc;
 }
 
-// Compact index of all noted segments (so that k_emit_candidates runs full warps): one thread per trajectory, one
-// atomic per warp.
-__global__ void __launch_bounds__(256) k_compact_segments(const ScanParams p)
+// Compact index of all noted segments (so that k_emit_candidates runs full warps): one thread per trajectory, two
+// atomics per warp.  Segments whose two samples sit in ONE step (the common case) are indexed from the front, those
+// that straddle two steps (two records to rebuild) from the back, so that almost every emit warp is of one kind.
+HB_DEV int warp_exclusive_base(int mine, int lane, int *counter)
 {
-    const long long traj = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    const int nd = (traj < p.n) ? min(p.desc_count[traj], HB_CAND_CAP) : 0;
-    int incl = nd;                                            // inclusive warp scan
+    int incl = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const int v = __shfl_up_sync(0xffffffffu, incl, o);
@@ -409,9 +407,29 @@ __global__ void __launch_bounds__(256) k_compact_segments(const ScanParams p)
     }
     const int total = __shfl_sync(0xffffffffu, incl, 31);
     int base = 0;
-    if (lane == 31 && total > 0) base = atomicAdd(p.desc_total, total);
-    base = __shfl_sync(0xffffffffu, base, 31) + incl - nd;
-    for (int i = 0; i < nd; ++i) p.desc_index[base + i] = (int)(traj * HB_CAND_CAP + i);
+    if (lane == 31 && total > 0) base = atomicAdd(counter, total);
+    return __shfl_sync(0xffffffffu, base, 31) + incl - mine;
+}
+
+__global__ void __launch_bounds__(256) k_compact_segments(const ScanParams p)
+{
+    const long long traj = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int nd = (traj < p.n) ? min(p.desc_count[traj], HB_CAND_CAP) : 0;
+    unsigned same = 0u;                                       // bit i: segment i has both samples in one step
+    for (int i = 0; i < nd; ++i) {
+        const double *d = p.desc + (traj * HB_CAND_CAP + i) * HB_DESC_DOUBLES;
+        if (d[2] == d[3]) same |= 1u << i;
+    }
+    const int n_same = __popc(same), n_split = nd - n_same;
+    int front = warp_exclusive_base(n_same, lane, &p.desc_total[0]);
+    int back = warp_exclusive_base(n_split, lane, &p.desc_total[1]);
+    const long long last = p.n * HB_CAND_CAP - 1;
+    for (int i = 0; i < nd; ++i) {
+        const int where = (int)(traj * HB_CAND_CAP + i);
+        if ((same >> i) & 1u) p.desc_index[front++] = where;
+        else p.desc_index[last - back++] = where;
+    }
 }
 
 // One thread per noted segment (grid-stride over the compact index): rebuild the two end states from the step
@@ -419,10 +437,12 @@ __global__ void __launch_bounds__(256) k_compact_segments(const ScanParams p)
 template <class AR>
 __global__ void __launch_bounds__(128) k_emit_candidates(const ScanParams p)
 {
-    const int total = *p.desc_total;
+    const int n_front = p.desc_total[0], total = n_front + p.desc_total[1];
+    const long long last = p.n * HB_CAND_CAP - 1;
     for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < total;
          it += (long long)gridDim.x * blockDim.x) {
-        const double *d = p.desc + (long long)p.desc_index[it] * HB_DESC_DOUBLES;
+        const long long at = (it < n_front) ? it : last - (it - n_front);
+        const double *d = p.desc + (long long)p.desc_index[at] * HB_DESC_DOUBLES;
         double d0, d1, d2, d3, gk, gk1, gm2, pad;
         hb_ld4(d, d0, d1, d2, d3);
         hb_ld4(d + 4, gk, gk1, gm2, pad);
@@ -578,7 +598,7 @@ extern "C" int hb_cr3bp_section2(const hb_cr3bp *sys, const hb_integ *integ, con
     HB_CUDA_TRY(cudaMemcpyAsync(&ends[1], t_eval + (m - 1), sizeof(double), cudaMemcpyDeviceToHost, st));
     HB_CUDA_TRY(cudaStreamSynchronize(st));
     HB_CUDA_TRY(cudaMemsetAsync(cand_count, 0, sizeof(int) * 2 * (size_t)n, st));
-    HB_CUDA_TRY(cudaMemsetAsync(desc_total, 0, sizeof(int), st));
+    HB_CUDA_TRY(cudaMemsetAsync(desc_total, 0, 2 * sizeof(int), st));
     mark(0, st);
     int rc = hb_cr3bp_record_launch(sys, integ, sec->idx, n, y0_soa, ends[0], ends[1], rec, rec_cap, yf_soa, n_acc, n_rej,
                                     status, workspace, st);
