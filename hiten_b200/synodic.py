@@ -193,6 +193,7 @@ class TubeSectionRunner:
         self._extra = None          # (indices, SectionHits) of the trajectories rerun with the fused kernel
         if self.steps_capacity > 0:
             nbytes = int(self.lib.hb_section2_scratch_bytes(self.n, self.steps_capacity))
+            self._owns_scratch = scratch is None
             if scratch is not None:
                 if scratch.numel() * scratch.element_size() < nbytes or scratch.device != self.device:
                     raise ValueError("scratch tensor too small or on another device")
@@ -228,6 +229,7 @@ class TubeSectionRunner:
             self._extra = (None, None)
             return
         idx = torch.nonzero(self.status[: self.n] == L.HB_TRAJ_RECORD_OVERFLOW).flatten()
+        self._grow_scratch(int(nt.value))
         sub = TubeSectionRunner(idx.numel(), self.mu, self.te, self.section, forward=self.forward, flip=self.flip,
                                 integ=self.integ, device=self.device)
         y0 = self._y0.view(6, self.n)[:, idx].contiguous()
@@ -238,6 +240,25 @@ class TubeSectionRunner:
             sub.status[: idx.numel()]
         self.per[idx] = sub.per[: idx.numel()]
         self._extra = (idx.cpu().numpy(), h)
+
+    def _grow_scratch(self, n_overflowed):
+        """More than 2 % of the batch did not fit: size the scratch for the longest trajectory seen (the propagation
+        kernel keeps counting steps past the capacity), if this runner owns its scratch and the memory is there --
+        the NEXT launch then runs without reruns."""
+        if not getattr(self, "_owns_scratch", False) or n_overflowed * 50 < self.n:
+            return
+        need = (int(self.nacc[: self.n].max().item()) + 31) // 32 * 32
+        if need <= self.steps_capacity:
+            return                                            # candidate-list overflow, not a step overflow
+        nbytes = int(self.lib.hb_section2_scratch_bytes(self.n, need))
+        have = self.scratch.numel() * 8
+        free, _ = torch.cuda.mem_get_info(self.device)
+        if nbytes > 0.8 * (free + have):
+            return
+        self.scratch = None
+        torch.cuda.empty_cache()
+        self.scratch = torch.empty(nbytes // 8, dtype=torch.float64, device=self.device)
+        self.steps_capacity = need
 
     def hit_count(self, stream=None):
         nh, no = L.C.c_int64(0), L.C.c_int64(0)

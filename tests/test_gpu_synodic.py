@@ -230,3 +230,7 @@ def test_pipeline_equals_fused_on_a_bench_sized_slice_with_overflow_rerun():
     assert np.array_equal(ha.times, hb_.times) and np.array_equal(ha.states, hb_.states)
     assert np.array_equal(ha.hits_per_traj, hb_.hits_per_traj)
     assert torch.equal(a.yf, b.yf) and torch.equal(a.nacc, b.nacc) and torch.equal(a.nrej, b.nrej)
+    # the runner has sized its scratch for the longest trajectory: the next launch needs no rerun
+    assert b.steps_capacity >= int(a.nacc.max().item()) > 96
+    b.launch(y0)
+    assert b.hit_count() == a.hit_count() and (b.status == 0).all().item() and b._extra == (None, None)
