@@ -260,3 +260,27 @@ def connections(pu, ps, Xu, Xs, eps, dv_tol, bal_tol):
     assert 0 <= k <= cap
     return dict(kind=kind[:k], dv=dv[:k], pt=pt[:k], su=su[:k], ss=ss[:k], iu=iu[:k], is_=is_[:k],
                 pairs_considered=int(considered.value))
+
+
+def manifold_ics(phi_dense, tt, period, eigvec_re, direction, fractions, displacements):
+    """ho_manifold_ics: x0W[D*K, 6] (displacement-major) and the STM sample index of every fraction."""
+    phi = np.ascontiguousarray(phi_dense, dtype=np.float64)
+    tt = np.ascontiguousarray(tt, dtype=np.float64)
+    ev = np.ascontiguousarray(eigvec_re, dtype=np.float64)
+    fr = np.ascontiguousarray(np.atleast_1d(fractions), dtype=np.float64)
+    dd = np.ascontiguousarray(np.atleast_1d(displacements), dtype=np.float64)
+    out = np.empty((dd.size * fr.size, 6))
+    idx = np.empty(fr.size, dtype=np.int64)
+    lib().ho_manifold_ics(_p(phi), _p(tt), C.c_int64(tt.size), C.c_double(period), _p(ev), C.c_int(int(direction)),
+                          _p(fr), C.c_int64(fr.size), _p(dd), C.c_int64(dd.size), _p(out),
+                          idx.ctypes.data_as(ip))
+    return out, idx
+
+
+def tube_filter(states, mu):
+    """ho_batch_tube_filter on states[n][m][6]: (min r1, min r2, max relative Jacobi error) per trajectory."""
+    s = np.ascontiguousarray(states, dtype=np.float64)
+    n, m = s.shape[0], s.shape[1]
+    out = np.empty((n, 3))
+    lib().ho_batch_tube_filter(_p(s), C.c_int64(n), C.c_int(m), C.c_double(mu), _p(out))
+    return out
