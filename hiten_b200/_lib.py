@@ -59,6 +59,10 @@ class HbCmLiftOpts(C.Structure):
                 ("max_expand", C.c_int32), ("symmetric", C.c_int32), ("section", C.c_int32), ("max_iter", C.c_int32)]
 
 
+class HbTubeFilterOpts(C.Structure):
+    _fields_ = [("mu", C.c_double), ("safe_r1", C.c_double), ("safe_r2", C.c_double), ("energy_tol", C.c_double)]
+
+
 class HitenB200Error(RuntimeError):
     pass
 
@@ -95,6 +99,9 @@ SIGNATURES = {
     "hb_cm_poincare_map_jit": (C.c_int, [C.POINTER(HbPolyHam), C.POINTER(HbCmOpts), C.c_int64, vp, vp, vp, vp, vp, vp]),
     "hb_cm_jit_compile_host": (C.c_int, [vp, C.POINTER(C.c_int64), C.c_int32, C.POINTER(HbCmOpts), C.POINTER(C.c_int64),
                                          C.c_char_p, C.c_int64]),
+    "hb_manifold_ics": (C.c_int, [vp, vp, C.c_int32, C.c_double, vp, C.c_int32, vp, C.c_int64, vp, C.c_int64, vp, vp,
+                                  vp]),
+    "hb_tube_filter": (C.c_int, [C.POINTER(HbTubeFilterOpts), C.c_int64, vp, C.c_int32, vp, vp, vp]),
     "hb_synodic_detect": (C.c_int, [C.POINTER(HbSection), C.c_int64, vp, vp, vp, C.c_int32, C.c_int32, vp, C.c_int64,
                                     vp, vp, vp]),
     "hb_read_hit_count": (C.c_int, [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), vp]),

@@ -26,6 +26,7 @@ import numpy as np
 
 from . import centermanifold as _cm
 from . import connections as _conn
+from . import manifold as _man
 from . import propagate as _prop
 from . import synodic as _syn
 
@@ -138,6 +139,11 @@ def _gpu_integrate(dim, mu, fwd, flip, y0, t_vals, integ, event=None):
     return t_vals.copy(), res.states[0]
 
 
+def _host(a):
+    """Device tensor -> numpy (one D2H copy); numpy stays numpy."""
+    return a.cpu().numpy() if hasattr(a, "cpu") else np.asarray(a)
+
+
 def _raise_on_status(status):
     bad = np.nonzero(np.asarray(status) > 1)[0]
     if bad.size:
@@ -239,7 +245,6 @@ def _make_run_compute(orig):
             return orig(self, step=step, integration_fraction=integration_fraction, NN=NN,
                         displacement=displacement, method=method, order=order, dt=dt, energy_tol=energy_tol,
                         safe_distance=safe_distance, show_progress=show_progress)
-        from hiten.algorithms.common.energy import _max_rel_energy_error
         orbit = self.orbit
         mu, forward = self.mu, self.forward
         dist_m = self.system.distance * 1e3                                 # manifold.py:341-345 (kept as is)
@@ -255,35 +260,35 @@ def _make_run_compute(orig):
             raise ValueError(f"Requested {label} eigenvector {NN} not available. "
                              f"Only {vecs.shape[1]} real {label} eigenvectors found.")
         eigvec = vecs[:, col_idx]
-        fractions = tuple(np.arange(0.0, 1.0, step))
-        xx, tt, _, PHI = self.compute_stm(steps=2000)
-        x0W = np.stack([self._compute_manifold_section(period=orbit.period, fraction=f, displacement=displacement,
-                                                       xx=xx, tt=tt, PHI=PHI, eigvec=eigvec).astype(np.float64)
-                        for f in fractions]) if fractions else np.empty((0, 6))
+        fractions = np.arange(0.0, 1.0, step)
+        ysos, dysos, states_list, times_list = [], [], [], []
+        attempts = len(fractions)
+        if attempts == 0:
+            return (ysos, dysos, states_list, times_list, 0, 0)
+        if np.any(np.asarray(eigvec).imag != 0.0):
+            # MAN.real of a genuinely complex eigenvector: not the device path's contract -> the reference's loop
+            return orig(self, step=step, integration_fraction=integration_fraction, NN=NN,
+                        displacement=displacement, method=method, order=order, dt=dt, energy_tol=energy_tol,
+                        safe_distance=safe_distance, show_progress=show_progress)
+        _, tt, _, PHI = self.compute_stm(steps=2000)
         tf = integration_fraction * 2 * np.pi
         steps = max(int(abs(tf) / dt) + 1, 100)
         t_eval = np.linspace(0.0, tf, steps)
-        ysos, dysos, states_list, times_list = [], [], [], []
-        successes, attempts = 0, len(fractions)
-        if attempts == 0:
-            return (ysos, dysos, states_list, times_list, 0, 0)
-        # the batch axis: every fraction in ONE launch (replaces the loop at manifold.py:381-440)
-        res = _prop.cr3bp_dense(x0W, mu, t_eval, forward=forward, flip=(0, 6), integ=_integ())
+        # the batch axis: initial conditions of every fraction (manifold.py:470-537), ONE dense propagation
+        # (replaces the loop at manifold.py:381-440) and the two filters (manifold.py:412-432), all in HBM;
+        # only the tubes that pass come back to the host
+        x0W, _ = _man.tube_initial_conditions(PHI, tt, orbit.period, eigvec, self.direction, fractions,
+                                              [displacement])
+        res = _prop.cr3bp_dense(x0W, mu, t_eval, forward=forward, flip=(0, 6), integ=_integ(), keep_on_device=True)
+        _, keep = _man.tube_filter(res.states, mu, safe_r1=safe_r1, safe_r2=safe_r2, energy_tol=energy_tol)
+        keep = _host(keep).astype(bool) & (_host(res.status) == 0)         # "discard and continue", manifold.py:438-440
+        sel = np.nonzero(keep)[0]
         times = forward * t_eval
-        for i in range(attempts):
-            if int(res.status[i]) != 0:
-                continue                                                    # "discard and continue", manifold.py:438-440
-            states = res.states[i]
-            x, y, z = states[:, 0], states[:, 1], states[:, 2]
-            r1 = np.sqrt((x + mu) ** 2 + y ** 2 + z ** 2)
-            r2 = np.sqrt((x - 1 + mu) ** 2 + y ** 2 + z ** 2)
-            if (r1.min() < safe_r1) or (r2.min() < safe_r2):
-                continue
-            if _max_rel_energy_error(states, mu) > energy_tol:
-                continue
-            states_list.append(states)
-            times_list.append(times.copy())
-            successes += 1
+        if sel.size:
+            kept = _host(res.states[sel] if sel.size < attempts else res.states)
+            states_list = [kept[i] for i in range(sel.size)]
+            times_list = [times.copy() for _ in range(sel.size)]
+        successes = int(sel.size)
         return (ysos, dysos, states_list, times_list, successes, attempts)
 
     _run_compute.__wrapped__ = orig

@@ -292,6 +292,34 @@ int hb_connections(const double *pu, int64_t n_u, const double *ps, int64_t n_s,
                    double eps, double dv_tol, double bal_tol, hb_connection *out, int64_t capacity, int64_t *n_out,
                    int64_t *n_dropped, int64_t *pairs_considered, void *scratch, int64_t scratch_bytes, void *stream);
 
+/* Manifold-tube initial conditions on the device: replaces the per-fraction host work of
+ * _ManifoldDynamicsService._compute_manifold_section + _totime (algorithms/types/services/manifold.py:470-573) for a
+ * whole tube.  phi_dense[n_samples][42] is the reference's PHI array of the orbit (row k = [Phi row-major, x] at
+ * tt[k]), exactly what hb_cr3bp_stm_dense writes; tt[n_samples] its (signed) sample times; eigvec[6] the real part of
+ * the chosen eigenvector; direction = +1 / -1 (manifold branch).  For every fraction f the sample index is the first
+ * minimum of |f*period - |tt[k]||; for every (fraction k, displacement j) the initial condition
+ *     x0W = x_k + (displacement_j / |MAN[0:3]|) * MAN,   MAN = direction * Phi_k @ eigvec,  tiny z / vz zeroed
+ * goes to trajectory i = j*n_fractions + k of the SoA array x0w_soa[6][n_fractions*n_displacements] that the
+ * propagation entry points read.  node_idx[n_fractions] (device, required) receives the sample indices.
+ * All pointers are device pointers.  Bit-identical to the reference (incl. its BLAS accumulation order).      */
+int hb_manifold_ics(const double *phi_dense, const double *tt, int32_t n_samples, double period,
+                    const double *eigvec, int32_t direction, const double *fractions, int64_t n_fractions,
+                    const double *displacements, int64_t n_displacements, double *x0w_soa, int32_t *node_idx,
+                    void *stream);
+
+/* Trajectory filters of Manifold.compute() on stored tubes: replaces the numpy safe-radius test of
+ * _run_compute (algorithms/types/services/manifold.py:412-424) and _max_rel_energy_error
+ * (algorithms/common/energy.py:27-76).  states is hb_cr3bp_dense's output [n][m][6]; out[i] = {min_k r1, min_k r2,
+ * max_k |C_k - C_0| / |C_0|} (absolute drift when |C_0| <= 1e-14), NaN samples propagate into the minima like
+ * np.min; keep[i] (optional) = 1 unless min r1 < safe_r1, min r2 < safe_r2 or the drift exceeds energy_tol.     */
+typedef struct {
+    double mu;
+    double safe_r1, safe_r2;   /* safe_distance * body radius / (distance * 1e3), manifold.py:341-345 */
+    double energy_tol;
+} hb_tube_filter_opts;
+int hb_tube_filter(const hb_tube_filter_opts *opts, int64_t n, const double *states, int32_t m, double *out,
+                   int32_t *keep, void *stream);
+
 /* Synodic-section crossing detection on precomputed trajectories (linear branch, the one the
  * reference's defaults select): replaces _SynodicDetectionBackend.run / detect_on_trajectory /
  * _detect_with_segment_refine / _order_and_dedup_hits (algorithms/poincare/synodic/backend.py:

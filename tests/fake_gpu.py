@@ -86,7 +86,21 @@ def find_connections(points_u, points_s, states_u, states_s, eps, dv_tol, bal_to
     return Connections(r["kind"], r["dv"], r["pt"], r["su"], r["ss"], r["iu"], r["is_"], tu, ts, r["pairs_considered"])
 
 
+def tube_initial_conditions(phi_dense, tt, period, eigvec, direction, fractions, displacements, **kw):
+    x0, idx = O.manifold_ics(phi_dense, tt, period, np.asarray(eigvec).real, direction, fractions, displacements)
+    return x0, idx.astype(np.int32)       # host [N, 6]: what the fake cr3bp_dense takes
+
+
+def tube_filter(states, mu, *, safe_r1=0.0, safe_r2=0.0, energy_tol=np.inf, **kw):
+    out = O.tube_filter(states, mu)
+    keep = ~((out[:, 0] < safe_r1) | (out[:, 1] < safe_r2)) & ~(out[:, 2] > energy_tol)
+    return out, keep.astype(np.int32)
+
+
 def patch(monkeypatch):
+    import hiten_b200.manifold as man
+    monkeypatch.setattr(man, "tube_initial_conditions", tube_initial_conditions)
+    monkeypatch.setattr(man, "tube_filter", tube_filter)
     import hiten_b200.centermanifold as cm
     import hiten_b200.propagate as prop
     import hiten_b200.synodic as syn

@@ -96,3 +96,11 @@ def test_argument_validation_needs_no_gpu():
     assert lib.hb_cr3bp_section2(C.byref(sysd), C.byref(integ), C.byref(sec), 8, None, None, 1, None, 0, None, None, None,
                                  None, None, None, 0, None, None) < 0             # m < 2, no workspace
     assert lib.hb_read_record_overflow(None, None, None) < 0
+    # manifold-tube entry points (8f#3)
+    assert lib.hb_manifold_ics(None, None, 2000, 2.75, None, 1, None, 0, None, 5, None, None, None) == 0   # empty tube
+    assert lib.hb_manifold_ics(None, None, 2000, 2.75, None, 1, None, 4, None, 5, None, None, None) < 0    # null arrays
+    assert lib.hb_manifold_ics(None, None, 2000, 2.75, None, 0, None, 0, None, 0, None, None, None) < 0    # direction 0
+    fo = _lib.HbTubeFilterOpts(0.0121, 0.0, 0.0, 1e-6)
+    assert lib.hb_tube_filter(C.byref(fo), 0, None, 10, None, None, None) == 0
+    assert lib.hb_tube_filter(C.byref(fo), 3, None, 10, None, None, None) < 0
+    assert lib.hb_tube_filter(C.byref(fo), 3, None, 0, None, None, None) < 0
