@@ -63,6 +63,14 @@ class HbTubeFilterOpts(C.Structure):
     _fields_ = [("mu", C.c_double), ("safe_r1", C.c_double), ("safe_r2", C.c_double), ("energy_tol", C.c_double)]
 
 
+class HbCorrectOpts(C.Structure):
+    _fields_ = [("ctrl", C.c_int32 * 2), ("res", C.c_int32 * 2), ("target", C.c_double * 2), ("event_idx", C.c_int32),
+                ("halo_quadratic", C.c_int32), ("event_offset", C.c_double), ("finite_difference", C.c_int32),
+                ("line_search", C.c_int32), ("tol", C.c_double), ("max_delta", C.c_double), ("fd_step", C.c_double),
+                ("alpha_reduction", C.c_double), ("min_alpha", C.c_double), ("armijo_c", C.c_double),
+                ("max_attempts", C.c_int32), ("_pad", C.c_int32)]
+
+
 class HitenB200Error(RuntimeError):
     pass
 
@@ -102,6 +110,9 @@ SIGNATURES = {
     "hb_manifold_ics": (C.c_int, [vp, vp, C.c_int32, C.c_double, vp, C.c_int32, vp, C.c_int64, vp, C.c_int64, vp, vp,
                                   vp]),
     "hb_tube_filter": (C.c_int, [C.POINTER(HbTubeFilterOpts), C.c_int64, vp, C.c_int32, vp, vp, vp]),
+    "hb_correct_scratch_bytes": (C.c_int64, [C.c_int64]),
+    "hb_correct_orbits": (C.c_int, [C.POINTER(HbCr3bp), C.POINTER(HbInteg), C.POINTER(HbCorrectOpts), C.c_int64, vp, vp,
+                                    vp, vp, vp, vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), vp, C.c_int64, vp, vp]),
     "hb_synodic_detect": (C.c_int, [C.POINTER(HbSection), C.c_int64, vp, vp, vp, C.c_int32, C.c_int32, vp, C.c_int64,
                                     vp, vp, vp]),
     "hb_read_hit_count": (C.c_int, [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), vp]),

@@ -320,6 +320,52 @@ typedef struct {
 int hb_tube_filter(const hb_tube_filter_opts *opts, int64_t n, const double *states, int32_t m, double *out,
                    int32_t *keep, void *stream);
 
+/* Batched single-shooting differential correction of periodic orbits: n independent Newton problems
+ * advanced in lock-step.  Replaces, per orbit, _NewtonBackend.run (algorithms/corrector/backends/newton.py:20-150)
+ * with the residual / Jacobian of _SingleShootingOrbitOperators (algorithms/corrector/operators.py:319-452): the
+ * residual is the state at the first crossing of the plane y[event_idx] = event_offset found by
+ * _SingleHitBackend._cross (algorithms/poincare/singlehit/backend.py:164-282: window [0, pi] after a 1e-12 alignment
+ * step, fallback window [pi/2 - 0.15, + pi]) restricted to res[] minus target[]; the Jacobian is the res x ctrl block
+ * of the STM at the event time (minus _halo_quadratic_term, algorithms/types/services/orbits.py:917-946, when
+ * halo_quadratic != 0) or central differences (finite_difference != 0, backends/base.py); the update is
+ * _solve_delta_dense (cond > 1e8 -> ridge 1e-12) followed by the inf-norm cap max_delta and either the Armijo
+ * back-tracking search (algorithms/corrector/stepping/armijo.py:60-170) or the plain step (stepping/plain.py).
+ * Two controls and two residuals (every shipped family: halo, Lyapunov, vertical).  sys->fwd must be +1 and
+ * integ->method HB_DOP853 (the shipped configs); integ supplies rtol / atol / arithmetic variant.
+ * x0_soa / xc_soa are [6][n] SoA device arrays (initial guesses in, corrected initial states out); half_period[n] is
+ * the event time of the corrected state (NaN unless converged); iterations[n], residual_norm[n] (inf-norm) and
+ * status[n] (HB_CORR_*) mirror CorrectorOutput / the reference's exceptions.  rk_steps6 / rk_steps42 (optional HOST
+ * outputs) receive the attempted 6-state and 42-state DOP853 steps of the whole call.  scratch: device block of
+ * hb_correct_scratch_bytes(n) bytes.  The call synchronises `stream` (it reads the number of orbits still active
+ * between launches -- 4 bytes -- and nothing else).
+ * Event propagation is the bit-exact path; the STM and the 2x2 solve are tolerance-level (see hb_cr3bp_stm), so
+ * corrected states agree with the reference at Newton-convergence level (<= 1e-10) and iteration counts to within
+ * one (the reference's |R| < 1e-12 test sits on the 1e-12 noise floor of its own event solver).                 */
+#define HB_CORR_CONVERGED 0
+#define HB_CORR_MAX_ATTEMPTS 1   /* ConvergenceError: not converged after max_attempts                      */
+#define HB_CORR_STEP_FAILED 2    /* ConvergenceError: step strategy found no productive step                */
+#define HB_CORR_NO_EVENT 3       /* no plane crossing for the current iterate (the reference raises)        */
+#define HB_CORR_SINGULAR 4       /* singular Jacobian / failed STM propagation                              */
+typedef struct {
+    int32_t ctrl[2], res[2];     /* OrbitCorrectionConfig.control_indices / residual_indices               */
+    double target[2];
+    int32_t event_idx;           /* _plane_crossing_factory coordinate                                     */
+    int32_t halo_quadratic;      /* extra_jacobian = _halo_quadratic_term                                  */
+    double event_offset;
+    int32_t finite_difference;   /* NumericalConfig.finite_difference                                      */
+    int32_t line_search;         /* NumericalConfig.line_search_enabled                                    */
+    double tol, max_delta;       /* ConvergenceOptions (max_delta = inf: no cap)                           */
+    double fd_step;              /* NumericalOptions                                                       */
+    double alpha_reduction, min_alpha, armijo_c;
+    int32_t max_attempts;
+    int32_t _pad;
+} hb_correct_opts;
+int64_t hb_correct_scratch_bytes(int64_t n);
+int hb_correct_orbits(const hb_cr3bp *sys, const hb_integ *integ, const hb_correct_opts *opts, int64_t n,
+                      const double *x0_soa, double *xc_soa, double *half_period, int32_t *iterations,
+                      double *residual_norm, int32_t *status, int64_t *rk_steps6, int64_t *rk_steps42,
+                      void *scratch, int64_t scratch_bytes, void *workspace, void *stream);
+
 /* Synodic-section crossing detection on precomputed trajectories (linear branch, the one the
  * reference's defaults select): replaces _SynodicDetectionBackend.run / detect_on_trajectory /
  * _detect_with_segment_refine / _order_and_dedup_hits (algorithms/poincare/synodic/backend.py:

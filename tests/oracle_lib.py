@@ -284,3 +284,39 @@ def tube_filter(states, mu):
     out = np.empty((n, 3))
     lib().ho_batch_tube_filter(_p(s), C.c_int64(n), C.c_int(m), C.c_double(mu), _p(out))
     return out
+
+
+class HoCorrectOpts(C.Structure):
+    _fields_ = [("ctrl", C.c_int * 2), ("res", C.c_int * 2), ("target", C.c_double * 2), ("event_idx", C.c_int),
+                ("event_offset", C.c_double), ("halo_quadratic", C.c_int), ("finite_difference", C.c_int),
+                ("tol", C.c_double), ("max_attempts", C.c_int), ("max_delta", C.c_double), ("fd_step", C.c_double),
+                ("line_search", C.c_int), ("alpha_reduction", C.c_double), ("min_alpha", C.c_double),
+                ("armijo_c", C.c_double)]
+
+
+# family -> (control indices, residual indices, event index, halo quadratic term, finite differences)
+# (algorithms/types/services/orbits.py:862-880, 1249-1262, 1440-1453)
+CORRECTION_FAMILIES = {"halo": ((0, 4), (3, 5), 1, 1, 0), "lyapunov": ((4, 5), (3, 2), 1, 0, 0),
+                       "vertical": ((5, 4), (3, 1), 2, 0, 1)}
+
+
+def correct_opts(family, tol=1e-12, max_attempts=50, max_delta=1e-2, fd_step=1e-8, line_search=True,
+                 alpha_reduction=0.5, min_alpha=1e-4, armijo_c=0.1):
+    ctrl, res, ev, quad, fd = CORRECTION_FAMILIES[family]
+    return HoCorrectOpts((C.c_int * 2)(*ctrl), (C.c_int * 2)(*res), (C.c_double * 2)(0.0, 0.0), ev, 0.0, quad, fd,
+                         tol, max_attempts, max_delta, fd_step, int(line_search), alpha_reduction, min_alpha,
+                         armijo_c)
+
+
+def correct_orbits(x0, mu, opts):
+    """ho_correct_orbit over rows of x0[N,6]: (x_corrected, half_period, iterations, residual_norm, status)."""
+    x0 = np.ascontiguousarray(np.atleast_2d(x0), dtype=np.float64)
+    n = len(x0)
+    xc, hp, it, rn, st = np.empty((n, 6)), np.empty(n), np.zeros(n, np.int32), np.empty(n), np.zeros(n, np.int32)
+    f = lib().ho_correct_orbit
+    f.restype = C.c_int
+    for i in range(n):
+        xo, h, k, r = np.empty(6), C.c_double(), C.c_int(), C.c_double()
+        st[i] = f(C.c_double(mu), C.byref(opts), _p(x0[i]), _p(xo), C.byref(h), C.byref(k), C.byref(r))
+        xc[i], hp[i], it[i], rn[i] = xo, h.value, k.value, r.value
+    return xc, hp, it, rn, st

@@ -104,3 +104,20 @@ def test_argument_validation_needs_no_gpu():
     assert lib.hb_tube_filter(C.byref(fo), 0, None, 10, None, None, None) == 0
     assert lib.hb_tube_filter(C.byref(fo), 3, None, 10, None, None, None) < 0
     assert lib.hb_tube_filter(C.byref(fo), 3, None, 0, None, None, None) < 0
+    # batched corrector (8f#4)
+    from hiten_b200 import corrector
+    assert lib.hb_correct_scratch_bytes(1000) > 1000 * 8 * 100 and lib.hb_correct_scratch_bytes(-1) < 0
+    co = corrector.make_opts("halo")
+    s6 = i64(5)
+    assert lib.hb_correct_orbits(C.byref(sysd), C.byref(integ), C.byref(co), 0, None, None, None, None, None, None,
+                                 C.byref(s6), None, None, 0, (C.c_char * 256)(), None) == 0 and s6.value == 0
+    assert lib.hb_correct_orbits(C.byref(sysd), C.byref(integ), C.byref(co), 4, None, None, None, None, None, None,
+                                 None, None, None, 0, (C.c_char * 256)(), None) < 0            # null arrays
+    back = _lib.HbCr3bp(0.0121, -1, -1, -1, 0)
+    assert lib.hb_correct_orbits(C.byref(back), C.byref(integ), C.byref(co), 0, None, None, None, None, None, None,
+                                 None, None, None, 0, (C.c_char * 256)(), None) == -2          # backward: unsupported
+    bad = corrector.make_opts("halo", control_indices=(0, 0))
+    assert lib.hb_correct_orbits(C.byref(sysd), C.byref(integ), C.byref(bad), 0, None, None, None, None, None, None,
+                                 None, None, None, 0, (C.c_char * 256)(), None) == -1
+    with pytest.raises(ValueError):
+        corrector.make_opts(control_indices=(0, 4, 5), residual_indices=(3, 5), event_idx=1)
