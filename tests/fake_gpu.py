@@ -97,7 +97,19 @@ def tube_filter(states, mu, *, safe_r1=0.0, safe_r2=0.0, energy_tol=np.inf, **kw
     return out, keep.astype(np.int32)
 
 
+def correct_orbits(x0, mu, opts, **kw):
+    from hiten_b200.corrector import CorrectionBatch
+    o = O.HoCorrectOpts((O.C.c_int * 2)(*opts.ctrl), (O.C.c_int * 2)(*opts.res), (O.C.c_double * 2)(*opts.target),
+                        opts.event_idx, opts.event_offset, opts.halo_quadratic, opts.finite_difference, opts.tol,
+                        opts.max_attempts, opts.max_delta, opts.fd_step, opts.line_search, opts.alpha_reduction,
+                        opts.min_alpha, opts.armijo_c)
+    xc, half, it, rn, st = O.correct_orbits(x0, mu, o)
+    return CorrectionBatch(xc, half, it, rn, st, 0, 0)
+
+
 def patch(monkeypatch):
+    import hiten_b200.corrector as corr
+    monkeypatch.setattr(corr, "correct_orbits", correct_orbits)
     import hiten_b200.manifold as man
     monkeypatch.setattr(man, "tube_initial_conditions", tube_initial_conditions)
     monkeypatch.setattr(man, "tube_filter", tube_filter)

@@ -164,3 +164,25 @@ def test_connections_backend_through_the_drop_in(ref, monkeypatch):
         assert (a.kind, a.delta_v, a.point2d, a.index_u, a.index_s, a.trajectory_index_u, a.trajectory_index_s) == \
                (b.kind, b.delta_v, b.point2d, b.index_u, b.index_s, b.trajectory_index_u, b.trajectory_index_s)
         assert np.array_equal(a.state_u, b.state_u) and np.array_equal(a.state_s, b.state_s)
+
+
+def test_correct_many_applies_results_like_the_reference(ref, monkeypatch):
+    """corrector.correct_many on reference orbit objects: options read from each orbit's own correction config,
+    one batch per configuration, results applied through the orbit's correction service."""
+    import fake_gpu
+    from hiten_b200 import corrector
+    system, l1, _ = ref
+    fake_gpu.patch(monkeypatch)
+    mk = lambda: [l1.create_orbit("halo", amplitude_z=az, zenith="southern") for az in (0.1, 0.25)] + \
+        [l1.create_orbit("lyapunov", amplitude_x=0.02)]
+    a, b = mk(), mk()
+    op = corrector.opts_from_reference(a[0])
+    assert tuple(op.ctrl) == (0, 4) and tuple(op.res) == (3, 5) and op.event_idx == 1 and op.halo_quadratic == 1
+    assert corrector.opts_from_reference(a[2]).halo_quadratic == 0
+    ref_res = [o.correct() for o in a]
+    res = corrector.correct_many(b)
+    for o_ref, o_new, r_ref, r_new in zip(a, b, ref_res, res):
+        assert np.abs(np.asarray(o_new.initial_state) - np.asarray(o_ref.initial_state)).max() <= 1e-10
+        assert abs(o_new.period - o_ref.period) <= 1e-10
+        assert r_new.converged and abs(r_new.iterations - r_ref.iterations) <= 1
+        assert abs(r_new.half_period - r_ref.half_period) <= 1e-10
