@@ -262,6 +262,59 @@ def secondary_configs(hb, torch, steps, flush, barrier):
                                          "note": "wall time incl. result D2H and ordering; the reference's pairing is an "
                                                  "O(N*M) = 4e12 double loop plus Python dicts"}
     del dd
+    # tube initial conditions from a dense STM (2000 nodes x 500 displacements) and the two trajectory
+    # filters on stored tubes (16384 x 4713 samples = 3.7 GB read once: HBM-bound)
+    from hiten_b200 import manifold as mf
+    gm = np.load(os.path.join(REPO, "tests", "golden", "manifold_ics.npz"))
+    phi = np.zeros((gm["sp_tt"].size, 42))
+    phi[gm["sp_rows"]] = gm["sp_phi_rows"]
+    dphi, dtt = torch.from_numpy(phi).cuda(), torch.from_numpy(gm["sp_tt"]).cuda()
+    dfr = torch.from_numpy(gm["fractions"][np.arange(2000) % gm["fractions"].size]).cuda()
+    ddisp = torch.from_numpy(np.logspace(-7, -5, 500)).cuda()
+
+    def run_ics():
+        hold["ics"] = mf.tube_initial_conditions(dphi, dtt, float(gm["period"]), gm["sp_eigvec"], 1, dfr, ddisp)
+
+    for _ in range(3):
+        run_ics()
+    t = time_steps(run_ics, steps, flush, barrier, torch)
+    out["manifold_ics_1e6"] = {"ms": 1e3 * t / steps, "ics_per_s": 1e6 * steps / t}
+    tube = torch.randn((16384, 4713, 6), dtype=torch.float64, device="cuda")
+
+    def run_filter():
+        hold["flt"] = mf.tube_filter(tube, float(gm["mu"]), safe_r1=3.3e-5, safe_r2=9e-6, energy_tol=1e-6)
+
+    for _ in range(3):
+        run_filter()
+    t = time_steps(run_filter, steps, flush, barrier, torch)
+    gbs = tube.numel() * 8 * steps / t / 1e9
+    out["tube_filter_16384x4713"] = {"ms": 1e3 * t / steps, "hbm_read_gbs": gbs, "samples_per_s": 16384 * 4713 * steps / t,
+                                     "note": "algorithmic bytes = 48 B per sample, read once"}
+    del tube
+    hold.pop("flt", None)
+    # batched differential correction, 1e5 perturbed halo guesses in one lock-step batch
+    from hiten_b200 import corrector as cr
+    gc = np.load(os.path.join(REPO, "tests", "golden", "correction.npz"))
+    for fam, nb in (("halo", 100_000), ("lyapunov", 100_000)):
+        base = gc[f"{fam}_x0"][gc[f"{fam}_iters"] >= 0]
+        xg = base[rng.integers(0, len(base), nb)].copy()
+        xg[:, cr.FAMILIES[fam][0]] += 1e-4 * rng.standard_normal((nb, 2))
+        xgd = torch.from_numpy(np.ascontiguousarray(xg.T)).cuda()
+        copts = cr.make_opts(fam)
+        best = 1e9
+        for _ in range(3):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            rcorr = cr.correct_orbits(xgd, float(gc["mu"]), copts)
+            torch.cuda.synchronize()
+            best = min(best, time.perf_counter() - t0)
+        out[f"correct_{fam}_1e5_orbits"] = {
+            "ms": 1e3 * best, "orbits_per_s": nb / best, "converged_fraction": float((rcorr.status == 0).float().mean().item()),
+            "mean_newton_iterations": float(rcorr.iterations.float().mean().item()),
+            "rk_steps_per_s": (rcorr.rk_steps6 + rcorr.rk_steps42) / best,
+            "note": "wall time of the whole Newton + Armijo loop (every event / STM propagation, solve and line-search "
+                    "decision on the GPU; the host reads 4 bytes between launches)"}
+    del xgd
     s = np.load(os.path.join(REPO, "tests", "golden", "stm_family.npz"))
     x0 = torch.from_numpy(np.ascontiguousarray(np.tile(s["x0"], (128, 1)).T)).cuda()
     T = torch.from_numpy(np.tile(s["period"], 128)).cuda()

@@ -113,6 +113,8 @@ SIGNATURES = {
     "hb_correct_scratch_bytes": (C.c_int64, [C.c_int64]),
     "hb_correct_orbits": (C.c_int, [C.POINTER(HbCr3bp), C.POINTER(HbInteg), C.POINTER(HbCorrectOpts), C.c_int64, vp, vp,
                                     vp, vp, vp, vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), vp, C.c_int64, vp, vp]),
+    "hb_section2_filter": (C.c_int, [C.POINTER(HbCr3bp), C.POINTER(HbInteg), C.POINTER(HbTubeFilterOpts), C.c_int64, vp,
+                                     C.c_int32, vp, vp, vp, C.c_int64, vp, vp, vp]),
     "hb_synodic_detect": (C.c_int, [C.POINTER(HbSection), C.c_int64, vp, vp, vp, C.c_int32, C.c_int32, vp, C.c_int64,
                                     vp, vp, vp]),
     "hb_read_hit_count": (C.c_int, [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), vp]),

@@ -20,10 +20,7 @@
 // vector product runs through OpenBLAS zgemv (two FMA lanes over elements 0..3, mul + add tail for 4..5) and the
 // 3-element norm is an FMA-accumulated dot.  Results are bit-identical to the reference
 // (tests/golden/manifold_ics.npz, tests/test_gpu_manifold.py).
-#include <math_constants.h>
-
-#include "../../include/hiten_b200.h"
-#include "hb_common.cuh"
+#include "hb_tubefilter.cuh"
 
 namespace {
 
@@ -104,38 +101,7 @@ __global__ void __launch_bounds__(128) k_manifold_ics(const double *__restrict__
     }
 }
 
-// ---- tube filters ------------------------------------------------------------------------------------------------
-HB_DEV double jacobi_ref(const double *s, double mu1, double mu2)
-{
-    const double a = __dadd_rn(s[0], mu2), b = __dsub_rn(s[0], mu1);
-    const double yy = __dmul_rn(s[1], s[1]), zz = __dmul_rn(s[2], s[2]);
-    const double r1 = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(a, a), yy), zz));
-    const double r2 = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(b, b), yy), zz));
-    const double pot = __dmul_rn(2.0, __dadd_rn(__ddiv_rn(mu1, r1), __ddiv_rn(mu2, r2)));
-    const double kin = __dadd_rn(__dadd_rn(__dmul_rn(s[3], s[3]), __dmul_rn(s[4], s[4])), __dmul_rn(s[5], s[5]));
-    return __dsub_rn(__dadd_rn(__dadd_rn(__dmul_rn(s[0], s[0]), yy), pot), kin);
-}
-
-struct NanMin {
-    double v;
-    bool nan;
-    HB_DEV void take(double x)
-    {
-        if (x != x) nan = true;
-        else if (x < v) v = x;
-    }
-    HB_DEV void warp_reduce()
-    {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double ov = __shfl_xor_sync(0xffffffffu, v, o);
-            if (ov < v) v = ov;
-        }
-        nan = __any_sync(0xffffffffu, nan);
-    }
-    HB_DEV double result() const { return nan ? CUDART_NAN : v; }
-};
-
+// ---- tube filters (per-sample arithmetic in hb_tubefilter.cuh) ----------------------------------------------------
 __global__ void __launch_bounds__(256) k_tube_filter(const double *__restrict__ states, long long n, int m,
                                                      hb_tube_filter_opts o, double *__restrict__ out,
                                                      int *__restrict__ keep)
@@ -150,36 +116,14 @@ __global__ void __launch_bounds__(256) k_tube_filter(const double *__restrict__ 
 #pragma unroll
         for (int d = 0; d < 6; ++d) s[d] = X[d];
         const double C0 = jacobi_ref(s, mu1, mu2), absC0 = fabs(C0);
-        NanMin m1{CUDART_INF, false}, m2{CUDART_INF, false};
-        double mx = 0.0;
+        TubeFilterAcc acc;
         for (int k = lane; k < m; k += 32) {
 #pragma unroll
             for (int d = 0; d < 6; ++d) s[d] = X[(long long)k * 6 + d];
-            // manifold.py:415-416: np.sqrt((x + mu)**2 + y**2 + z**2), np.sqrt((x - 1 + mu)**2 + y**2 + z**2)
-            const double a = __dadd_rn(s[0], o.mu), b = __dadd_rn(__dsub_rn(s[0], 1.0), o.mu);
-            const double yy = __dmul_rn(s[1], s[1]), zz = __dmul_rn(s[2], s[2]);
-            m1.take(__dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(a, a), yy), zz)));
-            m2.take(__dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(b, b), yy), zz)));
-            if (k > 0) {                                     // energy.py:62-73
-                const double dC = fabs(__dsub_rn(jacobi_ref(s, mu1, mu2), C0));
-                const double rel = absC0 > 1e-14 ? __ddiv_rn(dC, absC0) : dC;
-                if (rel > mx) mx = rel;
-            }
+            acc.sample(s, k, o.mu, mu1, mu2, C0, absC0);
         }
-        m1.warp_reduce();
-        m2.warp_reduce();
-#pragma unroll
-        for (int sh = 16; sh > 0; sh >>= 1) {
-            const double ov = __shfl_xor_sync(0xffffffffu, mx, sh);
-            if (ov > mx) mx = ov;
-        }
-        if (lane == 0) {
-            const double r1 = m1.result(), r2 = m2.result();
-            out[3 * traj + 0] = r1;
-            out[3 * traj + 1] = r2;
-            out[3 * traj + 2] = mx;
-            if (keep) keep[traj] = !((r1 < o.safe_r1) || (r2 < o.safe_r2)) && !(mx > o.energy_tol);
-        }
+        acc.warp_reduce();
+        if (lane == 0) acc.store(o, traj, out, keep);
     }
 }
 

@@ -23,6 +23,7 @@
 //
 // Reference: algorithms/poincare/synodic/backend.py:458-659 (_detect_with_segment_refine), :382-455.
 #include "hb_cr3bp_common.cuh"
+#include "hb_tubefilter.cuh"
 
 extern "C" int hb_cr3bp_record_launch(const hb_cr3bp *sys, const hb_integ *integ, int32_t section_idx, int64_t n,
                                       const double *y0_soa, double t0, double tf, double *rec, int32_t rec_cap,
@@ -508,6 +509,127 @@ __global__ void __launch_bounds__(256) k_order_dedup(const ScanParams p)
     if (p.hits_per_traj) p.hits_per_traj[traj] = dd.n;
 }
 
+
+// ---- trajectory filters on the step records (hb_section2_filter) -------------------------------------------
+// Manifold.compute() drops a trajectory when it comes closer than the safe radii to a primary or when its Jacobi
+// constant drifts (manifold.py:412-432) -- judged on the 4713 dense samples, which the section pipeline never
+// stores.  This kernel evaluates exactly those samples from the step records that hb_cr3bp_section2 left in its
+// scratch: one warp per trajectory; per chunk of 32 steps a lane builds the full interpolant of its step (three extra
+// stages + 7 x 6 coefficients, dense_cache) and parks it in shared memory (51 doubles per step, odd stride:
+// conflict-free), then the warp walks the chunk's grid samples 32 at a time -- owner step by binary search over the
+// chunk's ownership bounds, six-component Horner evaluation, the reference's r1 / r2 / Jacobi expressions
+// (hb_tubefilter.cuh) -- and reduces.  Same arithmetic per sample as hb_cr3bp_dense + hb_tube_filter: same bits.
+constexpr int HB_FILT_WARPS = 4;
+constexpr int HB_FILT_ROW = 51;       // F[7][6], y_old[6], t_old, hseg, 1/hseg
+constexpr int HB_FILT_SMEM = HB_FILT_WARPS * (32 * HB_FILT_ROW * 8 + 32 * 4);
+
+struct FilterParams {
+    PropParams prop;
+    long long n;
+    const double *rec;
+    int rec_cap;
+    const int *nacc;
+    const int *status;
+    const double *t_eval;
+    int m;
+    double inv_grid_dt;
+    hb_tube_filter_opts o;
+    double *out;            // [n][3]
+    int *keep;              // [n]: 1 keep, 0 discard, -1 not judged (trajectory has no complete record set)
+};
+
+template <class AR>
+__global__ void __launch_bounds__(32 * HB_FILT_WARPS) k_record_filter(const FilterParams p)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    extern __shared__ __align__(16) unsigned char filt_smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const long long traj = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (traj >= p.n) return;                                  // whole warp
+    double *rows = (double *)filt_smem + wid * (32 * HB_FILT_ROW);
+    int *cends = (int *)((double *)filt_smem + HB_FILT_WARPS * (32 * HB_FILT_ROW)) + wid * 32;
+    const int nacc = p.nacc[traj];
+    if (p.status[traj] != HB_TRAJ_OK || nacc > p.rec_cap || nacc < 1) {
+        if (lane == 0) {
+            p.out[3 * traj] = p.out[3 * traj + 1] = p.out[3 * traj + 2] = CUDART_NAN;
+            p.keep[traj] = -1;
+        }
+        return;
+    }
+    ScanParams sp{};                                           // first_at_or_after only reads the grid fields
+    sp.t_eval = p.t_eval; sp.m = p.m; sp.inv_grid_dt = p.inv_grid_dt;
+    const double mu1 = __dsub_rn(1.0, p.o.mu), mu2 = p.o.mu;
+    const double *rec0 = p.rec + traj * (long long)p.rec_cap * HB_REC_DOUBLES;
+    double s0[6];
+#pragma unroll
+    for (int d = 0; d < 6; ++d) s0[d] = rec0[HB_REC_YOLD + d];   // sample 0 = y0
+    const double C0 = jacobi_ref(s0, mu1, mu2), absC0 = fabs(C0);
+    TubeFilterAcc acc;
+    int carry_c = 0;
+    for (int base = 0; base < nacc; base += 32) {
+        const int s = base + lane;
+        const bool have_rec = s < nacc;
+        int cend = p.m;
+        double *row = rows + lane * HB_FILT_ROW;
+        if (have_rec) {
+            double t, t_new, y[6], yn[6], k[13][6], F[7][6];
+            load_record<AR>(rec0 + (long long)s * HB_REC_DOUBLES, p.prop, t, t_new, y, yn, k);
+            const double hseg = AR::sub(t_new, t);
+            if (hseg != 0.0) {
+                const Cr3bpRhs<AR, 2> rhs{p.prop};
+                dense_cache<AR>(y, yn, hseg, k, F, rhs);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 7; ++i)
+#pragma unroll
+                    for (int d = 0; d < 6; ++d) F[i][d] = 0.0;
+            }
+#pragma unroll
+            for (int i = 0; i < 7; ++i)
+#pragma unroll
+                for (int d = 0; d < 6; ++d) row[6 * i + d] = F[i][d];
+#pragma unroll
+            for (int d = 0; d < 6; ++d) row[42 + d] = y[d];
+            row[48] = t;
+            row[49] = hseg;
+            row[50] = (hseg != 0.0) ? AR::rcp(hseg) : 0.0;
+            if (s != nacc - 1) cend = first_at_or_after(sp, t_new, 0);
+        }
+        cends[lane] = cend;
+        __syncwarp();
+        const int cb = carry_c, ce = __shfl_sync(FULL, cend, 31);
+        for (int cs = cb; cs < ce; cs += 32) {
+            const int c = cs + lane;
+            if (c < ce) {
+                int lo = 0, hi = 31;                           // first step of the chunk with cend > c owns sample c
+#pragma unroll
+                for (int it = 0; it < 5; ++it) {
+                    const int mid = (lo + hi) >> 1;
+                    if (cends[mid] > c) hi = mid; else lo = mid + 1;
+                }
+                const double *r = rows + lo * HB_FILT_ROW;
+                double F[7][6], y[6], st[6];
+#pragma unroll
+                for (int i = 0; i < 7; ++i)
+#pragma unroll
+                    for (int d = 0; d < 6; ++d) F[i][d] = r[6 * i + d];
+#pragma unroll
+                for (int d = 0; d < 6; ++d) y[d] = r[42 + d];
+                const double hseg = r[49];
+                if (hseg != 0.0) dense_eval<AR>(y, F, xpar_by<AR>(p.t_eval[c], r[48], hseg, r[50]), st);
+                else {
+#pragma unroll
+                    for (int d = 0; d < 6; ++d) st[d] = y[d];
+                }
+                acc.sample(st, c, p.o.mu, mu1, mu2, C0, absC0);
+            }
+        }
+        carry_c = ce;
+        __syncwarp();
+    }
+    acc.warp_reduce();
+    if (lane == 0) acc.store(p.o, traj, p.out, p.keep);
+}
 }  // namespace
 
 namespace {
@@ -638,5 +760,47 @@ extern "C" int hb_cr3bp_section2(const hb_cr3bp *sys, const hb_integ *integ, con
     k_order_dedup<<<(unsigned)((n + threads - 1) / threads), threads, 0, st>>>(p);
     HB_CUDA_TRY(cudaGetLastError());
     mark(4, st);
+    return HB_OK;
+}
+
+// Trajectory filters of Manifold.compute() for the trajectories of the LAST hb_cr3bp_section2 call that used this
+// scratch block (declared in include/hiten_b200.h).
+extern "C" int hb_section2_filter(const hb_cr3bp *sys, const hb_integ *integ, const hb_tube_filter_opts *opts,
+                                  int64_t n, const double *t_eval, int32_t m, const int32_t *n_acc,
+                                  const int32_t *status, const void *scratch, int64_t scratch_bytes, double *out,
+                                  int32_t *keep, void *stream)
+{
+    if (!sys || !integ || !opts || n < 0 || m < 2) return HB_ERR_BADARG;
+    if (integ->method != HB_DOP853) return HB_ERR_UNSUPPORTED;
+    if (n == 0) return HB_OK;
+    if (!t_eval || !n_acc || !status || !scratch || !out || !keep) return HB_ERR_BADARG;
+    const long long per_traj_fixed =
+        (HB_CAND_CAP * (HB_CAND_DOUBLES + HB_DESC_DOUBLES) + HB_CAND_CAP / 2 + 1) * (long long)sizeof(double);
+    long long cap = ((scratch_bytes - 256) / n - per_traj_fixed) / (HB_REC_DOUBLES * (long long)sizeof(double));
+    cap -= cap % 32;                                 // the same record capacity hb_cr3bp_section2 derived
+    if (cap < 32) return HB_ERR_BADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    double ends[2];
+    HB_CUDA_TRY(cudaMemcpyAsync(&ends[0], t_eval, sizeof(double), cudaMemcpyDeviceToHost, st));
+    HB_CUDA_TRY(cudaMemcpyAsync(&ends[1], t_eval + (m - 1), sizeof(double), cudaMemcpyDeviceToHost, st));
+    HB_CUDA_TRY(cudaStreamSynchronize(st));
+    FilterParams p{};
+    int rc = fill_params(sys, integ, p.prop);
+    if (rc != HB_OK) return rc;
+    p.n = n; p.rec = (const double *)scratch; p.rec_cap = cap > 100000 ? 99968 : (int)cap;
+    p.nacc = n_acc; p.status = status; p.t_eval = t_eval; p.m = m;
+    p.inv_grid_dt = (ends[1] > ends[0]) ? (double)(m - 1) / (ends[1] - ends[0]) : 0.0;
+    p.o = *opts; p.out = out; p.keep = keep;
+    const long long blocks = (n + HB_FILT_WARPS - 1) / HB_FILT_WARPS;
+    if (blocks > 2147483647LL) return HB_ERR_BADARG;
+    static bool smem_set = false;
+    if (!smem_set) {
+        HB_CUDA_TRY(cudaFuncSetAttribute(k_record_filter<ArParity>, cudaFuncAttributeMaxDynamicSharedMemorySize, HB_FILT_SMEM));
+        HB_CUDA_TRY(cudaFuncSetAttribute(k_record_filter<ArFast>, cudaFuncAttributeMaxDynamicSharedMemorySize, HB_FILT_SMEM));
+        smem_set = true;
+    }
+    if (integ->arith == HB_ARITH_PARITY) k_record_filter<ArParity><<<(unsigned)blocks, 32 * HB_FILT_WARPS, HB_FILT_SMEM, st>>>(p);
+    else k_record_filter<ArFast><<<(unsigned)blocks, 32 * HB_FILT_WARPS, HB_FILT_SMEM, st>>>(p);
+    HB_CUDA_TRY(cudaGetLastError());
     return HB_OK;
 }

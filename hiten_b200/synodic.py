@@ -166,11 +166,14 @@ class TubeSectionRunner:
     buffers are created once; launch() enqueues the kernels, hit_count() / sorted_hits() read the result."""
 
     def __init__(self, n, mu, t_eval, section, *, forward=1, flip=None, integ=None, hit_capacity=None, device=None,
-                 steps_capacity=0, scratch=None):
+                 steps_capacity=0, scratch=None, filters=None):
         """steps_capacity > 0 selects the kernel pipeline hb_cr3bp_section2 with a scratch for that many accepted
         steps per trajectory (512 B per step); 0 the fused kernel hb_cr3bp_section.  Trajectories that do not fit
         the scratch are rerun with the fused kernel by hit_count() / sorted_hits(), so the result is the same.
-        `scratch` lets several runners share one (large) scratch tensor."""
+        `scratch` lets several runners share one (large) scratch tensor.
+        `filters` = (safe_r1, safe_r2, energy_tol) applies Manifold.compute()'s trajectory filters
+        (services/manifold.py:412-432) from the step records (hb_section2_filter, pipeline only): sorted_hits() then
+        returns the hits of the kept trajectories only -- what SynodicMap sees after manifold.compute()."""
         from . import propagate as P
         _require_cuda()
         self.lib = L.load()
@@ -191,6 +194,13 @@ class TubeSectionRunner:
         self.scratch = None
         self._y0 = None
         self._extra = None          # (indices, SectionHits) of the trajectories rerun with the fused kernel
+        self.filters = None
+        if filters is not None:
+            if self.steps_capacity <= 0:
+                raise ValueError("filters are computed from the step records: use steps_capacity > 0")
+            self.filters = L.HbTubeFilterOpts(float(mu), float(filters[0]), float(filters[1]), float(filters[2]))
+            self.filt = torch.empty((max(self.n, 1), 3), dtype=torch.float64, device=self.device)
+            self.keep = torch.empty(max(self.n, 1), dtype=torch.int32, device=self.device)
         if self.steps_capacity > 0:
             nbytes = int(self.lib.hb_section2_scratch_bytes(self.n, self.steps_capacity))
             self._owns_scratch = scratch is None
@@ -210,6 +220,12 @@ class TubeSectionRunner:
                                             self.nrej.data_ptr(), self.status.data_ptr(), self.scratch.data_ptr(),
                                             self.scratch.numel() * 8, self.ws.data_ptr(), _stream_ptr(stream))
             L.check(rc, "hb_cr3bp_section2")
+            if self.filters is not None:
+                rc = self.lib.hb_section2_filter(self.sys, self.integ, self.filters, self.n, self.te.data_ptr(),
+                                                 self.te.numel(), self.nacc.data_ptr(), self.status.data_ptr(),
+                                                 self.scratch.data_ptr(), self.scratch.numel() * 8,
+                                                 self.filt.data_ptr(), self.keep.data_ptr(), _stream_ptr(stream))
+                L.check(rc, "hb_section2_filter")
             return
         rc = self.lib.hb_cr3bp_section(self.sys, self.integ, self.section, self.n, y0_soa.data_ptr(),
                                        self.te.data_ptr(), self.te.numel(), self.hits.data_ptr(), self.cap,
@@ -234,6 +250,18 @@ class TubeSectionRunner:
                                 integ=self.integ, device=self.device)
         y0 = self._y0.view(6, self.n)[:, idx].contiguous()
         sub.launch(y0, stream)
+        if self.filters is not None:                          # no records for these: judge them on stored tubes
+            from . import manifold as M
+            from . import propagate as P
+            f = self.filters
+            for a in range(0, idx.numel(), 4096):
+                part = idx[a:a + 4096]
+                tube = P.cr3bp_dense(self._y0.view(6, self.n)[:, part].contiguous(), self.mu, self.te,
+                                     forward=self.forward, flip=self.flip, integ=self.integ, device=self.device,
+                                     stream=stream, keep_on_device=True)
+                q, k = M.tube_filter(tube.states, self.mu, safe_r1=f.safe_r1, safe_r2=f.safe_r2,
+                                     energy_tol=f.energy_tol, device=self.device, stream=stream)
+                self.filt[part], self.keep[part] = q, k
         h = sub.sorted_hits(stream)
         self.yf.view(6, self.n)[:, idx] = sub.yf.view(6, idx.numel())
         self.nacc[idx], self.nrej[idx], self.status[idx] = sub.nacc[: idx.numel()], sub.nrej[: idx.numel()], \
@@ -283,11 +311,25 @@ class TubeSectionRunner:
             seq = np.concatenate((seq, _seq_within(h.trajectory_indices)))
             t = np.concatenate((t, h.times))
             state = np.concatenate((state, h.states))
+        per = self.per[: self.n].cpu().numpy()
+        if self.filters is not None:                          # manifold.py:412-432: discarded tubes contribute nothing
+            kept = self.keep[: self.n].cpu().numpy() == 1
+            sel = kept[traj]
+            traj, seq, t, state = traj[sel], seq[sel], t[sel], state[sel]
+            per = np.where(kept, per, 0).astype(per.dtype)
         order = np.lexsort((seq, traj))
         traj, t, state = traj[order], t[order], state[order]
         sec = self.section
         pts = np.column_stack((state[:, sec.proj_i], state[:, sec.proj_j])) if len(t) else np.empty((0, 2))
-        return SectionHits(traj.copy(), t.copy(), state.copy(), pts, self.per[: self.n].cpu().numpy())
+        return SectionHits(traj.copy(), t.copy(), state.copy(), pts, per)
+
+    def filter_result(self, stream=None):
+        """(quantities[n,3] = min r1, min r2, max relative Jacobi drift; keep[n]: 1 kept, 0 discarded, -1 failed
+        propagation) as device tensors, once every trajectory has been judged."""
+        if self.filters is None:
+            raise ValueError("runner was created without filters")
+        self.hit_count(stream)
+        return self.filt[: self.n], self.keep[: self.n]
 
 
 def _seq_within(traj):

@@ -366,6 +366,17 @@ int hb_correct_orbits(const hb_cr3bp *sys, const hb_integ *integ, const hb_corre
                       double *residual_norm, int32_t *status, int64_t *rk_steps6, int64_t *rk_steps42,
                       void *scratch, int64_t scratch_bytes, void *workspace, void *stream);
 
+/* The same filter quantities for the trajectories of the LAST hb_cr3bp_section2 call that used `scratch`, computed from
+ * the step records it left there -- the section pipeline never stores the tube ("removing the need for
+ * dense output when the caller only wants sections").  Every one of the m grid samples is rebuilt from its step's
+ * interpolant and judged with the same arithmetic as hb_tube_filter: out / keep are bit-identical to hb_cr3bp_dense +
+ * hb_tube_filter.  Pass the same n, t_eval, m, n_acc, status, scratch and scratch_bytes as to hb_cr3bp_section2 (and the
+ * same sys / integ).  keep[i] = -1 (out = NaN) for trajectories without a complete record set (status != HB_TRAJ_OK,
+ * e.g. HB_TRAJ_RECORD_OVERFLOW): judge those on a stored tube.                                                   */
+int hb_section2_filter(const hb_cr3bp *sys, const hb_integ *integ, const hb_tube_filter_opts *opts, int64_t n,
+                       const double *t_eval, int32_t m, const int32_t *n_acc, const int32_t *status,
+                       const void *scratch, int64_t scratch_bytes, double *out, int32_t *keep, void *stream);
+
 /* Synodic-section crossing detection on precomputed trajectories (linear branch, the one the
  * reference's defaults select): replaces _SynodicDetectionBackend.run / detect_on_trajectory /
  * _detect_with_segment_refine / _order_and_dedup_hits (algorithms/poincare/synodic/backend.py:

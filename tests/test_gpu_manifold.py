@@ -79,3 +79,64 @@ def test_filter_many_tubes_vs_oracle():
     s = rng.uniform(-1.5, 1.5, size=(3000, 257, 6))
     out, _ = manifold.tube_filter(torch.from_numpy(s).cuda(), 0.0121505856)
     assert np.array_equal(out.cpu().numpy(), O.tube_filter(s, 0.0121505856))
+
+
+def _c1_section_runner(g, steps_capacity, energy_tol):
+    import torch
+    from hiten_b200 import synodic
+    mu = float(g["mu"])
+    t_eval = np.linspace(0.0, float(g["c1_tf"]), int(g["c1_steps"]))
+    sec = synodic.make_section("y", 0.0, ("x", "z"), -1)
+    r = synodic.TubeSectionRunner(len(g["c1_x0W"]), mu, t_eval, sec, forward=-1, flip=(0, 6),
+                                  steps_capacity=steps_capacity, filters=(3.318e-05, 9.04e-06, energy_tol))
+    r.launch(torch.from_numpy(np.ascontiguousarray(g["c1_x0W"].T)).cuda())
+    return r
+
+
+@pytest.mark.parametrize("steps_capacity", [160, 96])
+def test_record_filter_bit_exact_vs_reference(steps_capacity):
+    """hb_section2_filter: the filter quantities of the 50 default tubes rebuilt from the step records (capacity 96:
+    part of the batch overflows the records and is judged on stored tubes instead) equal the reference's own."""
+    g = np.load(G)
+    r = _c1_section_runner(g, steps_capacity, 1e-7)
+    out, keep = r.filter_result()
+    assert np.array_equal(out.cpu().numpy(), g["c1_filter"])
+    want = ~(g["c1_filter"][:, 2] > 1e-7)
+    assert np.array_equal(keep.cpu().numpy() == 1, want) and 0 < want.sum() < 50
+    # hits of discarded trajectories are gone, the others are the unfiltered run's
+    from hiten_b200 import synodic
+    h = r.sorted_hits()
+    plain = np.load(os.path.join(os.path.dirname(__file__), "golden", "synodic_c1.npz"))
+    assert np.array_equal(plain["x0W"], g["c1_x0W"])
+    sel = want[plain["hit_traj"]]
+    assert np.array_equal(h.trajectory_indices, plain["hit_traj"][sel])
+    assert np.array_equal(h.times, plain["hit_time"][sel]) and np.array_equal(h.states, plain["hit_state"][sel])
+    assert (h.hits_per_traj[~want] == 0).all()
+
+
+def test_record_filter_equals_stored_tube_filter_on_a_bench_slice():
+    """4000 trajectories of the bench batch, both arithmetic variants: records -> filter == dense tube -> filter."""
+    import torch
+    import bench
+    import hiten_b200 as hb
+    from hiten_b200 import manifold, synodic
+    n = 4000
+    ics, mu = bench.build_ics(n)
+    m = max(int(abs(bench.TF) / bench.GRID_DT) + 1, 100)
+    t_eval = np.linspace(0.0, bench.TF, m)
+    sec = synodic.make_section("y", 0.0, ("x", "z"), -1)
+    y0 = torch.from_numpy(np.ascontiguousarray(ics.T)).cuda()
+    for arith in ("parity", "fast"):
+        integ = hb.make_integ(arith=arith)
+        r = synodic.TubeSectionRunner(n, mu, t_eval, sec, forward=-1, flip=(0, 6), steps_capacity=192, integ=integ,
+                                      filters=(1e-3, 1e-3, 1e-9))
+        r.launch(y0)
+        out, keep = r.filter_result()
+        tube = hb.cr3bp_dense(y0, mu, t_eval, forward=-1, flip=(0, 6), integ=integ, keep_on_device=True)
+        ref, rkeep = manifold.tube_filter(tube.states, mu, safe_r1=1e-3, safe_r2=1e-3, energy_tol=1e-9)
+        if arith == "parity":
+            assert torch.equal(out, ref) and torch.equal(keep, rkeep)
+        else:
+            assert torch.allclose(out, ref, rtol=1e-6, atol=1e-12)
+        assert 0 < int(keep.sum()) < n
+        del tube
