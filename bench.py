@@ -489,6 +489,24 @@ def main():
             extra[label] = {"rk_steps_per_s": s2 * args.steps / t2, "ms_per_step": 1e3 * t2 / args.steps,
                             "crossings_per_s": r2.hit_count() * args.steps / t2}
             del r2
+        if args.steps_capacity > 0:
+            # the same step with Manifold.compute()'s trajectory filters judged from the step records:
+            # all 4713 samples of every trajectory are rebuilt and tested (safe radii, Jacobi drift)
+            r3 = synodic.TubeSectionRunner(n, mu, t_eval, sec, forward=-1, flip=(0, 6), integ=integ, device=dev,
+                                           steps_capacity=args.steps_capacity, scratch=runner.scratch,
+                                           filters=(3.318e-05, 9.04e-06, 1e-6))
+            for _ in range(3):
+                r3.launch(y0_soa)
+            t3 = time_steps(lambda: r3.launch(y0_soa), args.steps, flush, barrier, torch)
+            s3 = int((r3.nacc.sum() + r3.nrej.sum()).item())
+            kept = int((r3.filter_result()[1] == 1).sum().item())
+            filt_ms = 1e3 * t3 / args.steps - 1e3 * t_dev / args.steps
+            extra[f"section_{args.arith}_with_trajectory_filters"] = {
+                "rk_steps_per_s": s3 * args.steps / t3, "ms_per_step": 1e3 * t3 / args.steps,
+                "filter_kernel_ms": filt_ms, "samples_per_s": n * float(m) / (filt_ms * 1e-3) if filt_ms > 0 else None,
+                "kept_trajectories": kept,
+                "note": "hb_section2_filter: 6-component dense evaluation + r1, r2, Jacobi constant at every grid sample"}
+            del r3
         extra.update(secondary_configs(hb, torch, args.steps, flush, barrier))
 
     if rank == 0:

@@ -120,10 +120,10 @@ __global__ void __launch_bounds__(256) k_tube_filter(const double *__restrict__ 
         for (int k = lane; k < m; k += 32) {
 #pragma unroll
             for (int d = 0; d < 6; ++d) s[d] = X[(long long)k * 6 + d];
-            acc.sample(s, k, o.mu, mu1, mu2, C0, absC0);
+            acc.sample(s, k, o.mu, mu1, mu2, C0);
         }
         acc.warp_reduce();
-        if (lane == 0) acc.store(o, traj, out, keep);
+        if (lane == 0) acc.store(o, traj, absC0, out, keep);
     }
 }
 

@@ -516,10 +516,16 @@ __global__ void __launch_bounds__(256) k_order_dedup(const ScanParams p)
 // stores.  This kernel evaluates exactly those samples from the step records that hb_cr3bp_section2 left in its
 // scratch: one warp per trajectory; per chunk of 32 steps a lane builds the full interpolant of its step (three extra
 // stages + 7 x 6 coefficients, dense_cache) and parks it in shared memory (51 doubles per step, odd stride:
-// conflict-free), then the warp walks the chunk's grid samples 32 at a time -- owner step by binary search over the
-// chunk's ownership bounds, six-component Horner evaluation, the reference's r1 / r2 / Jacobi expressions
-// (hb_tubefilter.cuh) -- and reduces.  Same arithmetic per sample as hb_cr3bp_dense + hb_tube_filter: same bits.
+// conflict-free), then the warp takes the chunk's steps one after the other: coefficients broadcast from shared
+// memory into registers, the step's grid samples spread over the lanes 32 at a time -- six-component Horner
+// evaluation, the reference's r1 / r2 / Jacobi expressions (hb_tubefilter.cuh) -- and reduces.  Same arithmetic per
+// sample as hb_cr3bp_dense + hb_tube_filter: same bits.
 constexpr int HB_FILT_WARPS = 4;
+// 3 CTAs x 4 warps per SM (168 registers): measured 28.9 ms per 262144 trajectories vs 37.7 ms at 2 CTAs (255 registers)
+// and 39.1 ms at 4 CTAs (128 registers: the sample loop spills)
+#ifndef HB_FILT_MINBLOCKS
+#define HB_FILT_MINBLOCKS 3
+#endif
 constexpr int HB_FILT_ROW = 51;       // F[7][6], y_old[6], t_old, hseg, 1/hseg
 constexpr int HB_FILT_SMEM = HB_FILT_WARPS * (32 * HB_FILT_ROW * 8 + 32 * 4);
 
@@ -539,7 +545,7 @@ struct FilterParams {
 };
 
 template <class AR>
-__global__ void __launch_bounds__(32 * HB_FILT_WARPS) k_record_filter(const FilterParams p)
+__global__ void __launch_bounds__(32 * HB_FILT_WARPS, HB_FILT_MINBLOCKS) k_record_filter(const FilterParams p)
 {
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char filt_smem[];
@@ -597,38 +603,39 @@ __global__ void __launch_bounds__(32 * HB_FILT_WARPS) k_record_filter(const Filt
         }
         cends[lane] = cend;
         __syncwarp();
-        const int cb = carry_c, ce = __shfl_sync(FULL, cend, 31);
-        for (int cs = cb; cs < ce; cs += 32) {
-            const int c = cs + lane;
-            if (c < ce) {
-                int lo = 0, hi = 31;                           // first step of the chunk with cend > c owns sample c
-#pragma unroll
-                for (int it = 0; it < 5; ++it) {
-                    const int mid = (lo + hi) >> 1;
-                    if (cends[mid] > c) hi = mid; else lo = mid + 1;
-                }
-                const double *r = rows + lo * HB_FILT_ROW;
-                double F[7][6], y[6], st[6];
+        // the chunk's steps one after the other (warp-uniform loop): the step's 48 coefficients are read once from
+        // shared memory (broadcast) into registers, its samples go to the lanes 32 at a time
+        const int nst = min(32, nacc - base);
+        int c0 = carry_c;
+        for (int sl = 0; sl < nst; ++sl) {
+            const int c1 = cends[sl];
+            if (c0 < c1) {
+                const double *r = rows + sl * HB_FILT_ROW;
+                double F[7][6], y[6];
 #pragma unroll
                 for (int i = 0; i < 7; ++i)
 #pragma unroll
                     for (int d = 0; d < 6; ++d) F[i][d] = r[6 * i + d];
 #pragma unroll
                 for (int d = 0; d < 6; ++d) y[d] = r[42 + d];
-                const double hseg = r[49];
-                if (hseg != 0.0) dense_eval<AR>(y, F, xpar_by<AR>(p.t_eval[c], r[48], hseg, r[50]), st);
-                else {
+                const double t_old = r[48], hseg = r[49], inv = r[50];
+                for (int c = c0 + lane; c < c1; c += 32) {
+                    double st[6];
+                    if (hseg != 0.0) dense_eval<AR>(y, F, xpar_by<AR>(p.t_eval[c], t_old, hseg, inv), st);
+                    else {
 #pragma unroll
-                    for (int d = 0; d < 6; ++d) st[d] = y[d];
+                        for (int d = 0; d < 6; ++d) st[d] = y[d];
+                    }
+                    acc.sample(st, c, p.o.mu, mu1, mu2, C0);
                 }
-                acc.sample(st, c, p.o.mu, mu1, mu2, C0, absC0);
+                c0 = c1;
             }
         }
-        carry_c = ce;
+        carry_c = c0;
         __syncwarp();
     }
     acc.warp_reduce();
-    if (lane == 0) acc.store(p.o, traj, p.out, p.keep);
+    if (lane == 0) acc.store(p.o, traj, absC0, p.out, p.keep);
 }
 }  // namespace
 
