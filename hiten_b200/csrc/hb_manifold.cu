@@ -117,10 +117,29 @@ __global__ void __launch_bounds__(256) k_tube_filter(const double *__restrict__ 
         for (int d = 0; d < 6; ++d) s[d] = X[d];
         const double C0 = jacobi_ref(s, mu1, mu2), absC0 = fabs(C0);
         TubeFilterAcc acc;
-        for (int k = lane; k < m; k += 32) {
+        // two samples per lane and iteration, 16-byte loads (a sample is 48 B: 16-byte aligned whenever the array is):
+        // six independent loads in flight per lane instead of one dependent group
+        if ((reinterpret_cast<unsigned long long>(X) & 15ull) == 0) {
+            const double2 *X2 = reinterpret_cast<const double2 *>(X);
+            int k = lane;
+            for (; k + 32 < m; k += 64) {
+                const double2 a0 = X2[3ll * k], a1 = X2[3ll * k + 1], a2 = X2[3ll * k + 2];
+                const double2 b0 = X2[3ll * (k + 32)], b1 = X2[3ll * (k + 32) + 1], b2 = X2[3ll * (k + 32) + 2];
+                const double sa[6] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y}, sb[6] = {b0.x, b0.y, b1.x, b1.y, b2.x, b2.y};
+                acc.sample(sa, k, o.mu, mu1, mu2, C0);
+                acc.sample(sb, k + 32, o.mu, mu1, mu2, C0);
+            }
+            if (k < m) {
+                const double2 a0 = X2[3ll * k], a1 = X2[3ll * k + 1], a2 = X2[3ll * k + 2];
+                const double sa[6] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y};
+                acc.sample(sa, k, o.mu, mu1, mu2, C0);
+            }
+        } else {
+            for (int k = lane; k < m; k += 32) {
 #pragma unroll
-            for (int d = 0; d < 6; ++d) s[d] = X[(long long)k * 6 + d];
-            acc.sample(s, k, o.mu, mu1, mu2, C0);
+                for (int d = 0; d < 6; ++d) s[d] = X[(long long)k * 6 + d];
+                acc.sample(s, k, o.mu, mu1, mu2, C0);
+            }
         }
         acc.warp_reduce();
         if (lane == 0) acc.store(o, traj, absC0, out, keep);

@@ -77,8 +77,16 @@ def test_filter_many_tubes_vs_oracle():
     from hiten_b200 import manifold
     rng = np.random.default_rng(11)
     s = rng.uniform(-1.5, 1.5, size=(3000, 257, 6))
+    want = O.tube_filter(s, 0.0121505856)
     out, _ = manifold.tube_filter(torch.from_numpy(s).cuda(), 0.0121505856)
-    assert np.array_equal(out.cpu().numpy(), O.tube_filter(s, 0.0121505856))
+    assert np.array_equal(out.cpu().numpy(), want)
+    # an array that is only 8-byte aligned takes the scalar-load path: same numbers
+    flat = torch.empty(s.size + 1, dtype=torch.float64, device="cuda")
+    view = flat[1:].view(s.shape)
+    view.copy_(torch.from_numpy(s))
+    assert view.data_ptr() % 16 == 8
+    out, _ = manifold.tube_filter(view, 0.0121505856)
+    assert np.array_equal(out.cpu().numpy(), want)
 
 
 def _c1_section_runner(g, steps_capacity, energy_tol):
