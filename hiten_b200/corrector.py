@@ -91,13 +91,16 @@ def correct_orbits(x0, mu, opts, *, integ=None, device=None, stream=None, keep_o
         return CorrectionBatch(xc, half, it, rn, st, s6.value, s42.value)
 
 
-def opts_from_reference(orbit):
-    """hb_correct_opts from a reference PeriodicOrbit's own correction_config / correction_options, or None when
-    the configuration is outside this path (multiple shooting, != 2 controls, a non-plane event, another method)."""
+def opts_from_reference(orbit, options=None):
+    """hb_correct_opts from a reference PeriodicOrbit's own correction_config / correction_options (or the given
+    OrbitCorrectionOptions), or None when the configuration is outside this path (multiple shooting, != 2 controls,
+    a non-plane event, another integration method)."""
     from hiten.algorithms.poincare.singlehit import backend as sh
-    cfg, opt = orbit.correction_config, orbit.correction_options
+    cfg, opt = orbit.correction_config, (orbit.correction_options if options is None else options)
+    if not hasattr(opt, "base") or not hasattr(opt, "forward"):
+        return None
     ev = {sh._x_plane_crossing: 0, sh._y_plane_crossing: 1, sh._z_plane_crossing: 2}.get(getattr(cfg, "event_func", None))
-    if ev is None or not hasattr(cfg, "control_indices") or hasattr(cfg, "n_patches"):
+    if ev is None or type(cfg).__name__ != "OrbitCorrectionConfig":      # not the multiple-shooting subclass
         return None
     if len(cfg.control_indices) != 2 or len(cfg.residual_indices) != 2:
         return None

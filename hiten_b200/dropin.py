@@ -395,11 +395,59 @@ def _make_connections_run(orig):
     return run
 
 
+def _make_orbit_correct(orig):
+    """_OrbitCorrectionService.correct (algorithms/types/services/orbits.py:114-151) as ONE hb_correct_orbits call
+    (batch of one): the whole Newton + Armijo loop runs on the GPU.  Same cache key, same `apply_correction`, same
+    (state, period, result) return; non-convergence raises ConvergenceError like the reference's backend.  Only with
+    install(corrector="batched"): the result agrees with the reference's own Newton loop to <= 1e-10 (iteration count
+    within one), not bit for bit."""
+    def correct(self, *, options=None):
+        from . import corrector as _corr
+        if options is None:
+            options = self.correction_options
+        orbit = self.domain_obj
+        try:
+            op = _corr.opts_from_reference(orbit, options)
+        except Exception:
+            op = None
+        if op is None:
+            return orig(self, options=options)
+        from hiten.algorithms.corrector.types import OrbitCorrectionDomainPayload, OrbitCorrectionResult
+        from hiten.algorithms.types.exceptions import ConvergenceError
+        cache_key = self.make_key("correct", tuple(sorted(options.to_dict().items())))
+
+        def _factory():
+            x0 = np.asarray(orbit.initial_state, dtype=np.float64)[None, :]
+            res = _corr.correct_orbits(x0, float(orbit.mu), op, integ=_integ())
+            if int(res.status[0]) != 0:
+                raise ConvergenceError(f"Newton did not converge ({_corr.STATUS[int(res.status[0])]}, "
+                                       f"|R|={float(res.residual_norm[0]):.2e}).")
+            result = OrbitCorrectionResult(converged=True, x_corrected=np.asarray(res.x_corrected[0], dtype=float),
+                                           residual_norm=float(res.residual_norm[0]),
+                                           iterations=int(res.iterations[0]), half_period=float(res.half_period[0]))
+            payload = OrbitCorrectionDomainPayload._from_mapping({
+                "x_full": result.x_corrected, "half_period": result.half_period, "iterations": result.iterations,
+                "residual_norm": result.residual_norm})
+            self.apply_correction(payload)
+            return result.x_corrected, 2 * result.half_period, payload, result
+
+        state, period, payload, result = self.get_or_create(cache_key, _factory)
+        return state, period, result
+
+    correct.__wrapped__ = orig
+    return correct
+
+
 # ------------------------------------------------------------------------------------------------
 # install / uninstall
 # ------------------------------------------------------------------------------------------------
-def install(arith="parity"):
-    """Rebind the reference's funnels.  Requires `hiten` to be importable; idempotent."""
+def install(arith="parity", corrector="reference"):
+    """Rebind the reference's funnels.  Requires `hiten` to be importable; idempotent.
+    corrector="reference" keeps the reference's own Newton loop (its propagations run on the GPU through the rebound
+    `_propagate_dynsys` / `_DOP853.integrate`); corrector="batched" additionally rebinds
+    `_OrbitCorrectionService.correct` to hb_correct_orbits (one GPU call per correct())."""
+    if corrector not in ("reference", "batched"):
+        raise ValueError("corrector must be 'reference' or 'batched'")
     if _STATE["installed"]:
         _STATE["arith"] = arith
         return
@@ -433,6 +481,10 @@ def install(arith="parity"):
     _SynodicDetectionBackend.run = _make_synodic_run(_STATE["orig"]["synodic"])
     _CenterManifoldBackend.run = _make_cm_run(_STATE["orig"]["cm"])
     _ConnectionsBackend.run = _make_connections_run(_STATE["orig"]["connections"])
+    if corrector == "batched":
+        from hiten.algorithms.types.services.orbits import _OrbitCorrectionService
+        _STATE["orig"]["orbit_correct"] = _OrbitCorrectionService.correct
+        _OrbitCorrectionService.correct = _make_orbit_correct(_STATE["orig"]["orbit_correct"])
     _STATE["installed"] = True
 
 
@@ -452,6 +504,9 @@ def uninstall():
     _CenterManifoldBackend.run = o["cm"]
     from hiten.algorithms.connections.backends import _ConnectionsBackend
     _ConnectionsBackend.run = o["connections"]
+    if "orbit_correct" in o:
+        from hiten.algorithms.types.services.orbits import _OrbitCorrectionService
+        _OrbitCorrectionService.correct = o["orbit_correct"]
     _STATE.update(installed=False, orig={}, patched_modules=[])
     _TABLES.clear()
 

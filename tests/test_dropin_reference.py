@@ -186,3 +186,36 @@ def test_correct_many_applies_results_like_the_reference(ref, monkeypatch):
         assert abs(o_new.period - o_ref.period) <= 1e-10
         assert r_new.converged and abs(r_new.iterations - r_ref.iterations) <= 1
         assert abs(r_new.half_period - r_ref.half_period) <= 1e-10
+
+
+def test_batched_corrector_rebinds_orbit_correct(ref, monkeypatch):
+    """install(corrector="batched"): halo.correct() / lyapunov.correct() are ONE hb_correct_orbits call each, with the
+    reference's return values, caching and orbit update."""
+    import fake_gpu
+    import hiten_b200
+    from hiten.algorithms.types.services.orbits import _OrbitCorrectionService
+    system, l1, _ = ref
+    a = [l1.create_orbit("halo", amplitude_z=0.15, zenith="northern"), l1.create_orbit("lyapunov", amplitude_x=0.02)]
+    b = [l1.create_orbit("halo", amplitude_z=0.15, zenith="northern"), l1.create_orbit("lyapunov", amplitude_x=0.02)]
+    ref_res = [o.correct() for o in a]
+    orig = _OrbitCorrectionService.correct
+    hiten_b200.install(corrector="batched")
+    fake_gpu.patch(monkeypatch)
+    calls = []
+    import hiten_b200.corrector as corr
+    inner = corr.correct_orbits
+    monkeypatch.setattr(corr, "correct_orbits", lambda *a_, **k: (calls.append(1), inner(*a_, **k))[1])
+    try:
+        assert _OrbitCorrectionService.correct is not orig
+        for o_ref, o_new, r_ref in zip(a, b, ref_res):
+            r_new = o_new.correct()
+            assert r_new.converged and abs(r_new.iterations - r_ref.iterations) <= 1
+            assert np.abs(np.asarray(o_new.initial_state) - np.asarray(o_ref.initial_state)).max() <= 1e-10
+            assert abs(o_new.period - o_ref.period) <= 1e-10
+            assert o_new.correct() is r_new                 # cached like the reference
+        assert len(calls) == 2
+    finally:
+        hiten_b200.uninstall()
+    assert _OrbitCorrectionService.correct is orig
+    with pytest.raises(ValueError):
+        hiten_b200.install(corrector="nope")
