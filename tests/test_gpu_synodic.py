@@ -18,7 +18,7 @@ def _section(g):
                                 float(g["req_dedup_time_tol"]), float(g["req_dedup_point_tol"]))
 
 
-@pytest.mark.parametrize("name", ["c1", "c2"])
+@pytest.mark.parametrize("name", ["c1", "c2", "se"])
 def test_gpu_detector_bit_exact_on_identical_samples(name):
     """Same dense samples in -> identical hits out (integer/index work and IEEE arithmetic: bit-exact)."""
     from hiten_b200 import synodic
@@ -31,7 +31,7 @@ def test_gpu_detector_bit_exact_on_identical_samples(name):
     assert np.array_equal(got.points, g["hit_point"])
 
 
-@pytest.mark.parametrize("name", ["c1", "c2"])
+@pytest.mark.parametrize("name", ["c1", "c2", "se"])
 def test_gpu_tube_and_section_vs_reference(name):
     """Full GPU chain (Manifold.compute -> SynodicMap.compute): identical crossing counts, crossing points
     within 1e-9 in synodic coordinates (BASELINE.json north_star)."""
@@ -70,7 +70,7 @@ def test_detector_ragged_and_empty():
     assert len(empty.times) == 0
 
 
-@pytest.mark.parametrize("name", ["c1", "c2"])
+@pytest.mark.parametrize("name", ["c1", "c2", "se"])
 def test_fused_section_equals_two_kernel_chain(name):
     """hb_cr3bp_section (no dense tube) == hb_cr3bp_dense + hb_synodic_detect, bit for bit, and both match the
     reference's crossing counts / points."""
@@ -91,7 +91,7 @@ def test_fused_section_equals_two_kernel_chain(name):
     assert np.abs(fused.points - g["hit_point"]).max() <= 1e-9
 
 
-@pytest.mark.parametrize("name", ["c1", "c2"])
+@pytest.mark.parametrize("name", ["c1", "c2", "se"])
 @pytest.mark.parametrize("arith", ["parity", "fast"])
 def test_two_kernel_section_equals_fused(name, arith):
     """hb_cr3bp_section2 (record + scan) == hb_cr3bp_section, bit for bit; parity also == the reference's hits."""

@@ -26,7 +26,7 @@ def oracle_hits(g, n_threads=4):
     return dense, times, np.array(hi), np.array(ht), np.array(hs)
 
 
-@pytest.mark.parametrize("name,n_hits", [("c1", 121), ("c2", 679)])
+@pytest.mark.parametrize("name,n_hits", [("c1", 121), ("c2", 679), ("se", 23)])
 def test_section_hits_bit_exact(name, n_hits):
     g = np.load(os.path.join(HERE, "golden", f"synodic_{name}.npz"))
     dense, _, hi, ht, hs = oracle_hits(g)
