@@ -14,9 +14,10 @@ No reference file is edited.  What is rebound (paths relative to hiten/):
     becomes ONE batched dense propagation;
   * `_SynodicDetectionBackend.run` (algorithms/poincare/synodic/backend.py:823);
   * `_CenterManifoldBackend.run` (algorithms/poincare/centermanifold/backend.py:404);
-  * `_DOP853.integrate` (algorithms/integrators/rk.py:2221).
-Anything the GPU path cannot express (user-defined RHS or event callables, RK45 / fixed-step / symplectic generic
-integration, cubic synodic refinement) is handed to the reference's ORIGINAL function -- that is the reference's
+  * `_DOP853.integrate` (algorithms/integrators/rk.py:2221), `_RK45.integrate` (:1138) and
+    `_FixedStepRK.integrate` (:422; _RK4 / _RK6 / _RK8) for the 6-state CR3BP system.
+Anything the GPU path cannot express (user-defined RHS or event callables, polynomial-Hamiltonian systems outside the
+centre-manifold map, 42-state RK45 / fixed-step integration, cubic synodic refinement) is handed to the reference's ORIGINAL function -- that is the reference's
 own code for inputs outside this path, not a fallback of the kernels: for recognised inputs a missing library
 or GPU raises.
 """
@@ -24,6 +25,7 @@ import sys
 
 import numpy as np
 
+from . import _lib as _L
 from . import centermanifold as _cm
 from . import connections as _conn
 from . import manifold as _man
@@ -95,6 +97,15 @@ def _integ(kwargs=None, rtol=None, atol=None, max_step=None):
                             max_step=kwargs.get("max_step", 1e4) if max_step is None else max_step)
 
 
+def _hb_method(method, order):
+    """(method, order) of _propagate_dynsys -> HB_* integrator id, or None (base.py:430-453)."""
+    if method == "adaptive":
+        return {8: _L.HB_DOP853, 5: _L.HB_RK45}.get(order)
+    if method == "fixed":
+        return {4: _L.HB_RK4, 6: _L.HB_RK6, 8: _L.HB_RK8}.get(order)
+    return None
+
+
 def _rhs6_numpy(states, mu, fwd, flip):
     """Vectorised _crtbp_accel (+ direction wrapper) for the `derivatives` field of _Solution."""
     x, y, z, vx, vy, vz = states.T
@@ -161,7 +172,9 @@ def _make_propagate_dynsys(orig):
         from hiten.algorithms.integrators.types import _Solution
         rec = recognise_system(dynsys)
         known = {"rtol", "atol", "max_step", "event_fn", "event_cfg", "event_options"}
-        if rec is None or rec[2] != 1 or method != "adaptive" or order != 8 or (set(kwargs) - known):
+        hb_method = _hb_method(method, order)
+        if rec is None or rec[2] != 1 or hb_method is None or (set(kwargs) - known) or \
+                (hb_method != _L.HB_DOP853 and rec[0] != 6):
             return orig(dynsys, state0, t0, tf, forward=forward, steps=steps, method=method, order=order,
                         flip_indices=flip_indices, **kwargs)
         dim, mu, _, _ = rec
@@ -185,8 +198,15 @@ def _make_propagate_dynsys(orig):
         t_eval = np.linspace(t0, tf, steps)
         if steps >= 2 and np.isclose(t_eval[0], t_eval[-1]):          # base.py:421-424
             return _Solution(forward * t_eval, np.repeat(state0_np[None, :], repeats=len(t_eval), axis=0))
+        if hb_method == _L.HB_DOP853:
+            integ = _integ(kwargs)
+        elif hb_method == _L.HB_RK45:                     # AdaptiveRK(order=5, max_step, rtol, atol), base.py:446-450
+            integ = _prop.make_integ(method=_L.HB_RK45, arith=_STATE["arith"], rtol=kwargs.get("rtol", 1e-12),
+                                     atol=kwargs.get("atol", 1e-12), max_step=kwargs.get("max_step", 1e4))
+        else:                                             # RungeKutta(order=4|6|8): one step per grid interval
+            integ = _prop.make_integ(method=hb_method, arith=_STATE["arith"], n_fixed_steps=steps - 1)
         try:
-            times, states = _gpu_integrate(dim, mu, fwd, flip, state0_np, t_eval, _integ(kwargs), event)
+            times, states = _gpu_integrate(dim, mu, fwd, flip, state0_np, t_eval, integ, event)
         except LookupError:
             return orig(dynsys, state0, t0, tf, forward=forward, steps=steps, method=method, order=order,
                         flip_indices=flip_indices, **kwargs)
@@ -232,6 +252,51 @@ def _make_dop853_integrate(orig):
             return _Solution(times=times, states=states)
         derivs = _rhs6_numpy(states, mu, fwd, flip) if dim == 6 else None
         return _Solution(times=times, states=states, derivatives=derivs)
+
+    integrate.__wrapped__ = orig
+    integrate.__doc__ = orig.__doc__
+    return integrate
+
+
+def _make_rk_integrate(orig, kind):
+    """_RK45.integrate (rk.py:1138) / _FixedStepRK.integrate (rk.py:422) for the 6-state CR3BP system: grid
+    integration (hb_cr3bp_dense with the class's method) and recognised plane events (hb_cr3bp_event).  The fixed-step
+    event scan runs on the GPU only for a uniform grid (the kernel rebuilds linspace(t0, tf, n + 1)); anything else
+    goes to the reference's own method."""
+    def integrate(self, system, y0, t_vals, *, event_fn=None, event_cfg=None, event_options=None, **kwargs):
+        from hiten.algorithms.integrators.types import _Solution
+        rec = recognise_system(system)
+        ev = recognise_event(event_fn) if event_fn is not None else None
+        method = _L.HB_RK45 if kind == "rk45" else {"_RK4": _L.HB_RK4, "_RK6": _L.HB_RK6,
+                                                    "_RK8": _L.HB_RK8}.get(type(self).__name__)
+        if rec is None or rec[0] != 6 or method is None or (event_fn is not None and ev is None) or kwargs:
+            return orig(self, system, y0, t_vals, event_fn=event_fn, event_cfg=event_cfg,
+                        event_options=event_options, **kwargs)
+        self.validate_inputs(system, y0, t_vals)
+        if kind == "fixed":
+            const = self._maybe_constant_solution(system, y0, t_vals)
+            if const is not None:
+                return const
+        t_vals = np.asarray(t_vals, dtype=np.float64)
+        uniform = t_vals.size >= 2 and np.array_equal(t_vals, np.linspace(t_vals[0], t_vals[-1], t_vals.size))
+        if not np.all(np.diff(t_vals) > 0) or (kind == "fixed" and event_fn is not None and not uniform):
+            return orig(self, system, y0, t_vals, event_fn=event_fn, event_cfg=event_cfg,
+                        event_options=event_options, **kwargs)
+        dim, mu, fwd, flip = rec
+        if kind == "rk45":
+            integ = _prop.make_integ(method=method, arith=_STATE["arith"], rtol=self._rtol, atol=self._atol,
+                                     max_step=min(float(self._max_step), 1e300), min_step=self._min_step)
+        else:
+            integ = _prop.make_integ(method=method, arith=_STATE["arith"], n_fixed_steps=t_vals.size - 1)
+        event = None
+        if ev is not None:
+            event = (ev[0], ev[1], 0 if event_cfg is None else int(event_cfg.direction),
+                     float(event_options.xtol if event_options is not None else 1.0e-12),
+                     float(event_options.gtol if event_options is not None else 1.0e-12))
+        times, states = _gpu_integrate(dim, mu, fwd, flip, np.asarray(y0, dtype=np.float64), t_vals, integ, event)
+        if event is not None:
+            return _Solution(times=times, states=states)
+        return _Solution(times=times, states=states, derivatives=_rhs6_numpy(states, mu, fwd, flip))
 
     integrate.__wrapped__ = orig
     integrate.__doc__ = orig.__doc__
@@ -454,7 +519,7 @@ def install(arith="parity", corrector="reference"):
     import hiten  # noqa: F401
     import hiten.algorithms.dynamics.base as dbase
     from hiten.algorithms.connections.backends import _ConnectionsBackend
-    from hiten.algorithms.integrators.rk import _DOP853
+    from hiten.algorithms.integrators.rk import _DOP853, _RK45, _FixedStepRK
     from hiten.algorithms.poincare.centermanifold.backend import _CenterManifoldBackend
     from hiten.algorithms.poincare.synodic.backend import _SynodicDetectionBackend
     from hiten.algorithms.types.services.manifold import _ManifoldDynamicsService
@@ -471,12 +536,16 @@ def install(arith="parity", corrector="reference"):
     _STATE["orig"] = {
         "propagate": orig_prop,
         "dop853": _DOP853.integrate,
+        "rk45": _RK45.integrate,
+        "fixed_rk": _FixedStepRK.integrate,
         "run_compute": _ManifoldDynamicsService._run_compute,
         "synodic": _SynodicDetectionBackend.run,
         "cm": _CenterManifoldBackend.run,
         "connections": _ConnectionsBackend.run,
     }
     _DOP853.integrate = _make_dop853_integrate(_STATE["orig"]["dop853"])
+    _RK45.integrate = _make_rk_integrate(_STATE["orig"]["rk45"], "rk45")
+    _FixedStepRK.integrate = _make_rk_integrate(_STATE["orig"]["fixed_rk"], "fixed")
     _ManifoldDynamicsService._run_compute = _make_run_compute(_STATE["orig"]["run_compute"])
     _SynodicDetectionBackend.run = _make_synodic_run(_STATE["orig"]["synodic"])
     _CenterManifoldBackend.run = _make_cm_run(_STATE["orig"]["cm"])
@@ -499,6 +568,9 @@ def uninstall():
     for mod in _STATE["patched_modules"]:
         setattr(mod, "_propagate_dynsys", o["propagate"])
     _DOP853.integrate = o["dop853"]
+    from hiten.algorithms.integrators.rk import _RK45, _FixedStepRK
+    _RK45.integrate = o["rk45"]
+    _FixedStepRK.integrate = o["fixed_rk"]
     _ManifoldDynamicsService._run_compute = o["run_compute"]
     _SynodicDetectionBackend.run = o["synodic"]
     _CenterManifoldBackend.run = o["cm"]

@@ -18,7 +18,12 @@ def _tol(integ):
 
 def cr3bp_dense(y0, mu, t_eval, *, forward=1, flip=None, integ=None, **kw):
     s = O.system(O.SYS_CR3BP6, mu, fwd=forward, flip=flip)
-    dense, counts = O.batch_dense(s, O.DOP853, _tol(integ), np.asarray(y0), np.asarray(t_eval), 4)
+    if integ.method in (4, 6, 8):                      # fixed-step: one step per grid interval
+        y0 = np.asarray(y0)
+        dense = np.stack([O.fixed_dense(s, integ.method, y, np.asarray(t_eval)) for y in y0])
+        z = np.zeros(len(y0), np.int32)
+        return BatchResult(None, z, z, z, states=dense)
+    dense, counts = O.batch_dense(s, integ.method, _tol(integ), np.asarray(y0), np.asarray(t_eval), 4)
     n = len(dense)
     return BatchResult(None, counts[:, 0].astype(np.int32), counts[:, 1].astype(np.int32), np.zeros(n, np.int32),
                        states=dense)
@@ -40,7 +45,10 @@ def cr3bp_event(y0, mu, tmax, event_idx, *, event_offset=0.0, direction=0, xtol=
     y0 = np.asarray(y0)
     yf, th, st = np.empty_like(y0), np.empty(len(y0)), np.zeros(len(y0), np.int32)
     for i in range(len(y0)):
-        hit, t, yh, yl, _ = O.adaptive_event(s, O.DOP853, _tol(integ), ev, y0[i], t0, tmax)
+        if integ.method in (4, 6, 8):
+            hit, t, yh = O.fixed_event(s, integ.method, ev, y0[i], np.linspace(t0, tmax, integ.n_fixed_steps + 1))
+        else:
+            hit, t, yh, yl, _ = O.adaptive_event(s, integ.method, _tol(integ), ev, y0[i], t0, tmax)
         yf[i], th[i], st[i] = yh, t, 1 if hit else 0
     return BatchResult(yf, np.zeros(len(y0), np.int32), np.zeros(len(y0), np.int32), st, t_hit=th)
 

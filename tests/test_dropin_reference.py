@@ -219,3 +219,50 @@ def test_batched_corrector_rebinds_orbit_correct(ref, monkeypatch):
     assert _OrbitCorrectionService.correct is orig
     with pytest.raises(ValueError):
         hiten_b200.install(corrector="nope")
+
+
+def test_rk45_and_fixed_step_classes_and_propagate_variants(ref, monkeypatch):
+    """_RK45.integrate / _FixedStepRK.integrate and _propagate_dynsys(method="fixed" | order=5) with the drop-in:
+    the same arrays as the reference alone, bit for bit (grid integration and plane events)."""
+    import fake_gpu
+    import hiten_b200
+    import hiten.algorithms.dynamics.base as dbase
+    from hiten.algorithms.integrators.rk import RungeKutta
+    from hiten.algorithms.poincare.singlehit.backend import _g_y0
+    from hiten.algorithms.types.configs import EventConfig
+    system, l1, halo = ref
+    x0 = np.asarray(halo.initial_state, dtype=np.float64)
+    dyn = system.dynsys
+    grid = np.linspace(0.0, 1.5, 151)
+    cfg = EventConfig(direction=0, terminal=True)
+    y1 = dbase._propagate_dynsys(dyn, x0, 0.0, 0.05, steps=2).states[-1]
+
+    def run_all():
+        out = {}
+        for order in (4, 6, 8, 45):
+            integ = RungeKutta(order=order) if order != 45 else RungeKutta(order=45, rtol=1e-10, atol=1e-10)
+            sol = integ.integrate(dyn, x0, grid)
+            out[f"dense{order}"] = (sol.times.copy(), sol.states.copy())
+            ev = integ.integrate(dyn, y1, np.linspace(0.0, 2.0, 2001), event_fn=_g_y0, event_cfg=cfg)
+            out[f"event{order}"] = (ev.times.copy(), ev.states.copy())
+        for method, order in (("fixed", 4), ("fixed", 8), ("adaptive", 5)):
+            sol = dbase._propagate_dynsys(dyn, x0, 0.0, 1.0, forward=-1, steps=101, method=method, order=order)
+            out[f"prop_{method}{order}"] = (sol.times.copy(), sol.states.copy())
+        return out
+
+    want = run_all()
+    hiten_b200.install()
+    fake_gpu.patch(monkeypatch)
+    calls = []
+    import hiten_b200.propagate as prop
+    d0, e0 = prop.cr3bp_dense, prop.cr3bp_event
+    monkeypatch.setattr(prop, "cr3bp_dense", lambda *a, **k: (calls.append("dense"), d0(*a, **k))[1])
+    monkeypatch.setattr(prop, "cr3bp_event", lambda *a, **k: (calls.append("event"), e0(*a, **k))[1])
+    try:
+        got = run_all()
+    finally:
+        hiten_b200.uninstall()
+    assert calls.count("dense") == 7 and calls.count("event") == 4          # every call went through the GPU entry points
+    for k in want:
+        assert np.array_equal(got[k][0], want[k][0]), k
+        assert np.array_equal(got[k][1], want[k][1]), k
