@@ -152,6 +152,43 @@ def poincare_map(table, seeds, opts, *, device=None, stream=None, ws=None, jit=T
         return flags, out, tt
 
 
+_STATE_INDEX = {"q2": 0, "p2": 1, "q3": 2, "p3": 3}      # columns of a (q2, p2, q3, p3) state row
+
+
+def poincare_map_iterate(table, seeds, opts, n_iter, section_coord, *, device=None, stream=None, jit=True):
+    """The iteration loop of `_CenterManifoldEngine.solve._worker` (centermanifold/engine.py:163-191) with the seeds
+    resident in HBM: every pass maps the current seeds (`poincare_map`), drops the failed ones, zeroes the section
+    coordinate (`enforce_section_coordinate`, interfaces.py:338-346), accumulates the hits and feeds them back as the
+    next seeds.  Returns (states[M, 4], times[M], iteration[M]) as device tensors, in the reference's order (iteration
+    by iteration, seed order inside an iteration)."""
+    _require_cuda()
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    col = _STATE_INDEX[section_coord]
+    with torch.cuda.device(device):
+        cur = seeds if isinstance(seeds, torch.Tensor) and seeds.is_cuda else torch.from_numpy(
+            np.ascontiguousarray(seeds, dtype=np.float64)).to(device)
+        ws = workspace(device)
+        st_acc, t_acc, it_acc = [], [], []
+        for it in range(int(n_iter)):
+            if cur.shape[0] == 0:
+                break
+            flags, out, tt = poincare_map(table, cur, opts, device=device, stream=stream, ws=ws, jit=jit)
+            ok = flags == 1
+            nxt = out[ok].clone()
+            if nxt.shape[0] == 0:
+                break
+            nxt[:, col] = 0.0
+            st_acc.append(nxt)
+            t_acc.append(tt[ok])
+            it_acc.append(torch.full((nxt.shape[0],), it, dtype=torch.int32, device=device))
+            cur = nxt
+        if not st_acc:
+            z = torch.empty
+            return (z((0, 4), dtype=torch.float64, device=device), z(0, dtype=torch.float64, device=device),
+                    z(0, dtype=torch.int32, device=device))
+        return torch.cat(st_acc), torch.cat(t_acc), torch.cat(it_acc)
+
+
 def lift_plane_points(H_table, section_coord, plane_points, h0, *, initial_guess=1e-3, expand_factor=2.0, max_expand=40,
                       symmetric=False, xtol=1e-12, device=None, stream=None):
     """Batched _CenterManifoldInterface.lift_plane_point (interfaces.py:297-337): plane_points [N, 2] in the section's
