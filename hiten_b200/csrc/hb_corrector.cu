@@ -252,11 +252,13 @@ __global__ void k_newton_delta(Corr c, hb_correct_opts o, double mu, const int *
             t = b; b = d; d = t;
             t = b0; b0 = b1; b1 = t;
         }
-        const double l = __ddiv_rn(cc, a);
+        // np.linalg.solve = LAPACK dgesv on OpenBLAS kernels; roundings identified against numpy (oracle/ho_correct.c):
+        // multiplier c * (1/a), Schur update mul + sub, both substitutions fused, final quotients true divisions
+        const double l = __dmul_rn(cc, __ddiv_rn(1.0, a));
         const double u22 = __dsub_rn(d, __dmul_rn(l, b));
         if (a == 0.0 || u22 == 0.0 || !(fabs(u22) <= CUDART_INF)) { c.phase[i] = PH_SINGULAR; continue; }
-        double d1 = __ddiv_rn(__dsub_rn(b1, __dmul_rn(l, b0)), u22);
-        double d0 = __ddiv_rn(__dsub_rn(b0, __dmul_rn(b, d1)), a);
+        double d1 = __ddiv_rn(__fma_rn(-l, b0, b1), u22);
+        double d0 = __ddiv_rn(__fma_rn(-b, d1, b0), a);
         if (o.max_delta < CUDART_INF) {                             // armijo.py:98-107 / plain.py
             const double dn = fmax(fabs(d0), fabs(d1));
             if (dn > o.max_delta) {

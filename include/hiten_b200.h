@@ -338,8 +338,9 @@ int hb_tube_filter(const hb_tube_filter_opts *opts, int64_t n, const double *sta
  * outputs) receive the attempted 6-state and 42-state DOP853 steps of the whole call.  scratch: device block of
  * hb_correct_scratch_bytes(n) bytes.  The call synchronises `stream` (it reads the number of orbits still active
  * between launches -- 4 bytes -- and nothing else).
- * Event propagation is the bit-exact path; the STM and the 2x2 solve are tolerance-level (see hb_cr3bp_stm), so
- * corrected states agree with the reference at Newton-convergence level (<= 1e-10) and iteration counts to within
+ * Event propagation is the bit-exact path and the 2x2 solve reproduces np.linalg.solve bit for bit, so the
+ * finite-difference variant is bit-identical to the reference; the STM is tolerance-level (see hb_cr3bp_stm), so with
+ * the analytic Jacobian corrected states agree with the reference at Newton-convergence level (<= 1e-10) and iteration counts to within
  * one (the reference's |R| < 1e-12 test sits on the 1e-12 noise floor of its own event solver).                 */
 #define HB_CORR_CONVERGED 0
 #define HB_CORR_MAX_ATTEMPTS 1   /* ConvergenceError: not converged after max_attempts                      */

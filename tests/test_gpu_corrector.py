@@ -34,6 +34,13 @@ def test_families_match_reference(family):
     assert (res.residual_norm[ok] < 1e-12).all()
     assert (res.status[~ok] == 3).all() and np.isnan(res.half_period[~ok]).all()
     assert res.rk_steps6 > 0 and (res.rk_steps42 > 0) == (family != "vertical")
+    if family == "vertical":
+        # finite-difference Jacobian: no STM in the loop, every propagation is the bit-exact event path and the 2x2
+        # solve reproduces LAPACK's roundings -> the whole 25-iteration Newton / Armijo run is bit-identical
+        assert np.array_equal(res.iterations, g["vertical_iters"])
+        assert np.array_equal(res.x_corrected, g["vertical_xc"])
+        assert np.array_equal(res.half_period, g["vertical_half"])
+        assert np.array_equal(res.residual_norm, g["vertical_rnorm"])
 
 
 @pytest.mark.parametrize("family,line_search", [("halo", True), ("halo", False), ("lyapunov", True)])

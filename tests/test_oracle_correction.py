@@ -37,3 +37,20 @@ def test_correction_matches_reference(family):
     assert (rnorm[ok] < 1e-12).all()
     if (~ok).any():
         assert (status[~ok] == 3).all()                       # no crossing for an iterate: TypeError in the reference
+    if family == "vertical":                                  # finite differences: no STM in the loop -> bit-exact
+        assert np.array_equal(iters, g["vertical_iters"]) and np.array_equal(xc, g["vertical_xc"])
+        assert np.array_equal(half, g["vertical_half"]) and np.array_equal(rnorm, g["vertical_rnorm"])
+
+
+def test_solve_delta_reproduces_numpy_linalg_solve():
+    """_solve_delta_dense's np.linalg.solve (LAPACK dgesv on OpenBLAS) for 2x2 systems, bit for bit."""
+    rng = np.random.default_rng(0)
+    f = O.lib().ho_solve_delta2
+    for _ in range(3000):
+        J = rng.standard_normal((2, 2)) * 10 ** rng.uniform(-2, 2)
+        r = rng.standard_normal(2) * 10 ** rng.uniform(-6, 0)
+        if np.linalg.cond(J) > 1e8:
+            continue
+        d = np.empty(2)
+        assert f(O._p(np.ascontiguousarray(J)), O._p(r), O._p(d)) == 1
+        assert np.array_equal(d, np.linalg.solve(J, -r))
