@@ -54,6 +54,10 @@ class HbCmOpts(C.Structure):
                 ("sub_sin", C.c_double * HB_MAX_TAO_SUBSTEPS)]
 
 
+class HbSympOpts(C.Structure):
+    _fields_ = [("order", C.c_int32), ("arith", C.c_int32), ("m", C.c_int32), ("n_sub", C.c_int32)]
+
+
 class HbCmLiftOpts(C.Structure):
     _fields_ = [("h0", C.c_double), ("initial_guess", C.c_double), ("expand_factor", C.c_double), ("xtol", C.c_double),
                 ("max_expand", C.c_int32), ("symmetric", C.c_int32), ("section", C.c_int32), ("max_iter", C.c_int32)]
@@ -103,6 +107,10 @@ SIGNATURES = {
     "hb_connections": (C.c_int, [vp, C.c_int64, vp, C.c_int64, vp, vp, C.c_double, C.c_double, C.c_double, vp, C.c_int64,
                                  C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64), vp, C.c_int64, vp]),
     "hb_cm_lift": (C.c_int, [C.POINTER(HbPolyHam), C.POINTER(HbCmLiftOpts), C.c_int64, vp, vp, vp, vp]),
+    "hb_tao_grid_prepare": (C.c_int, [vp, C.c_int32, C.c_int32, C.c_double, C.POINTER(C.c_int32), vp, C.c_int64]),
+    "hb_ham_symplectic_dense": (C.c_int, [C.POINTER(HbPolyHam), C.POINTER(HbSympOpts), C.c_int64, vp, vp, vp, vp, vp]),
+    "hb_ham_symplectic_event": (C.c_int, [C.POINTER(HbPolyHam), C.POINTER(HbSympOpts), C.POINTER(HbEvent), C.c_int64, vp,
+                                          vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "hb_cm_poincare_map": (C.c_int, [C.POINTER(HbPolyHam), C.POINTER(HbCmOpts), C.c_int64, vp, vp, vp, vp, vp, vp]),
     "hb_cm_poincare_map_jit": (C.c_int, [C.POINTER(HbPolyHam), C.POINTER(HbCmOpts), C.c_int64, vp, vp, vp, vp, vp, vp]),
     "hb_cm_jit_compile_host": (C.c_int, [vp, C.POINTER(C.c_int64), C.c_int32, C.POINTER(HbCmOpts), C.POINTER(C.c_int64),

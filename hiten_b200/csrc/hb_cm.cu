@@ -44,8 +44,8 @@ struct CmParams {
 
 // ---- polynomial gradient -----------------------------------------------------------------------
 // pw points at this thread's column of the shared power table: pw[(v*(D+1)+e)*CM_BLOCK].
-template <class AR>
-__device__ __noinline__ void cm_grad(const CmParams &p, double *pw, const TermMeta *terms, const double (&pt)[6],
+template <class AR, class PRM>
+__device__ __noinline__ void cm_grad(const PRM &p, double *pw, const TermMeta *terms, const double (&pt)[6],
                                      double (&g)[6])
 {
     const int D1 = p.D + 1;
@@ -89,13 +89,59 @@ __device__ __noinline__ void cm_grad(const CmParams &p, double *pw, const TermMe
 }
 
 // rhs = [dH/dP, -dH/dQ]  (hamiltonian.py:80-90)
-template <class AR>
-HB_DEV void cm_rhs(const CmParams &p, double *pw, const TermMeta *terms, const double (&y)[6], double (&dy)[6])
+template <class AR, class PRM>
+HB_DEV void cm_rhs(const PRM &p, double *pw, const TermMeta *terms, const double (&y)[6], double (&dy)[6])
 {
     double g[6];
     cm_grad<AR>(p, pw, terms, y, g);
     dy[0] = g[3]; dy[1] = g[4]; dy[2] = g[5];
     dy[3] = -g[0]; dy[4] = -g[1]; dy[5] = -g[2];
+}
+
+// One _recursive_update_poly call (symplectic.py:509-560) flattened into its n_sub order-2 kernels
+// phi_a(ts/2) phi_b(ts/2) phi_c(ts) phi_b(ts/2) phi_a(ts/2) on the extended state [Q, P, X, Y]; ts / cos / sin per kernel
+// come from the host (hb_cm_prepare / hb_tao_grid_prepare: libm, as the reference evaluates them).
+template <class AR, class PRM>
+HB_DEV void tao_update(const PRM &p, double *pw, const TermMeta *terms, const double *sub_ts, const double *sub_cos,
+                       const double *sub_sin, int n_sub, double (&Q)[3], double (&P)[3], double (&X)[3], double (&Y)[3])
+{
+    double g[6], pt[6];
+    for (int j = 0; j < n_sub; ++j) {
+        const double ts = sub_ts[j], hd = AR::mul(0.5, ts);
+        const double c = sub_cos[j], s = sub_sin[j];
+#pragma unroll 1
+        for (int ph = 0; ph < 5; ++ph) {
+            if (ph == 2) {                   // phi_omega_H_c (symplectic.py:486-506)
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const double qpx = AR::add(Q[i], X[i]), qmx = AR::sub(Q[i], X[i]);
+                    const double ppy = AR::add(P[i], Y[i]), pmy = AR::sub(P[i], Y[i]);
+                    Q[i] = AR::mul(0.5, AR::add(AR::add(qpx, AR::mul(c, qmx)), AR::mul(s, pmy)));
+                    P[i] = AR::mul(0.5, AR::add(AR::sub(ppy, AR::mul(s, qmx)), AR::mul(c, pmy)));
+                    X[i] = AR::mul(0.5, AR::sub(AR::sub(qpx, AR::mul(c, qmx)), AR::mul(s, pmy)));
+                    Y[i] = AR::mul(0.5, AR::sub(AR::add(ppy, AR::mul(s, qmx)), AR::mul(c, pmy)));
+                }
+            } else if (ph == 0 || ph == 4) { // phi_H_a: gradient at (Q, Y); P -= d*dHdQ, X += d*dHdP
+#pragma unroll
+                for (int i = 0; i < 3; ++i) { pt[i] = Q[i]; pt[3 + i] = Y[i]; }
+                cm_grad<AR>(p, pw, terms, pt, g);
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    P[i] = AR::sub(P[i], AR::mul(hd, g[i]));
+                    X[i] = AR::add(X[i], AR::mul(hd, g[3 + i]));
+                }
+            } else {                         // phi_H_b: gradient at (X, P); Q += d*dHdP, Y -= d*dHdQ
+#pragma unroll
+                for (int i = 0; i < 3; ++i) { pt[i] = X[i]; pt[3 + i] = P[i]; }
+                cm_grad<AR>(p, pw, terms, pt, g);
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    Q[i] = AR::add(Q[i], AR::mul(hd, g[3 + i]));
+                    Y[i] = AR::sub(Y[i], AR::mul(hd, g[i]));
+                }
+            }
+        }
+    }
 }
 
 template <class AR>
@@ -148,43 +194,7 @@ __global__ void __launch_bounds__(CM_BLOCK) k_cm_map(const CmParams p)
                 // q_ext = [Q, P, X = Q, Y = P] rebuilt every dt (backend.py:289-291, symplectic.py:636-640)
                 double Q[3] = {so[0], so[1], so[2]}, P[3] = {so[3], so[4], so[5]};
                 double X[3] = {so[0], so[1], so[2]}, Y[3] = {so[3], so[4], so[5]};
-                double g[6], pt[6];
-                for (int j = 0; j < p.o.n_sub; ++j) {
-                    const double ts = p.o.sub_ts[j], hd = AR::mul(0.5, ts);
-                    const double c = p.o.sub_cos[j], s = p.o.sub_sin[j];
-#pragma unroll 1
-                    for (int ph = 0; ph < 5; ++ph) {
-                        if (ph == 2) {                   // phi_omega_H_c (symplectic.py:486-506)
-#pragma unroll
-                            for (int i = 0; i < 3; ++i) {
-                                const double qpx = AR::add(Q[i], X[i]), qmx = AR::sub(Q[i], X[i]);
-                                const double ppy = AR::add(P[i], Y[i]), pmy = AR::sub(P[i], Y[i]);
-                                Q[i] = AR::mul(0.5, AR::add(AR::add(qpx, AR::mul(c, qmx)), AR::mul(s, pmy)));
-                                P[i] = AR::mul(0.5, AR::add(AR::sub(ppy, AR::mul(s, qmx)), AR::mul(c, pmy)));
-                                X[i] = AR::mul(0.5, AR::sub(AR::sub(qpx, AR::mul(c, qmx)), AR::mul(s, pmy)));
-                                Y[i] = AR::mul(0.5, AR::sub(AR::add(ppy, AR::mul(s, qmx)), AR::mul(c, pmy)));
-                            }
-                        } else if (ph == 0 || ph == 4) { // phi_H_a: gradient at (Q, Y); P -= d*dHdQ, X += d*dHdP
-#pragma unroll
-                            for (int i = 0; i < 3; ++i) { pt[i] = Q[i]; pt[3 + i] = Y[i]; }
-                            cm_grad<AR>(p, pw, terms, pt, g);
-#pragma unroll
-                            for (int i = 0; i < 3; ++i) {
-                                P[i] = AR::sub(P[i], AR::mul(hd, g[i]));
-                                X[i] = AR::add(X[i], AR::mul(hd, g[3 + i]));
-                            }
-                        } else {                         // phi_H_b: gradient at (X, P); Q += d*dHdP, Y -= d*dHdQ
-#pragma unroll
-                            for (int i = 0; i < 3; ++i) { pt[i] = X[i]; pt[3 + i] = P[i]; }
-                            cm_grad<AR>(p, pw, terms, pt, g);
-#pragma unroll
-                            for (int i = 0; i < 3; ++i) {
-                                Q[i] = AR::add(Q[i], AR::mul(hd, g[3 + i]));
-                                Y[i] = AR::sub(Y[i], AR::mul(hd, g[i]));
-                            }
-                        }
-                    }
-                }
+                tao_update<AR>(p, pw, terms, p.o.sub_ts, p.o.sub_cos, p.o.sub_sin, p.o.n_sub, Q, P, X, Y);
 #pragma unroll
                 for (int i = 0; i < 3; ++i) { sn[i] = Q[i]; sn[3 + i] = P[i]; }
             } else {
@@ -268,6 +278,173 @@ void tao_schedule(double ts, int order, hb_cm_opts *o)
     }
 }
 
+
+// ---- _ExtendedSymplectic.integrate: the Tao integrator over a time grid --------------------------------------------
+// _integrate_symplectic (symplectic.py:564-653): the extended state [Q,P,X,Y] is built ONCE and carried across the grid
+// (the centre-manifold map above rebuilds it every dt); the step of grid interval i is np.diff(t_values)[i], so omega,
+// the triple-jump sub-steps and their cos/sin are per-interval values (hb_tao_grid_prepare evaluates them with the host
+// libm).  _integrate_symplectic_until_event (:657-782): the same loop with a terminal plane event, refined by bisection
+// on the cubic Hermite interpolant of the step (_hermite_refine_event_symplectic :282-367).
+struct SympParams {
+    long long n;
+    const double *y0;      // [n][6] = [Q, P]
+    int m, n_sub;
+    const double *tab;     // [m-1][3][n_sub]: sub_ts, cos, sin of every grid interval
+    const double *t_vals;  // [m] signed grid (event mode)
+    double *traj;          // [n][m][6] or nullptr
+    int ev_idx, ev_dir;
+    double ev_off, xtol, gtol;
+    int *hit;              // event mode outputs
+    double *t_hit, *y_hit; // [n], [n][6]
+    int *n_rows;           // trajectory rows written (i + 1 at a hit, m otherwise)
+    HbWorkspace *ws;
+    const TermMeta *terms;
+    int ptr[7];
+    int n_terms;
+    int D;
+};
+
+HB_DEV double pick6c(const double (&v)[6], int i)
+{
+    return (i == 0) ? v[0] : (i == 1) ? v[1] : (i == 2) ? v[2] : (i == 3) ? v[3] : (i == 4) ? v[4] : v[5];
+}
+
+// _hermite_eval_dense_symplectic (symplectic.py:229-279)
+template <class AR>
+HB_DEV void hermite_eval6(const double (&y0)[6], const double (&f0)[6], const double (&y1)[6], const double (&f1)[6],
+                          double x, double h, double (&out)[6])
+{
+    const double x2 = AR::mul(x, x), x3 = AR::mul(x2, x);
+    const double H00 = AR::add(AR::sub(AR::mul(2.0, x3), AR::mul(3.0, x2)), 1.0);
+    const double H10 = AR::add(AR::sub(x3, AR::mul(2.0, x2)), x);
+    const double H01 = AR::add(AR::mul(-2.0, x3), AR::mul(3.0, x2));
+    const double H11 = AR::sub(x3, x2);
+#pragma unroll
+    for (int d = 0; d < 6; ++d)
+        out[d] = AR::add(AR::add(AR::add(AR::mul(H00, y0[d]), AR::mul(H10, AR::mul(h, f0[d]))), AR::mul(H01, y1[d])),
+                         AR::mul(H11, AR::mul(h, f1[d])));
+}
+
+template <class AR, bool EVENT>
+__global__ void __launch_bounds__(CM_BLOCK) k_symp_grid(const SympParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    TermMeta *terms = reinterpret_cast<TermMeta *>(smem);
+    double *pw_all = reinterpret_cast<double *>(smem + (((size_t)p.n_terms * sizeof(TermMeta) + 15) & ~(size_t)15));
+    for (int i = threadIdx.x; i < p.n_terms; i += CM_BLOCK) terms[i] = p.terms[i];
+    __syncthreads();
+    double *pw = pw_all + threadIdx.x;
+
+    for (;;) {
+        const long long idx = hb_fetch_index(p.ws);
+        if (idx >= p.n) break;
+        const double *s0 = p.y0 + idx * 6;
+        double Q[3], P[3], X[3], Y[3], yo[6], fo[6], g_old = 0.0;
+#pragma unroll
+        for (int d = 0; d < 6; ++d) yo[d] = s0[d];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { Q[i] = X[i] = yo[i]; P[i] = Y[i] = yo[3 + i]; }
+        double *rows = p.traj ? p.traj + idx * (long long)p.m * 6 : nullptr;
+        if (rows) {
+#pragma unroll
+            for (int d = 0; d < 6; ++d) rows[d] = yo[d];
+        }
+        if (EVENT) {
+            cm_rhs<AR>(p, pw, terms, yo, fo);            // _eval_hamiltonian_derivative (symplectic.py:181-226)
+            g_old = AR::sub(pick6c(yo, p.ev_idx), p.ev_off);
+        }
+        int hit = 0, n_rows = p.m;
+        double th = 0.0, yh[6];
+        for (int i = 0; i < p.m - 1; ++i) {
+            const double *tb = p.tab + (size_t)i * 3 * p.n_sub;
+            tao_update<AR>(p, pw, terms, tb, tb + p.n_sub, tb + 2 * p.n_sub, p.n_sub, Q, P, X, Y);
+            double yn[6] = {Q[0], Q[1], Q[2], P[0], P[1], P[2]};
+            if (EVENT) {
+                double fn[6];
+                cm_rhs<AR>(p, pw, terms, yn, fn);
+                const double g_new = AR::sub(pick6c(yn, p.ev_idx), p.ev_off);
+                if (hb_event_crossed(g_old, g_new, p.ev_dir)) {
+                    const double t0 = p.t_vals[i], h = AR::sub(p.t_vals[i + 1], t0);
+                    double a = 0.0, b = 1.0, g_left = g_old, xh = 1.0;
+                    bool done = false;
+                    for (int it = 0; it < 128; ++it) {
+                        const double mid = AR::mul(0.5, AR::add(a, b));
+                        hermite_eval6<AR>(yo, fo, yn, fn, mid, h, yh);
+                        const double g_mid = AR::sub(pick6c(yh, p.ev_idx), p.ev_off);
+                        if (fabs(g_mid) <= p.gtol) { xh = mid; done = true; break; }
+                        if (hb_crossed_direction(g_left, g_mid, p.ev_dir)) b = mid;
+                        else { a = mid; g_left = g_mid; }
+                        if (AR::mul(AR::sub(b, a), fabs(h)) <= p.xtol) break;
+                    }
+                    if (!done) { xh = b; hermite_eval6<AR>(yo, fo, yn, fn, b, h, yh); }
+                    th = AR::add(t0, AR::mul(xh, h));
+                    hit = 1;
+                    n_rows = i + 1;
+                    break;
+                }
+                g_old = g_new;
+#pragma unroll
+                for (int d = 0; d < 6; ++d) { yo[d] = yn[d]; fo[d] = fn[d]; }
+            }
+            if (rows) {
+                double *o = rows + (long long)(i + 1) * 6;
+#pragma unroll
+                for (int d = 0; d < 6; ++d) o[d] = yn[d];
+            }
+        }
+        if (EVENT) {
+            if (!hit) {
+                th = p.t_vals[p.m - 1];
+#pragma unroll
+                for (int d = 0; d < 6; ++d) yh[d] = yo[d];
+            }
+            p.hit[idx] = hit;
+            p.t_hit[idx] = th;
+            p.n_rows[idx] = n_rows;
+#pragma unroll
+            for (int d = 0; d < 6; ++d) p.y_hit[idx * 6 + d] = yh[d];
+        }
+    }
+}
+
+template <class AR, bool EVENT>
+int launch_symp(const SympParams &p, size_t smem, cudaStream_t st)
+{
+    auto kern = k_symp_grid<AR, EVENT>;
+    HB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int dev = 0, sms = 148, per_sm = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    HB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CM_BLOCK, smem));
+    if (per_sm < 1) per_sm = 1;
+    long long blocks = (p.n + CM_BLOCK - 1) / CM_BLOCK;
+    const long long cap = (long long)sms * per_sm;       // persistent: resident CTAs pull trajectories from the queue
+    if (blocks > cap) blocks = cap;
+    kern<<<(unsigned)blocks, CM_BLOCK, smem, st>>>(p);
+    HB_CUDA_TRY(cudaGetLastError());
+    return HB_OK;
+}
+
+int symp_common(const hb_polyham *ham, const hb_symp_opts *o, int64_t n, const double *y0, const double *tao_tab,
+                void *workspace, SympParams &p, size_t &smem)
+{
+    if (!ham || !o || !workspace || n < 0) return HB_ERR_BADARG;
+    if (ham->n_dof != 3 || ham->max_deg < 0 || ham->max_deg > 30) return HB_ERR_UNSUPPORTED;
+    if (o->order < 2 || (o->order % 2) != 0 || o->order > 8) return HB_ERR_UNSUPPORTED;
+    if (o->m < 2 || o->n_sub <= 0 || o->n_sub > HB_MAX_TAO_SUBSTEPS) return HB_ERR_BADARG;   // prepare not called
+    if (o->arith != HB_ARITH_PARITY && o->arith != HB_ARITH_FAST) return HB_ERR_BADARG;
+    if (n > 0 && (!y0 || !tao_tab || !ham->terms)) return HB_ERR_BADARG;
+    p.n = n; p.y0 = y0; p.m = o->m; p.n_sub = o->n_sub; p.tab = tao_tab;
+    p.ws = (HbWorkspace *)workspace;
+    p.terms = (const TermMeta *)ham->terms;
+    for (int i = 0; i < 7; ++i) p.ptr[i] = (int)ham->ptr[i];
+    p.n_terms = (int)ham->ptr[6];
+    p.D = ham->max_deg;
+    smem = (((size_t)p.n_terms * sizeof(TermMeta) + 15) & ~(size_t)15) + (size_t)6 * (p.D + 1) * CM_BLOCK * sizeof(double);
+    if (smem > 227 * 1024) return HB_ERR_UNSUPPORTED;
+    return HB_OK;
+}
+
 }  // namespace
 
 extern "C" int hb_cm_prepare(hb_cm_opts *o, double c_omega)
@@ -310,4 +487,65 @@ extern "C" int hb_cm_poincare_map(const hb_polyham *ham, const hb_cm_opts *opts,
                         (size_t)6 * (p.D + 1) * CM_BLOCK * sizeof(double);
     if (smem > 227 * 1024) return HB_ERR_UNSUPPORTED;
     return (opts->arith == HB_ARITH_PARITY) ? dispatch<ArParity>(p, smem, st) : dispatch<ArFast>(p, smem, st);
+}
+
+extern "C" int hb_tao_grid_prepare(const double *t_vals_signed, int32_t m, int32_t order, double c_omega,
+                                   int32_t *n_sub_out, double *tab, int64_t tab_capacity)
+{
+    if (!t_vals_signed || !n_sub_out || m < 2) return HB_ERR_BADARG;
+    if (order < 2 || (order % 2) != 0 || order > 8) return HB_ERR_UNSUPPORTED;
+    int n_sub = 1;
+    for (int k = order; k > 2; k -= 2) n_sub *= 3;
+    *n_sub_out = n_sub;
+    if (!tab) return HB_OK;                                            // size query
+    if (tab_capacity < (int64_t)(m - 1) * 3 * n_sub) return HB_ERR_BADARG;
+    hb_cm_opts o;
+    for (int i = 0; i < m - 1; ++i) {
+        const double dt = t_vals_signed[i + 1] - t_vals_signed[i];     // np.diff(t_values) (symplectic.py:642)
+        const double omega = std::pow(c_omega * dt, -(double)order);   // _get_tao_omega (symplectic.py:38-60)
+        o.n_sub = 0;
+        tao_schedule(dt, order, &o);
+        double *row = tab + (size_t)i * 3 * n_sub;
+        for (int j = 0; j < n_sub; ++j) {
+            row[j] = o.sub_ts[j];
+            row[n_sub + j] = std::cos(2 * omega * o.sub_ts[j]);
+            row[2 * n_sub + j] = std::sin(2 * omega * o.sub_ts[j]);
+        }
+    }
+    return HB_OK;
+}
+
+extern "C" int hb_ham_symplectic_dense(const hb_polyham *ham, const hb_symp_opts *opts, int64_t n, const double *y0,
+                                       const double *tao_tab, double *traj, void *workspace, void *stream)
+{
+    SympParams p{};
+    size_t smem = 0;
+    const int rc = symp_common(ham, opts, n, y0, tao_tab, workspace, p, smem);
+    if (rc != HB_OK) return rc;
+    if (n > 0 && !traj) return HB_ERR_BADARG;
+    if (n == 0) return HB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    HB_CUDA_TRY(cudaMemsetAsync(workspace, 0, sizeof(HbWorkspace), st));
+    p.traj = traj;
+    return (opts->arith == HB_ARITH_PARITY) ? launch_symp<ArParity, false>(p, smem, st) : launch_symp<ArFast, false>(p, smem, st);
+}
+
+extern "C" int hb_ham_symplectic_event(const hb_polyham *ham, const hb_symp_opts *opts, const hb_event *ev, int64_t n,
+                                       const double *y0, const double *t_vals_signed, const double *tao_tab,
+                                       double *traj, int32_t *hit, double *t_hit, double *y_hit, int32_t *n_rows,
+                                       void *workspace, void *stream)
+{
+    SympParams p{};
+    size_t smem = 0;
+    const int rc = symp_common(ham, opts, n, y0, tao_tab, workspace, p, smem);
+    if (rc != HB_OK) return rc;
+    if (!ev || ev->idx < 0 || ev->idx > 5) return HB_ERR_BADARG;
+    if (n > 0 && (!t_vals_signed || !hit || !t_hit || !y_hit || !n_rows)) return HB_ERR_BADARG;
+    if (n == 0) return HB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    HB_CUDA_TRY(cudaMemsetAsync(workspace, 0, sizeof(HbWorkspace), st));
+    p.traj = traj; p.t_vals = t_vals_signed;
+    p.ev_idx = ev->idx; p.ev_dir = ev->direction; p.ev_off = ev->offset; p.xtol = ev->xtol; p.gtol = ev->gtol;
+    p.hit = hit; p.t_hit = t_hit; p.y_hit = y_hit; p.n_rows = n_rows;
+    return (opts->arith == HB_ARITH_PARITY) ? launch_symp<ArParity, true>(p, smem, st) : launch_symp<ArFast, true>(p, smem, st);
 }

@@ -15,9 +15,11 @@ No reference file is edited.  What is rebound (paths relative to hiten/):
   * `_SynodicDetectionBackend.run` (algorithms/poincare/synodic/backend.py:823);
   * `_CenterManifoldBackend.run` (algorithms/poincare/centermanifold/backend.py:404);
   * `_DOP853.integrate` (algorithms/integrators/rk.py:2221), `_RK45.integrate` (:1138) and
-    `_FixedStepRK.integrate` (:422; _RK4 / _RK6 / _RK8) for the 6-state CR3BP system.
-Anything the GPU path cannot express (user-defined RHS or event callables, polynomial-Hamiltonian systems outside the
-centre-manifold map, 42-state RK45 / fixed-step integration, cubic synodic refinement) is handed to the reference's ORIGINAL function -- that is the reference's
+    `_FixedStepRK.integrate` (:422; _RK4 / _RK6 / _RK8) for the 6-state CR3BP system;
+  * `_ExtendedSymplectic.integrate` (algorithms/integrators/symplectic.py:877) for the polynomial Hamiltonian systems
+    (grid and plane-event forms; `_propagate_dynsys(method="symplectic")` builds this class).
+Anything the GPU path cannot express (user-defined RHS or event callables, RK integration of polynomial-Hamiltonian
+systems outside the centre-manifold map, 42-state RK45 / fixed-step integration, cubic synodic refinement) is handed to the reference's ORIGINAL function -- that is the reference's
 own code for inputs outside this path, not a fallback of the kernels: for recognised inputs a missing library
 or GPU raises.
 """
@@ -30,6 +32,7 @@ from . import centermanifold as _cm
 from . import connections as _conn
 from . import manifold as _man
 from . import propagate as _prop
+from . import symplectic as _symp
 from . import synodic as _syn
 
 _STATE = {"installed": False, "orig": {}, "patched_modules": [], "arith": "parity"}
@@ -407,6 +410,70 @@ def _make_synodic_run(orig):
 _TABLES = {}
 
 
+def _poly_table(jac_H, clmo):
+    """Sparse term table of a reference Hamiltonian (cached per jac_H / clmo object pair)."""
+    key = (id(jac_H), id(clmo))
+    if key not in _TABLES:
+        if len(_TABLES) > 16:
+            _TABLES.clear()
+        _TABLES[key] = (_cm.PolyTable.from_reference(jac_H, clmo), jac_H)
+    return _TABLES[key][0]
+
+
+def recognise_hamiltonian(system):
+    """-> (base _HamiltonianSystem, fwd) for a 3-dof polynomial Hamiltonian system (possibly wrapped by
+    _DirectedSystem), else None."""
+    from hiten.algorithms.dynamics.base import _DirectedSystem
+    from hiten.algorithms.dynamics.hamiltonian import _HamiltonianSystem
+    base, fwd = system, 1
+    if isinstance(system, _DirectedSystem):
+        base, fwd = system._base, int(system._fwd)
+    if type(base) is _HamiltonianSystem and base.n_dof == 3:
+        return base, fwd
+    return None
+
+
+def _make_symplectic_integrate(orig):
+    """_ExtendedSymplectic.integrate (algorithms/integrators/symplectic.py:877-1004) for the reference's polynomial
+    Hamiltonian systems: grid integration (hb_ham_symplectic_dense) and recognised plane events
+    (hb_ham_symplectic_event).  `_propagate_dynsys(method="symplectic")` follows because it builds this class
+    (dynamics/base.py:436-444) -- including its double application of the direction sign to the returned times."""
+    def integrate(self, system, y0, t_vals, *, event_fn=None, event_cfg=None, event_options=None, **kwargs):
+        from hiten.algorithms.integrators.types import _Solution
+        rec = recognise_hamiltonian(system)
+        ev = recognise_event(event_fn) if event_fn is not None else None
+        if rec is None or (event_fn is not None and ev is None) or not 2 <= int(self._order) <= 8:
+            return orig(self, system, y0, t_vals, event_fn=event_fn, event_cfg=event_cfg,
+                        event_options=event_options, **kwargs)
+        self.validate_inputs(system, y0, t_vals)
+        t_vals = np.asarray(t_vals, dtype=np.float64)
+        if not np.all(np.diff(t_vals) != 0.0):
+            return orig(self, system, y0, t_vals, event_fn=event_fn, event_cfg=event_cfg,
+                        event_options=event_options, **kwargs)
+        base, fwd = rec
+        y0 = np.asarray(y0, dtype=np.float64)
+        table = _poly_table(base.jac_H, base.clmo_H)
+        t_int = t_vals if fwd == 1 else t_vals * (-1.0)                      # symplectic.py:963
+        if ev is None:
+            traj = _symp.integrate_symplectic(table, y0[None, :], t_int, self._order,
+                                              c_omega_heuristic=self.c_omega_heuristic, arith=_STATE["arith"])[0]
+            return _Solution(times=t_vals.copy() * fwd, states=traj)
+        event = (ev[0], ev[1], 0 if event_cfg is None else int(event_cfg.direction),
+                 float(event_options.xtol if event_options is not None else 1.0e-12),
+                 float(event_options.gtol if event_options is not None else 1.0e-12))
+        r = _symp.integrate_symplectic_until_event(table, y0[None, :], t_int, self._order, event,
+                                                   c_omega_heuristic=self.c_omega_heuristic, arith=_STATE["arith"],
+                                                   want_trajectory=True)
+        if bool(r.hit[0]):
+            return _Solution(times=np.array([t_vals[0], float(r.t_hit[0]) * fwd], dtype=np.float64),
+                             states=np.vstack([y0, r.y_hit[0]]))
+        return _Solution(times=t_vals.copy() * fwd, states=r.traj[0])
+
+    integrate.__wrapped__ = orig
+    integrate.__doc__ = orig.__doc__
+    return integrate
+
+
 def _make_cm_run(orig):
     def run(self, request):
         from hiten.algorithms.poincare.centermanifold.types import CenterManifoldBackendResponse
@@ -416,12 +483,7 @@ def _make_cm_run(orig):
                                                  flags=np.empty((0,), dtype=np.int64), metadata={})
         if request.method == "adaptive":
             raise NotImplementedError("Adaptive integrator is not implemented in CM backend; use 'fixed' (RK) or 'symplectic'.")
-        key = (id(request.jac_H), id(request.clmo_table))
-        if key not in _TABLES:
-            if len(_TABLES) > 16:
-                _TABLES.clear()
-            _TABLES[key] = (_cm.PolyTable.from_reference(request.jac_H, request.clmo_table), request.jac_H)
-        table = _TABLES[key][0]
+        table = _poly_table(request.jac_H, request.clmo_table)
         opts = _cm.make_opts(request.dt, request.max_steps, "symplectic" if request.method == "symplectic" else "fixed",
                              request.order, request.section_coord, request.c_omega_heuristic, _STATE["arith"])
         flags, out, tt = _cm.poincare_map(table, np.ascontiguousarray(seeds, dtype=np.float64), opts)
@@ -520,6 +582,7 @@ def install(arith="parity", corrector="reference"):
     import hiten.algorithms.dynamics.base as dbase
     from hiten.algorithms.connections.backends import _ConnectionsBackend
     from hiten.algorithms.integrators.rk import _DOP853, _RK45, _FixedStepRK
+    from hiten.algorithms.integrators.symplectic import _ExtendedSymplectic
     from hiten.algorithms.poincare.centermanifold.backend import _CenterManifoldBackend
     from hiten.algorithms.poincare.synodic.backend import _SynodicDetectionBackend
     from hiten.algorithms.types.services.manifold import _ManifoldDynamicsService
@@ -538,6 +601,7 @@ def install(arith="parity", corrector="reference"):
         "dop853": _DOP853.integrate,
         "rk45": _RK45.integrate,
         "fixed_rk": _FixedStepRK.integrate,
+        "symplectic": _ExtendedSymplectic.integrate,
         "run_compute": _ManifoldDynamicsService._run_compute,
         "synodic": _SynodicDetectionBackend.run,
         "cm": _CenterManifoldBackend.run,
@@ -546,6 +610,7 @@ def install(arith="parity", corrector="reference"):
     _DOP853.integrate = _make_dop853_integrate(_STATE["orig"]["dop853"])
     _RK45.integrate = _make_rk_integrate(_STATE["orig"]["rk45"], "rk45")
     _FixedStepRK.integrate = _make_rk_integrate(_STATE["orig"]["fixed_rk"], "fixed")
+    _ExtendedSymplectic.integrate = _make_symplectic_integrate(_STATE["orig"]["symplectic"])
     _ManifoldDynamicsService._run_compute = _make_run_compute(_STATE["orig"]["run_compute"])
     _SynodicDetectionBackend.run = _make_synodic_run(_STATE["orig"]["synodic"])
     _CenterManifoldBackend.run = _make_cm_run(_STATE["orig"]["cm"])
@@ -571,6 +636,8 @@ def uninstall():
     from hiten.algorithms.integrators.rk import _RK45, _FixedStepRK
     _RK45.integrate = o["rk45"]
     _FixedStepRK.integrate = o["fixed_rk"]
+    from hiten.algorithms.integrators.symplectic import _ExtendedSymplectic
+    _ExtendedSymplectic.integrate = o["symplectic"]
     _ManifoldDynamicsService._run_compute = o["run_compute"]
     _SynodicDetectionBackend.run = o["synodic"]
     _CenterManifoldBackend.run = o["cm"]

@@ -250,6 +250,37 @@ int hb_cm_poincare_map_jit(const hb_polyham *ham, const hb_cm_opts *opts, int64_
 int hb_cm_jit_compile_host(const void *terms_host, const int64_t *ptr, int32_t max_deg, const hb_cm_opts *opts,
                            int64_t *cubin_bytes, char *source_out, int64_t source_cap);
 
+/* ---- _ExtendedSymplectic.integrate (algorithms/integrators/symplectic.py:877-1004; reached from
+ * _propagate_dynsys(method="symplectic"), algorithms/dynamics/base.py:436-444): the Tao integrator of a polynomial
+ * Hamiltonian system over a TIME GRID, for a batch of initial states that share the grid. ------------------------- */
+typedef struct {
+    int32_t order;   /* 2, 4, 6, 8                                                          */
+    int32_t arith;   /* HB_ARITH_*                                                          */
+    int32_t m;       /* grid points (>= 2, integrators/base.py:183)                         */
+    int32_t n_sub;   /* order-2 Tao kernels per grid interval: from hb_tao_grid_prepare     */
+} hb_symp_opts;
+
+/* Host-only, needs no GPU.  t_vals_signed[m] is the grid the low-level routine sees (t_vals * fwd, symplectic.py:963).
+ * For every grid interval: dt = t[i+1] - t[i], omega = (c_omega*dt)^-order (_get_tao_omega :38-60), the triple-jump
+ * schedule of _recursive_update_poly (:543-560) and cos / sin(2*omega*ts) with the host libm, exactly as the reference
+ * evaluates them per step.  tab[(m-1)][3][n_sub] = {ts[], cos[], sin[]}; tab == NULL only returns *n_sub.      */
+int hb_tao_grid_prepare(const double *t_vals_signed, int32_t m, int32_t order, double c_omega, int32_t *n_sub,
+                        double *tab, int64_t tab_capacity);
+
+/* _integrate_symplectic (symplectic.py:564-653): y0[n][6] = [Q, P] -> traj[n][m][6] (row 0 = y0); the extended state
+ * [Q,P,X,Y] is carried across the grid.  tao_tab is the DEVICE copy of hb_tao_grid_prepare's table.  Bit-identical to the
+ * reference in the parity variant.                                                                              */
+int hb_ham_symplectic_dense(const hb_polyham *ham, const hb_symp_opts *opts, int64_t n, const double *y0,
+                            const double *tao_tab, double *traj, void *workspace, void *stream);
+
+/* _integrate_symplectic_until_event (symplectic.py:657-782) with the plane event g = y[idx] - offset, refined by
+ * bisection on the step's cubic Hermite interpolant (_hermite_refine_event_symplectic :282-367).  hit[i] = 1: t_hit[i]
+ * (on the signed grid) / y_hit[i][6] are the refined event, n_rows[i] the trajectory rows before it; hit[i] = 0:
+ * t_hit = t_vals[m-1], y_hit = last state, n_rows = m.  traj[n][m][6] may be NULL (rows past the event are untouched). */
+int hb_ham_symplectic_event(const hb_polyham *ham, const hb_symp_opts *opts, const hb_event *ev, int64_t n,
+                            const double *y0, const double *t_vals_signed, const double *tao_tab, double *traj,
+                            int32_t *hit, double *t_hit, double *y_hit, int32_t *n_rows, void *workspace, void *stream);
+
 /* Seed lifting for the centre-manifold map: replaces the per-seed Python Brent solves of
  * _CenterManifoldInterface.lift_plane_point / solve_missing_coord (algorithms/poincare/centermanifold/
  * interfaces.py:297-337, 212-268; solve_bracketed_brent algorithms/utils/rootfinding.py:92-190) that the seeding

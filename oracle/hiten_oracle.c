@@ -715,6 +715,60 @@ int ho_fixed_event(const ho_system *sys, int method, const ho_event *ev, const d
     return 0;
 }
 
+/* ---- _ExtendedSymplectic.integrate (symplectic.py:877-1004) --------------------------------------------------- */
+/* _integrate_symplectic (symplectic.py:564-653) */
+int ho_symplectic_dense(const ho_polyham *ham, const double *y0, const double *t_vals, int m, int order,
+                        double c_omega, double *traj)
+{
+    if (m < 1 || order < 2 || (order % 2) != 0) return -1;
+    double q[12];
+    memcpy(traj, y0, 6 * sizeof(double));
+    memcpy(q, y0, 6 * sizeof(double));
+    memcpy(q + 6, y0, 6 * sizeof(double));
+    for (int i = 0; i < m - 1; ++i) {
+        const double dt = t_vals[i + 1] - t_vals[i];                  /* np.diff(t_values) */
+        ho_tao_update(ham, q, dt, order, c_omega);
+        memcpy(traj + (size_t)(i + 1) * 6, q, 6 * sizeof(double));
+    }
+    return 0;
+}
+
+/* _integrate_symplectic_until_event (symplectic.py:657-782) */
+int ho_symplectic_event(const ho_polyham *ham, const ho_event *ev, const double *y0, const double *t_vals, int m,
+                        int order, double c_omega, double *t_hit, double *y_hit, double *traj, int *n_rows)
+{
+    if (m < 1 || order < 2 || (order % 2) != 0) return -1;
+    double q[12], y_old[6], y_new[6], f_old[6], f_new[6];
+    memcpy(y_old, y0, sizeof y_old);
+    if (traj) memcpy(traj, y0, 6 * sizeof(double));
+    ho_polyham_rhs(ham, y_old, f_old);                                 /* _eval_hamiltonian_derivative :181-226 */
+    double g_old = ev_g(ev, y_old);
+    memcpy(q, y0, 6 * sizeof(double));
+    memcpy(q + 6, y0, 6 * sizeof(double));
+    for (int i = 0; i < m - 1; ++i) {
+        const double dt = t_vals[i + 1] - t_vals[i];
+        ho_tao_update(ham, q, dt, order, c_omega);
+        memcpy(y_new, q, sizeof y_new);
+        ho_polyham_rhs(ham, y_new, f_new);
+        const double g_new = ev_g(ev, y_new);
+        if (event_crossed(g_old, g_new, ev->direction)) {
+            dense_ctx c; memset(&c, 0, sizeof c);
+            c.kind = 2; c.n = 6; c.y0 = y_old; c.f0 = f_old; c.y1 = y_new; c.f1 = f_new; c.h = dt;
+            refine_in_step(&c, ev, t_vals[i], t_hit, y_hit);
+            *n_rows = i + 1;
+            return 1;
+        }
+        if (traj) memcpy(traj + (size_t)(i + 1) * 6, y_new, sizeof y_new);
+        memcpy(y_old, y_new, sizeof y_old);
+        memcpy(f_old, f_new, sizeof f_old);
+        g_old = g_new;
+    }
+    *t_hit = t_vals[m - 1];
+    memcpy(y_hit, y_old, sizeof y_old);
+    *n_rows = m;
+    return 0;
+}
+
 /* ===================================================================================== */
 /* Batch drivers (pthreads; a shared atomic cursor hands out trajectories)                */
 /* ===================================================================================== */

@@ -100,6 +100,13 @@ static void tao_recursive(const ho_polyham *ham, double *q, double ts, int order
         tao_recursive(ham, q, gamma * ts, order - 2, omega);
     }
 }
+/* one _recursive_update_poly call on an extended state q_ext[12] = [Q,P,X,Y] (symplectic.py:509-560); exported for the
+ * grid / event drivers of _ExtendedSymplectic.integrate in hiten_oracle.c */
+void ho_tao_update(const ho_polyham *ham, double *q_ext, double dt, int order, double c_omega)
+{
+    const double omega = pow(c_omega * dt, -(double)order);     /* _get_tao_omega (symplectic.py:38-60) */
+    tao_recursive(ham, q_ext, dt, order, omega);
+}
 /* _integrate_symplectic over t_vals = [0, dt]  (symplectic.py:636-652) */
 static void tao_step(const ho_polyham *ham, const double *y, double dt, int order, double c_omega, double *y_new)
 {

@@ -22,6 +22,19 @@ struct ho_polyham {
 double ho_poly_eval_partial(const ho_polyham *ham, int p, const double *point6);
 void ho_polyham_rhs(const ho_polyham *ham, const double *y, double *dy);   /* dynamics/hamiltonian.py:35-90 */
 
+void ho_tao_update(const ho_polyham *ham, double *q_ext, double dt, int order, double c_omega);
+
+/* _ExtendedSymplectic.integrate (algorithms/integrators/symplectic.py:877-1004) on the SIGNED grid t_vals[m] the
+ * low-level routines see (t_vals * fwd): _integrate_symplectic (:564-653) -> traj[m][6]; the extended state is carried
+ * across the grid. */
+int ho_symplectic_dense(const ho_polyham *ham, const double *y0, const double *t_vals, int m, int order,
+                        double c_omega, double *traj);
+/* _integrate_symplectic_until_event (:657-782) + _hermite_refine_event_symplectic (:282-367).  Returns 1 on a hit
+ * (t_hit / y_hit refined, *n_rows = trajectory rows written before the event) or 0 (t_hit = t_vals[m-1], y_hit = last
+ * row, *n_rows = m).  traj[m][6] may be NULL. */
+int ho_symplectic_event(const ho_polyham *ham, const ho_event *ev, const double *y0, const double *t_vals, int m,
+                        int order, double c_omega, double *t_hit, double *y_hit, double *traj, int *n_rows);
+
 /* _poincare_map (algorithms/poincare/centermanifold/backend.py:314-382): seeds[n][4] = (q2,p2,q3,p3);
  * section: 0 q2, 1 p2, 2 q3, 3 p3; out[n][4], t_out[n], flags[n] (int64). */
 int ho_cm_poincare_map(const ho_polyham *ham, const double *seeds, int64_t n, double dt, int order, int max_steps,

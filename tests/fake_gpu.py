@@ -115,6 +115,28 @@ def correct_orbits(x0, mu, opts, **kw):
     return CorrectionBatch(xc, half, it, rn, st, 0, 0)
 
 
+def integrate_symplectic(table, y0, t_vals_signed, order, *, c_omega_heuristic=20.0, **kw):
+    ham = O.PolyHam(table.ptr, table.deg, table.coef, table.exp)
+    return np.stack([O.symplectic_dense(ham, y, t_vals_signed, order, c_omega_heuristic) for y in np.asarray(y0)])
+
+
+def integrate_symplectic_until_event(table, y0, t_vals_signed, order, event, *, c_omega_heuristic=20.0,
+                                     want_trajectory=False, **kw):
+    from hiten_b200.symplectic import SymplecticEventResult
+    ham = O.PolyHam(table.ptr, table.deg, table.coef, table.exp)
+    idx, offset, direction, xtol, gtol = event
+    ev = O.HoEvent(int(idx), float(offset), int(direction), xtol, gtol)
+    y0 = np.asarray(y0)
+    m = len(t_vals_signed)
+    hit, th, yh, nr, traj = np.zeros(len(y0), bool), np.zeros(len(y0)), np.zeros((len(y0), 6)), \
+        np.zeros(len(y0), np.int64), np.zeros((len(y0), m, 6))
+    for i in range(len(y0)):
+        hit[i], th[i], yh[i], rows = O.symplectic_event(ham, ev, y0[i], t_vals_signed, order, c_omega_heuristic)
+        nr[i] = len(rows)
+        traj[i, : len(rows)] = rows
+    return SymplecticEventResult(hit, th, yh, nr, traj if want_trajectory else None)
+
+
 def patch(monkeypatch):
     import hiten_b200.corrector as corr
     monkeypatch.setattr(corr, "correct_orbits", correct_orbits)
@@ -129,5 +151,8 @@ def patch(monkeypatch):
     monkeypatch.setattr(prop, "cr3bp_event", cr3bp_event)
     monkeypatch.setattr(syn, "detect", detect)
     monkeypatch.setattr(cm, "poincare_map", poincare_map)
+    import hiten_b200.symplectic as symp
+    monkeypatch.setattr(symp, "integrate_symplectic", integrate_symplectic)
+    monkeypatch.setattr(symp, "integrate_symplectic_until_event", integrate_symplectic_until_event)
     import hiten_b200.connections as conn
     monkeypatch.setattr(conn, "find_connections", find_connections)

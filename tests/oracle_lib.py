@@ -211,6 +211,31 @@ def cm_poincare_map(ham, seeds, dt, order, max_steps, use_symplectic, section, c
     return flags, out, tt
 
 
+def symplectic_dense(ham, y0, t_vals_signed, order, c_omega=20.0):
+    """_integrate_symplectic on the signed grid (t_vals * fwd): traj[m][6]."""
+    y0 = np.ascontiguousarray(y0, dtype=np.float64)
+    t = np.ascontiguousarray(t_vals_signed, dtype=np.float64)
+    out = np.empty((t.size, 6))
+    rc = lib().ho_symplectic_dense(C.byref(ham.struct), _p(y0), _p(t), int(t.size), int(order), C.c_double(c_omega),
+                                   _p(out))
+    assert rc == 0
+    return out
+
+
+def symplectic_event(ham, ev, y0, t_vals_signed, order, c_omega=20.0):
+    """_integrate_symplectic_until_event: (hit, t_hit (signed-grid time), y_hit[6], traj[n_rows][6])."""
+    y0 = np.ascontiguousarray(y0, dtype=np.float64)
+    t = np.ascontiguousarray(t_vals_signed, dtype=np.float64)
+    traj = np.zeros((t.size, 6))
+    th = C.c_double(0.0)
+    yh = np.empty(6)
+    nr = C.c_int(0)
+    hit = lib().ho_symplectic_event(C.byref(ham.struct), C.byref(ev), _p(y0), _p(t), int(t.size), int(order),
+                                    C.c_double(c_omega), C.byref(th), _p(yh), _p(traj), C.byref(nr))
+    assert hit in (0, 1)
+    return bool(hit), th.value, yh, traj[: nr.value]
+
+
 def batch_synodic_count(times, dense, idx, offset, direction, proj, segment_refine, tol_on_surface, dedup_time_tol,
                         dedup_point_tol, n_threads=1):
     """Total hit count over a uniformly sampled batch dense[N, m, dim] (bench.py CPU legs)."""

@@ -3,6 +3,7 @@ import ctypes
 import os
 import re
 
+import numpy as np
 import pytest
 
 import hiten_b200
@@ -121,3 +122,41 @@ def test_argument_validation_needs_no_gpu():
                                  None, None, None, 0, (C.c_char * 256)(), None) == -1
     with pytest.raises(ValueError):
         corrector.make_opts(control_indices=(0, 4, 5), residual_indices=(3, 5), event_idx=1)
+
+
+def test_tao_grid_table_is_host_only_and_matches_the_reference_formulas():
+    """hb_tao_grid_prepare (no GPU): per-interval omega = (c*dt)^-order (symplectic.py:38-60), the triple-jump sub-steps of
+    _recursive_update_poly (:543-560) and cos / sin(2*omega*ts), for ascending and descending (fwd = -1) grids."""
+    import math
+    from hiten_b200 import symplectic as S
+    t = np.linspace(0.5, 2.5, 41)
+    for order, n_expect in ((2, 1), (4, 3), (6, 9), (8, 27)):
+        for sign in (1.0, -1.0):
+            n_sub, tab = S.tao_grid_table(t * sign, order, 20.0)
+            assert n_sub == n_expect and tab.shape == (40, 3, n_expect)
+            dts = np.diff(t * sign)
+
+            def sched(ts, k):
+                if k == 2:
+                    return [ts]
+                gam = 1.0 / (2.0 - 2.0 ** (1.0 / (float(k) + 1.0)))
+                return sched(gam * ts, k - 2) + sched((1.0 - 2.0 * gam) * ts, k - 2) + sched(gam * ts, k - 2)
+            for i in (0, 17, 39):
+                ts = sched(float(dts[i]), order)
+                omega = (20.0 * float(dts[i])) ** (-float(order))
+                assert tab[i, 0].tolist() == ts
+                assert tab[i, 1].tolist() == [math.cos(2 * omega * x) for x in ts]
+                assert tab[i, 2].tolist() == [math.sin(2 * omega * x) for x in ts]
+    with pytest.raises(ValueError):
+        S.tao_grid_table([0.0], 4)
+    with pytest.raises(ValueError):
+        S.tao_grid_table([0.0, 1.0], 3)
+    lib, C = _lib.load(), ctypes
+    ham = _lib.HbPolyHam(3, 6, (C.c_int64 * 7)(0, 0, 0, 0, 0, 0, 0), None)
+    o = _lib.HbSympOpts(4, 0, 10, 0)                                     # n_sub = 0: prepare was not called
+    assert lib.hb_ham_symplectic_dense(C.byref(ham), C.byref(o), 4, None, None, None, None, None) < 0
+    o.n_sub = 3
+    assert lib.hb_ham_symplectic_dense(C.byref(ham), C.byref(o), 4, None, None, None, None, None) < 0   # no workspace
+    ev = _lib.HbEvent(9, 0, 0.0, 1e-12, 1e-12)                           # component 9 does not exist
+    assert lib.hb_ham_symplectic_event(C.byref(ham), C.byref(o), C.byref(ev), 0, None, None, None, None, None, None, None,
+                                       None, None, None) < 0

@@ -266,3 +266,65 @@ def test_rk45_and_fixed_step_classes_and_propagate_variants(ref, monkeypatch):
     for k in want:
         assert np.array_equal(got[k][0], want[k][0]), k
         assert np.array_equal(got[k][1], want[k][1]), k
+
+
+def test_symplectic_class_and_propagate_symplectic(ref, monkeypatch):
+    """_ExtendedSymplectic.integrate (grid + plane events, both time directions) and
+    _propagate_dynsys(method="symplectic") with the drop-in: the same arrays as the reference alone, bit for bit --
+    including the reference's double application of the direction sign to the times of a backward propagation."""
+    import fake_gpu
+    import hiten_b200
+    import hiten.algorithms.dynamics.base as dbase
+    from hiten.algorithms.dynamics.base import _DirectedSystem
+    from hiten.algorithms.integrators.symplectic import _ExtendedSymplectic
+    from hiten.algorithms.poincare.singlehit.backend import _get_cached_plane_event_fn
+    from hiten.algorithms.types.configs import EventConfig
+    system, l1, halo = ref
+    cm = l1.get_center_manifold(degree=6)
+    cm.compute()
+    hamsys = cm.poincare_map(energy=0.7).dynamics.hamsys
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "symplectic.npz"))
+    y0 = g["y0"][1]
+    fn = _get_cached_plane_event_fn(2, 0.0)
+
+    def run_all():
+        out = {}
+        for order, fwd in ((4, 1), (2, -1), (6, 1)):
+            integ = _ExtendedSymplectic(order=order)
+            sol = integ.integrate(_DirectedSystem(hamsys, fwd), y0.copy(), np.linspace(0.0, 1.0, 81))
+            out[f"grid{order}{fwd}"] = (sol.times.copy(), sol.states.copy())
+            ev = integ.integrate(_DirectedSystem(hamsys, fwd), y0.copy(), np.linspace(0.0, 6.0, 601), event_fn=fn,
+                                 event_cfg=EventConfig(direction=0, terminal=True))
+            out[f"event{order}{fwd}"] = (ev.times.copy(), ev.states.copy())
+        nohit = _ExtendedSymplectic(order=4).integrate(hamsys, y0.copy(), np.linspace(0.0, 0.05, 6),
+                                                       event_fn=_get_cached_plane_event_fn(2, 10.0),
+                                                       event_cfg=EventConfig(direction=0, terminal=True))
+        out["nohit"] = (nohit.times.copy(), nohit.states.copy())
+        for fwd in (1, -1):
+            sol = dbase._propagate_dynsys(hamsys, y0.copy(), 0.0, 1.0, forward=fwd, steps=41, method="symplectic", order=4)
+            out[f"prop{fwd}"] = (sol.times.copy(), sol.states.copy())
+        return out
+
+    want = run_all()
+    hiten_b200.install()
+    fake_gpu.patch(monkeypatch)
+    calls = []
+    import hiten_b200.symplectic as symp
+    d0, e0 = symp.integrate_symplectic, symp.integrate_symplectic_until_event
+    monkeypatch.setattr(symp, "integrate_symplectic", lambda *a, **k: (calls.append("grid"), d0(*a, **k))[1])
+    monkeypatch.setattr(symp, "integrate_symplectic_until_event", lambda *a, **k: (calls.append("event"), e0(*a, **k))[1])
+    try:
+        got = run_all()
+        # a user-defined event callable is not expressible on the GPU path: the reference's own method runs
+        n_before = len(calls)
+        _ExtendedSymplectic(order=4).integrate(hamsys, y0.copy(), np.linspace(0.0, 0.1, 11),
+                                               event_fn=lambda t, y: y[2] - 10.0,
+                                               event_cfg=EventConfig(direction=0, terminal=True))
+        assert len(calls) == n_before
+    finally:
+        hiten_b200.uninstall()
+    assert calls.count("grid") == 5 and calls.count("event") == 4
+    assert want["prop-1"][0][-1] > 0                                      # the reference's sign quirk
+    for k in want:
+        assert np.array_equal(got[k][0], want[k][0]), k
+        assert np.array_equal(got[k][1], want[k][1]), k
