@@ -203,6 +203,22 @@ def secondary_configs(hb, torch, steps, flush, barrier):
                       "ms_per_return": 1e3 * t / steps, "tflops": cm_steps * steps * 8100.0 / t / 1e12}
     out["cm_map_tao4_1e5_seeds"]["note"] = ("critical-path bound: the slowest seed needs ~1300 sequential steps of "
                                             "~20 us; 1e6 seeds fill the machine")
+    # the Tao integrator CLASS over a time grid (_ExtendedSymplectic.integrate): 1e5 trajectories x 100 grid intervals
+    from hiten_b200 import symplectic as symp
+    y6 = torch.zeros((100_000, 6), dtype=torch.float64, device="cuda")
+    sd = torch.from_numpy(g["seeds_p3"][rng.integers(0, 512, 100_000)]).cuda()
+    y6[:, 1], y6[:, 4], y6[:, 2], y6[:, 5] = sd[:, 0], sd[:, 1], sd[:, 2], sd[:, 3]
+    tg = np.linspace(0.0, 1.0, 101)
+
+    def run_symp():
+        hold["s"] = symp.integrate_symplectic(tab, y6, tg, 4)
+
+    for _ in range(3):
+        run_symp()
+    t = time_steps(run_symp, steps, flush, barrier, torch)
+    out["tao4_grid_1e5_trajectories_x_100_intervals"] = {
+        "steps_per_s": 1e7 * steps / t, "ms": 1e3 * t / steps, "tflops": 1e7 * steps * 12 * 610.0 / t / 1e12,
+        "note": "table-driven gradient (API-parity path); 12 gradient evaluations per Tao-4 step"}
     # BASELINE configs[0] / [1] as they are (50 / 200 trajectories): small-batch latency, not throughput
     from hiten_b200 import synodic as syn
     c1 = np.load(os.path.join(REPO, "tests", "golden", "c1_manifold.npz"))
