@@ -292,6 +292,7 @@ struct SympParams {
     const double *tab;     // [m-1][3][n_sub]: sub_ts, cos, sin of every grid interval
     const double *t_vals;  // [m] signed grid (event mode)
     double *traj;          // [n][m][6] or nullptr
+    double *derivs;        // [n][m][6] or nullptr (fixed-step RK grid form: _Solution.derivatives)
     int ev_idx, ev_dir;
     double ev_off, xtol, gtol;
     int *hit;              // event mode outputs
@@ -407,10 +408,111 @@ __global__ void __launch_bounds__(CM_BLOCK) k_symp_grid(const SympParams p)
     }
 }
 
-template <class AR, bool EVENT>
-int launch_symp(const SympParams &p, size_t smem, cudaStream_t st)
+// ---- _FixedStepRK.integrate on a polynomial Hamiltonian system: the `_ham` kernels of the RK classes ---------------
+// _integrate_fixed_rk_ham (rk.py:592-656: states AND derivatives on the grid, step h = t[i+1] - t[i]) and
+// _integrate_fixed_rk_until_event_ham (:722-757) with _hermite_refine_in_step (:331-391); stage loop
+// rk_embedded_step_ham_jit_kernel (:216-270).  The `_ham` kernels take system.rhs_params and never see a direction
+// wrapper (golden vectors: tests/golden/ham_rk.npz), so there is no direction argument here.
+template <class AR>
+struct SympRhs {
+    const SympParams &p;
+    double *pw;
+    const TermMeta *terms;
+    HB_DEV void operator()(const double (&y)[6], double (&dy)[6]) const { cm_rhs<AR>(p, pw, terms, y, dy); }
+};
+
+template <class AR, class TAB, bool EVENT>
+__global__ void __launch_bounds__(CM_BLOCK) k_ham_rk_grid(const SympParams p)
 {
-    auto kern = k_symp_grid<AR, EVENT>;
+    extern __shared__ __align__(16) unsigned char smem[];
+    TermMeta *terms = reinterpret_cast<TermMeta *>(smem);
+    double *pw_all = reinterpret_cast<double *>(smem + (((size_t)p.n_terms * sizeof(TermMeta) + 15) & ~(size_t)15));
+    for (int i = threadIdx.x; i < p.n_terms; i += CM_BLOCK) terms[i] = p.terms[i];
+    __syncthreads();
+    double *pw = pw_all + threadIdx.x;
+    const SympRhs<AR> rhs{p, pw, terms};
+
+    for (;;) {
+        const long long idx = hb_fetch_index(p.ws);
+        if (idx >= p.n) break;
+        const double *s0 = p.y0 + idx * 6;
+        double y[6], fp[6], yn[6], fn[6], g_prev = 0.0;
+#pragma unroll
+        for (int d = 0; d < 6; ++d) y[d] = s0[d];
+        rhs(y, fp);
+        double *rows = p.traj ? p.traj + idx * (long long)p.m * 6 : nullptr;
+        double *drows = p.derivs ? p.derivs + idx * (long long)p.m * 6 : nullptr;
+#pragma unroll
+        for (int d = 0; d < 6; ++d) {
+            if (rows) rows[d] = y[d];
+            if (drows) drows[d] = fp[d];
+        }
+        if (EVENT) g_prev = AR::sub(pick6c(y, p.ev_idx), p.ev_off);
+        int hit = 0, n_rows = p.m;
+        double th = 0.0, yh[6];
+        for (int i = 0; i < p.m - 1; ++i) {
+            const double tn = p.t_vals[i], h = AR::sub(p.t_vals[i + 1], tn);
+            double k[TAB::S][6];
+#pragma unroll
+            for (int d = 0; d < 6; ++d) k[0][d] = fp[d];
+            g_run_stages<AR, TAB, SympRhs<AR>, 1>(rhs, y, k, h);
+#pragma unroll
+            for (int d = 0; d < 6; ++d) yn[d] = y[d];
+            g_high_acc<AR, TAB, 0>(yn, k, h);
+            rhs(yn, fn);
+            if (EVENT) {
+                const double g_new = AR::sub(pick6c(yn, p.ev_idx), p.ev_off);
+                if (hb_event_crossed(g_prev, g_new, p.ev_dir)) {
+                    double a = 0.0, b = 1.0, g_left = g_prev, xh = 1.0;
+                    bool done = false;
+                    for (int it = 0; it < 128; ++it) {
+                        const double mid = AR::mul(0.5, AR::add(a, b));
+                        hermite_eval6<AR>(y, fp, yn, fn, mid, h, yh);
+                        const double g_mid = AR::sub(pick6c(yh, p.ev_idx), p.ev_off);
+                        if (fabs(g_mid) <= p.gtol) { xh = mid; done = true; break; }
+                        if (hb_crossed_direction(g_left, g_mid, p.ev_dir)) b = mid;
+                        else { a = mid; g_left = g_mid; }
+                        if (AR::mul(AR::sub(b, a), fabs(h)) <= p.xtol) break;
+                    }
+                    if (!done) { xh = b; hermite_eval6<AR>(y, fp, yn, fn, b, h, yh); }
+                    th = AR::add(tn, AR::mul(xh, h));
+                    hit = 1;
+                    n_rows = i + 1;
+                    break;
+                }
+                g_prev = g_new;
+            }
+#pragma unroll
+            for (int d = 0; d < 6; ++d) { y[d] = yn[d]; fp[d] = fn[d]; }
+            if (rows) {
+                double *o = rows + (long long)(i + 1) * 6;
+#pragma unroll
+                for (int d = 0; d < 6; ++d) o[d] = y[d];
+            }
+            if (drows) {
+                double *o = drows + (long long)(i + 1) * 6;
+#pragma unroll
+                for (int d = 0; d < 6; ++d) o[d] = fp[d];
+            }
+        }
+        if (EVENT) {
+            if (!hit) {
+                th = p.t_vals[p.m - 1];
+#pragma unroll
+                for (int d = 0; d < 6; ++d) yh[d] = y[d];
+            }
+            p.hit[idx] = hit;
+            p.t_hit[idx] = th;
+            p.n_rows[idx] = n_rows;
+#pragma unroll
+            for (int d = 0; d < 6; ++d) p.y_hit[idx * 6 + d] = yh[d];
+        }
+    }
+}
+
+template <class KERN>
+int launch_grid_kernel(KERN kern, const SympParams &p, size_t smem, cudaStream_t st)
+{
     HB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, sms = 148, per_sm = 1;
     cudaGetDevice(&dev);
@@ -425,16 +527,41 @@ int launch_symp(const SympParams &p, size_t smem, cudaStream_t st)
     return HB_OK;
 }
 
+template <class AR, bool EVENT>
+int launch_ham_rk(const SympParams &p, int method, size_t smem, cudaStream_t st)
+{
+    if (method == HB_RK4) return launch_grid_kernel(k_ham_rk_grid<AR, TabRK4, EVENT>, p, smem, st);
+    if (method == HB_RK6) return launch_grid_kernel(k_ham_rk_grid<AR, TabRK6, EVENT>, p, smem, st);
+    if (method == HB_RK8) return launch_grid_kernel(k_ham_rk_grid<AR, TabRK8, EVENT>, p, smem, st);
+    return HB_ERR_UNSUPPORTED;
+}
+
+template <class AR, bool EVENT>
+int launch_symp(const SympParams &p, size_t smem, cudaStream_t st)
+{
+    return launch_grid_kernel(k_symp_grid<AR, EVENT>, p, smem, st);
+}
+
+int ham_table(const hb_polyham *ham, int64_t n, const double *y0, void *workspace, SympParams &p, size_t &smem);
+
 int symp_common(const hb_polyham *ham, const hb_symp_opts *o, int64_t n, const double *y0, const double *tao_tab,
                 void *workspace, SympParams &p, size_t &smem)
 {
     if (!ham || !o || !workspace || n < 0) return HB_ERR_BADARG;
-    if (ham->n_dof != 3 || ham->max_deg < 0 || ham->max_deg > 30) return HB_ERR_UNSUPPORTED;
     if (o->order < 2 || (o->order % 2) != 0 || o->order > 8) return HB_ERR_UNSUPPORTED;
     if (o->m < 2 || o->n_sub <= 0 || o->n_sub > HB_MAX_TAO_SUBSTEPS) return HB_ERR_BADARG;   // prepare not called
     if (o->arith != HB_ARITH_PARITY && o->arith != HB_ARITH_FAST) return HB_ERR_BADARG;
-    if (n > 0 && (!y0 || !tao_tab || !ham->terms)) return HB_ERR_BADARG;
-    p.n = n; p.y0 = y0; p.m = o->m; p.n_sub = o->n_sub; p.tab = tao_tab;
+    if (n > 0 && !tao_tab) return HB_ERR_BADARG;
+    p.m = o->m; p.n_sub = o->n_sub; p.tab = tao_tab;
+    return ham_table(ham, n, y0, workspace, p, smem);
+}
+
+int ham_table(const hb_polyham *ham, int64_t n, const double *y0, void *workspace, SympParams &p, size_t &smem)
+{
+    if (!ham || !workspace || n < 0) return HB_ERR_BADARG;
+    if (ham->n_dof != 3 || ham->max_deg < 0 || ham->max_deg > 30) return HB_ERR_UNSUPPORTED;
+    if (n > 0 && (!y0 || !ham->terms)) return HB_ERR_BADARG;
+    p.n = n; p.y0 = y0;
     p.ws = (HbWorkspace *)workspace;
     p.terms = (const TermMeta *)ham->terms;
     for (int i = 0; i < 7; ++i) p.ptr[i] = (int)ham->ptr[i];
@@ -548,4 +675,46 @@ extern "C" int hb_ham_symplectic_event(const hb_polyham *ham, const hb_symp_opts
     p.ev_idx = ev->idx; p.ev_dir = ev->direction; p.ev_off = ev->offset; p.xtol = ev->xtol; p.gtol = ev->gtol;
     p.hit = hit; p.t_hit = t_hit; p.y_hit = y_hit; p.n_rows = n_rows;
     return (opts->arith == HB_ARITH_PARITY) ? launch_symp<ArParity, true>(p, smem, st) : launch_symp<ArFast, true>(p, smem, st);
+}
+
+extern "C" int hb_ham_rk_dense(const hb_polyham *ham, int32_t method, int32_t arith, int64_t n, const double *y0,
+                               const double *t_vals, int32_t m, double *traj, double *derivs, void *workspace,
+                               void *stream)
+{
+    if (method != HB_RK4 && method != HB_RK6 && method != HB_RK8) return HB_ERR_UNSUPPORTED;
+    if (arith != HB_ARITH_PARITY && arith != HB_ARITH_FAST) return HB_ERR_BADARG;
+    if (m < 2) return HB_ERR_BADARG;
+    SympParams p{};
+    size_t smem = 0;
+    const int rc = ham_table(ham, n, y0, workspace, p, smem);
+    if (rc != HB_OK) return rc;
+    if (n > 0 && (!traj || !t_vals)) return HB_ERR_BADARG;
+    if (n == 0) return HB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    HB_CUDA_TRY(cudaMemsetAsync(workspace, 0, sizeof(HbWorkspace), st));
+    p.m = m; p.t_vals = t_vals; p.traj = traj; p.derivs = derivs;
+    return (arith == HB_ARITH_PARITY) ? launch_ham_rk<ArParity, false>(p, method, smem, st)
+                                      : launch_ham_rk<ArFast, false>(p, method, smem, st);
+}
+
+extern "C" int hb_ham_rk_event(const hb_polyham *ham, int32_t method, int32_t arith, const hb_event *ev, int64_t n,
+                               const double *y0, const double *t_vals, int32_t m, double *traj, int32_t *hit,
+                               double *t_hit, double *y_hit, int32_t *n_rows, void *workspace, void *stream)
+{
+    if (method != HB_RK4 && method != HB_RK6 && method != HB_RK8) return HB_ERR_UNSUPPORTED;
+    if (arith != HB_ARITH_PARITY && arith != HB_ARITH_FAST) return HB_ERR_BADARG;
+    if (m < 2 || !ev || ev->idx < 0 || ev->idx > 5) return HB_ERR_BADARG;
+    SympParams p{};
+    size_t smem = 0;
+    const int rc = ham_table(ham, n, y0, workspace, p, smem);
+    if (rc != HB_OK) return rc;
+    if (n > 0 && (!t_vals || !hit || !t_hit || !y_hit || !n_rows)) return HB_ERR_BADARG;
+    if (n == 0) return HB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    HB_CUDA_TRY(cudaMemsetAsync(workspace, 0, sizeof(HbWorkspace), st));
+    p.m = m; p.t_vals = t_vals; p.traj = traj;
+    p.ev_idx = ev->idx; p.ev_dir = ev->direction; p.ev_off = ev->offset; p.xtol = ev->xtol; p.gtol = ev->gtol;
+    p.hit = hit; p.t_hit = t_hit; p.y_hit = y_hit; p.n_rows = n_rows;
+    return (arith == HB_ARITH_PARITY) ? launch_ham_rk<ArParity, true>(p, method, smem, st)
+                                      : launch_ham_rk<ArFast, true>(p, method, smem, st);
 }

@@ -261,6 +261,33 @@ def _make_dop853_integrate(orig):
     return integrate
 
 
+def _fixed_rk_ham(self, system, y0, t_vals, method, ev, event_cfg, event_options):
+    """The `_ham` branch of _FixedStepRK.integrate (rk.py:468-530) for the reference's bare polynomial
+    `_HamiltonianSystem` (a _DirectedSystem around it never reaches the `_ham` kernels in the reference -- it raises
+    there -- and is left to the reference's own method).  Returns None when the system is not that."""
+    from hiten.algorithms.dynamics.hamiltonian import _HamiltonianSystem
+    from hiten.algorithms.integrators.types import _Solution
+    if type(system) is not _HamiltonianSystem or system.n_dof != 3:
+        return None
+    self.validate_inputs(system, y0, t_vals)
+    const = self._maybe_constant_solution(system, y0, t_vals)
+    if const is not None:
+        return const
+    t_vals = np.asarray(t_vals, dtype=np.float64)
+    y0 = np.asarray(y0, dtype=np.float64)
+    table = _poly_table(system.jac_H, system.clmo_H)
+    order = {_L.HB_RK4: 4, _L.HB_RK6: 6, _L.HB_RK8: 8}[method]
+    if ev is None:
+        states, derivs = _symp.integrate_rk_ham(table, y0[None, :], t_vals, order, arith=_STATE["arith"])
+        return _Solution(times=t_vals[: states.shape[1]], states=states[0], derivatives=derivs[0])
+    event = (ev[0], ev[1], 0 if event_cfg is None else int(event_cfg.direction),
+             float(event_options.xtol if event_options is not None else 1.0e-12),
+             float(event_options.gtol if event_options is not None else 1.0e-12))
+    r = _symp.integrate_rk_ham_until_event(table, y0[None, :], t_vals, order, event, arith=_STATE["arith"])
+    t_end = float(r.t_hit[0]) if bool(r.hit[0]) else t_vals[-1]                    # rk.py:512-515
+    return _Solution(times=np.array([t_vals[0], t_end], dtype=np.float64), states=np.vstack([y0, r.y_hit[0]]))
+
+
 def _make_rk_integrate(orig, kind):
     """_RK45.integrate (rk.py:1138) / _FixedStepRK.integrate (rk.py:422) for the 6-state CR3BP system: grid
     integration (hb_cr3bp_dense with the class's method) and recognised plane events (hb_cr3bp_event).  The fixed-step
@@ -272,6 +299,10 @@ def _make_rk_integrate(orig, kind):
         ev = recognise_event(event_fn) if event_fn is not None else None
         method = _L.HB_RK45 if kind == "rk45" else {"_RK4": _L.HB_RK4, "_RK6": _L.HB_RK6,
                                                     "_RK8": _L.HB_RK8}.get(type(self).__name__)
+        if kind == "fixed" and method is not None and not kwargs and (event_fn is None or ev is not None):
+            sol = _fixed_rk_ham(self, system, y0, t_vals, method, ev, event_cfg, event_options)
+            if sol is not None:
+                return sol
         if rec is None or rec[0] != 6 or method is None or (event_fn is not None and ev is None) or kwargs:
             return orig(self, system, y0, t_vals, event_fn=event_fn, event_cfg=event_cfg,
                         event_options=event_options, **kwargs)

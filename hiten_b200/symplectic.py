@@ -102,3 +102,73 @@ def integrate_symplectic_until_event(table, y0, t_vals_signed, order, event, *, 
                                          n_rows.cpu().numpy().astype(np.int64),
                                          traj.cpu().numpy() if traj is not None else None)
         return SymplecticEventResult(hit.bool(), t_hit, y_hit, n_rows, traj)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Fixed-step RK classes on a polynomial Hamiltonian system (the `_ham` kernels, rk.py:592-656 / 722-757)
+# ------------------------------------------------------------------------------------------------------------------
+_RK_METHOD = {4: L.HB_RK4, 6: L.HB_RK6, 8: L.HB_RK8}
+
+
+def _prep_rk(table, y0, t_vals, order, arith, device):
+    host = not (isinstance(y0, torch.Tensor) and y0.is_cuda)
+    yd = torch.from_numpy(np.ascontiguousarray(y0, dtype=np.float64)).to(device) if host else y0.contiguous()
+    if yd.dim() != 2 or yd.shape[1] != 6:
+        raise ValueError("y0 must have shape (N, 6) = [Q, P]")
+    t = np.ascontiguousarray(t_vals, dtype=np.float64)
+    if t.ndim != 1 or t.size < 2:
+        raise ValueError("Must provide at least 2 time points")                 # integrators/base.py:183
+    if int(order) not in _RK_METHOD:
+        raise ValueError("RK order must be 4, 6, or 8")
+    ham, keep = table.device_struct(device)
+    return (host, yd, t, torch.from_numpy(t).to(device), _RK_METHOD[int(order)],
+            {"parity": L.HB_ARITH_PARITY, "fast": L.HB_ARITH_FAST}[arith], ham, keep)
+
+
+def integrate_rk_ham(table, y0, t_vals, order, *, arith="parity", want_derivatives=True, device=None, stream=None):
+    """_FixedStepRK._integrate_fixed_rk_ham for a batch: y0 [N, 6] -> (states [N, m, 6], derivatives [N, m, 6] or None)."""
+    _require_cuda()
+    lib = L.load()
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    with torch.cuda.device(device):
+        host, yd, t, td, method, ar, ham, keep = _prep_rk(table, y0, t_vals, order, arith, device)
+        n = int(yd.shape[0])
+        traj = torch.empty((n, t.size, 6), dtype=torch.float64, device=device)
+        der = torch.empty((n, t.size, 6), dtype=torch.float64, device=device) if want_derivatives else None
+        ws = workspace(device)
+        L.check(lib.hb_ham_rk_dense(ham, method, ar, n, yd.data_ptr(), td.data_ptr(), int(t.size), traj.data_ptr(),
+                                    der.data_ptr() if der is not None else None, ws.data_ptr(), _stream_ptr(stream)),
+                "hb_ham_rk_dense")
+        if host:
+            return traj.cpu().numpy(), (der.cpu().numpy() if der is not None else None)
+        return traj, der
+
+
+def integrate_rk_ham_until_event(table, y0, t_vals, order, event, *, arith="parity", want_trajectory=False, device=None,
+                                 stream=None):
+    """_FixedStepRK._integrate_fixed_rk_until_event_ham for a batch; `event` = (idx, offset, direction, xtol, gtol)."""
+    _require_cuda()
+    lib = L.load()
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    idx, offset, direction, xtol, gtol = event
+    if not 0 <= int(idx) < 6:
+        raise ValueError("event index must be in 0..5")
+    ev = L.HbEvent(int(idx), int(direction), float(offset), float(xtol), float(gtol))
+    with torch.cuda.device(device):
+        host, yd, t, td, method, ar, ham, keep = _prep_rk(table, y0, t_vals, order, arith, device)
+        n = int(yd.shape[0])
+        traj = torch.empty((n, t.size, 6), dtype=torch.float64, device=device) if want_trajectory else None
+        hit = torch.zeros(n, dtype=torch.int32, device=device)
+        n_rows = torch.zeros(n, dtype=torch.int32, device=device)
+        t_hit = torch.zeros(n, dtype=torch.float64, device=device)
+        y_hit = torch.zeros((n, 6), dtype=torch.float64, device=device)
+        ws = workspace(device)
+        L.check(lib.hb_ham_rk_event(ham, method, ar, L.C.byref(ev), n, yd.data_ptr(), td.data_ptr(), int(t.size),
+                                    traj.data_ptr() if traj is not None else None, hit.data_ptr(), t_hit.data_ptr(),
+                                    y_hit.data_ptr(), n_rows.data_ptr(), ws.data_ptr(), _stream_ptr(stream)),
+                "hb_ham_rk_event")
+        if host:
+            return SymplecticEventResult(hit.cpu().numpy().astype(bool), t_hit.cpu().numpy(), y_hit.cpu().numpy(),
+                                         n_rows.cpu().numpy().astype(np.int64),
+                                         traj.cpu().numpy() if traj is not None else None)
+        return SymplecticEventResult(hit.bool(), t_hit, y_hit, n_rows, traj)

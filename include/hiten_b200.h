@@ -281,6 +281,19 @@ int hb_ham_symplectic_event(const hb_polyham *ham, const hb_symp_opts *opts, con
                             const double *y0, const double *t_vals_signed, const double *tao_tab, double *traj,
                             int32_t *hit, double *t_hit, double *y_hit, int32_t *n_rows, void *workspace, void *stream);
 
+/* ---- _FixedStepRK.integrate on a polynomial Hamiltonian system: the `_ham` kernels of the RK classes
+ * (algorithms/integrators/rk.py: _integrate_fixed_rk_ham :592-656, rk_embedded_step_ham_jit_kernel :216-270,
+ * _integrate_fixed_rk_until_event_ham :722-757 + _hermite_refine_in_step :331-391).  method = HB_RK4 / HB_RK6 / HB_RK8;
+ * t_vals[m] is a DEVICE array (one step per grid interval, h = t[i+1] - t[i]); the reference's `_ham` kernels take
+ * system.rhs_params and never see a direction wrapper, so there is no direction argument.
+ * dense: y0[n][6] -> traj[n][m][6] and (optional) derivs[n][m][6] = _Solution.derivatives.
+ * event: as hb_ham_symplectic_event (hit / t_hit / y_hit / n_rows, traj optional).                              */
+int hb_ham_rk_dense(const hb_polyham *ham, int32_t method, int32_t arith, int64_t n, const double *y0,
+                    const double *t_vals, int32_t m, double *traj, double *derivs, void *workspace, void *stream);
+int hb_ham_rk_event(const hb_polyham *ham, int32_t method, int32_t arith, const hb_event *ev, int64_t n,
+                    const double *y0, const double *t_vals, int32_t m, double *traj, int32_t *hit, double *t_hit,
+                    double *y_hit, int32_t *n_rows, void *workspace, void *stream);
+
 /* Seed lifting for the centre-manifold map: replaces the per-seed Python Brent solves of
  * _CenterManifoldInterface.lift_plane_point / solve_missing_coord (algorithms/poincare/centermanifold/
  * interfaces.py:297-337, 212-268; solve_bracketed_brent algorithms/utils/rootfinding.py:92-190) that the seeding

@@ -137,6 +137,27 @@ def integrate_symplectic_until_event(table, y0, t_vals_signed, order, event, *, 
     return SymplecticEventResult(hit, th, yh, nr, traj if want_trajectory else None)
 
 
+def integrate_rk_ham(table, y0, t_vals, order, *, want_derivatives=True, **kw):
+    ham = O.PolyHam(table.ptr, table.deg, table.coef, table.exp)
+    s = O.system(O.SYS_POLYHAM, ham=ham)
+    states = np.stack([O.fixed_dense(s, int(order), y, np.asarray(t_vals)) for y in np.asarray(y0)])
+    derivs = np.stack([[O.polyham_rhs(ham, row) for row in tr] for tr in states]) if want_derivatives else None
+    return states, derivs
+
+
+def integrate_rk_ham_until_event(table, y0, t_vals, order, event, *, want_trajectory=False, **kw):
+    from hiten_b200.symplectic import SymplecticEventResult
+    ham = O.PolyHam(table.ptr, table.deg, table.coef, table.exp)
+    s = O.system(O.SYS_POLYHAM, ham=ham)
+    idx, offset, direction, xtol, gtol = event
+    ev = O.HoEvent(int(idx), float(offset), int(direction), xtol, gtol)
+    y0 = np.asarray(y0)
+    hit, th, yh = np.zeros(len(y0), bool), np.zeros(len(y0)), np.zeros((len(y0), 6))
+    for i in range(len(y0)):
+        hit[i], th[i], yh[i] = O.fixed_event(s, int(order), ev, y0[i], np.asarray(t_vals))
+    return SymplecticEventResult(hit, th, yh, np.zeros(len(y0), np.int64), None)
+
+
 def patch(monkeypatch):
     import hiten_b200.corrector as corr
     monkeypatch.setattr(corr, "correct_orbits", correct_orbits)
@@ -154,5 +175,7 @@ def patch(monkeypatch):
     import hiten_b200.symplectic as symp
     monkeypatch.setattr(symp, "integrate_symplectic", integrate_symplectic)
     monkeypatch.setattr(symp, "integrate_symplectic_until_event", integrate_symplectic_until_event)
+    monkeypatch.setattr(symp, "integrate_rk_ham", integrate_rk_ham)
+    monkeypatch.setattr(symp, "integrate_rk_ham_until_event", integrate_rk_ham_until_event)
     import hiten_b200.connections as conn
     monkeypatch.setattr(conn, "find_connections", find_connections)

@@ -328,3 +328,54 @@ def test_symplectic_class_and_propagate_symplectic(ref, monkeypatch):
     for k in want:
         assert np.array_equal(got[k][0], want[k][0]), k
         assert np.array_equal(got[k][1], want[k][1]), k
+
+
+def test_fixed_step_rk_classes_on_the_hamiltonian_system(ref, monkeypatch):
+    """RungeKutta(order=4|6|8).integrate(hamsys, ...) -- the `_ham` kernels of _FixedStepRK (grid with derivatives, plane
+    events, no-hit) -- with the drop-in: the same arrays as the reference alone, bit for bit; a _DirectedSystem around the
+    Hamiltonian system is left to the reference's own method (which raises, with or without the drop-in)."""
+    import fake_gpu
+    import hiten_b200
+    from hiten.algorithms.dynamics.base import _DirectedSystem
+    from hiten.algorithms.integrators.rk import RungeKutta
+    from hiten.algorithms.poincare.singlehit.backend import _get_cached_plane_event_fn
+    from hiten.algorithms.types.configs import EventConfig
+    system, l1, halo = ref
+    cm = l1.get_center_manifold(degree=6)
+    cm.compute()
+    hamsys = cm.poincare_map(energy=0.7).dynamics.hamsys
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "symplectic.npz"))
+    y0 = g["y0"][2]
+    cfg = EventConfig(direction=0, terminal=True)
+
+    def run_all():
+        out = {}
+        for order in (4, 6, 8):
+            sol = RungeKutta(order=order).integrate(hamsys, y0.copy(), np.linspace(0.0, 1.0, 51))
+            out[f"grid{order}"] = (sol.times.copy(), sol.states.copy(), sol.derivatives.copy())
+            ev = RungeKutta(order=order).integrate(hamsys, y0.copy(), np.linspace(0.0, 6.0, 301),
+                                                   event_fn=_get_cached_plane_event_fn(2, 0.0), event_cfg=cfg)
+            out[f"event{order}"] = (ev.times.copy(), ev.states.copy())
+        nh = RungeKutta(order=4).integrate(hamsys, y0.copy(), np.linspace(0.0, 0.05, 6),
+                                           event_fn=_get_cached_plane_event_fn(2, 10.0), event_cfg=cfg)
+        out["nohit"] = (nh.times.copy(), nh.states.copy())
+        return out
+
+    want = run_all()
+    hiten_b200.install()
+    fake_gpu.patch(monkeypatch)
+    calls = []
+    import hiten_b200.symplectic as symp
+    d0, e0 = symp.integrate_rk_ham, symp.integrate_rk_ham_until_event
+    monkeypatch.setattr(symp, "integrate_rk_ham", lambda *a, **k: (calls.append("grid"), d0(*a, **k))[1])
+    monkeypatch.setattr(symp, "integrate_rk_ham_until_event", lambda *a, **k: (calls.append("event"), e0(*a, **k))[1])
+    try:
+        got = run_all()
+        with pytest.raises(Exception):
+            RungeKutta(order=4).integrate(_DirectedSystem(hamsys, -1), y0.copy(), np.linspace(0.0, 1.0, 11))
+    finally:
+        hiten_b200.uninstall()
+    assert calls.count("grid") == 3 and calls.count("event") == 4
+    for k in want:
+        for a, b in zip(got[k], want[k]):
+            assert np.array_equal(a, b), k
