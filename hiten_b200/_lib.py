@@ -114,6 +114,10 @@ SIGNATURES = {
     "hb_ham_rk_dense": (C.c_int, [C.POINTER(HbPolyHam), C.c_int32, C.c_int32, C.c_int64, vp, vp, C.c_int32, vp, vp, vp, vp]),
     "hb_ham_rk_event": (C.c_int, [C.POINTER(HbPolyHam), C.c_int32, C.c_int32, C.POINTER(HbEvent), C.c_int64, vp, vp,
                                   C.c_int32, vp, vp, vp, vp, vp, vp, vp]),
+    "hb_ham_adaptive_dense": (C.c_int, [C.POINTER(HbPolyHam), C.POINTER(HbInteg), C.c_int64, vp, vp, C.c_int32, vp, vp, vp,
+                                        vp, vp, vp, vp]),
+    "hb_ham_adaptive_event": (C.c_int, [C.POINTER(HbPolyHam), C.POINTER(HbInteg), C.POINTER(HbEvent), C.c_int64, vp,
+                                        C.c_double, C.c_double, vp, vp, vp, vp, vp, vp, vp]),
     "hb_cm_poincare_map": (C.c_int, [C.POINTER(HbPolyHam), C.POINTER(HbCmOpts), C.c_int64, vp, vp, vp, vp, vp, vp]),
     "hb_cm_poincare_map_jit": (C.c_int, [C.POINTER(HbPolyHam), C.POINTER(HbCmOpts), C.c_int64, vp, vp, vp, vp, vp, vp]),
     "hb_cm_jit_compile_host": (C.c_int, [vp, C.POINTER(C.c_int64), C.c_int32, C.POINTER(HbCmOpts), C.POINTER(C.c_int64),

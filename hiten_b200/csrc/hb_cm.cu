@@ -15,7 +15,9 @@
 //   _integrate_rk_ham, _detect_crossing, _poincare_step, _poincare_map
 //                                           algorithms/poincare/centermanifold/backend.py:35-382
 //   _hermite_scalar                         algorithms/poincare/utils.py:54-97
+#include "hb_cr3bp_common.cuh"
 #include "hb_rkgen.cuh"
+#include "hb_rk45.cuh"
 
 #include <cmath>
 
@@ -536,6 +538,236 @@ int launch_ham_rk(const SympParams &p, int method, size_t smem, cudaStream_t st)
     return HB_ERR_UNSUPPORTED;
 }
 
+// ---- AdaptiveRK on a polynomial Hamiltonian system: the `_ham` kernels of _DOP853 / _RK45 ---------------------------
+// _integrate_dop853_ham (rk.py:2553-2676) / _integrate_rk45_ham (:1403-1456): the adaptive loops of hb_cr3bp.cu /
+// hb_cr3bp_rk.cu with the polynomial vector field, dense output at every t_eval AND the derivative re-evaluated there
+// (_Solution.derivatives); _integrate_dop853_until_event_ham (:2807-2868) / _integrate_rk45_until_event_ham (:1589-1633):
+// terminal plane event refined on the method's own dense interpolant.  Same controller (utils.py), same first step.
+struct HamAdParams {
+    SympParams s;          // batch, grid (t_vals = t_eval), outputs traj / derivs, event fields, hit / t_hit / y_hit
+    double rtol, atol, max_step, min_step, t0, tmax;
+    long long max_attempts;
+    int *nacc, *nrej, *status;
+};
+
+template <class AR>
+HB_DEV double ham_initial_step(const double (&y)[6], const double (&f)[6], const HamAdParams &q)   // utils.py:127-157
+{
+    double a[6], b[6];
+#pragma unroll
+    for (int d = 0; d < 6; ++d) {
+        const double sc = AR::madd(q.rtol, fabs(y[d]), q.atol);
+        a[d] = AR::div(y[d], sc);
+        b[d] = AR::div(f[d], sc);
+    }
+    const double sq = AR::sqrt(6.0);
+    const double d0 = AR::div(hbc::norm2_ext6(a), sq), d1 = AR::div(hbc::norm2_ext6(b), sq);
+    double h = (d0 < 1.0e-5 || d1 < 1.0e-5) ? 1.0e-6 : AR::div(AR::mul(0.01, d0), d1);
+    if (h > q.max_step) h = q.max_step;
+    if (h < q.min_step) h = q.min_step;
+    return h;
+}
+
+// METHOD: HB_DOP853 or HB_RK45; EVENT: terminal plane event instead of the dense grid
+template <class AR, int METHOD, bool EVENT>
+__global__ void __launch_bounds__(CM_BLOCK) k_ham_adaptive(const HamAdParams q)
+{
+    const SympParams &p = q.s;
+    extern __shared__ __align__(16) unsigned char smem[];
+    TermMeta *terms = reinterpret_cast<TermMeta *>(smem);
+    double *pw_all = reinterpret_cast<double *>(smem + (((size_t)p.n_terms * sizeof(TermMeta) + 15) & ~(size_t)15));
+    for (int i = threadIdx.x; i < p.n_terms; i += CM_BLOCK) terms[i] = p.terms[i];
+    __syncthreads();
+    double *pw = pw_all + threadIdx.x;
+    const SympRhs<AR> rhs{p, pw, terms};
+    constexpr bool D8 = METHOD == HB_DOP853;
+    constexpr int NK = D8 ? 13 : 6;
+
+    for (;;) {
+        const long long idx = hb_fetch_index(p.ws);
+        if (idx >= p.n) break;
+        const double *s0 = p.y0 + idx * 6;
+        double y[6], yh[6], k[NK][6], k6[6];
+#pragma unroll
+        for (int d = 0; d < 6; ++d) y[d] = s0[d];
+        rhs(y, k[0]);
+        double t = EVENT ? q.t0 : p.t_vals[0];
+        const double tf = EVENT ? q.tmax : p.t_vals[p.m - 1];
+        double h = ham_initial_step<AR>(y, k[0], q);
+        double err_prev = -1.0, g_prev = 0.0, t_end = 0.0;
+        if (EVENT) g_prev = AR::sub(pick6c(y, p.ev_idx), p.ev_off);
+        int nacc = 0, nrej = 0, cursor = 0, fin = -1;
+        long long attempts = 0;
+        double *rows = p.traj ? p.traj + idx * (long long)p.m * 6 : nullptr;
+        double *drows = p.derivs ? p.derivs + idx * (long long)p.m * 6 : nullptr;
+        double yo[6], fo[6];
+        while ((t - tf) < 0.0 && fin < 0) {
+            h = hb_clamp_step(h, q.max_step, q.min_step);
+            if (AR::add(t, h) > tf) h = fabs(AR::sub(tf, t));
+            double err;
+            if constexpr (D8) {
+                dop853_stages<AR>(y, k, h, yh, rhs);
+                double n5 = 0.0, n3 = 0.0;
+                dop853_err_sums<AR>(y, yh, k, h, q.rtol, q.atol, n5, n3);
+                err = dop853_err_norm<AR>(n5, n3, h, 6.0);
+            } else {
+                g_run_stages<AR, Tab45, SympRhs<AR>, 1>(rhs, y, k, h);
+#pragma unroll
+                for (int d = 0; d < 6; ++d) yh[d] = y[d];
+                g_high_acc<AR, Tab45, 0>(yh, k, h);
+                rhs(yh, k6);
+                double ev[6];
+#pragma unroll
+                for (int d = 0; d < 6; ++d) ev[d] = 0.0;
+                rk45_err_acc<AR, 0>(ev, k, k6, h);
+#pragma unroll
+                for (int d = 0; d < 6; ++d)
+                    ev[d] = AR::div(ev[d], AR::madd(q.rtol, fmax(fabs(y[d]), fabs(yh[d])), q.atol));
+                err = AR::div(hbc::norm2_ext6(ev), AR::sqrt(6.0));
+            }
+            ++attempts;
+            if (err <= 1.0) {
+                const double t_new = AR::add(t, h);
+                ++nacc;
+                const bool last = !((t_new - tf) < 0.0);
+                const double hseg = EVENT ? h : AR::sub(t_new, t);
+                bool crossed = false;
+                double g_new = 0.0;
+                if (EVENT) {
+                    g_new = AR::sub(pick6c(yh, p.ev_idx), p.ev_off);
+                    crossed = hb_event_crossed(g_prev, g_new, p.ev_dir);
+                }
+                if (crossed || (!EVENT && cursor < p.m && (last || p.t_vals[cursor] < t_new))) {
+                    // the method's dense interpolant of this step
+                    double F[D8 ? 7 : 1][6], Q[D8 ? 1 : 6][4];
+                    if constexpr (D8) {
+                        if (hseg != 0.0) dense_cache<AR>(y, yh, hseg, k, F, rhs);
+                    } else {
+#pragma unroll
+                        for (int d = 0; d < 6; ++d)
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) Q[d][c] = 0.0;
+                        rk45_q_acc<AR, 0, 0>(Q, k, k6);
+                    }
+                    auto eval = [&](double x, double (&o)[6]) {
+                        if constexpr (D8) dense_eval<AR>(y, F, x, o);
+                        else rk45_eval<AR>(y, Q, x, hseg, o);
+                    };
+                    if (EVENT) {
+                        // _dop853_refine_in_step_ham (rk.py:2106-2170) / _rk45_refine_in_step (:1072-1092)
+                        double a = 0.0, b = 1.0, g_left = g_prev, xh = 1.0;
+                        bool found = false;
+                        for (int it = 0; it < 128; ++it) {
+                            const double mid = AR::mul(0.5, AR::add(a, b));
+                            eval(mid, yo);
+                            const double g_mid = AR::sub(pick6c(yo, p.ev_idx), p.ev_off);
+                            if (fabs(g_mid) <= p.gtol) { xh = mid; found = true; break; }
+                            if (hb_crossed_direction(g_left, g_mid, p.ev_dir)) b = mid;
+                            else { a = mid; g_left = g_mid; }
+                            if (AR::mul(AR::sub(b, a), fabs(h)) <= p.xtol) break;
+                        }
+                        if (!found) xh = b;
+                        eval(xh, yo);
+                        t_end = AR::madd(xh, h, t);
+                        fin = HB_TRAJ_HIT;
+                    } else {
+                        while (cursor < p.m) {
+                            const double tq = p.t_vals[cursor];
+                            if (!(last || tq < t_new)) break;
+                            if (hseg == 0.0) {
+#pragma unroll
+                                for (int d = 0; d < 6; ++d) yo[d] = y[d];
+                            } else {
+                                eval(AR::div(AR::sub(tq, t), hseg), yo);
+                            }
+                            double *o = rows + (long long)cursor * 6;
+#pragma unroll
+                            for (int d = 0; d < 6; ++d) o[d] = yo[d];
+                            if (drows) {
+                                rhs(yo, fo);
+                                double *od = drows + (long long)cursor * 6;
+#pragma unroll
+                                for (int d = 0; d < 6; ++d) od[d] = fo[d];
+                            }
+                            ++cursor;
+                        }
+                    }
+                }
+                if (EVENT && !crossed) g_prev = g_new;
+                if (fin < 0) {
+                    t = t_new;
+#pragma unroll
+                    for (int d = 0; d < 6; ++d) { y[d] = yh[d]; k[0][d] = D8 ? k[NK - 1][d] : k6[d]; }
+                    if constexpr (D8) h = AR::mul(h, hb_pi_accept_factor<AR>(err, err_prev, 8.0));
+                    else h = AR::mul(h, hb_pi_accept_factor<AR>(err, err_prev, 5.0));
+                    err_prev = err;
+                }
+            } else {
+                ++nrej;
+                h = AR::mul(h, hb_pi_reject_factor<AR>(err, D8 ? 8.0 : 5.0));
+                h = hb_clamp_step(h, q.max_step, q.min_step);
+            }
+            if (fin < 0) {
+                if (!(h == h) || !(err == err)) fin = HB_TRAJ_NONFINITE;
+                else if (attempts >= q.max_attempts) fin = HB_TRAJ_MAXSTEPS;
+            }
+        }
+        if (fin < 0) fin = HB_TRAJ_OK;
+        if (EVENT) {
+            if (fin != HB_TRAJ_HIT) {
+                t_end = t;
+#pragma unroll
+                for (int d = 0; d < 6; ++d) yo[d] = y[d];
+            }
+            p.t_hit[idx] = t_end;
+#pragma unroll
+            for (int d = 0; d < 6; ++d) p.y_hit[idx * 6 + d] = yo[d];
+        } else {
+            for (; cursor < p.m; ++cursor) {       // zero-length span or early termination: hold the last state
+                double *o = rows + (long long)cursor * 6;
+#pragma unroll
+                for (int d = 0; d < 6; ++d) o[d] = y[d];
+                if (drows) {
+                    double *od = drows + (long long)cursor * 6;
+#pragma unroll
+                    for (int d = 0; d < 6; ++d) od[d] = k[0][d];
+                }
+            }
+        }
+        q.nacc[idx] = nacc; q.nrej[idx] = nrej; q.status[idx] = fin;
+    }
+}
+
+template <class KERN>
+int launch_ham_adaptive(KERN kern, const HamAdParams &q, size_t smem, cudaStream_t st)
+{
+    HB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int dev = 0, sms = 148, per_sm = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    HB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CM_BLOCK, smem));
+    if (per_sm < 1) per_sm = 1;
+    long long blocks = (q.s.n + CM_BLOCK - 1) / CM_BLOCK;
+    const long long cap = (long long)sms * per_sm;
+    if (blocks > cap) blocks = cap;
+    kern<<<(unsigned)blocks, CM_BLOCK, smem, st>>>(q);
+    HB_CUDA_TRY(cudaGetLastError());
+    return HB_OK;
+}
+
+template <bool EVENT>
+int dispatch_ham_adaptive(const HamAdParams &q, int method, int arith, size_t smem, cudaStream_t st)
+{
+    const bool par = arith == HB_ARITH_PARITY;
+    if (method == HB_DOP853)
+        return par ? launch_ham_adaptive(k_ham_adaptive<ArParity, HB_DOP853, EVENT>, q, smem, st)
+                   : launch_ham_adaptive(k_ham_adaptive<ArFast, HB_DOP853, EVENT>, q, smem, st);
+    if (method == HB_RK45)
+        return par ? launch_ham_adaptive(k_ham_adaptive<ArParity, HB_RK45, EVENT>, q, smem, st)
+                   : launch_ham_adaptive(k_ham_adaptive<ArFast, HB_RK45, EVENT>, q, smem, st);
+    return HB_ERR_UNSUPPORTED;
+}
+
 template <class AR, bool EVENT>
 int launch_symp(const SympParams &p, size_t smem, cudaStream_t st)
 {
@@ -717,4 +949,52 @@ extern "C" int hb_ham_rk_event(const hb_polyham *ham, int32_t method, int32_t ar
     p.hit = hit; p.t_hit = t_hit; p.y_hit = y_hit; p.n_rows = n_rows;
     return (arith == HB_ARITH_PARITY) ? launch_ham_rk<ArParity, true>(p, method, smem, st)
                                       : launch_ham_rk<ArFast, true>(p, method, smem, st);
+}
+
+static int ham_adaptive_fill(const hb_polyham *ham, const hb_integ *integ, int64_t n, const double *y0, void *workspace,
+                             int32_t *n_acc, int32_t *n_rej, int32_t *status, HamAdParams &q, size_t &smem)
+{
+    if (!integ) return HB_ERR_BADARG;
+    if (integ->method != HB_DOP853 && integ->method != HB_RK45) return HB_ERR_UNSUPPORTED;
+    if (integ->arith != HB_ARITH_PARITY && integ->arith != HB_ARITH_FAST) return HB_ERR_BADARG;
+    const int rc = ham_table(ham, n, y0, workspace, q.s, smem);
+    if (rc != HB_OK) return rc;
+    if (n > 0 && (!n_acc || !n_rej || !status)) return HB_ERR_BADARG;
+    q.rtol = integ->rtol; q.atol = integ->atol; q.max_step = integ->max_step; q.min_step = integ->min_step;
+    q.max_attempts = integ->max_attempts > 0 ? integ->max_attempts : 2147483647LL;
+    q.nacc = n_acc; q.nrej = n_rej; q.status = status;
+    return HB_OK;
+}
+
+extern "C" int hb_ham_adaptive_dense(const hb_polyham *ham, const hb_integ *integ, int64_t n, const double *y0,
+                                     const double *t_eval, int32_t m, double *states, double *derivs, int32_t *n_acc,
+                                     int32_t *n_rej, int32_t *status, void *workspace, void *stream)
+{
+    HamAdParams q{};
+    size_t smem = 0;
+    const int rc = ham_adaptive_fill(ham, integ, n, y0, workspace, n_acc, n_rej, status, q, smem);
+    if (rc != HB_OK) return rc;
+    if (m < 2 || (n > 0 && (!t_eval || !states))) return HB_ERR_BADARG;
+    if (n == 0) return HB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    HB_CUDA_TRY(cudaMemsetAsync(workspace, 0, sizeof(HbWorkspace), st));
+    q.s.m = m; q.s.t_vals = t_eval; q.s.traj = states; q.s.derivs = derivs;
+    return dispatch_ham_adaptive<false>(q, integ->method, integ->arith, smem, st);
+}
+
+extern "C" int hb_ham_adaptive_event(const hb_polyham *ham, const hb_integ *integ, const hb_event *ev, int64_t n,
+                                     const double *y0, double t0, double tmax, double *t_hit, double *y_hit,
+                                     int32_t *n_acc, int32_t *n_rej, int32_t *status, void *workspace, void *stream)
+{
+    HamAdParams q{};
+    size_t smem = 0;
+    const int rc = ham_adaptive_fill(ham, integ, n, y0, workspace, n_acc, n_rej, status, q, smem);
+    if (rc != HB_OK) return rc;
+    if (!ev || ev->idx < 0 || ev->idx > 5 || (n > 0 && (!t_hit || !y_hit))) return HB_ERR_BADARG;
+    if (n == 0) return HB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    HB_CUDA_TRY(cudaMemsetAsync(workspace, 0, sizeof(HbWorkspace), st));
+    q.t0 = t0; q.tmax = tmax; q.s.t_hit = t_hit; q.s.y_hit = y_hit;
+    q.s.ev_idx = ev->idx; q.s.ev_dir = ev->direction; q.s.ev_off = ev->offset; q.s.xtol = ev->xtol; q.s.gtol = ev->gtol;
+    return dispatch_ham_adaptive<true>(q, integ->method, integ->arith, smem, st);
 }

@@ -227,6 +227,10 @@ def _make_dop853_integrate(orig):
         ev = None
         if event_fn is not None:
             ev = recognise_event(event_fn)
+        if rec is None and not kwargs and (event_fn is None or ev is not None):
+            sol = _adaptive_ham(self, system, y0, t_vals, _L.HB_DOP853, ev, event_cfg, event_options)
+            if sol is not None:
+                return sol
         if rec is None or (event_fn is not None and (ev is None or rec[0] != 6)):
             return orig(self, system, y0, t_vals, event_fn=event_fn, event_cfg=event_cfg,
                         event_options=event_options, **kwargs)
@@ -259,6 +263,38 @@ def _make_dop853_integrate(orig):
     integrate.__wrapped__ = orig
     integrate.__doc__ = orig.__doc__
     return integrate
+
+
+def _adaptive_ham(self, system, y0, t_vals, method, ev, event_cfg, event_options):
+    """The `_ham` branch of _DOP853.integrate (rk.py:2256-2360) / _RK45.integrate (:1170-1262) for the reference's bare
+    polynomial `_HamiltonianSystem`.  Returns None when the system is not that (or the grid is not ascending)."""
+    from hiten.algorithms.dynamics.hamiltonian import _HamiltonianSystem
+    from hiten.algorithms.integrators.types import _Solution
+    if type(system) is not _HamiltonianSystem or system.n_dof != 3:
+        return None
+    self.validate_inputs(system, y0, t_vals)
+    const = self._maybe_constant_solution(system, y0, t_vals)
+    if const is not None:
+        return const
+    t_vals = np.asarray(t_vals, dtype=np.float64)
+    if not np.all(np.diff(t_vals) > 0):
+        return None
+    y0 = np.asarray(y0, dtype=np.float64)
+    table = _poly_table(system.jac_H, system.clmo_H)
+    integ = _prop.make_integ(method=method, arith=_STATE["arith"], rtol=self._rtol, atol=self._atol,
+                             max_step=min(float(self._max_step), 1e300), min_step=self._min_step)
+    if ev is None:
+        r = _symp.integrate_adaptive_ham(table, y0[None, :], t_vals, integ=integ)
+        _raise_on_status(r.status)
+        return _Solution(times=t_vals.copy(), states=r.states[0], derivatives=r.derivatives[0])
+    event = (ev[0], ev[1], 0 if event_cfg is None else int(event_cfg.direction),
+             float(event_options.xtol if event_options is not None else 1.0e-12),
+             float(event_options.gtol if event_options is not None else 1.0e-12))
+    r = _symp.integrate_adaptive_ham_until_event(table, y0[None, :], float(t_vals[0]), float(t_vals[-1]), event,
+                                                 integ=integ)
+    _raise_on_status(r.status)
+    t_end = float(r.t_hit[0]) if int(r.status[0]) == 1 else t_vals[-1]
+    return _Solution(times=np.array([t_vals[0], t_end], dtype=np.float64), states=np.vstack([y0, r.y_hit[0]]))
 
 
 def _fixed_rk_ham(self, system, y0, t_vals, method, ev, event_cfg, event_options):
@@ -299,8 +335,9 @@ def _make_rk_integrate(orig, kind):
         ev = recognise_event(event_fn) if event_fn is not None else None
         method = _L.HB_RK45 if kind == "rk45" else {"_RK4": _L.HB_RK4, "_RK6": _L.HB_RK6,
                                                     "_RK8": _L.HB_RK8}.get(type(self).__name__)
-        if kind == "fixed" and method is not None and not kwargs and (event_fn is None or ev is not None):
-            sol = _fixed_rk_ham(self, system, y0, t_vals, method, ev, event_cfg, event_options)
+        if rec is None and method is not None and not kwargs and (event_fn is None or ev is not None):
+            sol = (_fixed_rk_ham if kind == "fixed" else _adaptive_ham)(self, system, y0, t_vals, method, ev, event_cfg,
+                                                                        event_options)
             if sol is not None:
                 return sol
         if rec is None or rec[0] != 6 or method is None or (event_fn is not None and ev is None) or kwargs:

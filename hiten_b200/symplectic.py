@@ -172,3 +172,83 @@ def integrate_rk_ham_until_event(table, y0, t_vals, order, event, *, arith="pari
                                          n_rows.cpu().numpy().astype(np.int64),
                                          traj.cpu().numpy() if traj is not None else None)
         return SymplecticEventResult(hit.bool(), t_hit, y_hit, n_rows, traj)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# AdaptiveRK (DOP853 / RK45) on a polynomial Hamiltonian system (the `_ham` kernels, rk.py:2553-2676, 1403-1456, ...)
+# ------------------------------------------------------------------------------------------------------------------
+@dataclass
+class HamAdaptiveResult:
+    states: object       # dense: [N, m, 6]; event: None
+    derivatives: object  # dense: [N, m, 6] or None
+    t_hit: object        # event: [N]
+    y_hit: object        # event: [N, 6]
+    n_acc: object
+    n_rej: object
+    status: object       # HB_TRAJ_* per trajectory (1 = event hit)
+
+
+def _integ_struct(integ):
+    from .propagate import make_integ
+    return make_integ() if integ is None else integ
+
+
+def integrate_adaptive_ham(table, y0, t_eval, *, integ=None, want_derivatives=True, device=None, stream=None):
+    """_integrate_dop853_ham / _integrate_rk45_ham for a batch (integ.method = HB_DOP853 | HB_RK45)."""
+    _require_cuda()
+    lib = L.load()
+    integ = _integ_struct(integ)
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    with torch.cuda.device(device):
+        host = not (isinstance(y0, torch.Tensor) and y0.is_cuda)
+        yd = torch.from_numpy(np.ascontiguousarray(y0, dtype=np.float64)).to(device) if host else y0.contiguous()
+        if yd.dim() != 2 or yd.shape[1] != 6:
+            raise ValueError("y0 must have shape (N, 6) = [Q, P]")
+        t = np.ascontiguousarray(t_eval, dtype=np.float64)
+        if t.ndim != 1 or t.size < 2:
+            raise ValueError("Must provide at least 2 time points")
+        td = torch.from_numpy(t).to(device)
+        n = int(yd.shape[0])
+        st = torch.empty((n, t.size, 6), dtype=torch.float64, device=device)
+        der = torch.empty((n, t.size, 6), dtype=torch.float64, device=device) if want_derivatives else None
+        na, nr, ss = (torch.zeros(n, dtype=torch.int32, device=device) for _ in range(3))
+        ham, keep = table.device_struct(device)
+        ws = workspace(device)
+        L.check(lib.hb_ham_adaptive_dense(ham, L.C.byref(integ), n, yd.data_ptr(), td.data_ptr(), int(t.size),
+                                          st.data_ptr(), der.data_ptr() if der is not None else None, na.data_ptr(),
+                                          nr.data_ptr(), ss.data_ptr(), ws.data_ptr(), _stream_ptr(stream)),
+                "hb_ham_adaptive_dense")
+        if host:
+            return HamAdaptiveResult(st.cpu().numpy(), der.cpu().numpy() if der is not None else None, None, None,
+                                     na.cpu().numpy(), nr.cpu().numpy(), ss.cpu().numpy())
+        return HamAdaptiveResult(st, der, None, None, na, nr, ss)
+
+
+def integrate_adaptive_ham_until_event(table, y0, t0, tmax, event, *, integ=None, device=None, stream=None):
+    """_integrate_dop853_until_event_ham / _integrate_rk45_until_event_ham for a batch."""
+    _require_cuda()
+    lib = L.load()
+    integ = _integ_struct(integ)
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    idx, offset, direction, xtol, gtol = event
+    if not 0 <= int(idx) < 6:
+        raise ValueError("event index must be in 0..5")
+    ev = L.HbEvent(int(idx), int(direction), float(offset), float(xtol), float(gtol))
+    with torch.cuda.device(device):
+        host = not (isinstance(y0, torch.Tensor) and y0.is_cuda)
+        yd = torch.from_numpy(np.ascontiguousarray(y0, dtype=np.float64)).to(device) if host else y0.contiguous()
+        if yd.dim() != 2 or yd.shape[1] != 6:
+            raise ValueError("y0 must have shape (N, 6) = [Q, P]")
+        n = int(yd.shape[0])
+        th = torch.zeros(n, dtype=torch.float64, device=device)
+        yh = torch.zeros((n, 6), dtype=torch.float64, device=device)
+        na, nr, ss = (torch.zeros(n, dtype=torch.int32, device=device) for _ in range(3))
+        ham, keep = table.device_struct(device)
+        ws = workspace(device)
+        L.check(lib.hb_ham_adaptive_event(ham, L.C.byref(integ), L.C.byref(ev), n, yd.data_ptr(), float(t0), float(tmax),
+                                          th.data_ptr(), yh.data_ptr(), na.data_ptr(), nr.data_ptr(), ss.data_ptr(),
+                                          ws.data_ptr(), _stream_ptr(stream)), "hb_ham_adaptive_event")
+        if host:
+            return HamAdaptiveResult(None, None, th.cpu().numpy(), yh.cpu().numpy(), na.cpu().numpy(), nr.cpu().numpy(),
+                                     ss.cpu().numpy())
+        return HamAdaptiveResult(None, None, th, yh, na, nr, ss)

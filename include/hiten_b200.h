@@ -294,6 +294,21 @@ int hb_ham_rk_event(const hb_polyham *ham, int32_t method, int32_t arith, const 
                     const double *y0, const double *t_vals, int32_t m, double *traj, int32_t *hit, double *t_hit,
                     double *y_hit, int32_t *n_rows, void *workspace, void *stream);
 
+/* ---- AdaptiveRK on a polynomial Hamiltonian system: the `_ham` kernels of _DOP853 / _RK45
+ * (algorithms/integrators/rk.py: _integrate_dop853_ham :2553-2676 with _dop853_build_dense_cache_ham :1878,
+ * _integrate_dop853_until_event_ham :2807-2868 with _dop853_refine_in_step_ham :2106, _integrate_rk45_ham :1403-1456,
+ * _integrate_rk45_until_event_ham :1589-1633).  integ->method = HB_DOP853 or HB_RK45; same controller and first-step
+ * rule as the CR3BP kernels; no direction argument (see hb_ham_rk_dense).
+ * dense: y0[n][6], t_eval[m] (DEVICE, ascending) -> states[n][m][6] and (optional) derivs[n][m][6] = the vector field
+ *        re-evaluated at every output sample (_Solution.derivatives); n_acc / n_rej / status per trajectory.
+ * event: status[i] = HB_TRAJ_HIT with the refined t_hit[i] / y_hit[i][6], else t_hit = tmax reached, y_hit = last state. */
+int hb_ham_adaptive_dense(const hb_polyham *ham, const hb_integ *integ, int64_t n, const double *y0,
+                          const double *t_eval, int32_t m, double *states, double *derivs, int32_t *n_acc,
+                          int32_t *n_rej, int32_t *status, void *workspace, void *stream);
+int hb_ham_adaptive_event(const hb_polyham *ham, const hb_integ *integ, const hb_event *ev, int64_t n,
+                          const double *y0, double t0, double tmax, double *t_hit, double *y_hit, int32_t *n_acc,
+                          int32_t *n_rej, int32_t *status, void *workspace, void *stream);
+
 /* Seed lifting for the centre-manifold map: replaces the per-seed Python Brent solves of
  * _CenterManifoldInterface.lift_plane_point / solve_missing_coord (algorithms/poincare/centermanifold/
  * interfaces.py:297-337, 212-268; solve_bracketed_brent algorithms/utils/rootfinding.py:92-190) that the seeding

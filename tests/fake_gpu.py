@@ -158,6 +158,32 @@ def integrate_rk_ham_until_event(table, y0, t_vals, order, event, *, want_trajec
     return SymplecticEventResult(hit, th, yh, np.zeros(len(y0), np.int64), None)
 
 
+def integrate_adaptive_ham(table, y0, t_eval, *, integ=None, want_derivatives=True, **kw):
+    from hiten_b200.symplectic import HamAdaptiveResult
+    ham = O.PolyHam(table.ptr, table.deg, table.coef, table.exp)
+    s = O.system(O.SYS_POLYHAM, ham=ham)
+    y0 = np.asarray(y0)
+    states = np.stack([O.adaptive_dense(s, integ.method, _tol(integ), y, np.asarray(t_eval))[0] for y in y0])
+    derivs = np.stack([[O.polyham_rhs(ham, row) for row in tr] for tr in states]) if want_derivatives else None
+    z = np.zeros(len(y0), np.int32)
+    return HamAdaptiveResult(states, derivs, None, None, z, z, z)
+
+
+def integrate_adaptive_ham_until_event(table, y0, t0, tmax, event, *, integ=None, **kw):
+    from hiten_b200.symplectic import HamAdaptiveResult
+    ham = O.PolyHam(table.ptr, table.deg, table.coef, table.exp)
+    s = O.system(O.SYS_POLYHAM, ham=ham)
+    idx, offset, direction, xtol, gtol = event
+    ev = O.HoEvent(int(idx), float(offset), int(direction), xtol, gtol)
+    y0 = np.asarray(y0)
+    th, yh, st = np.zeros(len(y0)), np.zeros((len(y0), 6)), np.zeros(len(y0), np.int32)
+    for i in range(len(y0)):
+        hit, t, y, yl, _ = O.adaptive_event(s, integ.method, _tol(integ), ev, y0[i], t0, tmax)
+        th[i], yh[i], st[i] = t, y, 1 if hit else 0
+    z = np.zeros(len(y0), np.int32)
+    return HamAdaptiveResult(None, None, th, yh, z, z, st)
+
+
 def patch(monkeypatch):
     import hiten_b200.corrector as corr
     monkeypatch.setattr(corr, "correct_orbits", correct_orbits)
@@ -176,6 +202,8 @@ def patch(monkeypatch):
     monkeypatch.setattr(symp, "integrate_symplectic", integrate_symplectic)
     monkeypatch.setattr(symp, "integrate_symplectic_until_event", integrate_symplectic_until_event)
     monkeypatch.setattr(symp, "integrate_rk_ham", integrate_rk_ham)
+    monkeypatch.setattr(symp, "integrate_adaptive_ham", integrate_adaptive_ham)
+    monkeypatch.setattr(symp, "integrate_adaptive_ham_until_event", integrate_adaptive_ham_until_event)
     monkeypatch.setattr(symp, "integrate_rk_ham_until_event", integrate_rk_ham_until_event)
     import hiten_b200.connections as conn
     monkeypatch.setattr(conn, "find_connections", find_connections)

@@ -337,7 +337,7 @@ def test_fixed_step_rk_classes_on_the_hamiltonian_system(ref, monkeypatch):
     import fake_gpu
     import hiten_b200
     from hiten.algorithms.dynamics.base import _DirectedSystem
-    from hiten.algorithms.integrators.rk import RungeKutta
+    from hiten.algorithms.integrators.rk import AdaptiveRK, RungeKutta
     from hiten.algorithms.poincare.singlehit.backend import _get_cached_plane_event_fn
     from hiten.algorithms.types.configs import EventConfig
     system, l1, halo = ref
@@ -359,6 +359,16 @@ def test_fixed_step_rk_classes_on_the_hamiltonian_system(ref, monkeypatch):
         nh = RungeKutta(order=4).integrate(hamsys, y0.copy(), np.linspace(0.0, 0.05, 6),
                                            event_fn=_get_cached_plane_event_fn(2, 10.0), event_cfg=cfg)
         out["nohit"] = (nh.times.copy(), nh.states.copy())
+        for order in (5, 8):                                           # _RK45 / _DOP853 `_ham` kernels
+            integ = AdaptiveRK(order=order, rtol=1e-11, atol=1e-12)
+            sol = integ.integrate(hamsys, y0.copy(), np.linspace(0.0, 2.0, 41))
+            out[f"agrid{order}"] = (sol.times.copy(), sol.states.copy(), sol.derivatives.copy())
+            ev = integ.integrate(hamsys, y0.copy(), np.linspace(0.0, 6.0, 301),
+                                 event_fn=_get_cached_plane_event_fn(2, 0.0), event_cfg=cfg)
+            out[f"aevent{order}"] = (ev.times.copy(), ev.states.copy())
+            nh = integ.integrate(hamsys, y0.copy(), np.linspace(0.0, 0.05, 6),
+                                 event_fn=_get_cached_plane_event_fn(2, 10.0), event_cfg=cfg)
+            out[f"anohit{order}"] = (nh.times.copy(), nh.states.copy())
         return out
 
     want = run_all()
@@ -369,6 +379,9 @@ def test_fixed_step_rk_classes_on_the_hamiltonian_system(ref, monkeypatch):
     d0, e0 = symp.integrate_rk_ham, symp.integrate_rk_ham_until_event
     monkeypatch.setattr(symp, "integrate_rk_ham", lambda *a, **k: (calls.append("grid"), d0(*a, **k))[1])
     monkeypatch.setattr(symp, "integrate_rk_ham_until_event", lambda *a, **k: (calls.append("event"), e0(*a, **k))[1])
+    d1, e1 = symp.integrate_adaptive_ham, symp.integrate_adaptive_ham_until_event
+    monkeypatch.setattr(symp, "integrate_adaptive_ham", lambda *a, **k: (calls.append("agrid"), d1(*a, **k))[1])
+    monkeypatch.setattr(symp, "integrate_adaptive_ham_until_event", lambda *a, **k: (calls.append("aevent"), e1(*a, **k))[1])
     try:
         got = run_all()
         with pytest.raises(Exception):
@@ -376,6 +389,7 @@ def test_fixed_step_rk_classes_on_the_hamiltonian_system(ref, monkeypatch):
     finally:
         hiten_b200.uninstall()
     assert calls.count("grid") == 3 and calls.count("event") == 4
+    assert calls.count("agrid") == 2 and calls.count("aevent") == 4
     for k in want:
         for a, b in zip(got[k], want[k]):
             assert np.array_equal(a, b), k

@@ -71,3 +71,45 @@ def test_batch_vs_oracle(gold):
         assert hit == r.hit[i] and th == r.t_hit[i] and np.array_equal(yh, r.y_hit[i])
     with pytest.raises(ValueError):
         S.integrate_rk_ham(tab, y0[:2], t, 5)
+
+
+# ---- AdaptiveRK (DOP853 / RK45) `_ham` kernels: hb_ham_adaptive_dense / _event ---------------------------------------
+@pytest.mark.parametrize("order,method", [(853, 853), (45, 45)])
+def test_adaptive_grid_derivatives_and_events_vs_reference(gold, order, method):
+    import hiten_b200 as hb
+    from hiten_b200 import symplectic as S
+    h, tab, _, _ = gold
+    integ = hb.make_integ(method=method, rtol=1e-11, atol=1e-12, max_step=1e300)
+    r = S.integrate_adaptive_ham(tab, h["y0"][:4], h[f"grid_{order}"], integ=integ)
+    assert (r.status == 0).all()
+    print(f"[parity] AdaptiveRK {order} on the polynomial Hamiltonian: states bit-exact "
+          f"{np.array_equal(r.states, h[f'dense_{order}'])}, derivatives bit-exact "
+          f"{np.array_equal(r.derivatives, h[f'derivs_{order}'])}, steps {r.n_acc.tolist()} / {r.n_rej.tolist()}")
+    assert np.array_equal(r.states, h[f"dense_{order}"]) and np.array_equal(r.derivatives, h[f"derivs_{order}"])
+    e = S.integrate_adaptive_ham_until_event(tab, h["y0"][:4], 0.0, 6.0, (2, 0.0, 0, 1e-12, 1e-12), integ=integ)
+    assert (e.status == 1).all()
+    assert np.array_equal(e.t_hit, h[f"event_{order}"][:, 0]) and np.array_equal(e.y_hit, h[f"event_{order}"][:, 1:])
+    nh = S.integrate_adaptive_ham_until_event(tab, h["y0"][:1], 0.0, 0.05, (2, 10.0, 0, 1e-12, 1e-12), integ=integ)
+    assert nh.status[0] == 0 and nh.t_hit[0] == h[f"nohit_{order}"][0] and np.array_equal(nh.y_hit[0], h[f"nohit_{order}"][1:])
+    fast = S.integrate_adaptive_ham(tab, h["y0"][:4], h[f"grid_{order}"],
+                                    integ=hb.make_integ(method=method, arith="fast", rtol=1e-11, atol=1e-12, max_step=1e300))
+    assert np.abs(fast.states - h[f"dense_{order}"]).max() <= 1e-8
+
+
+def test_adaptive_batch_vs_oracle(gold):
+    import hiten_b200 as hb
+    from hiten_b200 import symplectic as S
+    h, tab, ham, g = gold
+    rng = np.random.default_rng(12)
+    seeds = g["seeds_p3"][rng.integers(0, len(g["seeds_p3"]), 1500)]
+    y0 = np.zeros((1500, 6))
+    y0[:, 1], y0[:, 4], y0[:, 2], y0[:, 5] = seeds[:, 0], seeds[:, 1], seeds[:, 2], seeds[:, 3]
+    sys_ = O.system(O.SYS_POLYHAM, ham=ham)
+    t = np.linspace(0.0, 3.0, 61)
+    for method, om in ((853, O.DOP853), (45, O.RK45)):
+        r = S.integrate_adaptive_ham(tab, y0, t, integ=hb.make_integ(method=method), want_derivatives=False)
+        assert r.derivatives is None and (r.status == 0).all()
+        for i in rng.integers(0, 1500, 12):
+            st, counts = O.adaptive_dense(sys_, om, O.default_tol(), y0[i], t)
+            assert np.array_equal(r.states[i], st)
+            assert r.n_acc[i] == counts[0] and r.n_rej[i] == counts[1]

@@ -67,3 +67,17 @@ def test_reference_rk_test_suite_assertions(pend, arith):
     fwd, bwd = check_reference_rk_assertions(g, _run_rk(tab, arith))
     if arith == "parity":
         assert np.array_equal(fwd, g["rk_rev_fwd"]) and np.array_equal(bwd, g["rk_rev_bwd"])
+
+
+@pytest.mark.parametrize("method,key", [(45, "rk_ivp_45"), (853, "rk_ivp_853")])
+def test_adaptive_classes_bit_exact_vs_reference_run(pend, method, key):
+    """AdaptiveRK(order=5 | 8) with the class defaults on the pendulum (test_rk.py:213-214) through hb_ham_adaptive_dense."""
+    import hiten_b200 as hb
+    from hiten_b200 import symplectic as S
+    g, tab = pend
+    rtol, atol, max_step, min_step = g["adaptive_defaults"]
+    integ = hb.make_integ(method=method, rtol=rtol, atol=atol, max_step=1e300, min_step=min_step)
+    r = S.integrate_adaptive_ham(tab, np.array([[0.1, 0, 0, 0, 0, 0.0]]), np.linspace(0.0, 20.0, 4000), integ=integ,
+                                 want_derivatives=False)
+    print(f"[parity] pendulum {key}: bit-exact {np.array_equal(r.states[0], g[key])}, steps {int(r.n_acc[0])}+{int(r.n_rej[0])}")
+    assert np.array_equal(r.states[0], g[key])
