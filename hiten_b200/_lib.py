@@ -111,6 +111,9 @@ SIGNATURES = {
     "hb_ham_symplectic_dense": (C.c_int, [C.POINTER(HbPolyHam), C.POINTER(HbSympOpts), C.c_int64, vp, vp, vp, vp, vp]),
     "hb_ham_symplectic_event": (C.c_int, [C.POINTER(HbPolyHam), C.POINTER(HbSympOpts), C.POINTER(HbEvent), C.c_int64, vp,
                                           vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "hb_ham_symplectic_jit": (C.c_int, [C.POINTER(HbPolyHam), C.POINTER(HbSympOpts), C.POINTER(HbEvent), C.c_int64, vp,
+                                        vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "hb_symp_jit_compile_host": (C.c_int, [vp, C.POINTER(C.c_int64), C.c_int32, C.POINTER(C.c_int64)]),
     "hb_ham_rk_dense": (C.c_int, [C.POINTER(HbPolyHam), C.c_int32, C.c_int32, C.c_int64, vp, vp, C.c_int32, vp, vp, vp, vp]),
     "hb_ham_rk_event": (C.c_int, [C.POINTER(HbPolyHam), C.c_int32, C.c_int32, C.POINTER(HbEvent), C.c_int64, vp, vp,
                                   C.c_int32, vp, vp, vp, vp, vp, vp, vp]),

@@ -318,6 +318,146 @@ std::string gen_source(const std::vector<TermHost> &terms, const int64_t *ptr, c
     return s;
 }
 
+// ---- the Tao integrator over a time grid (_ExtendedSymplectic.integrate, symplectic.py:564-782), specialised --------
+// Same generated gradient; the per-interval Tao parameters come from hb_tao_grid_prepare's table in HBM
+// (tab[m-1][3][n_sub], warp-uniform loads).  One trajectory per thread; `event` selects the terminal-plane-event form.
+const char *GRID_KERNEL = R"SRC(
+DEV void rhs(const double (&y)[6], double (&dy)[6])          // [dH/dP, -dH/dQ]
+{
+    double g[6];
+    grad(y, g);
+    dy[0] = g[3]; dy[1] = g[4]; dy[2] = g[5];
+    dy[3] = -g[0]; dy[4] = -g[1]; dy[5] = -g[2];
+}
+DEV double pick(const double (&v)[6], int i)
+{
+    return (i == 0) ? v[0] : (i == 1) ? v[1] : (i == 2) ? v[2] : (i == 3) ? v[3] : (i == 4) ? v[4] : v[5];
+}
+DEV void hermite6(const double (&y0)[6], const double (&f0)[6], const double (&y1)[6], const double (&f1)[6], double x,
+                  double h, double (&out)[6])                 // _hermite_eval_dense_symplectic (symplectic.py:229-279)
+{
+    const double x2 = MUL(x, x), x3 = MUL(x2, x);
+    const double H00 = ADD(SUB(MUL(2.0, x3), MUL(3.0, x2)), 1.0);
+    const double H10 = ADD(SUB(x3, MUL(2.0, x2)), x);
+    const double H01 = ADD(MUL(-2.0, x3), MUL(3.0, x2));
+    const double H11 = SUB(x3, x2);
+    UNROLL for (int d = 0; d < 6; ++d)
+        out[d] = ADD(ADD(ADD(MUL(H00, y0[d]), MUL(H10, MUL(h, f0[d]))), MUL(H01, y1[d])), MUL(H11, MUL(h, f1[d])));
+}
+DEV bool ev_crossed(double gp, double gn, int dir)            // utils.py:14-39
+{
+    if (dir == 0) return (gp < 0.0 && gn > 0.0) || (gp > 0.0 && gn < 0.0) || (gn == 0.0);
+    if (dir > 0) return (gp < 0.0 && gn > 0.0) || (gn == 0.0);
+    return (gp > 0.0 && gn < 0.0) || (gn == 0.0);
+}
+DEV bool ev_side(double gl, double gm, int dir)               // utils.py:43-69
+{
+    if (dir == 0) return (gl < 0.0 && gm > 0.0) || (gl > 0.0 && gm < 0.0);
+    if (dir > 0) return (gl < 0.0 && gm > 0.0);
+    return (gl > 0.0 && gm < 0.0);
+}
+extern "C" __global__ void __launch_bounds__(128) symp_grid(const double *y0, long long n, int m, int n_sub,
+                                                            const double *tab, const double *t_vals, double *traj,
+                                                            int event, int ev_idx, int ev_dir, double ev_off,
+                                                            double xtol, double gtol, int *hit, double *t_hit,
+                                                            double *y_hit, int *n_rows, u64 *cursor)
+{
+    for (;;) {
+        const long long idx = (long long)atomicAdd(cursor, 1ULL);
+        if (idx >= n) break;
+        const double *s0 = y0 + idx * 6;
+        double Q[3], P[3], X[3], Y[3], yo[6], fo[6], yh[6], g_old = 0.0, th = 0.0;
+        UNROLL for (int d = 0; d < 6; ++d) { yo[d] = s0[d]; fo[d] = 0.0; yh[d] = 0.0; }
+        UNROLL for (int i = 0; i < 3; ++i) { Q[i] = X[i] = yo[i]; P[i] = Y[i] = yo[3 + i]; }
+        double *rows = traj ? traj + idx * (long long)m * 6 : nullptr;
+        if (rows) { UNROLL for (int d = 0; d < 6; ++d) rows[d] = yo[d]; }
+        if (event) { rhs(yo, fo); g_old = SUB(pick(yo, ev_idx), ev_off); }
+        int got = 0, nr = m;
+        for (int i = 0; i < m - 1; ++i) {
+            const double *tb = tab + (size_t)i * 3 * n_sub;
+#pragma unroll 1
+            for (int j = 0; j < n_sub; ++j) {
+                const double ts = tb[j], hd = MUL(0.5, ts), c = tb[n_sub + j], s = tb[2 * n_sub + j];
+#pragma unroll 1
+                for (int ph = 0; ph < 5; ++ph) {
+                    if (ph == 2) {
+                        UNROLL for (int i3 = 0; i3 < 3; ++i3) {
+                            const double qpx = ADD(Q[i3], X[i3]), qmx = SUB(Q[i3], X[i3]);
+                            const double ppy = ADD(P[i3], Y[i3]), pmy = SUB(P[i3], Y[i3]);
+                            Q[i3] = MUL(0.5, ADD(ADD(qpx, MUL(c, qmx)), MUL(s, pmy)));
+                            P[i3] = MUL(0.5, ADD(SUB(ppy, MUL(s, qmx)), MUL(c, pmy)));
+                            X[i3] = MUL(0.5, SUB(SUB(qpx, MUL(c, qmx)), MUL(s, pmy)));
+                            Y[i3] = MUL(0.5, SUB(ADD(ppy, MUL(s, qmx)), MUL(c, pmy)));
+                        }
+                    } else {
+                        const bool isA = (ph == 0) || (ph == 4);         // phi_a: (Q,Y); phi_b: (X,P)
+                        double pt[6], g[6];
+                        UNROLL for (int i3 = 0; i3 < 3; ++i3) { pt[i3] = isA ? Q[i3] : X[i3]; pt[3 + i3] = isA ? Y[i3] : P[i3]; }
+                        grad(pt, g);
+                        UNROLL for (int i3 = 0; i3 < 3; ++i3) {
+                            const double dq = MUL(hd, g[i3]), dp = MUL(hd, g[3 + i3]);
+                            if (isA) { P[i3] = SUB(P[i3], dq); X[i3] = ADD(X[i3], dp); }
+                            else { Q[i3] = ADD(Q[i3], dp); Y[i3] = SUB(Y[i3], dq); }
+                        }
+                    }
+                }
+            }
+            double yn[6] = {Q[0], Q[1], Q[2], P[0], P[1], P[2]};
+            if (event) {
+                double fn[6];
+                rhs(yn, fn);
+                const double g_new = SUB(pick(yn, ev_idx), ev_off);
+                if (ev_crossed(g_old, g_new, ev_dir)) {
+                    const double t0 = t_vals[i], h = SUB(t_vals[i + 1], t0);
+                    double a = 0.0, b = 1.0, g_left = g_old, xh = 1.0;
+                    bool done = false;
+                    for (int it = 0; it < 128; ++it) {
+                        const double mid = MUL(0.5, ADD(a, b));
+                        hermite6(yo, fo, yn, fn, mid, h, yh);
+                        const double g_mid = SUB(pick(yh, ev_idx), ev_off);
+                        if (fabs(g_mid) <= gtol) { xh = mid; done = true; break; }
+                        if (ev_side(g_left, g_mid, ev_dir)) b = mid;
+                        else { a = mid; g_left = g_mid; }
+                        if (MUL(SUB(b, a), fabs(h)) <= xtol) break;
+                    }
+                    if (!done) { xh = b; hermite6(yo, fo, yn, fn, b, h, yh); }
+                    th = ADD(t0, MUL(xh, h));
+                    got = 1;
+                    nr = i + 1;
+                    break;
+                }
+                g_old = g_new;
+                UNROLL for (int d = 0; d < 6; ++d) { yo[d] = yn[d]; fo[d] = fn[d]; }
+            }
+            if (rows) {
+                double *o = rows + (long long)(i + 1) * 6;
+                UNROLL for (int d = 0; d < 6; ++d) o[d] = yn[d];
+            }
+        }
+        if (event) {
+            if (!got) {
+                th = t_vals[m - 1];
+                UNROLL for (int d = 0; d < 6; ++d) yh[d] = yo[d];
+            }
+            hit[idx] = got;
+            t_hit[idx] = th;
+            n_rows[idx] = nr;
+            UNROLL for (int d = 0; d < 6; ++d) y_hit[idx * 6 + d] = yh[d];
+        }
+    }
+}
+)SRC";
+
+std::string gen_grid_source(const std::vector<TermHost> &terms, const int64_t *ptr, int arith)
+{
+    std::string s;
+    appendf(s, "#define PARITY %d\n", arith == HB_ARITH_PARITY ? 1 : 0);
+    s += PRELUDE;
+    s += gen_grad(terms, ptr);
+    s += GRID_KERNEL;
+    return s;
+}
+
 // ---- NVRTC + driver API through dlopen -----------------------------------------------------------
 typedef int (*nvrtcCreate_t)(void **, const char *, const char *, int, const char *const *, const char *const *);
 typedef int (*nvrtcCompile_t)(void *, int, const char *const *);
@@ -442,6 +582,87 @@ extern "C" int hb_cm_jit_compile_host(const void *terms_host, const int64_t *ptr
         source_out[n] = 0;
     }
     return rc;
+}
+
+// source -> CUfunction (compiled once per process and source)
+static int get_function(const std::string &src, const char *name, void **fn_out)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_functions.find(src);
+    if (it != g_functions.end()) { *fn_out = it->second; return HB_OK; }
+    if (!load_driver()) return HB_ERR_NODEVICE;
+    std::vector<char> cubin;
+    int rc = compile_cubin(src, cubin);
+    if (rc != HB_OK) return rc;
+    void *mod = nullptr, *fn = nullptr;
+    int e = g_api.load(&mod, cubin.data());
+    if (e != 0) return 1000 + e;
+    e = g_api.getfn(&fn, mod, name);
+    if (e != 0) return 1000 + e;
+    g_functions.emplace(src, fn);
+    *fn_out = fn;
+    return HB_OK;
+}
+
+// Host-only: generate + compile the specialised GRID kernel for a term table in HOST memory (no GPU needed).
+extern "C" int hb_symp_jit_compile_host(const void *terms_host, const int64_t *ptr, int32_t arith, int64_t *cubin_bytes)
+{
+    if (!ptr || (ptr[6] > 0 && !terms_host) || (arith != HB_ARITH_PARITY && arith != HB_ARITH_FAST)) return HB_ERR_BADARG;
+    std::vector<TermHost> terms((size_t)ptr[6]);
+    if (ptr[6]) memcpy(terms.data(), terms_host, sizeof(TermHost) * (size_t)ptr[6]);
+    const std::string src = gen_grid_source(terms, ptr, arith);
+    std::lock_guard<std::mutex> lk(g_mu);
+    std::vector<char> cubin;
+    const int rc = compile_cubin(src, cubin);
+    if (rc == HB_OK && cubin_bytes) *cubin_bytes = (int64_t)cubin.size();
+    return rc;
+}
+
+// hb_ham_symplectic_dense / hb_ham_symplectic_event with the run-time specialised gradient: same arguments, same
+// results (bit-identical in the parity variant).  `ev` == NULL selects the grid form.
+extern "C" int hb_ham_symplectic_jit(const hb_polyham *ham, const hb_symp_opts *o, const hb_event *ev, int64_t n,
+                                     const double *y0, const double *t_vals_signed, const double *tao_tab, double *traj,
+                                     int32_t *hit, double *t_hit, double *y_hit, int32_t *n_rows, void *workspace,
+                                     void *stream)
+{
+    if (!ham || !o || !workspace || n < 0) return HB_ERR_BADARG;
+    if (ham->n_dof != 3 || ham->max_deg < 0 || ham->max_deg > 60) return HB_ERR_UNSUPPORTED;
+    if (o->order < 2 || (o->order % 2) != 0 || o->order > 8) return HB_ERR_UNSUPPORTED;
+    if (o->m < 2 || o->n_sub <= 0 || o->n_sub > HB_MAX_TAO_SUBSTEPS) return HB_ERR_BADARG;
+    if (o->arith != HB_ARITH_PARITY && o->arith != HB_ARITH_FAST) return HB_ERR_BADARG;
+    if (n > 0 && (!y0 || !tao_tab || (ham->ptr[6] > 0 && !ham->terms))) return HB_ERR_BADARG;
+    if (ev) {
+        if (ev->idx < 0 || ev->idx > 5) return HB_ERR_BADARG;
+        if (n > 0 && (!t_vals_signed || !hit || !t_hit || !y_hit || !n_rows)) return HB_ERR_BADARG;
+    } else if (n > 0 && !traj) return HB_ERR_BADARG;
+    if (n == 0) return HB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    std::vector<TermHost> terms((size_t)ham->ptr[6]);
+    if (ham->ptr[6]) {
+        HB_CUDA_TRY(cudaMemcpyAsync(terms.data(), ham->terms, sizeof(TermHost) * terms.size(), cudaMemcpyDeviceToHost, st));
+        HB_CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    void *fn = nullptr;
+    int rc = get_function(gen_grid_source(terms, ham->ptr, o->arith), "symp_grid", &fn);
+    if (rc != HB_OK) return rc;
+    HB_CUDA_TRY(cudaMemsetAsync(workspace, 0, sizeof(HbWorkspace), st));
+    int dev = 0, sms = 148, per_sm = 2;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_api.occ && g_api.occ(&per_sm, fn, 128, 0) != 0) per_sm = 2;
+    if (per_sm < 1) per_sm = 1;
+    long long blocks = (n + 127) / 128;
+    const long long cap = (long long)sms * per_sm;
+    if (blocks > cap) blocks = cap;
+    long long nn = n;
+    int m = o->m, n_sub = o->n_sub, event = ev ? 1 : 0, ev_idx = ev ? ev->idx : 0, ev_dir = ev ? ev->direction : 0;
+    double ev_off = ev ? ev->offset : 0.0, xtol = ev ? ev->xtol : 0.0, gtol = ev ? ev->gtol : 0.0;
+    unsigned long long *cursor = (unsigned long long *)workspace;
+    void *args[] = {(void *)&y0, (void *)&nn, (void *)&m, (void *)&n_sub, (void *)&tao_tab, (void *)&t_vals_signed,
+                    (void *)&traj, (void *)&event, (void *)&ev_idx, (void *)&ev_dir, (void *)&ev_off, (void *)&xtol,
+                    (void *)&gtol, (void *)&hit, (void *)&t_hit, (void *)&y_hit, (void *)&n_rows, (void *)&cursor};
+    const int e = g_api.launch(fn, (unsigned)blocks, 1, 1, 128, 1, 1, 0, (void *)st, args, nullptr);
+    return e == 0 ? HB_OK : 1000 + e;
 }
 
 // Same contract as hb_cm_poincare_map (hb_cm.cu), specialised kernel.

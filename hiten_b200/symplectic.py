@@ -46,10 +46,23 @@ def _prep(table, y0, t_vals_signed, order, c_omega_heuristic, arith, device):
     return host, yd, t, tabd, o, ham, keep
 
 
+def jit_compile_host(table, arith="parity"):
+    """Generate + compile the specialised grid kernel offline (no GPU): returns the cubin size in bytes."""
+    rec = table.packed()
+    ptr = (L.C.c_int64 * 7)(*[int(x) for x in table.ptr])
+    nbytes = L.C.c_int64(0)
+    L.check(L.load().hb_symp_jit_compile_host(rec.ctypes.data if rec.size else None, ptr,
+                                              {"parity": L.HB_ARITH_PARITY, "fast": L.HB_ARITH_FAST}[arith],
+                                              L.C.byref(nbytes)), "hb_symp_jit_compile_host")
+    return int(nbytes.value)
+
+
 def integrate_symplectic(table, y0, t_vals_signed, order, *, c_omega_heuristic=20.0, arith="parity", device=None,
-                         stream=None):
+                         stream=None, jit=True):
     """_integrate_symplectic for a batch: y0 [N, 6] -> traj [N, m, 6] on the signed grid (t_vals * fwd).
-    Host ndarray in -> ndarray out; CUDA tensor in -> CUDA tensor out.  Bit-identical to the reference (parity)."""
+    Host ndarray in -> ndarray out; CUDA tensor in -> CUDA tensor out.  Bit-identical to the reference (parity).
+    jit=True (default) runs the kernel specialised for this Hamiltonian (hb_ham_symplectic_jit), jit=False the
+    table-driven kernel (hb_ham_symplectic_dense); both give the same bits in the parity variant."""
     _require_cuda()
     lib = L.load()
     device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -58,8 +71,13 @@ def integrate_symplectic(table, y0, t_vals_signed, order, *, c_omega_heuristic=2
         n = int(yd.shape[0])
         traj = torch.empty((n, t.size, 6), dtype=torch.float64, device=device)
         ws = workspace(device)
-        L.check(lib.hb_ham_symplectic_dense(ham, L.C.byref(o), n, yd.data_ptr(), tabd.data_ptr(), traj.data_ptr(),
-                                            ws.data_ptr(), _stream_ptr(stream)), "hb_ham_symplectic_dense")
+        if jit:
+            L.check(lib.hb_ham_symplectic_jit(ham, L.C.byref(o), None, n, yd.data_ptr(), None, tabd.data_ptr(),
+                                              traj.data_ptr(), None, None, None, None, ws.data_ptr(),
+                                              _stream_ptr(stream)), "hb_ham_symplectic_jit")
+        else:
+            L.check(lib.hb_ham_symplectic_dense(ham, L.C.byref(o), n, yd.data_ptr(), tabd.data_ptr(), traj.data_ptr(),
+                                                ws.data_ptr(), _stream_ptr(stream)), "hb_ham_symplectic_dense")
         return traj.cpu().numpy() if host else traj
 
 
@@ -73,7 +91,7 @@ class SymplecticEventResult:
 
 
 def integrate_symplectic_until_event(table, y0, t_vals_signed, order, event, *, c_omega_heuristic=20.0, arith="parity",
-                                     want_trajectory=False, device=None, stream=None):
+                                     want_trajectory=False, device=None, stream=None, jit=True):
     """_integrate_symplectic_until_event for a batch; `event` = (idx, offset, direction, xtol, gtol) of the plane event
     g = y[idx] - offset."""
     _require_cuda()
@@ -93,10 +111,11 @@ def integrate_symplectic_until_event(table, y0, t_vals_signed, order, event, *, 
         t_hit = torch.zeros(n, dtype=torch.float64, device=device)
         y_hit = torch.zeros((n, 6), dtype=torch.float64, device=device)
         ws = workspace(device)
-        L.check(lib.hb_ham_symplectic_event(ham, L.C.byref(o), L.C.byref(ev), n, yd.data_ptr(), td.data_ptr(),
-                                            tabd.data_ptr(), traj.data_ptr() if traj is not None else None,
-                                            hit.data_ptr(), t_hit.data_ptr(), y_hit.data_ptr(), n_rows.data_ptr(),
-                                            ws.data_ptr(), _stream_ptr(stream)), "hb_ham_symplectic_event")
+        fn = lib.hb_ham_symplectic_jit if jit else lib.hb_ham_symplectic_event
+        L.check(fn(ham, L.C.byref(o), L.C.byref(ev), n, yd.data_ptr(), td.data_ptr(), tabd.data_ptr(),
+                   traj.data_ptr() if traj is not None else None, hit.data_ptr(), t_hit.data_ptr(), y_hit.data_ptr(),
+                   n_rows.data_ptr(), ws.data_ptr(), _stream_ptr(stream)),
+                "hb_ham_symplectic_jit" if jit else "hb_ham_symplectic_event")
         if host:
             return SymplecticEventResult(hit.cpu().numpy().astype(bool), t_hit.cpu().numpy(), y_hit.cpu().numpy(),
                                          n_rows.cpu().numpy().astype(np.int64),

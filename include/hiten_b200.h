@@ -281,6 +281,16 @@ int hb_ham_symplectic_event(const hb_polyham *ham, const hb_symp_opts *opts, con
                             const double *y0, const double *t_vals_signed, const double *tao_tab, double *traj,
                             int32_t *hit, double *t_hit, double *y_hit, int32_t *n_rows, void *workspace, void *stream);
 
+/* The same two calls with a kernel SPECIALISED at run time for this Hamiltonian (hb_cm_jit.cu: the generated straight-line
+ * gradient of hb_cm_poincare_map_jit inside the grid loop; NVRTC, cached per Hamiltonian and arithmetic).  ev == NULL:
+ * hb_ham_symplectic_dense (hit / t_hit / y_hit / n_rows unused); otherwise hb_ham_symplectic_event.  Bit-identical to the
+ * table-driven kernels in the parity variant; returns HB_ERR_UNSUPPORTED if NVRTC is not available.              */
+int hb_ham_symplectic_jit(const hb_polyham *ham, const hb_symp_opts *opts, const hb_event *ev, int64_t n,
+                          const double *y0, const double *t_vals_signed, const double *tao_tab, double *traj,
+                          int32_t *hit, double *t_hit, double *y_hit, int32_t *n_rows, void *workspace, void *stream);
+/* Host-only: generate + compile that kernel for a term table in HOST memory (no GPU needed); *cubin_bytes = cubin size. */
+int hb_symp_jit_compile_host(const void *terms_host, const int64_t *ptr, int32_t arith, int64_t *cubin_bytes);
+
 /* ---- _FixedStepRK.integrate on a polynomial Hamiltonian system: the `_ham` kernels of the RK classes
  * (algorithms/integrators/rk.py: _integrate_fixed_rk_ham :592-656, rk_embedded_step_ham_jit_kernel :216-270,
  * _integrate_fixed_rk_until_event_ham :722-757 + _hermite_refine_in_step :331-391).  method = HB_RK4 / HB_RK6 / HB_RK8;

@@ -160,3 +160,15 @@ def test_tao_grid_table_is_host_only_and_matches_the_reference_formulas():
     ev = _lib.HbEvent(9, 0, 0.0, 1e-12, 1e-12)                           # component 9 does not exist
     assert lib.hb_ham_symplectic_event(C.byref(ham), C.byref(o), C.byref(ev), 0, None, None, None, None, None, None, None,
                                        None, None, None) < 0
+
+
+def test_specialised_grid_kernel_compiles_offline():
+    """hb_symp_jit_compile_host: the run-time specialised Tao grid kernel (generated gradient + grid / event loop) compiles
+    for sm_100a with NVRTC without a GPU, in both arithmetic variants, for the CM table and for the pendulum."""
+    from hiten_b200 import symplectic as S
+    from hiten_b200.centermanifold import PolyTable
+    for f in ("cm_map.npz", "pendulum.npz"):
+        g = np.load(os.path.join(REPO, "tests", "golden", f))
+        tab = PolyTable(g["jac_ptr"], g["jac_deg"], g["jac_coef"], g["jac_exp"])
+        for arith in ("parity", "fast"):
+            assert S.jit_compile_host(tab, arith) > 4096

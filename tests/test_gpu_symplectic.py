@@ -22,37 +22,41 @@ def gold():
             O.PolyHam(g["jac_ptr"], g["jac_deg"], g["jac_coef"], g["jac_exp"]), g)
 
 
+@pytest.mark.parametrize("jit", [True, False], ids=["specialised", "table"])
 @pytest.mark.parametrize("name", DENSE)
-def test_grid_trajectories_vs_reference(gold, name):
+def test_grid_trajectories_vs_reference(gold, name, jit):
     from hiten_b200 import symplectic as S
     s, tab, _, _ = gold
     order, fwd, t0, tf, steps, c_om = s[name + "_cfg"]
     t_signed = np.linspace(t0, tf, int(steps)) * fwd
     ref = s[name]
-    traj = S.integrate_symplectic(tab, s["y0"][: ref.shape[0]], t_signed, int(order), c_omega_heuristic=c_om)
+    traj = S.integrate_symplectic(tab, s["y0"][: ref.shape[0]], t_signed, int(order), c_omega_heuristic=c_om, jit=jit)
     print(f"[parity] Tao grid {name}: {ref.shape[0]} x {int(steps)} samples, max |d| {np.abs(traj - ref).max():.2e}, "
           f"bit-exact {np.array_equal(traj, ref)}")
     assert np.array_equal(traj, ref)                                                  # bit-exact
-    fast = S.integrate_symplectic(tab, s["y0"][: ref.shape[0]], t_signed, int(order), c_omega_heuristic=c_om, arith="fast")
+    fast = S.integrate_symplectic(tab, s["y0"][: ref.shape[0]], t_signed, int(order), c_omega_heuristic=c_om, arith="fast",
+                                  jit=jit)
     assert np.abs(fast - ref).max() <= 1e-9
 
 
+@pytest.mark.parametrize("jit", [True, False], ids=["specialised", "table"])
 @pytest.mark.parametrize("name", EVENTS)
-def test_terminal_events_vs_reference(gold, name):
+def test_terminal_events_vs_reference(gold, name, jit):
     from hiten_b200 import symplectic as S
     s, tab, _, _ = gold
     order, fwd, tf, steps, idx, off, direction = s[name + "_cfg"]
     t_signed = np.linspace(0.0, tf, int(steps)) * fwd
     ref = s[name]
     r = S.integrate_symplectic_until_event(tab, s["y0"], t_signed, int(order), (int(idx), off, int(direction), 1e-12, 1e-12),
-                                           want_trajectory=True)
+                                           want_trajectory=True, jit=jit)
     assert np.array_equal(r.hit, ref[:, 0].astype(bool))                              # identical hit flags
     assert np.array_equal(r.t_hit * fwd, ref[:, 1]) and np.array_equal(r.y_hit, ref[:, 2:])   # bit-exact
     full = S.integrate_symplectic(tab, s["y0"], t_signed, int(order))
     for i in range(len(ref)):
         assert np.array_equal(r.traj[i, : r.n_rows[i]], full[i, : r.n_rows[i]])
         assert r.n_rows[i] == (int(steps) if not r.hit[i] else r.n_rows[i]) and 1 <= r.n_rows[i] <= int(steps)
-    r2 = S.integrate_symplectic_until_event(tab, s["y0"], t_signed, int(order), (int(idx), off, int(direction), 1e-12, 1e-12))
+    r2 = S.integrate_symplectic_until_event(tab, s["y0"], t_signed, int(order), (int(idx), off, int(direction), 1e-12, 1e-12),
+                                            jit=jit)
     assert r2.traj is None and np.array_equal(r2.t_hit, r.t_hit) and np.array_equal(r2.y_hit, r.y_hit)
 
 
