@@ -218,7 +218,8 @@ def secondary_configs(hb, torch, steps, flush, barrier):
     t = time_steps(run_symp, steps, flush, barrier, torch)
     out["tao4_grid_1e5_trajectories_x_100_intervals"] = {
         "steps_per_s": 1e7 * steps / t, "ms": 1e3 * t / steps, "tflops": 1e7 * steps * 12 * 610.0 / t / 1e12,
-        "note": "table-driven gradient (API-parity path); 12 gradient evaluations per Tao-4 step"}
+        "note": "_ExtendedSymplectic.integrate through hb_ham_symplectic_jit (run-time specialised gradient); 12 gradient "
+                "evaluations of ~610 flop per Tao-4 step (SURVEY 8d), 48 B written per step"}
     # BASELINE configs[0] / [1] as they are (50 / 200 trajectories): small-batch latency, not throughput
     from hiten_b200 import synodic as syn
     c1 = np.load(os.path.join(REPO, "tests", "golden", "c1_manifold.npz"))
