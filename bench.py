@@ -202,7 +202,7 @@ def secondary_configs(hb, torch, steps, flush, barrier):
         out[label] = {"steps_per_s": cm_steps * steps / t, "crossings_per_s": int(f.sum().item()) * steps / t,
                       "ms_per_return": 1e3 * t / steps, "tflops": cm_steps * steps * 8100.0 / t / 1e12}
     out["cm_map_tao4_1e5_seeds"]["note"] = ("critical-path bound: the slowest seed needs ~1300 sequential steps of "
-                                            "~20 us; 1e6 seeds fill the machine")
+                                            "~9 us (11.9 ms on its own); 1e6 seeds fill the machine")
     # the Tao integrator CLASS over a time grid (_ExtendedSymplectic.integrate): 1e5 trajectories x 100 grid intervals
     from hiten_b200 import symplectic as symp
     y6 = torch.zeros((100_000, 6), dtype=torch.float64, device="cuda")

@@ -181,9 +181,23 @@ extern "C" __global__ void __launch_bounds__(256) cm_map(const double *seeds, lo
     long long idx = -1;
     int it = 0, it_stop = 0;
     bool have = false, exhausted = false;
+    // First fill WITHOUT the queue: item = rank * 32 + lane, warps ranked warp-index-major across the grid (warp 0 of every
+    // CTA first, then warp 1 of every CTA, ...).  A short work list -- the later rounds, when a few thousand slow seeds
+    // are left -- then occupies FULL warps, one per CTA and so about one per SM sub-partition, instead of one or two
+    // lanes of every resident warp (with the per-lane queue each of the 16 warps of an SM held a couple of seeds and a
+    // step cost 16 warps' worth of issue slots).  Refills while a round is running still come from the queue, which
+    // starts behind the statically assigned items.
+    const long long lanes_total = (long long)gridDim.x * blockDim.x;
+    bool first_fill = true;
     for (;;) {
         if (!have && !exhausted) {
-            const long long k = (long long)atomicAdd(cursor, 1ULL);
+            long long k;
+            if (first_fill) {
+                k = ((long long)(threadIdx.x >> 5) * gridDim.x + blockIdx.x) * 32 + (threadIdx.x & 31);
+                first_fill = false;
+            } else {
+                k = lanes_total + (long long)atomicAdd(cursor, 1ULL);
+            }
             if (k < count) {
                 if (list_in) {
                     idx = list_in[k];

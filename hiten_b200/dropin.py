@@ -17,9 +17,12 @@ No reference file is edited.  What is rebound (paths relative to hiten/):
   * `_DOP853.integrate` (algorithms/integrators/rk.py:2221), `_RK45.integrate` (:1138) and
     `_FixedStepRK.integrate` (:422; _RK4 / _RK6 / _RK8) for the 6-state CR3BP system;
   * `_ExtendedSymplectic.integrate` (algorithms/integrators/symplectic.py:877) for the polynomial Hamiltonian systems
-    (grid and plane-event forms; `_propagate_dynsys(method="symplectic")` builds this class).
-Anything the GPU path cannot express (user-defined RHS or event callables, RK integration of polynomial-Hamiltonian
-systems outside the centre-manifold map, 42-state RK45 / fixed-step integration, cubic synodic refinement) is handed to the reference's ORIGINAL function -- that is the reference's
+    (grid and plane-event forms; `_propagate_dynsys(method="symplectic")` builds this class);
+  * the `_ham` branches of the three RK classes above for the reference's bare `_HamiltonianSystem` (grid with
+    derivatives, plane events).
+Anything the GPU path cannot express (user-defined RHS or event callables, a `_DirectedSystem` around a Hamiltonian
+system in the RK classes -- which raises inside the reference --, 42-state RK45 / fixed-step integration, cubic synodic
+refinement) is handed to the reference's ORIGINAL function -- that is the reference's
 own code for inputs outside this path, not a fallback of the kernels: for recognised inputs a missing library
 or GPU raises.
 """
