@@ -234,3 +234,50 @@ def test_pipeline_equals_fused_on_a_bench_sized_slice_with_overflow_rerun():
     assert b.steps_capacity >= int(a.nacc.max().item()) > 96
     b.launch(y0)
     assert b.hit_count() == a.hit_count() and (b.status == 0).all().item() and b._extra == (None, None)
+
+
+def test_full_size_1e6_trajectories_oracle_sample_and_order_invariance():
+    """BASELINE configs[4] at full size (the bench batch: 1e6 trajectories through hb_cr3bp_section2). Size-independent
+    checks: (a) a strided sample of 512 trajectories equals the oracle bit for bit (hit times, hit states, end states);
+    (b) the reversed batch gives the same per-trajectory results under the index map — the persistent work queue and
+    the per-trajectory candidate lists make the result independent of scheduling; (c) every hit lies on the section."""
+    import torch
+    import bench
+    from hiten_b200 import synodic
+    n = bench.N_PER_GPU
+    ics, mu = bench.build_ics(n)
+    m = max(int(abs(bench.TF) / bench.GRID_DT) + 1, 100)
+    t_eval = np.linspace(0.0, bench.TF, m)
+    sec = synodic.make_section("y", 0.0, ("x", "z"), -1)
+    run = synodic.TubeSectionRunner(n, mu, t_eval, sec, forward=-1, flip=(0, 6), steps_capacity=160)   # the bench step
+    y0 = torch.from_numpy(np.ascontiguousarray(ics.T)).cuda()
+    run.launch(y0)
+    h = run.sorted_hits()
+    assert (run.status == 0).all().item()
+    yf = run.yf.t().cpu().numpy().copy()
+    nacc = run.nacc.cpu().numpy().copy()
+    assert len(h.times) == run.hit_count() > n
+    # (c) on the plane: a linear root between dense samples (exact up to rounding) or a left node within the
+    # reference's on-surface tolerance 1e-6 (synodic/backend.py:555-572)
+    assert np.abs(h.states[:, 1]).max() <= 1e-6 and np.median(np.abs(h.states[:, 1])) <= 1e-15
+    # (a) oracle on a strided sample
+    pick = np.arange(0, n, n // 512)[:512]
+    s = O.system(O.SYS_CR3BP6, mu, fwd=-1, flip=(0, 6))
+    dense, cnt = O.batch_dense(s, O.DOP853, O.default_tol(), ics[pick], t_eval, 8)
+    assert np.array_equal(dense[:, -1, :], yf[pick])
+    starts = np.concatenate(([0], np.cumsum(h.hits_per_traj)))
+    for j, i in enumerate(pick):
+        t, x = O.synodic_detect(-t_eval, dense[j], 1, 0.0, -1, (0, 2), 50, 1e-6, 1e-9, 1e-6)
+        a, b = starts[i], starts[i + 1]
+        assert b - a == len(t)
+        assert np.array_equal(h.times[a:b], t) and np.array_equal(h.states[a:b], x)
+        assert np.all(h.trajectory_indices[a:b] == i)
+    # (b) reversed batch
+    run.launch(torch.flip(y0, dims=[1]).contiguous())
+    hr = run.sorted_hits()
+    assert (run.status == 0).all().item()
+    assert np.array_equal(run.yf.t().cpu().numpy(), yf[::-1])
+    assert np.array_equal(run.nacc.cpu().numpy(), nacc[::-1])
+    assert np.array_equal(hr.hits_per_traj, h.hits_per_traj[::-1])
+    order = np.lexsort((np.arange(len(hr.times)), n - 1 - hr.trajectory_indices))     # stable within a trajectory
+    assert np.array_equal(hr.times[order], h.times) and np.array_equal(hr.states[order], h.states)
