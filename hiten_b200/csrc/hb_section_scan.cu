@@ -237,6 +237,20 @@ HB_DEV void mbar_wait(unsigned mbar, unsigned parity)
                      : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
 }
 
+// Can the segment between two neighbouring grid samples (event values gl, gr) produce a hit in process_segment()?
+// A left node within the on-surface tolerance may; otherwise a directed section needs the segment itself to cross in
+// that direction: the 51 sub-interval values are rounded points of the straight line from gl to gr, which rises or
+// falls by |gr - gl| / 51 >= max(|gl|, |gr|) / 51 per sub-interval -- far above their rounding error -- so a segment
+// running the other way has no sub-interval with (g_lo > 0, g_hi <= 0).  Segments dropped here are the upward
+// crossings of a direction = -1 section: half of all flagged segments of a tube.
+HB_DEV bool segment_may_hit(int dir, double gl, double gr, double tol)
+{
+    if (fabs(gl) < tol) return true;
+    if (dir < 0) return gl > 0.0 && gr <= 0.0;
+    if (dir > 0) return gl < 0.0 && gr >= 0.0;
+    return !((gl > 0.0 && gr > 0.0) || (gl < 0.0 && gr < 0.0));
+}
+
 template <class AR, int C>      // C = section component (compile time: the unused parts of the extra stages fall away)
 __global__ void __launch_bounds__(32 * HB_SCAN_WARPS, 3) k_step_scan(const ScanParams p)
 {
@@ -256,6 +270,7 @@ __global__ void __launch_bounds__(32 * HB_SCAN_WARPS, 3) k_step_scan(const ScanP
     unsigned phase = 0;
     const int nacc = min(p.nacc[traj], p.rec_cap);
     const double off = p.sink.sec.offset, tol_s = p.sink.sec.tol_on_surface;
+    const int sdir = p.sink.sec.direction;
     int ndesc = 0;                         // segments noted so far (warp-uniform)
     int carry_c = 0;                       // first grid sample not owned yet
     int carry_step = 0;                    // step that owns sample carry_c - 1
@@ -339,8 +354,7 @@ __global__ void __launch_bounds__(32 * HB_SCAN_WARPS, 3) k_step_scan(const ScanP
         const int s_prev = (q >= 0) ? base + q : carry_step;
         bool scan = false;
         {                                                     // the segment that ends at this step's first sample
-            const bool same = (g_prev > 0.0 && g_first > 0.0) || (g_prev < 0.0 && g_first < 0.0);
-            const bool flag = owns && c0 > 0 && (!same || fabs(g_prev) < tol_s);
+            const bool flag = owns && c0 > 0 && segment_may_hit(sdir, g_prev, g_first, tol_s);
             const unsigned fm = __ballot_sync(FULL, flag);
             if (flag)
                 store_segment(p, traj, ndesc + __popc(fm & ((1u << lane) - 1u)), c0, s_prev, s, g_prev, g_first,
@@ -384,8 +398,7 @@ __global__ void __launch_bounds__(32 * HB_SCAN_WARPS, 3) k_step_scan(const ScanP
                 double g_m2 = __shfl_up_sync(FULL, g, 2);
                 if (lane == 0) { g_m1 = c1; g_m2 = c2; }
                 if (lane == 1) g_m2 = c1;
-                const bool same = (g_m1 > 0.0 && g > 0.0) || (g_m1 < 0.0 && g < 0.0);
-                const bool flagged = valid && (!same || fabs(g_m1) < tol_s);
+                const bool flagged = valid && segment_may_hit(sdir, g_m1, g, tol_s);
                 const unsigned fm = __ballot_sync(FULL, flagged);
                 if (flagged) store_segment(p, traj, ndesc + __popc(fm & ((1u << lane) - 1u)), cs, sL, sL, g_m1, g, g_m2);
                 ndesc += __popc(fm);
