@@ -224,6 +224,11 @@ HB_DEV void store_segment(const ScanParams &p, long long traj, int slot, int cs,
 #ifndef HB_SCAN_PREFETCH
 #define HB_SCAN_PREFETCH 0
 #endif
+// HB_SCAN_PIPELINED = 1 issues the next chunk's copies as soon as the rows of this chunk have been read: they fly
+// during the scan phase, which works on the headers in registers. Measured on 1e6 trajectories: 11.27 -> 10.90 ms.
+#ifndef HB_SCAN_PIPELINED
+#define HB_SCAN_PIPELINED 1
+#endif
 constexpr int HB_SCAN_WARPS = 4;
 constexpr int HB_SCAN_ROW = HB_REC_DOUBLES * 8 + 16;
 constexpr int HB_SCAN_SMEM = HB_SCAN_WARPS * (32 * HB_SCAN_ROW + 16);
@@ -275,15 +280,11 @@ __global__ void __launch_bounds__(32 * HB_SCAN_WARPS, 3) k_step_scan(const ScanP
     int carry_c = 0;                       // first grid sample not owned yet
     int carry_step = 0;                    // step that owns sample carry_c - 1
     double carry1 = 0.0, carry2 = 0.0;     // event function at samples carry_c - 1, carry_c - 2
-    for (int base = 0; base < nacc; base += 32) {
-        const int s = base + lane;
-        const bool have_rec = s < nacc;
-        double hdr[11];
-#pragma unroll
-        for (int i = 0; i < 11; ++i) hdr[i] = 0.0;
-        int cend = p.m;
-        if (have_rec) {
-            const double *src = p.rec + (traj * p.rec_cap + s) * HB_REC_DOUBLES;
+    // one 512-byte bulk copy per lane (the lane's own record of the chunk) or a plain arrival
+    auto issue_chunk = [&](int b) {
+        const int sb = b + lane;
+        if (sb < nacc) {
+            const double *src = p.rec + (traj * p.rec_cap + sb) * HB_REC_DOUBLES;
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(HB_REC_DOUBLES * 8)
                          : "memory");
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -291,13 +292,27 @@ __global__ void __launch_bounds__(32 * HB_SCAN_WARPS, 3) k_step_scan(const ScanP
 #if HB_SCAN_PREFETCH
             // the next chunk's record of this lane: start it towards L2 now, so that the blocking wait of the next
             // round pays an L2 hit instead of a DRAM round trip
-            if (s + 32 < nacc)
+            if (sb + 32 < nacc)
                 asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src + 32 * HB_REC_DOUBLES),
                              "r"(HB_REC_DOUBLES * 8) : "memory");
 #endif
         } else {
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
         }
+    };
+#if HB_SCAN_PIPELINED
+    if (nacc > 0) issue_chunk(0);
+#endif
+    for (int base = 0; base < nacc; base += 32) {
+        const int s = base + lane;
+        const bool have_rec = s < nacc;
+        double hdr[11];
+#pragma unroll
+        for (int i = 0; i < 11; ++i) hdr[i] = 0.0;
+        int cend = p.m;
+#if !HB_SCAN_PIPELINED
+        issue_chunk(base);
+#endif
         mbar_wait(mbar, phase);
         phase ^= 1u;
         if (have_rec) {
@@ -326,6 +341,12 @@ __global__ void __launch_bounds__(32 * HB_SCAN_WARPS, 3) k_step_scan(const ScanP
             }
             if (s != nacc - 1) cend = first_at_or_after(p, v[1], 0);
         }
+#if HB_SCAN_PIPELINED
+        // the rows are not read again in this round (the scan below runs on the headers in registers): the next
+        // chunk's copies fly while this chunk is scanned
+        __syncwarp();
+        if (base + 32 < nacc) issue_chunk(base + 32);
+#endif
         int c0 = __shfl_up_sync(FULL, cend, 1);               // t_new of a step is t_old of the next, bit for bit
         if (lane == 0) c0 = carry_c;
         const int nown = (have_rec && c0 < cend) ? cend - c0 : 0;
