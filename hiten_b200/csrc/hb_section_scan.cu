@@ -229,9 +229,19 @@ HB_DEV void store_segment(const ScanParams &p, long long traj, int slot, int cs,
 #ifndef HB_SCAN_PIPELINED
 #define HB_SCAN_PIPELINED 1
 #endif
-constexpr int HB_SCAN_WARPS = 4;
-constexpr int HB_SCAN_ROW = HB_REC_DOUBLES * 8 + 16;
+// Staging geometry: a record carries 62 doubles (HB_REC_K12 + 6); rows of 62 x 8 = 496 B = 31 x 16 B need no padding
+// (31 is odd: the 16-byte reads of a quarter warp fall in 8 different bank groups), so a warp stages 15.9 KB and 13
+// one-warp CTAs fit an SM (13 x (15.9 + 1 KB reserved) = 220 KB); with 528-byte rows and 4-warp CTAs it was 12 warps.
+#ifndef HB_SCAN_WARPS
+#define HB_SCAN_WARPS 1
+#endif
+#ifndef HB_SCAN_MINBLOCKS
+#define HB_SCAN_MINBLOCKS 13
+#endif
+constexpr int HB_SCAN_COPY = (HB_REC_K12 + 6) * 8;
+constexpr int HB_SCAN_ROW = HB_SCAN_COPY;
 constexpr int HB_SCAN_SMEM = HB_SCAN_WARPS * (32 * HB_SCAN_ROW + 16);
+static_assert(HB_SCAN_COPY % 16 == 0 && (HB_SCAN_ROW / 16) % 2 == 1, "row: 16-byte multiple, odd number of 16-byte units");
 
 HB_DEV unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 HB_DEV void mbar_wait(unsigned mbar, unsigned parity)
@@ -257,7 +267,7 @@ HB_DEV bool segment_may_hit(int dir, double gl, double gr, double tol)
 }
 
 template <class AR, int C>      // C = section component (compile time: the unused parts of the extra stages fall away)
-__global__ void __launch_bounds__(32 * HB_SCAN_WARPS, 3) k_step_scan(const ScanParams p)
+__global__ void __launch_bounds__(32 * HB_SCAN_WARPS, HB_SCAN_MINBLOCKS) k_step_scan(const ScanParams p)
 {
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(128) unsigned char scan_smem[];
@@ -285,10 +295,10 @@ __global__ void __launch_bounds__(32 * HB_SCAN_WARPS, 3) k_step_scan(const ScanP
         const int sb = b + lane;
         if (sb < nacc) {
             const double *src = p.rec + (traj * p.rec_cap + sb) * HB_REC_DOUBLES;
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(HB_REC_DOUBLES * 8)
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(HB_SCAN_COPY)
                          : "memory");
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(row_u32), "l"(src), "r"(HB_REC_DOUBLES * 8), "r"(mbar) : "memory");
+                         ::"r"(row_u32), "l"(src), "r"(HB_SCAN_COPY), "r"(mbar) : "memory");
 #if HB_SCAN_PREFETCH
             // the next chunk's record of this lane: start it towards L2 now, so that the blocking wait of the next
             // round pays an L2 hit instead of a DRAM round trip
