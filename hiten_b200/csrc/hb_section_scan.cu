@@ -135,6 +135,27 @@ HB_DEV int first_at_or_after(const ScanParams &p, double tv, int lo)
     return c;
 }
 
+// The same lookup for the scan kernel, returning the grid values around the answer as well: t_eval[c], t_eval[c - 1]
+// and t_eval[c - 2] are fetched in ONE round of independent loads (the grid does not stay in the little L1 left beside
+// the staging rows, so every dependent lookup is a round trip to L2).  te0 = t_eval[0], loaded once per warp.
+HB_DEV int first_at_or_after3(const ScanParams &p, double te0, double tv, double &tc, double &tm1, double &tm2)
+{
+    int c = (int)fmin(fmax((tv - te0) * p.inv_grid_dt, 0.0), (double)p.m);
+    if (c > 0 && c < p.m) {
+        const double a = p.t_eval[c - 1], b = p.t_eval[c], z = p.t_eval[max(c - 2, 0)];
+        if (a < tv && !(b < tv)) {
+            tc = b; tm1 = a; tm2 = z;
+            return c;
+        }
+    }
+    while (c < p.m && p.t_eval[c] < tv) ++c;
+    while (c > 0 && !(p.t_eval[c - 1] < tv)) --c;
+    tc = p.t_eval[min(c, p.m - 1)];
+    tm1 = p.t_eval[max(c - 1, 0)];
+    tm2 = p.t_eval[max(c - 2, 0)];
+    return c;
+}
+
 // _detect_with_segment_refine on ONE segment (linear branch), emitting raw candidates in order
 template <class EMIT>
 HB_DEV void segment_candidates(const hb_section &sec, bool has_prev, double g_prev, double gk, double gk1, double t0,
@@ -290,6 +311,8 @@ __global__ void __launch_bounds__(32 * HB_SCAN_WARPS, HB_SCAN_MINBLOCKS) k_step_
     int carry_c = 0;                       // first grid sample not owned yet
     int carry_step = 0;                    // step that owns sample carry_c - 1
     double carry1 = 0.0, carry2 = 0.0;     // event function at samples carry_c - 1, carry_c - 2
+    const double te0 = p.t_eval[0];
+    double carry_t = te0;                  // t_eval[carry_c]
     // one 512-byte bulk copy per lane (the lane's own record of the chunk) or a plain arrival
     auto issue_chunk = [&](int b) {
         const int sb = b + lane;
@@ -320,6 +343,7 @@ __global__ void __launch_bounds__(32 * HB_SCAN_WARPS, HB_SCAN_MINBLOCKS) k_step_
 #pragma unroll
         for (int i = 0; i < 11; ++i) hdr[i] = 0.0;
         int cend = p.m;
+        double t_c = 0.0, t_cm1 = 0.0, t_cm2 = 0.0;   // t_eval[cend], t_eval[cend - 1], t_eval[cend - 2]
 #if !HB_SCAN_PIPELINED
         issue_chunk(base);
 #endif
@@ -349,7 +373,8 @@ __global__ void __launch_bounds__(32 * HB_SCAN_WARPS, HB_SCAN_MINBLOCKS) k_step_
 #pragma unroll
                 for (int i = 0; i < 7; ++i) hdr[4 + i] = f[i];
             }
-            if (s != nacc - 1) cend = first_at_or_after(p, v[1], 0);
+            if (s != nacc - 1) cend = first_at_or_after3(p, te0, v[1], t_c, t_cm1, t_cm2);
+            else { t_cm1 = p.t_eval[p.m - 1]; t_cm2 = p.t_eval[max(p.m - 2, 0)]; }
         }
 #if HB_SCAN_PIPELINED
         // the rows are not read again in this round (the scan below runs on the headers in registers): the next
@@ -358,18 +383,19 @@ __global__ void __launch_bounds__(32 * HB_SCAN_WARPS, HB_SCAN_MINBLOCKS) k_step_
         if (base + 32 < nacc) issue_chunk(base + 32);
 #endif
         int c0 = __shfl_up_sync(FULL, cend, 1);               // t_new of a step is t_old of the next, bit for bit
-        if (lane == 0) c0 = carry_c;
+        double t_c0 = __shfl_up_sync(FULL, t_c, 1);                       // t_eval[c0]: the previous lane's t_eval[cend]
+        if (lane == 0) { c0 = carry_c; t_c0 = carry_t; }
         const int nown = (have_rec && c0 < cend) ? cend - c0 : 0;
         const bool owns = nown > 0;
         // event function at the first (g_first), last (A) and second-to-last (B) owned sample
         double g_first = 0.0, A = 0.0, B = 0.0;
         const double inv_h = (hdr[2] != 0.0) ? AR::rcp(hdr[2]) : 0.0;
         if (owns) {
-            g_first = g_comp<AR>(hdr, xpar_by<AR>(p.t_eval[c0], hdr[0], hdr[2], inv_h), off);
+            g_first = g_comp<AR>(hdr, xpar_by<AR>(t_c0, hdr[0], hdr[2], inv_h), off);
             A = g_first;
             if (nown >= 2) {
-                A = g_comp<AR>(hdr, xpar_by<AR>(p.t_eval[cend - 1], hdr[0], hdr[2], inv_h), off);
-                B = (nown >= 3) ? g_comp<AR>(hdr, xpar_by<AR>(p.t_eval[cend - 2], hdr[0], hdr[2], inv_h), off) : g_first;
+                A = g_comp<AR>(hdr, xpar_by<AR>(t_cm1, hdr[0], hdr[2], inv_h), off);
+                B = (nown >= 3) ? g_comp<AR>(hdr, xpar_by<AR>(t_cm2, hdr[0], hdr[2], inv_h), off) : g_first;
             }
         }
         const unsigned own_mask = __ballot_sync(FULL, owns);
@@ -451,6 +477,7 @@ __global__ void __launch_bounds__(32 * HB_SCAN_WARPS, HB_SCAN_MINBLOCKS) k_step_
             carry_step = base + qL;
         }
         carry_c = __shfl_sync(FULL, cend, 31);
+        carry_t = shfl_d(t_c, 31);
         __syncwarp();                                         // every lane is done with its row before the next copy
     }
     if (lane == 0) p.desc_count[traj] = ndesc;
