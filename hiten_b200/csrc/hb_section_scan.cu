@@ -304,7 +304,10 @@ __global__ void __launch_bounds__(32 * HB_SCAN_WARPS, HB_SCAN_MINBLOCKS) k_step_
     }
     __syncwarp();
     unsigned phase = 0;
-    const int nacc = min(p.nacc[traj], p.rec_cap);
+    // Pipelined: the first chunk is requested BEFORE the trajectory's step count is known (the count is a DRAM round
+    // trip of its own): until then every row of the scratch is fair game -- rows past the count hold stale bytes that
+    // no lane looks at.
+    int nacc = HB_SCAN_PIPELINED ? p.rec_cap : min(p.nacc[traj], p.rec_cap);
     const double off = p.sink.sec.offset, tol_s = p.sink.sec.tol_on_surface;
     const int sdir = p.sink.sec.direction;
     int ndesc = 0;                         // segments noted so far (warp-uniform)
@@ -334,7 +337,9 @@ __global__ void __launch_bounds__(32 * HB_SCAN_WARPS, HB_SCAN_MINBLOCKS) k_step_
         }
     };
 #if HB_SCAN_PIPELINED
-    if (nacc > 0) issue_chunk(0);
+    issue_chunk(0);
+    nacc = min(p.nacc[traj], p.rec_cap);
+    if (nacc <= 0) mbar_wait(mbar, phase);                    // nothing to scan: let the requested rows land before exit
 #endif
     for (int base = 0; base < nacc; base += 32) {
         const int s = base + lane;
