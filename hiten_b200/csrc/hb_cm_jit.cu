@@ -20,6 +20,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
 #include <mutex>
 #include <string>
 #include <unordered_map>
@@ -499,7 +500,15 @@ struct Api {
 
 std::mutex g_mu;
 Api g_api;
-std::unordered_map<std::string, void *> g_functions;   // generated source -> CUfunction (per process, one device)
+// (device ordinal, generated source) -> CUfunction.  A CUfunction belongs to the context that was current at
+// cuModuleLoadData -- the primary context of the current device -- so every device gets its own module.
+std::unordered_map<std::string, void *> g_functions;
+inline std::string fn_key(const std::string &src)
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return std::to_string(dev) + "|" + src;
+}
 std::string g_last_log;
 
 bool load_nvrtc()
@@ -598,11 +607,12 @@ extern "C" int hb_cm_jit_compile_host(const void *terms_host, const int64_t *ptr
     return rc;
 }
 
-// source -> CUfunction (compiled once per process and source)
+// source -> CUfunction (compiled and loaded once per process, device and source)
 static int get_function(const std::string &src, const char *name, void **fn_out)
 {
     std::lock_guard<std::mutex> lk(g_mu);
-    auto it = g_functions.find(src);
+    const std::string key = fn_key(src);
+    auto it = g_functions.find(key);
     if (it != g_functions.end()) { *fn_out = it->second; return HB_OK; }
     if (!load_driver()) return HB_ERR_NODEVICE;
     std::vector<char> cubin;
@@ -613,7 +623,7 @@ static int get_function(const std::string &src, const char *name, void **fn_out)
     if (e != 0) return 1000 + e;
     e = g_api.getfn(&fn, mod, name);
     if (e != 0) return 1000 + e;
-    g_functions.emplace(src, fn);
+    g_functions.emplace(key, fn);
     *fn_out = fn;
     return HB_OK;
 }
@@ -696,23 +706,8 @@ extern "C" int hb_cm_poincare_map_jit(const hb_polyham *ham, const hb_cm_opts *o
     }
     const std::string src = gen_source(terms, ham->ptr, *opts);
     void *fn = nullptr;
-    {
-        std::lock_guard<std::mutex> lk(g_mu);
-        auto it = g_functions.find(src);
-        if (it != g_functions.end()) fn = it->second;
-        else {
-            if (!load_driver()) return HB_ERR_NODEVICE;
-            std::vector<char> cubin;
-            rc = compile_cubin(src, cubin);
-            if (rc != HB_OK) return rc;
-            void *mod = nullptr;
-            int e = g_api.load(&mod, cubin.data());
-            if (e != 0) return 1000 + e;
-            e = g_api.getfn(&fn, mod, "cm_map");
-            if (e != 0) return 1000 + e;
-            g_functions.emplace(src, fn);
-        }
-    }
+    rc = get_function(src, "cm_map", &fn);
+    if (rc != HB_OK) return rc;
     HB_CUDA_TRY(cudaMemsetAsync(workspace, 0, sizeof(HbWorkspace), st));
     int dev = 0, sms = 148, per_sm = 2;
     cudaGetDevice(&dev);
@@ -732,14 +727,15 @@ extern "C" int hb_cm_poincare_map_jit(const hb_polyham *ham, const hb_cm_opts *o
     {
         // keep the stream-ordered pool's memory across calls (the default releases it at every synchronisation and
         // the next call pays for a fresh 100+ MB allocation)
-        static bool pool_set = false;
-        if (!pool_set) {
+        static std::atomic<unsigned long long> pool_set{0ULL};       // one bit per device ordinal
+        const unsigned long long bit = 1ULL << (dev & 63);
+        if (!(pool_set.load() & bit)) {
             cudaMemPool_t pool = nullptr;
             if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess && pool) {
                 unsigned long long keep = ~0ULL;
                 cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
             }
-            pool_set = true;
+            pool_set.fetch_or(bit);
         }
     }
     HB_CUDA_TRY(cudaMallocAsync((void **)&tmp, b_cont + 2 * b_list + b_ctr, st));

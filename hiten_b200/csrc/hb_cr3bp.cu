@@ -233,13 +233,9 @@ template <class AR, int MODE, int NEG>
 int launch_one(const PropParams &p, unsigned grid, cudaStream_t st)
 {
     constexpr int smem = (MODE == MODE_RECORD) ? HB_BLOCK * HB_REC_ROW_BYTES : 0;
-    if (smem > 48 * 1024) {
-        static bool set = false;        // per instantiation
-        if (!set) {
-            HB_CUDA_TRY(cudaFuncSetAttribute(k_dop853_6<AR, MODE, NEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            set = true;
-        }
-    }
+    // the opt-in is per device (and cheap): set on every launch, so a second device in the same process gets it too
+    if (smem > 48 * 1024)
+        HB_CUDA_TRY(cudaFuncSetAttribute(k_dop853_6<AR, MODE, NEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     k_dop853_6<AR, MODE, NEG><<<grid, HB_BLOCK, smem, st>>>(p);
     HB_CUDA_TRY(cudaGetLastError());
     return HB_OK;

@@ -731,11 +731,8 @@ namespace {
 template <class AR, int C>
 int launch_scan_c(const ScanParams &p, unsigned grid, cudaStream_t st)
 {
-    static bool smem_set = false;       // (per instantiation)
-    if (!smem_set) {
-        HB_CUDA_TRY(cudaFuncSetAttribute(k_step_scan<AR, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, HB_SCAN_SMEM));
-        smem_set = true;
-    }
+    // per-device attribute: set on every launch (cheap), so any device of the process gets the opt-in
+    HB_CUDA_TRY(cudaFuncSetAttribute(k_step_scan<AR, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, HB_SCAN_SMEM));
     k_step_scan<AR, C><<<grid, 32 * HB_SCAN_WARPS, HB_SCAN_SMEM, st>>>(p);
     return HB_OK;
 }
@@ -888,12 +885,10 @@ extern "C" int hb_section2_filter(const hb_cr3bp *sys, const hb_integ *integ, co
     p.o = *opts; p.out = out; p.keep = keep;
     const long long blocks = (n + HB_FILT_WARPS - 1) / HB_FILT_WARPS;
     if (blocks > 2147483647LL) return HB_ERR_BADARG;
-    static bool smem_set = false;
-    if (!smem_set) {
+    if (integ->arith == HB_ARITH_PARITY)
         HB_CUDA_TRY(cudaFuncSetAttribute(k_record_filter<ArParity>, cudaFuncAttributeMaxDynamicSharedMemorySize, HB_FILT_SMEM));
+    else
         HB_CUDA_TRY(cudaFuncSetAttribute(k_record_filter<ArFast>, cudaFuncAttributeMaxDynamicSharedMemorySize, HB_FILT_SMEM));
-        smem_set = true;
-    }
     if (integ->arith == HB_ARITH_PARITY) k_record_filter<ArParity><<<(unsigned)blocks, 32 * HB_FILT_WARPS, HB_FILT_SMEM, st>>>(p);
     else k_record_filter<ArFast><<<(unsigned)blocks, 32 * HB_FILT_WARPS, HB_FILT_SMEM, st>>>(p);
     HB_CUDA_TRY(cudaGetLastError());

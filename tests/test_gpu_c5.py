@@ -1,0 +1,126 @@
+"""GPU parity on BASELINE configs[4] as the reference runs it (examples/heteroclinic_connection.py:29-63):
+L1 halo Az = 0.5 S stable tube (integration_fraction 0.9) and L2 halo Az = 0.3663368 N unstable tube (1.0), step 0.005,
+section x = 1 - mu / (y, z) / direction -1 with the stable-manifold flip of connections/interfaces.py:350, trajectory
+filters of Manifold.compute(), then the connection search -- against tests/golden/c5_connection.npz, the reference's own
+numbers for this flow (tests/golden/make_c5.py).  Parity arithmetic: bit for bit."""
+import os
+
+import numpy as np
+import pytest
+
+from test_oracle_c5 import ENERGY_TOL, IDX, c5, reference_safe_radii
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def section_of(g, key):
+    from hiten_b200 import synodic
+    axis = int(np.nonzero(g[f"{key}_req_normal"])[0][0])
+    return synodic.make_section(axis, float(g[f"{key}_req_offset"]), tuple(str(c) for c in g[f"{key}_req_plane_coords"]),
+                                int(g[f"{key}_req_direction"]), int(g[f"{key}_req_segment_refine"]),
+                                float(g[f"{key}_req_tol_on_surface"]), float(g[f"{key}_req_dedup_time_tol"]),
+                                float(g[f"{key}_req_dedup_point_tol"]))
+
+
+def check_hits(g, key, h, keep):
+    """h: SectionHits over ALL trajectories of the tube (discarded ones contribute nothing); the reference numbers its
+    hits by position among the KEPT trajectories (SynodicMap sees manifold.result's states_list)."""
+    rank = np.cumsum(keep) - 1
+    assert keep[h.trajectory_indices].all()
+    assert np.array_equal(rank[h.trajectory_indices], g[f"{key}_hit_traj"])
+    assert np.array_equal(h.times, g[f"{key}_hit_time"])
+    assert np.array_equal(h.states, g[f"{key}_hit_state"])
+    assert np.array_equal(h.points, g[f"{key}_hit_point"])
+
+
+@pytest.mark.parametrize("key", ["l1", "l2"])
+@pytest.mark.parametrize("steps_capacity", [192, 96])
+def test_c5_tube_section_runner_with_filters_bit_exact(key, steps_capacity):
+    """TubeSectionRunner(filters=...): the section pipeline (hb_cr3bp_section2 + hb_section2_filter) on the two C5
+    tubes.  Capacity 96 forces the overflow path (fused-kernel rerun + stored-tube filter) on the long arcs."""
+    import torch
+    from hiten_b200 import synodic
+    g = c5()
+    mu, tf, steps, fwd = float(g["mu"]), float(g[f"{key}_tf"]), int(g[f"{key}_steps"]), int(g[f"{key}_forward"])
+    t_eval = np.linspace(0.0, tf, steps)
+    r1, r2 = reference_safe_radii()
+    run = synodic.TubeSectionRunner(200, mu, t_eval, section_of(g, key), forward=fwd, flip=(0, 6),
+                                    steps_capacity=steps_capacity, filters=(r1, r2, ENERGY_TOL))
+    run.launch(torch.from_numpy(np.ascontiguousarray(g[f"{key}_x0W"].T)).cuda())
+    h = run.sorted_hits()
+    q, keep = run.filter_result()
+    keep = keep.cpu().numpy() == 1
+    assert (run.status == 0).all().item()
+    assert np.array_equal(run.yf.t().cpu().numpy(), g[f"{key}_yf"])
+    assert np.array_equal(keep, g[f"{key}_kept"])
+    check_hits(g, key, h, keep)
+
+
+@pytest.mark.parametrize("key", ["l1", "l2"])
+def test_c5_stored_tube_chain_and_fused_kernel_bit_exact(key):
+    """The two other forms of the same step: dense tube + tube filter + detector on the stored tube (what the drop-in's
+    _run_compute / _SynodicDetectionBackend.run do), and the fused kernel hb_cr3bp_section."""
+    import hiten_b200 as hb
+    from hiten_b200 import manifold, synodic
+    g = c5()
+    mu, tf, steps, fwd = float(g["mu"]), float(g[f"{key}_tf"]), int(g[f"{key}_steps"]), int(g[f"{key}_forward"])
+    t_eval = np.linspace(0.0, tf, steps)
+    r1, r2 = reference_safe_radii()
+    sec = section_of(g, key)
+    tube = hb.cr3bp_dense(g[f"{key}_x0W"], mu, t_eval, forward=fwd, flip=(0, 6), keep_on_device=True)
+    assert np.array_equal(tube.states[:, -1, :].cpu().numpy(), g[f"{key}_yf"])
+    _, keep = manifold.tube_filter(tube.states, mu, safe_r1=r1, safe_r2=r2, energy_tol=ENERGY_TOL)
+    keep = keep.cpu().numpy() == 1
+    assert np.array_equal(keep, g[f"{key}_kept"])
+    sel = np.nonzero(keep)[0]
+    got = synodic.detect(tube.states[sel], fwd * t_eval, sec)
+    assert np.array_equal(got.trajectory_indices, g[f"{key}_hit_traj"])
+    assert np.array_equal(got.times, g[f"{key}_hit_time"]) and np.array_equal(got.states, g[f"{key}_hit_state"])
+    fused, res = synodic.tube_section(g[f"{key}_x0W"][sel], mu, t_eval, sec, forward=fwd, flip=(0, 6), steps_capacity=0)
+    assert np.array_equal(fused.trajectory_indices, g[f"{key}_hit_traj"])
+    assert np.array_equal(fused.times, g[f"{key}_hit_time"]) and np.array_equal(fused.states, g[f"{key}_hit_state"])
+    assert np.array_equal(res.yf, g[f"{key}_yf"][sel])
+
+
+def test_c5_connections_bit_exact_vs_reference():
+    from hiten_b200 import connections as cn
+    g = c5()
+    r = cn.find_connections(g["conn_pu"], g["conn_ps"], g["conn_Xu"], g["conn_Xs"], float(g["conn_eps"]),
+                            float(g["conn_dv_tol"]), float(g["conn_bal_tol"]), traj_indices_u=g["conn_tu"],
+                            traj_indices_s=g["conn_ts"])
+    assert r.pairs_considered == int(g["conn_pairs_considered"]) and len(r.delta_v) == 6
+    assert np.array_equal(r.index_u, g["conn_iu"]) and np.array_equal(r.index_s, g["conn_is"])
+    assert np.array_equal(r.kind, g["conn_kind"]) and np.array_equal(r.delta_v, g["conn_dv"])
+    assert np.array_equal(r.point2d, g["conn_pt"])
+    assert np.array_equal(r.state_u, g["conn_su"]) and np.array_equal(r.state_s, g["conn_ss"])
+    assert np.array_equal(r.trajectory_index_u, g["conn_tiu"]) and np.array_equal(r.trajectory_index_s, g["conn_tis"])
+
+
+def test_c5_whole_flow_on_the_device_gives_the_reference_connections():
+    """Tubes -> filters -> section hits -> connection search without leaving the device API: the 6 connections of the
+    reference's example, bit for bit (Delta-v, meeting point, both states, trajectory indices)."""
+    import torch
+    from hiten_b200 import connections as cn
+    from hiten_b200 import synodic
+    g = c5()
+    mu = float(g["mu"])
+    r1, r2 = reference_safe_radii()
+    hits = {}
+    for key in ("l1", "l2"):
+        tf, steps, fwd = float(g[f"{key}_tf"]), int(g[f"{key}_steps"]), int(g[f"{key}_forward"])
+        run = synodic.TubeSectionRunner(200, mu, np.linspace(0.0, tf, steps), section_of(g, key), forward=fwd,
+                                        flip=(0, 6), steps_capacity=192, filters=(r1, r2, ENERGY_TOL))
+        run.launch(torch.from_numpy(np.ascontiguousarray(g[f"{key}_x0W"].T)).cuda())
+        h = run.sorted_hits()
+        keep = run.filter_result()[1].cpu().numpy() == 1
+        hits[key] = (h, (np.cumsum(keep) - 1)[h.trajectory_indices])
+    (hu, tu), (hs, ts) = hits["l1"], hits["l2"]
+    r = cn.find_connections(hu.points, hs.points, hu.states, hs.states, float(g["conn_eps"]), float(g["conn_dv_tol"]),
+                            float(g["conn_bal_tol"]), traj_indices_u=tu, traj_indices_s=ts)
+    # the reference's request lists the same hits in worker-completion order: compare through the hits themselves
+    assert len(r.delta_v) == 6
+    assert np.array_equal(r.delta_v, g["conn_dv"]) and np.array_equal(r.kind, g["conn_kind"])
+    assert np.array_equal(r.point2d, g["conn_pt"])
+    assert np.array_equal(r.state_u, g["conn_su"]) and np.array_equal(r.state_s, g["conn_ss"])
+    assert np.array_equal(r.trajectory_index_u, g["conn_tiu"]) and np.array_equal(r.trajectory_index_s, g["conn_tis"])

@@ -1,0 +1,252 @@
+"""GPU: hiten_b200.install() under the REAL reference with the REAL CUDA library (no stand-ins).
+
+The reference package is imported from oracle/_ref (oracle/build_ref.sh: unmodified copy + import stubs, shipped with the
+snapshot) or, in the build container, from the read-only checkout.  Its own user-level calls -- orbit.manifold().compute(),
+SynodicMap.compute(), cm.poincare_map().compute(), ConnectionPipeline.solve() -- then run with the funnels rebound to
+libhiten_b200.so, and the results are compared with the golden vectors the unpatched reference produced
+(tests/golden/make_*.py).
+
+Two kinds of check per flow:
+  * seam, bit for bit: the generating orbit is corrected and its STM / eigen-data computed by the unpatched reference
+    first (cached in its services), then install(): the tube, the trajectory filters, the section hits and the
+    connections that come out of the rebound calls equal the golden vectors exactly;
+  * everything installed from the first call (the orbit's own correction and STM run on the GPU too, which agree with
+    the reference to ~1e-12 / 2e-11, amplified along the manifold): identical crossing counts, points within 1e-6.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+import _refenv  # noqa: E402
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(_refenv.available() is None, reason="no reference package (run oracle/build_ref.sh)")]
+
+
+def G(name):
+    return np.load(os.path.join(HERE, "golden", name))
+
+
+@pytest.fixture(scope="module")
+def ref():
+    _refenv.enable()
+    import hiten_b200
+    assert not hiten_b200.dropin.is_installed()
+    from hiten import System
+    system = System.from_bodies("earth", "moon")
+    yield system
+    hiten_b200.uninstall()
+
+
+def _prime(manifold):
+    """Let the unpatched reference compute (and cache) everything _run_compute reads besides the tube itself."""
+    svc = manifold.dynamics
+    svc.compute_stm(steps=2000)
+    svc.eigenvalues, svc.eigenvectors
+    return svc
+
+
+def _library_loaded():
+    with open("/proc/self/maps") as f:
+        return any("libhiten_b200.so" in line for line in f)
+
+
+def test_c1_manifold_and_synodic_map_seam_bit_exact(ref):
+    """configs[0] + its section: unpatched orbit/STM, then the rebound manifold.compute() and
+    SynodicMap.compute() on the real kernels == the reference's 50 tubes' ends and 121 hits, bit for bit."""
+    import hiten_b200
+    from hiten import SynodicMap
+    g = G("synodic_c1.npz")
+    l1 = ref.get_libration_point(1)
+    halo = l1.create_orbit("halo", amplitude_z=0.2, zenith="southern")
+    halo.correct()
+    assert np.array_equal(np.asarray(halo.initial_state, float), g["orbit_x0"])
+    manifold = halo.manifold(stable=True, direction="positive")
+    _prime(manifold)
+    hiten_b200.install()
+    try:
+        ysos, dysos, states_list, times_list, successes, attempts = manifold.compute(show_progress=False)
+        assert (successes, attempts) == (50, 50) and states_list[0].shape == (int(g["steps"]), 6)
+        assert np.array_equal(np.stack([s[0] for s in states_list]), g["x0W"])
+        assert np.array_equal(np.stack([s[-1] for s in states_list]), g["yf"])
+        assert times_list[0][-1] == -float(g["tf"])
+        smap = SynodicMap(manifold)
+        smap.compute(section_axis="y", section_offset=0.0, plane_coords=("x", "z"), direction=-1)
+        sec = smap.dynamics.get_section()
+        pts, sts = np.asarray(sec.points, float), np.asarray(sec.states, float)
+        assert pts.shape == (121, 2)
+        # worker chunks complete in any order (synodic/engine.py:137): compare as sets of rows
+        a, b = np.lexsort(sts.T[::-1]), np.lexsort(g["hit_state"].T[::-1])
+        assert np.array_equal(sts[a], g["hit_state"][b]) and np.array_equal(pts[a], g["hit_point"][b])
+    finally:
+        hiten_b200.uninstall()
+    assert _library_loaded()
+
+
+def test_c1_everything_installed_counts_and_points(ref):
+    """The same flow with the drop-in active from the first call: halo.correct() (the reference's Newton loop over GPU
+    event / STM propagations), the orbit's STM, the tube and the section all run on the device."""
+    import hiten_b200
+    from hiten import SynodicMap
+    g = G("synodic_c1.npz")
+    hiten_b200.install()
+    try:
+        l1 = ref.get_libration_point(1)
+        halo = l1.create_orbit("halo", amplitude_z=0.2, zenith="southern")
+        halo.correct()
+        assert np.abs(np.asarray(halo.initial_state, float) - g["orbit_x0"]).max() <= 1e-10
+        assert abs(halo.period - float(g["orbit_period"])) <= 1e-10
+        manifold = halo.manifold(stable=True, direction="positive")
+        _, _, states_list, times_list, successes, attempts = manifold.compute(show_progress=False)
+        assert (successes, attempts) == (50, 50)
+        assert np.abs(np.stack([s[0] for s in states_list]) - g["x0W"]).max() <= 1e-10     # measured 2.7e-11
+        smap = SynodicMap(manifold)
+        smap.compute(section_axis="y", section_offset=0.0, plane_coords=("x", "z"), direction=-1)
+        pts = np.asarray(smap.get_points())
+        assert pts.shape == (121, 2)                                  # identical crossing count
+        d = np.abs(np.sort(pts[:, 0]) - np.sort(g["hit_point"][:, 0])).max()
+        print(f"[dropin] C1 fully installed: 121 hits, max |d x| of sorted crossing points {d:.2e}")
+        assert d <= 1e-6
+    finally:
+        hiten_b200.uninstall()
+
+
+@pytest.fixture(scope="module")
+def cm(ref):
+    l1 = ref.get_libration_point(1)
+    c = l1.get_center_manifold(degree=6)
+    c.compute()
+    return c
+
+
+def test_c2_vertical_tube_and_section_everything_installed(ref, cm):
+    """configs[1]: vertical orbit from the centre manifold, manifold.compute(step=0.005) -> 200 tubes, SynodicMap y = 0,
+    (x, z), direction -1 -> the reference's 679 hits (count identical; points at the tolerance the orbit's own
+    correction leaves)."""
+    import hiten_b200
+    from hiten import SynodicMap, VerticalOrbit
+    g = G("synodic_c2.npz")
+    l1 = ref.get_libration_point(1)
+    hiten_b200.install()
+    try:
+        ic_seed = cm.to_synodic([0.0, 0.0], 0.6, "q3")
+        orbit = VerticalOrbit(l1, initial_state=ic_seed)
+        orbit.correct()
+        assert np.abs(np.asarray(orbit.initial_state, float) - g["orbit_x0"]).max() <= 1e-9
+        manifold = orbit.manifold(stable=True, direction="positive")
+        _, _, states_list, _, successes, attempts = manifold.compute(step=0.005, show_progress=False)
+        assert (successes, attempts) == (200, 200)
+        smap = SynodicMap(manifold)
+        smap.compute(section_axis="y", section_offset=0.0, plane_coords=("x", "z"), direction=-1)
+        pts = np.asarray(smap.get_points())
+        print(f"[dropin] C2 fully installed: {len(pts)} hits (reference 679)")
+        assert pts.shape == (679, 2)
+        d = np.abs(np.sort(pts[:, 0]) - np.sort(g["hit_point"][:, 0])).max()
+        assert d <= 1e-5
+    finally:
+        hiten_b200.uninstall()
+
+
+def test_c3_centre_manifold_map_with_and_without_the_drop_in(ref, cm):
+    """configs[2] through the public API: cm.poincare_map(0.7).compute("p3") with the drop-in == without it, bit for
+    bit (the CM path is bit-exact), on the real kernels."""
+    import hiten_b200
+    from hiten.algorithms.poincare.centermanifold.options import CenterManifoldMapOptions
+    from hiten.algorithms.poincare.core.options import IterationOptions, SeedingOptions
+    from hiten.algorithms.types.options import IntegrationOptions, WorkerOptions
+
+    def run():
+        pm = cm.poincare_map(energy=0.7)
+        opts = CenterManifoldMapOptions(
+            integration=IntegrationOptions(dt=0.01, order=4, c_omega_heuristic=20, max_steps=2000),
+            iteration=IterationOptions(n_iter=2), seeding=SeedingOptions(n_seeds=20), workers=WorkerOptions(n_workers=1))
+        pm.compute(section_coord="p3", options=opts)
+        return np.asarray(pm.get_points(section_coord="p3"))
+
+    want = run()
+    hiten_b200.install()
+    try:
+        got = run()
+    finally:
+        hiten_b200.uninstall()
+    assert got.shape == want.shape and got.shape[0] > 0
+    assert np.array_equal(got, want)
+
+
+def test_c5_heteroclinic_example_seam_bit_exact(ref):
+    """configs[4] as examples/heteroclinic_connection.py runs it: both halos corrected and primed by the unpatched
+    reference, then install(): the two manifold.compute() calls (incl. the energy filter that drops part of the L2
+    tube) and ConnectionPipeline.solve() (two SynodicMap sections + the connection search) run on the GPU and return the
+    reference's own 6 connections, bit for bit."""
+    import hiten_b200
+    from hiten.algorithms.connections import ConnectionPipeline
+    from hiten.algorithms.connections.config import ConnectionConfig
+    from hiten.algorithms.connections.options import ConnectionOptions
+    from hiten.algorithms.poincare import SynodicMapConfig
+    g = G("c5_connection.npz")
+    mu = ref.mu
+    l1, l2 = ref.get_libration_point(1), ref.get_libration_point(2)
+    halo_l1 = l1.create_orbit("halo", amplitude_z=0.5, zenith="southern")
+    halo_l1.correct()
+    halo_l2 = l2.create_orbit("halo", amplitude_z=0.3663368, zenith="northern")
+    halo_l2.correct()
+    assert np.array_equal(np.asarray(halo_l1.initial_state, float), g["l1_orbit_x0"])
+    assert np.array_equal(np.asarray(halo_l2.initial_state, float), g["l2_orbit_x0"])
+    manifold_l1 = halo_l1.manifold(stable=True, direction="positive")
+    manifold_l2 = halo_l2.manifold(stable=False, direction="negative")
+    _prime(manifold_l1)
+    _prime(manifold_l2)
+    hiten_b200.install()
+    try:
+        r1 = manifold_l1.compute(integration_fraction=0.9, step=0.005, show_progress=False)
+        r2 = manifold_l2.compute(integration_fraction=1.0, step=0.005, show_progress=False)
+        for key, res in (("l1", r1), ("l2", r2)):
+            states_list, successes, attempts = res[2], res[4], res[5]
+            kept = g[f"{key}_kept"]
+            assert (successes, attempts) == (int(kept.sum()), 200)
+            assert np.array_equal(np.stack([s[0] for s in states_list]), g[f"{key}_x0W"][kept])
+            assert np.array_equal(np.stack([s[-1] for s in states_list]), g[f"{key}_yf"][kept])
+        section_cfg = SynodicMapConfig(section_axis="x", section_offset=1 - mu, plane_coords=("y", "z"))
+        conn = ConnectionPipeline.with_default_engine(config=ConnectionConfig(section=section_cfg, direction=-1))
+        result = conn.solve(manifold_l1, manifold_l2,
+                            options=ConnectionOptions(delta_v_tol=1, ballistic_tol=1e-8, eps2d=1e-3))
+        res = list(result.connections) if hasattr(result, "connections") else list(result)
+    finally:
+        hiten_b200.uninstall()
+    assert len(res) == 6
+    assert np.array_equal(np.array([r.delta_v for r in res]), g["conn_dv"])
+    assert np.array_equal(np.array([0 if r.kind == "ballistic" else 1 for r in res]), g["conn_kind"])
+    assert np.array_equal(np.array([r.point2d for r in res]).reshape(-1, 2), g["conn_pt"])
+    assert np.array_equal(np.array([r.state_u for r in res]).reshape(-1, 6), g["conn_su"])
+    assert np.array_equal(np.array([r.state_s for r in res]).reshape(-1, 6), g["conn_ss"])
+    assert np.array_equal(np.array([r.trajectory_index_u for r in res]), g["conn_tiu"])
+    assert np.array_equal(np.array([r.trajectory_index_s for r in res]), g["conn_tis"])
+
+
+def test_propagate_dynsys_and_compute_stm_on_the_device(ref):
+    """The two funnels everything else calls, rebound and run on the real kernels against the unpatched reference in the
+    same process: 6-state grid bit for bit, 42-state STM within 1e-8 (BASELINE.json north_star; measured ~2e-11)."""
+    import hiten_b200
+    import hiten.algorithms.dynamics.base as dbase
+    from hiten.algorithms.dynamics.rtbp import _compute_stm
+    g = G("synodic_c1.npz")
+    x0 = g["orbit_x0"]
+    want = dbase._propagate_dynsys(ref.dynsys, x0, 0.0, 1.3, forward=-1, steps=50, flip_indices=slice(0, 6))
+    x_ref, t_ref, phi_ref, PHI_ref = _compute_stm(ref.var_dynsys, x0, 1.1, steps=40, forward=-1)
+    hiten_b200.install()
+    try:
+        got = dbase._propagate_dynsys(ref.dynsys, x0, 0.0, 1.3, forward=-1, steps=50, flip_indices=slice(0, 6))
+        assert type(got) is type(want)
+        assert np.array_equal(got.times, want.times) and np.array_equal(got.states, want.states)
+        x, t, phi, PHI = _compute_stm(ref.var_dynsys, x0, 1.1, steps=40, forward=-1)
+        assert np.array_equal(t, t_ref) and PHI.shape == PHI_ref.shape
+        assert np.abs(PHI - PHI_ref).max() <= 1e-8 * np.abs(PHI_ref).max()
+        print(f"[dropin] _compute_stm on the device vs reference: {np.abs(PHI - PHI_ref).max() / np.abs(PHI_ref).max():.2e}")
+        with pytest.raises(ValueError):
+            dbase._propagate_dynsys(ref.dynsys, x0[:5], 0.0, 1.0)
+    finally:
+        hiten_b200.uninstall()
