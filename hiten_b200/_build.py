@@ -29,11 +29,36 @@ def _deps():
     return out
 
 
+HASH_PATH = LIB_PATH + ".srchash"
+
+
+def source_hash():
+    """Content hash of everything the library is built from (sources, public header, flags): modification times do
+    not survive the copy to a GPU box, contents do."""
+    import hashlib
+    h = hashlib.sha1(" ".join(NVCC_FLAGS).encode())
+    for d in sorted(_deps()):
+        if os.path.isfile(d):
+            h.update(os.path.basename(d).encode())
+            with open(d, "rb") as f:
+                h.update(f.read())
+    return h.hexdigest()
+
+
 def needs_build():
+    """True when the library is missing or was built from other sources than the ones on disk."""
     if not os.path.exists(LIB_PATH):
         return True
-    t = os.path.getmtime(LIB_PATH)
-    return any(os.path.getmtime(d) > t for d in _deps())
+    try:
+        with open(HASH_PATH) as f:
+            return f.read().strip() != source_hash()
+    except OSError:
+        return True
+
+
+def have_nvcc():
+    import shutil
+    return os.path.exists(os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")) or shutil.which("nvcc") is not None
 
 
 def build(force=False, verbose=False, extra_flags=(), out=None):
@@ -53,6 +78,9 @@ def build(force=False, verbose=False, extra_flags=(), out=None):
         sys.stderr.write(res.stderr)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    if out is None and not extra_flags:
+        with open(HASH_PATH, "w") as f:
+            f.write(source_hash())
     return target
 
 

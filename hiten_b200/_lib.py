@@ -94,7 +94,10 @@ SIGNATURES = {
                                    C.c_int32, vp, C.c_int64, vp, vp, vp, vp, vp, vp, vp]),
     "hb_section2_scratch_bytes": (C.c_int64, [C.c_int64, C.c_int32]),
     "hb_cr3bp_section2": (C.c_int, [C.POINTER(HbCr3bp), C.POINTER(HbInteg), C.POINTER(HbSection), C.c_int64, vp, vp,
-                                    C.c_int32, vp, C.c_int64, vp, vp, vp, vp, vp, vp, C.c_int64, vp, vp]),
+                                    C.c_int32, vp, C.c_int64, vp, vp, vp, vp, vp, vp, C.c_int64, vp, vp, vp]),
+    "hb_section3_scratch_bytes": (C.c_int64, [C.c_int64, C.c_int32]),
+    "hb_cr3bp_section3": (C.c_int, [C.POINTER(HbCr3bp), C.POINTER(HbInteg), C.POINTER(HbSection), C.c_int64, vp, vp,
+                                    C.c_int32, vp, C.c_int64, vp, vp, vp, vp, vp, vp, C.c_int64, vp, vp, vp]),
     "hb_cr3bp_event": (C.c_int, [C.POINTER(HbCr3bp), C.POINTER(HbInteg), C.POINTER(HbEvent), C.c_int64, vp,
                                  C.c_double, C.c_double, vp, vp, vp, vp, vp, vp, vp, vp]),
     "hb_dfma_peak": (C.c_int, [C.c_double, C.POINTER(C.c_double), vp]),
@@ -137,8 +140,6 @@ SIGNATURES = {
                                     vp, vp, vp]),
     "hb_read_hit_count": (C.c_int, [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), vp]),
     "hb_read_record_overflow": (C.c_int, [vp, C.POINTER(C.c_int64), vp]),
-    "hb_section2_profile": (C.c_int, [C.c_int32]),
-    "hb_section2_read_profile": (C.c_int, [C.POINTER(C.c_float)]),
     "hb_selftest_arith": (C.c_int, [vp, vp, C.c_int64, vp, vp, vp, vp, vp, vp]),
 }
 
@@ -152,14 +153,19 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    path = os.environ.get("HITEN_B200_LIB", _build.LIB_PATH)   # override: kernel-variant experiments
-    if not os.path.exists(path):
-        try:
-            _build.build()
-        except Exception as exc:  # pragma: no cover
-            raise HitenB200Error(
-                f"libhiten_b200.so is missing and could not be built ({exc}); "
-                "run `python -c 'import __graft_entry__ as g; g.build()'`") from exc
+    path = os.environ.get("HITEN_B200_LIB")                    # override: kernel-variant experiments
+    if path is None:
+        path = _build.LIB_PATH
+        missing = not os.path.exists(path)
+        if missing or (_build.needs_build() and _build.have_nvcc()):
+            try:
+                _build.build()
+            except Exception as exc:  # pragma: no cover
+                if missing:
+                    raise HitenB200Error(
+                        f"libhiten_b200.so is missing and could not be built ({exc}); "
+                        "run `python -c 'import __graft_entry__ as g; g.build()'`") from exc
+                raise HitenB200Error(f"libhiten_b200.so is older than its sources and the rebuild failed: {exc}") from exc
     lib = C.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported

@@ -166,10 +166,12 @@ __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) k_dop853_6(const PropP
 #pragma unroll
                         for (int d = 0; d < 6; d += 2) q[7 + 3 * (j - 5) + d / 2] = make_double2(k[j][d], k[j][d + 1]);
                     q[31] = make_double2(0.0, 0.0);
+#ifndef HB_REC_NOCOPY
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(r),
                                  "r"((unsigned)__cvta_generic_to_shared(rec_row)), "r"(HB_REC_DOUBLES * 8) : "memory");
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+#endif
                 }
             }
             if (MODE == MODE_RECORD || MODE == MODE_FINAL) {   // the dense interpolant at tf on the last segment

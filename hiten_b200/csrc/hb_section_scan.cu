@@ -22,7 +22,7 @@
 // HB_CAND_CAP, get status HB_TRAJ_RECORD_OVERFLOW: rerun those with hb_cr3bp_section.
 //
 // Reference: algorithms/poincare/synodic/backend.py:458-659 (_detect_with_segment_refine), :382-455.
-#include "hb_cr3bp_common.cuh"
+#include "hb_scan.cuh"
 #include "hb_tubefilter.cuh"
 
 extern "C" int hb_cr3bp_record_launch(const hb_cr3bp *sys, const hb_integ *integ, int32_t section_idx, int64_t n,
@@ -32,198 +32,7 @@ extern "C" int hb_cr3bp_record_launch(const hb_cr3bp *sys, const hb_integ *integ
 
 namespace {
 using namespace hbc;
-
-constexpr int HB_CAND_CAP = 32;       // candidate hits per trajectory (before de-duplication)
-constexpr int HB_CAND_DOUBLES = 8;    // key, t, state[6]
-constexpr int HB_DESC_DOUBLES = 8;    // traj, cs, step of cs-1, step of cs, g(cs-1), g(cs), g(cs-2), pad
-
-struct ScanParams {
-    PropParams prop;        // mu, 1-mu, sign mask (vector field of the extra stages)
-    long long n;
-    const double *rec;      // [n][rec_cap][HB_REC_DOUBLES] stage records
-    int rec_cap;
-    const int *nacc;
-    int *status;
-    const double *t_eval;
-    int m;
-    double tsign, inv_grid_dt;
-    HitSink sink;
-    int *hits_per_traj;
-    int *cand_count;        // [n]
-    double *cand;           // [n][HB_CAND_CAP][HB_CAND_DOUBLES]
-    int *desc_count;        // [n]   segments that can hold a hit, found by k_step_scan
-    double *desc;           // [n][HB_CAND_CAP][HB_DESC_DOUBLES]
-    int *desc_total;        // [2]   entries at the front / at the back of the compact index below
-    int *desc_index;        // [n * HB_CAND_CAP] positions in desc of all noted segments (k_compact_segments)
-};
-
-template <class AR>
-HB_DEV double g_comp(const double *hdr, double xq, double offset)     // hdr = record header
-{
-    const double hseg = hdr[2];
-    double ge = hdr[3];
-    if (hseg != 0.0) {
-        const double omx = AR::sub(1.0, xq);
-        double v = 0.0;
-#pragma unroll
-        for (int i = 6; i >= 0; --i) {
-            v = AR::add(v, hdr[4 + i]);
-            v = AR::mul(v, ((6 - i) % 2 == 0) ? xq : omx);
-        }
-        ge = AR::add(v, hdr[3]);
-    }
-    return __dsub_rn(ge, offset);
-}
-template <class AR>
-HB_DEV double xpar(double tq, double t, double hseg) { return (hseg == 0.0) ? 0.0 : AR::div(AR::sub(tq, t), hseg); }
-// the same quotient with the reciprocal of hseg prepared once (AR::rcp): used where many samples share a step
-template <class AR>
-HB_DEV double xpar_by(double tq, double t, double hseg, double inv)
-{
-    return (hseg == 0.0) ? 0.0 : AR::div_by(AR::sub(tq, t), hseg, inv);
-}
-
-// y_old, y_new and the stage rows the dense output uses (k[1..4] do not enter it; k[0] = f(y_old) is recomputed)
-template <class AR>
-HB_DEV void load_record(const double *r, const PropParams &pp, double &t_old, double &t_new, double (&y)[6],
-                        double (&yn)[6], double (&k)[13][6])
-{
-    double v[HB_REC_DOUBLES];
-#pragma unroll
-    for (int i = 0; i < HB_REC_DOUBLES; i += 4) hb_ld4(r + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
-    t_old = v[0]; t_new = v[1];
-#pragma unroll
-    for (int d = 0; d < 6; ++d) {
-        y[d] = v[HB_REC_YOLD + d];
-        yn[d] = v[HB_REC_YNEW + d];
-#pragma unroll
-        for (int j = 1; j < 5; ++j) k[j][d] = 0.0;
-#pragma unroll
-        for (int j = 5; j < 13; ++j) k[j][d] = v[HB_REC_K5 + 6 * (j - 5) + d];
-    }
-    crtbp_rhs<AR, 2>(y, pp, k[0]);
-}
-
-template <class AR>
-__device__ __noinline__ void states_from_record(const double *r, const PropParams &pp, double tq0, double tq1,
-                                                double (&out0)[6], double (&out1)[6])
-{
-    double t, t_new, y[6], yn[6], k[13][6], F[7][6];
-    load_record<AR>(r, pp, t, t_new, y, yn, k);
-    const double hseg = AR::sub(t_new, t);
-    if (hseg == 0.0) {
-#pragma unroll
-        for (int d = 0; d < 6; ++d) { out0[d] = y[d]; out1[d] = y[d]; }
-        return;
-    }
-    const Cr3bpRhs<AR, 2> rhs{pp};
-    dense_cache<AR>(y, yn, hseg, k, F, rhs);
-    dense_eval<AR>(y, F, xpar<AR>(tq0, t, hseg), out0);
-    dense_eval<AR>(y, F, xpar<AR>(tq1, t, hseg), out1);
-}
-
-// first index c in [lo, m] with t_eval[c] >= tv  (guess from the uniform spacing, then fix up)
-HB_DEV int first_at_or_after(const ScanParams &p, double tv, int lo)
-{
-    int c = (int)fmin(fmax((tv - p.t_eval[0]) * p.inv_grid_dt, (double)lo), (double)p.m);
-    if (c > lo && c < p.m) {                                  // the guess is usually exact: settle it with two
-        const double a = p.t_eval[c - 1], b = p.t_eval[c];    // independent loads instead of two dependent rounds
-        if (a < tv && !(b < tv)) return c;
-    }
-    while (c < p.m && p.t_eval[c] < tv) ++c;
-    while (c > lo && !(p.t_eval[c - 1] < tv)) --c;
-    return c;
-}
-
-// The same lookup for the scan kernel, returning the grid values around the answer as well: t_eval[c], t_eval[c - 1]
-// and t_eval[c - 2] are fetched in ONE round of independent loads (the grid does not stay in the little L1 left beside
-// the staging rows, so every dependent lookup is a round trip to L2).  te0 = t_eval[0], loaded once per warp.
-HB_DEV int first_at_or_after3(const ScanParams &p, double te0, double tv, double &tc, double &tm1, double &tm2)
-{
-    int c = (int)fmin(fmax((tv - te0) * p.inv_grid_dt, 0.0), (double)p.m);
-    if (c > 0 && c < p.m) {
-        const double a = p.t_eval[c - 1], b = p.t_eval[c], z = p.t_eval[max(c - 2, 0)];
-        if (a < tv && !(b < tv)) {
-            tc = b; tm1 = a; tm2 = z;
-            return c;
-        }
-    }
-    while (c < p.m && p.t_eval[c] < tv) ++c;
-    while (c > 0 && !(p.t_eval[c - 1] < tv)) --c;
-    tc = p.t_eval[min(c, p.m - 1)];
-    tm1 = p.t_eval[max(c - 1, 0)];
-    tm2 = p.t_eval[max(c - 2, 0)];
-    return c;
-}
-
-// _detect_with_segment_refine on ONE segment (linear branch), emitting raw candidates in order
-template <class EMIT>
-HB_DEV void segment_candidates(const hb_section &sec, bool has_prev, double g_prev, double gk, double gk1, double t0,
-                               double t1, const double (&x0)[6], const double (&x1)[6], EMIT emit)
-{
-    const int dir = sec.direction;
-    bool accept_left = false;
-    if (fabs(gk) < sec.tol_on_surface) {
-        if (dir == 0) accept_left = true;
-        else if (dir > 0) accept_left = (gk1 >= 0.0) || (has_prev && g_prev <= 0.0);
-        else accept_left = (gk1 <= 0.0) || (has_prev && g_prev >= 0.0);
-    }
-    const int r = sec.segment_refine;
-    double xh[6];
-    int order = 0;
-    if (r > 0) {
-        if (accept_left) emit(order++, t0, x0);
-        const double step = __ddiv_rn(1.0, (double)(r + 1));
-        for (int mm = 0; mm <= r; ++mm) {
-            const double s_lo = __dmul_rn((double)mm, step), s_hi = __dmul_rn((double)(mm + 1), step);
-            if (s_hi > 1.0 + 1e-15) break;
-            if (accept_left && mm == 0) continue;
-            const double g_lo = __dadd_rn(__dmul_rn(__dsub_rn(1.0, s_lo), gk), __dmul_rn(s_lo, gk1));
-            const double g_hi = __dadd_rn(__dmul_rn(__dsub_rn(1.0, s_hi), gk), __dmul_rn(s_hi, gk1));
-            bool crosses;
-            if (dir == 0) crosses = (__dmul_rn(g_lo, g_hi) <= 0.0) && (g_lo != g_hi);
-            else if (dir > 0) crosses = (g_lo < 0.0) && (g_hi >= 0.0);
-            else crosses = (g_lo > 0.0) && (g_hi <= 0.0);
-            if (!crosses) continue;
-            double s_star;
-            if (g_lo == g_hi) s_star = __dmul_rn(0.5, __dadd_rn(s_lo, s_hi));
-            else {
-                double al = __ddiv_rn(g_lo, __dsub_rn(g_lo, g_hi));
-                al = fmin(1.0, fmax(0.0, al));
-                s_star = __dadd_rn(s_lo, __dmul_rn(al, __dsub_rn(s_hi, s_lo)));
-            }
-            const double th = __dadd_rn(__dmul_rn(__dsub_rn(1.0, s_star), t0), __dmul_rn(s_star, t1));
-#pragma unroll
-            for (int d = 0; d < 6; ++d) xh[d] = __dadd_rn(x0[d], __dmul_rn(s_star, __dsub_rn(x1[d], x0[d])));
-            emit(order++, th, xh);
-        }
-    } else {
-        if (accept_left) { emit(order++, t0, x0); return; }
-        bool crosses;
-        if (dir == 0) crosses = (__dmul_rn(gk, gk1) <= 0.0) && (gk != gk1);
-        else if (dir > 0) crosses = (gk < 0.0) && (gk1 >= 0.0);
-        else crosses = (gk > 0.0) && (gk1 <= 0.0);
-        if (!crosses) return;
-        double al = __ddiv_rn(gk, __dsub_rn(gk, gk1));
-        al = fmin(1.0, fmax(0.0, al));
-        const double th = __dadd_rn(__dmul_rn(__dsub_rn(1.0, al), t0), __dmul_rn(al, t1));
-#pragma unroll
-        for (int d = 0; d < 6; ++d) xh[d] = __dadd_rn(x0[d], __dmul_rn(al, __dsub_rn(x1[d], x0[d])));
-        emit(order++, th, xh);
-    }
-}
-
-// k_step_scan only NOTES the segments that can hold a hit (8 numbers each, per-trajectory list); k_emit_candidates turns them
-// into candidate hits.  Keeping the state reconstruction out of the scan kernel keeps it small (no spills, no call).
-// (the warp owns its trajectory, so slots come from a warp-uniform counter and a ballot -- no atomics, no waiting)
-HB_DEV void store_segment(const ScanParams &p, long long traj, int slot, int cs, int s0, int s1, double gk, double gk1,
-                          double gm2)
-{
-    if (slot >= HB_CAND_CAP) return;                          // counted, reported as overflow by k_order_dedup
-    double *d = p.desc + (traj * HB_CAND_CAP + slot) * HB_DESC_DOUBLES;
-    hb_st4(d, (double)traj, (double)cs, (double)s0, (double)s1);
-    hb_st4(d + 4, gk, gk1, gm2, 0.0);
-}
+using namespace hbscan;
 
 // One warp per trajectory, a lane per accepted step (chunks of 32 steps).  Each lane
 //   1. rebuilds the EVENT COMPONENT of its step's dense interpolant from the stage record (three extra stages +
@@ -263,29 +72,6 @@ constexpr int HB_SCAN_COPY = (HB_REC_K12 + 6) * 8;
 constexpr int HB_SCAN_ROW = HB_SCAN_COPY;
 constexpr int HB_SCAN_SMEM = HB_SCAN_WARPS * (32 * HB_SCAN_ROW + 16);
 static_assert(HB_SCAN_COPY % 16 == 0 && (HB_SCAN_ROW / 16) % 2 == 1, "row: 16-byte multiple, odd number of 16-byte units");
-
-HB_DEV unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-HB_DEV void mbar_wait(unsigned mbar, unsigned parity)
-{
-    unsigned done = 0;
-    while (!done)
-        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
-}
-
-// Can the segment between two neighbouring grid samples (event values gl, gr) produce a hit in process_segment()?
-// A left node within the on-surface tolerance may; otherwise a directed section needs the segment itself to cross in
-// that direction: the 51 sub-interval values are rounded points of the straight line from gl to gr, which rises or
-// falls by |gr - gl| / 51 >= max(|gl|, |gr|) / 51 per sub-interval -- far above their rounding error -- so a segment
-// running the other way has no sub-interval with (g_lo > 0, g_hi <= 0).  Segments dropped here are the upward
-// crossings of a direction = -1 section: half of all flagged segments of a tube.
-HB_DEV bool segment_may_hit(int dir, double gl, double gr, double tol)
-{
-    if (fabs(gl) < tol) return true;
-    if (dir < 0) return gl > 0.0 && gr <= 0.0;
-    if (dir > 0) return gl < 0.0 && gr >= 0.0;
-    return !((gl > 0.0 && gr > 0.0) || (gl < 0.0 && gr < 0.0));
-}
 
 template <class AR, int C>      // C = section component (compile time: the unused parts of the extra stages fall away)
 __global__ void __launch_bounds__(32 * HB_SCAN_WARPS, HB_SCAN_MINBLOCKS) k_step_scan(const ScanParams p)
@@ -419,8 +205,8 @@ __global__ void __launch_bounds__(32 * HB_SCAN_WARPS, HB_SCAN_MINBLOCKS) k_step_
             const bool flag = owns && c0 > 0 && segment_may_hit(sdir, g_prev, g_first, tol_s);
             const unsigned fm = __ballot_sync(FULL, flag);
             if (flag)
-                store_segment(p, traj, ndesc + __popc(fm & ((1u << lane) - 1u)), c0, s_prev, s, g_prev, g_first,
-                              c0 > 1 ? gm2 : 0.0);
+                store_segment(p, traj, ndesc + __popc(fm & ((1u << lane) - 1u)), c0, traj * p.rec_cap + s_prev,
+                              traj * p.rec_cap + s, g_prev, g_first, c0 > 1 ? gm2 : 0.0);
             ndesc += __popc(fm);
         }
         if (owns) {
@@ -462,7 +248,9 @@ __global__ void __launch_bounds__(32 * HB_SCAN_WARPS, HB_SCAN_MINBLOCKS) k_step_
                 if (lane == 1) g_m2 = c1;
                 const bool flagged = valid && segment_may_hit(sdir, g_m1, g, tol_s);
                 const unsigned fm = __ballot_sync(FULL, flagged);
-                if (flagged) store_segment(p, traj, ndesc + __popc(fm & ((1u << lane) - 1u)), cs, sL, sL, g_m1, g, g_m2);
+                if (flagged)
+                    store_segment(p, traj, ndesc + __popc(fm & ((1u << lane) - 1u)), cs, traj * p.rec_cap + sL,
+                                  traj * p.rec_cap + sL, g_m1, g, g_m2);
                 ndesc += __popc(fm);
                 const int nvalid = min(32, b1 - b);
                 const double l1 = shfl_d(g, nvalid - 1);
@@ -541,15 +329,15 @@ __global__ void __launch_bounds__(128) k_emit_candidates(const ScanParams p)
         hb_ld4(d, d0, d1, d2, d3);
         hb_ld4(d + 4, gk, gk1, gm2, pad);
         const long long traj = (long long)d0;
-        const int cs = (int)d1, s0 = (int)d2, s1 = (int)d3;
-        const double *base = p.rec + traj * (long long)p.rec_cap * HB_REC_DOUBLES;
+        const int cs = (int)d1;
+        const long long r0 = (long long)d2, r1 = (long long)d3;
         double x0[6], x1[6];
-        if (s0 == s1) {
-            states_from_record<AR>(base + (long long)s1 * HB_REC_DOUBLES, p.prop, p.t_eval[cs - 1], p.t_eval[cs], x0, x1);
+        if (r0 == r1) {
+            states_from_record<AR>(p.rec + r1 * HB_REC_DOUBLES, p.prop, p.t_eval[cs - 1], p.t_eval[cs], x0, x1);
         } else {
             double dummy[6];
-            states_from_record<AR>(base + (long long)s0 * HB_REC_DOUBLES, p.prop, p.t_eval[cs - 1], p.t_eval[cs - 1], x0, dummy);
-            states_from_record<AR>(base + (long long)s1 * HB_REC_DOUBLES, p.prop, p.t_eval[cs], p.t_eval[cs], x1, dummy);
+            states_from_record<AR>(p.rec + r0 * HB_REC_DOUBLES, p.prop, p.t_eval[cs - 1], p.t_eval[cs - 1], x0, dummy);
+            states_from_record<AR>(p.rec + r1 * HB_REC_DOUBLES, p.prop, p.t_eval[cs], p.t_eval[cs], x1, dummy);
         }
         auto emit = [&](int order, double th, const double (&xh)[6]) {
             const int k = atomicAdd(&p.cand_count[traj], 1);
@@ -750,28 +538,18 @@ int launch_scan(const ScanParams &p, unsigned grid, cudaStream_t st)
 }
 }  // namespace
 
-// Optional per-kernel timing of the pipeline (bench.py's roofline): CUDA events recorded on the launching stream
-// between the kernels.  Off by default; not thread safe (one profiled caller at a time).
-namespace {
-constexpr int HB_S2_STAGES = 4;      // propagate+record, step scan, emit, order+dedup
-bool g_profile = false;
-cudaEvent_t g_ev[HB_S2_STAGES + 1] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-inline void mark(int i, cudaStream_t st) { if (g_profile && g_ev[i]) cudaEventRecord(g_ev[i], st); }
-}  // namespace
-
-extern "C" int hb_section2_profile(int32_t enable)
+// B2 + B3 (shared with hb_section_stream.cu)
+int hbscan::hb_scan_finish(const ScanParams &p, int arith, cudaStream_t st, cudaEvent_t ev_emit_done)
 {
-    if (enable && !g_ev[0])
-        for (int i = 0; i <= HB_S2_STAGES; ++i) HB_CUDA_TRY(cudaEventCreate(&g_ev[i]));
-    g_profile = enable != 0;
-    return HB_OK;
-}
-
-extern "C" int hb_section2_read_profile(float *ms_out)
-{
-    if (!ms_out || !g_ev[0]) return HB_ERR_BADARG;
-    HB_CUDA_TRY(cudaEventSynchronize(g_ev[HB_S2_STAGES]));
-    for (int i = 0; i < HB_S2_STAGES; ++i) HB_CUDA_TRY(cudaEventElapsedTime(&ms_out[i], g_ev[i], g_ev[i + 1]));
+    k_compact_segments<<<(unsigned)((p.n + 255) / 256), 256, 0, st>>>(p);
+    HB_CUDA_TRY(cudaGetLastError());
+    const unsigned tb = (unsigned)sm_count() * 8u;
+    if (arith == HB_ARITH_PARITY) k_emit_candidates<ArParity><<<tb, 128, 0, st>>>(p);
+    else k_emit_candidates<ArFast><<<tb, 128, 0, st>>>(p);
+    HB_CUDA_TRY(cudaGetLastError());
+    if (ev_emit_done) HB_CUDA_TRY(cudaEventRecord(ev_emit_done, st));
+    k_order_dedup<<<(unsigned)((p.n + 255) / 256), 256, 0, st>>>(p);
+    HB_CUDA_TRY(cudaGetLastError());
     return HB_OK;
 }
 
@@ -787,9 +565,11 @@ extern "C" int hb_cr3bp_section2(const hb_cr3bp *sys, const hb_integ *integ, con
                                  const double *y0_soa, const double *t_eval, int32_t m, hb_hit *hits,
                                  int64_t hit_capacity, int32_t *hits_per_traj, double *yf_soa, int32_t *n_acc,
                                  int32_t *n_rej, int32_t *status, void *scratch, int64_t scratch_bytes, void *workspace,
-                                 void *stream)
+                                 void *stream, void *const *stage_events)
 {
     if (!sys || !integ || !sec) return HB_ERR_BADARG;
+    // optional caller-owned CUDA events, recorded on `stream` around the four stages (no library state involved)
+    auto mark = [&](int i, cudaStream_t s_) { if (stage_events && stage_events[i]) cudaEventRecord((cudaEvent_t)stage_events[i], s_); };
     if (integ->method != HB_DOP853) return HB_ERR_UNSUPPORTED;
     if (sec->idx < 0 || sec->idx > 5 || sec->proj_i < 0 || sec->proj_i > 5 || sec->proj_j < 0 || sec->proj_j > 5 ||
         sec->segment_refine < 0 || hit_capacity < 0)
@@ -833,24 +613,14 @@ extern "C" int hb_cr3bp_section2(const hb_cr3bp *sys, const hb_integ *integ, con
     p.sink.sec = *sec; p.sink.hits = hits; p.sink.capacity = hit_capacity; p.sink.ws = (HbWorkspace *)workspace;
     p.hits_per_traj = hits_per_traj;
     p.cand_count = cand_count; p.cand = cand; p.desc_count = desc_count; p.desc = desc; p.desc_total = desc_total; p.desc_index = desc_index;
-    const int threads = 256;
     const long long b1 = (n + HB_SCAN_WARPS - 1) / HB_SCAN_WARPS;      // one warp per trajectory
     if (b1 > 2147483647LL) return HB_ERR_BADARG;
     rc = (integ->arith == HB_ARITH_PARITY) ? launch_scan<ArParity>(p, (unsigned)b1, st) : launch_scan<ArFast>(p, (unsigned)b1, st);
     if (rc != HB_OK) return rc;
     HB_CUDA_TRY(cudaGetLastError());
     mark(2, st);
-    {
-        k_compact_segments<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p);
-        HB_CUDA_TRY(cudaGetLastError());
-        const unsigned tb = (unsigned)sm_count() * 8u;
-        if (integ->arith == HB_ARITH_PARITY) k_emit_candidates<ArParity><<<tb, 128, 0, st>>>(p);
-        else k_emit_candidates<ArFast><<<tb, 128, 0, st>>>(p);
-        HB_CUDA_TRY(cudaGetLastError());
-    }
-    mark(3, st);
-    k_order_dedup<<<(unsigned)((n + threads - 1) / threads), threads, 0, st>>>(p);
-    HB_CUDA_TRY(cudaGetLastError());
+    rc = hb_scan_finish(p, integ->arith, st, stage_events ? (cudaEvent_t)stage_events[3] : nullptr);
+    if (rc != HB_OK) return rc;
     mark(4, st);
     return HB_OK;
 }

@@ -166,10 +166,14 @@ class TubeSectionRunner:
     buffers are created once; launch() enqueues the kernels, hit_count() / sorted_hits() read the result."""
 
     def __init__(self, n, mu, t_eval, section, *, forward=1, flip=None, integ=None, hit_capacity=None, device=None,
-                 steps_capacity=0, scratch=None, filters=None):
-        """steps_capacity > 0 selects the kernel pipeline hb_cr3bp_section2 with a scratch for that many accepted
-        steps per trajectory (512 B per step); 0 the fused kernel hb_cr3bp_section.  Trajectories that do not fit
-        the scratch are rerun with the fused kernel by hit_count() / sorted_hits(), so the result is the same.
+                 steps_capacity=0, scratch=None, filters=None, pool_records=0):
+        """Three forms of the same step, same hits bit for bit:
+        pool_records > 0 selects hb_cr3bp_section3: step records handed from propagating to scanning warps through
+        shared memory inside one kernel; the scratch holds the candidate lists and a pool of `pool_records` step
+        records per trajectory (512 B each; 8 is plenty for a tube) -- no per-trajectory step capacity;
+        steps_capacity > 0 selects the kernel pipeline hb_cr3bp_section2 with an HBM scratch for that many accepted
+        steps per trajectory (512 B per step); both 0: the fused kernel hb_cr3bp_section.  Trajectories that do not fit
+        the scratch / pool are rerun with the fused kernel by hit_count() / sorted_hits(), so the result is the same.
         `scratch` lets several runners share one (large) scratch tensor.
         `filters` = (safe_r1, safe_r2, energy_tol) applies Manifold.compute()'s trajectory filters
         (services/manifold.py:412-432) from the step records (hb_section2_filter, pipeline only): sorted_hits() then
@@ -191,18 +195,23 @@ class TubeSectionRunner:
         self.cap = int(hit_capacity) if hit_capacity is not None else max(1024, 8 * self.n)
         self.hits = torch.empty(self.cap * 9, dtype=torch.float64, device=self.device)
         self.steps_capacity = int(steps_capacity)
+        self.pool_records = int(pool_records)
+        if self.pool_records > 0 and self.steps_capacity > 0:
+            raise ValueError("choose pool_records (hb_cr3bp_section3) or steps_capacity (hb_cr3bp_section2), not both")
+        self.stage_events = None        # set_stage_events(): caller-owned CUDA events around the pipeline's stages
         self.scratch = None
         self._y0 = None
         self._extra = None          # (indices, SectionHits) of the trajectories rerun with the fused kernel
         self.filters = None
         if filters is not None:
             if self.steps_capacity <= 0:
-                raise ValueError("filters are computed from the step records: use steps_capacity > 0")
+                raise ValueError("filters are computed from the step records of hb_cr3bp_section2: use steps_capacity > 0")
             self.filters = L.HbTubeFilterOpts(float(mu), float(filters[0]), float(filters[1]), float(filters[2]))
             self.filt = torch.empty((max(self.n, 1), 3), dtype=torch.float64, device=self.device)
             self.keep = torch.empty(max(self.n, 1), dtype=torch.int32, device=self.device)
-        if self.steps_capacity > 0:
-            nbytes = int(self.lib.hb_section2_scratch_bytes(self.n, self.steps_capacity))
+        if self.steps_capacity > 0 or self.pool_records > 0:
+            nbytes = int(self.lib.hb_section2_scratch_bytes(self.n, self.steps_capacity)) if self.steps_capacity > 0 \
+                else int(self.lib.hb_section3_scratch_bytes(self.n, self.pool_records))
             self._owns_scratch = scratch is None
             if scratch is not None:
                 if scratch.numel() * scratch.element_size() < nbytes or scratch.device != self.device:
@@ -211,14 +220,36 @@ class TubeSectionRunner:
             else:
                 self.scratch = torch.empty(nbytes // 8, dtype=torch.float64, device=self.device)
 
+    def set_stage_events(self, events):
+        """events: list of torch.cuda.Event(enable_timing=True) the library records on the launch stream around the
+        pipeline's stages (5 for hb_cr3bp_section2, 4 for hb_cr3bp_section3), or None.  bench.py's roofline uses it."""
+        if events is None:
+            self.stage_events = None
+            return
+        for e in events:
+            e.record()                                       # torch creates the CUDA event lazily, on first record
+        arr = (L.C.c_void_p * len(events))(*[e.cuda_event for e in events])
+        self.stage_events = (arr, list(events))
+
     def launch(self, y0_soa, stream=None):
         self._y0, self._extra = y0_soa, None
+        sev = None if self.stage_events is None else self.stage_events[0]
+        if self.scratch is not None and self.pool_records > 0:
+            rc = self.lib.hb_cr3bp_section3(self.sys, self.integ, self.section, self.n, y0_soa.data_ptr(),
+                                            self.te.data_ptr(), self.te.numel(), self.hits.data_ptr(), self.cap,
+                                            self.per.data_ptr(), self.yf.data_ptr(), self.nacc.data_ptr(),
+                                            self.nrej.data_ptr(), self.status.data_ptr(), self.scratch.data_ptr(),
+                                            self.scratch.numel() * 8, self.ws.data_ptr(), _stream_ptr(stream), sev)
+            L.check(rc, "hb_cr3bp_section3")
+            if self.filters is not None:
+                raise L.HitenB200Error("filters need the step records of hb_cr3bp_section2 (steps_capacity > 0)")
+            return
         if self.scratch is not None:
             rc = self.lib.hb_cr3bp_section2(self.sys, self.integ, self.section, self.n, y0_soa.data_ptr(),
                                             self.te.data_ptr(), self.te.numel(), self.hits.data_ptr(), self.cap,
                                             self.per.data_ptr(), self.yf.data_ptr(), self.nacc.data_ptr(),
                                             self.nrej.data_ptr(), self.status.data_ptr(), self.scratch.data_ptr(),
-                                            self.scratch.numel() * 8, self.ws.data_ptr(), _stream_ptr(stream))
+                                            self.scratch.numel() * 8, self.ws.data_ptr(), _stream_ptr(stream), sev)
             L.check(rc, "hb_cr3bp_section2")
             if self.filters is not None:
                 rc = self.lib.hb_section2_filter(self.sys, self.integ, self.filters, self.n, self.te.data_ptr(),
@@ -273,7 +304,7 @@ class TubeSectionRunner:
         """More than 2 % of the batch did not fit: size the scratch for the longest trajectory seen (the propagation
         kernel keeps counting steps past the capacity), if this runner owns its scratch and the memory is there --
         the NEXT launch then runs without reruns."""
-        if not getattr(self, "_owns_scratch", False) or n_overflowed * 50 < self.n:
+        if not getattr(self, "_owns_scratch", False) or n_overflowed * 50 < self.n or self.steps_capacity <= 0:
             return
         need = (int(self.nacc[: self.n].max().item()) + 31) // 32 * 32
         if need <= self.steps_capacity:
@@ -359,17 +390,21 @@ class TubeSectionStream:
     come back in pinned host buffers.  The two buffer sets share one step scratch (compute is serial anyway)."""
 
     def __init__(self, n, mu, t_eval, section, *, forward=1, flip=None, integ=None, hit_capacity=None, device=None,
-                 steps_capacity=160, scratch=None):
+                 steps_capacity=0, scratch=None, pool_records=8):
+        """Default: hb_cr3bp_section3 (pool_records step records per trajectory in the scratch); steps_capacity > 0
+        (with pool_records = 0) selects hb_cr3bp_section2."""
         _require_cuda()
+        if steps_capacity > 0:
+            pool_records = 0
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.n = int(n)
         with torch.cuda.device(self.device):
             r0 = TubeSectionRunner(n, mu, t_eval, section, forward=forward, flip=flip, integ=integ,
                                    hit_capacity=hit_capacity, device=self.device, steps_capacity=steps_capacity,
-                                   scratch=scratch)
+                                   scratch=scratch, pool_records=pool_records)
             r1 = TubeSectionRunner(n, mu, t_eval, section, forward=forward, flip=flip, integ=integ,
                                    hit_capacity=hit_capacity, device=self.device, steps_capacity=steps_capacity,
-                                   scratch=r0.scratch)
+                                   scratch=r0.scratch, pool_records=pool_records)
             self.runners = (r0, r1)
             self.s_in, self.s_run, self.s_out = (torch.cuda.Stream(self.device) for _ in range(3))
             self.d_in = [torch.empty((self.n, 6), dtype=torch.float64, device=self.device) for _ in range(2)]

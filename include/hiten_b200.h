@@ -160,14 +160,29 @@ int64_t hb_section2_scratch_bytes(int64_t n, int32_t steps_capacity);
 int hb_cr3bp_section2(const hb_cr3bp *sys, const hb_integ *integ, const hb_section *sec, int64_t n,
                       const double *y0_soa, const double *t_eval, int32_t m, hb_hit *hits, int64_t hit_capacity,
                       int32_t *hits_per_traj, double *yf_soa, int32_t *n_acc, int32_t *n_rej, int32_t *status,
-                      void *scratch, int64_t scratch_bytes, void *workspace, void *stream);
+                      void *scratch, int64_t scratch_bytes, void *workspace, void *stream,
+                      void *const *stage_events /* NULL, or 5 caller-owned cudaEvent_t recorded on `stream` before /
+                      between / after the stages propagate+record, step scan, candidate emission, order+dedup
+                      (measurement aid of bench.py; entries may be NULL; the library keeps no state) */);
 
-/* Per-kernel timing of hb_cr3bp_section2 (measurement aid, used by bench.py): after hb_section2_profile(1) every
- * call records CUDA events on its stream between the four stages (propagate + record, step scan, candidate
- * emission, order + dedup); hb_section2_read_profile waits for the last call and returns the four durations
- * in ms.  Not thread safe.                                                                           */
-int hb_section2_profile(int32_t enable);
-int hb_section2_read_profile(float *ms_out /* [4] */);
+/* The same step -- same hits, counts and end states, bit for bit -- with the step records handed from the propagating
+ * warps to scanning warps THROUGH SHARED MEMORY inside one persistent kernel (hb_section_stream.cu): nothing but
+ * initial conditions, end states, the few step records that hold a noted segment and the hits touch HBM.  No per-
+ * trajectory step capacity and no 512 B-per-step scratch: `scratch` holds the candidate / segment lists (4.2 KB per
+ * trajectory) and a pool of `pool_records_per_traj` step records per trajectory on average (512 B each; a tube needs
+ * ~3, ask for 8).  Trajectories with more than 32 noted segments or candidates, or that found the pool exhausted, get
+ * status = HB_TRAJ_RECORD_OVERFLOW and NO hits (count: hb_read_record_overflow) -- rerun those with hb_cr3bp_section.
+ * Trajectories that end in HB_TRAJ_MAXSTEPS / HB_TRAJ_NONFINITE report no hits.
+ * Replaces the same reference routines as hb_cr3bp_section: services/manifold.py:381-440 (tube) +
+ * poincare/synodic/backend.py:458-659, 382-455 (section).
+ * stage_events: NULL, or 4 caller-owned cudaEvent_t recorded before the propagate+scan kernel, after it, after the
+ * candidate emission and after order+dedup.                                                          */
+int64_t hb_section3_scratch_bytes(int64_t n, int32_t pool_records_per_traj);
+int hb_cr3bp_section3(const hb_cr3bp *sys, const hb_integ *integ, const hb_section *sec, int64_t n,
+                      const double *y0_soa, const double *t_eval, int32_t m, hb_hit *hits, int64_t hit_capacity,
+                      int32_t *hits_per_traj, double *yf_soa, int32_t *n_acc, int32_t *n_rej, int32_t *status,
+                      void *scratch, int64_t scratch_bytes, void *workspace, void *stream,
+                      void *const *stage_events);
 
 /* Propagation with a terminal plane event (event always terminal, as in the reference):
  * replaces _integrate_dop853_until_event + _dop853_refine_in_step (rk.py:2680-2803, 2006-2102).

@@ -95,7 +95,13 @@ def test_argument_validation_needs_no_gpu():
     assert lib.hb_cm_lift(C.byref(ham), C.byref(o), 4, None, None, None, None) < 0    # null arrays
     sysd, integ, sec = _lib.HbCr3bp(0.0121, 1, -1, -1, 0), hiten_b200.make_integ(), hiten_b200.synodic.make_section("y")
     assert lib.hb_cr3bp_section2(C.byref(sysd), C.byref(integ), C.byref(sec), 8, None, None, 1, None, 0, None, None, None,
-                                 None, None, None, 0, None, None) < 0             # m < 2, no workspace
+                                 None, None, None, 0, None, None, None) < 0       # m < 2, no workspace
+    assert lib.hb_cr3bp_section3(C.byref(sysd), C.byref(integ), C.byref(sec), 8, None, None, 1, None, 0, None, None, None,
+                                 None, None, None, 0, None, None, None) < 0
+    # section3 scratch: 4.2 KB of lists per trajectory + 512 B per pooled record, monotone in both arguments
+    a3, b3 = lib.hb_section3_scratch_bytes(1000, 4), lib.hb_section3_scratch_bytes(1000, 8)
+    assert b3 - a3 == 1000 * 4 * 512 and lib.hb_section3_scratch_bytes(2000, 4) > a3
+    assert lib.hb_section3_scratch_bytes(-1, 4) < 0 and lib.hb_section3_scratch_bytes(10, 0) < 0
     assert lib.hb_read_record_overflow(None, None, None) < 0
     # manifold-tube entry points (8f#3)
     assert lib.hb_manifold_ics(None, None, 2000, 2.75, None, 1, None, 0, None, 5, None, None, None) == 0   # empty tube
