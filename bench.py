@@ -1,16 +1,18 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the B200-native HITEN propagation hot path.
 
-Workload (BASELINE.json configs[4] geometry at per-GPU size; "C5-tube"): stable-manifold tube of the
-Earth-Moon L1 halo (Az=0.2 S) of configs[0]: 2000 orbit nodes x D displacements log-spaced in
-[1e-7, 1e-5], every trajectory propagated backward over tf = 0.75*2*pi with
-DOP853 at rtol = atol = 1e-12 -- N = 131072 trajectories per GPU (8 GPUs ~ 1e6 = configs[4]),
-weak scaling, no data-path collective, one gather of end states at the end of a step (N > 1).
+Workload = BASELINE.json configs[4] as the reference runs it (examples/heteroclinic_connection.py:29-63):
+the stable-manifold tube of the Earth-Moon L1 halo (Az = 0.5 S; backward, 0.9 x 2 pi) and the unstable-manifold tube of
+the L2 halo (Az = 0.3663368 N; forward, 2 pi), each 2000 orbit nodes x displacements log-spaced in [1e-7, 1e-5], every
+trajectory propagated with DOP853 at rtol = atol = 1e-12, dense samples on Manifold.compute()'s dt = 1e-3 grid streamed
+through the synodic detector for the section x = 1 - mu / (y, z) / direction -1 (+1 for the stable tube, the flip of
+connections/interfaces.py:350).  1e6 trajectories per GPU and step (5e5 per tube); hits + end states out.
+Parity with the reference on this geometry: tests/test_gpu_c5.py (bit for bit against tests/golden/c5_connection.npz).
 
-A "step" = one pass of the hot path over the per-GPU batch: the fused tube + synodic-section kernel
-(hb_cr3bp_section: DOP853 propagation, dense samples on the reference's dt = 1e-3 grid streamed through the
-reference's section detector, hits appended to a buffer, end states written).  metric = fp64 CR3BP RK steps/s
-(attempted DOP853 steps, accepted + rejected, whole job); crossings/s is reported beside it.
+A "step" = one pass of the hot path over the per-GPU batch (both tubes).  metric = fp64 CR3BP RK steps/s (attempted
+DOP853 steps, accepted + rejected, whole job); crossings/s is reported beside it.  N > 1: one rank per GPU, interleaved
+index shards (weak scaling: 1e6 per GPU), no data-path collective, one NCCL gather of hit records, hit counts and end
+states per tube at the end of a step; extra.strong_scaling times configs[4]'s 1e6 TOTAL over the N GPUs.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--arith parity|fast] [--impl ours|reference]
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
@@ -18,6 +20,7 @@ reference's section detector, hits appended to a buffer, end states written).  m
 Prints ONE JSON line on rank 0.
 """
 import argparse
+import ctypes
 import json
 import os
 import sys
@@ -27,28 +30,20 @@ import time
 import numpy as np
 
 REPO = os.path.dirname(os.path.abspath(__file__))
-for _p in (REPO, os.path.join(REPO, "tests")):
+for _p in (REPO, os.path.join(REPO, "tests"), os.path.join(REPO, "tests", "golden")):
     if _p not in sys.path:
         sys.path.insert(0, _p)
 
 FLOP_PER_STEP = 1350.0          # algorithmic flop per attempted 6-state DOP853 step
 FLOP_PER_SEGMENT = 1050.0       # dense-output cache of one accepted step (3 RHS + D/A_ext rows)
-FLOP_PER_SAMPLE = 84.0          # one dense sample (7-term Horner x 6 components)
-GRID_DT = 1.0e-3                # Manifold.compute default dt -> 4713 samples over tf
-N_PER_GPU = 1_000_000            # BASELINE configs[4]: 1e6 manifold trajectories (fits one B200: 82 GB of step scratch)
-TF = 0.75 * 2.0 * np.pi
-
-
-def build_ics(n, rank=0, world=1):
-    """Deterministic synthetic batch: 2000 tube nodes x displacements, interleaved over ranks."""
-    from hiten_b200.manifold import manifold_initial_conditions
-    t = np.load(os.path.join(REPO, "tests", "golden", "tube_nodes_c1.npz"))
-    total = n * world
-    n_disp = (total + 1999) // 2000
-    disp = np.logspace(-7.0, -5.0, n_disp)
-    ics = manifold_initial_conditions(t["x_node"], t["man"], disp)[:total]
-    # displacement-major order: neighbouring lanes carry neighbouring orbit phases
-    return np.ascontiguousarray(ics[rank::world][:n]), float(t["mu"])
+N_PER_GPU = 1_000_000           # BASELINE configs[4]: 1e6 manifold trajectories (both tubes together)
+STEPS_CAPACITY = 192            # accepted steps per trajectory the hb_cr3bp_section2 scratch holds (C5 needs <= 183)
+TUBES = ("l1", "l2")
+WORKLOAD = ("C5 = BASELINE configs[4] as examples/heteroclinic_connection.py runs it: EM L1 halo (Az=0.5 S) stable tube "
+            "(backward, 0.9*2pi, 5655 samples) + EM L2 halo (Az=0.3663368 N) unstable tube (forward, 2pi, 6284 samples), "
+            "2000 orbit nodes x log-spaced displacements [1e-7,1e-5] each, DOP853 rtol=atol=1e-12, dense samples on the "
+            "dt=1e-3 grid streamed through the synodic detector x=1-mu / (y,z) / direction -1 (+1 for the stable tube), "
+            "segment_refine=50; hits + end states out")
 
 
 class ClockSampler:
@@ -100,68 +95,157 @@ class ClockSampler:
                 "samples": len(self.samples)}
 
 
-def cpu_tube_section(ics, mu, n_threads):
-    """The same step on the CPU oracle: dense tube on the dt=1e-3 grid + section detection. Returns RK steps, hits."""
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU arms: the oracle port (all host threads) and the reference's own code (oracle/_ref, when it shipped)
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_port_step(ics, mu, n_threads):
+    """The same step on the CPU oracle (C restatement): dense tube on the dt = 1e-3 grid + section detection, both
+    tubes.  Returns (RK steps, hits)."""
     import oracle_lib as O
-    s = O.system(O.SYS_CR3BP6, mu, fwd=-1, flip=(0, 6))
-    m = max(int(abs(TF) / GRID_DT) + 1, 100)
-    t_eval = np.linspace(0.0, TF, m)
-    times = -t_eval
+    from hiten_b200 import workloads as W
     steps, hits = 0, 0
-    chunk = 512                                            # 512 x 4713 x 48 B = 116 MB of dense output at a time
-    for a in range(0, len(ics), chunk):
-        dense, c = O.batch_dense(s, O.DOP853, O.default_tol(), ics[a:a + chunk], t_eval, n_threads)
-        steps += int(c.sum())
-        hits += O.batch_synodic_count(times, dense, 1, 0.0, -1, (0, 2), 50, 1e-6, 1e-9, 1e-6, n_threads)
+    for key in TUBES:
+        fwd = W.C5_TUBES[key]["forward"]
+        s = O.system(O.SYS_CR3BP6, mu, fwd=fwd, flip=(0, 6))
+        t_eval = W.c5_grid(key)
+        chunk = 512                                            # 512 x 6284 x 48 B = 154 MB of dense output at a time
+        x = ics[key]
+        for a in range(0, len(x), chunk):
+            dense, c = O.batch_dense(s, O.DOP853, O.default_tol(), x[a:a + chunk], t_eval, n_threads)
+            steps += int(c.sum())
+            hits += O.batch_synodic_count(fwd * t_eval, dense, 0, 1.0 - mu, W.C5_TUBES[key]["direction"], (1, 2), 50,
+                                          1e-6, 1e-9, 1e-6, n_threads)
     return steps, hits
 
 
-def cpu_port_throughput(ics, mu, n_threads, seconds_target=12.0):
-    """The oracle (C port of the reference algorithm) on the host cores, bounded sample of the same step."""
+def cpu_port_throughput(ics, mu, n_threads, seconds_target=10.0):
+    """Bounded sample of the step on the oracle port, all host threads."""
+    take = lambda k: {key: ics[key][:k] for key in TUBES}
     t0 = time.perf_counter()
-    cpu_tube_section(ics[:256], mu, n_threads)
+    cpu_port_step(take(128), mu, n_threads)
     dt = max(time.perf_counter() - t0, 1e-4)
-    n = int(min(len(ics), max(512, 256 / dt * seconds_target)))
+    n = int(min(len(ics["l1"]), max(256, 128 / dt * seconds_target)))
     t0 = time.perf_counter()
-    steps, _ = cpu_tube_section(ics[:n], mu, n_threads)
+    steps, _ = cpu_port_step(take(n), mu, n_threads)
     dt = time.perf_counter() - t0
-    return steps / dt, n, dt
+    return steps / dt, 2 * n, dt
+
+
+class ReferenceArm:
+    """The reference's OWN code on this step: `_propagate_dynsys` per initial condition, exactly as the fraction loop of
+    `_ManifoldDynamicsService._run_compute` calls it (services/manifold.py:399-409), then `_SynodicDetectionBackend.run`
+    on the tube (synodic/backend.py:823) with the request SynodicMap.compute() builds.  The package is imported from
+    oracle/_ref (unmodified copy, oracle/build_ref.sh) -- /root/reference does not exist on the GPU box.  The reference
+    has no parallel driver for the propagation loop and its detection is a Python loop under the GIL: 1 core."""
+
+    def __init__(self):
+        import _refenv
+        self.src = _refenv.enable()
+        from hiten import System
+        from hiten.algorithms.dynamics.base import _propagate_dynsys
+        from hiten.algorithms.poincare.synodic.backend import _SynodicDetectionBackend
+        from hiten.algorithms.poincare.synodic.types import SynodicBackendRequest
+        self.system = System.from_bodies("earth", "moon")
+        self.prop, self.backend, self.Request = _propagate_dynsys, _SynodicDetectionBackend(), SynodicBackendRequest
+
+    def step(self, ics, mu):
+        """-> (number of hits, seconds).  RK step counts come from the oracle (bit-identical controller)."""
+        from hiten_b200 import workloads as W
+        hits = 0
+        t0 = time.perf_counter()
+        for key in TUBES:
+            tube = W.C5_TUBES[key]
+            t_eval = W.c5_grid(key)
+            trajs = []
+            for x0 in ics[key]:
+                sol = self.prop(dynsys=self.system.dynsys, state0=x0, t0=0.0, tf=float(t_eval[-1]), forward=tube["forward"],
+                                steps=len(t_eval), method="adaptive", order=8, flip_indices=slice(0, 6))
+                trajs.append((sol.times, sol.states))
+            normal = np.zeros(6)
+            normal[0] = 1.0
+            req = self.Request(trajectories=trajs, normal=normal, trajectory_indices=list(range(len(trajs))),
+                               offset=1.0 - mu, plane_coords=("y", "z"), interp_kind="linear", segment_refine=50,
+                               tol_on_surface=1e-6, dedup_time_tol=1e-9, dedup_point_tol=1e-6, max_hits_per_traj=None,
+                               newton_max_iter=10, direction=tube["direction"])
+            hits += len(self.backend.run(req).points)
+        return hits, time.perf_counter() - t0
+
+
+def oracle_step_count(ics, mu):
+    import oracle_lib as O
+    from hiten_b200 import workloads as W
+    total = 0
+    for key in TUBES:
+        s = O.system(O.SYS_CR3BP6, mu, fwd=W.C5_TUBES[key]["forward"], flip=(0, 6))
+        _, c = O.batch_final(s, O.DOP853, O.default_tol(), ics[key], 0.0, float(W.c5_grid(key)[-1]), 4)
+        total += int(c.sum())
+    return total
+
+
+def reference_available():
+    import _refenv
+    return _refenv.available() is not None
 
 
 def run_reference(args):
-    """--impl reference: the reference algorithm's CPU restatement (oracle port, all host threads) on the same
-    step -- tube propagation, dense samples on the dt=1e-3 grid, section detection -- on a bounded sample."""
+    """--impl reference: the reference's own CPU implementation of the step (oracle/_ref) on a bounded sample of the
+    same batch; the oracle port (all host threads) when the reference package did not ship."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import oracle_lib as O
+    from hiten_b200 import workloads as W
+    ics_all, mu = W.c5_batch(N_PER_GPU)
     n_threads = O.lib().ho_max_threads()
-    sample = 8192
-    ics, mu = build_ics(sample)
-    for _ in range(args.warmup):
-        cpu_tube_section(ics[:512], mu, n_threads)
-    steps_total, hits_total, t_total = 0.0, 0.0, 0.0
-    for _ in range(args.steps):
-        t0 = time.perf_counter()
-        st, hi = cpu_tube_section(ics, mu, n_threads)
-        t_total += time.perf_counter() - t0
-        steps_total += st
-        hits_total += hi
-    val = steps_total / t_total
+    if reference_available():
+        arm = ReferenceArm()
+        per_tube = 16                                             # ~80 ms per trajectory: ~2.6 s per step
+        pick = lambda k: {key: ics_all[key][:: max(1, len(ics_all[key]) // k)][:k] for key in TUBES}
+        sample = pick(per_tube)
+        for _ in range(max(args.warmup, 1)):
+            arm.step(pick(1), mu)                                 # Numba compiles on the first call
+        rk_steps = oracle_step_count(sample, mu)
+        hits_total, t_total = 0, 0.0
+        for _ in range(args.steps):
+            h, dt = arm.step(sample, mu)
+            hits_total += h
+            t_total += dt
+        val = rk_steps * args.steps / t_total
+        kind, cores = "reference", 1
+        what = (f"{2 * per_tube} trajectories per step ({per_tube} per tube, strided through the batch): "
+                "_propagate_dynsys per initial condition + _SynodicDetectionBackend.run, the reference's own code from "
+                f"oracle/_ref ({os.path.basename(arm.src.rstrip('/'))})")
+        port_v, port_n, port_dt = cpu_port_throughput(ics_all, mu, n_threads, seconds_target=5.0)
+        port = {"value": port_v, "unit": "RK steps/s", "cores": n_threads, "kind": "port",
+                "sample": f"{port_n} trajectories, {port_dt:.1f} s"}
+    else:
+        sample = {key: ics_all[key][:4096] for key in TUBES}
+        for _ in range(args.warmup):
+            cpu_port_step({key: sample[key][:256] for key in TUBES}, mu, n_threads)
+        steps_total, hits_total, t_total = 0.0, 0.0, 0.0
+        for _ in range(args.steps):
+            t0 = time.perf_counter()
+            st, hi = cpu_port_step(sample, mu, n_threads)
+            t_total += time.perf_counter() - t0
+            steps_total += st
+            hits_total += hi
+        val = steps_total / t_total
+        kind, cores, port = "port", n_threads, None
+        what = "8192 trajectories per step (4096 per tube), CPU oracle port (oracle/_ref absent)"
     line = {
         "impl": "reference", "metric": "fp64 CR3BP RK steps/s", "value": val, "unit": "RK steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "crossings_per_s": hits_total / t_total,
-        "config": {"workload": "C5-tube (BASELINE configs[4] trajectories, configs[1] section): EM L1 halo (Az=0.2 S) "
-                               "stable-manifold tube, DOP853 rtol=atol=1e-12, backward tf=0.75*2pi, dense samples on "
-                               "the dt=1e-3 grid (4713) + synodic detector y=0 / (x,z) / direction=-1; "
-                               f"bounded sample of {sample} trajectories per step (CPU oracle port)"},
-        "cpu_baseline": {"value": val, "unit": "RK steps/s", "cores": n_threads, "kind": "port",
-                         "sample": f"{sample} trajectories per step, {args.steps} steps"},
+        "config": {"workload": WORKLOAD + "; bounded sample: " + what},
+        "cpu_baseline": {"value": val, "unit": "RK steps/s", "cores": cores, "kind": kind, "sample": what},
         "e2e": {"value": val, "unit": "RK steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if port is not None:
+        line["cpu_baseline_port"] = port
     print(json.dumps(line))
 
 
@@ -188,8 +272,22 @@ def secondary_configs(hb, torch, steps, flush, barrier):
     rng = np.random.default_rng(1)
     opts = cm.make_opts(0.01, 2000, "symplectic", 4, "p3", 20.0, "parity")
     hold = {}
+    # configs[2]'s seeds: uniform in +-0.9 x the turning-point box on (q2, p2), lifted onto the energy
+    # surface with hb_cm_lift (the reference's lift_plane_point), the first n valid ones -- all distinct
+    Hs = cm.PolyTable.single(g["H_deg"], g["H_coef"], g["H_exp"])
+    box = 0.9 * g["turning_q2_p2"]
+
+    def lifted_seeds(n_seeds):
+        got, have = [], 0
+        while have < n_seeds:
+            pts = torch.from_numpy(rng.uniform(-1.0, 1.0, (2 * n_seeds, 2)) * box).cuda()
+            ok, st = cm.lift_plane_points(Hs, "p3", pts, float(g["energy"]))
+            got.append(st[ok])
+            have += int(ok.sum().item())
+        return torch.cat(got)[:n_seeds].contiguous()
+
     for n_seeds, label in ((100_000, "cm_map_tao4_1e5_seeds"), (1_000_000, "cm_map_tao4_1e6_seeds")):
-        seeds = torch.from_numpy(g["seeds_p3"][rng.integers(0, 512, n_seeds)]).cuda()
+        seeds = lifted_seeds(n_seeds)
 
         def run_cm():
             hold["r"] = cm.poincare_map(tab, seeds, opts)
@@ -199,7 +297,8 @@ def secondary_configs(hb, torch, steps, flush, barrier):
         t = time_steps(run_cm, steps, flush, barrier, torch)
         f, _, tt = hold["r"]
         cm_steps = float((tt / 0.01).ceil().sum().item())
-        out[label] = {"steps_per_s": cm_steps * steps / t, "crossings_per_s": int(f.sum().item()) * steps / t,
+        out[label] = {"distinct_lifted_seeds": int(torch.unique(seeds, dim=0).shape[0]),
+                      "steps_per_s": cm_steps * steps / t, "crossings_per_s": int(f.sum().item()) * steps / t,
                       "ms_per_return": 1e3 * t / steps, "tflops": cm_steps * steps * 8100.0 / t / 1e12}
     out["cm_map_tao4_1e5_seeds"]["note"] = ("critical-path bound: the slowest seed needs ~1300 sequential steps of "
                                             "~9 us (11.9 ms on its own); 1e6 seeds fill the machine")
@@ -357,10 +456,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--arith", default="parity", choices=["parity", "fast"])
     ap.add_argument("--n-per-gpu", type=int, default=N_PER_GPU)
-    ap.add_argument("--steps-capacity", type=int, default=160,
-                    help="accepted steps per trajectory the hb_cr3bp_section2 scratch holds (0: fused hb_cr3bp_section)")
+    ap.add_argument("--pipeline", default="section2", choices=["section2", "section3", "fused"],
+                    help="section2: step records through an HBM scratch (default, fastest); section3: records handed over "
+                         "in shared memory inside one kernel (no step scratch); fused: hb_cr3bp_section")
+    ap.add_argument("--steps-capacity", type=int, default=STEPS_CAPACITY)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extra", action="store_true", help="skip the secondary (propagate-only / fast) timings")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary timings")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -372,7 +473,8 @@ def main():
     import torch.distributed as dist
     import hiten_b200 as hb
     from hiten_b200 import propagate as P
-    from hiten_b200 import synodic
+    from hiten_b200 import sharded, synodic
+    from hiten_b200 import workloads as W
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -386,31 +488,46 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     n = args.n_per_gpu
-    ics, mu = build_ics(n, rank, world)
     integ = hb.make_integ(arith=args.arith)
-    m = max(int(abs(TF) / GRID_DT) + 1, 100)                              # manifold.py:396-397 -> 4713
-    t_eval = np.linspace(0.0, TF, m)
-    sec = synodic.make_section("y", 0.0, ("x", "z"), -1)                  # configs[1]'s SynodicMap call
-    runner = synodic.TubeSectionRunner(n, mu, t_eval, sec, forward=-1, flip=(0, 6), integ=integ, device=dev,
-                                       steps_capacity=args.steps_capacity)
-    y0_soa = torch.from_numpy(np.ascontiguousarray(ics.T)).to(dev)       # resident input [6, N]
-    host_in = torch.from_numpy(ics).pin_memory()                          # e2e input  [N, 6]
+    kind = {"section2": dict(steps_capacity=args.steps_capacity), "section3": dict(pool_records=8), "fused": {}}[args.pipeline]
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)  # > 126 MB L2
-    gather_yf = gather_cnt = None
-    if world > 1 and rank == 0:
-        gather_yf = [torch.empty((6, n), dtype=torch.float64, device=dev) for _ in range(world)]
-        gather_cnt = [torch.empty(n, dtype=torch.int32, device=dev) for _ in range(world)]
 
-    def step_resident():
-        runner.launch(y0_soa)
-        if world > 1:                                   # the one exchange: end states + hit counts to rank 0
-            dist.gather(runner.yf, gather_yf, dst=0)
-            dist.gather(runner.per, gather_cnt, dst=0)
+    def make_job(n_total_global):
+        """Runners + resident inputs of this rank for a job of n_total_global trajectories (both tubes, all ranks)."""
+        ics, mu = W.c5_batch(n_total_global, rank, world)
+        job = {"ics": ics, "mu": mu, "tubes": {}}
+        scratch = None
+        for key in TUBES:
+            x = ics[key]
+            d = sharded.DistributedTubeSection(
+                n_total_global // 2, mu, W.c5_grid(key), W.c5_section(key, mu), forward=W.C5_TUBES[key]["forward"],
+                flip=(0, 6), integ=integ,
+                runner_factory=lambda nl, key=key: synodic.TubeSectionRunner(
+                    nl, mu, W.c5_grid(key), W.c5_section(key, mu), forward=W.C5_TUBES[key]["forward"], flip=(0, 6),
+                    integ=integ, device=dev, scratch=scratch, **kind))
+            assert len(d.index) == len(x)
+            if scratch is None:
+                scratch = d.runner.scratch
+            job["tubes"][key] = {"dist": d, "run": d.runner,
+                                 "y0": torch.from_numpy(np.ascontiguousarray(x.T)).to(dev),      # resident input [6, n]
+                                 "host": torch.from_numpy(x).pin_memory()}                      # e2e input [n, 6]
+        job["scratch"] = scratch
+        return job
 
-    def make_e2e():
-        # the public streaming API: host batches in (pinned), host results out (pinned), double-buffered copies
-        return synodic.TubeSectionStream(n, mu, t_eval, sec, forward=-1, flip=(0, 6), integ=integ, device=dev,
-                                         steps_capacity=args.steps_capacity, scratch=runner.scratch)
+    job = make_job(n * world)
+    mu = job["mu"]
+
+    def step_of(j):
+        def step():
+            for key in TUBES:
+                t = j["tubes"][key]
+                t["run"].launch(t["y0"])
+            if world > 1:                                   # the one exchange: hit records, counts, end states -> rank 0
+                for key in TUBES:
+                    j["tubes"][key]["dist"].gather_device()
+        return step
+
+    step_resident = step_of(job)
 
     def barrier():
         if world > 1:
@@ -427,175 +544,283 @@ def main():
     t_dev = time_steps(step_resident, args.steps, flush, barrier, torch)
     wall = time.perf_counter() - wall0
     clocks = sampler.stop()
-    n_hits = runner.hit_count()
-    steps_acc = int(runner.nacc.sum().item())
-    steps_per_pass = steps_acc + int(runner.nrej.sum().item())
-    ok = bool((runner.status == 0).all().item())
-    t_kernel_local = t_dev
 
-    # per-kernel split of the pipeline (CUDA events recorded inside hb_cr3bp_section2, same stream), separate pass
+    def tallies(j):
+        acc = rej = hits = over = 0
+        ok = True
+        for key in TUBES:
+            run = j["tubes"][key]["run"]
+            if run.scratch is not None:
+                nt = ctypes.c_int64(0)
+                run.lib.hb_read_record_overflow(run.ws.data_ptr(), ctypes.byref(nt), None)
+                over += int(nt.value)
+            hits += run.hit_count()
+            acc += int(run.nacc.sum().item())
+            rej += int(run.nrej.sum().item())
+            ok = ok and bool((run.status == 0).all().item())
+        return acc, rej, hits, over, ok
+
+    steps_acc, steps_rej, n_hits, n_overflow, ok = tallies(job)
+    steps_per_pass = steps_acc + steps_rej
+
+    # per-kernel split of the pipeline: caller-owned CUDA events recorded by the library between its kernels on the
+    # launching stream, in a separate pass over the same inputs
     stage_ms = None
-    if args.steps_capacity > 0:
-        import ctypes
-        lib = runner.lib
-        lib.hb_section2_profile(1)
-        acc = np.zeros(4)
-        buf = (ctypes.c_float * 4)()
-        for i in range(args.steps):
-            flush.fill_(float(i))
-            runner.launch(y0_soa)
-            lib.hb_section2_read_profile(buf)
-            acc += np.array(list(buf))
-        lib.hb_section2_profile(0)
-        stage_ms = (acc / args.steps).tolist()
+    if args.pipeline != "fused":
+        n_ev = 5 if args.pipeline == "section2" else 4
+        acc_ms = np.zeros(n_ev - 1)
+        for key in TUBES:
+            t = job["tubes"][key]
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(n_ev)]
+            t["run"].set_stage_events(ev)
+            for i in range(args.steps):
+                flush.fill_(float(i))
+                t["run"].launch(t["y0"])
+                torch.cuda.synchronize()
+                acc_ms += np.array([ev[a].elapsed_time(ev[a + 1]) for a in range(n_ev - 1)])
+            t["run"].set_stage_events(None)
+        stage_ms = (acc_ms / args.steps).tolist()
 
     # e2e: host buffers in, host results out, every step's H2D and D2H inside the timed region (overlapped with the
-    # neighbouring steps' compute by TubeSectionStream's double buffering)
-    stream_api = make_e2e()
-    for r in stream_api.run([host_in] * 3):
-        pass
+    # neighbouring steps' compute by TubeSectionStream's double buffering); hits are put in the reference's order
+    streams = {}
+    for key in TUBES:
+        skw = dict(steps_capacity=args.steps_capacity) if args.pipeline == "section2" else \
+            (dict(steps_capacity=0, pool_records=8) if args.pipeline == "section3" else dict(steps_capacity=0, pool_records=0))
+        streams[key] = synodic.TubeSectionStream(len(job["ics"][key]), mu, W.c5_grid(key), W.c5_section(key, mu),
+                                                 forward=W.C5_TUBES[key]["forward"], flip=(0, 6), integ=integ, device=dev,
+                                                 scratch=job["scratch"], **skw)
+
+    def e2e_pass(k):
+        total, last_ordered = 0, None
+        for key in TUBES:
+            for r in streams[key].run([job["tubes"][key]["host"]] * k):
+                last_ordered = r.hits                       # already in the reference's order (sorted on the device)
+                last = r.n_hits
+            total += last
+        return total, last_ordered
+
+    e2e_pass(2)
     barrier()
     e2e_t0 = time.perf_counter()
-    k_e2e = 0
-    for r in stream_api.run([host_in] * args.steps):
-        k_e2e = r.n_hits
+    k_e2e, _ = e2e_pass(args.steps)
     barrier()
     e2e_t = time.perf_counter() - e2e_t0
-    e2e_ok = bool(k_e2e == n_hits and (r.status == 0).all())
-    del stream_api
+    e2e_ok = bool(k_e2e == n_hits)
+    del streams
 
-    tt = torch.tensor([t_dev, e2e_t, float(steps_per_pass), float(n_hits), float(steps_acc)], dtype=torch.float64,
-                      device=dev)
+    # strong scaling (configs[4] = 1e6 trajectories in total over the N GPUs): same step on 1/N of the batch per rank
+    strong = None
+    if world > 1:
+        del job["tubes"]
+        sjob = make_job(n)
+        sstep = step_of(sjob)
+        for _ in range(3):
+            sstep()
+        barrier()
+        ts = time_steps(sstep, args.steps, flush, barrier, torch)
+        s_acc, s_rej, s_hits, _, s_ok = tallies(sjob)
+        strong = [ts, float(s_acc + s_rej), float(s_hits)]
+    else:
+        strong = [t_dev, float(steps_per_pass), float(n_hits)]
+
+    tt = torch.tensor([t_dev, e2e_t, float(steps_per_pass), float(n_hits), float(steps_acc), strong[0], strong[1], strong[2],
+                       float(n_overflow)], dtype=torch.float64, device=dev)
     if world > 1:
         tmax = tt.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = tt.clone()
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        t_dev, e2e_t = tmax[0].item(), tmax[1].item()
+        t_dev, e2e_t, strong_t = tmax[0].item(), tmax[1].item(), tmax[5].item()
         total_steps_pass, total_hits, total_acc = tsum[2].item(), tsum[3].item(), tsum[4].item()
+        strong_steps, strong_hits, total_overflow = tsum[6].item(), tsum[7].item(), tsum[8].item()
     else:
         total_steps_pass, total_hits, total_acc = float(steps_per_pass), float(n_hits), float(steps_acc)
+        strong_t, strong_steps, strong_hits, total_overflow = strong[0], strong[1], strong[2], float(n_overflow)
 
-    extra = {}
+    extra = {"strong_scaling": {"total_trajectories": n, "n_gpus": world, "ms_per_step": 1e3 * strong_t / args.steps,
+                                "rk_steps_per_s": strong_steps * args.steps / strong_t,
+                                "crossings_per_s": strong_hits * args.steps / strong_t,
+                                "note": "configs[4]'s 1e6 trajectories in TOTAL, 1/N per GPU, same step incl. the gather; "
+                                        "efficiency = rk_steps_per_s / (N x the N=1 value)"}}
     if not args.no_extra and world == 1:
-        # secondary numbers that explain the headline: propagation only (end states), both arithmetic variants,
-        # and the fused step in the other variant
         ws = P.workspace(dev)
+        y0_l1, tf_l1 = job["tubes"]["l1"]["y0"], float(W.c5_grid("l1")[-1])
         for name in ("parity", "fast"):
             ig = hb.make_integ(arith=name)
             hold = {}
 
             def prop():
-                hold["r"] = hb.cr3bp_propagate(y0_soa, mu, TF, forward=-1, flip=(0, 6), integ=ig, ws=ws)
+                hold["r"] = hb.cr3bp_propagate(y0_l1, mu, tf_l1, forward=-1, flip=(0, 6), integ=ig, ws=ws)
 
             for _ in range(3):
                 prop()
             tp = time_steps(prop, args.steps, flush, barrier, torch)
             sp = int((hold["r"].n_acc.sum() + hold["r"].n_rej.sum()).item())
-            extra[f"propagate_only_{name}"] = {"rk_steps_per_s": sp * args.steps / tp,
-                                               "tflops": sp * args.steps * FLOP_PER_STEP / tp / 1e12}
+            extra[f"propagate_only_{name}_l1_tube"] = {"rk_steps_per_s": sp * args.steps / tp, "ms": 1e3 * tp / args.steps,
+                                                       "tflops": sp * args.steps * FLOP_PER_STEP / tp / 1e12}
+        # the same step in the other arithmetic variant and through the other two forms of the pipeline
         other = "fast" if args.arith == "parity" else "parity"
-        for label, ar, cap in ((f"section_{other}", other, args.steps_capacity),
-                               ("section_fused_kernel_parity", "parity", 0), ("section_fused_kernel_fast", "fast", 0)):
-            r2 = synodic.TubeSectionRunner(n, mu, t_eval, sec, forward=-1, flip=(0, 6), integ=hb.make_integ(arith=ar),
-                                           device=dev, steps_capacity=cap, scratch=runner.scratch if cap > 0 else None)
-            for _ in range(3):
-                r2.launch(y0_soa)
-            t2 = time_steps(lambda: r2.launch(y0_soa), args.steps, flush, barrier, torch)
-            s2 = int((r2.nacc.sum() + r2.nrej.sum()).item())
-            extra[label] = {"rk_steps_per_s": s2 * args.steps / t2, "ms_per_step": 1e3 * t2 / args.steps,
-                            "crossings_per_s": r2.hit_count() * args.steps / t2}
-            del r2
-        if args.steps_capacity > 0:
-            # the same step with Manifold.compute()'s trajectory filters judged from the step records:
-            # all 4713 samples of every trajectory are rebuilt and tested (safe radii, Jacobi drift)
-            r3 = synodic.TubeSectionRunner(n, mu, t_eval, sec, forward=-1, flip=(0, 6), integ=integ, device=dev,
-                                           steps_capacity=args.steps_capacity, scratch=runner.scratch,
-                                           filters=(3.318e-05, 9.04e-06, 1e-6))
-            for _ in range(3):
-                r3.launch(y0_soa)
-            t3 = time_steps(lambda: r3.launch(y0_soa), args.steps, flush, barrier, torch)
-            s3 = int((r3.nacc.sum() + r3.nrej.sum()).item())
-            kept = int((r3.filter_result()[1] == 1).sum().item())
-            filt_ms = 1e3 * t3 / args.steps - 1e3 * t_dev / args.steps
-            extra[f"section_{args.arith}_with_trajectory_filters"] = {
-                "rk_steps_per_s": s3 * args.steps / t3, "ms_per_step": 1e3 * t3 / args.steps,
-                "filter_kernel_ms": filt_ms, "samples_per_s": n * float(m) / (filt_ms * 1e-3) if filt_ms > 0 else None,
-                "kept_trajectories": kept,
-                "note": "hb_section2_filter: 6-component dense evaluation + r1, r2, Jacobi constant at every grid sample"}
-            del r3
-        extra.update(secondary_configs(hb, torch, args.steps, flush, barrier))
+        for label, ar, kw in ((f"step_{other}", other, kind), ("step_section3_parity", "parity", dict(pool_records=8)),
+                              ("step_fused_kernel_parity", "parity", {})):
+            if label == "step_section3_parity" and args.pipeline == "section3":
+                continue
+            rs = {key: synodic.TubeSectionRunner(len(job["ics"][key]), mu, W.c5_grid(key), W.c5_section(key, mu),
+                                                 forward=W.C5_TUBES[key]["forward"], flip=(0, 6),
+                                                 integ=hb.make_integ(arith=ar), device=dev,
+                                                 scratch=job["scratch"] if "steps_capacity" in kw else None, **kw)
+                  for key in TUBES}
+
+            def step2():
+                for key in TUBES:
+                    rs[key].launch(job["tubes"][key]["y0"])
+
+            for _ in range(2):
+                step2()
+            t2 = time_steps(step2, max(args.steps // 2, 2), flush, barrier, torch)
+            s2 = sum(int((rs[key].nacc.sum() + rs[key].nrej.sum()).item()) for key in TUBES)
+            k2 = sum(rs[key].hit_count() for key in TUBES)
+            extra[label] = {"rk_steps_per_s": s2 * max(args.steps // 2, 2) / t2, "ms_per_step": 1e3 * t2 / max(args.steps // 2, 2),
+                            "crossings_per_pass": k2, "tflops_whole_step": s2 * max(args.steps // 2, 2) * FLOP_PER_STEP / t2 / 1e12}
+            del rs
+            torch.cuda.empty_cache()
+        if "step_fast" in extra:
+            extra["step_fast"]["parity_verdict"] = (
+                "vs the reference's golden vectors (tests/test_gpu_fast_verdict.py): crossing counts identical on all five "
+                "golden tubes (1209 crossings), crossing points <= 1e-9 on 1208 of 1209 (all 386 of C5; max 2.4e-9 on one C1 "
+                "hit), end states > 1e-9 relative on 23 of 670 trajectories (max 7.5e-8, inside the reference's own 1-ulp "
+                "sensitivity): NOT the parity headline")
+        if args.pipeline == "section2":
+            # the step with Manifold.compute()'s trajectory filters judged from the step records
+            r1, r2 = W.c5_safe_radii()
+            rf = {key: synodic.TubeSectionRunner(len(job["ics"][key]), mu, W.c5_grid(key), W.c5_section(key, mu),
+                                                 forward=W.C5_TUBES[key]["forward"], flip=(0, 6), integ=integ, device=dev,
+                                                 steps_capacity=args.steps_capacity, scratch=job["scratch"],
+                                                 filters=(r1, r2, W.ENERGY_TOL)) for key in TUBES}
+
+            def step3():
+                for key in TUBES:
+                    rf[key].launch(job["tubes"][key]["y0"])
+
+            step3()
+            t3 = time_steps(step3, 2, flush, barrier, torch)
+            kept = {key: int((rf[key].filter_result()[1] == 1).sum().item()) for key in TUBES}
+            extra["step_with_trajectory_filters"] = {
+                "ms_per_step": 1e3 * t3 / 2, "kept_trajectories": kept,
+                "note": "hb_section2_filter: 6-component dense evaluation + r1, r2, Jacobi constant at every grid sample "
+                        "(safe radii 3.318e-05 / 9.04e-06, energy_tol 1e-6 as Manifold.compute())"}
+            del rf
+        # the connection search between the two hit sets of the last step
+        from hiten_b200 import connections as cn
+        hu, hs = job["tubes"]["l1"]["run"].sorted_hits(), job["tubes"]["l2"]["run"].sorted_hits()
+        t0 = time.perf_counter()
+        rc = cn.find_connections(hu.points, hs.points, hu.states, hs.states, 1e-3, 1.0, 1e-8,
+                                 traj_indices_u=hu.trajectory_indices, traj_indices_s=hs.trajectory_indices)
+        extra["connections_between_the_two_sections"] = {
+            "ms": 1e3 * (time.perf_counter() - t0), "hits_u": len(hu.times), "hits_s": len(hs.times),
+            "pairs_considered": rc.pairs_considered, "accepted": int(len(rc.delta_v)),
+            "note": "ConnectionPipeline.solve's backend step (eps2d=1e-3, delta_v_tol=1, ballistic_tol=1e-8) on this step's "
+                    "hits, wall time incl. H2D of the hit sets and D2H of the result"}
+        extra.update(secondary_configs(hb, torch, max(args.steps // 2, 2), flush, barrier))
 
     if rank == 0:
         value = total_steps_pass * args.steps / t_dev
         e2e_value = total_steps_pass * args.steps / e2e_t
         peak = hb.dfma_peak(200.0)
-        # Roofline of the DOMINANT kernel (k_dop853_6 in record mode + its first-step pre-pass): attempted steps x
-        # 1350 algorithmic flop over that kernel's own duration.  With the fused kernel (--steps-capacity 0) the
-        # whole step is one kernel and the accepted steps' dense caches (1050 flop) are added.
+        hbm = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))["hbm_gbs"] \
+            if os.path.exists(os.path.join(REPO, "MEASURED_PEAKS.json")) else 6500.0
+        rec_bytes = steps_acc * 512.0
         if stage_ms is not None:
+            # Roofline of the DOMINANT kernel (the propagation kernel of both tubes: k_dop853_6 in record mode + its
+            # first-step pre-pass, or the producer/consumer kernel of section3): attempted steps x 1350 flop over that
+            # kernel's own duration.
             achieved = steps_per_pass * FLOP_PER_STEP / (stage_ms[0] * 1e-3)
-            hbm = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))["hbm_gbs"] \
-                if os.path.exists(os.path.join(REPO, "MEASURED_PEAKS.json")) else 6500.0
-            rec_bytes = steps_acc * 512.0
-            extra["pipeline"] = {
-                "stage_ms": dict(zip(("propagate_record", "step_scan", "emit_candidates", "order_dedup"), stage_ms)),
-                "share_of_step_dominant": stage_ms[0] / sum(stage_ms),
-                "propagate_record_hbm_write_gbs": rec_bytes / (stage_ms[0] * 1e-3) / 1e9,
-                "step_scan_hbm_read_gbs": rec_bytes / (stage_ms[1] * 1e-3) / 1e9,
-                "step_scan_frac_of_hbm_peak": rec_bytes / (stage_ms[1] * 1e-3) / 1e9 / hbm,
-                "hbm_peak_gbs": hbm,
-            }
+            names = ("propagate_record", "step_scan", "emit_candidates", "order_dedup") if args.pipeline == "section2" \
+                else ("propagate_and_scan", "emit_candidates", "order_dedup")
+            extra["pipeline"] = {"stage_ms": dict(zip(names, stage_ms)), "share_of_step_dominant": stage_ms[0] / sum(stage_ms),
+                                 "hbm_peak_gbs": hbm}
+            if args.pipeline == "section2":
+                extra["pipeline"].update({
+                    "propagate_record_hbm_write_gbs": rec_bytes / (stage_ms[0] * 1e-3) / 1e9,
+                    "step_scan_hbm_read_gbs": rec_bytes / (stage_ms[1] * 1e-3) / 1e9,
+                    "step_scan_frac_of_hbm_peak": rec_bytes / (stage_ms[1] * 1e-3) / 1e9 / hbm})
+            traffic = (rec_bytes if args.pipeline == "section2" else 0.0) + len(job["ics"]["l1"]) * 2 * (48 + 48 + 12)
         else:
-            achieved = (steps_per_pass * FLOP_PER_STEP + steps_acc * FLOP_PER_SEGMENT) * args.steps / t_kernel_local
+            achieved = (steps_per_pass * FLOP_PER_STEP + steps_acc * FLOP_PER_SEGMENT) * args.steps / t_dev
+            traffic = None
         for v in extra.values():
-            if "tflops" in v:
+            if isinstance(v, dict) and "tflops" in v:
                 v["frac_of_fp64_peak"] = v["tflops"] * 1e12 / peak
+            if isinstance(v, dict) and "tflops_whole_step" in v:
+                v["frac_of_fp64_peak_whole_step"] = v["tflops_whole_step"] * 1e12 / peak
+        launches_per_tube = {"section2": 6 if args.arith == "parity" else 5, "section3": 5 if args.arith == "parity" else 4,
+                             "fused": 2 if args.arith == "parity" else 1}[args.pipeline]
         line = {
             "metric": "fp64 CR3BP RK steps/s", "value": value, "unit": "RK steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "crossings_per_s": total_hits * args.steps / t_dev,
+            "whole_step_tflops": total_steps_pass * args.steps * FLOP_PER_STEP / t_dev / 1e12,
+            "whole_step_frac_of_fp64_peak": total_steps_pass * args.steps * FLOP_PER_STEP / t_dev / (peak * world),
             "config": {
-                "workload": "C5-tube (BASELINE configs[4] = 1e6 trajectories per GPU, configs[1] section): EM L1 halo (Az=0.2 S) "
-                            "stable-manifold tube, 2000 nodes x log-spaced displacements, DOP853 rtol=atol=1e-12, "
-                            "backward tf=0.75*2pi, dense samples on the dt=1e-3 grid (4713) streamed through the "
-                            "synodic detector y=0 / (x,z) / direction=-1 (segment_refine=50), hits + end states out",
-                "trajectories_per_gpu": n, "grid_samples": m, "arith": args.arith,
-                "path": "hb_cr3bp_section2 (propagate+record -> step scan -> emit -> order+dedup)"
-                        if args.steps_capacity > 0 else "hb_cr3bp_section (fused kernel)",
-                "steps_capacity": args.steps_capacity,
-                "l2": "flushed between timed iterations (256 MB fill); inputs 48 B and step records ~44 KB per trajectory (>> L2)",
+                "workload": WORKLOAD,
+                "trajectories_per_gpu": n, "trajectories_per_tube_per_gpu": n // 2,
+                "grid_samples": {key: int(len(W.c5_grid(key))) for key in TUBES}, "arith": args.arith,
+                "path": {"section2": "hb_cr3bp_section2 per tube (propagate+record -> step scan -> emit -> order+dedup)",
+                         "section3": "hb_cr3bp_section3 per tube (propagating + scanning warps in one kernel -> emit -> order+dedup)",
+                         "fused": "hb_cr3bp_section per tube (fused kernel)"}[args.pipeline],
+                "steps_capacity": args.steps_capacity if args.pipeline == "section2" else None,
+                "record_overflow_trajectories_rerun": total_overflow,
+                "l2": "flushed between timed iterations (256 MB fill); inputs 48 B and step records ~50 KB per trajectory (>> L2)",
                 "rk_steps_per_pass": total_steps_pass, "accepted_steps_per_pass": total_acc,
                 "crossings_per_pass": total_hits, "all_status_ok": ok,
+                "exchange": None if world == 1 else "per tube: all-gather of hit counts, NCCL gather of hit records "
+                                                    "(padded to the largest shard) and end states to rank 0, inside the timed step",
             },
             "roofline": {"bound": "fp64", "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "TFLOP/s",
-                         "frac": achieved / peak,
-                         "traffic": (4.437e10 if (n == N_PER_GPU and args.steps_capacity > 0 and args.arith == "parity") else None),
-                         "kernel": "k_dop853_6<MODE_RECORD> (+ k_first_steps)" if stage_ms is not None
-                                   else "k_dop853_6_section",
-                         "note": "FP64 FMA pipe roofline of the dominant kernel (its HBM side: 512 B written per "
-                                 "accepted step = 44.3 GB per launch at ~2.2 TB/s, a third of the HBM roof; traffic = "
-                                 "dram read+write of one ncu --set full capture, profiles/r01_pipeline_v5_summary.md). "
-                                 "achieved = attempted steps x 1350 algorithmic flop (SURVEY 8d) / the kernel's own "
-                                 "duration (CUDA events recorded between the pipeline's kernels on the launching "
-                                 "stream); peak = hb_dfma_peak measured in this process"},
+                         "frac": achieved / peak, "traffic": traffic,
+                         "kernel": {"section2": "k_dop853_6<MODE_RECORD> (+ k_first_steps), both tubes",
+                                    "section3": "k_tube_section_pc (+ k_first_steps), both tubes",
+                                    "fused": "k_dop853_6_section, both tubes"}[args.pipeline],
+                         "note": "FP64 FMA pipe roofline of the dominant kernel: achieved = attempted steps x 1350 algorithmic "
+                                 "flop (SURVEY 8d) / the kernel's own duration (CUDA events recorded between the pipeline's "
+                                 "kernels on the launching stream); peak = hb_dfma_peak measured in this process "
+                                 "(MEASURED_PEAKS.json has no FP64 entry). traffic = bytes this run moved through HBM for that "
+                                 "kernel, counted from the run: 512 B per accepted step record + 108 B per trajectory "
+                                 "(ncu dram bytes of the same kernel: profiles/r02_*)"},
             "e2e": {"value": e2e_value, "unit": "RK steps/s", "h2d_bytes_per_step": int(n * 48),
                     "d2h_bytes_per_step": int(n * (48 + 16) + 72 * k_e2e), "same_hits_as_resident_run": e2e_ok,
-                    "api": "synodic.TubeSectionStream.run (pinned host batches in, pinned host results out)",
+                    "api": "synodic.TubeSectionStream.run per tube (pinned host batches in, pinned host results out, hits "
+                           "put in the reference's order (trajectory, seq) inside the timed region)",
                     "crossings_per_s": total_hits * args.steps / e2e_t},
-            "gpu_launches": world * args.steps * ((6 if args.arith == "parity" else 5) if args.steps_capacity > 0
-                                          else (2 if args.arith == "parity" else 1)),
+            "gpu_launches": world * args.steps * 2 * launches_per_tube,
             "clocks": clocks, "wall_s_timed_region": wall, "extra": extra,
         }
         if not args.no_cpu_baseline and world == 1:
             import oracle_lib as O
             nthr = O.lib().ho_max_threads()
-            v, ns, dt = cpu_port_throughput(ics, mu, nthr)
-            line["cpu_baseline"] = {"value": v, "unit": "RK steps/s", "cores": nthr, "kind": "port",
-                                    "sample": f"{ns} trajectories of the same batch (tube propagation + dense grid + "
-                                              f"section detection per trajectory), {dt:.1f} s"}
+            v, ns, dt = cpu_port_throughput(job["ics"], mu, nthr)
+            port = {"value": v, "unit": "RK steps/s", "cores": nthr, "kind": "port",
+                    "sample": f"{ns} trajectories of the same batch (tube propagation + dense grid + section detection per "
+                              f"trajectory), {dt:.1f} s"}
+            line["cpu_baseline"] = port
+            if reference_available():
+                try:
+                    arm = ReferenceArm()
+                    pick = lambda k: {key: job["ics"][key][:: max(1, len(job["ics"][key]) // k)][:k] for key in TUBES}
+                    arm.step(pick(1), mu)                       # Numba compiles here
+                    sample = pick(24)
+                    h, dt = arm.step(sample, mu)
+                    line["cpu_baseline"] = {
+                        "value": oracle_step_count(sample, mu) / dt, "unit": "RK steps/s", "cores": 1, "kind": "reference",
+                        "crossings_per_s": h / dt,
+                        "sample": f"48 trajectories of the same batch (24 per tube, strided): the reference's own "
+                                  f"_propagate_dynsys per initial condition + _SynodicDetectionBackend.run from oracle/_ref, "
+                                  f"{dt:.1f} s on 1 core (it has no parallel driver for this loop)"}
+                    line["cpu_baseline_port"] = port
+                except Exception as exc:                        # the reference failed to import / run: keep the port
+                    line["cpu_baseline_note"] = f"reference arm failed ({type(exc).__name__}: {exc}); port reported"
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

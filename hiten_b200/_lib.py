@@ -11,6 +11,7 @@ from . import _build
 HB_OK = 0
 HB_RK4, HB_RK6, HB_RK8, HB_RK45, HB_DOP853 = 4, 6, 8, 45, 853
 HB_ARITH_PARITY, HB_ARITH_FAST = 0, 1
+HB_RECORDS_ALL, HB_RECORDS_NEAR_SECTION = 0, 1
 HB_TRAJ_OK, HB_TRAJ_HIT, HB_TRAJ_MAXSTEPS, HB_TRAJ_NONFINITE, HB_TRAJ_RECORD_OVERFLOW = 0, 1, 2, 3, 4
 
 ERRORS = {-1: "HB_ERR_BADARG", -2: "HB_ERR_UNSUPPORTED", -3: "HB_ERR_NODEVICE"}
@@ -94,7 +95,7 @@ SIGNATURES = {
                                    C.c_int32, vp, C.c_int64, vp, vp, vp, vp, vp, vp, vp]),
     "hb_section2_scratch_bytes": (C.c_int64, [C.c_int64, C.c_int32]),
     "hb_cr3bp_section2": (C.c_int, [C.POINTER(HbCr3bp), C.POINTER(HbInteg), C.POINTER(HbSection), C.c_int64, vp, vp,
-                                    C.c_int32, vp, C.c_int64, vp, vp, vp, vp, vp, vp, C.c_int64, vp, vp, vp]),
+                                    C.c_int32, vp, C.c_int64, vp, vp, vp, vp, vp, vp, C.c_int64, vp, vp, vp, C.c_int32]),
     "hb_section3_scratch_bytes": (C.c_int64, [C.c_int64, C.c_int32]),
     "hb_cr3bp_section3": (C.c_int, [C.POINTER(HbCr3bp), C.POINTER(HbInteg), C.POINTER(HbSection), C.c_int64, vp, vp,
                                     C.c_int32, vp, C.c_int64, vp, vp, vp, vp, vp, vp, C.c_int64, vp, vp, vp]),

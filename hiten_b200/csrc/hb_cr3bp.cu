@@ -19,7 +19,36 @@
 namespace {
 using namespace hbc;
 
-enum { MODE_FINAL = 0, MODE_DENSE = 1, MODE_EVENT = 2, MODE_RECORD = 3 };
+enum { MODE_FINAL = 0, MODE_DENSE = 1, MODE_EVENT = 2, MODE_RECORD = 3, MODE_RECORD_NEAR = 4 };
+constexpr bool is_record(int mode) { return mode == MODE_RECORD || mode == MODE_RECORD_NEAR; }
+
+// One accepted step's record in the thread's own (padded) shared-memory row, then ONE 512-byte bulk store.
+HB_DEV void assemble_record(double *rec_row, double t, double t_new, const double (&y)[6], const double (&yh)[6],
+                            const double (&k)[13][6], int step, bool last)
+{
+    double2 *q = (double2 *)rec_row;
+    q[0] = make_double2(t, t_new);
+#pragma unroll
+    for (int d = 0; d < 6; d += 2) {
+        q[1 + d / 2] = make_double2(y[d], y[d + 1]);
+        q[4 + d / 2] = make_double2(yh[d], yh[d + 1]);
+    }
+#pragma unroll
+    for (int j = 5; j < 13; ++j)
+#pragma unroll
+        for (int d = 0; d < 6; d += 2) q[7 + 3 * (j - 5) + d / 2] = make_double2(k[j][d], k[j][d + 1]);
+    *(int2 *)(rec_row + HB_REC_META) = make_int2(step, last ? HB_REC_LAST : 0);
+    rec_row[HB_REC_META + 1] = 0.0;
+}
+HB_DEV void store_record(const double *rec_row, double *dst)
+{
+#ifndef HB_REC_NOCOPY
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
+                 "r"((unsigned)__cvta_generic_to_shared(rec_row)), "r"(HB_REC_DOUBLES * 8) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+#endif
+}
 
 // ---------------------------------------------------------------------------------------------
 // The persistent-thread kernel.
@@ -33,11 +62,15 @@ __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) k_dop853_6(const PropP
     // copy engine as ONE 512-byte bulk store.  Sixteen per-lane 32-byte vector stores instead cost the LSU one tag
     // lookup per lane per store and capped the kernel at ~1.6 TB/s of record writes (measured).
     extern __shared__ __align__(128) unsigned char rec_smem[];
-    double *rec_row = (double *)(rec_smem + (MODE == MODE_RECORD ? threadIdx.x * HB_REC_ROW_BYTES : 0));
+    double *rec_row = (double *)(rec_smem + (is_record(MODE) ? threadIdx.x * HB_REC_ROW_BYTES : 0));
     double t = 0.0, h = 0.0, err_prev = -1.0, tf = 0.0, g_prev = 0.0;
     long long idx = -1;
     long long attempts = 0;
     int nacc = 0, nrej = 0, cursor = 0;
+    // MODE_RECORD_NEAR: records written so far; the row holds the previous step's record, not written yet (pending);
+    // that step could come near the section plane (prev_near)
+    int nrec = 0;
+    bool pending = false, prev_near = false;
     bool have = false, exhausted = false;
     for (;;) {
         if (!have && !exhausted) {
@@ -51,6 +84,7 @@ __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) k_dop853_6(const PropP
                 h = p.h0 ? p.h0[idx] : initial_step<AR>(y, k[0], p);
                 err_prev = -1.0;
                 nacc = 0; nrej = 0; cursor = 0; attempts = 0;
+                nrec = 0; pending = false; prev_near = false;
                 if (MODE == MODE_EVENT) g_prev = AR::sub(pick6(y, p.ev_idx), p.ev_off);
                 have = true;
                 if (!((t - tf) < 0.0)) {
@@ -66,6 +100,7 @@ __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) k_dop853_6(const PropP
                     }
                     if (MODE == MODE_EVENT) p.t_hit[idx] = t;
                     p.nacc[idx] = 0; p.nrej[idx] = 0; p.status[idx] = HB_TRAJ_OK;
+                    if (MODE == MODE_RECORD_NEAR) p.nrec[idx] = 0;
                     have = false;
                 }
             } else {
@@ -154,27 +189,48 @@ __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) k_dop853_6(const PropP
                     double *r = p.rec + ((long long)idx * p.rec_cap + (nacc - 1)) * HB_REC_DOUBLES;
                     // the previous record of this thread must have left the row (a whole step ago: no wait in practice)
                     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                    double2 *q = (double2 *)rec_row;
-                    q[0] = make_double2(t, t_new);
-#pragma unroll
-                    for (int d = 0; d < 6; d += 2) {
-                        q[1 + d / 2] = make_double2(y[d], y[d + 1]);
-                        q[4 + d / 2] = make_double2(yh[d], yh[d + 1]);
+                    assemble_record(rec_row, t, t_new, y, yh, k, nacc - 1, last);
+                    store_record(rec_row, r);
+                }
+            } else if (MODE == MODE_RECORD_NEAR) {
+                // Sparse records: only the steps whose interpolant can come near the section plane (screened in fast
+                // arithmetic with a widened margin, dop853_step_near_plane) and their two neighbours -- the scan needs
+                // the sample before and after a noted segment -- are written.  The row always holds the last accepted
+                // step, so the step BEFORE a near one can still be written when the near one shows up.
+                const double hseg = AR::sub(t_new, t);
+                bool near = true;
+                if (hseg != 0.0 && fabs(hseg) * p.inv_grid_dt >= 2.0) {      // shorter steps may own no grid sample: keep
+                    const Cr3bpRhs<ArFast, NEG> rf{p};
+                    const double off = p.sink.sec.offset, tol = p.sink.sec.tol_on_surface;
+#ifdef HB_NEAR_ONLY_C0
+                    near = dop853_step_near_plane<0>(y, yh, hseg, k, rf, off, tol);
+#else
+                    switch (p.sink.sec.idx) {
+                    case 0: near = dop853_step_near_plane<0>(y, yh, hseg, k, rf, off, tol); break;
+                    case 1: near = dop853_step_near_plane<1>(y, yh, hseg, k, rf, off, tol); break;
+                    case 2: near = dop853_step_near_plane<2>(y, yh, hseg, k, rf, off, tol); break;
+                    case 3: near = dop853_step_near_plane<3>(y, yh, hseg, k, rf, off, tol); break;
+                    case 4: near = dop853_step_near_plane<4>(y, yh, hseg, k, rf, off, tol); break;
+                    default: near = dop853_step_near_plane<5>(y, yh, hseg, k, rf, off, tol); break;
                     }
-#pragma unroll
-                    for (int j = 5; j < 13; ++j)
-#pragma unroll
-                        for (int d = 0; d < 6; d += 2) q[7 + 3 * (j - 5) + d / 2] = make_double2(k[j][d], k[j][d + 1]);
-                    q[31] = make_double2(0.0, 0.0);
-#ifndef HB_REC_NOCOPY
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(r),
-                                 "r"((unsigned)__cvta_generic_to_shared(rec_row)), "r"(HB_REC_DOUBLES * 8) : "memory");
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 #endif
                 }
+                if (near && pending) {                        // the step before this one: write it first
+                    if (nrec < p.rec_cap) store_record(rec_row, p.rec + ((long long)idx * p.rec_cap + nrec) * HB_REC_DOUBLES);
+                    ++nrec;
+                }
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the row is free again
+                assemble_record(rec_row, t, t_new, y, yh, k, nacc - 1, last);
+                if (near || prev_near) {
+                    if (nrec < p.rec_cap) store_record(rec_row, p.rec + ((long long)idx * p.rec_cap + nrec) * HB_REC_DOUBLES);
+                    ++nrec;
+                    pending = false;
+                } else {
+                    pending = true;
+                }
+                prev_near = near;
             }
-            if (MODE == MODE_RECORD || MODE == MODE_FINAL) {   // the dense interpolant at tf on the last segment
+            if (is_record(MODE) || MODE == MODE_FINAL) {   // the dense interpolant at tf on the last segment
                 if (last) {
                     const double hseg = AR::sub(t_new, t);
                     double yo[6];
@@ -195,7 +251,8 @@ __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) k_dop853_6(const PropP
                     }
 #pragma unroll
                     for (int d = 0; d < 6; ++d) p.yf[(long long)d * p.n + idx] = yo[d];
-                    fin = (MODE == MODE_RECORD && nacc > p.rec_cap) ? HB_TRAJ_RECORD_OVERFLOW : HB_TRAJ_OK;
+                    fin = ((MODE == MODE_RECORD && nacc > p.rec_cap) || (MODE == MODE_RECORD_NEAR && nrec > p.rec_cap))
+                              ? HB_TRAJ_RECORD_OVERFLOW : HB_TRAJ_OK;
                 }
             }
             // advance
@@ -222,10 +279,11 @@ __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) k_dop853_6(const PropP
         }
         if (fin >= 0) {
             p.nacc[idx] = nacc; p.nrej[idx] = nrej; p.status[idx] = fin;
+            if (MODE == MODE_RECORD_NEAR) p.nrec[idx] = nrec;
             have = false;
         }
     }
-    if (MODE == MODE_RECORD) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (is_record(MODE)) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -234,7 +292,7 @@ __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) k_dop853_6(const PropP
 template <class AR, int MODE, int NEG>
 int launch_one(const PropParams &p, unsigned grid, cudaStream_t st)
 {
-    constexpr int smem = (MODE == MODE_RECORD) ? HB_BLOCK * HB_REC_ROW_BYTES : 0;
+    constexpr int smem = is_record(MODE) ? HB_BLOCK * HB_REC_ROW_BYTES : 0;
     // the opt-in is per device (and cheap): set on every launch, so a second device in the same process gets it too
     if (smem > 48 * 1024)
         HB_CUDA_TRY(cudaFuncSetAttribute(k_dop853_6<AR, MODE, NEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -354,7 +412,8 @@ int hb_cr3bp_event(const hb_cr3bp *sys, const hb_integ *integ, const hb_event *e
 // Kernel A of the two-kernel section path (hb_section_scan.cu): propagate and record every step's interpolant.
 int hb_cr3bp_record_launch(const hb_cr3bp *sys, const hb_integ *integ, int32_t section_idx, int64_t n,
                            const double *y0_soa, double t0, double tf, double *rec, int32_t rec_cap, double *yf_soa,
-                           int32_t *n_acc, int32_t *n_rej, int32_t *status, void *workspace, cudaStream_t st)
+                           int32_t *n_acc, int32_t *n_rej, int32_t *status, void *workspace, cudaStream_t st,
+                           const hb_section *near_section, double inv_grid_dt, int32_t *n_rec)
 {
     PropParams p{};
     int rc = fill_params(sys, integ, p);
@@ -364,6 +423,12 @@ int hb_cr3bp_record_launch(const hb_cr3bp *sys, const hb_integ *integ, int32_t s
     p.yf = yf_soa; p.nacc = n_acc; p.nrej = n_rej; p.status = status;
     p.rec = rec; p.rec_cap = rec_cap; p.sink.sec.idx = section_idx;
     p.ws = (HbWorkspace *)workspace;
+    if (near_section) {                                  // sparse records: only steps near this section plane
+        p.sink.sec = *near_section;
+        p.inv_grid_dt = inv_grid_dt;
+        p.nrec = n_rec;
+        return launch<MODE_RECORD_NEAR>(p, integ->arith, st);
+    }
     return launch<MODE_RECORD>(p, integ->arith, st);
 }
 

@@ -41,8 +41,9 @@ struct PropParams {
     double tsign;          // sign applied to grid times for the detector (times = forward * t_eval)
     double inv_grid_dt;    // (m-1)/(t_eval[m-1]-t_eval[0]): first guess when locating grid samples
     const double *h0;      // first step sizes from k_first_steps (null: computed inline when a trajectory starts)
-    double *rec;           // MODE_RECORD: per-step stage records [n][rec_cap][HB_REC_DOUBLES]
+    double *rec;           // MODE_RECORD / MODE_RECORD_NEAR: per-step stage records [n][rec_cap][HB_REC_DOUBLES]
     int rec_cap;
+    int *nrec;             // MODE_RECORD_NEAR: records written per trajectory (only steps near the section plane + neighbours)
 };
 
 // One accepted step as stored by MODE_RECORD (hb_cr3bp.cu) and consumed by the scan kernels (hb_section_scan.cu):
@@ -56,7 +57,9 @@ struct PropParams {
 #define HB_REC_YOLD 2
 #define HB_REC_YNEW 8
 #define HB_REC_K5 14      // k[5..11] (7 x 6)
-#define HB_REC_K12 56     // k[12] = f(y_new); [62], [63] unused
+#define HB_REC_K12 56     // k[12] = f(y_new)
+#define HB_REC_META 62    // sparse records: int32 step number (0-based), int32 flags (HB_REC_LAST); [63] unused
+#define HB_REC_LAST 1     // the trajectory's last accepted step (owns every grid sample that is left)
 #define HB_REC_ROW_BYTES (HB_REC_DOUBLES * 8 + 16)   // shared-memory staging row, padded: conflict-free 16 B accesses
 
 HB_DEV void hb_st4(double *p, double a, double b, double c, double d)

@@ -265,6 +265,59 @@ HB_DEV void dense_component(const double (&y_old)[6], const double (&y_new)[6], 
     for (int i = 0; i < 4; ++i) f[3 + i] = AR::mul(h, da[i]);
 }
 
+template <int I, int R>
+HB_DEV void d_acc1(double &acc, const double (&kc)[16])
+{
+    if constexpr (R < 16) {
+        if constexpr (HB_DOP853_D[I][R] != 0.0) {
+            constexpr double c = HB_DOP853_D[I][R];
+            acc = fma(c, kc[R], acc);
+        }
+        d_acc1<I, R + 1>(acc, kc);
+    }
+}
+
+// Screening for the sparse step records of hb_cr3bp_section2 (records = "near"): can the dense interpolant of this
+// accepted step come anywhere near the section plane?  Evaluates component C of the interpolant in FAST arithmetic
+// (FMA-contracted, approximate reciprocal square roots: |difference to the separately rounded values| < 1e-12 for O(1)
+// states) and applies the quiet-step bound of the scan kernel -- |p(x) - (y0 + x F0)| <= sum_{i>=1}|F_i| / 4 on [0, 1] --
+// with the margin widened by 1e-8 (1 + |y_C| + |offset|), four orders above that difference.  Returns false only when
+// every point of the interpolant on [0, 1] stays on one side of the plane, farther from it than the on-surface
+// tolerance: such a step has no sample on or across the section and its record is not needed by the scan.
+// RHSF: the vector field in ArFast arithmetic.
+template <int C, class RHSF>
+HB_DEV bool dop853_step_near_plane(const double (&y_old)[6], const double (&y_new)[6], double h,
+                                   const double (&k)[13][6], const RHSF &rhs, double offset, double tol)
+{
+    double kx[3][6];
+    ext_stage<ArFast, RHSF, 13>(y_old, h, k, kx, rhs);
+    ext_stage<ArFast, RHSF, 14>(y_old, h, k, kx, rhs);
+    ext_stage<ArFast, RHSF, 15>(y_old, h, k, kx, rhs);
+    double S = 0.0;
+    {
+        // rows 3..6 of F, component C only: h * sum_R D[i][R] k_R[C]
+        double kc[16];
+#pragma unroll
+        for (int R = 0; R < 13; ++R) kc[R] = k[R][C];
+#pragma unroll
+        for (int R = 13; R < 16; ++R) kc[R] = kx[R - 13][C];
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        d_acc1<0, 0>(a0, kc);
+        d_acc1<1, 0>(a1, kc);
+        d_acc1<2, 0>(a2, kc);
+        d_acc1<3, 0>(a3, kc);
+        S = fabs(h * a0) + fabs(h * a1) + fabs(h * a2) + fabs(h * a3);
+    }
+    const double dy = y_new[C] - y_old[C];
+    const double f1 = fma(h, k[0][C], -dy);
+    const double f2 = fma(-h, k[12][C] + k[0][C], 2.0 * dy);
+    S += fabs(f1) + fabs(f2);
+    const double g_old = y_old[C] - offset, g_new = y_new[C] - offset;
+    const double margin = 0.25 * S + tol + 1.0e-8 * (1.0 + fabs(y_old[C]) + fabs(dy) + fabs(offset));
+    const bool same = (g_old > 0.0 && g_new > 0.0) || (g_old < 0.0 && g_new < 0.0);
+    return !(same && fmin(fabs(g_old), fabs(g_new)) > margin);
+}
+
 // _dop853_eval_dense (rk.py:1989-2003): alternating x / (1-x) Horner form.
 template <class AR>
 HB_DEV void dense_eval(const double (&y_old)[6], const double (&F)[7][6], double x, double (&out)[6])

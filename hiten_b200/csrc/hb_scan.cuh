@@ -14,12 +14,17 @@ constexpr int HB_CAND_CAP = 32;       // candidate hits per trajectory (before d
 constexpr int HB_CAND_DOUBLES = 8;    // key, t, state[6]
 constexpr int HB_DESC_DOUBLES = 8;    // traj, cs, record of cs-1, record of cs, g(cs-1), g(cs), g(cs-2), pad
 
+// per-trajectory part of the hb_cr3bp_section2 scratch besides the step records, in doubles: candidate and segment
+// lists, four counters (candidates, segments, records, pad: 2 doubles), the compact segment index (HB_CAND_CAP ints)
+constexpr long long HB_S2_FIXED_DOUBLES = HB_CAND_CAP * (HB_CAND_DOUBLES + HB_DESC_DOUBLES) + HB_CAND_CAP / 2 + 2;
+
 struct ScanParams {
     PropParams prop;        // mu, 1-mu, sign mask (vector field of the extra stages)
     long long n;
     const double *rec;      // step records, HB_REC_DOUBLES doubles each: [n][rec_cap] (section2) or a pool (section3)
     int rec_cap;            // records per trajectory in the scratch (section2); INT_MAX: no per-trajectory limit
     const int *nacc;
+    const int *nrec;        // sparse records (hb_cr3bp_section2, records = near): records per trajectory; else NULL
     int *status;
     const double *t_eval;
     int m;

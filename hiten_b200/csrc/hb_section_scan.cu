@@ -28,7 +28,8 @@
 extern "C" int hb_cr3bp_record_launch(const hb_cr3bp *sys, const hb_integ *integ, int32_t section_idx, int64_t n,
                                       const double *y0_soa, double t0, double tf, double *rec, int32_t rec_cap,
                                       double *yf_soa, int32_t *n_acc, int32_t *n_rej, int32_t *status, void *workspace,
-                                      cudaStream_t st);
+                                      cudaStream_t st, const hb_section *near_section, double inv_grid_dt,
+                                      int32_t *n_rec);
 
 namespace {
 using namespace hbc;
@@ -68,15 +69,26 @@ using namespace hbscan;
 #ifndef HB_SCAN_MINBLOCKS
 #define HB_SCAN_MINBLOCKS 13
 #endif
-constexpr int HB_SCAN_COPY = (HB_REC_K12 + 6) * 8;
-constexpr int HB_SCAN_ROW = HB_SCAN_COPY;
-constexpr int HB_SCAN_SMEM = HB_SCAN_WARPS * (32 * HB_SCAN_ROW + 16);
-static_assert(HB_SCAN_COPY % 16 == 0 && (HB_SCAN_ROW / 16) % 2 == 1, "row: 16-byte multiple, odd number of 16-byte units");
+// Sparse records carry their step number and flags in [62]: the whole 512-byte record is copied, into 528-byte rows (33
+// x 16 B); there the scan is a small part of the step, so the lower occupancy does not matter.
+template <bool SPARSE> struct ScanGeom {
+    static constexpr int COPY = SPARSE ? HB_REC_DOUBLES * 8 : (HB_REC_K12 + 6) * 8;
+    static constexpr int ROW = SPARSE ? HB_REC_DOUBLES * 8 + 16 : COPY;
+    static constexpr int SMEM = HB_SCAN_WARPS * (32 * ROW + 16);
+    static_assert(COPY % 16 == 0 && (ROW / 16) % 2 == 1, "row: 16-byte multiple, odd number of 16-byte units");
+};
 
-template <class AR, int C>      // C = section component (compile time: the unused parts of the extra stages fall away)
+// SPARSE: the scratch holds only the records of steps that can come near the section plane and their neighbours
+// (MODE_RECORD_NEAR of hb_cr3bp.cu), p.nrec of them per trajectory, each tagged with its step number: lanes whose step
+// does not follow the previous lane's step start an "island".  Every step that was left out is provably quiet and at
+// least two grid spacings long (it owns samples, all of them away from the plane and on one side), so an island's first
+// step -- itself such a quiet step, written only because its successor is near the plane, or the trajectory's first
+// step -- has no segment to test against its predecessor; it finds its first sample with its own grid lookup.
+template <class AR, int C, bool SPARSE>  // C = section component (compile time: the unused parts of the extra stages fall away)
 __global__ void __launch_bounds__(32 * HB_SCAN_WARPS, HB_SCAN_MINBLOCKS) k_step_scan(const ScanParams p)
 {
     constexpr unsigned FULL = 0xffffffffu;
+    constexpr int HB_SCAN_COPY = ScanGeom<SPARSE>::COPY, HB_SCAN_ROW = ScanGeom<SPARSE>::ROW;
     extern __shared__ __align__(128) unsigned char scan_smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const long long traj = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -93,12 +105,14 @@ __global__ void __launch_bounds__(32 * HB_SCAN_WARPS, HB_SCAN_MINBLOCKS) k_step_
     // Pipelined: the first chunk is requested BEFORE the trajectory's step count is known (the count is a DRAM round
     // trip of its own): until then every row of the scratch is fair game -- rows past the count hold stale bytes that
     // no lane looks at.
-    int nacc = HB_SCAN_PIPELINED ? p.rec_cap : min(p.nacc[traj], p.rec_cap);
+    const int *count = SPARSE ? p.nrec : p.nacc;        // records of this trajectory in the scratch
+    int nacc = HB_SCAN_PIPELINED ? p.rec_cap : min(count[traj], p.rec_cap);
     const double off = p.sink.sec.offset, tol_s = p.sink.sec.tol_on_surface;
     const int sdir = p.sink.sec.direction;
     int ndesc = 0;                         // segments noted so far (warp-uniform)
     int carry_c = 0;                       // first grid sample not owned yet
-    int carry_step = 0;                    // step that owns sample carry_c - 1
+    int carry_step = 0;                    // record that owns sample carry_c - 1
+    int carry_no = -1;                     // SPARSE: step number of the last record of the previous chunk
     double carry1 = 0.0, carry2 = 0.0;     // event function at samples carry_c - 1, carry_c - 2
     const double te0 = p.t_eval[0];
     double carry_t = te0;                  // t_eval[carry_c]
@@ -124,7 +138,7 @@ __global__ void __launch_bounds__(32 * HB_SCAN_WARPS, HB_SCAN_MINBLOCKS) k_step_
     };
 #if HB_SCAN_PIPELINED
     issue_chunk(0);
-    nacc = min(p.nacc[traj], p.rec_cap);
+    nacc = min(count[traj], p.rec_cap);
     if (nacc <= 0) mbar_wait(mbar, phase);                    // nothing to scan: let the requested rows land before exit
 #endif
     for (int base = 0; base < nacc; base += 32) {
@@ -135,6 +149,8 @@ __global__ void __launch_bounds__(32 * HB_SCAN_WARPS, HB_SCAN_MINBLOCKS) k_step_
         for (int i = 0; i < 11; ++i) hdr[i] = 0.0;
         int cend = p.m;
         double t_c = 0.0, t_cm1 = 0.0, t_cm2 = 0.0;   // t_eval[cend], t_eval[cend - 1], t_eval[cend - 2]
+        int step_no = s, own_c0 = 0;                  // SPARSE: the record's step number; first sample at or after t_old
+        double own_t_c0 = te0;
 #if !HB_SCAN_PIPELINED
         issue_chunk(base);
 #endif
@@ -164,8 +180,18 @@ __global__ void __launch_bounds__(32 * HB_SCAN_WARPS, HB_SCAN_MINBLOCKS) k_step_
 #pragma unroll
                 for (int i = 0; i < 7; ++i) hdr[4 + i] = f[i];
             }
-            if (s != nacc - 1) cend = first_at_or_after3(p, te0, v[1], t_c, t_cm1, t_cm2);
+            bool is_last = s == nacc - 1;
+            if (SPARSE) {
+                const int2 meta = *(const int2 *)(r + HB_REC_META);
+                step_no = meta.x;
+                is_last = (meta.y & HB_REC_LAST) != 0;
+            }
+            if (!is_last) cend = first_at_or_after3(p, te0, v[1], t_c, t_cm1, t_cm2);
             else { t_cm1 = p.t_eval[p.m - 1]; t_cm2 = p.t_eval[max(p.m - 2, 0)]; }
+            if (SPARSE && step_no > 0) {              // (only an island's first lane uses it; the lookup is cheap)
+                double d1, d2;
+                own_c0 = first_at_or_after3(p, te0, v[0], own_t_c0, d1, d2);
+            }
         }
 #if HB_SCAN_PIPELINED
         // the rows are not read again in this round (the scan below runs on the headers in registers): the next
@@ -176,6 +202,13 @@ __global__ void __launch_bounds__(32 * HB_SCAN_WARPS, HB_SCAN_MINBLOCKS) k_step_
         int c0 = __shfl_up_sync(FULL, cend, 1);               // t_new of a step is t_old of the next, bit for bit
         double t_c0 = __shfl_up_sync(FULL, t_c, 1);                       // t_eval[c0]: the previous lane's t_eval[cend]
         if (lane == 0) { c0 = carry_c; t_c0 = carry_t; }
+        bool adjacent = true;                                 // this record's step follows the previous record's step
+        if (SPARSE) {
+            int prev_no = __shfl_up_sync(FULL, step_no, 1);
+            if (lane == 0) prev_no = carry_no;
+            adjacent = step_no == prev_no + 1;
+            if (!adjacent) { c0 = own_c0; t_c0 = own_t_c0; }  // island start (or the trajectory's first step: c0 = 0)
+        }
         const int nown = (have_rec && c0 < cend) ? cend - c0 : 0;
         const bool owns = nown > 0;
         // event function at the first (g_first), last (A) and second-to-last (B) owned sample
@@ -202,7 +235,7 @@ __global__ void __launch_bounds__(32 * HB_SCAN_WARPS, HB_SCAN_MINBLOCKS) k_step_
         const int s_prev = (q >= 0) ? base + q : carry_step;
         bool scan = false;
         {                                                     // the segment that ends at this step's first sample
-            const bool flag = owns && c0 > 0 && segment_may_hit(sdir, g_prev, g_first, tol_s);
+            const bool flag = owns && c0 > 0 && adjacent && segment_may_hit(sdir, g_prev, g_first, tol_s);
             const unsigned fm = __ballot_sync(FULL, flag);
             if (flag)
                 store_segment(p, traj, ndesc + __popc(fm & ((1u << lane) - 1u)), c0, traj * p.rec_cap + s_prev,
@@ -271,6 +304,7 @@ __global__ void __launch_bounds__(32 * HB_SCAN_WARPS, HB_SCAN_MINBLOCKS) k_step_
         }
         carry_c = __shfl_sync(FULL, cend, 31);
         carry_t = shfl_d(t_c, 31);
+        if (SPARSE) carry_no = __shfl_sync(FULL, step_no, 31);
         __syncwarp();                                         // every lane is done with its row before the next copy
     }
     if (lane == 0) p.desc_count[traj] = ndesc;
@@ -359,7 +393,8 @@ __global__ void __launch_bounds__(256) k_order_dedup(const ScanParams p)
     const long long traj = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (traj >= p.n) return;
     int k = p.cand_count[traj];
-    if (p.nacc[traj] > p.rec_cap || k > HB_CAND_CAP || p.desc_count[traj] > HB_CAND_CAP) {
+    const int n_records = p.nrec ? p.nrec[traj] : p.nacc[traj];
+    if (n_records > p.rec_cap || k > HB_CAND_CAP || p.desc_count[traj] > HB_CAND_CAP) {
         // incomplete: report no hits for this trajectory; the caller reruns it with hb_cr3bp_section
         p.status[traj] = HB_TRAJ_RECORD_OVERFLOW;
         atomicAdd(&p.sink.ws->rec_overflow, 1ULL);
@@ -520,8 +555,13 @@ template <class AR, int C>
 int launch_scan_c(const ScanParams &p, unsigned grid, cudaStream_t st)
 {
     // per-device attribute: set on every launch (cheap), so any device of the process gets the opt-in
-    HB_CUDA_TRY(cudaFuncSetAttribute(k_step_scan<AR, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, HB_SCAN_SMEM));
-    k_step_scan<AR, C><<<grid, 32 * HB_SCAN_WARPS, HB_SCAN_SMEM, st>>>(p);
+    if (p.nrec) {
+        HB_CUDA_TRY(cudaFuncSetAttribute(k_step_scan<AR, C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ScanGeom<true>::SMEM));
+        k_step_scan<AR, C, true><<<grid, 32 * HB_SCAN_WARPS, ScanGeom<true>::SMEM, st>>>(p);
+        return HB_OK;
+    }
+    HB_CUDA_TRY(cudaFuncSetAttribute(k_step_scan<AR, C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ScanGeom<false>::SMEM));
+    k_step_scan<AR, C, false><<<grid, 32 * HB_SCAN_WARPS, ScanGeom<false>::SMEM, st>>>(p);
     return HB_OK;
 }
 template <class AR>
@@ -557,17 +597,17 @@ extern "C" int64_t hb_section2_scratch_bytes(int64_t n, int32_t steps_capacity)
 {
     if (n < 0 || steps_capacity < 1) return -1;
     steps_capacity = (steps_capacity + 31) / 32 * 32;
-    return n * ((int64_t)steps_capacity * HB_REC_DOUBLES + HB_CAND_CAP * (HB_CAND_DOUBLES + HB_DESC_DOUBLES) + HB_CAND_CAP / 2 + 1) *
-               (int64_t)sizeof(double) + 256;
+    return n * ((int64_t)steps_capacity * HB_REC_DOUBLES + HB_S2_FIXED_DOUBLES) * (int64_t)sizeof(double) + 256;
 }
 
 extern "C" int hb_cr3bp_section2(const hb_cr3bp *sys, const hb_integ *integ, const hb_section *sec, int64_t n,
                                  const double *y0_soa, const double *t_eval, int32_t m, hb_hit *hits,
                                  int64_t hit_capacity, int32_t *hits_per_traj, double *yf_soa, int32_t *n_acc,
                                  int32_t *n_rej, int32_t *status, void *scratch, int64_t scratch_bytes, void *workspace,
-                                 void *stream, void *const *stage_events)
+                                 void *stream, void *const *stage_events, int32_t records)
 {
     if (!sys || !integ || !sec) return HB_ERR_BADARG;
+    if (records != HB_RECORDS_ALL && records != HB_RECORDS_NEAR_SECTION) return HB_ERR_BADARG;
     // optional caller-owned CUDA events, recorded on `stream` around the four stages (no library state involved)
     auto mark = [&](int i, cudaStream_t s_) { if (stage_events && stage_events[i]) cudaEventRecord((cudaEvent_t)stage_events[i], s_); };
     if (integ->method != HB_DOP853) return HB_ERR_UNSUPPORTED;
@@ -579,8 +619,7 @@ extern "C" int hb_cr3bp_section2(const hb_cr3bp *sys, const hb_integ *integ, con
         return HB_ERR_BADARG;
     cudaStream_t st = (cudaStream_t)stream;
     if (n == 0) { HB_CUDA_TRY(cudaMemsetAsync(workspace, 0, sizeof(HbWorkspace), st)); return HB_OK; }
-    const long long per_traj_fixed =
-        (HB_CAND_CAP * (HB_CAND_DOUBLES + HB_DESC_DOUBLES) + HB_CAND_CAP / 2 + 1) * (long long)sizeof(double);
+    const long long per_traj_fixed = HB_S2_FIXED_DOUBLES * (long long)sizeof(double);
     long long cap = ((scratch_bytes - 256) / n - per_traj_fixed) / (HB_REC_DOUBLES * (long long)sizeof(double));
     cap -= cap % 32;                                 // keeps every trajectory's records 32-step aligned
     if (cap < 32) return HB_ERR_BADARG;
@@ -588,9 +627,10 @@ extern "C" int hb_cr3bp_section2(const hb_cr3bp *sys, const hb_integ *integ, con
     double *rec = (double *)scratch;
     double *cand = rec + n * (long long)rec_cap * HB_REC_DOUBLES;
     double *desc = cand + n * (long long)HB_CAND_CAP * HB_CAND_DOUBLES;
-    int *cand_count = (int *)(desc + n * (long long)HB_CAND_CAP * HB_DESC_DOUBLES);    // n doubles = 2n ints
+    int *cand_count = (int *)(desc + n * (long long)HB_CAND_CAP * HB_DESC_DOUBLES);    // 2n doubles = 4n ints
     int *desc_count = cand_count + n;
-    int *desc_index = desc_count + n;                 // n * HB_CAND_CAP ints
+    int *rec_count = desc_count + n;                  // sparse records: records per trajectory
+    int *desc_index = rec_count + 2 * n;              // n * HB_CAND_CAP ints
     int *desc_total = desc_index + n * (long long)HB_CAND_CAP;   // first of the 256 trailing bytes
     double ends[2];
     HB_CUDA_TRY(cudaMemcpyAsync(&ends[0], t_eval, sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -599,17 +639,20 @@ extern "C" int hb_cr3bp_section2(const hb_cr3bp *sys, const hb_integ *integ, con
     HB_CUDA_TRY(cudaMemsetAsync(cand_count, 0, sizeof(int) * 2 * (size_t)n, st));
     HB_CUDA_TRY(cudaMemsetAsync(desc_total, 0, 2 * sizeof(int), st));
     mark(0, st);
+    const bool sparse = records == HB_RECORDS_NEAR_SECTION;
+    const double inv_grid_dt = (ends[1] > ends[0]) ? (double)(m - 1) / (ends[1] - ends[0]) : 0.0;
     int rc = hb_cr3bp_record_launch(sys, integ, sec->idx, n, y0_soa, ends[0], ends[1], rec, rec_cap, yf_soa, n_acc, n_rej,
-                                    status, workspace, st);
+                                    status, workspace, st, sparse ? sec : nullptr, inv_grid_dt, sparse ? rec_count : nullptr);
     if (rc != HB_OK) return rc;
     mark(1, st);
     ScanParams p{};
     rc = fill_params(sys, integ, p.prop);
     if (rc != HB_OK) return rc;
     p.n = n; p.rec = rec; p.rec_cap = rec_cap; p.nacc = n_acc; p.status = status;
+    p.nrec = sparse ? rec_count : nullptr;
     p.t_eval = t_eval; p.m = m;
     p.tsign = sys->fwd < 0 ? -1.0 : 1.0;
-    p.inv_grid_dt = (ends[1] > ends[0]) ? (double)(m - 1) / (ends[1] - ends[0]) : 0.0;
+    p.inv_grid_dt = inv_grid_dt;
     p.sink.sec = *sec; p.sink.hits = hits; p.sink.capacity = hit_capacity; p.sink.ws = (HbWorkspace *)workspace;
     p.hits_per_traj = hits_per_traj;
     p.cand_count = cand_count; p.cand = cand; p.desc_count = desc_count; p.desc = desc; p.desc_total = desc_total; p.desc_index = desc_index;
@@ -636,8 +679,7 @@ extern "C" int hb_section2_filter(const hb_cr3bp *sys, const hb_integ *integ, co
     if (integ->method != HB_DOP853) return HB_ERR_UNSUPPORTED;
     if (n == 0) return HB_OK;
     if (!t_eval || !n_acc || !status || !scratch || !out || !keep) return HB_ERR_BADARG;
-    const long long per_traj_fixed =
-        (HB_CAND_CAP * (HB_CAND_DOUBLES + HB_DESC_DOUBLES) + HB_CAND_CAP / 2 + 1) * (long long)sizeof(double);
+    const long long per_traj_fixed = HB_S2_FIXED_DOUBLES * (long long)sizeof(double);
     long long cap = ((scratch_bytes - 256) / n - per_traj_fixed) / (HB_REC_DOUBLES * (long long)sizeof(double));
     cap -= cap % 32;                                 // the same record capacity hb_cr3bp_section2 derived
     if (cap < 32) return HB_ERR_BADARG;

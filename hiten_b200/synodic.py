@@ -98,7 +98,7 @@ def _auto_steps_capacity(n, device, want=160):
 
 
 def tube_section(y0, mu, t_eval, section, *, forward=1, flip=None, integ=None, hit_capacity=None, device=None,
-                 stream=None, ws=None, sort=True, steps_capacity="auto"):
+                 stream=None, ws=None, sort=True, steps_capacity="auto", records="near"):
     """Manifold.compute() + SynodicMap.compute() in one call: propagate a batch over the t_eval grid and detect the
     section hits on the device, without storing the dense tube.  Returns (SectionHits, BatchResult with end states).
 
@@ -116,7 +116,8 @@ def tube_section(y0, mu, t_eval, section, *, forward=1, flip=None, integ=None, h
             steps_capacity = _auto_steps_capacity(n, device) if sort else 0
         if steps_capacity and sort and n > 0:
             run = TubeSectionRunner(n, mu, t_eval, section, forward=forward, flip=flip, integ=integ,
-                                    hit_capacity=hit_capacity, device=device, steps_capacity=int(steps_capacity))
+                                    hit_capacity=hit_capacity, device=device, steps_capacity=int(steps_capacity),
+                                    records=records)
             run.launch(y0d, stream)
             h = run.sorted_hits(stream)
             if host:
@@ -166,7 +167,7 @@ class TubeSectionRunner:
     buffers are created once; launch() enqueues the kernels, hit_count() / sorted_hits() read the result."""
 
     def __init__(self, n, mu, t_eval, section, *, forward=1, flip=None, integ=None, hit_capacity=None, device=None,
-                 steps_capacity=0, scratch=None, filters=None, pool_records=0):
+                 steps_capacity=0, scratch=None, filters=None, pool_records=0, records="near"):
         """Three forms of the same step, same hits bit for bit:
         pool_records > 0 selects hb_cr3bp_section3: step records handed from propagating to scanning warps through
         shared memory inside one kernel; the scratch holds the candidate lists and a pool of `pool_records` step
@@ -175,6 +176,9 @@ class TubeSectionRunner:
         steps per trajectory (512 B per step); both 0: the fused kernel hb_cr3bp_section.  Trajectories that do not fit
         the scratch / pool are rerun with the fused kernel by hit_count() / sorted_hits(), so the result is the same.
         `scratch` lets several runners share one (large) scratch tensor.
+        records (hb_cr3bp_section2 only): "near" (default) -- the propagation kernel records only the steps that can come
+        near the section plane and their neighbours, steps_capacity counts those (a tube needs ~10-30; 64 is plenty);
+        "all" -- every accepted step (what `filters` needs; steps_capacity = accepted steps per trajectory).
         `filters` = (safe_r1, safe_r2, energy_tol) applies Manifold.compute()'s trajectory filters
         (services/manifold.py:412-432) from the step records (hb_section2_filter, pipeline only): sorted_hits() then
         returns the hits of the kept trajectories only -- what SynodicMap sees after manifold.compute()."""
@@ -196,6 +200,9 @@ class TubeSectionRunner:
         self.hits = torch.empty(self.cap * 9, dtype=torch.float64, device=self.device)
         self.steps_capacity = int(steps_capacity)
         self.pool_records = int(pool_records)
+        if records not in ("near", "all"):
+            raise ValueError("records must be 'near' or 'all'")
+        self.records = L.HB_RECORDS_ALL if (records == "all" or filters is not None) else L.HB_RECORDS_NEAR_SECTION
         if self.pool_records > 0 and self.steps_capacity > 0:
             raise ValueError("choose pool_records (hb_cr3bp_section3) or steps_capacity (hb_cr3bp_section2), not both")
         self.stage_events = None        # set_stage_events(): caller-owned CUDA events around the pipeline's stages
@@ -249,7 +256,8 @@ class TubeSectionRunner:
                                             self.te.data_ptr(), self.te.numel(), self.hits.data_ptr(), self.cap,
                                             self.per.data_ptr(), self.yf.data_ptr(), self.nacc.data_ptr(),
                                             self.nrej.data_ptr(), self.status.data_ptr(), self.scratch.data_ptr(),
-                                            self.scratch.numel() * 8, self.ws.data_ptr(), _stream_ptr(stream), sev)
+                                            self.scratch.numel() * 8, self.ws.data_ptr(), _stream_ptr(stream), sev,
+                                            self.records)
             L.check(rc, "hb_cr3bp_section2")
             if self.filters is not None:
                 rc = self.lib.hb_section2_filter(self.sys, self.integ, self.filters, self.n, self.te.data_ptr(),
@@ -307,6 +315,8 @@ class TubeSectionRunner:
         if not getattr(self, "_owns_scratch", False) or n_overflowed * 50 < self.n or self.steps_capacity <= 0:
             return
         need = (int(self.nacc[: self.n].max().item()) + 31) // 32 * 32
+        if self.records == L.HB_RECORDS_NEAR_SECTION:         # only recorded steps count: double until it fits
+            need = min(need, 2 * ((self.steps_capacity + 31) // 32 * 32))
         if need <= self.steps_capacity:
             return                                            # candidate-list overflow, not a step overflow
         nbytes = int(self.lib.hb_section2_scratch_bytes(self.n, need))
@@ -375,7 +385,7 @@ def _seq_within(traj):
 class HostBatchResult:
     """One batch of TubeSectionStream, in pinned host memory (valid until two more batches have been drained)."""
     n_hits: int
-    hits: np.ndarray            # [K] HIT_DTYPE records, unordered ((traj, seq) gives the reference order)
+    hits: np.ndarray            # [K] HIT_DTYPE records in the reference's order (by trajectory, then along it)
     end_states: np.ndarray      # [N, 6]
     n_acc: np.ndarray           # [N]
     n_rej: np.ndarray           # [N]
@@ -390,9 +400,11 @@ class TubeSectionStream:
     come back in pinned host buffers.  The two buffer sets share one step scratch (compute is serial anyway)."""
 
     def __init__(self, n, mu, t_eval, section, *, forward=1, flip=None, integ=None, hit_capacity=None, device=None,
-                 steps_capacity=0, scratch=None, pool_records=8):
+                 steps_capacity=0, scratch=None, pool_records=8, ordered=True):
         """Default: hb_cr3bp_section3 (pool_records step records per trajectory in the scratch); steps_capacity > 0
-        (with pool_records = 0) selects hb_cr3bp_section2."""
+        (with pool_records = 0) selects hb_cr3bp_section2.  ordered=True returns every batch's hits in the reference's
+        order (sorted on the device before the copy to the host)."""
+        self.ordered = bool(ordered)
         _require_cuda()
         if steps_capacity > 0:
             pool_records = 0
@@ -452,7 +464,14 @@ class TubeSectionStream:
             h32[2].copy_(run.status[: self.n], non_blocking=True)
             h32[3].copy_(run.per[: self.n], non_blocking=True)
             km = run._main_hits
-            self.h_hits[slot][: km * 9].copy_(run.hits[: km * 9], non_blocking=True)
+            if self.ordered and km:
+                # the reference's hit order (by trajectory, then along the trajectory), restored on the device: one
+                # 64-bit key sort instead of a host lexsort of the records
+                rec = run.hits[: km * 9].view(km, 9)
+                key = rec[:, 0].view(torch.int64) * 65536 + rec[:, 1].view(torch.int64)
+                self.h_hits[slot][: km * 9].view(km, 9).copy_(rec[torch.argsort(key)], non_blocking=True)
+            else:
+                self.h_hits[slot][: km * 9].copy_(run.hits[: km * 9], non_blocking=True)
             self.s_out.synchronize()
             self.ev_free[slot].record(self.s_out)
         rec = self.h_hits[slot][: km * 9].numpy().view(HIT_DTYPE)
@@ -462,6 +481,8 @@ class TubeSectionStream:
             extra["traj"], extra["seq"] = idx[h.trajectory_indices], _seq_within(h.trajectory_indices)
             extra["t"], extra["state"] = h.times, h.states
             rec = np.concatenate((rec, extra))
+            if self.ordered:
+                rec = rec[np.lexsort((rec["seq"], rec["traj"]))]
             self.h_yf[slot].copy_(run.yf.view(6, self.n).t())
         return HostBatchResult(k, rec, self.h_yf[slot].numpy(), h32[0].numpy(), h32[1].numpy(), h32[2].numpy(),
                                h32[3].numpy())

@@ -61,3 +61,18 @@ def c5_batch(n_total, rank=0, world=1):
         ics = manifold_initial_conditions(t[f"{key}_x_node"], t[f"{key}_man"], disp)[:half]
         out[key] = np.ascontiguousarray(ics[rank::world])
     return out, float(t["mu"])
+
+
+# ---- the round-1 bench workload: BASELINE configs[0]'s tube (EM L1 halo Az = 0.2 S, stable / positive) scaled by
+# displacement, with configs[1]'s section y = 0 / (x, z) / direction -1.  Kept for the large-batch parity tests.
+C1_TF = 0.75 * 2.0 * np.pi
+
+
+def c1_tube_batch(n, rank=0, world=1):
+    """Deterministic batch: 2000 tube nodes x displacements log-spaced in [1e-7, 1e-5], interleaved over ranks."""
+    t = np.load(os.path.join(REPO, "tests", "golden", "tube_nodes_c1.npz"))
+    total = n * world
+    n_disp = (total + 1999) // 2000
+    disp = np.logspace(-7.0, -5.0, n_disp)
+    ics = manifold_initial_conditions(t["x_node"], t["man"], disp)[:total]
+    return np.ascontiguousarray(ics[rank::world][:n]), float(t["mu"])

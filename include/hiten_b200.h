@@ -156,6 +156,8 @@ int hb_cr3bp_section(const hb_cr3bp *sys, const hb_integ *integ, const hb_sectio
  * (512 B per step + 4.1 KB per trajectory).  Trajectories that need more steps, or have more than 32 candidate
  * hits, get status = HB_TRAJ_RECORD_OVERFLOW and NO hits; their number is read with hb_read_record_overflow --
  * rerun those with hb_cr3bp_section.                                                                 */
+#define HB_RECORDS_ALL 0
+#define HB_RECORDS_NEAR_SECTION 1
 int64_t hb_section2_scratch_bytes(int64_t n, int32_t steps_capacity);
 int hb_cr3bp_section2(const hb_cr3bp *sys, const hb_integ *integ, const hb_section *sec, int64_t n,
                       const double *y0_soa, const double *t_eval, int32_t m, hb_hit *hits, int64_t hit_capacity,
@@ -163,7 +165,13 @@ int hb_cr3bp_section2(const hb_cr3bp *sys, const hb_integ *integ, const hb_secti
                       void *scratch, int64_t scratch_bytes, void *workspace, void *stream,
                       void *const *stage_events /* NULL, or 5 caller-owned cudaEvent_t recorded on `stream` before /
                       between / after the stages propagate+record, step scan, candidate emission, order+dedup
-                      (measurement aid of bench.py; entries may be NULL; the library keeps no state) */);
+                      (measurement aid of bench.py; entries may be NULL; the library keeps no state) */,
+                      int32_t records /* HB_RECORDS_ALL: every accepted step is recorded (steps_capacity = accepted steps
+                      per trajectory; what hb_section2_filter needs).  HB_RECORDS_NEAR_SECTION: the propagation kernel
+                      screens every accepted step (event component of its dense interpolant in fast arithmetic, quiet-step
+                      bound with a widened margin) and records only the steps that can come near the section plane plus
+                      their two neighbours -- about a tenth of the steps of a tube; steps_capacity then counts RECORDED
+                      steps per trajectory.  Same hits bit for bit (every step left out is provably free of hits). */);
 
 /* The same step -- same hits, counts and end states, bit for bit -- with the step records handed from the propagating
  * warps to scanning warps THROUGH SHARED MEMORY inside one persistent kernel (hb_section_stream.cu): nothing but

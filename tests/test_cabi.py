@@ -95,7 +95,7 @@ def test_argument_validation_needs_no_gpu():
     assert lib.hb_cm_lift(C.byref(ham), C.byref(o), 4, None, None, None, None) < 0    # null arrays
     sysd, integ, sec = _lib.HbCr3bp(0.0121, 1, -1, -1, 0), hiten_b200.make_integ(), hiten_b200.synodic.make_section("y")
     assert lib.hb_cr3bp_section2(C.byref(sysd), C.byref(integ), C.byref(sec), 8, None, None, 1, None, 0, None, None, None,
-                                 None, None, None, 0, None, None, None) < 0       # m < 2, no workspace
+                                 None, None, None, 0, None, None, None, 0) < 0    # m < 2, no workspace
     assert lib.hb_cr3bp_section3(C.byref(sysd), C.byref(integ), C.byref(sec), 8, None, None, 1, None, 0, None, None, None,
                                  None, None, None, 0, None, None, None) < 0
     # section3 scratch: 4.2 KB of lists per trajectory + 512 B per pooled record, monotone in both arguments

@@ -83,6 +83,29 @@ def test_c5_stored_tube_chain_and_fused_kernel_bit_exact(key):
     assert np.array_equal(res.yf, g[f"{key}_yf"][sel])
 
 
+@pytest.mark.parametrize("key", ["l1", "l2"])
+@pytest.mark.parametrize("records", ["near", "all"])
+def test_c5_section2_without_filters_equals_stored_tube_chain(key, records):
+    """The bench step's form (no trajectory filters; sparse or full step records) on the 200 golden trajectories of each
+    tube against the stored-tube chain: every trajectory's hits, discarded ones included."""
+    import torch
+    import hiten_b200 as hb
+    from hiten_b200 import synodic
+    g = c5()
+    mu, tf, steps, fwd = float(g["mu"]), float(g[f"{key}_tf"]), int(g[f"{key}_steps"]), int(g[f"{key}_forward"])
+    t_eval = np.linspace(0.0, tf, steps)
+    sec = section_of(g, key)
+    run = synodic.TubeSectionRunner(200, mu, t_eval, sec, forward=fwd, flip=(0, 6), steps_capacity=192, records=records)
+    run.launch(torch.from_numpy(np.ascontiguousarray(g[f"{key}_x0W"].T)).cuda())
+    h = run.sorted_hits()
+    tube = hb.cr3bp_dense(g[f"{key}_x0W"], mu, t_eval, forward=fwd, flip=(0, 6), keep_on_device=True)
+    want = synodic.detect(tube.states, fwd * t_eval, sec)
+    assert (run.status == 0).all().item() and len(want.times) >= len(g[f"{key}_hit_time"])
+    assert np.array_equal(h.trajectory_indices, want.trajectory_indices)
+    assert np.array_equal(h.times, want.times) and np.array_equal(h.states, want.states)
+    assert np.array_equal(run.yf.t().cpu().numpy(), g[f"{key}_yf"])
+
+
 def test_c5_connections_bit_exact_vs_reference():
     from hiten_b200 import connections as cn
     g = c5()

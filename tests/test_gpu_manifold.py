@@ -125,13 +125,13 @@ def test_record_filter_bit_exact_vs_reference(steps_capacity):
 def test_record_filter_equals_stored_tube_filter_on_a_bench_slice():
     """4000 trajectories of the bench batch, both arithmetic variants: records -> filter == dense tube -> filter."""
     import torch
-    import bench
+    from hiten_b200 import workloads as W
     import hiten_b200 as hb
     from hiten_b200 import manifold, synodic
     n = 4000
-    ics, mu = bench.build_ics(n)
-    m = max(int(abs(bench.TF) / bench.GRID_DT) + 1, 100)
-    t_eval = np.linspace(0.0, bench.TF, m)
+    ics, mu = W.c1_tube_batch(n)
+    m = max(int(abs(W.C1_TF) / W.GRID_DT) + 1, 100)
+    t_eval = np.linspace(0.0, W.C1_TF, m)
     sec = synodic.make_section("y", 0.0, ("x", "z"), -1)
     y0 = torch.from_numpy(np.ascontiguousarray(ics.T)).cuda()
     for arith in ("parity", "fast"):

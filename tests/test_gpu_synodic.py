@@ -93,8 +93,10 @@ def test_fused_section_equals_two_kernel_chain(name):
 
 @pytest.mark.parametrize("name", ["c1", "c2", "se"])
 @pytest.mark.parametrize("arith", ["parity", "fast"])
-def test_two_kernel_section_equals_fused(name, arith):
-    """hb_cr3bp_section2 (record + scan) == hb_cr3bp_section, bit for bit; parity also == the reference's hits."""
+@pytest.mark.parametrize("records", ["all", "near"])
+def test_two_kernel_section_equals_fused(name, arith, records):
+    """hb_cr3bp_section2 (record + scan; every step recorded, or only the steps near the section plane) ==
+    hb_cr3bp_section, bit for bit; parity also == the reference's hits."""
     import torch
     import hiten_b200 as hb
     from hiten_b200 import synodic
@@ -105,7 +107,8 @@ def test_two_kernel_section_equals_fused(name, arith):
     y0 = torch.from_numpy(np.ascontiguousarray(g["x0W"].T)).cuda()
     integ = hb.make_integ(arith=arith)
     a = synodic.TubeSectionRunner(len(g["x0W"]), mu, t_eval, sec, forward=fwd, flip=(0, 6), integ=integ)
-    b = synodic.TubeSectionRunner(len(g["x0W"]), mu, t_eval, sec, forward=fwd, flip=(0, 6), integ=integ, steps_capacity=256)
+    b = synodic.TubeSectionRunner(len(g["x0W"]), mu, t_eval, sec, forward=fwd, flip=(0, 6), integ=integ, steps_capacity=256,
+                                  records=records)
     a.launch(y0); b.launch(y0)
     ha, hb_ = a.sorted_hits(), b.sorted_hits()
     assert (b.status == 0).all().item()
@@ -128,7 +131,8 @@ def test_two_kernel_overflow_is_flagged():
     g = np.load(os.path.join(HERE, "golden", "synodic_c1.npz"))
     t_eval = np.linspace(0.0, float(g["tf"]), int(g["steps"]))
     y0 = torch.from_numpy(np.ascontiguousarray(g["x0W"].T)).cuda()
-    r = synodic.TubeSectionRunner(50, float(g["mu"]), t_eval, _section(g), forward=-1, flip=(0, 6), steps_capacity=80)
+    r = synodic.TubeSectionRunner(50, float(g["mu"]), t_eval, _section(g), forward=-1, flip=(0, 6), steps_capacity=80,
+                                  records="all")
     r.launch(y0)
     st = r.status.cpu().numpy()
     na = r.nacc.cpu().numpy()
@@ -144,7 +148,8 @@ def test_two_kernel_overflow_is_flagged():
 @pytest.mark.parametrize("axis,offset,plane,direction", [
     ("x", 0.95, ("y", "vy"), 0), ("y", 0.0, ("x", "z"), 1), ("z", 0.0, ("x", "y"), 0),
     ("vx", 0.0, ("x", "y"), 0), ("vy", 0.0, ("x", "z"), -1), ("vz", 0.0, ("x", "y"), 0)])
-def test_pipeline_every_section_component(axis, offset, plane, direction):
+@pytest.mark.parametrize("records", ["all", "near"])
+def test_pipeline_every_section_component(axis, offset, plane, direction, records):
     """The scan kernel is instantiated per section component: each one against the fused kernel AND against the
     stored tube + detector chain (parity arithmetic: bit for bit), on the 200-trajectory tube of config 2."""
     import torch
@@ -155,7 +160,7 @@ def test_pipeline_every_section_component(axis, offset, plane, direction):
     t_eval = np.linspace(0.0, tf, steps)
     sec = synodic.make_section(axis, offset, plane, direction)
     a, ra = synodic.tube_section(g["x0W"], mu, t_eval, sec, forward=fwd, flip=(0, 6), steps_capacity=0)
-    b, rb = synodic.tube_section(g["x0W"], mu, t_eval, sec, forward=fwd, flip=(0, 6), steps_capacity=192)
+    b, rb = synodic.tube_section(g["x0W"], mu, t_eval, sec, forward=fwd, flip=(0, 6), steps_capacity=192, records=records)
     dense = hb.cr3bp_dense(g["x0W"], mu, t_eval, forward=fwd, flip=(0, 6), keep_on_device=True)
     c = synodic.detect(dense.states, fwd * t_eval, sec)
     assert len(c.times) > 0, "test section has no crossings"
@@ -211,16 +216,16 @@ def test_pipeline_equals_fused_on_a_bench_sized_slice_with_overflow_rerun():
     """20000 trajectories of the bench batch: the pipeline (with a scratch too small for the longest trajectories, so
     that the fused-kernel rerun path is exercised) returns exactly the fused kernel's hits, counts and end states."""
     import torch
-    import bench
+    from hiten_b200 import workloads as W
     from hiten_b200 import synodic
     n = 20000
-    ics, mu = bench.build_ics(n)
-    m = max(int(abs(bench.TF) / bench.GRID_DT) + 1, 100)
-    t_eval = np.linspace(0.0, bench.TF, m)
+    ics, mu = W.c1_tube_batch(n)
+    m = max(int(abs(W.C1_TF) / W.GRID_DT) + 1, 100)
+    t_eval = np.linspace(0.0, W.C1_TF, m)
     sec = synodic.make_section("y", 0.0, ("x", "z"), -1)
     y0 = torch.from_numpy(np.ascontiguousarray(ics.T)).cuda()
     a = synodic.TubeSectionRunner(n, mu, t_eval, sec, forward=-1, flip=(0, 6))
-    b = synodic.TubeSectionRunner(n, mu, t_eval, sec, forward=-1, flip=(0, 6), steps_capacity=96)
+    b = synodic.TubeSectionRunner(n, mu, t_eval, sec, forward=-1, flip=(0, 6), steps_capacity=96, records="all")
     a.launch(y0); b.launch(y0)
     overflowed = int((b.status == 4).sum().item())
     ha, hb_ = a.sorted_hits(), b.sorted_hits()
@@ -242,12 +247,12 @@ def test_full_size_1e6_trajectories_oracle_sample_and_order_invariance():
     (b) the reversed batch gives the same per-trajectory results under the index map — the persistent work queue and
     the per-trajectory candidate lists make the result independent of scheduling; (c) every hit lies on the section."""
     import torch
-    import bench
+    from hiten_b200 import workloads as W
     from hiten_b200 import synodic
-    n = bench.N_PER_GPU
-    ics, mu = bench.build_ics(n)
-    m = max(int(abs(bench.TF) / bench.GRID_DT) + 1, 100)
-    t_eval = np.linspace(0.0, bench.TF, m)
+    n = 1_000_000
+    ics, mu = W.c1_tube_batch(n)
+    m = max(int(abs(W.C1_TF) / W.GRID_DT) + 1, 100)
+    t_eval = np.linspace(0.0, W.C1_TF, m)
     sec = synodic.make_section("y", 0.0, ("x", "z"), -1)
     run = synodic.TubeSectionRunner(n, mu, t_eval, sec, forward=-1, flip=(0, 6), steps_capacity=160)   # the bench step
     y0 = torch.from_numpy(np.ascontiguousarray(ics.T)).cuda()
@@ -281,3 +286,31 @@ def test_full_size_1e6_trajectories_oracle_sample_and_order_invariance():
     assert np.array_equal(hr.hits_per_traj, h.hits_per_traj[::-1])
     order = np.lexsort((np.arange(len(hr.times)), n - 1 - hr.trajectory_indices))     # stable within a trajectory
     assert np.array_equal(hr.times[order], h.times) and np.array_equal(hr.states[order], h.states)
+
+
+def test_sparse_records_small_capacity_overflow_rerun_and_record_counts():
+    """records="near": a tube needs a few dozen recorded steps per trajectory; a capacity of 32 overflows some
+    trajectories (flagged, rerun: same final hits), and the recorded share of the accepted steps is small."""
+    import torch
+    from hiten_b200 import synodic
+    from hiten_b200 import workloads as W
+    n = 20000
+    ics, mu = W.c1_tube_batch(n)
+    m = max(int(abs(W.C1_TF) / W.GRID_DT) + 1, 100)
+    t_eval = np.linspace(0.0, W.C1_TF, m)
+    sec = synodic.make_section("y", 0.0, ("x", "z"), -1)
+    y0 = torch.from_numpy(np.ascontiguousarray(ics.T)).cuda()
+    a = synodic.TubeSectionRunner(n, mu, t_eval, sec, forward=-1, flip=(0, 6), steps_capacity=192, records="all")
+    b = synodic.TubeSectionRunner(n, mu, t_eval, sec, forward=-1, flip=(0, 6), steps_capacity=96, records="near")
+    c = synodic.TubeSectionRunner(n, mu, t_eval, sec, forward=-1, flip=(0, 6), steps_capacity=32, records="near")
+    for r in (a, b, c):
+        r.launch(y0)
+    assert int((b.status == 4).sum().item()) == 0
+    n_over = int((c.status == 4).sum().item())
+    ha, hb_, hc = a.sorted_hits(), b.sorted_hits(), c.sorted_hits()
+    print(f"[sparse] 20000 trajectories: capacity 32 overflows {n_over}")
+    for h in (hb_, hc):
+        assert np.array_equal(h.trajectory_indices, ha.trajectory_indices)
+        assert np.array_equal(h.times, ha.times) and np.array_equal(h.states, ha.states)
+        assert np.array_equal(h.hits_per_traj, ha.hits_per_traj)
+    assert torch.equal(a.yf, b.yf) and torch.equal(a.yf, c.yf) and (c.status == 0).all().item()

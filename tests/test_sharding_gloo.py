@@ -22,10 +22,10 @@ def _worker(rank, world, port, out_path):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    import bench
+    from hiten_b200 import workloads as W
     import oracle_lib as O
     n = 24
-    ics, mu = bench.build_ics(n, rank, world)                     # ics_all[rank::world][:n]
+    ics, mu = W.c1_tube_batch(n, rank, world)                     # ics_all[rank::world][:n]
     s = O.system(O.SYS_CR3BP6, mu, fwd=-1, flip=(0, 6))
     yf, counts = O.batch_final(s, O.DOP853, O.default_tol(), ics, 0.0, 1.0, 1)
     t_yf = torch.from_numpy(np.ascontiguousarray(yf.T))            # [6, n] like the kernels' SoA output
@@ -48,7 +48,7 @@ def _worker(rank, world, port, out_path):
 
 def test_two_rank_shard_and_gather(tmp_path):
     sys.path.insert(0, REPO)
-    import bench
+    from hiten_b200 import workloads as W
     import oracle_lib as O
     O.build()
     world, n = 2, 24
@@ -56,7 +56,7 @@ def test_two_rank_shard_and_gather(tmp_path):
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
     got = np.load(out)
-    ics, mu = bench.build_ics(n * world)                           # the unsharded batch
+    ics, mu = W.c1_tube_batch(n * world)                           # the unsharded batch
     s = O.system(O.SYS_CR3BP6, mu, fwd=-1, flip=(0, 6))
     yf, counts = O.batch_final(s, O.DOP853, O.default_tol(), ics, 0.0, 1.0, 1)
     assert np.array_equal(got["yf"], yf)                           # shards re-interleave to the unsharded result
@@ -66,9 +66,9 @@ def test_two_rank_shard_and_gather(tmp_path):
 
 def test_shards_partition_the_batch():
     sys.path.insert(0, REPO)
-    import bench
-    full, _ = bench.build_ics(64)
-    parts = [bench.build_ics(16, r, 4)[0] for r in range(4)]
+    from hiten_b200 import workloads as W
+    full, _ = W.c1_tube_batch(64)
+    parts = [W.c1_tube_batch(16, r, 4)[0] for r in range(4)]
     rebuilt = np.empty_like(full)
     for r in range(4):
         rebuilt[r::4] = parts[r]
