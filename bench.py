@@ -37,7 +37,8 @@ for _p in (REPO, os.path.join(REPO, "tests"), os.path.join(REPO, "tests", "golde
 FLOP_PER_STEP = 1350.0          # algorithmic flop per attempted 6-state DOP853 step
 FLOP_PER_SEGMENT = 1050.0       # dense-output cache of one accepted step (3 RHS + D/A_ext rows)
 N_PER_GPU = 1_000_000           # BASELINE configs[4]: 1e6 manifold trajectories (both tubes together)
-STEPS_CAPACITY = 192            # accepted steps per trajectory the hb_cr3bp_section2 scratch holds (C5 needs <= 183)
+STEPS_CAPACITY = 128            # RECORDED steps per trajectory the hb_cr3bp_section2 scratch holds (sparse records:
+                                # a C5 trajectory writes ~11 of its ~100 accepted steps; 183 with --records all)
 TUBES = ("l1", "l2")
 WORKLOAD = ("C5 = BASELINE configs[4] as examples/heteroclinic_connection.py runs it: EM L1 halo (Az=0.5 S) stable tube "
             "(backward, 0.9*2pi, 5655 samples) + EM L2 halo (Az=0.3663368 N) unstable tube (forward, 2pi, 6284 samples), "
@@ -459,11 +460,15 @@ def main():
     ap.add_argument("--pipeline", default="section2", choices=["section2", "section3", "fused"],
                     help="section2: step records through an HBM scratch (default, fastest); section3: records handed over "
                          "in shared memory inside one kernel (no step scratch); fused: hb_cr3bp_section")
-    ap.add_argument("--steps-capacity", type=int, default=STEPS_CAPACITY)
+    ap.add_argument("--steps-capacity", type=int, default=None)
+    ap.add_argument("--records", default="near", choices=["near", "all"],
+                    help="section2: record only the steps near the section plane (default) or every accepted step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary timings")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.steps_capacity is None:
+        args.steps_capacity = STEPS_CAPACITY if args.records == "near" else 192
 
     if args.impl == "reference":
         run_reference(args)
@@ -489,7 +494,7 @@ def main():
 
     n = args.n_per_gpu
     integ = hb.make_integ(arith=args.arith)
-    kind = {"section2": dict(steps_capacity=args.steps_capacity), "section3": dict(pool_records=8), "fused": {}}[args.pipeline]
+    kind = {"section2": dict(steps_capacity=args.steps_capacity, records=args.records), "section3": dict(pool_records=8), "fused": {}}[args.pipeline]
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)  # > 126 MB L2
 
     def make_job(n_total_global):
@@ -562,6 +567,8 @@ def main():
 
     steps_acc, steps_rej, n_hits, n_overflow, ok = tallies(job)
     steps_per_pass = steps_acc + steps_rej
+    records_written = sum(int(job["tubes"][key]["run"].records_written().sum().item()) for key in TUBES) \
+        if args.pipeline == "section2" else 0
 
     # per-kernel split of the pipeline: caller-owned CUDA events recorded by the library between its kernels on the
     # launching stream, in a separate pass over the same inputs
@@ -585,7 +592,7 @@ def main():
     # neighbouring steps' compute by TubeSectionStream's double buffering); hits are put in the reference's order
     streams = {}
     for key in TUBES:
-        skw = dict(steps_capacity=args.steps_capacity) if args.pipeline == "section2" else \
+        skw = dict(steps_capacity=args.steps_capacity, records=args.records) if args.pipeline == "section2" else \
             (dict(steps_capacity=0, pool_records=8) if args.pipeline == "section3" else dict(steps_capacity=0, pool_records=0))
         streams[key] = synodic.TubeSectionStream(len(job["ics"][key]), mu, W.c5_grid(key), W.c5_section(key, mu),
                                                  forward=W.C5_TUBES[key]["forward"], flip=(0, 6), integ=integ, device=dev,
@@ -661,15 +668,23 @@ def main():
                                                        "tflops": sp * args.steps * FLOP_PER_STEP / tp / 1e12}
         # the same step in the other arithmetic variant and through the other two forms of the pipeline
         other = "fast" if args.arith == "parity" else "parity"
-        for label, ar, kw in ((f"step_{other}", other, kind), ("step_section3_parity", "parity", dict(pool_records=8)),
-                              ("step_fused_kernel_parity", "parity", {})):
+        variants = [(f"step_{other}", other, kind), ("step_section3_parity", "parity", dict(pool_records=8)),
+                    ("step_fused_kernel_parity", "parity", {})]
+        if args.pipeline == "section2" and args.records == "near":
+            variants.insert(1, ("step_section2_all_records_parity", "parity", dict(steps_capacity=192, records="all")))
+        for label, ar, kw in variants:
             if label == "step_section3_parity" and args.pipeline == "section3":
                 continue
             rs = {key: synodic.TubeSectionRunner(len(job["ics"][key]), mu, W.c5_grid(key), W.c5_section(key, mu),
                                                  forward=W.C5_TUBES[key]["forward"], flip=(0, 6),
                                                  integ=hb.make_integ(arith=ar), device=dev,
-                                                 scratch=job["scratch"] if "steps_capacity" in kw else None, **kw)
-                  for key in TUBES}
+                                                 scratch=job["scratch"] if kw is kind and "steps_capacity" in kw else None, **kw)
+                  for key in (TUBES[:1] if kw is not kind and "steps_capacity" in kw else TUBES)}
+            if len(rs) == 1:                                 # all-records scratch (49 GB): the second tube shares it
+                rs[TUBES[1]] = synodic.TubeSectionRunner(len(job["ics"][TUBES[1]]), mu, W.c5_grid(TUBES[1]),
+                                                         W.c5_section(TUBES[1], mu), forward=W.C5_TUBES[TUBES[1]]["forward"],
+                                                         flip=(0, 6), integ=hb.make_integ(arith=ar), device=dev,
+                                                         scratch=rs[TUBES[0]].scratch, **kw)
 
             def step2():
                 for key in TUBES:
@@ -693,10 +708,12 @@ def main():
         if args.pipeline == "section2":
             # the step with Manifold.compute()'s trajectory filters judged from the step records
             r1, r2 = W.c5_safe_radii()
-            rf = {key: synodic.TubeSectionRunner(len(job["ics"][key]), mu, W.c5_grid(key), W.c5_section(key, mu),
-                                                 forward=W.C5_TUBES[key]["forward"], flip=(0, 6), integ=integ, device=dev,
-                                                 steps_capacity=args.steps_capacity, scratch=job["scratch"],
-                                                 filters=(r1, r2, W.ENERGY_TOL)) for key in TUBES}
+            rf, fscratch = {}, None
+            for key in TUBES:                                # every accepted step is recorded here: own (larger) scratch
+                rf[key] = synodic.TubeSectionRunner(len(job["ics"][key]), mu, W.c5_grid(key), W.c5_section(key, mu),
+                                                    forward=W.C5_TUBES[key]["forward"], flip=(0, 6), integ=integ, device=dev,
+                                                    steps_capacity=192, scratch=fscratch, filters=(r1, r2, W.ENERGY_TOL))
+                fscratch = rf[key].scratch
 
             def step3():
                 for key in TUBES:
@@ -709,7 +726,8 @@ def main():
                 "ms_per_step": 1e3 * t3 / 2, "kept_trajectories": kept,
                 "note": "hb_section2_filter: 6-component dense evaluation + r1, r2, Jacobi constant at every grid sample "
                         "(safe radii 3.318e-05 / 9.04e-06, energy_tol 1e-6 as Manifold.compute())"}
-            del rf
+            del rf, fscratch
+            torch.cuda.empty_cache()
         # the connection search between the two hit sets of the last step
         from hiten_b200 import connections as cn
         hu, hs = job["tubes"]["l1"]["run"].sorted_hits(), job["tubes"]["l2"]["run"].sorted_hits()
@@ -729,7 +747,7 @@ def main():
         peak = hb.dfma_peak(200.0)
         hbm = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))["hbm_gbs"] \
             if os.path.exists(os.path.join(REPO, "MEASURED_PEAKS.json")) else 6500.0
-        rec_bytes = steps_acc * 512.0
+        rec_bytes = records_written * 512.0
         if stage_ms is not None:
             # Roofline of the DOMINANT kernel (the propagation kernel of both tubes: k_dop853_6 in record mode + its
             # first-step pre-pass, or the producer/consumer kernel of section3): attempted steps x 1350 flop over that
@@ -767,10 +785,13 @@ def main():
                 "workload": WORKLOAD,
                 "trajectories_per_gpu": n, "trajectories_per_tube_per_gpu": n // 2,
                 "grid_samples": {key: int(len(W.c5_grid(key))) for key in TUBES}, "arith": args.arith,
-                "path": {"section2": "hb_cr3bp_section2 per tube (propagate+record -> step scan -> emit -> order+dedup)",
+                "path": {"section2": "hb_cr3bp_section2 per tube (propagate + screen + record -> step scan -> emit -> order+dedup)",
                          "section3": "hb_cr3bp_section3 per tube (propagating + scanning warps in one kernel -> emit -> order+dedup)",
                          "fused": "hb_cr3bp_section per tube (fused kernel)"}[args.pipeline],
                 "steps_capacity": args.steps_capacity if args.pipeline == "section2" else None,
+                "step_records": None if args.pipeline != "section2" else
+                                {"mode": args.records, "written_per_pass_this_gpu": records_written,
+                                 "share_of_accepted_steps": records_written / max(steps_acc, 1)},
                 "record_overflow_trajectories_rerun": total_overflow,
                 "l2": "flushed between timed iterations (256 MB fill); inputs 48 B and step records ~50 KB per trajectory (>> L2)",
                 "rk_steps_per_pass": total_steps_pass, "accepted_steps_per_pass": total_acc,
@@ -787,7 +808,7 @@ def main():
                                  "flop (SURVEY 8d) / the kernel's own duration (CUDA events recorded between the pipeline's "
                                  "kernels on the launching stream); peak = hb_dfma_peak measured in this process "
                                  "(MEASURED_PEAKS.json has no FP64 entry). traffic = bytes this run moved through HBM for that "
-                                 "kernel, counted from the run: 512 B per accepted step record + 108 B per trajectory "
+                                 "kernel, counted from the run: 512 B per step record written + 108 B per trajectory "
                                  "(ncu dram bytes of the same kernel: profiles/r02_*)"},
             "e2e": {"value": e2e_value, "unit": "RK steps/s", "h2d_bytes_per_step": int(n * 48),
                     "d2h_bytes_per_step": int(n * (48 + 16) + 72 * k_e2e), "same_hits_as_resident_run": e2e_ok,

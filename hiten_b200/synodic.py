@@ -329,6 +329,24 @@ class TubeSectionRunner:
         self.scratch = torch.empty(nbytes // 8, dtype=torch.float64, device=self.device)
         self.steps_capacity = need
 
+    def records_written(self):
+        """hb_cr3bp_section2 only: step records per trajectory the last launch wrote to the scratch (int32 device tensor
+        [n]) -- the accepted steps with records="all", the steps near the section plane and their neighbours with
+        records="near".  Reads the scratch with the layout hb_cr3bp_section2 derives from its size."""
+        if self.scratch is None or self.steps_capacity <= 0:
+            raise ValueError("no step scratch")
+        if self.records == L.HB_RECORDS_ALL:
+            return self.nacc[: self.n].clamp(max=self._rec_cap())
+        n, cap = self.n, self._rec_cap()
+        off_ints = 2 * (n * cap * 64 + 2 * n * 32 * 8) + 2 * n               # past records, cand, desc, two counters
+        return self.scratch.view(torch.int32)[off_ints: off_ints + n]
+
+    def _rec_cap(self):
+        fixed = (32 * 16 + 16 + 2) * 8                                        # HB_S2_FIXED_DOUBLES of hb_scan.cuh
+        cap = ((self.scratch.numel() * 8 - 256) // self.n - fixed) // 512
+        cap -= cap % 32
+        return min(cap, 99968)
+
     def hit_count(self, stream=None):
         nh, no = L.C.c_int64(0), L.C.c_int64(0)
         L.check(self.lib.hb_read_hit_count(self.ws.data_ptr(), L.C.byref(nh), L.C.byref(no), _stream_ptr(stream)),
@@ -400,7 +418,7 @@ class TubeSectionStream:
     come back in pinned host buffers.  The two buffer sets share one step scratch (compute is serial anyway)."""
 
     def __init__(self, n, mu, t_eval, section, *, forward=1, flip=None, integ=None, hit_capacity=None, device=None,
-                 steps_capacity=0, scratch=None, pool_records=8, ordered=True):
+                 steps_capacity=0, scratch=None, pool_records=8, ordered=True, records="near"):
         """Default: hb_cr3bp_section3 (pool_records step records per trajectory in the scratch); steps_capacity > 0
         (with pool_records = 0) selects hb_cr3bp_section2.  ordered=True returns every batch's hits in the reference's
         order (sorted on the device before the copy to the host)."""
@@ -413,10 +431,10 @@ class TubeSectionStream:
         with torch.cuda.device(self.device):
             r0 = TubeSectionRunner(n, mu, t_eval, section, forward=forward, flip=flip, integ=integ,
                                    hit_capacity=hit_capacity, device=self.device, steps_capacity=steps_capacity,
-                                   scratch=scratch, pool_records=pool_records)
+                                   scratch=scratch, pool_records=pool_records, records=records)
             r1 = TubeSectionRunner(n, mu, t_eval, section, forward=forward, flip=flip, integ=integ,
                                    hit_capacity=hit_capacity, device=self.device, steps_capacity=steps_capacity,
-                                   scratch=r0.scratch, pool_records=pool_records)
+                                   scratch=r0.scratch, pool_records=pool_records, records=records)
             self.runners = (r0, r1)
             self.s_in, self.s_run, self.s_out = (torch.cuda.Stream(self.device) for _ in range(3))
             self.d_in = [torch.empty((self.n, 6), dtype=torch.float64, device=self.device) for _ in range(2)]
