@@ -56,6 +56,9 @@ def _norm_flip(flip, dim):
     idx = np.asarray(flip, dtype=np.int64).ravel()
     if idx.size == 0:
         raise LookupError("empty flip")
+    if np.any(idx < -dim) or np.any(idx >= dim):
+        raise LookupError("flip index out of range")           # the reference's own IndexError
+    idx = idx % dim                                             # numpy's negative indexing: -1 is the last component
     srt = np.sort(idx)
     if not np.array_equal(srt, np.arange(srt[0], srt[0] + idx.size)):
         raise LookupError("non-contiguous flip")
@@ -567,6 +570,130 @@ def _make_cm_run(orig):
     return run
 
 
+# ------------------------------------------------------------------------------------------------
+# centre-manifold seeding: the per-candidate Brent solves of the seeding strategies and of the engine's
+# lifting loop become ONE hb_cm_lift batch per map computation
+# ------------------------------------------------------------------------------------------------
+import threading as _threading
+
+_LIFT_CACHE = {}                 # (id(H_blocks), section, h0, p0, p1) -> (q2, p2, q3, p3) or None, filled by a generate()
+_TLS = _threading.local()        # n_seeds of the options of the compute() call running on this thread
+
+
+def _h_table(H_blocks, clmo_table):
+    key = ("H", id(H_blocks), id(clmo_table))
+    if key not in _TABLES:
+        if len(_TABLES) > 16:
+            _TABLES.clear()
+        _TABLES[key] = (_cm.PolyTable.from_hamiltonian(H_blocks, clmo_table), H_blocks)
+    return _TABLES[key][0]
+
+
+def _make_strategy_generate(orig):
+    """`<seeding strategy>.generate` (algorithms/poincare/centermanifold/strategies.py:67-520).  Every strategy walks
+    its candidate plane points and asks `_build_seed` (seeding.py:121-178) whether a point can be lifted onto the
+    energy surface -- one Python Brent solve each -- and some stop as soon as enough valid seeds are found.  Here the
+    strategy's own code runs twice: a PROBE pass in which `_build_seed` only records the candidate (and says "invalid",
+    so no early exit hides later candidates), ONE hb_cm_lift batch over all candidates, then a REPLAY pass -- same
+    numpy random state -- in which `_build_seed` answers from the batch.  Same seeds, same order, same early exits; the
+    lifted states are kept for the engine's lifting loop (`lift_plane_point`)."""
+    def generate(self, *, h0, H_blocks, clmo_table, solve_missing_coord_fn, find_turning_fn):
+        section = self.config.section_coord
+        turning = {}
+
+        def turning_fn(name):                                   # two more Brent solves per pass otherwise
+            if name not in turning:
+                turning[name] = find_turning_fn(name)
+            return turning[name]
+
+        cands = []
+        rng_state = np.random.get_state()
+        # _RandomSeeding draws from an unseeded np.random.default_rng(): both passes get the same fresh seed
+        entropy = np.random.SeedSequence().entropy
+        real_default_rng = np.random.default_rng
+        np.random.default_rng = lambda *a, **k: real_default_rng(*a, **k) if (a or k) else real_default_rng(entropy)
+        self._build_seed = lambda plane_vals, *, solve_missing_coord_fn: (cands.append(tuple(float(v) for v in plane_vals)),
+                                                                          None)[1]
+        try:
+            orig(self, h0=h0, H_blocks=H_blocks, clmo_table=clmo_table, solve_missing_coord_fn=solve_missing_coord_fn,
+                 find_turning_fn=turning_fn)
+        except BaseException:
+            np.random.default_rng = real_default_rng
+            raise
+        finally:
+            del self._build_seed
+        np.random.set_state(rng_state)
+        if not cands:
+            np.random.default_rng = real_default_rng
+            return orig(self, h0=h0, H_blocks=H_blocks, clmo_table=clmo_table,
+                        solve_missing_coord_fn=solve_missing_coord_fn, find_turning_fn=turning_fn)
+        ok, states = _cm.lift_plane_points(_h_table(H_blocks, clmo_table), section, np.asarray(cands, dtype=np.float64),
+                                           float(h0))
+        if len(_LIFT_CACHE) > 4_000_000:
+            _LIFT_CACHE.clear()
+        for c, good, st in zip(cands, ok, states):
+            _LIFT_CACHE[(id(H_blocks), section, float(h0), c[0], c[1])] = tuple(float(v) for v in st) if good else None
+        answers = iter(zip(cands, ok))
+
+        def build(plane_vals, *, solve_missing_coord_fn):
+            c, good = next(answers)
+            if c != tuple(float(v) for v in plane_vals):          # the strategy did not replay the same candidates
+                return type(self)._build_seed(self, plane_vals, solve_missing_coord_fn=solve_missing_coord_fn)
+            return plane_vals if good else None
+
+        self._build_seed = build
+        try:
+            return orig(self, h0=h0, H_blocks=H_blocks, clmo_table=clmo_table,
+                        solve_missing_coord_fn=solve_missing_coord_fn, find_turning_fn=turning_fn)
+        finally:
+            del self._build_seed
+            np.random.default_rng = real_default_rng
+
+    generate.__wrapped__ = orig
+    return generate
+
+
+def _make_lift_plane_point(orig):
+    """_CenterManifoldInterface.lift_plane_point (interfaces.py:297-337): answered from the batch the seeding strategy
+    just lifted (bit-identical: hb_cm_lift reproduces the reference's bracket expansion and Brent iteration); any other
+    point, or non-default solver settings, goes through the reference's own method."""
+    def lift_plane_point(self, plane, *, section_coord, h0, H_blocks, clmo_table, **kw):
+        if not kw:
+            key = (id(H_blocks), section_coord, float(h0), float(plane[0]), float(plane[1]))
+            if key in _LIFT_CACHE:
+                return _LIFT_CACHE[key]
+        return orig(self, plane, section_coord=section_coord, h0=h0, H_blocks=H_blocks, clmo_table=clmo_table, **kw)
+
+    lift_plane_point.__wrapped__ = orig
+    return lift_plane_point
+
+
+def _make_create_problem(orig):
+    """Remember the n_seeds of the options this compute() call was given: the reference's strategies read
+    `getattr(map_config, "n_seeds", 20)` (core/strategies.py:102-121) and the config has no such field, so
+    SeedingOptions(n_seeds=...) never reaches them.  With install(cm_seeds_from_options=True) it does."""
+    def create_problem(self, *, domain_obj, config, options):
+        n = None
+        try:
+            n = int(options.seeding.n_seeds)
+        except Exception:
+            pass
+        _TLS.n_seeds = n
+        return orig(self, domain_obj=domain_obj, config=config, options=options)
+
+    create_problem.__wrapped__ = orig
+    return create_problem
+
+
+def _make_n_seeds(orig_prop):
+    def n_seeds(self):
+        n = getattr(_TLS, "n_seeds", None)
+        if _STATE.get("cm_seeds_from_options") and n is not None:
+            return n
+        return orig_prop.fget(self)
+    return property(n_seeds)
+
+
 def _make_connections_run(orig):
     def run(self, request):
         """_ConnectionsBackend.run (algorithms/connections/backends.py:425-540) through hb_connections."""
@@ -639,15 +766,27 @@ def _make_orbit_correct(orig):
 # ------------------------------------------------------------------------------------------------
 # install / uninstall
 # ------------------------------------------------------------------------------------------------
-def install(arith="parity", corrector="reference"):
+def install(arith="parity", corrector="reference", cm_seeds_from_options=False):
     """Rebind the reference's funnels.  Requires `hiten` to be importable; idempotent.
     corrector="reference" keeps the reference's own Newton loop (its propagations run on the GPU through the rebound
     `_propagate_dynsys` / `_DOP853.integrate`); corrector="batched" additionally rebinds
-    `_OrbitCorrectionService.correct` to hb_correct_orbits (one GPU call per correct())."""
+    `_OrbitCorrectionService.correct` to hb_correct_orbits (one GPU call per correct()).
+    cm_seeds_from_options=True lets `SeedingOptions(n_seeds=...)` reach the centre-manifold seeding strategies (the
+    reference always seeds 20, core/strategies.py:102-121), which is what makes BASELINE configs[2]'s 1e5 seeds
+    reachable from cm.poincare_map().compute(); False keeps the reference's behaviour."""
     if corrector not in ("reference", "batched"):
         raise ValueError("corrector must be 'reference' or 'batched'")
     if _STATE["installed"]:
         _STATE["arith"] = arith
+        _STATE["cm_seeds_from_options"] = bool(cm_seeds_from_options)
+        want_batched = corrector == "batched"
+        if want_batched != ("orbit_correct" in _STATE["orig"]):           # the corrector choice changed: re-bind it
+            from hiten.algorithms.types.services.orbits import _OrbitCorrectionService
+            if want_batched:
+                _STATE["orig"]["orbit_correct"] = _OrbitCorrectionService.correct
+                _OrbitCorrectionService.correct = _make_orbit_correct(_STATE["orig"]["orbit_correct"])
+            else:
+                _OrbitCorrectionService.correct = _STATE["orig"].pop("orbit_correct")
         return
     import hiten  # noqa: F401
     import hiten.algorithms.dynamics.base as dbase
@@ -686,6 +825,22 @@ def install(arith="parity", corrector="reference"):
     _SynodicDetectionBackend.run = _make_synodic_run(_STATE["orig"]["synodic"])
     _CenterManifoldBackend.run = _make_cm_run(_STATE["orig"]["cm"])
     _ConnectionsBackend.run = _make_connections_run(_STATE["orig"]["connections"])
+    # centre-manifold seeding: batched lifting behind the strategies and the engine's lifting loop
+    import hiten.algorithms.poincare.centermanifold.strategies as cm_strat
+    from hiten.algorithms.poincare.centermanifold.interfaces import _CenterManifoldInterface
+    from hiten.algorithms.poincare.core.strategies import _SeedingStrategyBase
+    _STATE["cm_seeds_from_options"] = bool(cm_seeds_from_options)
+    strat_classes = [c for c in vars(cm_strat).values()
+                     if isinstance(c, type) and c.__module__ == cm_strat.__name__ and "generate" in vars(c)]
+    _STATE["orig"]["cm_generate"] = {c: c.generate for c in strat_classes}
+    for c in strat_classes:
+        c.generate = _make_strategy_generate(c.generate)
+    _STATE["orig"]["cm_lift"] = _CenterManifoldInterface.lift_plane_point
+    _STATE["orig"]["cm_create_problem"] = _CenterManifoldInterface.create_problem
+    _STATE["orig"]["cm_n_seeds"] = _SeedingStrategyBase.__dict__["n_seeds"]
+    _CenterManifoldInterface.lift_plane_point = _make_lift_plane_point(_STATE["orig"]["cm_lift"])
+    _CenterManifoldInterface.create_problem = _make_create_problem(_STATE["orig"]["cm_create_problem"])
+    _SeedingStrategyBase.n_seeds = _make_n_seeds(_STATE["orig"]["cm_n_seeds"])
     if corrector == "batched":
         from hiten.algorithms.types.services.orbits import _OrbitCorrectionService
         _STATE["orig"]["orbit_correct"] = _OrbitCorrectionService.correct
@@ -717,8 +872,18 @@ def uninstall():
     if "orbit_correct" in o:
         from hiten.algorithms.types.services.orbits import _OrbitCorrectionService
         _OrbitCorrectionService.correct = o["orbit_correct"]
+    if "cm_generate" in o:
+        from hiten.algorithms.poincare.centermanifold.interfaces import _CenterManifoldInterface
+        from hiten.algorithms.poincare.core.strategies import _SeedingStrategyBase
+        for c, fn in o["cm_generate"].items():
+            c.generate = fn
+        _CenterManifoldInterface.lift_plane_point = o["cm_lift"]
+        _CenterManifoldInterface.create_problem = o["cm_create_problem"]
+        _SeedingStrategyBase.n_seeds = o["cm_n_seeds"]
     _STATE.update(installed=False, orig={}, patched_modules=[])
     _TABLES.clear()
+    _LIFT_CACHE.clear()
+    _TLS.n_seeds = None
 
 
 def is_installed():

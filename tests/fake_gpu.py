@@ -85,6 +85,14 @@ def poincare_map(table, seeds, opts, **kw):
     return O.cm_poincare_map(ham, seeds, opts.dt, order, opts.max_steps, symp, sec, c_omega, 4)
 
 
+def lift_plane_points(H_table, section_coord, plane_points, h0, *, initial_guess=1e-3, expand_factor=2.0, max_expand=40,
+                      symmetric=False, xtol=1e-12, **kw):
+    ham = O.PolyHam(H_table.ptr, H_table.deg, H_table.coef, H_table.exp)
+    ok, out = O.cm_lift(ham, section_coord, np.asarray(plane_points, dtype=np.float64), h0, initial_guess, expand_factor,
+                        max_expand, symmetric, xtol)
+    return ok.astype(bool), out
+
+
 def find_connections(points_u, points_s, states_u, states_s, eps, dv_tol, bal_tol, *, traj_indices_u=None,
                      traj_indices_s=None, **kw):
     from hiten_b200.connections import Connections
@@ -198,6 +206,7 @@ def patch(monkeypatch):
     monkeypatch.setattr(prop, "cr3bp_event", cr3bp_event)
     monkeypatch.setattr(syn, "detect", detect)
     monkeypatch.setattr(cm, "poincare_map", poincare_map)
+    monkeypatch.setattr(cm, "lift_plane_points", lift_plane_points)
     import hiten_b200.symplectic as symp
     monkeypatch.setattr(symp, "integrate_symplectic", integrate_symplectic)
     monkeypatch.setattr(symp, "integrate_symplectic_until_event", integrate_symplectic_until_event)

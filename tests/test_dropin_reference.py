@@ -393,3 +393,67 @@ def test_fixed_step_rk_classes_on_the_hamiltonian_system(ref, monkeypatch):
     for k in want:
         for a, b in zip(got[k], want[k]):
             assert np.array_equal(a, b), k
+
+
+def test_centre_manifold_seeding_is_batched_and_identical(ref, monkeypatch):
+    """Every seeding strategy with the drop-in: the candidates are lifted in ONE batch (no per-point Brent solve in
+    `_build_seed`, none in the engine's lifting loop), and the seeds the strategy returns / the states the engine lifts
+    are identical to the reference alone.  With cm_seeds_from_options the options' n_seeds reaches the strategy."""
+    import fake_gpu
+    import hiten_b200
+    from hiten_b200 import centermanifold as cmod
+    from hiten.algorithms.poincare.centermanifold.config import CenterManifoldMapConfig
+    from hiten.algorithms.poincare.centermanifold.interfaces import _CenterManifoldInterface
+    from hiten.algorithms.poincare.centermanifold.strategies import _make_strategy
+    system, l1, halo = ref
+    cm = l1.get_center_manifold(degree=6)
+    cm.compute()
+    pm = cm.poincare_map(energy=0.7)
+    hamsys = pm.dynamics.hamsys
+    H_blocks, clmo = hamsys.poly_H(), hamsys.clmo_table
+    iface = _CenterManifoldInterface()
+    solve = lambda var, fixed: iface.solve_missing_coord(var, fixed, h0=0.7, H_blocks=H_blocks, clmo_table=clmo)
+    turn = lambda name: iface.find_turning(name, h0=0.7, H_blocks=H_blocks, clmo_table=clmo)
+
+    def run(strategy, section):
+        from hiten.algorithms.types.configs import IntegrationConfig
+        cfg = CenterManifoldMapConfig(section_coord=section, seed_strategy=strategy,
+                                      seed_axis=("q2" if section in ("q3", "p3") else "q3") if strategy == "single" else None,
+                                      integration=IntegrationConfig(method="symplectic"))
+        st = _make_strategy(cfg)
+        pts = st.generate(h0=0.7, H_blocks=H_blocks, clmo_table=clmo, solve_missing_coord_fn=solve, find_turning_fn=turn)
+        lifted = [iface.lift_plane_point(p, section_coord=section, h0=0.7, H_blocks=H_blocks, clmo_table=clmo) for p in pts]
+        return pts, lifted
+
+    cases = [("single", "p3"), ("axis_aligned", "q3"), ("level_sets", "p3"), ("radial", "q2")]
+    want = {c: run(*c) for c in cases}
+    hiten_b200.install()
+    fake_gpu.patch(monkeypatch)
+    calls, brent = [], []
+    inner = cmod.lift_plane_points
+    monkeypatch.setattr(cmod, "lift_plane_points", lambda *a, **k: (calls.append(len(a[2])), inner(*a, **k))[1])
+    try:
+        for c in cases:
+            n_before = len(calls)
+            got = run(*c)
+            assert len(calls) == n_before + 1 and calls[-1] >= len(got[0])   # one batch per generate()
+            assert got[0] == want[c][0] and got[1] == want[c][1], c
+        # random seeding: reproducible inside one generate() (probe and replay see the same draws), valid seeds only
+        pts, lifted = run("random", "p3")
+        assert len(pts) == 20 and all(s is not None for s in lifted)
+        # n_seeds from the options reaches the strategies only when asked for
+        from hiten.algorithms.poincare.centermanifold.options import CenterManifoldMapOptions
+        from hiten.algorithms.poincare.core.options import IterationOptions, SeedingOptions
+        from hiten.algorithms.types.options import IntegrationOptions, WorkerOptions
+        opts = CenterManifoldMapOptions(
+            integration=IntegrationOptions(dt=0.01, order=4, c_omega_heuristic=20, max_steps=2000),
+            iteration=IterationOptions(n_iter=1), seeding=SeedingOptions(n_seeds=64), workers=WorkerOptions(n_workers=1))
+        pm.compute(section_coord="p3", options=opts)
+        n_default = len(np.asarray(pm.get_points(section_coord="p3")))
+        hiten_b200.install(cm_seeds_from_options=True)
+        pm2 = cm.poincare_map(energy=0.65)                  # another energy: nothing cached
+        pm2.compute(section_coord="p3", options=opts)
+        n_more = len(np.asarray(pm2.get_points(section_coord="p3")))
+        assert n_default <= 20 < n_more <= 64
+    finally:
+        hiten_b200.uninstall()

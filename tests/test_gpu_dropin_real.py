@@ -250,3 +250,55 @@ def test_propagate_dynsys_and_compute_stm_on_the_device(ref):
             dbase._propagate_dynsys(ref.dynsys, x0[:5], 0.0, 1.0)
     finally:
         hiten_b200.uninstall()
+
+
+def test_c3_1e5_seeds_through_the_public_api(ref, cm):
+    """BASELINE configs[2] at its stated size from the user's call: install(cm_seeds_from_options=True), then
+    cm.poincare_map(0.7).compute("p3") with SeedingOptions(n_seeds=100000): the seeding strategy's candidates are lifted
+    in one hb_cm_lift batch, the engine's lifting loop reads that batch, the map runs on the GPU.  A 256-seed sample of
+    the first backend request is recomputed by the unpatched reference backend: flags, states and times identical."""
+    import hiten_b200
+    from hiten.algorithms.poincare.centermanifold.backend import _CenterManifoldBackend
+    from hiten.algorithms.poincare.centermanifold.options import CenterManifoldMapOptions
+    from hiten.algorithms.poincare.centermanifold.types import CenterManifoldBackendRequest
+    from hiten.algorithms.poincare.core.options import IterationOptions, SeedingOptions
+    from hiten.algorithms.types.options import IntegrationOptions, WorkerOptions
+    import time
+    hiten_b200.install(cm_seeds_from_options=True)
+    seen = []
+    try:
+        patched_run = _CenterManifoldBackend.run
+
+        def spy(self, request):
+            resp = patched_run(self, request)
+            seen.append((request, resp))
+            return resp
+
+        _CenterManifoldBackend.run = spy
+        pm = cm.poincare_map(energy=0.7)
+        opts = CenterManifoldMapOptions(
+            integration=IntegrationOptions(dt=0.01, order=4, c_omega_heuristic=20, max_steps=2000),
+            iteration=IterationOptions(n_iter=1), seeding=SeedingOptions(n_seeds=100_000), workers=WorkerOptions(n_workers=1))
+        t0 = time.perf_counter()
+        pm.compute(section_coord="p3", options=opts)
+        dt = time.perf_counter() - t0
+        pts = np.asarray(pm.get_points(section_coord="p3"))
+        _CenterManifoldBackend.run = patched_run
+    finally:
+        hiten_b200.uninstall()
+    req, resp = seen[0]
+    n_seeds = len(req.seeds)
+    print(f"[dropin] C3: {n_seeds} lifted seeds -> {len(pts)} section points in {dt:.1f} s wall (strategy + lifting + map)")
+    assert n_seeds > 90_000 and len(pts) > 0.9 * n_seeds and len(np.unique(req.seeds, axis=0)) == n_seeds
+    # the unpatched reference backend on a strided 256-seed sample of the same request
+    pick = np.arange(0, n_seeds, n_seeds // 256)[:256]
+    sub = CenterManifoldBackendRequest(seeds=req.seeds[pick], dt=req.dt, jac_H=req.jac_H, clmo_table=req.clmo_table,
+                                       section_coord=req.section_coord, forward=req.forward, max_steps=req.max_steps,
+                                       method=req.method, order=req.order, c_omega_heuristic=req.c_omega_heuristic)
+    want = _CenterManifoldBackend().run(sub)                       # the reference's own code (uninstalled above)
+    flags = np.asarray(resp.flags)
+    assert np.array_equal(flags[pick], np.asarray(want.flags))
+    rows = np.cumsum(flags.astype(bool)) - 1                        # response rows of the successful seeds
+    ok = flags[pick].astype(bool)
+    assert np.array_equal(np.asarray(resp.states)[rows[pick][ok]], np.asarray(want.states))
+    assert np.array_equal(np.asarray(resp.times)[rows[pick][ok]], np.asarray(want.times))
