@@ -40,8 +40,11 @@ struct StmParams {
     double *dense_out;        // [n][m][42]
 };
 
+#ifndef HB_STM_PARITY_FIELD
+#define HB_STM_PARITY_FIELD 0
+#endif
 #ifndef HB_STM_RHS_NOINLINE
-#define HB_STM_RHS_NOINLINE 1
+#define HB_STM_RHS_NOINLINE HB_STM_PARITY_FIELD       // the called form only pays for the large (old parity) field
 #endif
 struct StmV6 { double a, b, c, d, e, f; };
 
@@ -57,7 +60,14 @@ struct StmRhsImpl {
         const double z = __shfl_sync(gmask, v[2], 6, 8);
         const double mu = p.mu, mu2 = p.om;
         double oxx, oyy, ozz, oxy, oxz, oyz, ax, ay, az;
-        if constexpr (AR::parity) {
+        // The reference evaluates these entries with libm pow (r2**1.5, r2**2.5: not correctly rounded) and sums F @ Phi
+        // with a SIMD dot product, so NO arithmetic reproduces its bits here (header note): the 42-state path is a
+        // tolerance statement in both variants.  The separately rounded form below (2 sqrt.rn, 4 refined reciprocals,
+        // 10 correctly rounded quotients: ~230 instructions, executed by all 8 lanes of a group for ONE trajectory) buys
+        // nothing over the FMA / rsqrt form (~60 instructions, |difference| ~ 1e-15) -- measured against the reference:
+        // 2.0e-11 vs 1.2e-11 of |Phi| on the 100-member halo family -- so both variants use the latter
+        // (HB_STM_PARITY_FIELD=1 brings the old form back).  Stage sums, error norm and controller stay in AR.
+        if constexpr (AR::parity && HB_STM_PARITY_FIELD) {
             const double xm = AR::add(x, mu), xo = AR::sub(x, mu2);
             const double xm2 = AR::mul(xm, xm), xo2 = AR::mul(xo, xo), yy = AR::mul(y, y), zz = AR::mul(z, z);
             const double r2 = AR::add(AR::add(xm2, yy), zz);
