@@ -197,6 +197,7 @@ class TubeSectionRunner:
         self.mu, self.forward, self.flip = mu, forward, flip
         self.sys = P.make_sys(mu, forward, flip)
         self.cap = int(hit_capacity) if hit_capacity is not None else max(1024, 8 * self.n)
+        self._fixed_cap = hit_capacity is not None           # an explicit capacity is a hard limit (overflow raises)
         self.hits = torch.empty(self.cap * 9, dtype=torch.float64, device=self.device)
         self.steps_capacity = int(steps_capacity)
         self.pool_records = int(pool_records)
@@ -352,7 +353,14 @@ class TubeSectionRunner:
         L.check(self.lib.hb_read_hit_count(self.ws.data_ptr(), L.C.byref(nh), L.C.byref(no), _stream_ptr(stream)),
                 "hb_read_hit_count")
         if no.value:
-            raise L.HitenB200Error(f"hit buffer overflow: {no.value} hits dropped (capacity {self.cap})")
+            # more hits than the buffer holds (the reference has no such cap): the workspace counted every hit, so
+            # size the buffer for all of them and run the batch again -- like detect() and the fused path of tube_section
+            if self._fixed_cap or self._y0 is None:
+                raise L.HitenB200Error(f"hit buffer overflow: {no.value} hits dropped (capacity {self.cap})")
+            self.cap = int(nh.value) + 16
+            self.hits = torch.empty(self.cap * 9, dtype=torch.float64, device=self.device)
+            self.launch(self._y0, stream)
+            return self.hit_count(stream)
         self._main_hits = int(nh.value)
         self._rerun_overflowed(stream)
         extra = self._extra[1] if self._extra is not None else None

@@ -314,3 +314,47 @@ def test_sparse_records_small_capacity_overflow_rerun_and_record_counts():
         assert np.array_equal(h.times, ha.times) and np.array_equal(h.states, ha.states)
         assert np.array_equal(h.hits_per_traj, ha.hits_per_traj)
     assert torch.equal(a.yf, b.yf) and torch.equal(a.yf, c.yf) and (c.status == 0).all().item()
+
+
+def test_hit_buffer_grows_instead_of_raising_and_segment_refine_zero():
+    """(a) a propagation with more than 8 crossings per trajectory overflows the default hit buffer: the runner sizes it
+    for all hits and reruns (the reference has no cap); an explicit hit_capacity stays a hard limit.  (b) the
+    segment_refine = 0 branch of the detector (one linear root per sample segment, backend.py:782-821) through the
+    pipeline, the fused kernel and the stored-tube detector: identical hits, equal to the oracle's."""
+    import torch
+    import hiten_b200 as hb
+    from hiten_b200 import synodic
+    from hiten_b200._lib import HitenB200Error
+    g = np.load(os.path.join(HERE, "golden", "synodic_c2.npz"))
+    mu, fwd = float(g["mu"]), int(g["forward"])
+    x0 = np.tile(g["x0W"], (2, 1))                                   # 400 trajectories, ~3.4 crossings each
+    t_eval = np.linspace(0.0, float(g["tf"]), int(g["steps"]))
+    y0 = torch.from_numpy(np.ascontiguousarray(x0.T)).cuda()
+    run = synodic.TubeSectionRunner(len(x0), mu, t_eval, _section(g), forward=fwd, flip=(0, 6), steps_capacity=192)
+    run.cap = 256                                                    # (the default is max(1024, 8 n): force the overflow)
+    run.hits = torch.empty(run.cap * 9, dtype=torch.float64, device="cuda")
+    run.launch(y0)
+    h = run.sorted_hits()
+    k = len(g["hit_time"])
+    assert len(h.times) == 2 * k > 256 and run.cap >= 2 * k
+    assert np.array_equal(h.times[:k], g["hit_time"]) and np.array_equal(h.times[k:], g["hit_time"])
+    tight = synodic.TubeSectionRunner(len(x0), mu, t_eval, _section(g), forward=fwd, flip=(0, 6), steps_capacity=192,
+                                      hit_capacity=64)
+    tight.launch(y0)
+    with pytest.raises(HitenB200Error):
+        tight.hit_count()
+    # (b)
+    sec0 = synodic.make_section("y", 0.0, ("x", "z"), -1, segment_refine=0)
+    a, _ = synodic.tube_section(g["x0W"], mu, t_eval, sec0, forward=fwd, flip=(0, 6), steps_capacity=0)
+    b, _ = synodic.tube_section(g["x0W"], mu, t_eval, sec0, forward=fwd, flip=(0, 6), steps_capacity=192)
+    dense = hb.cr3bp_dense(g["x0W"], mu, t_eval, forward=fwd, flip=(0, 6), keep_on_device=True)
+    c = synodic.detect(dense.states, fwd * t_eval, sec0)
+    assert len(c.times) > 100
+    for hh in (a, b):
+        assert np.array_equal(hh.trajectory_indices, c.trajectory_indices)
+        assert np.array_equal(hh.times, c.times) and np.array_equal(hh.states, c.states)
+    tube = dense.states.cpu().numpy()
+    for i in (0, 57, 199):
+        t, x = O.synodic_detect(fwd * t_eval, tube[i], 1, 0.0, -1, (0, 2), 0, 1e-6, 1e-9, 1e-6)
+        sel = c.trajectory_indices == i
+        assert np.array_equal(c.times[sel], t) and np.array_equal(c.states[sel], x)
