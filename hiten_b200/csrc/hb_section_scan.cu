@@ -331,7 +331,11 @@ __global__ void __launch_bounds__(256) k_compact_segments(const ScanParams p)
 {
     const long long traj = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    const int nd = (traj < p.n) ? min(p.desc_count[traj], HB_CAND_CAP) : 0;
+    // a trajectory with more noted segments than its list holds -- or marked that way because the record pool of
+    // hb_cr3bp_section3 ran dry, in which case the list is only partly written -- is reported as overflowed by
+    // k_order_dedup and rerun by the caller: none of its segments is indexed
+    const int cnt = (traj < p.n) ? p.desc_count[traj] : 0;
+    const int nd = (cnt > HB_CAND_CAP) ? 0 : cnt;
     unsigned same = 0u;                                       // bit i: segment i has both samples in one step
     for (int i = 0; i < nd; ++i) {
         const double *d = p.desc + (traj * HB_CAND_CAP + i) * HB_DESC_DOUBLES;

@@ -76,7 +76,10 @@ def test_section3_forward_time_and_small_pool_overflow_rerun():
     y0 = torch.from_numpy(np.ascontiguousarray(x0.T)).cuda()
     ref = synodic.TubeSectionRunner(len(x0), mu, t_eval, sec, forward=1, steps_capacity=192)
     ref.launch(y0)
+    n_ref_over = int((ref.status == 4).sum().item())
     want = ref.sorted_hits()
+    print(f"[section3] reference run: {len(want.times)} hits, {n_ref_over} record overflows, "
+          f"max records {int(ref.records_written().max().item())}")
     big = synodic.TubeSectionRunner(len(x0), mu, t_eval, sec, forward=1, pool_records=16)
     big.launch(y0)
     got = big.sorted_hits()
