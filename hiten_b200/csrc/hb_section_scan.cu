@@ -74,7 +74,10 @@ using namespace hbscan;
 template <bool SPARSE> struct ScanGeom {
     static constexpr int COPY = SPARSE ? HB_REC_DOUBLES * 8 : (HB_REC_K12 + 6) * 8;
     static constexpr int ROW = SPARSE ? HB_REC_DOUBLES * 8 + 16 : COPY;
-    static constexpr int SMEM = HB_SCAN_WARPS * (32 * ROW + 16);
+    // records per chunk: a sparse trajectory has ~10 records, so 16-row chunks halve the staging memory (8.4 KB per
+    // warp: the occupancy is then bounded by registers, 16 warps per SM instead of 12) at no cost in rounds
+    static constexpr int CH = SPARSE ? 16 : 32;
+    static constexpr int SMEM = HB_SCAN_WARPS * (CH * ROW + 16);
     static_assert(COPY % 16 == 0 && (ROW / 16) % 2 == 1, "row: 16-byte multiple, odd number of 16-byte units");
 };
 
@@ -88,14 +91,14 @@ template <class AR, int C, bool SPARSE>  // C = section component (compile time:
 __global__ void __launch_bounds__(32 * HB_SCAN_WARPS, HB_SCAN_MINBLOCKS) k_step_scan(const ScanParams p)
 {
     constexpr unsigned FULL = 0xffffffffu;
-    constexpr int HB_SCAN_COPY = ScanGeom<SPARSE>::COPY, HB_SCAN_ROW = ScanGeom<SPARSE>::ROW;
+    constexpr int HB_SCAN_COPY = ScanGeom<SPARSE>::COPY, HB_SCAN_ROW = ScanGeom<SPARSE>::ROW, CH = ScanGeom<SPARSE>::CH;
     extern __shared__ __align__(128) unsigned char scan_smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const long long traj = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (traj >= p.n) return;                                  // whole warp
-    unsigned char *wbase = scan_smem + wid * (32 * HB_SCAN_ROW + 16);
-    const double *row_ptr = (const double *)(wbase + lane * HB_SCAN_ROW);
-    const unsigned mbar = smem_u32(wbase + 32 * HB_SCAN_ROW), row_u32 = smem_u32(row_ptr);
+    unsigned char *wbase = scan_smem + wid * (CH * HB_SCAN_ROW + 16);
+    const double *row_ptr = (const double *)(wbase + (lane & (CH - 1)) * HB_SCAN_ROW);
+    const unsigned mbar = smem_u32(wbase + CH * HB_SCAN_ROW), row_u32 = smem_u32(row_ptr);
     if (lane == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 32;" ::"r"(mbar) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -106,7 +109,9 @@ __global__ void __launch_bounds__(32 * HB_SCAN_WARPS, HB_SCAN_MINBLOCKS) k_step_
     // trip of its own): until then every row of the scratch is fair game -- rows past the count hold stale bytes that
     // no lane looks at.
     const int *count = SPARSE ? p.nrec : p.nacc;        // records of this trajectory in the scratch
-    int nacc = HB_SCAN_PIPELINED ? p.rec_cap : min(count[traj], p.rec_cap);
+    // (sparse records: a trajectory has ~10 of them, so the count is read first -- requesting a full chunk blindly
+    // would read 16 KB per trajectory, three times what is there)
+    int nacc = (HB_SCAN_PIPELINED && !SPARSE) ? p.rec_cap : min(count[traj], p.rec_cap);
     const double off = p.sink.sec.offset, tol_s = p.sink.sec.tol_on_surface;
     const int sdir = p.sink.sec.direction;
     int ndesc = 0;                         // segments noted so far (warp-uniform)
@@ -119,7 +124,7 @@ __global__ void __launch_bounds__(32 * HB_SCAN_WARPS, HB_SCAN_MINBLOCKS) k_step_
     // one 512-byte bulk copy per lane (the lane's own record of the chunk) or a plain arrival
     auto issue_chunk = [&](int b) {
         const int sb = b + lane;
-        if (sb < nacc) {
+        if (lane < CH && sb < nacc) {
             const double *src = p.rec + (traj * p.rec_cap + sb) * HB_REC_DOUBLES;
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(HB_SCAN_COPY)
                          : "memory");
@@ -128,8 +133,8 @@ __global__ void __launch_bounds__(32 * HB_SCAN_WARPS, HB_SCAN_MINBLOCKS) k_step_
 #if HB_SCAN_PREFETCH
             // the next chunk's record of this lane: start it towards L2 now, so that the blocking wait of the next
             // round pays an L2 hit instead of a DRAM round trip
-            if (sb + 32 < nacc)
-                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src + 32 * HB_REC_DOUBLES),
+            if (sb + CH < nacc)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src + CH * HB_REC_DOUBLES),
                              "r"(HB_REC_DOUBLES * 8) : "memory");
 #endif
         } else {
@@ -141,9 +146,9 @@ __global__ void __launch_bounds__(32 * HB_SCAN_WARPS, HB_SCAN_MINBLOCKS) k_step_
     nacc = min(count[traj], p.rec_cap);
     if (nacc <= 0) mbar_wait(mbar, phase);                    // nothing to scan: let the requested rows land before exit
 #endif
-    for (int base = 0; base < nacc; base += 32) {
+    for (int base = 0; base < nacc; base += CH) {
         const int s = base + lane;
-        const bool have_rec = s < nacc;
+        const bool have_rec = lane < CH && s < nacc;
         double hdr[11];
 #pragma unroll
         for (int i = 0; i < 11; ++i) hdr[i] = 0.0;
@@ -197,7 +202,7 @@ __global__ void __launch_bounds__(32 * HB_SCAN_WARPS, HB_SCAN_MINBLOCKS) k_step_
         // the rows are not read again in this round (the scan below runs on the headers in registers): the next
         // chunk's copies fly while this chunk is scanned
         __syncwarp();
-        if (base + 32 < nacc) issue_chunk(base + 32);
+        if (base + CH < nacc) issue_chunk(base + CH);
 #endif
         int c0 = __shfl_up_sync(FULL, cend, 1);               // t_new of a step is t_old of the next, bit for bit
         double t_c0 = __shfl_up_sync(FULL, t_c, 1);                       // t_eval[c0]: the previous lane's t_eval[cend]
@@ -302,9 +307,9 @@ __global__ void __launch_bounds__(32 * HB_SCAN_WARPS, HB_SCAN_MINBLOCKS) k_step_
             carry1 = a;
             carry_step = base + qL;
         }
-        carry_c = __shfl_sync(FULL, cend, 31);
-        carry_t = shfl_d(t_c, 31);
-        if (SPARSE) carry_no = __shfl_sync(FULL, step_no, 31);
+        carry_c = __shfl_sync(FULL, cend, CH - 1);
+        carry_t = shfl_d(t_c, CH - 1);
+        if (SPARSE) carry_no = __shfl_sync(FULL, step_no, CH - 1);
         __syncwarp();                                         // every lane is done with its row before the next copy
     }
     if (lane == 0) p.desc_count[traj] = ndesc;

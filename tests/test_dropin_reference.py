@@ -448,8 +448,9 @@ def test_centre_manifold_seeding_is_batched_and_identical(ref, monkeypatch):
         opts = CenterManifoldMapOptions(
             integration=IntegrationOptions(dt=0.01, order=4, c_omega_heuristic=20, max_steps=2000),
             iteration=IterationOptions(n_iter=1), seeding=SeedingOptions(n_seeds=64), workers=WorkerOptions(n_workers=1))
-        pm.compute(section_coord="p3", options=opts)
-        n_default = len(np.asarray(pm.get_points(section_coord="p3")))
+        pm0 = cm.poincare_map(energy=0.66)                  # an energy no other test used: the reference caches sections
+        pm0.compute(section_coord="p3", options=opts)       # by option NAMES only (services/base.py:155-172)
+        n_default = len(np.asarray(pm0.get_points(section_coord="p3")))
         hiten_b200.install(cm_seeds_from_options=True)
         pm2 = cm.poincare_map(energy=0.65)                  # another energy: nothing cached
         pm2.compute(section_coord="p3", options=opts)
