@@ -77,7 +77,10 @@ template <bool SPARSE> struct ScanGeom {
     // records per chunk: a sparse trajectory has ~10 records, so 16-row chunks halve the staging memory (8.4 KB per
     // warp: the occupancy is then bounded by registers, 16 warps per SM instead of 12) at no cost in rounds
     static constexpr int CH = SPARSE ? 16 : 32;
-    static constexpr int SMEM = HB_SCAN_WARPS * (CH * ROW + 16);
+    // ... and two such trajectories share a warp, one per half (GW lanes): the kernel is bound by per-warp latency with
+    // a third of the lanes busy otherwise.  PACK x CH = 32 rows per warp in both modes.
+    static constexpr int PACK = 32 / CH;
+    static constexpr int SMEM = HB_SCAN_WARPS * (32 * ROW + 16);
     static_assert(COPY % 16 == 0 && (ROW / 16) % 2 == 1, "row: 16-byte multiple, odd number of 16-byte units");
 };
 
@@ -92,13 +95,20 @@ __global__ void __launch_bounds__(32 * HB_SCAN_WARPS, HB_SCAN_MINBLOCKS) k_step_
 {
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int HB_SCAN_COPY = ScanGeom<SPARSE>::COPY, HB_SCAN_ROW = ScanGeom<SPARSE>::ROW, CH = ScanGeom<SPARSE>::CH;
+    constexpr int PACK = ScanGeom<SPARSE>::PACK, GW = 32 / PACK;         // trajectories per warp, lanes per trajectory
+    constexpr unsigned GMASK = (GW == 32) ? FULL : ((1u << GW) - 1u);
+    static_assert(GW == CH, "a group's lanes are the rows of its chunk");
     extern __shared__ __align__(128) unsigned char scan_smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const long long traj = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (traj >= p.n) return;                                  // whole warp
-    unsigned char *wbase = scan_smem + wid * (CH * HB_SCAN_ROW + 16);
-    const double *row_ptr = (const double *)(wbase + (lane & (CH - 1)) * HB_SCAN_ROW);
-    const unsigned mbar = smem_u32(wbase + CH * HB_SCAN_ROW), row_u32 = smem_u32(row_ptr);
+    const int gl = lane & (GW - 1), gb = lane & ~(GW - 1);               // lane within its group, the group's first lane
+    const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (warp_id * PACK >= p.n) return;                        // whole warp
+    const long long traj_raw = warp_id * PACK + (lane / GW);
+    const bool traj_ok = traj_raw < p.n;                      // (an odd batch leaves the last warp's second half idle)
+    const long long traj = traj_ok ? traj_raw : p.n - 1;
+    unsigned char *wbase = scan_smem + wid * (32 * HB_SCAN_ROW + 16);
+    const double *row_ptr = (const double *)(wbase + lane * HB_SCAN_ROW);
+    const unsigned mbar = smem_u32(wbase + 32 * HB_SCAN_ROW), row_u32 = smem_u32(row_ptr);
     if (lane == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 32;" ::"r"(mbar) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -111,10 +121,10 @@ __global__ void __launch_bounds__(32 * HB_SCAN_WARPS, HB_SCAN_MINBLOCKS) k_step_
     const int *count = SPARSE ? p.nrec : p.nacc;        // records of this trajectory in the scratch
     // (sparse records: a trajectory has ~10 of them, so the count is read first -- requesting a full chunk blindly
     // would read 16 KB per trajectory, three times what is there)
-    int nacc = (HB_SCAN_PIPELINED && !SPARSE) ? p.rec_cap : min(count[traj], p.rec_cap);
+    int nacc = (HB_SCAN_PIPELINED && !SPARSE) ? p.rec_cap : (traj_ok ? min(count[traj], p.rec_cap) : 0);
     const double off = p.sink.sec.offset, tol_s = p.sink.sec.tol_on_surface;
     const int sdir = p.sink.sec.direction;
-    int ndesc = 0;                         // segments noted so far (warp-uniform)
+    int ndesc = 0;                         // segments noted so far (uniform within a group, like the carries below)
     int carry_c = 0;                       // first grid sample not owned yet
     int carry_step = 0;                    // record that owns sample carry_c - 1
     int carry_no = -1;                     // SPARSE: step number of the last record of the previous chunk
@@ -123,8 +133,8 @@ __global__ void __launch_bounds__(32 * HB_SCAN_WARPS, HB_SCAN_MINBLOCKS) k_step_
     double carry_t = te0;                  // t_eval[carry_c]
     // one 512-byte bulk copy per lane (the lane's own record of the chunk) or a plain arrival
     auto issue_chunk = [&](int b) {
-        const int sb = b + lane;
-        if (lane < CH && sb < nacc) {
+        const int sb = b + gl;
+        if (sb < nacc) {
             const double *src = p.rec + (traj * p.rec_cap + sb) * HB_REC_DOUBLES;
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(HB_SCAN_COPY)
                          : "memory");
@@ -142,13 +152,19 @@ __global__ void __launch_bounds__(32 * HB_SCAN_WARPS, HB_SCAN_MINBLOCKS) k_step_
         }
     };
 #if HB_SCAN_PIPELINED
-    issue_chunk(0);
-    nacc = min(count[traj], p.rec_cap);
-    if (nacc <= 0) mbar_wait(mbar, phase);                    // nothing to scan: let the requested rows land before exit
+    if (!SPARSE) {
+        issue_chunk(0);
+        nacc = min(count[traj], p.rec_cap);
+        if (nacc <= 0) mbar_wait(mbar, phase);                // nothing to scan: let the requested rows land before exit
+    } else {
+        issue_chunk(0);
+    }
 #endif
-    for (int base = 0; base < nacc; base += CH) {
-        const int s = base + lane;
-        const bool have_rec = lane < CH && s < nacc;
+    int nacc_max = nacc;                                      // the warp runs as many rounds as its longest trajectory needs
+    if (PACK > 1) nacc_max = max(nacc_max, __shfl_xor_sync(FULL, nacc_max, GW & 31));
+    for (int base = 0; base < nacc_max; base += CH) {
+        const int s = base + gl;
+        const bool have_rec = s < nacc;
         double hdr[11];
 #pragma unroll
         for (int i = 0; i < 11; ++i) hdr[i] = 0.0;
@@ -202,15 +218,15 @@ __global__ void __launch_bounds__(32 * HB_SCAN_WARPS, HB_SCAN_MINBLOCKS) k_step_
         // the rows are not read again in this round (the scan below runs on the headers in registers): the next
         // chunk's copies fly while this chunk is scanned
         __syncwarp();
-        if (base + CH < nacc) issue_chunk(base + CH);
+        if (base + CH < nacc_max) issue_chunk(base + CH);
 #endif
         int c0 = __shfl_up_sync(FULL, cend, 1);               // t_new of a step is t_old of the next, bit for bit
         double t_c0 = __shfl_up_sync(FULL, t_c, 1);                       // t_eval[c0]: the previous lane's t_eval[cend]
-        if (lane == 0) { c0 = carry_c; t_c0 = carry_t; }
+        if (gl == 0) { c0 = carry_c; t_c0 = carry_t; }
         bool adjacent = true;                                 // this record's step follows the previous record's step
         if (SPARSE) {
             int prev_no = __shfl_up_sync(FULL, step_no, 1);
-            if (lane == 0) prev_no = carry_no;
+            if (gl == 0) prev_no = carry_no;
             adjacent = step_no == prev_no + 1;
             if (!adjacent) { c0 = own_c0; t_c0 = own_t_c0; }  // island start (or the trajectory's first step: c0 = 0)
         }
@@ -227,23 +243,25 @@ __global__ void __launch_bounds__(32 * HB_SCAN_WARPS, HB_SCAN_MINBLOCKS) k_step_
                 B = (nown >= 3) ? g_comp<AR>(hdr, xpar_by<AR>(t_cm2, hdr[0], hdr[2], inv_h), off) : g_first;
             }
         }
-        const unsigned own_mask = __ballot_sync(FULL, owns);
-        const unsigned two_mask = __ballot_sync(FULL, nown >= 2);
+        // (masks and lane numbers below are relative to the lane's group)
+        const unsigned own_mask = (__ballot_sync(FULL, owns) >> gb) & GMASK;
+        const unsigned two_mask = (__ballot_sync(FULL, nown >= 2) >> gb) & GMASK;
         // nearest owner below this lane (q) and below that (q2): they hold samples c0 - 1 and (maybe) c0 - 2
-        const unsigned below = own_mask & ((1u << lane) - 1u);
+        const unsigned below = own_mask & ((1u << gl) - 1u);
         const int q = below ? 31 - __clz(below) : -1;
         const unsigned below2 = (q >= 0) ? (own_mask & ((1u << q) - 1u)) : 0u;
         const int q2 = below2 ? 31 - __clz(below2) : -1;
-        const double Aq = shfl_d(A, q >= 0 ? q : 0), Bq = shfl_d(B, q >= 0 ? q : 0), Aq2 = shfl_d(A, q2 >= 0 ? q2 : 0);
+        const double Aq = shfl_d(A, gb + (q >= 0 ? q : 0)), Bq = shfl_d(B, gb + (q >= 0 ? q : 0)),
+                     Aq2 = shfl_d(A, gb + (q2 >= 0 ? q2 : 0));
         const double g_prev = (q >= 0) ? Aq : carry1;
         const double gm2 = (q >= 0) ? (((two_mask >> q) & 1u) ? Bq : (q2 >= 0 ? Aq2 : carry1)) : carry2;
         const int s_prev = (q >= 0) ? base + q : carry_step;
         bool scan = false;
         {                                                     // the segment that ends at this step's first sample
             const bool flag = owns && c0 > 0 && adjacent && segment_may_hit(sdir, g_prev, g_first, tol_s);
-            const unsigned fm = __ballot_sync(FULL, flag);
+            const unsigned fm = (__ballot_sync(FULL, flag) >> gb) & GMASK;
             if (flag)
-                store_segment(p, traj, ndesc + __popc(fm & ((1u << lane) - 1u)), c0, traj * p.rec_cap + s_prev,
+                store_segment(p, traj, ndesc + __popc(fm & ((1u << gl) - 1u)), c0, traj * p.rec_cap + s_prev,
                               traj * p.rec_cap + s, g_prev, g_first, c0 > 1 ? gm2 : 0.0);
             ndesc += __popc(fm);
         }
@@ -272,7 +290,9 @@ __global__ void __launch_bounds__(32 * HB_SCAN_WARPS, HB_SCAN_MINBLOCKS) k_step_
             const int b0 = __shfl_sync(FULL, c0, L), b1 = __shfl_sync(FULL, cend, L);
             double c1 = shfl_d(g_first, L), c2 = shfl_d(g_prev, L);
             const double binv = shfl_d(inv_h, L);
-            const int sL = base + L;
+            const int sL = base + (L & (GW - 1));
+            const long long trajL = __shfl_sync(FULL, traj, L);      // (the whole warp scans: L may be in the other group)
+            int ndL = __shfl_sync(FULL, ndesc, L);
             double tq_next = p.t_eval[min(b0 + 1 + lane, b1 - 1)];
             for (int b = b0 + 1; b < b1; b += 32) {
                 const int cs = b + lane;
@@ -287,32 +307,41 @@ __global__ void __launch_bounds__(32 * HB_SCAN_WARPS, HB_SCAN_MINBLOCKS) k_step_
                 const bool flagged = valid && segment_may_hit(sdir, g_m1, g, tol_s);
                 const unsigned fm = __ballot_sync(FULL, flagged);
                 if (flagged)
-                    store_segment(p, traj, ndesc + __popc(fm & ((1u << lane) - 1u)), cs, traj * p.rec_cap + sL,
-                                  traj * p.rec_cap + sL, g_m1, g, g_m2);
-                ndesc += __popc(fm);
+                    store_segment(p, trajL, ndL + __popc(fm & ((1u << lane) - 1u)), cs, trajL * p.rec_cap + sL,
+                                  trajL * p.rec_cap + sL, g_m1, g, g_m2);
+                ndL += __popc(fm);
                 const int nvalid = min(32, b1 - b);
                 const double l1 = shfl_d(g, nvalid - 1);
                 const double l2 = shfl_d(g, nvalid >= 2 ? nvalid - 2 : 0);
                 c2 = (nvalid >= 2) ? l2 : c1;
                 c1 = l1;
             }
+            if ((L & ~(GW - 1)) == gb) ndesc = ndL;            // the owner's group keeps its segment count
         }
-        // carries for the next chunk
-        if (own_mask) {
-            const int qL = 31 - __clz(own_mask);
+        // carries for the next chunk (per group; the shuffles run for every lane)
+        {
+            const int qL = own_mask ? 31 - __clz(own_mask) : 0;
             const unsigned bl = own_mask & ((1u << qL) - 1u);
             const int qL2 = bl ? 31 - __clz(bl) : -1;
-            const double a = shfl_d(A, qL), b = shfl_d(B, qL), a2 = shfl_d(A, qL2 >= 0 ? qL2 : 0);
-            carry2 = ((two_mask >> qL) & 1u) ? b : (qL2 >= 0 ? a2 : carry1);
-            carry1 = a;
-            carry_step = base + qL;
+            const double a = shfl_d(A, gb + qL), b = shfl_d(B, gb + qL), a2 = shfl_d(A, gb + (qL2 >= 0 ? qL2 : 0));
+            if (own_mask) {
+                carry2 = ((two_mask >> qL) & 1u) ? b : (qL2 >= 0 ? a2 : carry1);
+                carry1 = a;
+                carry_step = base + qL;
+            }
         }
-        carry_c = __shfl_sync(FULL, cend, CH - 1);
-        carry_t = shfl_d(t_c, CH - 1);
-        if (SPARSE) carry_no = __shfl_sync(FULL, step_no, CH - 1);
+        {
+            const int cl = __shfl_sync(FULL, cend, gb + CH - 1);
+            const double tl = shfl_d(t_c, gb + CH - 1);
+            const int nl = __shfl_sync(FULL, step_no, gb + CH - 1);
+            if (base + CH <= nacc) {                          // (a group whose records ran out keeps its carries: unused)
+                carry_c = cl; carry_t = tl;
+                if (SPARSE) carry_no = nl;
+            }
+        }
         __syncwarp();                                         // every lane is done with its row before the next copy
     }
-    if (lane == 0) p.desc_count[traj] = ndesc;
+    if (gl == 0 && traj_ok) p.desc_count[traj] = ndesc;
 }
 
 // Compact index of all noted segments (so that k_emit_candidates runs full warps): one thread per trajectory, two
@@ -665,7 +694,8 @@ extern "C" int hb_cr3bp_section2(const hb_cr3bp *sys, const hb_integ *integ, con
     p.sink.sec = *sec; p.sink.hits = hits; p.sink.capacity = hit_capacity; p.sink.ws = (HbWorkspace *)workspace;
     p.hits_per_traj = hits_per_traj;
     p.cand_count = cand_count; p.cand = cand; p.desc_count = desc_count; p.desc = desc; p.desc_total = desc_total; p.desc_index = desc_index;
-    const long long b1 = (n + HB_SCAN_WARPS - 1) / HB_SCAN_WARPS;      // one warp per trajectory
+    const int per_block = HB_SCAN_WARPS * (sparse ? ScanGeom<true>::PACK : 1);   // trajectories per block (warp or half-warp each)
+    const long long b1 = (n + per_block - 1) / per_block;
     if (b1 > 2147483647LL) return HB_ERR_BADARG;
     rc = (integ->arith == HB_ARITH_PARITY) ? launch_scan<ArParity>(p, (unsigned)b1, st) : launch_scan<ArFast>(p, (unsigned)b1, st);
     if (rc != HB_OK) return rc;
