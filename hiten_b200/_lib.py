@@ -139,6 +139,8 @@ SIGNATURES = {
                                      C.c_int32, vp, vp, vp, C.c_int64, vp, vp, vp]),
     "hb_synodic_detect": (C.c_int, [C.POINTER(HbSection), C.c_int64, vp, vp, vp, C.c_int32, C.c_int32, vp, C.c_int64,
                                     vp, vp, vp]),
+    "hb_synodic_detect_cubic": (C.c_int, [C.POINTER(HbSection), C.c_int32, C.c_int64, vp, vp, vp, C.c_int32, C.c_int32, vp,
+                                          C.c_int64, vp, vp, vp]),
     "hb_read_hit_count": (C.c_int, [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), vp]),
     "hb_read_record_overflow": (C.c_int, [vp, C.POINTER(C.c_int64), vp]),
     "hb_selftest_arith": (C.c_int, [vp, vp, C.c_int64, vp, vp, vp, vp, vp, vp]),

@@ -117,6 +117,167 @@ HB_DEV bool process_segment(const HitSink &p, Dedup &dd, long long traj, int lan
     return true;
 }
 
+// ---- the CUBIC branch of the detector (interp_kind == "cubic") --------------------------------------------------------
+// Reference: backend.py _detect_with_segment_refine :541-553 (slopes of g from the neighbouring samples), :584-631 (Hermite g
+// on the sub-intervals, Newton on the cubic clamped to the sub-interval), :627-645 (cubic Hermite hit state),
+// _refine_hits_cubic :274-379 (segment_refine == 0: Newton clamped to [0, 1]); poincare/utils.py _hermite_scalar :54-98,
+// _hermite_der :101-148.  _hermite_* are Numba functions, where `x ** 2` with a literal exponent is x * x; the weights of the
+// hit state are plain Python floats, where `x ** 2` is libm pow(x, 2.0) (hb_pow_libm restates glibc's pow bit for bit).
+// Every cubic formula is guarded by `dt > 0.0` in the reference, so a trajectory with decreasing times (a backward tube)
+// gets the linear formulas -- reproduced.
+HB_DEV double hb_sq_rn(double x) { return __dmul_rn(x, x); }
+HB_DEV double hermite_scalar(double s, double y0, double y1, double dy0, double dy1, double dt)
+{
+    const double oms = __dsub_rn(1.0, s);
+    const double h00 = __dmul_rn(__dadd_rn(1.0, __dmul_rn(2.0, s)), hb_sq_rn(oms));
+    const double h10 = __dmul_rn(s, hb_sq_rn(oms));
+    const double h01 = __dmul_rn(hb_sq_rn(s), __dsub_rn(3.0, __dmul_rn(2.0, s)));
+    const double h11 = __dmul_rn(hb_sq_rn(s), __dsub_rn(s, 1.0));
+    return __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(h00, y0), __dmul_rn(__dmul_rn(h10, dy0), dt)), __dmul_rn(h01, y1)),
+                     __dmul_rn(__dmul_rn(h11, dy1), dt));
+}
+HB_DEV double hermite_der(double s, double y0, double y1, double dy0, double dy1, double dt)
+{
+    const double oms = __dsub_rn(1.0, s), sm1 = __dsub_rn(s, 1.0), two_s = __dmul_rn(2.0, s), six_s = __dmul_rn(6.0, s);
+    const double dh00 = __dsub_rn(__dadd_rn(__dmul_rn(six_s, sm1), __dmul_rn(hb_sq_rn(oms), 2.0)),
+                                  __dmul_rn(__dmul_rn(2.0, oms), __dadd_rn(1.0, two_s)));
+    const double dh10 = __dadd_rn(hb_sq_rn(oms), __dmul_rn(s, __dmul_rn(2.0, sm1)));
+    const double dh01 = __dsub_rn(__dmul_rn(six_s, oms), __dmul_rn(two_s, __dsub_rn(3.0, two_s)));
+    const double dh11 = __dadd_rn(__dmul_rn(two_s, sm1), hb_sq_rn(s));
+    return __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(dh00, y0), __dmul_rn(__dmul_rn(dh10, dy0), dt)), __dmul_rn(dh01, y1)),
+                     __dmul_rn(__dmul_rn(dh11, dy1), dt));
+}
+// CPython float ** 2 (float_pow: shortcuts for a base of 1 and 0, libm pow otherwise)
+HB_DEV double hb_py_sq(double x)
+{
+    if (x == 1.0) return 1.0;
+    if (x == 0.0) return 0.0;
+    return hb_pow_libm(x, 2.0);
+}
+// hit state at s on segment k (backend.py:627-645): cubic Hermite through samples k-1 .. k+2 when they exist
+HB_DEV void cubic_hit_state(const double *T, const double *X, int m, int k, double s, double dt, double (&xh)[6])
+{
+    const double *x0 = X + (long long)k * 6, *x1 = x0 + 6;
+    if (dt > 0.0 && k - 1 >= 0 && k + 2 < m) {
+        const double *xm = x0 - 6, *xp = x0 + 12;
+        const double dtm = __dsub_rn(T[k + 1], T[k - 1]), dtp = __dsub_rn(T[k + 2], T[k]);
+        const double oms = __dsub_rn(1.0, s);
+        const double h00 = __dmul_rn(__dadd_rn(1.0, __dmul_rn(2.0, s)), hb_py_sq(oms));
+        const double h10 = __dmul_rn(s, hb_py_sq(oms));
+        const double h01 = __dmul_rn(hb_py_sq(s), __dsub_rn(3.0, __dmul_rn(2.0, s)));
+        const double h11 = __dmul_rn(hb_py_sq(s), __dsub_rn(s, 1.0));
+#pragma unroll
+        for (int d = 0; d < 6; ++d) {
+            const double dx0 = __ddiv_rn(__dsub_rn(x1[d], xm[d]), dtm), dx1 = __ddiv_rn(__dsub_rn(xp[d], x0[d]), dtp);
+            xh[d] = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(h00, x0[d]), __dmul_rn(__dmul_rn(h10, dx0), dt)),
+                                        __dmul_rn(h01, x1[d])), __dmul_rn(__dmul_rn(h11, dx1), dt));
+        }
+    } else {
+#pragma unroll
+        for (int d = 0; d < 6; ++d) xh[d] = __dadd_rn(x0[d], __dmul_rn(s, __dsub_rn(x1[d], x0[d])));
+    }
+}
+
+// Per-segment logic of the cubic request, executed warp-uniformly (every lane the same segment k of samples T / X).
+HB_DEV bool process_segment_cubic(const HitSink &p, Dedup &dd, long long traj, int lane, int k, int m, const double *T,
+                                  const double *X, int newton_max_iter)
+{
+    const int dir = p.sec.direction, ci = p.sec.idx;
+    const double off = p.sec.offset;
+    const double t0 = T[k], t1 = T[k + 1], dt = __dsub_rn(t1, t0);
+    const double gk = __dsub_rn(X[(long long)k * 6 + ci], off), gk1 = __dsub_rn(X[(long long)(k + 1) * 6 + ci], off);
+    const bool has_prev = k - 1 >= 0;
+    const double g_prev = has_prev ? __dsub_rn(X[(long long)(k - 1) * 6 + ci], off) : 0.0;
+    const bool cubic = dt > 0.0;
+    double d0 = 0.0, d1 = 0.0;
+    if (cubic) {
+        d0 = has_prev ? __ddiv_rn(__dsub_rn(gk1, g_prev), __dsub_rn(t1, T[k - 1])) : __ddiv_rn(__dsub_rn(gk1, gk), dt);
+        d1 = (k + 2 < m) ? __ddiv_rn(__dsub_rn(__dsub_rn(X[(long long)(k + 2) * 6 + ci], off), gk), __dsub_rn(T[k + 2], t0))
+                         : __ddiv_rn(__dsub_rn(gk1, gk), dt);
+    }
+    bool accept_left = false;
+    if (fabs(gk) < p.sec.tol_on_surface) {
+        if (dir == 0) accept_left = true;
+        else if (dir > 0) accept_left = (gk1 >= 0.0) || (has_prev && g_prev <= 0.0);
+        else accept_left = (gk1 <= 0.0) || (has_prev && g_prev >= 0.0);
+    }
+    const int r = p.sec.segment_refine;
+    double xh[6];
+    if (r > 0) {
+        if (accept_left) {
+#pragma unroll
+            for (int d = 0; d < 6; ++d) xh[d] = X[(long long)k * 6 + d];
+            if (!push_hit(p, dd, traj, t0, xh, lane)) return false;
+        }
+        const double step = __ddiv_rn(1.0, (double)(r + 1));
+        for (int mm = 0; mm <= r; ++mm) {
+            const double s_lo = __dmul_rn((double)mm, step), s_hi = __dmul_rn((double)(mm + 1), step);
+            if (s_hi > 1.0 + 1e-15) break;
+            if (accept_left && mm == 0) continue;
+            double g_lo, g_hi;
+            if (cubic) {
+                g_lo = hermite_scalar(s_lo, gk, gk1, d0, d1, dt);
+                g_hi = hermite_scalar(s_hi, gk, gk1, d0, d1, dt);
+            } else {
+                g_lo = __dadd_rn(__dmul_rn(__dsub_rn(1.0, s_lo), gk), __dmul_rn(s_lo, gk1));
+                g_hi = __dadd_rn(__dmul_rn(__dsub_rn(1.0, s_hi), gk), __dmul_rn(s_hi, gk1));
+            }
+            bool crosses;
+            if (dir == 0) crosses = (__dmul_rn(g_lo, g_hi) <= 0.0) && (g_lo != g_hi);
+            else if (dir > 0) crosses = (g_lo < 0.0) && (g_hi >= 0.0);
+            else crosses = (g_lo > 0.0) && (g_hi <= 0.0);
+            if (!crosses) continue;
+            double s_star;
+            if (g_lo == g_hi) s_star = __dmul_rn(0.5, __dadd_rn(s_lo, s_hi));
+            else {
+                double al = __ddiv_rn(g_lo, __dsub_rn(g_lo, g_hi));
+                al = fmin(1.0, fmax(0.0, al));
+                s_star = __dadd_rn(s_lo, __dmul_rn(al, __dsub_rn(s_hi, s_lo)));
+            }
+            if (cubic) {
+                for (int it = 0; it < newton_max_iter; ++it) {
+                    const double f = hermite_scalar(s_star, gk, gk1, d0, d1, dt);
+                    const double df = hermite_der(s_star, gk, gk1, d0, d1, dt);
+                    if (df == 0.0) break;
+                    s_star = __dsub_rn(s_star, __ddiv_rn(f, df));
+                    if (s_star < s_lo) { s_star = s_lo; break; }
+                    if (s_star > s_hi) { s_star = s_hi; break; }
+                }
+            }
+            const double th = __dadd_rn(__dmul_rn(__dsub_rn(1.0, s_star), t0), __dmul_rn(s_star, t1));
+            cubic_hit_state(T, X, m, k, s_star, dt, xh);
+            if (!push_hit(p, dd, traj, th, xh, lane)) return false;
+        }
+    } else {
+        if (accept_left) {
+#pragma unroll
+            for (int d = 0; d < 6; ++d) xh[d] = X[(long long)k * 6 + d];
+            return push_hit(p, dd, traj, t0, xh, lane);
+        }
+        bool crosses;
+        if (dir == 0) crosses = (__dmul_rn(gk, gk1) <= 0.0) && (gk != gk1);
+        else if (dir > 0) crosses = (gk < 0.0) && (gk1 >= 0.0);
+        else crosses = (gk > 0.0) && (gk1 <= 0.0);
+        if (!crosses) return true;
+        double s_star = __ddiv_rn(gk, __dsub_rn(gk, gk1));
+        s_star = fmin(1.0, fmax(0.0, s_star));
+        if (cubic) {
+            for (int it = 0; it < newton_max_iter; ++it) {
+                const double f = hermite_scalar(s_star, gk, gk1, d0, d1, dt);
+                const double df = hermite_der(s_star, gk, gk1, d0, d1, dt);
+                if (df == 0.0) break;
+                s_star = __dsub_rn(s_star, __ddiv_rn(f, df));
+                if (s_star < 0.0) { s_star = 0.0; break; }
+                if (s_star > 1.0) { s_star = 1.0; break; }
+            }
+        }
+        const double th = __dadd_rn(__dmul_rn(__dsub_rn(1.0, s_star), t0), __dmul_rn(s_star, t1));
+        cubic_hit_state(T, X, m, k, s_star, dt, xh);
+        return push_hit(p, dd, traj, th, xh, lane);
+    }
+    return true;
+}
+
 
 // Warp-cooperative form of process_segment for the fused section kernel: every lane calls it with the SAME
 // (broadcast) segment values; the r+1 sub-intervals of _detect_with_segment_refine are tested 32 at a time

@@ -21,8 +21,7 @@ No reference file is edited.  What is rebound (paths relative to hiten/):
   * the `_ham` branches of the three RK classes above for the reference's bare `_HamiltonianSystem` (grid with
     derivatives, plane events).
 Anything the GPU path cannot express (user-defined RHS or event callables, a `_DirectedSystem` around a Hamiltonian
-system in the RK classes -- which raises inside the reference --, 42-state RK45 / fixed-step integration, cubic synodic
-refinement) is handed to the reference's ORIGINAL function -- that is the reference's
+system in the RK classes -- which raises inside the reference --, 42-state RK45 / fixed-step integration) is handed to the reference's ORIGINAL function -- that is the reference's
 own code for inputs outside this path, not a fallback of the kernels: for recognised inputs a missing library
 or GPU raises.
 """
@@ -445,9 +444,9 @@ def _make_synodic_run(orig):
         nz = np.nonzero(normal)[0]
         trajs = list(request.trajectories)
         one_hot = normal.size == 6 and nz.size == 1 and normal[nz[0]] == 1.0
-        linear = request.interp_kind != "cubic"        # the reference's own test (backend.py:762)
+        cubic = request.interp_kind == "cubic"         # the reference's own test (backend.py:762)
         names_ok = all(isinstance(c, str) and c.lower() in _syn.IDX for c in request.plane_coords)
-        if not (one_hot and linear and names_ok) or any(np.asarray(s).shape[1] != 6 for _, s in trajs if len(s)):
+        if not (one_hot and names_ok) or any(np.asarray(s).shape[1] != 6 for _, s in trajs if len(s)):
             return orig(self, request)
         sec = _syn.make_section(int(nz[0]), float(request.offset), request.plane_coords, request.direction,
                                 int(request.segment_refine), request.tol_on_surface, request.dedup_time_tol,
@@ -460,7 +459,8 @@ def _make_synodic_run(orig):
             states = np.concatenate([np.asarray(trajs[k][1], dtype=np.float64).reshape(-1, 6) for k in range(n)])
             times = np.concatenate([np.asarray(trajs[k][0], dtype=np.float64).ravel() for k in range(n)])
             off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
-            got = _syn.detect(states, times, sec, offsets=off)
+            got = _syn.detect(states, times, sec, offsets=off, interp_kind="cubic" if cubic else "linear",
+                              newton_max_iter=int(request.newton_max_iter))
             for k, t, s, p in zip(got.trajectory_indices, got.times, got.states, got.points):
                 hits[int(k)].append(_SectionHit(time=float(t), state=s.copy(), point2d=p.copy(),
                                                 trajectory_index=idxs[int(k)]))

@@ -37,12 +37,17 @@ def make_section(section_axis="x", section_offset=0.0, plane_coords=("y", "vy"),
                        float(tol_on_surface), float(dedup_time_tol), float(dedup_point_tol))
 
 
-def detect(states, times, section, *, offsets=None, hit_capacity=None, device=None, stream=None, ws=None):
+def detect(states, times, section, *, offsets=None, hit_capacity=None, device=None, stream=None, ws=None,
+           interp_kind="linear", newton_max_iter=4):
     """Detect section hits.
 
     states : CUDA tensor / ndarray [N, m, 6] (uniform) or [sum m_i, 6] with `offsets` [N + 1];
     times  : [m] shared signed times, [N, m], or concatenated [sum m_i].
+    interp_kind : "linear" (what the shipped SynodicMap always requests) or "cubic" with `newton_max_iter` Newton steps
+    (backend.py:695-701, 762; hb_synodic_detect_cubic).
     """
+    if interp_kind not in ("linear", "cubic"):
+        raise ValueError("interp_kind must be 'linear' or 'cubic'")
     _require_cuda()
     lib = L.load()
     device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -68,9 +73,12 @@ def detect(states, times, section, *, offsets=None, hit_capacity=None, device=No
         while True:
             hits = torch.empty(cap * 9, dtype=torch.float64, device=device)      # 72-byte records
             per = torch.empty(max(n, 1), dtype=torch.int32, device=device)
-            rc = lib.hb_synodic_detect(section, n, st.data_ptr(), tm.data_ptr(),
-                                       None if off_t is None else off_t.data_ptr(), m, shared, hits.data_ptr(), cap,
-                                       per.data_ptr(), ws.data_ptr(), _stream_ptr(stream))
+            tail = (n, st.data_ptr(), tm.data_ptr(), None if off_t is None else off_t.data_ptr(), m, shared,
+                    hits.data_ptr(), cap, per.data_ptr(), ws.data_ptr(), _stream_ptr(stream))
+            if interp_kind == "cubic":
+                rc = lib.hb_synodic_detect_cubic(section, int(newton_max_iter), *tail)
+            else:
+                rc = lib.hb_synodic_detect(section, *tail)
             L.check(rc, "hb_synodic_detect")
             nh, no = L.C.c_int64(0), L.C.c_int64(0)
             L.check(lib.hb_read_hit_count(ws.data_ptr(), L.C.byref(nh), L.C.byref(no), _stream_ptr(stream)),

@@ -486,6 +486,15 @@ int hb_synodic_detect(const hb_section *sec, int64_t n_traj, const double *state
                       const int64_t *offsets, int32_t m_uniform, int32_t times_shared, hb_hit *hits,
                       int64_t hit_capacity, int32_t *hits_per_traj, void *workspace, void *stream);
 
+/* The same call for a request with interp_kind == "cubic" (backend.py:762): cubic Hermite g through the neighbouring
+ * samples on the segment_refine + 1 sub-intervals, `newton_max_iter` Newton steps on the cubic clamped to the
+ * sub-interval, cubic Hermite hit state (_detect_with_segment_refine :541-645; segment_refine == 0: _refine_hits_cubic
+ * :274-379; poincare/utils.py _hermite_scalar / _hermite_der :54-148).  Where the reference's own `dt > 0.0` guards
+ * fail (decreasing times: a backward tube) it computes the linear formulas, and so does this.  Bit-identical hits. */
+int hb_synodic_detect_cubic(const hb_section *sec, int32_t newton_max_iter, int64_t n_traj, const double *states,
+                            const double *times, const int64_t *offsets, int32_t m_uniform, int32_t times_shared,
+                            hb_hit *hits, int64_t hit_capacity, int32_t *hits_per_traj, void *workspace, void *stream);
+
 /* Hit / overflow counters of the last call that used `workspace` (synchronises `stream`). */
 int hb_read_hit_count(const void *workspace, int64_t *n_hits, int64_t *n_overflow, void *stream);
 

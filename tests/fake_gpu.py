@@ -53,8 +53,9 @@ def cr3bp_event(y0, mu, tmax, event_idx, *, event_offset=0.0, direction=0, xtol=
     return BatchResult(yf, np.zeros(len(y0), np.int32), np.zeros(len(y0), np.int32), st, t_hit=th)
 
 
-def detect(states, times, section, *, offsets=None, **kw):
+def detect(states, times, section, *, offsets=None, interp_kind="linear", newton_max_iter=4, **kw):
     states, times = np.asarray(states), np.asarray(times)
+    cubic = interp_kind == "cubic"
     if offsets is None:
         n, m = states.shape[:2]
         offsets = np.arange(n + 1) * m
@@ -65,9 +66,11 @@ def detect(states, times, section, *, offsets=None, **kw):
     per = np.zeros(len(offsets) - 1, np.int32)
     for k in range(len(offsets) - 1):
         a, b = offsets[k], offsets[k + 1]
-        t, x = O.synodic_detect(times[a:b], states[a:b], section.idx, section.offset, section.direction,
-                                (section.proj_i, section.proj_j), section.segment_refine, section.tol_on_surface,
-                                section.dedup_time_tol, section.dedup_point_tol, section.max_hits_per_traj, cap=256)
+        args = (times[a:b], states[a:b], section.idx, section.offset, section.direction,
+                (section.proj_i, section.proj_j), section.segment_refine, section.tol_on_surface,
+                section.dedup_time_tol, section.dedup_point_tol, section.max_hits_per_traj)
+        t, x = (O.synodic_detect_cubic(*args, newton_max_iter=newton_max_iter, cap=256) if cubic
+                else O.synodic_detect(*args, cap=256))
         per[k] = len(t)
         ti += [k] * len(t); tt += list(t); ss += list(x)
     ss = np.array(ss).reshape(-1, 6)

@@ -169,6 +169,23 @@ def synodic_detect(times, states, idx, offset=0.0, direction=0, proj=(0, 2), seg
     return ht[:k].copy(), hs[:k].copy()
 
 
+def synodic_detect_cubic(times, states, idx, offset=0.0, direction=0, proj=(0, 2), segment_refine=50,
+                         tol_on_surface=1e-6, dedup_time_tol=1e-9, dedup_point_tol=1e-6, max_hits=0, newton_max_iter=4,
+                         cap=64):
+    """The same with interp_kind="cubic" (backend.py:274-379, 541-645)."""
+    times = np.ascontiguousarray(times, dtype=np.float64)
+    states = np.ascontiguousarray(states, dtype=np.float64)
+    m, dim = states.shape
+    ht = np.empty(cap)
+    hs = np.empty((cap, dim))
+    lib().ho_synodic_detect_cubic.restype = C.c_int
+    k = lib().ho_synodic_detect_cubic(_p(times), _p(states), m, dim, int(idx), C.c_double(offset), int(direction),
+                                      int(proj[0]), int(proj[1]), int(segment_refine), C.c_double(tol_on_surface),
+                                      C.c_double(dedup_time_tol), C.c_double(dedup_point_tol), int(max_hits),
+                                      int(newton_max_iter), _p(ht), _p(hs), cap)
+    return ht[:k].copy(), hs[:k].copy()
+
+
 class HoPolyHam(C.Structure):
     _fields_ = [("n_dof", C.c_int), ("max_deg", C.c_int), ("ptr", C.c_int64 * 7), ("deg", C.c_void_p),
                 ("coef", C.c_void_p), ("exp", C.c_void_p)]

@@ -458,3 +458,37 @@ def test_centre_manifold_seeding_is_batched_and_identical(ref, monkeypatch):
         assert n_default <= 20 < n_more <= 64
     finally:
         hiten_b200.uninstall()
+
+
+def test_cubic_synodic_request_goes_through_the_drop_in(ref, monkeypatch):
+    """A request with interp_kind="cubic" (backend.py:762; never issued by the shipped SynodicMap) is served by the
+    rebound backend too: same hits as the reference's own cubic branch, bit for bit."""
+    import fake_gpu
+    import hiten_b200
+    import oracle_lib as O
+    from hiten.algorithms.poincare.synodic.backend import _SynodicDetectionBackend
+    from hiten.algorithms.poincare.synodic.types import SynodicBackendRequest
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "synodic_cubic.npz"))
+    tf, steps, fwd = float(g["l2_tf"]), int(g["l2_steps"]), int(g["l2_forward"])
+    t_eval = np.linspace(0.0, tf, steps)
+    dense, _ = O.batch_dense(O.system(O.SYS_CR3BP6, 0.012154535289174722, fwd=fwd, flip=(0, 6)), O.DOP853,
+                             O.default_tol(), g["l2_x0W"][:6], t_eval, 4)
+    normal = np.zeros(6); normal[1] = 1.0
+    import dataclasses
+    fields = {f.name for f in dataclasses.fields(SynodicBackendRequest)}
+    kw = dict(trajectories=[(fwd * t_eval, d) for d in dense], trajectory_indices=list(range(len(dense))), normal=normal,
+              offset=0.0, plane_coords=("x", "z"), interp_kind="cubic", segment_refine=50, tol_on_surface=1e-6,
+              dedup_time_tol=1e-9, dedup_point_tol=1e-6, max_hits_per_traj=None, newton_max_iter=10, direction=-1)
+    req = SynodicBackendRequest(**{k: v for k, v in kw.items() if k in fields})
+    want = _SynodicDetectionBackend().run(req)
+    hiten_b200.install()
+    fake_gpu.patch(monkeypatch)
+    try:
+        got = _SynodicDetectionBackend().run(req)
+    finally:
+        hiten_b200.uninstall()
+    assert len(want.times) > 0 and np.array_equal(got.times, want.times)
+    assert np.array_equal(got.states, want.states) and np.array_equal(got.points, want.points)
+    assert np.array_equal(got.trajectory_indices, want.trajectory_indices)
+    sel = g["l2_r50_dm_traj"] < 6
+    assert np.array_equal(got.times, g["l2_r50_dm_time"][sel]) and np.array_equal(got.states, g["l2_r50_dm_state"][sel])

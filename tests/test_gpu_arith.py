@@ -49,3 +49,28 @@ def test_pow_matches_libm_bit_for_bit():
     ulp = np.abs(got - ref) / np.spacing(ref)
     print(f"[parity] pow vs libm: exact {np.mean(ulp == 0):.6f}, max {ulp.max():.1f} ulp")
     assert np.array_equal(got, ref)
+
+
+def test_pow_squares_match_python_float_pow():
+    """`x ** 2` on Python floats (the weights of the cubic detector's hit state, backend.py:632-635) is libm pow(x, 2.0):
+    the device restatement must give the same bits for arguments in (0, 1], tiny ones included."""
+    import math
+    import torch
+    from hiten_b200 import _lib as L
+    lib = L.load()
+    rng = np.random.default_rng(9)
+    n = 300_000
+    x = np.concatenate([rng.uniform(0.0, 1.0, n // 2), 10.0 ** rng.uniform(-17, 0, n // 4),
+                        1.0 - 10.0 ** rng.uniform(-17, -1, n - n // 2 - n // 4)])
+    x = x[(x > 0.0) & (x < 1.0)]
+    n = len(x)
+    y = np.full(n, 2.0)
+    ty, tx = torch.from_numpy(y).cuda(), torch.from_numpy(x).cuda()
+    outs = [torch.empty(n, dtype=torch.float64, device="cuda") for _ in range(5)]
+    L.check(lib.hb_selftest_arith(ty.data_ptr(), tx.data_ptr(), n, *[o.data_ptr() for o in outs],
+                                  L.vp(torch.cuda.current_stream().cuda_stream)), "hb_selftest_arith")
+    got = outs[4].cpu().numpy()
+    ref = np.array([v ** 2 for v in x.tolist()])
+    assert np.array_equal(ref, np.array([math.pow(v, 2.0) for v in x.tolist()]))
+    print(f"[parity] pow(x, 2) vs libm: exact {np.mean(got == ref):.6f}; libm == x*x on {np.mean(ref == x * x):.6f}")
+    assert np.array_equal(got, ref)

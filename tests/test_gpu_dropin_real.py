@@ -313,3 +313,34 @@ def test_c3_1e5_seeds_through_the_public_api(ref, cm):
     ok = flags[pick].astype(bool)
     assert np.array_equal(np.asarray(resp.states)[rows[pick][ok]], np.asarray(want.states))
     assert np.array_equal(np.asarray(resp.times)[rows[pick][ok]], np.asarray(want.times))
+
+
+def test_cubic_synodic_request_through_the_rebound_backend(ref):
+    """interp_kind="cubic" (backend.py:762) is served by hb_synodic_detect_cubic under install(): the rebound
+    _SynodicDetectionBackend.run returns the hits of the reference's own cubic branch bit for bit (golden
+    synodic_cubic.npz and the unpatched backend run in this process)."""
+    import dataclasses
+    import hiten_b200
+    from hiten.algorithms.poincare.synodic.backend import _SynodicDetectionBackend
+    from hiten.algorithms.poincare.synodic.types import SynodicBackendRequest
+    g = G("synodic_cubic.npz")
+    tf, steps, fwd = float(g["l2_tf"]), int(g["l2_steps"]), int(g["l2_forward"])
+    t_eval = np.linspace(0.0, tf, steps)
+    dense = hiten_b200.cr3bp_dense(g["l2_x0W"], float(ref.mu), t_eval, forward=fwd, flip=(0, 6)).states
+    normal = np.zeros(6); normal[1] = 1.0
+    fields = {f.name for f in dataclasses.fields(SynodicBackendRequest)}
+    kw = dict(trajectories=[(fwd * t_eval, d) for d in dense], trajectory_indices=list(range(len(dense))), normal=normal,
+              offset=0.0, plane_coords=("x", "z"), interp_kind="cubic", segment_refine=50, tol_on_surface=1e-6,
+              dedup_time_tol=1e-9, dedup_point_tol=1e-6, max_hits_per_traj=None, newton_max_iter=10, direction=-1)
+    req = SynodicBackendRequest(**{k: v for k, v in kw.items() if k in fields})
+    assert not hiten_b200.dropin.is_installed()
+    want = _SynodicDetectionBackend().run(req)
+    hiten_b200.install()
+    try:
+        got = _SynodicDetectionBackend().run(req)
+    finally:
+        hiten_b200.uninstall()
+    assert _library_loaded() and len(want.times) == 72
+    assert np.array_equal(got.times, want.times) and np.array_equal(got.states, want.states)
+    assert np.array_equal(got.points, want.points) and np.array_equal(got.trajectory_indices, want.trajectory_indices)
+    assert np.array_equal(got.times, g["l2_r50_dm_time"]) and np.array_equal(got.states, g["l2_r50_dm_state"])
