@@ -1,4 +1,4 @@
-// hb_stm.cu -- batched 42-dimensional state + STM (variational) propagation with DOP853.
+// hb_stm.cu -- batched 42-dimensional state + STM (variational) propagation: DOP853 (tuned), RK45 and fixed-step RK4/6/8.
 //
 // A lane group of 8 per trajectory (4 trajectories per warp): lane j < 6 carries column j of the
 // state-transition matrix Phi (6 values), lane 6 carries the state x (6 values), lane 7 idles.
@@ -18,6 +18,8 @@
 // here r^3 = r2*sqrt(r2) and r^5 = (r2*r2)*sqrt(r2), which agrees with it to an ulp or two.  STM parity
 // is therefore a tolerance statement (1e-8 relative to |Phi|), not a bit-exact one.
 #include "hb_dop853.cuh"
+#include "hb_rkgen.cuh"
+#include "hb_rk45.cuh"
 
 namespace {
 
@@ -351,10 +353,219 @@ __global__ void __launch_bounds__(256, 1) k_dop853_stm(const StmParams p)
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// The reference's other integrators on the 42-state system (_compute_stm(..., method=, order=) -> _propagate_dynsys,
+// rtbp.py:258-340): adaptive RK45 (rk45_step_jit_kernel rk.py:842-898, _integrate_rk45 :1269-1399, dense output
+// :971-1034) and fixed-step RK4 / RK6 / RK8 over the grid (rk_embedded_step_jit_kernel :155-215, _integrate_fixed_rk
+// :533-588).  Same lane-group mapping and vector field as k_dop853_stm; the stage / error / dense-output machinery is the
+// 6-state kernels' (hb_rkgen.cuh, hb_rk45.cuh) on each lane's column, the error norm is reduced over the group.
+// API-parity kernels (tolerance statement like every 42-state result), not tuned.
+// ---------------------------------------------------------------------------------------------------------------------
+template <class AR, int MODE>
+__global__ void __launch_bounds__(256, 1) k_rk45_stm(const StmParams p)
+{
+    const int lane = threadIdx.x & 31;
+    const int role = lane & 7;
+    const unsigned gmask = 0xFFu << (lane & 24);
+    using AS = typename StageArith<AR>::type;
+    const StmRhs<AS> rhs{p, gmask, role == 6};
+    double y[6], yh[6], k[6][6], k6[6];
+    double t = 0.0, h = 0.0, err_prev = -1.0, tf = 0.0;
+    long long idx = -1, attempts = 0;
+    int nacc = 0, nrej = 0, cursor = 0;
+    bool have = false, exhausted = false;
+    auto put = [&](double *row, const double (&v)[6]) {
+        if (role < 7) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) row[role == 6 ? 36 + i : 6 * i + role] = v[i];
+        }
+    };
+    for (;;) {
+        if (!have && !exhausted) {
+            long long got = 0;
+            if (role == 0) got = hb_fetch_index(p.ws);
+            idx = __shfl_sync(gmask, got, 0, 8);
+            if (idx < p.n) {
+#pragma unroll
+                for (int i = 0; i < 6; ++i) {
+                    double v = (role == i) ? 1.0 : 0.0;
+                    if (role == 6) v = p.x0[(long long)i * p.n + idx];
+                    if (role == 7) v = 0.0;
+                    y[i] = v;
+                }
+                rhs(y, k[0]);
+                t = p.t0;
+                tf = p.tf_arr ? p.tf_arr[idx] : p.tf;
+                if (MODE == SMODE_DENSE) {
+                    const double *te = p.t_eval + (p.t_eval_per_traj ? idx * (long long)p.m : 0);
+                    t = te[0];
+                    tf = te[p.m - 1];
+                }
+                double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                for (int d = 0; d < 6; ++d) {
+                    const double sc = AR::madd(p.rtol, fabs(y[d]), p.atol);
+                    const double a = AR::div(y[d], sc), b = AR::div(k[0][d], sc);
+                    s0 = fma(a, a, s0);
+                    s1 = fma(b, b, s1);
+                }
+                s0 = group_sum(s0, gmask);
+                s1 = group_sum(s1, gmask);
+                const double sq = AR::sqrt(42.0);
+                const double d0 = AR::div(AR::sqrt(s0), sq), d1 = AR::div(AR::sqrt(s1), sq);
+                h = (d0 < 1.0e-5 || d1 < 1.0e-5) ? 1.0e-6 : AR::div(AR::mul(0.01, d0), d1);
+                if (h > p.max_step) h = p.max_step;
+                if (h < p.min_step) h = p.min_step;
+                err_prev = -1.0;
+                nacc = 0; nrej = 0; cursor = 0; attempts = 0;
+                have = true;
+                if (!((t - tf) < 0.0)) {
+                    if (MODE == SMODE_FINAL) put(p.phi_out + idx * 42, y);
+                    else for (int c = 0; c < p.m; ++c) put(p.dense_out + (idx * (long long)p.m + c) * 42, y);
+                    if (role == 0) { p.nacc[idx] = 0; p.nrej[idx] = 0; p.status[idx] = HB_TRAJ_OK; }
+                    have = false;
+                }
+            } else {
+                exhausted = true;
+            }
+        }
+        if (__all_sync(0xffffffffu, !have && exhausted)) break;
+        if (!have) continue;
+
+        h = hb_clamp_step(h, p.max_step, p.min_step);
+        if (AR::add(t, h) > tf) h = fabs(AR::sub(tf, t));
+        g_run_stages<AS, Tab45, StmRhs<AS>, 1>(rhs, y, k, h);
+#pragma unroll
+        for (int d = 0; d < 6; ++d) yh[d] = y[d];
+        g_high_acc<AS, Tab45, 0>(yh, k, h);
+        rhs(yh, k6);
+        double ev[6], ssq = 0.0;
+#pragma unroll
+        for (int d = 0; d < 6; ++d) ev[d] = 0.0;
+        rk45_err_acc<AS, 0>(ev, k, k6, h);
+#pragma unroll
+        for (int d = 0; d < 6; ++d) {
+            const double sc = AS::madd(p.rtol, fmax(fabs(y[d]), fabs(yh[d])), p.atol);
+            const double e = AS::div(ev[d], sc);
+            ssq = fma(e, e, ssq);
+        }
+        ssq = group_sum(ssq, gmask);
+        const double err = AR::div(AR::sqrt(ssq), AR::sqrt(42.0));          // norm(err / scale) / sqrt(n), rk.py:1333
+        ++attempts;
+        int fin = -1;
+        const double h_factor = hb_pi_factor<AR>(err, err_prev, err <= 1.0, 5.0);
+        if (err <= 1.0) {
+            const double t_new = AR::add(t, h);
+            ++nacc;
+            const bool last = !((t_new - tf) < 0.0);
+            if (MODE == SMODE_DENSE || last) {
+                const double hseg = AR::sub(t_new, t);
+                double Q[6][4] = {}, yo[6];
+                rk45_q_acc<AS, 0, 0>(Q, k, k6);
+                if (MODE == SMODE_DENSE) {
+                    const double *te = p.t_eval + (p.t_eval_per_traj ? idx * (long long)p.m : 0);
+                    while (cursor < p.m) {
+                        const double tq = te[cursor];
+                        if (!(last || tq < t_new)) break;
+                        rk45_eval<AS>(y, Q, AR::div(AR::sub(tq, t), hseg), hseg, yo);
+                        put(p.dense_out + (idx * (long long)p.m + cursor) * 42, yo);
+                        ++cursor;
+                    }
+                } else {
+                    rk45_eval<AS>(y, Q, AR::div(AR::sub(tf, t), hseg), hseg, yo);
+                    put(p.phi_out + idx * 42, yo);
+                }
+                if (last) fin = HB_TRAJ_OK;
+            }
+            t = t_new;
+#pragma unroll
+            for (int d = 0; d < 6; ++d) { y[d] = yh[d]; k[0][d] = k6[d]; }
+            h = AR::mul(h, h_factor);
+            err_prev = err;
+        } else {
+            ++nrej;
+            h = AR::mul(h, h_factor);
+            h = hb_clamp_step(h, p.max_step, p.min_step);
+        }
+        if (fin < 0) {
+            if (!(h == h) || !(err == err)) fin = HB_TRAJ_NONFINITE;
+            else if (attempts >= p.max_attempts) fin = HB_TRAJ_MAXSTEPS;
+            if (fin >= 0) {
+                if (MODE == SMODE_FINAL) put(p.phi_out + idx * 42, y);
+                else for (; cursor < p.m; ++cursor) put(p.dense_out + (idx * (long long)p.m + cursor) * 42, y);
+            }
+        }
+        if (fin >= 0) {
+            if (role == 0) { p.nacc[idx] = nacc; p.nrej[idx] = nrej; p.status[idx] = fin; }
+            have = false;
+        }
+    }
+}
+
+// Fixed-step RK4 / RK6 / RK8: one step per grid interval -- t_eval[m] (DENSE) or linspace(t0, tf, n_fixed + 1) (FINAL).
+// Every group of a batch takes the same number of steps, so the plain per-group loop stays convergent.
+template <class AR, class TAB, int MODE>
+__global__ void __launch_bounds__(256, 1) k_rkfixed_stm(const StmParams p, const int n_fixed)
+{
+    const int lane = threadIdx.x & 31;
+    const int role = lane & 7;
+    const unsigned gmask = 0xFFu << (lane & 24);
+    using AS = typename StageArith<AR>::type;
+    const StmRhs<AS> rhs{p, gmask, role == 6};
+    const int npts = (MODE == SMODE_DENSE) ? p.m : n_fixed + 1;
+    for (;;) {
+        long long got = 0;
+        if (role == 0) got = hb_fetch_index(p.ws);
+        const long long idx = __shfl_sync(gmask, got, 0, 8);
+        if (idx >= p.n) break;
+        double y[6], yn[6], k[TAB::S][6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            double v = (role == i) ? 1.0 : 0.0;
+            if (role == 6) v = p.x0[(long long)i * p.n + idx];
+            if (role == 7) v = 0.0;
+            y[i] = v;
+        }
+        const double *te = (MODE == SMODE_DENSE) ? p.t_eval + (p.t_eval_per_traj ? idx * (long long)p.m : 0) : nullptr;
+        const double tf = p.tf_arr ? p.tf_arr[idx] : p.tf;
+        const double lin_step = (n_fixed > 0) ? AR::div(AR::sub(tf, p.t0), (double)n_fixed) : 0.0;
+        auto grid = [&](int i) -> double {
+            if (MODE == SMODE_DENSE) return te[i];
+            return (i == n_fixed) ? tf : AR::madd((double)i, lin_step, p.t0);         // numpy.linspace
+        };
+        auto put = [&](double *row, const double (&v)[6]) {
+            if (role < 7) {
+#pragma unroll
+                for (int i = 0; i < 6; ++i) row[role == 6 ? 36 + i : 6 * i + role] = v[i];
+            }
+        };
+        if (MODE == SMODE_DENSE) put(p.dense_out + idx * (long long)p.m * 42, y);
+        int fin = HB_TRAJ_OK;
+        for (int i = 0; i + 1 < npts; ++i) {
+            const double tn = grid(i);
+            const double h = AR::sub(grid(i + 1), tn);
+            rhs(y, k[0]);
+            g_run_stages<AS, TAB, StmRhs<AS>, 1>(rhs, y, k, h);
+#pragma unroll
+            for (int d = 0; d < 6; ++d) yn[d] = y[d];
+            g_high_acc<AS, TAB, 0>(yn, k, h);
+#pragma unroll
+            for (int d = 0; d < 6; ++d) y[d] = yn[d];
+            if (MODE == SMODE_DENSE) put(p.dense_out + (idx * (long long)p.m + i + 1) * 42, y);
+            const unsigned bad = __ballot_sync(gmask, !(y[0] == y[0])) & gmask;
+            if (bad) fin = HB_TRAJ_NONFINITE;
+        }
+        if (MODE == SMODE_FINAL) put(p.phi_out + idx * 42, y);
+        if (role == 0) { p.nacc[idx] = npts - 1; p.nrej[idx] = 0; p.status[idx] = fin; }
+    }
+}
+
 int fill(const hb_cr3bp *sys, const hb_integ *integ, StmParams &p)
 {
     if (!sys || !integ) return HB_ERR_BADARG;
-    if (integ->method != HB_DOP853) return HB_ERR_UNSUPPORTED;
+    if (integ->method != HB_DOP853 && integ->method != HB_RK45 && integ->method != HB_RK4 && integ->method != HB_RK6 &&
+        integ->method != HB_RK8)
+        return HB_ERR_UNSUPPORTED;
     if (integ->arith != HB_ARITH_PARITY && integ->arith != HB_ARITH_FAST) return HB_ERR_BADARG;
     p.mu = sys->mu;
     p.om = 1.0 - sys->mu;
@@ -371,9 +582,23 @@ int fill(const hb_cr3bp *sys, const hb_integ *integ, StmParams &p)
     return HB_OK;
 }
 
-template <int MODE>
-int launch(const StmParams &p, int arith, cudaStream_t st)
+template <class AR, int MODE>
+int launch_rk(const StmParams &p, int method, int n_fixed, unsigned blocks, cudaStream_t st)
 {
+    switch (method) {
+    case HB_RK45: k_rk45_stm<AR, MODE><<<blocks, 256, 0, st>>>(p); break;
+    case HB_RK4: k_rkfixed_stm<AR, TabRK4, MODE><<<blocks, 256, 0, st>>>(p, n_fixed); break;
+    case HB_RK6: k_rkfixed_stm<AR, TabRK6, MODE><<<blocks, 256, 0, st>>>(p, n_fixed); break;
+    case HB_RK8: k_rkfixed_stm<AR, TabRK8, MODE><<<blocks, 256, 0, st>>>(p, n_fixed); break;
+    default: return HB_ERR_UNSUPPORTED;
+    }
+    return HB_OK;
+}
+
+template <int MODE>
+int launch(const StmParams &p, int arith, cudaStream_t st, int method = HB_DOP853, int n_fixed = 0)
+{
+    if (method != HB_DOP853 && method != HB_RK45 && MODE == SMODE_FINAL && n_fixed < 1) return HB_ERR_BADARG;
     HB_CUDA_TRY(cudaMemsetAsync(p.ws, 0, sizeof(HbWorkspace), st));
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -382,7 +607,11 @@ int launch(const StmParams &p, int arith, cudaStream_t st)
     long long blocks = (p.n * 8 + threads - 1) / threads;
     if (blocks > sms) blocks = sms;                  // persistent: one CTA per SM
     if (blocks < 1) blocks = 1;
-    if (arith == HB_ARITH_PARITY) k_dop853_stm<ArParity, MODE><<<(unsigned)blocks, threads, 0, st>>>(p);
+    if (method != HB_DOP853) {
+        const int rc = (arith == HB_ARITH_PARITY) ? launch_rk<ArParity, MODE>(p, method, n_fixed, (unsigned)blocks, st)
+                                                  : launch_rk<ArFast, MODE>(p, method, n_fixed, (unsigned)blocks, st);
+        if (rc != HB_OK) return rc;
+    } else if (arith == HB_ARITH_PARITY) k_dop853_stm<ArParity, MODE><<<(unsigned)blocks, threads, 0, st>>>(p);
     else k_dop853_stm<ArFast, MODE><<<(unsigned)blocks, threads, 0, st>>>(p);
     HB_CUDA_TRY(cudaGetLastError());
     return HB_OK;
@@ -401,7 +630,7 @@ extern "C" int hb_cr3bp_stm(const hb_cr3bp *sys, const hb_integ *integ, int64_t 
     if (n == 0) return HB_OK;
     p.n = n; p.x0 = x0_soa; p.t0 = t0; p.tf = tf; p.tf_arr = tf_per_traj; p.phi_out = phi_out;
     p.nacc = n_acc; p.nrej = n_rej; p.status = status; p.ws = (HbWorkspace *)workspace;
-    return launch<SMODE_FINAL>(p, integ->arith, (cudaStream_t)stream);
+    return launch<SMODE_FINAL>(p, integ->arith, (cudaStream_t)stream, integ->method, integ->n_fixed_steps);
 }
 
 extern "C" int hb_cr3bp_stm_dense(const hb_cr3bp *sys, const hb_integ *integ, int64_t n, const double *x0_soa,
@@ -416,5 +645,5 @@ extern "C" int hb_cr3bp_stm_dense(const hb_cr3bp *sys, const hb_integ *integ, in
     if (n == 0) return HB_OK;
     p.n = n; p.x0 = x0_soa; p.t_eval = t_eval; p.m = m; p.t_eval_per_traj = t_eval_per_traj ? 1 : 0;
     p.dense_out = phi_dense; p.nacc = n_acc; p.nrej = n_rej; p.status = status; p.ws = (HbWorkspace *)workspace;
-    return launch<SMODE_DENSE>(p, integ->arith, (cudaStream_t)stream);
+    return launch<SMODE_DENSE>(p, integ->arith, (cudaStream_t)stream, integ->method, integ->n_fixed_steps);
 }

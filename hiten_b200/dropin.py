@@ -21,7 +21,8 @@ No reference file is edited.  What is rebound (paths relative to hiten/):
   * the `_ham` branches of the three RK classes above for the reference's bare `_HamiltonianSystem` (grid with
     derivatives, plane events).
 Anything the GPU path cannot express (user-defined RHS or event callables, a `_DirectedSystem` around a Hamiltonian
-system in the RK classes -- which raises inside the reference --, 42-state RK45 / fixed-step integration) is handed to the reference's ORIGINAL function -- that is the reference's
+system in the RK classes -- which raises inside the reference --, the 42-state system handed directly to the RK45 /
+fixed-step CLASSES instead of through _propagate_dynsys / _compute_stm) is handed to the reference's ORIGINAL function -- that is the reference's
 own code for inputs outside this path, not a fallback of the kernels: for recognised inputs a missing library
 or GPU raises.
 """
@@ -181,8 +182,7 @@ def _make_propagate_dynsys(orig):
         rec = recognise_system(dynsys)
         known = {"rtol", "atol", "max_step", "event_fn", "event_cfg", "event_options"}
         hb_method = _hb_method(method, order)
-        if rec is None or rec[2] != 1 or hb_method is None or (set(kwargs) - known) or \
-                (hb_method != _L.HB_DOP853 and rec[0] != 6):
+        if rec is None or rec[2] != 1 or hb_method is None or (set(kwargs) - known):
             return orig(dynsys, state0, t0, tf, forward=forward, steps=steps, method=method, order=order,
                         flip_indices=flip_indices, **kwargs)
         dim, mu, _, _ = rec

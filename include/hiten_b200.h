@@ -212,7 +212,10 @@ int hb_dfma_peak(double millis, double *flops_per_s, void *stream);
  * The initial condition is PHI0 = [I6 row-major, x0]; sys->flip_lo/hi select the derivative block the
  * backward wrapper negates: (36,42) = state only (what _compute_stm passes), <0 = everything.
  * phi_out[i][0..41] is the reference's flat PHI row at tf (Phi row-major in [0,36), state in [36,42)),
- * with the same dense-interpolant-at-tf semantics as hb_cr3bp_propagate.                          */
+ * with the same dense-interpolant-at-tf semantics as hb_cr3bp_propagate.
+ * integ->method: HB_DOP853 (the shipped default, the tuned kernel), HB_RK45 (_compute_stm(..., order=5): rk.py:1138-1399)
+ * or HB_RK4 / HB_RK6 / HB_RK8 (method="fixed": rk.py:422-588; integ->n_fixed_steps steps over linspace(t0, tf), or one
+ * step per interval of t_eval in the dense call).                                                  */
 int hb_cr3bp_stm(const hb_cr3bp *sys, const hb_integ *integ, int64_t n, const double *x0_soa, double t0,
                  double tf, const double *tf_per_traj, double *phi_out, int32_t *n_acc, int32_t *n_rej,
                  int32_t *status, void *workspace, void *stream);

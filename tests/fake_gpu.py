@@ -33,7 +33,12 @@ def cr3bp_stm_dense(x0, mu, t_eval, *, forward=1, flip=(36, 42), integ=None, **k
     s = O.system(O.SYS_VAR42, mu, fwd=forward, flip=flip)
     x0 = np.asarray(x0)
     y0 = np.concatenate([np.tile(np.eye(6).ravel(), (len(x0), 1)), x0], axis=1)
-    dense, counts = O.batch_dense(s, O.DOP853, _tol(integ), y0, np.asarray(t_eval), 4)
+    method = O.DOP853 if integ is None else integ.method
+    if method in (4, 6, 8):                             # fixed-step: one step per grid interval
+        dense = np.stack([O.fixed_dense(s, method, y, np.asarray(t_eval)) for y in y0])
+        counts = np.zeros((len(x0), 2), np.int64)
+    else:
+        dense, counts = O.batch_dense(s, method, _tol(integ), y0, np.asarray(t_eval), 4)
     return BatchResult(None, counts[:, 0].astype(np.int32), counts[:, 1].astype(np.int32),
                        np.zeros(len(x0), np.int32), states=dense)
 

@@ -492,3 +492,41 @@ def test_cubic_synodic_request_goes_through_the_drop_in(ref, monkeypatch):
     assert np.array_equal(got.trajectory_indices, want.trajectory_indices)
     sel = g["l2_r50_dm_traj"] < 6
     assert np.array_equal(got.times, g["l2_r50_dm_time"][sel]) and np.array_equal(got.states, g["l2_r50_dm_state"][sel])
+
+
+def test_compute_stm_with_the_other_integrators_goes_through_the_drop_in(ref, monkeypatch):
+    """_compute_stm(..., method="fixed", order=4 | 8) and (method="adaptive", order=5) reach the 42-state kernels under
+    install() (rtbp.py:258-340 -> _propagate_dynsys); results agree with the reference alone within the 42-state
+    tolerance and with the golden rows."""
+    import fake_gpu
+    import hiten_b200
+    from hiten.algorithms.dynamics import rtbp
+    system, l1, halo = ref
+    here = os.path.dirname(os.path.abspath(__file__))
+    g = np.load(os.path.join(here, "golden", "stm_variants.npz"))
+    fam = np.load(os.path.join(here, "golden", "stm_family.npz"))
+    x0, T = fam["x0"][0], float(fam["period"][0])
+    calls = []
+    hiten_b200.install()
+    fake_gpu.patch(monkeypatch)
+    import hiten_b200.propagate as prop
+    orig_dense = prop.cr3bp_stm_dense
+
+    def spy(*a, **kw):
+        calls.append(kw["integ"].method)
+        return orig_dense(*a, **kw)
+
+    monkeypatch.setattr(prop, "cr3bp_stm_dense", spy)
+    try:
+        for name in ("rk4_fwd", "rk8_fwd", "rk45_bwd"):
+            kind, order, steps, fwd, frac = g[f"case_{name}"]
+            x, times, phiT, PHI = rtbp._compute_stm(system.var_dynsys, x0, float(frac) * T, steps=int(steps), forward=int(fwd),
+                                                    method="fixed" if kind else "adaptive", order=int(order))
+            ref_rows = g[f"{name}_m0_PHI"]
+            rows = np.asarray(PHI)[g[f"{name}_idx"]]
+            scale = np.abs(ref_rows[:, :36]).max(axis=1, keepdims=True)
+            assert (np.abs(rows[:, :36] - ref_rows[:, :36]) / scale).max() <= 1e-9
+            assert times[-1] == g[f"{name}_m0_tlast"]
+    finally:
+        hiten_b200.uninstall()
+    assert calls == [4, 8, 45]
