@@ -530,3 +530,31 @@ def test_compute_stm_with_the_other_integrators_goes_through_the_drop_in(ref, mo
     finally:
         hiten_b200.uninstall()
     assert calls == [4, 8, 45]
+
+
+def test_invariant_torus_stm_pass_runs_on_the_42_state_path(ref, monkeypatch):
+    """_TorusDynamicsService.prepare (types/services/torus.py:215) calls _compute_stm(var_dynsys, x0, T, steps=n_theta1):
+    under install() that is ONE dense 42-state launch; the torus grid equals the reference's own within the STM tolerance."""
+    import fake_gpu
+    import hiten_b200
+    import hiten_b200.propagate as prop
+    from hiten import InvariantTori
+    system, l1, halo = ref
+    halo.propagate()
+    want = np.asarray(InvariantTori(halo).compute(epsilon=1e-3, n_theta1=64, n_theta2=16))
+    calls = []
+    hiten_b200.install()
+    fake_gpu.patch(monkeypatch)
+    orig_dense = prop.cr3bp_stm_dense
+
+    def spy(x0, mu, t_eval, **kw):
+        calls.append(len(t_eval))
+        return orig_dense(x0, mu, t_eval, **kw)
+
+    monkeypatch.setattr(prop, "cr3bp_stm_dense", spy)
+    try:
+        got = np.asarray(InvariantTori(halo).compute(epsilon=1e-3, n_theta1=64, n_theta2=16))
+    finally:
+        hiten_b200.uninstall()
+    assert 64 in calls
+    assert got.shape == want.shape and np.abs(got - want).max() <= 1e-9

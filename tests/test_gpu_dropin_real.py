@@ -344,3 +344,34 @@ def test_cubic_synodic_request_through_the_rebound_backend(ref):
     assert np.array_equal(got.times, want.times) and np.array_equal(got.states, want.states)
     assert np.array_equal(got.points, want.points) and np.array_equal(got.trajectory_indices, want.trajectory_indices)
     assert np.array_equal(got.times, g["l2_r50_dm_time"]) and np.array_equal(got.states, g["l2_r50_dm_state"])
+
+
+def test_invariant_torus_and_compute_stm_variants_on_the_real_kernels(ref):
+    """InvariantTori.compute() (its STM pass is _compute_stm with steps = n_theta1, types/services/torus.py:215) and
+    _compute_stm(method="fixed" / order=5) under install() with the real library: equal to the unpatched reference within
+    the 42-state tolerance."""
+    import hiten_b200
+    from hiten import InvariantTori
+    from hiten.algorithms.dynamics import rtbp
+    l1 = ref.get_libration_point(1)
+    halo = l1.create_orbit("halo", amplitude_z=0.2, zenith="southern")
+    halo.correct()
+    halo.propagate()
+    assert not hiten_b200.dropin.is_installed()
+    want = np.asarray(InvariantTori(halo).compute(epsilon=1e-3, n_theta1=64, n_theta2=16))
+    x0, T = np.asarray(halo.initial_state, float), float(halo.period)
+    ref_rows = {}
+    for key, kw in (("rk4", dict(method="fixed", order=4, steps=801)), ("rk45", dict(method="adaptive", order=5, steps=50))):
+        ref_rows[key] = np.asarray(rtbp._compute_stm(ref.var_dynsys, x0, T, forward=1, **kw)[3])
+    hiten_b200.install()
+    try:
+        got = np.asarray(InvariantTori(halo).compute(epsilon=1e-3, n_theta1=64, n_theta2=16))
+        for key, kw in (("rk4", dict(method="fixed", order=4, steps=801)), ("rk45", dict(method="adaptive", order=5, steps=50))):
+            rows = np.asarray(rtbp._compute_stm(ref.var_dynsys, x0, T, forward=1, **kw)[3])
+            scale = np.abs(ref_rows[key][:, :36]).max(axis=1, keepdims=True)
+            assert (np.abs(rows[:, :36] - ref_rows[key][:, :36]) / scale).max() <= 1e-8
+            assert np.abs(rows[:, 36:] - ref_rows[key][:, 36:]).max() <= 1e-9
+    finally:
+        hiten_b200.uninstall()
+    assert _library_loaded()
+    assert got.shape == want.shape and np.abs(got - want).max() <= 1e-8
