@@ -643,11 +643,21 @@ def _make_strategy_generate(orig):
 
         self._build_seed = build
         try:
-            return orig(self, h0=h0, H_blocks=H_blocks, clmo_table=clmo_table,
-                        solve_missing_coord_fn=solve_missing_coord_fn, find_turning_fn=turning_fn)
+            seeds = orig(self, h0=h0, H_blocks=H_blocks, clmo_table=clmo_table,
+                         solve_missing_coord_fn=solve_missing_coord_fn, find_turning_fn=turning_fn)
         finally:
             del self._build_seed
             np.random.default_rng = real_default_rng
+        # The engine lifts the returned seeds on the section of the compute() call (engine.py:139-149), which is NOT the
+        # strategy's own config.section_coord when the caller passes section_coord at run time (the strategy keeps the
+        # config it was built with): one more batch on that section, so that the engine's loop is answered from it too.
+        sec_run = getattr(_TLS, "section", None)
+        if sec_run is not None and sec_run != section and seeds:
+            pts = np.asarray([(float(p_[0]), float(p_[1])) for p_ in seeds], dtype=np.float64)
+            ok2, st2 = _cm.lift_plane_points(_h_table(H_blocks, clmo_table), sec_run, pts, float(h0))
+            for c, good, st in zip(pts.tolist(), ok2, st2):
+                _LIFT_CACHE[(id(H_blocks), sec_run, float(h0), c[0], c[1])] = tuple(float(v) for v in st) if good else None
+        return seeds
 
     generate.__wrapped__ = orig
     return generate
@@ -679,6 +689,7 @@ def _make_create_problem(orig):
         except Exception:
             pass
         _TLS.n_seeds = n
+        _TLS.section = getattr(config, "section_coord", None)      # the section the engine will lift the seeds on
         return orig(self, domain_obj=domain_obj, config=config, options=options)
 
     create_problem.__wrapped__ = orig

@@ -456,6 +456,17 @@ def test_centre_manifold_seeding_is_batched_and_identical(ref, monkeypatch):
         pm2.compute(section_coord="p3", options=opts)
         n_more = len(np.asarray(pm2.get_points(section_coord="p3")))
         assert n_default <= 20 < n_more <= 64
+        # the engine's lifting loop of a compute("p3") call is answered from a batch as well, although the strategy
+        # validates its candidates on ITS config's section (q3): no per-seed Brent solve is left (only turning points)
+        solves = []
+        orig_solve = _CenterManifoldInterface.solve_missing_coord
+        monkeypatch.setattr(_CenterManifoldInterface, "solve_missing_coord",
+                            lambda self, *a, **k: (solves.append(1), orig_solve(self, *a, **k))[1])
+        pm3 = cm.poincare_map(energy=0.64)
+        n_batches = len(calls)
+        pm3.compute(section_coord="p3", options=opts)
+        assert len(np.asarray(pm3.get_points(section_coord="p3"))) > 20
+        assert len(calls) == n_batches + 2 and len(solves) <= 4, (len(calls) - n_batches, len(solves))
     finally:
         hiten_b200.uninstall()
 
