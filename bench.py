@@ -174,6 +174,36 @@ class ReferenceArm:
         return hits, time.perf_counter() - t0
 
 
+_FORK_ARM = None          # ReferenceArm of the parent, inherited by forked workers (their Numba code is already compiled)
+
+
+def _ref_worker(job):
+    shard, mu = job
+    return _FORK_ARM.step(shard, mu)[0]
+
+
+def reference_all_cores(arm, ics_all, mu, per_tube_per_worker, steps, n_procs):
+    """The reference's own code on every host core: it has no parallel driver for this loop (and its @njit kernels hold the
+    GIL), so the batch is sharded by index over `n_procs` FORKED worker processes -- each runs exactly ReferenceArm.step
+    on its shard ("run warm worker processes over index shards and state the core count").  Forked after the
+    parent's warm-up call, so no worker compiles anything.  -> (RK steps/s, hits/s, trajectories per step, seconds)."""
+    global _FORK_ARM
+    import multiprocessing as mp
+    _FORK_ARM = arm
+    k = per_tube_per_worker * n_procs
+    sample = {key: ics_all[key][:: max(1, len(ics_all[key]) // k)][:k] for key in TUBES}
+    shards = [({key: sample[key][w::n_procs] for key in TUBES}, mu) for w in range(n_procs)]
+    rk_steps = oracle_step_count(sample, mu)
+    with mp.get_context("fork").Pool(n_procs) as pool:
+        pool.map(_ref_worker, [({key: sample[key][:1] for key in TUBES}, mu)] * n_procs)      # every worker is up
+        t0 = time.perf_counter()
+        hits = 0
+        for _ in range(steps):
+            hits += sum(pool.map(_ref_worker, shards, chunksize=1))
+        dt = time.perf_counter() - t0
+    return rk_steps * steps / dt, hits / dt, 2 * k, dt
+
+
 def oracle_step_count(ics, mu):
     import oracle_lib as O
     from hiten_b200 import workloads as W
@@ -213,11 +243,18 @@ def run_reference(args):
             h, dt = arm.step(sample, mu)
             hits_total += h
             t_total += dt
-        val = rk_steps * args.steps / t_total
-        kind, cores = "reference", 1
-        what = (f"{2 * per_tube} trajectories per step ({per_tube} per tube, strided through the batch): "
-                "_propagate_dynsys per initial condition + _SynodicDetectionBackend.run, the reference's own code from "
-                f"oracle/_ref ({os.path.basename(arm.src.rstrip('/'))})")
+        single = {"value": rk_steps * args.steps / t_total, "unit": "RK steps/s", "cores": 1, "kind": "reference",
+                  "crossings_per_s": hits_total / t_total,
+                  "sample": f"{2 * per_tube} trajectories per step in ONE process (the reference as shipped: no parallel "
+                            "driver for this loop)"}
+        n_procs = max(1, min(os.cpu_count() or 1, 64))
+        val, hits_per_s, n_traj, t_all = reference_all_cores(arm, ics_all, mu, per_tube, args.steps, n_procs)
+        hits_total, t_total = hits_per_s * t_all, t_all
+        kind, cores = "reference", n_procs
+        what = (f"{n_traj} trajectories per step ({per_tube} per tube and worker, strided through the batch), sharded by "
+                f"index over {n_procs} forked worker processes, each running the reference's own code from "
+                f"oracle/_ref ({os.path.basename(arm.src.rstrip('/'))}): _propagate_dynsys per initial condition + "
+                "_SynodicDetectionBackend.run")
         port_v, port_n, port_dt = cpu_port_throughput(ics_all, mu, n_threads, seconds_target=5.0)
         port = {"value": port_v, "unit": "RK steps/s", "cores": n_threads, "kind": "port",
                 "sample": f"{port_n} trajectories, {port_dt:.1f} s"}
@@ -247,6 +284,8 @@ def run_reference(args):
     }
     if port is not None:
         line["cpu_baseline_port"] = port
+    if kind == "reference":
+        line["cpu_baseline_single_core"] = single
     print(json.dumps(line))
 
 
