@@ -567,8 +567,13 @@ def main():
                 t = j["tubes"][key]
                 t["run"].launch(t["y0"])
             if world > 1:                                   # the one exchange: hit records, counts, end states -> rank 0
-                for key in TUBES:
-                    j["tubes"][key]["dist"].gather_device()
+                peer = [j["tubes"][key]["dist"].start_gather() for key in TUBES]    # tube 1's copies run under tube 2
+                for key, started in zip(TUBES, peer):
+                    d = j["tubes"][key]["dist"]
+                    if started:
+                        d.finish_gather()
+                    else:
+                        d.gather_device()
         return step
 
     step_resident = step_of(job)
@@ -835,8 +840,13 @@ def main():
                 "l2": "flushed between timed iterations (256 MB fill); inputs 48 B and step records ~50 KB per trajectory (>> L2)",
                 "rk_steps_per_pass": total_steps_pass, "accepted_steps_per_pass": total_acc,
                 "crossings_per_pass": total_hits, "all_status_ok": ok,
-                "exchange": None if world == 1 else "per tube: all-gather of hit counts, NCCL gather of hit records "
-                                                    "(padded to the largest shard) and end states to rank 0, inside the timed step",
+                "exchange": None if world == 1 else (
+                    "per tube, inside the timed step: every rank writes its hit records and end states into rank 0's "
+                    "receive buffer over NVLink peer memory (symmetric memory, copy engines; tube 1's transfer runs under "
+                    "tube 2's propagation), one signal-pad barrier at the end"
+                    if all(job["tubes"][key]["dist"].px is not None for key in TUBES) else
+                    "per tube: all-gather of hit counts, NCCL gather of hit records (padded to the largest shard) and end "
+                    "states to rank 0, inside the timed step"),
             },
             "roofline": {"bound": "fp64", "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "TFLOP/s",
                          "frac": achieved / peak, "traffic": traffic,

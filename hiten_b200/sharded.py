@@ -8,8 +8,11 @@ chunks exactly like this.  Two forms:
   ShardedTubeSection       one process driving N devices (per-device runner, workspace and stream; peer copies to
                            device 0 at the end) -- what a user of the drop-in gets on a multi-GPU box;
   DistributedTubeSection   one process per GPU under torch.distributed (NCCL), the launch bench.py is run with:
-                           rank r owns trajectories r, r + W, r + 2W, ...; hits are gathered to rank 0 with a padded
-                           NCCL gather after an all-gather of the counts.
+                           rank r owns trajectories r, r + W, r + 2W, ...; the final exchange writes every rank's hit
+                           records and end states straight into rank 0's receive buffer over NVLink peer memory with the
+                           COPY ENGINES (PeerExchange: symmetric memory, no SM work, so the transfer of one tube runs
+                           under the propagation of the next); without peer memory it is a padded NCCL gather after an
+                           all-gather of the counts.
 
 Sharding is interleaved (i mod W) so that a tube's phase-dependent cost spreads evenly (8e).  Both return hits with
 GLOBAL trajectory indices in the reference's order (by trajectory, then along the trajectory).
@@ -92,14 +95,74 @@ class ShardedTubeSection:
         return _syn.SectionHits(traj, t, state, pts, per), yf, status
 
 
+class PeerExchange:
+    """Rank 0's receive buffer, mapped into every rank's address space (torch symmetric memory over NVLink / NVSwitch).
+    Rank r owns slot r: [8 doubles of header | hit records | end states].  A rank fills its slot with plain device-to-
+    device copies on its own copy stream -- cudaMemcpyAsync on a peer-mapped pointer, i.e. the copy engines: no SM is
+    needed, so the copies of one tube overlap the persistent propagation kernel of the next, which owns every register
+    of every SM.  finish() is the only synchronisation: a stream-ordered barrier over the group's signal pads."""
+
+    HEADER = 8
+
+    def __init__(self, hit_slots, n_max, device, group=None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        self.group = dist.group.WORLD if group is None else group
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.hit_slots, self.n_max = int(hit_slots), int(n_max)
+        self.slot = self.HEADER + 9 * self.hit_slots + 6 * self.n_max
+        with torch.cuda.device(device):
+            self.buf = symm.empty(self.world * self.slot, dtype=torch.float64, device=device)
+            self.hdl = symm.rendezvous(self.buf, self.group)
+            self.mine = self.hdl.get_buffer(0, (self.slot,), torch.float64, self.rank * self.slot)   # my slot on rank 0
+            self.stream = torch.cuda.Stream(device)
+            self.hdr_host = torch.zeros(self.HEADER, dtype=torch.float64).pin_memory()
+            self.hdr_dev = torch.zeros(self.HEADER, dtype=torch.float64, device=device)
+            self.cnt_host = torch.zeros(4, dtype=torch.int64).pin_memory()
+
+    def put(self, k, hits, yf_flat):
+        """Enqueue the copies of this rank's slot on the copy stream (k hit records, the end states)."""
+        with torch.cuda.stream(self.stream):
+            self.hdr_host[0], self.hdr_host[1] = float(k), float(yf_flat.numel() // 6)
+            self.hdr_dev.copy_(self.hdr_host, non_blocking=True)
+            self.mine[: self.HEADER].copy_(self.hdr_dev, non_blocking=True)
+            if k:
+                self.mine[self.HEADER: self.HEADER + 9 * k].copy_(hits[: 9 * k], non_blocking=True)
+            o = self.HEADER + 9 * self.hit_slots
+            self.mine[o: o + yf_flat.numel()].copy_(yf_flat, non_blocking=True)
+
+    def finish(self):
+        with torch.cuda.stream(self.stream):
+            self.hdl.barrier(channel=0)
+        self.stream.synchronize()
+
+    def received(self):
+        """Rank 0: (hit record tensors per rank, counts, end-state tensors per rank) as views of the receive buffer."""
+        rows = self.buf.view(self.world, self.slot)
+        hdr = rows[:, : self.HEADER].cpu()
+        hits, yfs, counts = [], [], []
+        o = self.HEADER + 9 * self.hit_slots
+        for r in range(self.world):
+            k, nl = int(hdr[r, 0].item()), int(hdr[r, 1].item())
+            counts.append(k)
+            hits.append(rows[r, self.HEADER: self.HEADER + 9 * k])
+            yfs.append(rows[r, o: o + 6 * nl].view(6, nl))
+        return hits, torch.tensor(counts, dtype=torch.int64), yfs
+
+
 class DistributedTubeSection:
     """One process per GPU (torch.distributed initialised by the caller, NCCL on GPUs / gloo in the CPU tests).
     `runner_factory(n_local)` builds the rank's runner -- by default a TubeSectionRunner on the current device."""
 
     def __init__(self, n_global, mu, t_eval, section, *, forward=1, flip=None, integ=None, steps_capacity=192,
-                 pool_records=0, hit_capacity=None, runner_factory=None, group=None):
+                 pool_records=0, hit_capacity=None, runner_factory=None, group=None, exchange="auto"):
+        """exchange: "peer" (PeerExchange), "nccl" (padded gather) or "auto" (peer when the process group runs on NCCL
+        and symmetric memory can be set up, else nccl; HITEN_B200_EXCHANGE overrides)."""
+        import os
         import torch.distributed as dist
         self.dist, self.group = dist, group
+        self._exchange = os.environ.get("HITEN_B200_EXCHANGE", exchange)
+        self.px = None
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.n_global, self.section = int(n_global), section
@@ -112,14 +175,60 @@ class DistributedTubeSection:
         self.runner = runner_factory(len(self.index))
         # shards differ by at most one trajectory: pad the end-state exchange to the largest
         self.n_max = (self.n_global + self.world - 1) // self.world
+        if self.world > 1 and self._exchange in ("auto", "peer") and hasattr(self.runner, "yf") \
+                and getattr(self.runner.yf, "is_cuda", False):
+            try:
+                self.px = PeerExchange(max(1024, 3 * self.n_max), self.n_max, self.runner.yf.device, group)
+            except Exception as exc:                       # no peer mapping on this box / backend: NCCL gather instead
+                if self._exchange == "peer":
+                    raise
+                self.px = None
+                self.peer_error = repr(exc)
 
     def launch(self, y0_soa_local, stream=None):
         self.runner.launch(y0_soa_local, stream)
 
+    def start_gather(self, stream=None):
+        """Peer form of the exchange, first half: wait (host) for THIS runner's pipeline only -- later launches on the
+        same stream keep running --, read its hit counter, and enqueue the copies into rank 0's receive buffer on the
+        copy stream.  Returns False when the peer path is not available (use gather_device)."""
+        if self.px is None:
+            return False
+        run, px = self.runner, self.px
+        main = torch.cuda.current_stream(run.yf.device) if stream is None else stream
+        ev = getattr(run, "done_event", None)
+        if ev is None:
+            ev = torch.cuda.Event()
+            ev.record(main)
+        px.stream.wait_event(ev)
+        with torch.cuda.stream(px.stream):
+            px.cnt_host.copy_(run.ws[:4], non_blocking=True)      # cursor, hit_count, overflow, rec_overflow
+        px.stream.synchronize()
+        k, dropped, rec_over = int(px.cnt_host[1]), int(px.cnt_host[2]), int(px.cnt_host[3])
+        if dropped or rec_over or k > px.hit_slots:
+            k = run.hit_count(stream)                          # rare: regrow / rerun on the main stream, then copy
+            k = min(k, run._main_hits, px.hit_slots)
+            px.stream.wait_stream(main)
+        else:
+            run._main_hits, run._extra = k, (None, None)
+        px.put(k, run.hits, run.yf.view(-1)[: 6 * len(self.index)])
+        return True
+
+    def finish_gather(self):
+        """Second half: all ranks' copies have landed on rank 0.  -> (hit record tensors per rank | None, counts | None,
+        end-state tensors per rank | None)."""
+        self.px.finish()
+        if self.rank != 0:
+            return None, None, None
+        return self.px.received()
+
     def gather_device(self):
         """The one exchange of the path, on the device, stream-ordered after launch(): end states + per-trajectory hit
-        counts (fixed size) and the hit records (all-gather of the counts, then a gather padded to the largest) to rank 0.
+        counts (fixed size) and the hit records to rank 0 -- over peer memory when available (start_gather +
+        finish_gather), else an all-gather of the counts and a gather padded to the largest shard.
         Returns (hit record tensors per rank | None, counts, end-state tensors per rank | None) without host work."""
+        if self.world > 1 and self.start_gather():
+            return self.finish_gather()
         dist, run = self.dist, self.runner
         dev = run.yf.device
         k = torch.tensor([run.hit_count()], dtype=torch.int64, device=dev)      # also completes overflow reruns

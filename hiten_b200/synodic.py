@@ -209,6 +209,7 @@ class TubeSectionRunner:
         self.hits = torch.empty(self.cap * 9, dtype=torch.float64, device=self.device)
         self.steps_capacity = int(steps_capacity)
         self.pool_records = int(pool_records)
+        self.done_event = None
         if records not in ("near", "all"):
             raise ValueError("records must be 'near' or 'all'")
         self.records = L.HB_RECORDS_ALL if (records == "all" or filters is not None) else L.HB_RECORDS_NEAR_SECTION
@@ -248,6 +249,15 @@ class TubeSectionRunner:
         self.stage_events = (arr, list(events))
 
     def launch(self, y0_soa, stream=None):
+        try:
+            self._launch(y0_soa, stream)
+        finally:
+            # end of THIS pipeline on the launch stream: lets a caller wait for it while later launches keep running
+            if self.done_event is None:
+                self.done_event = torch.cuda.Event()
+            self.done_event.record(torch.cuda.current_stream(self.device) if stream is None else stream)
+
+    def _launch(self, y0_soa, stream=None):
         self._y0, self._extra = y0_soa, None
         sev = None if self.stage_events is None else self.stage_events[0]
         if self.scratch is not None and self.pool_records > 0:
