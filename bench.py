@@ -560,6 +560,7 @@ def main():
 
     job = make_job(n * world)
     mu = job["mu"]
+    peer_exchange = world > 1 and all(job["tubes"][key]["dist"].px is not None for key in TUBES)
 
     def step_of(j):
         def step():
@@ -844,7 +845,7 @@ def main():
                     "per tube, inside the timed step: every rank writes its hit records and end states into rank 0's "
                     "receive buffer over NVLink peer memory (symmetric memory, copy engines; tube 1's transfer runs under "
                     "tube 2's propagation), one signal-pad barrier at the end"
-                    if all(job["tubes"][key]["dist"].px is not None for key in TUBES) else
+                    if peer_exchange else
                     "per tube: all-gather of hit counts, NCCL gather of hit records (padded to the largest shard) and end "
                     "states to rank 0, inside the timed step"),
             },
