@@ -494,6 +494,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--concurrent-tubes", type=int, default=1,
+                    help="1: the two tubes' pipelines on two streams with a step scratch each; 0: one after the other")
     ap.add_argument("--arith", default="parity", choices=["parity", "fast"])
     ap.add_argument("--n-per-gpu", type=int, default=N_PER_GPU)
     ap.add_argument("--pipeline", default="section2", choices=["section2", "section3", "fused"],
@@ -548,7 +550,7 @@ def main():
                 flip=(0, 6), integ=integ,
                 runner_factory=lambda nl, key=key: synodic.TubeSectionRunner(
                     nl, mu, W.c5_grid(key), W.c5_section(key, mu), forward=W.C5_TUBES[key]["forward"], flip=(0, 6),
-                    integ=integ, device=dev, scratch=scratch, **kind))
+                    integ=integ, device=dev, scratch=None if args.concurrent_tubes else scratch, **kind))
             assert len(d.index) == len(x)
             if scratch is None:
                 scratch = d.runner.scratch
@@ -562,19 +564,35 @@ def main():
     mu = job["mu"]
     peer_exchange = world > 1 and all(job["tubes"][key]["dist"].px is not None for key in TUBES)
 
+    side = [torch.cuda.Stream(dev) for _ in TUBES] if args.concurrent_tubes else None
+
     def step_of(j):
         def step():
-            for key in TUBES:
+            # The two tubes' pipelines on two streams (each with its own step scratch): the propagation kernels are
+            # persistent with one CTA per SM, so tube 2's CTAs take over an SM the moment tube 1's CTA there runs out of
+            # trajectories, and tube 1's scan / emit kernels fill the SMs tube 2's propagation vacates -- the idle tail of
+            # each persistent launch is covered by the other tube's work.
+            main = torch.cuda.current_stream()
+            for i, key in enumerate(TUBES):
                 t = j["tubes"][key]
-                t["run"].launch(t["y0"])
+                if side is not None:
+                    side[i].wait_stream(main)
+                    t["run"].launch(t["y0"], side[i])
+                else:
+                    t["run"].launch(t["y0"])
             if world > 1:                                   # the one exchange: hit records, counts, end states -> rank 0
-                peer = [j["tubes"][key]["dist"].start_gather() for key in TUBES]    # tube 1's copies run under tube 2
-                for key, started in zip(TUBES, peer):
+                peer = [j["tubes"][key]["dist"].start_gather(None if side is None else side[i])
+                        for i, key in enumerate(TUBES)]     # tube 1's copies run under tube 2's propagation
+                for i, (key, started) in enumerate(zip(TUBES, peer)):
                     d = j["tubes"][key]["dist"]
                     if started:
                         d.finish_gather()
                     else:
-                        d.gather_device()
+                        with torch.cuda.stream(main if side is None else side[i]):
+                            d.gather_device()
+            if side is not None:
+                for st_ in side:
+                    main.wait_stream(st_)
         return step
 
     step_resident = step_of(job)
@@ -696,6 +714,9 @@ def main():
                                 "note": "configs[4]'s 1e6 trajectories in TOTAL, 1/N per GPU, same step incl. the gather; "
                                         "efficiency = rk_steps_per_s / (N x the N=1 value)"}}
     if not args.no_extra and world == 1:
+        if args.concurrent_tubes and args.pipeline != "fused":       # the secondary lines run one tube at a time: one scratch
+            job["tubes"][TUBES[1]]["run"].scratch = job["scratch"]
+            torch.cuda.empty_cache()
         ws = P.workspace(dev)
         y0_l1, tf_l1 = job["tubes"]["l1"]["y0"], float(W.c5_grid("l1")[-1])
         for name in ("parity", "fast"):
@@ -833,6 +854,9 @@ def main():
                 "path": {"section2": "hb_cr3bp_section2 per tube (propagate + screen + record -> step scan -> emit -> order+dedup)",
                          "section3": "hb_cr3bp_section3 per tube (propagating + scanning warps in one kernel -> emit -> order+dedup)",
                          "fused": "hb_cr3bp_section per tube (fused kernel)"}[args.pipeline],
+                "tube_scheduling": ("the two tubes' pipelines on two streams, a step scratch each: a persistent propagation "
+                                    "launch's idle tail is covered by the other tube's kernels" if args.concurrent_tubes
+                                    else "one tube after the other on one stream"),
                 "steps_capacity": args.steps_capacity if args.pipeline == "section2" else None,
                 "step_records": None if args.pipeline != "section2" else
                                 {"mode": args.records, "written_per_pass_this_gpu": records_written,
