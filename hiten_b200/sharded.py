@@ -100,7 +100,9 @@ class PeerExchange:
     Rank r owns slot r: [8 doubles of header | hit records | end states].  A rank fills its slot with plain device-to-
     device copies on its own copy stream -- cudaMemcpyAsync on a peer-mapped pointer, i.e. the copy engines: no SM is
     needed, so the copies of one tube overlap the persistent propagation kernel of the next, which owns every register
-    of every SM.  finish() is the only synchronisation: a stream-ordered barrier over the group's signal pads."""
+    of every SM.  finish() is the only synchronisation: a stream-ordered barrier over the group's signal pads.  Every
+    put() must be followed by finish() on all ranks before the next put(); the tensors received() returns are views of
+    the receive buffer and are overwritten by the next exchange."""
 
     HEADER = 8
 
@@ -155,9 +157,11 @@ class DistributedTubeSection:
     `runner_factory(n_local)` builds the rank's runner -- by default a TubeSectionRunner on the current device."""
 
     def __init__(self, n_global, mu, t_eval, section, *, forward=1, flip=None, integ=None, steps_capacity=192,
-                 pool_records=0, hit_capacity=None, runner_factory=None, group=None, exchange="auto"):
+                 pool_records=0, hit_capacity=None, runner_factory=None, group=None, exchange="auto",
+                 peer_hit_slots=None):
         """exchange: "peer" (PeerExchange), "nccl" (padded gather) or "auto" (peer when the process group runs on NCCL
-        and symmetric memory can be set up, else nccl; HITEN_B200_EXCHANGE overrides)."""
+        and symmetric memory can be set up, else nccl; HITEN_B200_EXCHANGE overrides).  peer_hit_slots: hit records per
+        rank the receive buffer holds (default 4 per trajectory; more hits than that raise)."""
         import os
         import torch.distributed as dist
         self.dist, self.group = dist, group
@@ -178,7 +182,8 @@ class DistributedTubeSection:
         if self.world > 1 and self._exchange in ("auto", "peer") and hasattr(self.runner, "yf") \
                 and getattr(self.runner.yf, "is_cuda", False):
             try:
-                self.px = PeerExchange(max(1024, 3 * self.n_max), self.n_max, self.runner.yf.device, group)
+                slots = int(peer_hit_slots) if peer_hit_slots else max(1024, 4 * self.n_max)
+                self.px = PeerExchange(slots, self.n_max, self.runner.yf.device, group)
             except Exception as exc:                       # no peer mapping on this box / backend: NCCL gather instead
                 if self._exchange == "peer":
                     raise
@@ -205,14 +210,37 @@ class DistributedTubeSection:
             px.cnt_host.copy_(run.ws[:4], non_blocking=True)      # cursor, hit_count, overflow, rec_overflow
         px.stream.synchronize()
         k, dropped, rec_over = int(px.cnt_host[1]), int(px.cnt_host[2]), int(px.cnt_host[3])
-        if dropped or rec_over or k > px.hit_slots:
-            k = run.hit_count(stream)                          # rare: regrow / rerun on the main stream, then copy
-            k = min(k, run._main_hits, px.hit_slots)
+        hits = run.hits
+        if dropped or rec_over:
+            # rare: the hit buffer was too small (regrow + relaunch) or trajectories outgrew the step scratch (rerun with
+            # the fused kernel) -- completed on the main stream; the rerun trajectories' records travel with the rest
+            with torch.cuda.stream(main):
+                k, hits = self._all_records(main)
             px.stream.wait_stream(main)
         else:
             run._main_hits, run._extra = k, (None, None)
-        px.put(k, run.hits, run.yf.view(-1)[: 6 * len(self.index)])
+        if k > px.hit_slots:
+            from ._lib import HitenB200Error
+            raise HitenB200Error(f"peer exchange: {k} hits on rank {self.rank} exceed the {px.hit_slots} record slots of its "
+                                 "share of rank 0's receive buffer; pass a larger peer_hit_slots")
+        px.put(k, hits, run.yf.view(-1)[: 6 * len(self.index)])
         return True
+
+    def _all_records(self, stream=None):
+        """(k, device tensor holding k 72-byte records): this shard's hits including those of the trajectories that were
+        rerun with the fused kernel (kept on the host by the runner)."""
+        run = self.runner
+        k = run.hit_count(stream)
+        km = run._main_hits
+        extra = run._extra if run._extra is not None else (None, None)
+        if extra[1] is None or not len(extra[1].times):
+            return km, run.hits
+        idx, h = extra
+        rec = np.empty(len(h.times), dtype=_syn.HIT_DTYPE)
+        rec["traj"], rec["seq"] = idx[h.trajectory_indices], _syn._seq_within(h.trajectory_indices)
+        rec["t"], rec["state"] = h.times, h.states
+        ext = torch.from_numpy(rec.view(np.float64).copy()).to(run.hits.device)
+        return k, torch.cat((run.hits[: km * 9], ext))
 
     def finish_gather(self):
         """Second half: all ranks' copies have landed on rank 0.  -> (hit record tensors per rank | None, counts | None,
@@ -231,15 +259,15 @@ class DistributedTubeSection:
             return self.finish_gather()
         dist, run = self.dist, self.runner
         dev = run.yf.device
-        k = torch.tensor([run.hit_count()], dtype=torch.int64, device=dev)      # also completes overflow reruns
+        kk, recs = self._all_records()                                          # also completes overflow reruns
+        k = torch.tensor([kk], dtype=torch.int64, device=dev)
         if self.world == 1:
-            return [run.hits[: int(k.item()) * 9]], k, [run.yf]
+            return [recs[: kk * 9]], k, [run.yf]
         counts = [torch.zeros_like(k) for _ in range(self.world)]
         dist.all_gather(counts, k, group=self.group)
         kmax = int(max(int(c.item()) for c in counts))
         send = torch.zeros(max(kmax, 1) * 9, dtype=torch.float64, device=dev)
-        km = min(int(k.item()), run._main_hits)
-        send[: km * 9] = run.hits[: km * 9]
+        send[: kk * 9] = recs[: kk * 9]
         yf = torch.zeros((6, self.n_max), dtype=torch.float64, device=dev)
         yf[:, : len(self.index)] = run.yf.view(6, -1)
         if self.rank == 0:

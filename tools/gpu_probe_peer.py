@@ -10,13 +10,14 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 n_total = int(sys.argv[1]) if len(sys.argv) > 1 else 200_000
+cap = int(sys.argv[2]) if len(sys.argv) > 2 else 128          # a small step capacity forces reruns with the fused kernel
 ics, mu = W.c5_batch(n_total * world, rank, world)
 res = {}
 for mode in ("nccl", "peer"):
     ds = {}
     for key in ("l1", "l2"):
         ds[key] = sharded.DistributedTubeSection(n_total * world // 2, mu, W.c5_grid(key), W.c5_section(key, mu),
-                                                 forward=W.C5_TUBES[key]["forward"], flip=(0, 6), steps_capacity=128,
+                                                 forward=W.C5_TUBES[key]["forward"], flip=(0, 6), steps_capacity=cap,
                                                  exchange=mode)
     y0 = {key: torch.from_numpy(np.ascontiguousarray(ics[key].T)).cuda() for key in ds}
     out = None
@@ -31,7 +32,10 @@ for mode in ("nccl", "peer"):
         else:
             out = {key: ds[key].gather_device() for key in ds}
         torch.cuda.synchronize(); dist.barrier(); dt = time.perf_counter() - t0
+    local = torch.tensor([ds[key].runner.hit_count() for key in ds], dtype=torch.int64, device="cuda")
+    dist.all_reduce(local)
     if rank == 0:
+        assert [int(out[key][1].sum()) for key in ds] == local.tolist(), (mode, local.tolist())
         res[mode] = {key: ([h.clone() for h in out[key][0]], out[key][1].clone(), [y.clone() for y in out[key][2]]) for key in ds}
         print(mode, "ms per step", 1e3 * dt, "hits", {key: int(out[key][1].sum()) for key in ds})
 if rank == 0:
