@@ -340,8 +340,9 @@ def secondary_configs(hb, torch, steps, flush, barrier):
         out[label] = {"distinct_lifted_seeds": int(torch.unique(seeds, dim=0).shape[0]),
                       "steps_per_s": cm_steps * steps / t, "crossings_per_s": int(f.sum().item()) * steps / t,
                       "ms_per_return": 1e3 * t / steps, "tflops": cm_steps * steps * 8100.0 / t / 1e12}
-    out["cm_map_tao4_1e5_seeds"]["note"] = ("critical-path bound: the slowest seed needs ~1300 sequential steps of "
-                                            "~9 us (11.9 ms on its own); 1e6 seeds fill the machine")
+    out["cm_map_tao4_1e5_seeds"]["note"] = ("critical-path bound: the slowest seed needs ~1300 sequential steps; the late "
+                                            "rounds (short work lists) run with four warps per 32 seeds (cm_map_split: "
+                                            "~5.6 us per step instead of ~9.2); 1e6 seeds fill the machine")
     # the Tao integrator CLASS over a time grid (_ExtendedSymplectic.integrate): 1e5 trajectories x 100 grid intervals
     from hiten_b200 import symplectic as symp
     y6 = torch.zeros((100_000, 6), dtype=torch.float64, device="cuda")

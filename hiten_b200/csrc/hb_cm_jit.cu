@@ -94,6 +94,68 @@ std::string gen_grad(const std::vector<TermHost> &terms, const int64_t *ptr)
     return s;
 }
 
+// The same gradient split over the four warps of a CTA (cm_map_split below): warp w evaluates the partial derivatives
+// assigned to it -- whole partials, each summed exactly as in grad(), so the numbers are the same -- and the warps exchange
+// them through shared memory.  Partials are dealt out by descending term count to the least loaded warp.
+std::string gen_grad_parts(const std::vector<TermHost> &terms, const int64_t *ptr)
+{
+    int owner[6], load[4] = {0, 0, 0, 0}, order[6] = {0, 1, 2, 3, 4, 5};
+    for (int a = 0; a < 6; ++a)
+        for (int b = a + 1; b < 6; ++b)
+            if (ptr[order[b] + 1] - ptr[order[b]] > ptr[order[a] + 1] - ptr[order[a]]) { const int t = order[a]; order[a] = order[b]; order[b] = t; }
+    for (int a = 0; a < 6; ++a) {
+        int w = 0;
+        for (int c = 1; c < 4; ++c) if (load[c] < load[w]) w = c;
+        owner[order[a]] = w;
+        load[w] += (int)(ptr[order[a] + 1] - ptr[order[a]]) + 1;
+    }
+    std::string s;
+    for (int w = 0; w < 4; ++w) {
+        int maxe[6] = {0, 0, 0, 0, 0, 0};
+        for (int q = 0; q < 6; ++q) {
+            if (owner[q] != w) continue;
+            for (int64_t i = ptr[q]; i < ptr[q + 1]; ++i)
+                for (int v = 0; v < 6; ++v) {
+                    const int e = (int)((terms[(size_t)i].ex >> (8 * v)) & 0xff);
+                    if (e > maxe[v]) maxe[v] = e;
+                }
+        }
+        appendf(s, "DEV void grad_part%d(const double (&pt)[6], double *gs, int lane)\n{\n", w);
+        for (int v = 0; v < 6; ++v)
+            for (int e = 1; e <= maxe[v]; ++e) {
+                if (e == 1) appendf(s, "    const double w%d_1 = pt[%d];\n", v, v);
+                else appendf(s, "    const double w%d_%d = MUL(w%d_%d, pt[%d]);\n", v, e, v, e - 1, v);
+            }
+        for (int q = 0; q < 6; ++q) {
+            if (owner[q] != w) continue;
+            appendf(s, "    {\n        double tot = 0.0, acc = 0.0;\n");
+            int dcur = -1;
+            for (int64_t i = ptr[q]; i < ptr[q + 1]; ++i) {
+                const TermHost &t = terms[(size_t)i];
+                const int d = (int)(t.ex >> 48);
+                if (d != dcur) {
+                    if (dcur >= 0) s += "        tot = ADD(tot, acc); acc = 0.0;\n";
+                    dcur = d;
+                }
+                std::string prod;
+                for (int v = 0; v < 6; ++v) {
+                    const int e = (int)((t.ex >> (8 * v)) & 0xff);
+                    if (!e) continue;
+                    char wn[32];
+                    snprintf(wn, sizeof wn, "w%d_%d", v, e);
+                    prod = prod.empty() ? std::string(wn) : "MUL(" + prod + ", " + wn + ")";
+                }
+                if (prod.empty()) prod = "1.0";
+                s += "        acc = MADD(" + hexf(t.coef) + ", " + prod + ", acc);\n";
+            }
+            if (dcur >= 0) s += "        tot = ADD(tot, acc);\n";
+            appendf(s, "        gs[%d * 32 + lane] = tot;\n    }\n", q);
+        }
+        s += "}\n";
+    }
+    return s;
+}
+
 template <int S>
 std::string gen_rk_step(const double (&A)[S][S], const double (&B)[S])
 {
@@ -113,7 +175,7 @@ std::string gen_rk_step(const double (&A)[S][S], const double (&B)[S])
             if (A[i][j] != 0.0)
                 appendf(s, "            { const double ha = MUL(DT, %s); UNROLL for (int d = 0; d < 6; ++d) ys[d] = MADD(ha, k[%d][d], ys[d]); }\n",
                         hexf(A[i][j]).c_str(), j);
-        appendf(s, "            rhs(ys, k[%d]);\n", i);
+        appendf(s, "            RHS(ys, k[%d]);\n", i);
     }
     s += "            UNROLL for (int d = 0; d < 6; ++d) sn[d] = so[d];\n";
     for (int j = 0; j < S; ++j)
@@ -154,6 +216,8 @@ DEV void rhs(const double (&y)[6], double (&dy)[6])          // [dH/dP, -dH/dQ]
     dy[0] = g[3]; dy[1] = g[4]; dy[2] = g[5];
     dy[3] = -g[0]; dy[4] = -g[1]; dy[5] = -g[2];
 }
+#define GRAD(a, b) grad(a, b)
+#define RHS(a, b) rhs(a, b)
 DEV double hermite(double s, double y0, double y1, double dy0, double dy1)
 {
     const double oms = SUB(1.0, s);
@@ -177,6 +241,7 @@ extern "C" __global__ void __launch_bounds__(256) cm_map(const double *seeds, lo
     // ONE flat loop: a lane that is done with its item pulls the next one at the top of the same loop (with the
     // item loop nested around the step loop the lanes of a warp reconverge behind the step loop).
     const long long count = list_in ? (long long)*count_in : n;
+    if (list_in && count <= SPLIT_MAX) return;               // a short list: cm_map_split takes this round
     double so[6], sn[6], rn[6], ro[6];
     double elapsed = 0.0;
     long long idx = -1;
@@ -211,7 +276,7 @@ extern "C" __global__ void __launch_bounds__(256) cm_map(const double *seeds, lo
                     const double *sd = seeds + idx * 4;
                     so[0] = 0.0; so[1] = sd[0]; so[2] = sd[2]; so[3] = 0.0; so[4] = sd[1]; so[5] = sd[3];
 #if !TAO
-                    rhs(so, ro);
+                    RHS(so, ro);
 #else
                     UNROLL for (int d = 0; d < 6; ++d) ro[d] = 0.0;
 #endif
@@ -252,7 +317,7 @@ const char *TAO_STEP = R"SRC(
                         const bool isA = (ph == 0) || (ph == 4);         // phi_a: (Q,Y); phi_b: (X,P)
                         double pt[6], g[6];
                         UNROLL for (int i = 0; i < 3; ++i) { pt[i] = isA ? Q[i] : X[i]; pt[3 + i] = isA ? Y[i] : P[i]; }
-                        grad(pt, g);
+                        GRAD(pt, g);
                         UNROLL for (int i = 0; i < 3; ++i) {
                             const double dq = MUL(hd, g[i]), dp = MUL(hd, g[3 + i]);
                             if (isA) { P[i] = SUB(P[i], dq); X[i] = ADD(X[i], dp); }
@@ -265,7 +330,7 @@ const char *TAO_STEP = R"SRC(
 )SRC";
 
 const char *KERNEL_TAIL = R"SRC(
-            rhs(sn, rn);
+            RHS(sn, rn);
             const double f_old = so[FIDX], f_new = sn[FIDX];
             bool crossed = false;
             if (!(MUL(f_old, f_new) >= 0.0)) crossed = GOOD_DIR;
@@ -274,7 +339,7 @@ const char *KERNEL_TAIL = R"SRC(
             if (crossed) {
                 const double alpha = DIV(f_old, SUB(f_old, f_new));
 #if TAO
-                rhs(so, ro);
+                RHS(so, ro);
 #endif
                 o0 = hermite(alpha, so[1], sn[1], ro[1], rn[1]);
                 o1 = hermite(alpha, so[4], sn[4], ro[4], rn[4]);
@@ -304,12 +369,161 @@ const char *KERNEL_TAIL = R"SRC(
 }
 )SRC";
 
+// cm_map_split: the late rounds of the map.  Return times are heavy-tailed, so the last rounds hold a few thousand seeds
+// and the time of a return is the slowest seed's ~1300 sequential steps: a warp alone on an SM sub-partition issues one
+// FP64 instruction every 2.9 cycles whatever the rest of the machine does.  Here FOUR warps (one per sub-partition) share
+// 32 seeds: every warp carries the full state of the CTA's seeds, evaluates its quarter of the gradient's partial
+// derivatives (grad_part<w>) and the warps exchange them through shared memory -- one CTA barrier per gradient, double
+// buffered.  Every partial is summed by one warp in the reference's order, so the numbers are those of cm_map; all warps
+// apply the same updates and take the same decisions, warp 0 writes.  Barriers must be reached by every thread, so the
+// step is executed unconditionally (idle slots integrate a dummy state) and the crossing-only gradient is taken CTA-wide.
+const char *SPLIT_HEAD = R"SRC(
+#undef GRAD
+#undef RHS
+DEV void grad_split(const double (&pt)[6], double (&g)[6], double *gsh, int &ph, int w, int lane)
+{
+    double *gs = gsh + ph * 192;
+    if (w == 0) grad_part0(pt, gs, lane);
+    else if (w == 1) grad_part1(pt, gs, lane);
+    else if (w == 2) grad_part2(pt, gs, lane);
+    else grad_part3(pt, gs, lane);
+    __syncthreads();
+    UNROLL for (int q = 0; q < 6; ++q) g[q] = gs[q * 32 + lane];
+    ph ^= 1;
+}
+DEV void rhs_split(const double (&y)[6], double (&dy)[6], double *gsh, int &ph, int w, int lane)
+{
+    double g[6];
+    grad_split(y, g, gsh, ph, w, lane);
+    dy[0] = g[3]; dy[1] = g[4]; dy[2] = g[5];
+    dy[3] = -g[0]; dy[4] = -g[1]; dy[5] = -g[2];
+}
+#define GRAD(a, b) grad_split(a, b, gsh, xbuf_, warp_, lane_)
+#define RHS(a, b) rhs_split(a, b, gsh, xbuf_, warp_, lane_)
+extern "C" __global__ void __launch_bounds__(128) cm_map_split(const double *seeds, long long n, int *flags, double *out,
+                                                               double *t_out, u64 *cursor, const int *list_in,
+                                                               const int *count_in, int *list_out, int *count_out,
+                                                               double *cont)
+{
+    const long long count = list_in ? (long long)*count_in : n;
+    if (count > SPLIT_MAX) return;                           // a long list: cm_map takes this round
+    __shared__ double gsh[2 * 192];
+    __shared__ long long item_sh[32];
+    const int warp_ = threadIdx.x >> 5, lane_ = threadIdx.x & 31;
+    int xbuf_ = 0;
+    double so[6], sn[6], rn[6], ro[6];
+    UNROLL for (int d = 0; d < 6; ++d) { so[d] = 0.0; ro[d] = 0.0; }
+    double elapsed = 0.0;
+    long long idx = -1;
+    int it = 0, it_stop = 0;
+    bool have = false, exhausted = false, first_fill = true;
+    for (;;) {
+        // refill: warp 0 hands out the items, every warp loads the same seed into its replica of slot `lane_`
+        if (warp_ == 0) {
+            long long k = -2;                                // -2: slot busy (or done), nothing to hand out
+            if (!have && !exhausted) {
+                if (first_fill) k = (long long)blockIdx.x * 32 + lane_;
+                else k = (long long)gridDim.x * 32 + (long long)atomicAdd(cursor, 1ULL);
+                if (k >= count) k = -1;
+            }
+            item_sh[lane_] = k;
+        }
+        first_fill = false;
+        __syncthreads();
+        const long long k = item_sh[lane_];
+        if (k >= 0) {
+            if (list_in) {
+                idx = list_in[k];
+                const double *c = cont + idx * 16;
+                elapsed = c[0]; it = (int)c[1];
+                UNROLL for (int d = 0; d < 6; ++d) { so[d] = c[2 + d]; ro[d] = c[8 + d]; }
+                have = true;
+            } else {
+                idx = k;
+                const double *sd = seeds + idx * 4;
+                so[0] = 0.0; so[1] = sd[0]; so[2] = sd[2]; so[3] = 0.0; so[4] = sd[1]; so[5] = sd[3];
+                UNROLL for (int d = 0; d < 6; ++d) ro[d] = 0.0;
+                elapsed = 0.0; it = 0;
+                have = MAX_STEPS > 0;
+                if (!have && warp_ == 0) {
+                    flags[idx] = 0; t_out[idx] = 0.0;
+                    out[idx * 4 + 0] = 0.0; out[idx * 4 + 1] = 0.0; out[idx * 4 + 2] = 0.0; out[idx * 4 + 3] = 0.0;
+                }
+            }
+            it_stop = it + QUOTA;
+        } else if (k == -1) {
+            exhausted = true;
+        }
+        const bool fresh = (k >= 0) && !list_in;
+        if (__syncthreads_and(!have && exhausted)) break;
+#if !TAO
+        if (__syncthreads_or(fresh)) {                       // rhs of a new seed (fixed-step RK keeps f(so) across steps)
+            double r0[6];
+            RHS(so, r0);
+            if (fresh) { UNROLL for (int d = 0; d < 6; ++d) ro[d] = r0[d]; }
+        }
+#endif
+        {
+)SRC";
+
+const char *SPLIT_TAIL = R"SRC(
+            RHS(sn, rn);
+            const double f_old = so[FIDX], f_new = sn[FIDX];
+            bool crossed = false;
+            if (have && !(MUL(f_old, f_new) >= 0.0)) crossed = GOOD_DIR;
+            double tc = 0.0, o0 = 0.0, o1 = 0.0, o2 = 0.0, o3 = 0.0;
+            bool done = false;
+#if TAO
+            if (__syncthreads_or(crossed)) {                 // the crossing-only gradient, taken by the whole CTA
+                double r0[6];
+                RHS(so, r0);
+                if (crossed) { UNROLL for (int d = 0; d < 6; ++d) ro[d] = r0[d]; }
+            }
+#endif
+            if (crossed) {
+                const double alpha = DIV(f_old, SUB(f_old, f_new));
+                o0 = hermite(alpha, so[1], sn[1], ro[1], rn[1]);
+                o1 = hermite(alpha, so[4], sn[4], ro[4], rn[4]);
+                o2 = hermite(alpha, so[2], sn[2], ro[2], rn[2]);
+                o3 = hermite(alpha, so[5], sn[5], ro[5], rn[5]);
+                tc = ADD(elapsed, MUL(alpha, DT));
+                done = true;
+            } else if (have) {
+                UNROLL for (int d = 0; d < 6; ++d) { so[d] = sn[d]; ro[d] = rn[d]; }
+                elapsed = ADD(elapsed, DT);
+                done = ++it >= MAX_STEPS;
+            }
+            if (have && done) {
+                if (warp_ == 0) {
+                    flags[idx] = crossed ? 1 : 0;
+                    t_out[idx] = tc;
+                    out[idx * 4 + 0] = o0; out[idx * 4 + 1] = o1; out[idx * 4 + 2] = o2; out[idx * 4 + 3] = o3;
+                }
+                have = false;
+            } else if (have && it >= it_stop) {               // quota used up: park the state for the next round
+                if (warp_ == 0) {
+                    double *c = cont + idx * 16;
+                    c[0] = elapsed; c[1] = (double)it;
+                    UNROLL for (int d = 0; d < 6; ++d) { c[2 + d] = so[d]; c[8 + d] = ro[d]; }
+                    list_out[atomicAdd(count_out, 1)] = (int)idx;
+                }
+                have = false;
+            }
+            if (!have) { UNROLL for (int d = 0; d < 6; ++d) { so[d] = 0.0; ro[d] = 0.0; } }   // idle slot: dummy state
+        }
+    }
+}
+)SRC";
+
+// seeds per round up to which cm_map_split runs it: four 128-thread CTAs per SM, 32 seeds each
+constexpr int HB_CM_SPLIT_MAX = 148 * 4 * 32;
+
 std::string gen_source(const std::vector<TermHost> &terms, const int64_t *ptr, const hb_cm_opts &o)
 {
     std::string s;
     const bool tao = o.method == HB_SYMPLECTIC;
-    appendf(s, "#define PARITY %d\n#define TAO %d\n#define MAX_STEPS %d\n#define DT %s\n#define QUOTA %d\n",
-            o.arith == HB_ARITH_PARITY ? 1 : 0, tao ? 1 : 0, o.max_steps, hexf(o.dt).c_str(), HB_CM_QUOTA);
+    appendf(s, "#define PARITY %d\n#define TAO %d\n#define MAX_STEPS %d\n#define DT %s\n#define QUOTA %d\n#define SPLIT_MAX %d\n",
+            o.arith == HB_ARITH_PARITY ? 1 : 0, tao ? 1 : 0, o.max_steps, hexf(o.dt).c_str(), HB_CM_QUOTA, HB_CM_SPLIT_MAX);
     static const int fidx[4] = {1, 4, 2, 5};                       // q2, p2, q3, p3 in [q1,q2,q3,p1,p2,p3]
     static const char *good[4] = {"(sn[4] > 0.0)", "(rn[1] > 0.0)", "(sn[5] > 0.0)", "(rn[2] > 0.0)"};
     appendf(s, "#define FIDX %d\n#define GOOD_DIR %s\n", fidx[o.section], good[o.section]);
@@ -324,12 +538,18 @@ std::string gen_source(const std::vector<TermHost> &terms, const int64_t *ptr, c
     }
     s += PRELUDE;
     s += gen_grad(terms, ptr);
+    s += gen_grad_parts(terms, ptr);
+    std::string step;
+    if (tao) step = TAO_STEP;
+    else if (o.method == HB_RK4) step = gen_rk_step<4>(HB_RK4_A, HB_RK4_B);
+    else if (o.method == HB_RK6) step = gen_rk_step<7>(HB_RK6_A, HB_RK6_B);
+    else step = gen_rk_step<13>(HB_RK8_A, HB_RK8_B);
     s += KERNEL_HEAD;
-    if (tao) s += TAO_STEP;
-    else if (o.method == HB_RK4) s += gen_rk_step<4>(HB_RK4_A, HB_RK4_B);
-    else if (o.method == HB_RK6) s += gen_rk_step<7>(HB_RK6_A, HB_RK6_B);
-    else s += gen_rk_step<13>(HB_RK8_A, HB_RK8_B);
+    s += step;
     s += KERNEL_TAIL;
+    s += SPLIT_HEAD;
+    s += step;
+    s += SPLIT_TAIL;
     return s;
 }
 
@@ -500,8 +720,9 @@ struct Api {
 
 std::mutex g_mu;
 Api g_api;
-// (device ordinal, generated source) -> CUfunction.  A CUfunction belongs to the context that was current at
-// cuModuleLoadData -- the primary context of the current device -- so every device gets its own module.
+// (device ordinal, generated source) -> CUmodule, (the same, kernel name) -> CUfunction.  A module belongs to the context
+// that was current at cuModuleLoadData -- the primary context of the current device -- so every device gets its own.
+std::unordered_map<std::string, void *> g_modules;
 std::unordered_map<std::string, void *> g_functions;
 inline std::string fn_key(const std::string &src)
 {
@@ -611,17 +832,22 @@ extern "C" int hb_cm_jit_compile_host(const void *terms_host, const int64_t *ptr
 static int get_function(const std::string &src, const char *name, void **fn_out)
 {
     std::lock_guard<std::mutex> lk(g_mu);
-    const std::string key = fn_key(src);
+    const std::string mkey = fn_key(src), key = std::string(name) + "|" + mkey;
     auto it = g_functions.find(key);
     if (it != g_functions.end()) { *fn_out = it->second; return HB_OK; }
     if (!load_driver()) return HB_ERR_NODEVICE;
-    std::vector<char> cubin;
-    int rc = compile_cubin(src, cubin);
-    if (rc != HB_OK) return rc;
     void *mod = nullptr, *fn = nullptr;
-    int e = g_api.load(&mod, cubin.data());
-    if (e != 0) return 1000 + e;
-    e = g_api.getfn(&fn, mod, name);
+    auto im = g_modules.find(mkey);
+    if (im != g_modules.end()) mod = im->second;
+    else {
+        std::vector<char> cubin;
+        const int rc = compile_cubin(src, cubin);
+        if (rc != HB_OK) return rc;
+        const int e = g_api.load(&mod, cubin.data());
+        if (e != 0) return 1000 + e;
+        g_modules.emplace(mkey, mod);
+    }
+    const int e = g_api.getfn(&fn, mod, name);
     if (e != 0) return 1000 + e;
     g_functions.emplace(key, fn);
     *fn_out = fn;
@@ -705,8 +931,10 @@ extern "C" int hb_cm_poincare_map_jit(const hb_polyham *ham, const hb_cm_opts *o
         HB_CUDA_TRY(cudaStreamSynchronize(st));
     }
     const std::string src = gen_source(terms, ham->ptr, *opts);
-    void *fn = nullptr;
+    void *fn = nullptr, *fn_split = nullptr;
     rc = get_function(src, "cm_map", &fn);
+    if (rc != HB_OK) return rc;
+    rc = get_function(src, "cm_map_split", &fn_split);
     if (rc != HB_OK) return rc;
     HB_CUDA_TRY(cudaMemsetAsync(workspace, 0, sizeof(HbWorkspace), st));
     int dev = 0, sms = 148, per_sm = 2;
@@ -718,6 +946,14 @@ extern "C" int hb_cm_poincare_map_jit(const hb_polyham *ham, const hb_cm_opts *o
     const long long cap = (long long)sms * per_sm;
     if (blocks > cap) blocks = cap;
     if (n > 2147483647LL) return HB_ERR_UNSUPPORTED;
+    // cm_map_split (four warps per 32 seeds) takes the rounds whose work list is short -- and a small batch from the start
+    int per_sm_split = 4;
+    if (g_api.occ && g_api.occ(&per_sm_split, fn_split, 128, 0) != 0) per_sm_split = 4;
+    if (per_sm_split < 1) per_sm_split = 1;
+    if (per_sm_split > 4) per_sm_split = 4;
+    const long long n_split = n < HB_CM_SPLIT_MAX ? n : HB_CM_SPLIT_MAX;
+    long long blocks_split = (n_split + 31) / 32;
+    if (blocks_split > (long long)sms * per_sm_split) blocks_split = (long long)sms * per_sm_split;
     // rounds of HB_CM_QUOTA steps; round r resumes what round r-1 parked (device-side lists and counts: no host
     // synchronisation, rounds without work return at once)
     const int rounds = opts->max_steps > 0 ? (opts->max_steps + HB_CM_QUOTA - 1) / HB_CM_QUOTA : 1;
@@ -753,7 +989,10 @@ extern "C" int hb_cm_poincare_map_jit(const hb_polyham *ham, const hb_cm_opts *o
         int *count_out = (int *)(ctr + 16 * (size_t)r + 8);
         void *args[] = {(void *)&seeds, (void *)&nn, (void *)&flags, (void *)&out, (void *)&t_out, (void *)&cursor,
                         (void *)&list_in, (void *)&count_in, (void *)&list_out, (void *)&count_out, (void *)&cont};
-        e = g_api.launch(fn, (unsigned)blocks, 1, 1, 256, 1, 1, 0, (void *)st, args, nullptr);
+        // each kernel looks at the round's count and returns at once when the other form takes it; round 0's count is n
+        if (r > 0 || n > HB_CM_SPLIT_MAX) e = g_api.launch(fn, (unsigned)blocks, 1, 1, 256, 1, 1, 0, (void *)st, args, nullptr);
+        if (e == 0 && (r > 0 || n <= HB_CM_SPLIT_MAX))
+            e = g_api.launch(fn_split, (unsigned)blocks_split, 1, 1, 128, 1, 1, 0, (void *)st, args, nullptr);
     }
     cudaFreeAsync(tmp, st);
     return e == 0 ? HB_OK : 1000 + e;

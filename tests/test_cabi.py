@@ -51,7 +51,12 @@ def test_specialised_cm_kernel_compiles_offline():
         for arith in ("parity", "fast"):
             nbytes, src = cm.jit_compile_host(tab, cm.make_opts(0.01, 2000, method, order, "p3", 20.0, arith), True)
             assert nbytes > 10_000
-            assert src.count("acc = MADD(") == 119 and "extern \"C\" __global__" in src
+            # 119 terms in grad() and the same 119 dealt out over grad_part0..3 (cm_map_split: four warps per 32 seeds)
+            assert src.count("acc = MADD(") == 2 * 119 and "extern \"C\" __global__" in src
+            parts = [src.split(f"DEV void grad_part{w}(")[1].split("DEV void grad_part" if w < 3 else "const char")[0]
+                     for w in range(4)]
+            counts = [p_.split("\n}\n")[0].count("acc = MADD(") for p_ in parts]
+            assert sum(counts) == 119 and max(counts) <= 40, counts
 
 
 def test_tao_schedule_matches_reference_recursion():
