@@ -93,3 +93,22 @@ def test_iterated_map_on_device_matches_the_engine_loop():
     assert np.array_equal(tt.cpu().numpy(), np.concatenate(rt))
     assert np.array_equal(it.cpu().numpy(), np.concatenate(ri))
     assert len(rs) == 5 and st.shape[0] > 1000
+
+
+@pytest.mark.parametrize("order,symp", [(4, True), (4, False), (8, False)])
+def test_split_and_plain_kernels_hand_rounds_over_bit_exactly(order, symp):
+    """40000 DISTINCT seeds: round 0 runs in cm_map (the list is longer than the split threshold), the later rounds -- the
+    seeds that need more than 160 steps -- in cm_map_split (four warps per 32 seeds); 3000 seeds run in cm_map_split from
+    the start.  Both against the table-driven kernel (one thread per seed, no rounds): identical flags, states and times."""
+    from hiten_b200 import centermanifold as cmod
+    g = np.load(os.path.join(HERE, "golden", "cm_map.npz"))
+    tab = _table(g)
+    rng = np.random.default_rng(7)
+    base = g["seeds_p3"]
+    for n in (40_000, 3_000):
+        seeds = base[rng.integers(0, len(base), n)] * (1.0 - 0.5 * rng.random((n, 1)))
+        opts = cmod.make_opts(0.01, 2000, "symplectic" if symp else "fixed", order, "p3", 20.0)
+        f1, o1, t1 = cmod.poincare_map(tab, seeds, opts, jit=True)
+        f0, o0, t0 = cmod.poincare_map(tab, seeds, opts, jit=False)
+        assert f1.sum() > 0.99 * n and (t1 / 0.01).max() > 400          # several rounds were needed
+        assert np.array_equal(f1, f0) and np.array_equal(o1, o0) and np.array_equal(t1, t0)
