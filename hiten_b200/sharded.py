@@ -189,6 +189,11 @@ class DistributedTubeSection:
                     raise
                 self.px = None
                 self.peer_error = repr(exc)
+            # the exchange is collective: every rank must have come to the same choice
+            ok = torch.tensor([1 if self.px is not None else 0], dtype=torch.int32, device=self.runner.yf.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if int(ok.item()) == 0:
+                self.px = None
 
     def launch(self, y0_soa_local, stream=None):
         self.runner.launch(y0_soa_local, stream)
