@@ -263,12 +263,13 @@ __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) k_dop853_6(const PropP
         }
         {   // The controller's factor AFTER the record / screening block, where the stage vectors are dead (measured: 1 % off
             // the record kernel).  One convergent pow: accepted and rejected lanes evaluate err**(-1/9) and err**(-1/8) in the
-            // same instructions (the exponent is a per-lane operand).
+            // same instructions (the exponent is a per-lane operand); err_prev**alpha is carried from the step where
+            // err_prev was the current error and shares that step's logarithm (in the parity build `err_prev` holds that
+            // power, -1 before the first accepted step).
             const bool accepted = err <= 1.0;
-            const double h_factor = hb_pi_factor<AR>(err, err_prev, accepted, 8.0);
+            const double h_factor = hb_pi_factor_carried<AR>(err, err_prev, accepted, 8.0);   // err_prev: see there
             h = AR::mul(h, h_factor);
-            if (accepted) err_prev = err;
-            else h = hb_clamp_step(h, p.max_step, p.min_step);
+            if (!accepted) h = hb_clamp_step(h, p.max_step, p.min_step);
         }
         if (fin < 0) {
             if (!(h == h) || !(err == err)) fin = HB_TRAJ_NONFINITE;
