@@ -498,6 +498,10 @@ def main():
     ap.add_argument("--concurrent-tubes", type=int, default=1,
                     help="1: the two tubes' pipelines on two streams with a step scratch each; 0: one after the other")
     ap.add_argument("--arith", default="parity", choices=["parity", "fast"])
+    ap.add_argument("--max-ctas", default="auto",
+                    help="auto: when the two tubes run on two streams and a tube has fewer than 4 trajectories per lane of a "
+                         "full-device persistent launch, each tube's launch is capped at half the SMs so that the two run "
+                         "side by side (the strong-scaling shards); 0: every launch uses every SM; N: cap at N CTAs")
     ap.add_argument("--n-per-gpu", type=int, default=N_PER_GPU)
     ap.add_argument("--pipeline", default="section2", choices=["section2", "section3", "fused"],
                     help="section2: step records through an HBM scratch (default, fastest); section3: records handed over "
@@ -539,10 +543,21 @@ def main():
     kind = {"section2": dict(steps_capacity=args.steps_capacity, records=args.records), "section3": dict(pool_records=8), "fused": {}}[args.pipeline]
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)  # > 126 MB L2
 
+    sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+
+    def ctas_for(n_tube_local):
+        if args.max_ctas != "auto":
+            return int(args.max_ctas)
+        if not args.concurrent_tubes or args.pipeline == "section3":
+            return 0
+        return sm_count // 2 if n_tube_local < 4 * sm_count * 256 else 0
+
     def make_job(n_total_global):
         """Runners + resident inputs of this rank for a job of n_total_global trajectories (both tubes, all ranks)."""
         ics, mu = W.c5_batch(n_total_global, rank, world)
         job = {"ics": ics, "mu": mu, "tubes": {}}
+        integ = hb.make_integ(arith=args.arith, max_ctas=ctas_for(n_total_global // 2 // world))
+        job["max_ctas"] = int(integ.max_ctas)
         scratch = None
         for key in TUBES:
             x = ics[key]
@@ -563,6 +578,7 @@ def main():
 
     job = make_job(n * world)
     mu = job["mu"]
+    main_max_ctas = job["max_ctas"]
     peer_exchange = world > 1 and all(job["tubes"][key]["dist"].px is not None for key in TUBES)
 
     side = [torch.cuda.Stream(dev) for _ in TUBES] if args.concurrent_tubes else None
@@ -692,8 +708,10 @@ def main():
         ts = time_steps(sstep, args.steps, flush, barrier, torch)
         s_acc, s_rej, s_hits, _, s_ok = tallies(sjob)
         strong = [ts, float(s_acc + s_rej), float(s_hits)]
+        strong_max_ctas = sjob["max_ctas"]
     else:
         strong = [t_dev, float(steps_per_pass), float(n_hits)]
+        strong_max_ctas = main_max_ctas
 
     tt = torch.tensor([t_dev, e2e_t, float(steps_per_pass), float(n_hits), float(steps_acc), strong[0], strong[1], strong[2],
                        float(n_overflow)], dtype=torch.float64, device=dev)
@@ -712,6 +730,7 @@ def main():
     extra = {"strong_scaling": {"total_trajectories": n, "n_gpus": world, "ms_per_step": 1e3 * strong_t / args.steps,
                                 "rk_steps_per_s": strong_steps * args.steps / strong_t,
                                 "crossings_per_s": strong_hits * args.steps / strong_t,
+                                "max_ctas_per_launch": strong_max_ctas or None,
                                 "note": "configs[4]'s 1e6 trajectories in TOTAL, 1/N per GPU, same step incl. the gather; "
                                         "efficiency = rk_steps_per_s / (N x the N=1 value)"}}
     if not args.no_extra and world == 1:
@@ -858,6 +877,7 @@ def main():
                 "tube_scheduling": ("the two tubes' pipelines on two streams, a step scratch each: a persistent propagation "
                                     "launch's idle tail is covered by the other tube's kernels" if args.concurrent_tubes
                                     else "one tube after the other on one stream"),
+                "max_ctas_per_launch": main_max_ctas or None,
                 "steps_capacity": args.steps_capacity if args.pipeline == "section2" else None,
                 "step_records": None if args.pipeline != "section2" else
                                 {"mode": args.records, "written_per_pass_this_gpu": records_written,

@@ -324,6 +324,7 @@ int launch(PropParams &p, int arith, cudaStream_t st)
     }
     long long blocks_needed = (p.n + HB_BLOCK - 1) / HB_BLOCK;
     long long grid = (long long)HB_MINBLOCKS * sm_count();   // persistent: resident CTAs only
+    if (p.max_ctas > 0 && p.max_ctas < grid) grid = p.max_ctas;   // the caller shares the device between concurrent batches
     if (blocks_needed < grid) grid = blocks_needed;
     if (grid < 1) grid = 1;
     if (arith == HB_ARITH_PARITY) return launch_neg<ArParity, MODE>(p, (unsigned)grid, st);

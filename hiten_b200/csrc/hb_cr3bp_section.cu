@@ -282,6 +282,7 @@ int launch_section(const PropParams &p_in, cudaStream_t st)
     }
     long long blocks_needed = (p.n + HB_BLOCK - 1) / HB_BLOCK;
     long long grid = (long long)HB_MINBLOCKS * sm_count();
+    if (p.max_ctas > 0 && p.max_ctas < grid) grid = p.max_ctas;
     if (blocks_needed < grid) grid = blocks_needed;
     if (grid < 1) grid = 1;
     if (p.negmask == 0u) k_dop853_6_section<AR, 0><<<(unsigned)grid, HB_BLOCK, 0, st>>>(p);

@@ -596,6 +596,7 @@ extern "C" int hb_cr3bp_section3(const hb_cr3bp *sys, const hb_integ *integ, con
     p.desc_index = desc_index;
     sp.pool = pool; sp.pool_cap = pool_cap; sp.pool_count = pool_count;
     long long grid = sm_count();                                       // persistent: one CTA per SM
+    if (integ->max_ctas > 0 && integ->max_ctas < grid) grid = integ->max_ctas;
     const long long need = (n + 32 * PC_NP - 1) / (32 * PC_NP);
     if (need < grid) grid = need;
     rc = (integ->arith == HB_ARITH_PARITY) ? launch_pc1<ArParity>(sp, (unsigned)grid, st)

@@ -40,11 +40,11 @@ def make_sys(mu, forward=1, flip=None):
 
 
 def make_integ(method=L.HB_DOP853, arith="parity", rtol=1e-12, atol=1e-12, max_step=1e4, min_step=None,
-               max_attempts=0, n_fixed_steps=0):
+               max_attempts=0, n_fixed_steps=0, max_ctas=0):
     ar = {"parity": L.HB_ARITH_PARITY, "fast": L.HB_ARITH_FAST}[arith] if isinstance(arith, str) else int(arith)
     return L.HbInteg(int(method), ar, float(rtol), float(atol), float(max_step),
                      default_min_step() if min_step is None else float(min_step), int(max_attempts),
-                     int(n_fixed_steps), 0)
+                     int(n_fixed_steps), int(max_ctas))
 
 
 def _stream_ptr(stream=None):

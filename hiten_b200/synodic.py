@@ -105,14 +105,36 @@ def _auto_steps_capacity(n, device, want=160):
     return cap if cap >= 64 else 0
 
 
+def _auto_plan(n, device, records, free_bytes=None):
+    """(chunk, steps_capacity) for tube_section(steps_capacity="auto"): the kernel pipeline with a step scratch for `chunk`
+    trajectories at a time -- the whole batch when its scratch fits half of the free HBM, else equal chunks that do (a
+    B200 holds ~1.2e6 trajectories of sparse records per chunk; the chunks reuse one scratch).  (n, 0): tiny batch, fused
+    kernel.  free_bytes: override of the free-memory probe (tests)."""
+    if n < 256:
+        return n, 0
+    cap = 128 if records == "near" else 160
+    lib = L.load()
+    per_traj = int(lib.hb_section2_scratch_bytes(1024, cap)) / 1024.0 + 400.0     # + hits, end states, counters
+    free = torch.cuda.mem_get_info(device)[0] if free_bytes is None else int(free_bytes)
+    fit = int(0.5 * free / per_traj)
+    if fit >= n:
+        return n, cap
+    if fit < 1024:
+        return n, 0                                             # no room for a useful scratch: fused kernel, no scratch
+    n_chunks = -(-n // fit)
+    chunk = -(-n // n_chunks)
+    return chunk + (-chunk) % 256, cap
+
+
 def tube_section(y0, mu, t_eval, section, *, forward=1, flip=None, integ=None, hit_capacity=None, device=None,
-                 stream=None, ws=None, sort=True, steps_capacity="auto", records="near"):
+                 stream=None, ws=None, sort=True, steps_capacity="auto", records="near", _free_bytes=None):
     """Manifold.compute() + SynodicMap.compute() in one call: propagate a batch over the t_eval grid and detect the
     section hits on the device, without storing the dense tube.  Returns (SectionHits, BatchResult with end states).
 
-    steps_capacity: "auto" (default) picks the kernel pipeline hb_cr3bp_section2 when the batch is large enough and
-    its step scratch fits the free device memory, else the fused kernel hb_cr3bp_section; an int forces the scratch
-    size (0 = fused kernel).  Both give the same hits, bit for bit."""
+    steps_capacity: "auto" (default) picks the kernel pipeline hb_cr3bp_section2 when the batch is large enough -- in
+    equal chunks that reuse one step scratch when the whole batch's scratch does not fit half of the free device memory
+    (any batch size runs: 1e7 trajectories are ~9 chunks on a B200) -- else the fused kernel hb_cr3bp_section; an int
+    forces the scratch size (0 = fused kernel).  All forms give the same hits, bit for bit."""
     from . import propagate as P
     _require_cuda()
     lib = L.load()
@@ -120,8 +142,12 @@ def tube_section(y0, mu, t_eval, section, *, forward=1, flip=None, integ=None, h
     with torch.cuda.device(device):
         y0d, host = P._to_device_soa(y0, device)
         n = y0d.shape[1]
+        chunk = n
         if steps_capacity == "auto":
-            steps_capacity = _auto_steps_capacity(n, device) if sort else 0
+            chunk, steps_capacity = _auto_plan(n, device, records, _free_bytes) if sort else (n, 0)
+        if steps_capacity and sort and n > 0 and chunk < n:
+            return _tube_section_chunked(y0d, host, chunk, int(steps_capacity), mu, t_eval, section, forward, flip, integ,
+                                         device, stream, records)
         if steps_capacity and sort and n > 0:
             run = TubeSectionRunner(n, mu, t_eval, section, forward=forward, flip=flip, integ=integ,
                                     hit_capacity=hit_capacity, device=device, steps_capacity=int(steps_capacity),
@@ -168,6 +194,38 @@ def tube_section(y0, mu, t_eval, section, *, forward=1, flip=None, integ=None, h
         rec = rec[np.lexsort((rec["seq"], rec["traj"]))]
         pts = np.column_stack((rec["state"][:, section.proj_i], rec["state"][:, section.proj_j])) if k else np.empty((0, 2))
         return SectionHits(rec["traj"].copy(), rec["t"].copy(), rec["state"].copy(), pts, per[:n].cpu().numpy()), res
+
+
+def _tube_section_chunked(y0d, host, chunk, steps_capacity, mu, t_eval, section, forward, flip, integ, device, stream,
+                          records):
+    """tube_section over a batch whose step scratch does not fit: `chunk` trajectories at a time through one runner (and
+    one scratch); the last, shorter chunk gets a runner of its own size on the same scratch.  Trajectory indices of the
+    hits are those of the whole batch."""
+    from . import propagate as P
+    n = y0d.shape[1]
+    yf, nacc, nrej, status = P._alloc_out(n, device)
+    per = np.zeros(n, dtype=np.int32)
+    parts = []
+    run = None
+    for a in range(0, n, chunk):
+        b = min(a + chunk, n)
+        if run is None or run.n != b - a:
+            scratch = None if run is None else run.scratch
+            run = TubeSectionRunner(b - a, mu, t_eval, section, forward=forward, flip=flip, integ=integ, device=device,
+                                    steps_capacity=steps_capacity, records=records, scratch=scratch)
+        run.launch(y0d[:, a:b].contiguous(), stream)
+        h = run.sorted_hits(stream)
+        parts.append((h.trajectory_indices + a, h.times, h.states, h.points))
+        per[a:b] = h.hits_per_traj
+        yf[:, a:b] = run.yf
+        nacc[a:b], nrej[a:b], status[a:b] = run.nacc, run.nrej, run.status
+    hits = SectionHits(np.concatenate([q[0] for q in parts]), np.concatenate([q[1] for q in parts]),
+                       np.concatenate([q[2] for q in parts]), np.concatenate([q[3] for q in parts]), per)
+    if host:
+        res = P.BatchResult(yf.t().contiguous().cpu().numpy(), nacc.cpu().numpy(), nrej.cpu().numpy(), status.cpu().numpy())
+    else:
+        res = P.BatchResult(yf, nacc, nrej, status)
+    return hits, res
 
 
 class TubeSectionRunner:

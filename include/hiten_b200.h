@@ -75,7 +75,10 @@ typedef struct {
     double max_step, min_step;
     int64_t max_attempts; /* safety cap per trajectory (the reference has none); <=0 -> 2^31-1 */
     int32_t n_fixed_steps;/* fixed-step methods: number of equal steps over [t0, tf]             */
-    int32_t _pad;
+    int32_t max_ctas;     /* 0: the persistent DOP853 launches use every SM.  > 0: at most this many CTAs (one CTA owns an
+                             SM's register file), so that two small batches launched on two streams run side by side --
+                             each on its share of the SMs with twice as many trajectories per lane -- instead of one after
+                             the other with two launch tails (no counterpart in the reference; results do not depend on it) */
 } hb_integ;
 
 /* Plane event g(t,y) = y[idx] - offset (algorithms/poincare/singlehit/backend.py:30-67) with the

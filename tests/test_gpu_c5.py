@@ -147,3 +147,61 @@ def test_c5_whole_flow_on_the_device_gives_the_reference_connections():
     assert np.array_equal(r.point2d, g["conn_pt"])
     assert np.array_equal(r.state_u, g["conn_su"]) and np.array_equal(r.state_s, g["conn_ss"])
     assert np.array_equal(r.trajectory_index_u, g["conn_tiu"]) and np.array_equal(r.trajectory_index_s, g["conn_tis"])
+
+
+def test_c5_two_tubes_side_by_side_with_capped_grids_same_bits():
+    """hb_integ.max_ctas: the two tubes' pipelines on two streams, each persistent launch capped at half the SMs (how
+    bench.py runs the strong-scaling shards), against one uncapped tube after the other: hits, end states and step
+    counts bit for bit on 20000 trajectories per tube."""
+    import torch
+    import hiten_b200 as hb
+    from hiten_b200 import synodic
+    from hiten_b200 import workloads as W
+    ics, mu = W.c5_batch(40000)
+    dev = torch.device("cuda", 0)
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    res = {}
+    for cap in (0, max(sms // 2, 1)):
+        integ = hb.make_integ(max_ctas=cap)
+        runs, streams = {}, {}
+        for key in ("l1", "l2"):
+            runs[key] = synodic.TubeSectionRunner(len(ics[key]), mu, W.c5_grid(key), W.c5_section(key, mu),
+                                                  forward=W.C5_TUBES[key]["forward"], flip=(0, 6), integ=integ, device=dev,
+                                                  steps_capacity=128, records="near")
+            streams[key] = torch.cuda.Stream(dev) if cap else torch.cuda.current_stream()
+        y0 = {key: torch.from_numpy(np.ascontiguousarray(ics[key].T)).to(dev) for key in runs}
+        torch.cuda.synchronize()
+        for key in runs:
+            runs[key].launch(y0[key], streams[key])
+        torch.cuda.synchronize()
+        res[cap] = {key: (runs[key].sorted_hits(), runs[key].yf.cpu().numpy(), runs[key].nacc.cpu().numpy(),
+                          runs[key].nrej.cpu().numpy()) for key in runs}
+    a, b = res[0], res[max(sms // 2, 1)]
+    for key in a:
+        assert len(a[key][0].times) > 1000
+        assert np.array_equal(a[key][0].trajectory_indices, b[key][0].trajectory_indices)
+        assert np.array_equal(a[key][0].times, b[key][0].times) and np.array_equal(a[key][0].states, b[key][0].states)
+        for i in (1, 2, 3):
+            assert np.array_equal(a[key][i], b[key][i])
+
+
+def test_tube_section_in_chunks_equals_one_launch():
+    """tube_section(steps_capacity="auto") on a batch whose step scratch does not fit the free memory (forced here with
+    the free-memory override): three chunks through one scratch, the last one shorter -- same hits, counts and end states
+    as the single launch, trajectory indices of the whole batch."""
+    import hiten_b200 as hb
+    from hiten_b200 import synodic
+    from hiten_b200 import workloads as W
+    ics, mu = W.c5_batch(6000)
+    x = ics["l2"]
+    assert len(x) == 3000
+    kw = dict(forward=W.C5_TUBES["l2"]["forward"], flip=(0, 6))
+    chunk, cap = synodic._auto_plan(3000, "cuda:0", "near", free_bytes=160e6)
+    assert cap == 128 and 1024 <= chunk < 1600
+    h1, r1 = synodic.tube_section(x, mu, W.c5_grid("l2"), W.c5_section("l2", mu), **kw)
+    h3, r3 = synodic.tube_section(x, mu, W.c5_grid("l2"), W.c5_section("l2", mu), _free_bytes=160e6, **kw)
+    assert len(h1.times) > 100
+    assert np.array_equal(h1.trajectory_indices, h3.trajectory_indices)
+    assert np.array_equal(h1.times, h3.times) and np.array_equal(h1.states, h3.states)
+    assert np.array_equal(h1.points, h3.points) and np.array_equal(h1.hits_per_traj, h3.hits_per_traj)
+    assert np.array_equal(r1.yf, r3.yf) and np.array_equal(r1.n_acc, r3.n_acc) and np.array_equal(r1.status, r3.status)
