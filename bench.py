@@ -583,6 +583,8 @@ def main():
 
     side = [torch.cuda.Stream(dev) for _ in TUBES] if args.concurrent_tubes else None
 
+    trace = [] if os.environ.get("HITEN_B200_BENCH_TRACE") else None     # host time stamps inside a step (debug aid)
+
     def step_of(j):
         def step():
             # The two tubes' pipelines on two streams (each with its own step scratch): the propagation kernels are
@@ -590,6 +592,7 @@ def main():
             # trajectories, and tube 1's scan / emit kernels fill the SMs tube 2's propagation vacates -- the idle tail of
             # each persistent launch is covered by the other tube's work.
             main = torch.cuda.current_stream()
+            ts = [time.perf_counter()] if trace is not None else None
             for i, key in enumerate(TUBES):
                 t = j["tubes"][key]
                 if side is not None:
@@ -597,9 +600,14 @@ def main():
                     t["run"].launch(t["y0"], side[i])
                 else:
                     t["run"].launch(t["y0"])
+            if ts is not None:
+                ts.append(time.perf_counter())
             if world > 1:                                   # the one exchange: hit records, counts, end states -> rank 0
-                peer = [j["tubes"][key]["dist"].start_gather(None if side is None else side[i])
-                        for i, key in enumerate(TUBES)]     # tube 1's copies run under tube 2's propagation
+                peer = []
+                for i, key in enumerate(TUBES):             # tube 1's copies run under tube 2's propagation
+                    peer.append(j["tubes"][key]["dist"].start_gather(None if side is None else side[i]))
+                    if ts is not None:
+                        ts.append(time.perf_counter())
                 for i, (key, started) in enumerate(zip(TUBES, peer)):
                     d = j["tubes"][key]["dist"]
                     if started:
@@ -607,9 +615,13 @@ def main():
                     else:
                         with torch.cuda.stream(main if side is None else side[i]):
                             d.gather_device()
+                    if ts is not None:
+                        ts.append(time.perf_counter())
             if side is not None:
                 for st_ in side:
                     main.wait_stream(st_)
+            if ts is not None:
+                trace.append([1e3 * (b - ts[0]) for b in ts[1:]])
         return step
 
     step_resident = step_of(job)
@@ -705,7 +717,12 @@ def main():
         for _ in range(3):
             sstep()
         barrier()
+        if trace is not None:
+            del trace[:]
         ts = time_steps(sstep, args.steps, flush, barrier, torch)
+        if trace is not None:
+            print(f"[trace rank {rank}] strong leg, ms since step start (launched, start_gather x2, finish x2): "
+                  f"{np.mean(np.array(trace), axis=0).round(3).tolist()}", file=sys.stderr)
         s_acc, s_rej, s_hits, _, s_ok = tallies(sjob)
         strong = [ts, float(s_acc + s_rej), float(s_hits)]
         strong_max_ctas = sjob["max_ctas"]

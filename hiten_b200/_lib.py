@@ -143,6 +143,7 @@ SIGNATURES = {
                                           C.c_int64, vp, vp, vp]),
     "hb_read_hit_count": (C.c_int, [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), vp]),
     "hb_read_record_overflow": (C.c_int, [vp, C.POINTER(C.c_int64), vp]),
+    "hb_peer_put": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, vp, C.c_int64, vp, C.c_int64, vp, vp]),
     "hb_selftest_arith": (C.c_int, [vp, vp, C.c_int64, vp, vp, vp, vp, vp, vp]),
 }
 

@@ -20,6 +20,7 @@ GLOBAL trajectory indices in the reference's order (by trajectory, then along th
 import numpy as np
 import torch
 
+from . import _lib as _L
 from . import synodic as _syn
 
 
@@ -111,7 +112,7 @@ class PeerExchange:
         import torch.distributed._symmetric_memory as symm
         self.group = dist.group.WORLD if group is None else group
         self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
-        self.hit_slots, self.n_max = int(hit_slots), int(n_max)
+        self.hit_slots, self.n_max = int(hit_slots) + int(hit_slots) % 2, int(n_max)     # even: 16-byte aligned slots
         self.slot = self.HEADER + 9 * self.hit_slots + 6 * self.n_max
         with torch.cuda.device(device):
             self.buf = symm.empty(self.world * self.slot, dtype=torch.float64, device=device)
@@ -121,6 +122,31 @@ class PeerExchange:
             self.hdr_host = torch.zeros(self.HEADER, dtype=torch.float64).pin_memory()
             self.hdr_dev = torch.zeros(self.HEADER, dtype=torch.float64, device=device)
             self.cnt_host = torch.zeros(4, dtype=torch.int64).pin_memory()
+            # my slot in EVERY rank's buffer (hb_peer_put writes its header to all of them)
+            self.mine_all = [self.hdl.get_buffer(r, (self.slot,), torch.float64, self.rank * self.slot)
+                             for r in range(self.world)]
+            self.slot_ptrs = (_L.C.c_void_p * self.world)(*[t.data_ptr() for t in self.mine_all])
+            self.hdr_all_host = torch.zeros((self.world, self.HEADER), dtype=torch.float64).pin_memory()
+            self.hdr_all_dev = torch.zeros((self.world, self.HEADER), dtype=torch.float64, device=device)
+
+    def put_device(self, hits, yf_flat, n_local, ws, stream):
+        """The same transfer as put() done by a kernel on `stream` (hb_peer_put): the hit count is read on the device, so
+        no host wait is needed between the pipeline and the exchange; the closing barrier and the read-back of the
+        headers all shards wrote into THIS rank's buffer are enqueued behind it.  Small shards (see
+        DistributedTubeSection)."""
+        lib = _L.load()
+        _L.check(lib.hb_peer_put(self.slot_ptrs, self.world, 0, hits.data_ptr(), self.hit_slots, yf_flat.data_ptr(),
+                                 int(n_local), ws.data_ptr(), _L.vp(stream.cuda_stream)), "hb_peer_put")
+        with torch.cuda.stream(stream):
+            self.hdl.barrier(channel=0)
+            self.hdr_all_dev.copy_(self.buf.view(self.world, self.slot)[:, : self.HEADER])
+            self.hdr_all_host.copy_(self.hdr_all_dev, non_blocking=True)
+
+    def finish_device(self, stream):
+        """Closes an exchange started with put_device on `stream` (the one host wait of that form).  -> host tensor
+        [world, 8] on every rank: {hits, n_local, dropped, record overflows, sendable, ...} of every shard."""
+        stream.synchronize()
+        return self.hdr_all_host
 
     def put(self, k, hits, yf_flat):
         """Enqueue the copies of this rank's slot on the copy stream (k hit records, the end states)."""
@@ -138,10 +164,10 @@ class PeerExchange:
             self.hdl.barrier(channel=0)
         self.stream.synchronize()
 
-    def received(self):
+    def received(self, hdr=None):
         """Rank 0: (hit record tensors per rank, counts, end-state tensors per rank) as views of the receive buffer."""
         rows = self.buf.view(self.world, self.slot)
-        hdr = rows[:, : self.HEADER].cpu()
+        hdr = rows[:, : self.HEADER].cpu() if hdr is None else hdr
         hits, yfs, counts = [], [], []
         o = self.HEADER + 9 * self.hit_slots
         for r in range(self.world):
@@ -158,15 +184,21 @@ class DistributedTubeSection:
 
     def __init__(self, n_global, mu, t_eval, section, *, forward=1, flip=None, integ=None, steps_capacity=192,
                  pool_records=0, hit_capacity=None, runner_factory=None, group=None, exchange="auto",
-                 peer_hit_slots=None):
+                 peer_hit_slots=None, device_put="auto"):
         """exchange: "peer" (PeerExchange), "nccl" (padded gather) or "auto" (peer when the process group runs on NCCL
         and symmetric memory can be set up, else nccl; HITEN_B200_EXCHANGE overrides).  peer_hit_slots: hit records per
-        rank the receive buffer holds (default 4 per trajectory; more hits than that raise)."""
+        rank the receive buffer holds (default 4 per trajectory; more hits than that raise).
+        device_put (peer exchange only): True -- the shard is written into rank 0's buffer by a kernel that reads the hit
+        count on the device (hb_peer_put: no host wait between pipeline and exchange); False -- by the copy engines after
+        the host has read the count (overlaps a later persistent launch that owns the SMs); "auto" -- the kernel for
+        shards below 4 trajectories per lane of a full-device launch (where the host round trips are a visible share of
+        the step and the SMs are idle when the pipeline ends), HITEN_B200_PEER_PUT=kernel|copy overrides."""
         import os
         import torch.distributed as dist
         self.dist, self.group = dist, group
         self._exchange = os.environ.get("HITEN_B200_EXCHANGE", exchange)
         self.px = None
+        self._device_put, self._pending = os.environ.get("HITEN_B200_PEER_PUT", device_put), None
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.n_global, self.section = int(n_global), section
@@ -194,18 +226,31 @@ class DistributedTubeSection:
             dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
             if int(ok.item()) == 0:
                 self.px = None
+            if self.px is not None:
+                dp = self._device_put
+                if dp in ("kernel", "copy"):
+                    dp = dp == "kernel"
+                elif dp == "auto":
+                    sms = torch.cuda.get_device_properties(self.runner.yf.device).multi_processor_count
+                    dp = self.n_max < 4 * sms * 256
+                self._device_put = bool(dp) and self.world <= 16
 
     def launch(self, y0_soa_local, stream=None):
         self.runner.launch(y0_soa_local, stream)
 
-    def start_gather(self, stream=None):
-        """Peer form of the exchange, first half: wait (host) for THIS runner's pipeline only -- later launches on the
-        same stream keep running --, read its hit counter, and enqueue the copies into rank 0's receive buffer on the
-        copy stream.  Returns False when the peer path is not available (use gather_device)."""
+    def start_gather(self, stream=None, device_put=None):
+        """Peer form of the exchange, first half.  Copy-engine form: wait (host) for THIS runner's pipeline only -- later
+        launches on the same stream keep running --, read its hit counter, and enqueue the copies into rank 0's receive
+        buffer on the copy stream.  Kernel form (device_put, small shards): enqueue hb_peer_put behind the pipeline on its
+        own stream; nothing waits.  Returns False when the peer path is not available (use gather_device)."""
         if self.px is None:
             return False
         run, px = self.runner, self.px
         main = torch.cuda.current_stream(run.yf.device) if stream is None else stream
+        if self._device_put if device_put is None else device_put:
+            px.put_device(run.hits, run.yf.view(-1), len(self.index), run.ws, main)
+            self._pending = main
+            return True
         ev = getattr(run, "done_event", None)
         if ev is None:
             ev = torch.cuda.Event()
@@ -250,10 +295,24 @@ class DistributedTubeSection:
     def finish_gather(self):
         """Second half: all ranks' copies have landed on rank 0.  -> (hit record tensors per rank | None, counts | None,
         end-state tensors per rank | None)."""
-        self.px.finish()
+        hdr = None
+        if self._pending is not None:
+            main, self._pending = self._pending, None
+            hdr = self.px.finish_device(main)               # [world, 8] on every rank: all take the same branch below
+            if bool((hdr[:, 4] != 1.0).any()):
+                # some shard dropped hits, overflowed its step scratch or its slot: second, host-sized round (reruns
+                # and regrown buffers are completed there; too many hits for the slot raise as in the copy form)
+                with torch.cuda.stream(main):
+                    self.start_gather(main, device_put=False)
+                self.px.finish()
+                hdr = None
+            else:
+                self.runner._main_hits, self.runner._extra = int(hdr[self.rank, 0]), (None, None)
+        else:
+            self.px.finish()
         if self.rank != 0:
             return None, None, None
-        return self.px.received()
+        return self.px.received(hdr)
 
     def gather_device(self):
         """The one exchange of the path, on the device, stream-ordered after launch(): end states + per-trajectory hit

@@ -504,6 +504,20 @@ int hb_synodic_detect_cubic(const hb_section *sec, int32_t newton_max_iter, int6
 /* Hit / overflow counters of the last call that used `workspace` (synchronises `stream`). */
 int hb_read_hit_count(const void *workspace, int64_t *n_hits, int64_t *n_overflow, void *stream);
 
+/* Sharded runs (trajectories shard by index over the GPUs, one exchange at the end -- hit records and end
+ * states to the gathering rank; the seam in the reference is its worker pool, algorithms/poincare/synodic/engine.py:92-139):
+ * writes this shard's result into its slot of the gathering rank's receive buffer over NVLink peer memory, stream-ordered
+ * behind the pipeline that produced it and WITHOUT a host round trip -- the hit count is read from `workspace` on the
+ * device.  peer_slots[r] (r < world <= 16) = device pointer, mapped into this process, of this shard's slot in rank r's
+ * buffer; slot layout in doubles: [8 header | 9 * hit_slots hit records | 6 * n_local end states (SoA)], 16-byte aligned,
+ * hit_slots even.  Every rank's slot gets the header {hits, n_local, dropped hits, trajectories with
+ * HB_TRAJ_RECORD_OVERFLOW, sendable (1 / 0), 0, 0, 0}; rank dst's also the payload -- unless hits were dropped, step
+ * records overflowed or the hits exceed hit_slots (sendable = 0: the caller completes the shard and sends it with
+ * host-sized copies; after the closing barrier all ranks see that flag).  For small shards (the copy-engine path of
+ * hiten_b200/sharded.py overlaps better when a later persistent launch owns the SMs).                */
+int hb_peer_put(void *const *peer_slots, int32_t world, int32_t dst, const hb_hit *hits, int64_t hit_slots,
+                const double *yf_soa, int64_t n_local, const void *workspace, void *stream);
+
 /* Number of trajectories of the last hb_cr3bp_section2 call that got HB_TRAJ_RECORD_OVERFLOW (no hits were
  * reported for them; rerun those with hb_cr3bp_section).  Synchronises `stream`.                   */
 int hb_read_record_overflow(const void *workspace, int64_t *n_traj, void *stream);

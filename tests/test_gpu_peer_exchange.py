@@ -1,5 +1,5 @@
 """GPU (needs >= 2 devices; skipped on a one-GPU box): DistributedTubeSection's exchange over NVLink peer memory
-(sharded.PeerExchange: symmetric memory, copy engines) delivers the same hit records and end states to rank 0 as the padded
+(sharded.PeerExchange: symmetric memory; copy engines, or the hb_peer_put kernel for small shards) delivers the same hit records and end states to rank 0 as the padded
 NCCL gather on the same launch -- two ranks under torchrun, tools/gpu_probe_peer.py."""
 import os
 import subprocess
@@ -14,7 +14,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 @pytest.mark.parametrize("cap", [128, 8])
 def test_peer_exchange_equals_nccl_gather_on_two_ranks(cap):
     """cap = 8 recorded steps per trajectory: most trajectories outgrow the step scratch and are rerun with the fused kernel;
-    their records (kept on the host by the runner) must reach rank 0 as well, through both forms of the exchange."""
+    their records (kept on the host by the runner) must reach rank 0 as well, through every form of the exchange (the kernel
+    form then takes its host-sized second round)."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")

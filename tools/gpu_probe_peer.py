@@ -1,4 +1,5 @@
-"""2+ ranks: DistributedTubeSection's peer exchange against the NCCL gather on the same launch (same records on rank 0),
+"""2+ ranks: DistributedTubeSection's peer exchange -- copy-engine form and kernel form (hb_peer_put) -- against the NCCL gather
+on the same launch (same records on rank 0),
 and the time of both.  Run: python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/gpu_probe_peer.py"""
 import os, sys, time
 import numpy as np, torch, torch.distributed as dist
@@ -13,19 +14,19 @@ n_total = int(sys.argv[1]) if len(sys.argv) > 1 else 200_000
 cap = int(sys.argv[2]) if len(sys.argv) > 2 else 128          # a small step capacity forces reruns with the fused kernel
 ics, mu = W.c5_batch(n_total * world, rank, world)
 res = {}
-for mode in ("nccl", "peer"):
+for mode in ("nccl", "peer", "peer_kernel"):
     ds = {}
     for key in ("l1", "l2"):
         ds[key] = sharded.DistributedTubeSection(n_total * world // 2, mu, W.c5_grid(key), W.c5_section(key, mu),
                                                  forward=W.C5_TUBES[key]["forward"], flip=(0, 6), steps_capacity=cap,
-                                                 exchange=mode)
+                                                 exchange=mode.split("_")[0], device_put=(mode == "peer_kernel"))
     y0 = {key: torch.from_numpy(np.ascontiguousarray(ics[key].T)).cuda() for key in ds}
     out = None
     for it in range(4):
         dist.barrier(); torch.cuda.synchronize(); t0 = time.perf_counter()
         for key in ds:
             ds[key].launch(y0[key])
-        if mode == "peer":
+        if mode != "nccl":
             for key in ds:
                 assert ds[key].start_gather()
             out = {key: ds[key].finish_gather() for key in ds}
@@ -39,8 +40,8 @@ for mode in ("nccl", "peer"):
         res[mode] = {key: ([h.clone() for h in out[key][0]], out[key][1].clone(), [y.clone() for y in out[key][2]]) for key in ds}
         print(mode, "ms per step", 1e3 * dt, "hits", {key: int(out[key][1].sum()) for key in ds})
 if rank == 0:
-    for key in ("l1", "l2"):
-        a, b = res["nccl"][key], res["peer"][key]
+    for mode, key in [(m, k) for m in ("peer", "peer_kernel") for k in ("l1", "l2")]:
+        a, b = res["nccl"][key], res[mode][key]
         assert torch.equal(a[1].cpu(), b[1].cpu())
         for r in range(world):
             k = int(a[1][r])
@@ -50,5 +51,5 @@ if rank == 0:
             assert torch.equal(ordered(a[0][r]), ordered(b[0][r])), (key, r)
             nl = b[2][r].shape[1]
             assert torch.equal(a[2][r][:, :nl], b[2][r]), (key, r)
-    print("peer exchange == nccl gather: OK")
+    print("peer exchange == nccl gather: OK (copy-engine form and hb_peer_put form)")
 dist.destroy_process_group()
