@@ -726,9 +726,15 @@ def main():
         s_acc, s_rej, s_hits, _, s_ok = tallies(sjob)
         strong = [ts, float(s_acc + s_rej), float(s_hits)]
         strong_max_ctas = sjob["max_ctas"]
+        d0 = sjob["tubes"][TUBES[0]]["dist"]
+        strong_exchange = ("nccl gather" if d0.px is None else
+                           "hb_peer_put: each rank's kernel reads its hit count on the device and writes records + end states "
+                           "into rank 0's buffer over NVLink peer memory, no host wait before the closing barrier"
+                           if d0._device_put is True else "peer memory, copy engines (as the weak-scaling step)")
     else:
         strong = [t_dev, float(steps_per_pass), float(n_hits)]
         strong_max_ctas = main_max_ctas
+        strong_exchange = None
 
     tt = torch.tensor([t_dev, e2e_t, float(steps_per_pass), float(n_hits), float(steps_acc), strong[0], strong[1], strong[2],
                        float(n_overflow)], dtype=torch.float64, device=dev)
@@ -747,7 +753,7 @@ def main():
     extra = {"strong_scaling": {"total_trajectories": n, "n_gpus": world, "ms_per_step": 1e3 * strong_t / args.steps,
                                 "rk_steps_per_s": strong_steps * args.steps / strong_t,
                                 "crossings_per_s": strong_hits * args.steps / strong_t,
-                                "max_ctas_per_launch": strong_max_ctas or None,
+                                "max_ctas_per_launch": strong_max_ctas or None, "exchange": strong_exchange,
                                 "note": "configs[4]'s 1e6 trajectories in TOTAL, 1/N per GPU, same step incl. the gather; "
                                         "efficiency = rk_steps_per_s / (N x the N=1 value)"}}
     if not args.no_extra and world == 1:
