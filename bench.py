@@ -949,12 +949,13 @@ def main():
                     arm = ReferenceArm()
                     pick = lambda k: {key: job["ics"][key][:: max(1, len(job["ics"][key]) // k)][:k] for key in TUBES}
                     arm.step(pick(1), mu)                       # Numba compiles here
-                    sample = pick(24)
+                    sample = pick(120)                            # ~12 s of the reference's own code on one core
                     h, dt = arm.step(sample, mu)
                     line["cpu_baseline"] = {
                         "value": oracle_step_count(sample, mu) / dt, "unit": "RK steps/s", "cores": 1, "kind": "reference",
                         "crossings_per_s": h / dt,
-                        "sample": f"48 trajectories of the same batch (24 per tube, strided): the reference's own "
+                        "sample": f"{sum(len(v) for v in sample.values())} trajectories of the same batch (120 per tube, "
+                                  f"strided): the reference's own "
                                   f"_propagate_dynsys per initial condition + _SynodicDetectionBackend.run from oracle/_ref, "
                                   f"{dt:.1f} s on 1 core (it has no parallel driver for this loop)"}
                     line["cpu_baseline_port"] = port

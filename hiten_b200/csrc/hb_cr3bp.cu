@@ -78,10 +78,21 @@ __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) k_dop853_6(const PropP
             if (idx < p.n) {
 #pragma unroll
                 for (int d = 0; d < 6; ++d) y[d] = p.y0[(long long)d * p.n + idx];
-                crtbp_rhs<AR, NEG>(y, p, k[0]);
+                if (p.h0) {
+                    // the pre-pass left h0 and the accelerations of f(y0) in the output rows: a start is loads only
+                    h = p.h0[idx];
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) {
+                        const bool ng = NEG == 1 || (NEG == 2 && ((p.negmask >> d) & 1u));
+                        k[0][d] = ng ? hb_flip_sign(y[3 + d]) : y[3 + d];
+                        k[0][3 + d] = p.h0[(long long)(3 + d) * p.n + idx];
+                    }
+                } else {
+                    crtbp_rhs<AR, NEG>(y, p, k[0]);
+                    h = initial_step<AR>(y, k[0], p);
+                }
                 t = p.t0;
                 tf = p.tf_arr ? p.tf_arr[idx] : p.tf;
-                h = p.h0 ? p.h0[idx] : initial_step<AR>(y, k[0], p);
                 err_prev = -1.0;
                 nacc = 0; nrej = 0; cursor = 0; attempts = 0;
                 nrec = 0; pending = false; prev_near = false;

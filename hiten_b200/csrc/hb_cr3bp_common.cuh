@@ -63,6 +63,11 @@ struct PropParams {
 #define HB_REC_LAST 1     // the trajectory's last accepted step (owns every grid sample that is left)
 #define HB_REC_ROW_BYTES (HB_REC_DOUBLES * 8 + 16)   // shared-memory staging row, padded: conflict-free 16 B accesses
 
+HB_DEV double hb_flip_sign(double x)      // -x, bit for bit (also for zeros and NaNs), without the FP64 pipe
+{
+    return __hiloint2double(__double2hiint(x) ^ (int)0x80000000, __double2loint(x));
+}
+
 HB_DEV void hb_st4(double *p, double a, double b, double c, double d)
 {
     asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
@@ -118,7 +123,14 @@ HB_DEV void crtbp_rhs(const double (&s)[6], const PropParams &p, double (&out)[6
     if constexpr (NEG == 0) {
         out[0] = vx; out[1] = vy; out[2] = vz; out[3] = ax; out[4] = ay; out[5] = az;
     } else if constexpr (NEG == 1) {
-        out[0] = -vx; out[1] = -vy; out[2] = -vz; out[3] = -ax; out[4] = -ay; out[5] = -az;
+        if constexpr (AR::parity) {
+            // sign flips on the integer pipe: the compiler otherwise spends ~50 DADD (-0 - x) per step on the FP64 pipe,
+            // which bounds this kernel, wherever it cannot fold the sign into a consumer
+            out[0] = hb_flip_sign(vx); out[1] = hb_flip_sign(vy); out[2] = hb_flip_sign(vz);
+            out[3] = hb_flip_sign(ax); out[4] = hb_flip_sign(ay); out[5] = hb_flip_sign(az);
+        } else {
+            out[0] = -vx; out[1] = -vy; out[2] = -vz; out[3] = -ax; out[4] = -ay; out[5] = -az;
+        }
     } else {
         out[0] = (p.negmask & 1u) ? -vx : vx;
         out[1] = (p.negmask & 2u) ? -vy : vy;
@@ -186,8 +198,9 @@ HB_DEV double initial_step(const double (&y)[6], const double (&f)[6], const Pro
 // First step sizes of all trajectories in one convergent pass.  Inside the persistent kernels a trajectory start
 // is executed by whichever lanes just ran out of work while the rest of the warp waits; in the parity build the
 // start (12 divisions + two emulated x87 norms) costs about half a step, ~15 % of the warp's time.  The values
-// are parked in the FIRST ROW of the output array yf (each thread reads its entry before it writes that
-// trajectory's end state), so no scratch is needed; callers whose yf overlaps y0 keep the inline path.
+// are parked in the FIRST ROW of the output array yf, the accelerations of f(y0) in rows 3..5 (each thread reads its
+// entries before it writes that trajectory's end state), so no scratch is needed; callers whose yf overlaps y0 keep
+// the inline path.
 template <class AR, int NEG>
 __global__ void __launch_bounds__(128) k_first_steps(const PropParams p, double *h0)
 {
@@ -198,6 +211,10 @@ __global__ void __launch_bounds__(128) k_first_steps(const PropParams p, double 
     for (int d = 0; d < 6; ++d) y[d] = p.y0[(long long)d * p.n + idx];
     crtbp_rhs<AR, NEG>(y, p, f);
     h0[idx] = initial_step<AR>(y, f, p);
+    // the accelerations of f(y0) ride along in rows 3..5 (k_dop853_6 then starts a trajectory with loads only: inside the
+    // persistent kernel the vector field of a refill runs at ~2 of 32 lanes); f[0..2] are the (signed) velocities
+#pragma unroll
+    for (int d = 3; d < 6; ++d) h0[(long long)d * p.n + idx] = f[d];
 }
 
 template <class AR>
@@ -205,8 +222,8 @@ inline int first_steps_prepass(PropParams &p, cudaStream_t st)
 {
     p.h0 = nullptr;
     if (!p.yf || p.n < 128) return HB_OK;                                   // tiny batches: not worth a launch
-    const double *a0 = p.y0, *a1 = p.y0 + 6 * p.n, *b0 = p.yf, *b1 = p.yf + p.n;
-    if (b0 < a1 && a0 < b1) return HB_OK;                                   // in-place call: yf row 0 is live input
+    const double *a0 = p.y0, *a1 = p.y0 + 6 * p.n, *b0 = p.yf, *b1 = p.yf + 6 * p.n;
+    if (b0 < a1 && a0 < b1) return HB_OK;                                   // in-place call: yf rows are live input
     const unsigned grid = (unsigned)((p.n + 127) / 128);
     if (p.negmask == 0u) k_first_steps<AR, 0><<<grid, 128, 0, st>>>(p, p.yf);
     else if (p.negmask == 63u) k_first_steps<AR, 1><<<grid, 128, 0, st>>>(p, p.yf);
