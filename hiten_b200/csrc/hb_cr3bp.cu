@@ -53,7 +53,9 @@ HB_DEV void store_record(const double *rec_row, double *dst)
 // ---------------------------------------------------------------------------------------------
 // The persistent-thread kernel.
 // ---------------------------------------------------------------------------------------------
-template <class AR, int MODE, int NEG>
+// CSEC (MODE_RECORD_NEAR only): the section component the screening evaluates, resolved at compile time -- a switch on
+// the section index inside the step loop cost 1 % (an indirect branch into code far from the loop, every accepted step).
+template <class AR, int MODE, int NEG, int CSEC = 0>
 __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) k_dop853_6(const PropParams p)
 {
     double y[6], yh[6], k[13][6];
@@ -212,18 +214,7 @@ __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) k_dop853_6(const PropP
                 if (hseg != 0.0 && fabs(hseg) * p.inv_grid_dt >= 2.0) {      // shorter steps may own no grid sample: keep
                     const Cr3bpRhs<ArFast, NEG> rf{p};
                     const double off = p.sink.sec.offset, tol = p.sink.sec.tol_on_surface;
-#ifdef HB_NEAR_ONLY_C0
-                    near = dop853_step_near_plane<0>(y, yh, hseg, k, rf, off, tol);
-#else
-                    switch (p.sink.sec.idx) {
-                    case 0: near = dop853_step_near_plane<0>(y, yh, hseg, k, rf, off, tol); break;
-                    case 1: near = dop853_step_near_plane<1>(y, yh, hseg, k, rf, off, tol); break;
-                    case 2: near = dop853_step_near_plane<2>(y, yh, hseg, k, rf, off, tol); break;
-                    case 3: near = dop853_step_near_plane<3>(y, yh, hseg, k, rf, off, tol); break;
-                    case 4: near = dop853_step_near_plane<4>(y, yh, hseg, k, rf, off, tol); break;
-                    default: near = dop853_step_near_plane<5>(y, yh, hseg, k, rf, off, tol); break;
-                    }
-#endif
+                    near = dop853_step_near_plane<CSEC>(y, yh, hseg, k, rf, off, tol);
                 }
                 if (near && pending) {                        // the step before this one: write it first
                     if (nrec < p.rec_cap) store_record(rec_row, p.rec + ((long long)idx * p.rec_cap + nrec) * HB_REC_DOUBLES);
@@ -267,10 +258,14 @@ __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) k_dop853_6(const PropP
             }
             // advance
             t = t_new;
-#pragma unroll
-            for (int d = 0; d < 6; ++d) { y[d] = yh[d]; k[0][d] = k[12][d]; }
         } else {
             ++nrej;
+        }
+        {   // y <- y_new, k1 <- k13 (FSAL) as selects outside the branch: the compiler merged the two paths with ~75 register
+            // moves per step when the copy sat inside it (measured: 1.2 % of the record kernel)
+            const bool acc_ = err <= 1.0;
+#pragma unroll
+            for (int d = 0; d < 6; ++d) { y[d] = acc_ ? yh[d] : y[d]; k[0][d] = acc_ ? k[12][d] : k[0][d]; }
         }
         {   // The controller's factor AFTER the record / screening block, where the stage vectors are dead (measured: 1 % off
             // the record kernel).  One convergent pow: accepted and rejected lanes evaluate err**(-1/9) and err**(-1/8) in the
@@ -305,24 +300,42 @@ __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) k_dop853_6(const PropP
 // ---------------------------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------------------------
-template <class AR, int MODE, int NEG>
+template <class AR, int MODE, int NEG, int CSEC = 0>
 int launch_one(const PropParams &p, unsigned grid, cudaStream_t st)
 {
     constexpr int smem = is_record(MODE) ? HB_BLOCK * HB_REC_ROW_BYTES : 0;
     // the opt-in is per device (and cheap): set on every launch, so a second device in the same process gets it too
     if (smem > 48 * 1024)
-        HB_CUDA_TRY(cudaFuncSetAttribute(k_dop853_6<AR, MODE, NEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    k_dop853_6<AR, MODE, NEG><<<grid, HB_BLOCK, smem, st>>>(p);
+        HB_CUDA_TRY(cudaFuncSetAttribute(k_dop853_6<AR, MODE, NEG, CSEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    k_dop853_6<AR, MODE, NEG, CSEC><<<grid, HB_BLOCK, smem, st>>>(p);
     HB_CUDA_TRY(cudaGetLastError());
     return HB_OK;
+}
+
+template <class AR, int MODE, int NEG>
+int launch_sec(const PropParams &p, unsigned grid, cudaStream_t st)
+{
+    if constexpr (MODE == MODE_RECORD_NEAR) {
+        switch (p.sink.sec.idx) {
+        case 0: return launch_one<AR, MODE, NEG, 0>(p, grid, st);
+        case 1: return launch_one<AR, MODE, NEG, 1>(p, grid, st);
+        case 2: return launch_one<AR, MODE, NEG, 2>(p, grid, st);
+        case 3: return launch_one<AR, MODE, NEG, 3>(p, grid, st);
+        case 4: return launch_one<AR, MODE, NEG, 4>(p, grid, st);
+        case 5: return launch_one<AR, MODE, NEG, 5>(p, grid, st);
+        default: return HB_ERR_BADARG;
+        }
+    } else {
+        return launch_one<AR, MODE, NEG>(p, grid, st);
+    }
 }
 
 template <class AR, int MODE>
 int launch_neg(const PropParams &p, unsigned grid, cudaStream_t st)
 {
-    if (p.negmask == 0u) return launch_one<AR, MODE, 0>(p, grid, st);
-    if (p.negmask == 63u) return launch_one<AR, MODE, 1>(p, grid, st);
-    return launch_one<AR, MODE, 2>(p, grid, st);
+    if (p.negmask == 0u) return launch_sec<AR, MODE, 0>(p, grid, st);
+    if (p.negmask == 63u) return launch_sec<AR, MODE, 1>(p, grid, st);
+    return launch_sec<AR, MODE, 2>(p, grid, st);
 }
 
 template <int MODE>
