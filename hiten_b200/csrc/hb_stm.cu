@@ -276,7 +276,9 @@ __global__ void __launch_bounds__(256, 1) k_dop853_stm(const StmParams p)
         ++attempts;
         int fin = -1;
 
-        const double h_factor = hb_pi_factor<AR>(err, err_prev, err <= 1.0, 8.0);   // both branches, one pow
+        // both branches, one logarithm: err_prev ** alpha is carried from the step where err_prev was the current error
+        // (hb_pi_factor_carried, same bits as hb_pi_factor; in the parity build `err_prev` holds that power)
+        const double h_factor = hb_pi_factor_carried<AR>(err, err_prev, err <= 1.0, 8.0);
         if (err <= 1.0) {
             const double t_new = AR::add(t, h);
             ++nacc;
@@ -332,7 +334,6 @@ __global__ void __launch_bounds__(256, 1) k_dop853_stm(const StmParams p)
 #pragma unroll
             for (int d = 0; d < 6; ++d) { y[d] = yh[d]; k[0][d] = k[12][d]; }
             h = AR::mul(h, h_factor);
-            err_prev = err;
         } else {
             ++nrej;
             h = AR::mul(h, h_factor);

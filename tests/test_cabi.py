@@ -133,6 +133,15 @@ def test_argument_validation_needs_no_gpu():
                                  None, None, None, 0, (C.c_char * 256)(), None) == -1
     with pytest.raises(ValueError):
         corrector.make_opts(control_indices=(0, 4, 5), residual_indices=(3, 5), event_idx=1)
+    # peer put (8e): world size, alignment and parity of the slot are checked before any launch
+    slots = (C.c_void_p * 2)(0x1000, 0x2000)
+    assert lib.hb_peer_put(None, 2, 0, None, 0, None, 0, 0x1000, None) < 0                       # no slot table
+    assert lib.hb_peer_put(slots, 17, 0, None, 0, None, 0, 0x1000, None) < 0                     # more than 16 ranks
+    assert lib.hb_peer_put(slots, 2, 2, None, 0, None, 0, 0x1000, None) < 0                      # destination outside the group
+    assert lib.hb_peer_put(slots, 2, 0, 0x3000, 3, None, 0, 0x1000, None) < 0                    # odd number of record slots
+    assert lib.hb_peer_put((C.c_void_p * 2)(0x1008, 0x2000), 2, 0, None, 0, None, 0, 0x1000, None) < 0   # slot not 16-byte aligned
+    assert lib.hb_peer_put(slots, 2, 0, None, 0, None, 0, None, None) < 0                        # no workspace
+    assert hiten_b200.make_integ(max_ctas=74).max_ctas == 74 and hiten_b200.make_integ().max_ctas == 0
 
 
 def test_tao_grid_table_is_host_only_and_matches_the_reference_formulas():
