@@ -556,15 +556,15 @@ def main():
         """Runners + resident inputs of this rank for a job of n_total_global trajectories (both tubes, all ranks)."""
         ics, mu = W.c5_batch(n_total_global, rank, world)
         job = {"ics": ics, "mu": mu, "tubes": {}}
-        integ = hb.make_integ(arith=args.arith, max_ctas=ctas_for(n_total_global // 2 // world))
-        job["max_ctas"] = int(integ.max_ctas)
+        job["max_ctas"] = ctas_for(n_total_global // 2 // world)
         scratch = None
         for key in TUBES:
             x = ics[key]
+            integ = hb.make_integ(arith=args.arith, max_ctas=job["max_ctas"])
             d = sharded.DistributedTubeSection(
                 n_total_global // 2, mu, W.c5_grid(key), W.c5_section(key, mu), forward=W.C5_TUBES[key]["forward"],
                 flip=(0, 6), integ=integ,
-                runner_factory=lambda nl, key=key: synodic.TubeSectionRunner(
+                runner_factory=lambda nl, key=key, integ=integ: synodic.TubeSectionRunner(
                     nl, mu, W.c5_grid(key), W.c5_section(key, mu), forward=W.C5_TUBES[key]["forward"], flip=(0, 6),
                     integ=integ, device=dev, scratch=None if args.concurrent_tubes else scratch, **kind))
             assert len(d.index) == len(x)
