@@ -11,8 +11,9 @@ chunks exactly like this.  Two forms:
                            rank r owns trajectories r, r + W, r + 2W, ...; the final exchange writes every rank's hit
                            records and end states straight into rank 0's receive buffer over NVLink peer memory with the
                            COPY ENGINES (PeerExchange: symmetric memory, no SM work, so the transfer of one tube runs
-                           under the propagation of the next); without peer memory it is a padded NCCL gather after an
-                           all-gather of the counts.
+                           under the propagation of the next) or, for small shards, with the hb_peer_put KERNEL, which
+                           reads the hit count on the device and needs no host wait between pipeline and exchange;
+                           without peer memory it is a padded NCCL gather after an all-gather of the counts.
 
 Sharding is interleaved (i mod W) so that a tube's phase-dependent cost spreads evenly (8e).  Both return hits with
 GLOBAL trajectory indices in the reference's order (by trajectory, then along the trajectory).
