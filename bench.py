@@ -499,7 +499,7 @@ def main():
                     help="1: the two tubes' pipelines on two streams with a step scratch each; 0: one after the other")
     ap.add_argument("--arith", default="parity", choices=["parity", "fast"])
     ap.add_argument("--max-ctas", default="auto",
-                    help="auto: when the two tubes run on two streams and a tube has fewer than 4 trajectories per lane of a "
+                    help="auto: when the two tubes run on two streams and a tube has fewer than 8 trajectories per lane of a "
                          "full-device persistent launch, each tube's launch is capped at half the SMs so that the two run "
                          "side by side (the strong-scaling shards); 0: every launch uses every SM; N: cap at N CTAs")
     ap.add_argument("--n-per-gpu", type=int, default=N_PER_GPU)
@@ -550,7 +550,7 @@ def main():
             return int(args.max_ctas)
         if not args.concurrent_tubes or args.pipeline == "section3":
             return 0
-        return sm_count // 2 if n_tube_local < 4 * sm_count * 256 else 0
+        return sm_count // 2 if n_tube_local < 8 * sm_count * 256 else 0
 
     def make_job(n_total_global):
         """Runners + resident inputs of this rank for a job of n_total_global trajectories (both tubes, all ranks)."""

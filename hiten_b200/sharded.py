@@ -192,7 +192,7 @@ class DistributedTubeSection:
         device_put (peer exchange only): True -- the shard is written into rank 0's buffer by a kernel that reads the hit
         count on the device (hb_peer_put: no host wait between pipeline and exchange); False -- by the copy engines after
         the host has read the count (overlaps a later persistent launch that owns the SMs); "auto" -- the kernel for
-        shards below 4 trajectories per lane of a full-device launch (where the host round trips are a visible share of
+        shards below 8 trajectories per lane of a full-device launch (where the host round trips are a visible share of
         the step and the SMs are idle when the pipeline ends), HITEN_B200_PEER_PUT=kernel|copy overrides."""
         import os
         import torch.distributed as dist
@@ -233,7 +233,7 @@ class DistributedTubeSection:
                     dp = dp == "kernel"
                 elif dp == "auto":
                     sms = torch.cuda.get_device_properties(self.runner.yf.device).multi_processor_count
-                    dp = self.n_max < 4 * sms * 256
+                    dp = self.n_max < 8 * sms * 256
                 self._device_put = bool(dp) and self.world <= 16
 
     def launch(self, y0_soa_local, stream=None):
