@@ -192,3 +192,18 @@ def test_specialised_grid_kernel_compiles_offline():
         tab = PolyTable(g["jac_ptr"], g["jac_deg"], g["jac_coef"], g["jac_exp"])
         for arith in ("parity", "fast"):
             assert S.jit_compile_host(tab, arith) > 4096
+
+
+def test_tube_section_chunk_plan_is_host_arithmetic():
+    """synodic._auto_plan (tube_section's "auto" form): whole batch when its step scratch fits half of the free memory,
+    equal 256-aligned chunks that do when it does not, the fused kernel for tiny batches or no room at all."""
+    from hiten_b200 import synodic
+    per = _lib.load().hb_section2_scratch_bytes(1024, 128) / 1024.0 + 400.0
+    assert synodic._auto_plan(100, "cuda:0", "near", free_bytes=1e12) == (100, 0)                  # tiny: fused kernel
+    assert synodic._auto_plan(1_000_000, "cuda:0", "near", free_bytes=180e9) == (1_000_000, 128)   # fits a B200
+    assert synodic._auto_plan(1_000_000, "cuda:0", "all", free_bytes=180e9)[1] == 160
+    chunk, cap = synodic._auto_plan(10_000_000, "cuda:0", "near", free_bytes=170e9)
+    assert cap == 128 and chunk % 256 == 0 and chunk * per <= 0.5 * 170e9 + 256 * per
+    n_chunks = -(-10_000_000 // chunk)
+    assert 8 <= n_chunks <= 10 and (n_chunks - 1) * chunk < 10_000_000
+    assert synodic._auto_plan(50_000, "cuda:0", "near", free_bytes=10e6) == (50_000, 0)            # no room: fused kernel
