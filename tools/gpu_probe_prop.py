@@ -22,6 +22,8 @@ for _ in range(4):
 steps = int((r.n_acc.sum() + r.n_rej.sum()).item())
 chk = float(r.yf.double().sum().item())
 print(json.dumps({"what": "propagate_only", "n": n, "ms": best, "steps_per_s": steps / best * 1e3, "checksum": chk}))
+if os.environ.get("PROBE_PROP_ONLY") == "1":      # large batches: the section pipeline's step scratch would not fit
+    sys.exit(0)
 run = synodic.TubeSectionRunner(n, mu, te, W.c5_section(key, mu), forward=-1, flip=(0, 6), integ=integ, steps_capacity=192)
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
 run.set_stage_events(ev)
