@@ -659,6 +659,39 @@ def main():
 
     steps_acc, steps_rej, n_hits, n_overflow, ok = tallies(job)
     steps_per_pass = steps_acc + steps_rej
+
+    def ordered_leg(j, stepfn, ref_steps, ref_hits):
+        """Secondary line: the same step with each tube's persistent propagation launch handing out its trajectories
+        LONGEST FIRST (hb_integ.order -- a scheduling hint, outputs stay in the caller's indexing; SURVEY 8e "sorting by
+        expected cost").  The cost is the step count of the previous pass over the same batch, i.e. the best case of
+        what a caller with similar successive batches gets from TubeSectionRunner.order_by_cost(); it is NOT the headline,
+        which hands the trajectories out in the order the workload generator produced them."""
+        if args.pipeline != "section2":
+            return None
+        try:
+            for key in TUBES:
+                j["tubes"][key]["run"].order_by_cost()
+            for _ in range(2):
+                stepfn()
+            barrier()
+            t_o = time_steps(stepfn, args.steps, flush, barrier, torch)
+            a_, r_, h_, _, ok_ = tallies(j)
+        finally:
+            for key in TUBES:
+                j["tubes"][key]["run"].set_order(None)
+        v = torch.tensor([t_o, float(a_ + r_), float(h_)], dtype=torch.float64, device=dev)
+        if world > 1:
+            vmax = v.clone()
+            dist.all_reduce(vmax, op=dist.ReduceOp.MAX)
+            dist.all_reduce(v, op=dist.ReduceOp.SUM)
+            v[0] = vmax[0]
+        t_o, st_o, hi_o = v[0].item(), v[1].item(), v[2].item()
+        return {"ms_per_step": 1e3 * t_o / args.steps, "rk_steps_per_s": st_o * args.steps / t_o,
+                "crossings_per_s": hi_o * args.steps / t_o,
+                "same_steps_and_crossings_as_natural_order": bool(a_ + r_ == ref_steps and h_ == ref_hits and ok_),
+                "order": "per tube, argsort(-(n_acc + n_rej)) of the previous pass over the same batch (hb_integ.order)"}
+
+    cost_ordered = ordered_leg(job, step_resident, steps_per_pass, n_hits)
     records_written = sum(int(job["tubes"][key]["run"].records_written().sum().item()) for key in TUBES) \
         if args.pipeline == "section2" else 0
 
@@ -725,6 +758,7 @@ def main():
                   f"{np.mean(np.array(trace), axis=0).round(3).tolist()}", file=sys.stderr)
         s_acc, s_rej, s_hits, _, s_ok = tallies(sjob)
         strong = [ts, float(s_acc + s_rej), float(s_hits)]
+        strong_ordered = ordered_leg(sjob, sstep, s_acc + s_rej, s_hits)
         strong_max_ctas = sjob["max_ctas"]
         d0 = sjob["tubes"][TUBES[0]]["dist"]
         strong_exchange = ("nccl gather" if d0.px is None else
@@ -733,6 +767,7 @@ def main():
                            if d0._device_put is True else "peer memory, copy engines (as the weak-scaling step)")
     else:
         strong = [t_dev, float(steps_per_pass), float(n_hits)]
+        strong_ordered = cost_ordered
         strong_max_ctas = main_max_ctas
         strong_exchange = None
 
@@ -755,7 +790,9 @@ def main():
                                 "crossings_per_s": strong_hits * args.steps / strong_t,
                                 "max_ctas_per_launch": strong_max_ctas or None, "exchange": strong_exchange,
                                 "note": "configs[4]'s 1e6 trajectories in TOTAL, 1/N per GPU, same step incl. the gather; "
-                                        "efficiency = rk_steps_per_s / (N x the N=1 value)"}}
+                                        "efficiency = rk_steps_per_s / (N x the N=1 value)",
+                                "cost_ordered": strong_ordered},
+             "cost_ordered": cost_ordered}
     if not args.no_extra and world == 1:
         if args.concurrent_tubes and args.pipeline != "fused":       # the secondary lines run one tube at a time: one scratch
             job["tubes"][TUBES[1]]["run"].scratch = job["scratch"]

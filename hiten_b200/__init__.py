@@ -7,7 +7,7 @@ from . import _lib
 from ._lib import HitenB200Error
 from .dropin import install, uninstall
 from .propagate import (BatchResult, cr3bp_dense, cr3bp_event, cr3bp_propagate, cr3bp_stm, cr3bp_stm_dense,
-                        dfma_peak, make_integ)
+                        cost_order, dfma_peak, make_integ, with_order)
 
 __all__ = ["install", "uninstall", "BatchResult", "HitenB200Error", "cr3bp_dense", "cr3bp_event", "cr3bp_propagate", "cr3bp_stm", "cr3bp_stm_dense", "dfma_peak",
-           "make_integ", "_lib"]
+           "make_integ", "with_order", "cost_order", "_lib"]

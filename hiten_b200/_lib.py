@@ -25,7 +25,7 @@ class HbCr3bp(C.Structure):
 class HbInteg(C.Structure):
     _fields_ = [("method", C.c_int32), ("arith", C.c_int32), ("rtol", C.c_double), ("atol", C.c_double),
                 ("max_step", C.c_double), ("min_step", C.c_double), ("max_attempts", C.c_int64),
-                ("n_fixed_steps", C.c_int32), ("max_ctas", C.c_int32)]
+                ("n_fixed_steps", C.c_int32), ("max_ctas", C.c_int32), ("order", C.c_void_p)]
 
 
 class HbEvent(C.Structure):

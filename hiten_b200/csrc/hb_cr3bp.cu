@@ -78,6 +78,7 @@ __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) k_dop853_6(const PropP
         if (!have && !exhausted) {
             idx = hb_fetch_index(p.ws);
             if (idx < p.n) {
+                if (p.order) idx = p.order[idx];          // scheduling hint: outputs stay in the caller's indexing
 #pragma unroll
                 for (int d = 0; d < 6; ++d) y[d] = p.y0[(long long)d * p.n + idx];
                 if (p.h0) {

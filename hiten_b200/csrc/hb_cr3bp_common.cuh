@@ -45,6 +45,7 @@ struct PropParams {
     int rec_cap;
     int *nrec;             // MODE_RECORD_NEAR: records written per trajectory (only steps near the section plane + neighbours)
     int max_ctas;          // host side only: cap on the persistent launch's grid (hb_integ.max_ctas; 0 = every SM)
+    const int *order;      // hb_integ.order: trajectory handed out q-th (null: q itself)
 };
 
 // One accepted step as stored by MODE_RECORD (hb_cr3bp.cu) and consumed by the scan kernels (hb_section_scan.cu):
@@ -253,6 +254,7 @@ inline int fill_params(const hb_cr3bp *sys, const hb_integ *integ, PropParams &p
     p.max_step = integ->max_step; p.min_step = integ->min_step;
     p.max_attempts = integ->max_attempts > 0 ? integ->max_attempts : 2147483647LL;
     p.max_ctas = integ->max_ctas > 0 ? integ->max_ctas : 0;
+    p.order = integ->order;
     return HB_OK;
 }
 

@@ -44,7 +44,47 @@ def make_integ(method=L.HB_DOP853, arith="parity", rtol=1e-12, atol=1e-12, max_s
     ar = {"parity": L.HB_ARITH_PARITY, "fast": L.HB_ARITH_FAST}[arith] if isinstance(arith, str) else int(arith)
     return L.HbInteg(int(method), ar, float(rtol), float(atol), float(max_step),
                      default_min_step() if min_step is None else float(min_step), int(max_attempts),
-                     int(n_fixed_steps), int(max_ctas))
+                     int(n_fixed_steps), int(max_ctas), None)
+
+
+def with_order(integ, order):
+    """Copy of `integ` whose persistent DOP853 launches hand out trajectory order[q] q-th (hb_integ.order).  `order`:
+    int32 CUDA tensor holding a permutation of 0..n-1 (the returned struct holds a reference to it), or None."""
+    out = L.HbInteg.from_buffer_copy(integ)
+    if order is None:
+        out.order = None
+    else:
+        if not (isinstance(order, torch.Tensor) and order.is_cuda and order.dtype == torch.int32 and order.dim() == 1
+                and order.is_contiguous()):
+            raise ValueError("order must be a contiguous 1-D int32 CUDA tensor")
+        out.order = order.data_ptr()
+        out._order_ref = order                               # the struct keeps the tensor alive
+    return out
+
+
+def check_order(order, n):
+    """Raise unless `order` holds every index 0..n-1 exactly once (the kernels trust it: a wrong entry is an out-of-bounds
+    access).  One small device pass + a host read; callers set an order once per batch shape, not per launch."""
+    if order.numel() != n:
+        raise ValueError(f"order must hold one entry per trajectory ({order.numel()} != {n})")
+    if n and not bool((torch.bincount(order.clamp(0, n - 1).to(torch.int64), minlength=n) == 1).all().item()):
+        raise ValueError("order is not a permutation of 0..n-1")
+    if n and (int(order.min().item()) < 0 or int(order.max().item()) >= n):
+        raise ValueError("order is not a permutation of 0..n-1")
+
+
+def _check_integ_order(integ, n):
+    ref = getattr(integ, "_order_ref", None)
+    if ref is not None:
+        check_order(ref, n)
+    elif integ.order:
+        raise ValueError("hb_integ.order set without hiten_b200.with_order (nothing keeps the device array alive)")
+
+
+def cost_order(cost):
+    """Launch order for `with_order`: most expensive first.  cost: CUDA tensor [n] (e.g. n_acc + n_rej of an earlier,
+    similar batch).  Stable, so equal costs keep their index order."""
+    return torch.argsort(cost.to(torch.int64), descending=True, stable=True).to(torch.int32).contiguous()
 
 
 def _stream_ptr(stream=None):
@@ -87,6 +127,7 @@ def cr3bp_propagate(y0, mu, tf, *, t0=0.0, forward=1, flip=None, tf_per_traj=Non
         yf, nacc, nrej, status = _alloc_out(n, device)
         ws = workspace(device) if ws is None else ws
         integ = make_integ() if integ is None else integ
+        _check_integ_order(integ, n)
         sys_ = make_sys(mu, forward, flip)
         tfp = None
         if tf_per_traj is not None:
@@ -119,6 +160,7 @@ def cr3bp_dense(y0, mu, t_eval, *, forward=1, flip=None, integ=None, device=None
         _, nacc, nrej, status = _alloc_out(n, device)
         ws = workspace(device) if ws is None else ws
         integ = make_integ() if integ is None else integ
+        _check_integ_order(integ, n)
         sys_ = make_sys(mu, forward, flip)
         rc = lib.hb_cr3bp_dense(sys_, integ, n, y0d.data_ptr(), te.data_ptr(), m, out.data_ptr(), nacc.data_ptr(),
                                 nrej.data_ptr(), status.data_ptr(), ws.data_ptr(), _stream_ptr(stream))
@@ -142,6 +184,7 @@ def cr3bp_event(y0, mu, tmax, event_idx, *, event_offset=0.0, direction=0, xtol=
         th = torch.empty(n, dtype=torch.float64, device=device)
         ws = workspace(device) if ws is None else ws
         integ = make_integ() if integ is None else integ
+        _check_integ_order(integ, n)
         sys_ = make_sys(mu, forward, flip)
         ev = L.HbEvent(int(event_idx), int(direction), float(event_offset), float(xtol), float(gtol))
         tmp = None

@@ -276,6 +276,7 @@ class TubeSectionRunner:
         self.stage_events = None        # set_stage_events(): caller-owned CUDA events around the pipeline's stages
         self.scratch = None
         self._y0 = None
+        self._order, self._integ_ordered = None, None        # set_order(): launch order of the persistent propagation kernel
         self._extra = None          # (indices, SectionHits) of the trajectories rerun with the fused kernel
         self.filters = None
         if filters is not None:
@@ -294,6 +295,26 @@ class TubeSectionRunner:
                 self.scratch = scratch
             else:
                 self.scratch = torch.empty(nbytes // 8, dtype=torch.float64, device=self.device)
+
+    def set_order(self, order):
+        """Scheduling hint for the pipeline's persistent propagation launch (hb_integ.order): `order` is an int32 CUDA
+        tensor with a permutation of 0..n-1 -- trajectory order[q] is handed out q-th -- or None for 0, 1, 2, ...
+        Results do not depend on it (outputs stay in the caller's indexing); longest expected trajectories first
+        shortens the launch's tail.  Honoured by hb_cr3bp_section2 (steps_capacity > 0)."""
+        from . import propagate as P
+        if order is not None:
+            P.check_order(order, self.n)                      # the kernel trusts it
+        self._order = order                                   # keeps the tensor alive
+        self._integ_ordered = None if order is None else P.with_order(self.integ, order)
+
+    def order_by_cost(self, cost=None):
+        """set_order(most expensive first).  cost: CUDA tensor [n]; default: the attempted steps (n_acc + n_rej) of this
+        runner's LAST launch -- for callers whose next batch resembles the last one (the same tube cut by another
+        section, the next displacement set of the same orbit, the next iteration of a continuation)."""
+        from . import propagate as P
+        if cost is None:
+            cost = self.nacc[: self.n] + self.nrej[: self.n]
+        self.set_order(P.cost_order(cost))
 
     def set_stage_events(self, events):
         """events: list of torch.cuda.Event(enable_timing=True) the library records on the launch stream around the
@@ -329,7 +350,8 @@ class TubeSectionRunner:
                 raise L.HitenB200Error("filters need the step records of hb_cr3bp_section2 (steps_capacity > 0)")
             return
         if self.scratch is not None:
-            rc = self.lib.hb_cr3bp_section2(self.sys, self.integ, self.section, self.n, y0_soa.data_ptr(),
+            rc = self.lib.hb_cr3bp_section2(self.sys, self.integ if self._integ_ordered is None else self._integ_ordered,
+                                            self.section, self.n, y0_soa.data_ptr(),
                                             self.te.data_ptr(), self.te.numel(), self.hits.data_ptr(), self.cap,
                                             self.per.data_ptr(), self.yf.data_ptr(), self.nacc.data_ptr(),
                                             self.nrej.data_ptr(), self.status.data_ptr(), self.scratch.data_ptr(),

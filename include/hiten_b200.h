@@ -79,6 +79,11 @@ typedef struct {
                              SM's register file), so that two small batches launched on two streams run side by side --
                              each on its share of the SMs with twice as many trajectories per lane -- instead of one after
                              the other with two launch tails (no counterpart in the reference; results do not depend on it) */
+    const int32_t *order; /* NULL: the persistent DOP853 launches hand out trajectories 0, 1, 2, ...  Else a DEVICE array
+                             holding a permutation of 0..n-1 (the caller's responsibility): trajectory order[q] is the q-th to
+                             be handed out.  Outputs stay in the caller's indexing, so results do not depend on it; it is a
+                             scheduling hint -- longest expected trajectories first shortens the launch's tail (SURVEY 8e:
+                             "sorting by expected cost"; step counts spread 60..236 inside one manifold tube) */
 } hb_integ;
 
 /* Plane event g(t,y) = y[idx] - offset (algorithms/poincare/singlehit/backend.py:30-67) with the

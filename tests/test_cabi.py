@@ -142,6 +142,13 @@ def test_argument_validation_needs_no_gpu():
     assert lib.hb_peer_put((C.c_void_p * 2)(0x1008, 0x2000), 2, 0, None, 0, None, 0, 0x1000, None) < 0   # slot not 16-byte aligned
     assert lib.hb_peer_put(slots, 2, 0, None, 0, None, 0, None, None) < 0                        # no workspace
     assert hiten_b200.make_integ(max_ctas=74).max_ctas == 74 and hiten_b200.make_integ().max_ctas == 0
+    # hb_integ.order (scheduling hint): null by default; with_order copies the settings and checks the tensor
+    base = hiten_b200.make_integ(rtol=1e-10, max_ctas=3)
+    assert base.order is None and C.sizeof(base) == 64
+    same = hiten_b200.with_order(base, None)
+    assert same is not base and same.order is None and same.rtol == 1e-10 and same.max_ctas == 3
+    with pytest.raises(ValueError):
+        hiten_b200.with_order(base, [2, 0, 1])                                                  # not a CUDA int32 tensor
 
 
 def test_tao_grid_table_is_host_only_and_matches_the_reference_formulas():

@@ -185,6 +185,54 @@ def test_c5_two_tubes_side_by_side_with_capped_grids_same_bits():
             assert np.array_equal(a[key][i], b[key][i])
 
 
+def test_c5_launch_order_is_a_scheduling_hint_only():
+    """hb_integ.order: the persistent propagation launch hands out the trajectories longest-first (the step counts of a
+    first launch as the cost) or in a random order -- hits, end states, step counts and record counts are those of the
+    natural order bit for bit (outputs stay in the caller's indexing), for the pipeline and for hb_cr3bp_propagate."""
+    import torch
+    import hiten_b200 as hb
+    from hiten_b200 import synodic
+    from hiten_b200 import workloads as W
+    ics, mu = W.c5_batch(40000)
+    dev = torch.device("cuda", 0)
+    for key in ("l1", "l2"):
+        run = synodic.TubeSectionRunner(len(ics[key]), mu, W.c5_grid(key), W.c5_section(key, mu),
+                                        forward=W.C5_TUBES[key]["forward"], flip=(0, 6), device=dev, steps_capacity=128,
+                                        records="near")
+        y0 = torch.from_numpy(np.ascontiguousarray(ics[key].T)).to(dev)
+
+        def snapshot():
+            run.launch(y0)
+            h = run.sorted_hits()
+            return (h.trajectory_indices, h.times, h.states, run.yf.cpu().numpy(), run.nacc.cpu().numpy(),
+                    run.nrej.cpu().numpy(), run.status.cpu().numpy(), run.records_written().cpu().numpy())
+        a = snapshot()
+        assert len(a[1]) > 1000 and a[4].max() > 1.5 * a[4].min()
+        run.order_by_cost()                                   # longest first, from the launch above
+        order = run._order.cpu().numpy()
+        assert np.array_equal(np.sort(order), np.arange(run.n))
+        cost = a[4] + a[5]
+        assert np.all(np.diff(cost[order]) <= 0)
+        b = snapshot()
+        g = torch.Generator().manual_seed(5)
+        run.set_order(torch.randperm(run.n, generator=g).to(torch.int32).to(dev))
+        c = snapshot()
+        run.set_order(None)
+        d = snapshot()
+        for other in (b, c, d):
+            for u, v in zip(a, other):
+                assert np.array_equal(u, v)
+        # the plain propagation entry point honours the same hint
+        tf = float(W.c5_grid(key)[-1])
+        kw = dict(forward=W.C5_TUBES[key]["forward"], flip=(0, 6))
+        r0 = hb.cr3bp_propagate(y0, mu, tf, **kw)
+        ordered = hb.with_order(hb.make_integ(), hb.cost_order(r0.n_acc + r0.n_rej))
+        r1 = hb.cr3bp_propagate(y0, mu, tf, integ=ordered, **kw)
+        assert torch.equal(r0.yf, r1.yf) and torch.equal(r0.n_acc, r1.n_acc) and torch.equal(r0.n_rej, r1.n_rej)
+        with pytest.raises(ValueError):
+            run.set_order(torch.zeros(3, dtype=torch.int32, device=dev))
+
+
 def test_tube_section_in_chunks_equals_one_launch():
     """tube_section(steps_capacity="auto") on a batch whose step scratch does not fit the free memory (forced here with
     the free-memory override): three chunks through one scratch, the last one shorter -- same hits, counts and end states
