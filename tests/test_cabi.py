@@ -149,6 +149,17 @@ def test_argument_validation_needs_no_gpu():
     assert same is not base and same.order is None and same.rtol == 1e-10 and same.max_ctas == 3
     with pytest.raises(ValueError):
         hiten_b200.with_order(base, [2, 0, 1])                                                  # not a CUDA int32 tensor
+    # the launch order is checked on the host side of the boundary (the kernels trust it): a permutation, nothing else
+    import torch
+    from hiten_b200 import propagate as P_
+    cost = torch.tensor([5, 9, 5, 1, 9], dtype=torch.int32)
+    order = hiten_b200.cost_order(cost)
+    assert order.dtype == torch.int32 and order.tolist() == [1, 4, 0, 2, 3]                    # most expensive first, stable
+    P_.check_order(order, 5)
+    for bad_order, n_ in ((torch.tensor([0, 1, 1], dtype=torch.int32), 3), (torch.tensor([0, 1, 3], dtype=torch.int32), 3),
+                          (torch.tensor([0, -1, 2], dtype=torch.int32), 3), (order, 4)):
+        with pytest.raises(ValueError):
+            P_.check_order(bad_order, n_)
 
 
 def test_tao_grid_table_is_host_only_and_matches_the_reference_formulas():
