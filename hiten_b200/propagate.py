@@ -84,7 +84,8 @@ def _check_integ_order(integ, n):
 def cost_order(cost):
     """Launch order for `with_order`: most expensive first.  cost: CUDA tensor [n] (e.g. n_acc + n_rej of an earlier,
     similar batch).  Stable, so equal costs keep their index order."""
-    return torch.argsort(cost.to(torch.int64), descending=True, stable=True).to(torch.int32).contiguous()
+    key = cost if cost.is_floating_point() else cost.to(torch.int64)
+    return torch.argsort(key, descending=True, stable=True).to(torch.int32).contiguous()
 
 
 def _stream_ptr(stream=None):
