@@ -8,9 +8,10 @@ it finishes one, every attempted step costs one loop iteration) is simulated for
   node mean     longest first with a cost known per orbit node only;
   pilot         longest first with a cost MODEL that needs no earlier pass: the true costs of every K-th displacement row
                 (a pilot of 2000 x ceil(250 / K) trajectories), interpolated linearly in the displacement index.
-Prints the makespan of each order in loop iterations and relative to the perfect balance (sum / lanes).
+Prints the makespan of each order in loop iterations and relative to the perfect balance (sum / lanes), and the number of
+warp-level refill events (with exact costs the lanes of a warp hold equally long trajectories and refill together).
 usage: python tools/sim_launch_order.py [n_per_tube] [threads]"""
-import heapq, os, sys
+import os, sys
 import numpy as np
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "tests"))
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
@@ -22,15 +23,32 @@ threads = int(sys.argv[2]) if len(sys.argv) > 2 else 16
 LANES = 148 * 256
 
 
-def makespan(cost, order, lanes=LANES):
+def simulate(cost, order, lanes=LANES):
+    """-> (loop iterations until the last lane is done, WARP-LEVEL refill events: iterations in which at least one lane of a
+    warp takes a new trajectory -- each is a divergent ~1.5 us refill the warp's other lanes wait for)."""
     c = cost[order]
-    if len(c) <= lanes:
-        return float(c.max())
-    heap = list(c[:lanes].astype(float))
-    heapq.heapify(heap)
-    for v in c[lanes:]:
-        heapq.heapreplace(heap, heap[0] + v)
-    return max(heap)
+    n = len(c)
+    rem = np.zeros(lanes, dtype=np.int64)
+    active = np.zeros(lanes, dtype=bool)
+    nxt = it = events = 0
+    while True:
+        need = np.flatnonzero(~active)
+        if nxt < n and len(need):
+            got = need[: min(len(need), n - nxt)]
+            rem[got] = c[nxt:nxt + len(got)]
+            active[got] = True
+            nxt += len(got)
+            events += len(np.unique(got // 32))
+        if not active.any():
+            return float(it), events
+        m = rem[active].min()                     # jump to the next finishing time
+        rem[active] -= m
+        it += m
+        active &= rem != 0
+
+
+def makespan(cost, order):
+    return simulate(cost, order)
 
 
 ics, mu = W.c5_batch(2 * n_tube)
@@ -61,5 +79,6 @@ for key in ("l1", "l2"):
         res[f"pilot 1/{K} rows ({len(pil) * 2000} trajectories, R2 {expl:.3f})"] = makespan(cost, np.argsort(-pred, kind="stable"))
     print(f"{key}: {n} trajectories, attempted steps min / mean / max {cost.min()} / {cost.mean():.1f} / {cost.max()}, "
           f"perfect balance {ideal:.0f} iterations per lane")
-    for k, v in res.items():
-        print(f"   {k:58s} makespan {v:8.0f} = {v / ideal:.3f} x perfect   ({100 * (v / res['natural'] - 1):+.1f} % vs natural)")
+    for k, (v, ev) in res.items():
+        print(f"   {k:58s} makespan {v:8.0f} = {v / ideal:.3f} x perfect   ({100 * (v / res['natural'][0] - 1):+.1f} % vs natural)"
+              f"   warp refill events {ev}")
